@@ -1,0 +1,304 @@
+"""Problem definitions shared by the golden-fixture generator, the oracle tests and the GPU
+parity tests.  ``build(tda, name)`` constructs the posteriors / proposal with the classes of
+the given module -- either the unmodified reference (``tinyDA``) or this repo's
+``tinyda_b200`` -- from identical raw arrays; the class names and constructor arguments are
+the same on both sides, which is the point of the drop-in surface.  Forward models are
+always the device-resident model classes (NumPy-callable, so the reference accepts them).
+"""
+import numpy as np
+import scipy.stats as stats
+
+from tinyda_b200.models import LinearModel, Rosenbrock, Poisson1D
+
+
+def _exp_cov(d, ell=0.2):
+    x = np.linspace(0, 1, d)
+    return np.exp(-np.abs(x[:, None] - x[None, :]) / ell)
+
+
+def _linear_levels(rng, d, ms, sigma, prior, coarse_mode="subset", perturb=0.0):
+    """Fine operator G (ms[-1] x d) and coarser ones: row subsets (strided) of the fine one,
+    optionally perturbed (so that there is a model bias for the error model)."""
+    m_f = ms[-1]
+    G = rng.standard_normal((m_f, d)) / np.sqrt(d)
+    truth = prior.rvs(random_state=rng)
+    truth = np.atleast_1d(truth)
+    y = G @ truth + sigma * rng.standard_normal(m_f)
+    out = []
+    for i, m in enumerate(ms):
+        if coarse_mode == "subset":
+            idx = np.arange(0, m_f, m_f // m)[:m]
+        else:
+            idx = np.arange(m_f)
+        Gl = G[idx].copy()
+        if i < len(ms) - 1 and perturb:
+            Gl = Gl + perturb * (len(ms) - 1 - i) * rng.standard_normal(Gl.shape)
+        out.append((Gl, y[idx].copy()))
+    return out
+
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+# Each case returns a dict:
+#   build(tda) -> (posteriors(list), proposal, kwargs for chain/sample)
+#   n_chains, iterations, seed, store_F (bool)
+
+@case
+def mh_rwmh_linreg():
+    """cfg1: README linear regression (examples/Basic Sampler.ipynb), RWMH with adaptive scaling."""
+    rng = np.random.default_rng(1)
+    x = np.linspace(0, 1, 100)
+    y = 1 + 2 * x + 0.2 * rng.standard_normal(100)
+    prior = stats.multivariate_normal(np.zeros(2), np.eye(2))
+    G = np.stack([np.ones_like(x), x], axis=1)
+
+    def build(tda):
+        lik = tda.GaussianLogLike(y, 0.04 * np.eye(100))
+        post = tda.Posterior(prior, lik, LinearModel(G))
+        prop = tda.GaussianRandomWalk(C=np.eye(2), scaling=0.1, adaptive=True)
+        return [post], prop, {}
+    return dict(build=build, n_chains=4, iterations=350, seed=11, prior=prior)
+
+
+@case
+def mh_rwmh_dense():
+    """RWMH with a dense proposal covariance, non-zero prior mean, dense likelihood covariance."""
+    rng = np.random.default_rng(21)
+    d, m = 5, 12
+    A = rng.standard_normal((d, d))
+    prior = stats.multivariate_normal(rng.standard_normal(d), A @ A.T + d * np.eye(d))
+    (G, y), = _linear_levels(rng, d, [m], 0.3, prior)
+    B = rng.standard_normal((m, m))
+    cov = 0.09 * (np.eye(m) + 0.05 * (B @ B.T))
+    Cp = 0.05 * (np.eye(d) + 0.3 * np.ones((d, d)))
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, cov), LinearModel(G, offset=0.1 * np.arange(m)))
+        return [post], tda.GaussianRandomWalk(C=Cp, scaling=0.7), {}
+    return dict(build=build, n_chains=3, iterations=120, seed=22, prior=prior)
+
+
+@case
+def mh_pcn_diag():
+    """pCN, diagonal (non-isotropic) likelihood."""
+    rng = np.random.default_rng(31)
+    d, m = 8, 16
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d))
+    (G, y), = _linear_levels(rng, d, [m], 0.2, prior)
+    var = 0.04 * (1 + np.arange(m) / m)
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, np.diag(var)), LinearModel(G))
+        return [post], tda.CrankNicolson(scaling=0.2, adaptive=True, period=40), {}
+    return dict(build=build, n_chains=3, iterations=130, seed=32, prior=prior)
+
+
+@case
+def da_pcn_small():
+    """cfg2 in miniature: two-level DA, pCN, coarse = strided observation subset, J=3."""
+    rng = np.random.default_rng(2)
+    d = 8
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d))
+    (Gc, yc), (Gf, yf) = _linear_levels(rng, d, [8, 32], 0.1, prior)
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.GaussianLogLike(yc, 0.01 * np.eye(8)), LinearModel(Gc))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(yf, 0.01 * np.eye(32)), LinearModel(Gf))
+        return [pc, pf], tda.CrankNicolson(scaling=0.1), dict(subchain_length=3)
+    return dict(build=build, n_chains=4, iterations=80, seed=42, prior=prior)
+
+
+@case
+def da_pcn_cfg2():
+    """cfg2 at its real shape (64 params, 1024 / 128 observations, J=10), few chains."""
+    rng = np.random.default_rng(2)
+    d = 64
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d))
+    G = rng.standard_normal((1024, d)) / 8
+    truth = prior.rvs(random_state=rng)
+    y = G @ truth + 0.1 * rng.standard_normal(1024)
+    idx = np.arange(0, 1024, 8)
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.GaussianLogLike(y[idx], 0.01 * np.eye(128)), LinearModel(G[idx]))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(y, 0.01 * np.eye(1024)), LinearModel(G))
+        return [pc, pf], tda.CrankNicolson(scaling=0.05), dict(subchain_length=10)
+    return dict(build=build, n_chains=2, iterations=25, seed=43, prior=prior, store_F=False)
+
+
+@case
+def da_rwmh_adaptive():
+    """DA with adaptively scaled RWMH: the adaptation window contains alignment entries
+    (SURVEY.md appendix A.9)."""
+    rng = np.random.default_rng(5)
+    d = 4
+    prior = stats.multivariate_normal(0.2 * np.ones(d), np.eye(d))
+    (Gc, yc), (Gf, yf) = _linear_levels(rng, d, [6, 24], 0.2, prior, perturb=0.02)
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.GaussianLogLike(yc, 0.04 * np.eye(6)), LinearModel(Gc))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(yf, 0.04 * np.eye(24)), LinearModel(Gf))
+        prop = tda.GaussianRandomWalk(C=0.02 * np.eye(d), scaling=1.0, adaptive=True, period=25)
+        return [pc, pf], prop, dict(subchain_length=4)
+    return dict(build=build, n_chains=3, iterations=90, seed=52, prior=prior)
+
+
+@case
+def da_aem_linear():
+    """DA + state-independent adaptive error model; coarse model = perturbed fine model."""
+    rng = np.random.default_rng(6)
+    d, m = 4, 10
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    (Gc, yc), (Gf, yf) = _linear_levels(rng, d, [m, m], 0.1, prior, coarse_mode="same", perturb=0.05)
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.AdaptiveGaussianLogLike(yc, 0.01 * np.eye(m)), LinearModel(Gc))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(yf, 0.01 * np.eye(m)), LinearModel(Gf))
+        prop = tda.GaussianRandomWalk(C=0.01 * np.eye(d))
+        return [pc, pf], prop, dict(subchain_length=3, adaptive_error_model="state-independent")
+    return dict(build=build, n_chains=3, iterations=60, seed=62, prior=prior)
+
+
+@case
+def mlda3_linear():
+    """3-level MLDA without error model, J=[3,2], different output sizes per level."""
+    rng = np.random.default_rng(7)
+    d = 6
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d, 0.5))
+    lv = _linear_levels(rng, d, [6, 12, 24], 0.15, prior, perturb=0.02)
+
+    def build(tda):
+        posts = [tda.Posterior(prior, tda.GaussianLogLike(y, 0.0225 * np.eye(len(y))), LinearModel(G))
+                 for G, y in lv]
+        prop = tda.GaussianRandomWalk(C=0.03 * np.eye(d), adaptive=True, period=20)
+        return posts, prop, dict(subchain_length=[3, 2])
+    return dict(build=build, n_chains=3, iterations=40, seed=72, prior=prior)
+
+
+@case
+def mlda3_aem_linear():
+    """3-level MLDA + state-independent AEM (bias sums across levels, lazy refresh order)."""
+    rng = np.random.default_rng(8)
+    d, m = 4, 8
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    lv = _linear_levels(rng, d, [m, m, m], 0.1, prior, coarse_mode="same", perturb=0.04)
+
+    def build(tda):
+        posts = []
+        for i, (G, y) in enumerate(lv):
+            lk = tda.AdaptiveGaussianLogLike(y, 0.01 * np.eye(m)) if i < 2 else tda.GaussianLogLike(y, 0.01 * np.eye(m))
+            posts.append(tda.Posterior(prior, lk, LinearModel(G)))
+        prop = tda.GaussianRandomWalk(C=0.01 * np.eye(d))
+        return posts, prop, dict(subchain_length=[3, 2], adaptive_error_model="state-independent")
+    return dict(build=build, n_chains=3, iterations=30, seed=82, prior=prior)
+
+
+@case
+def mlda4_aem_poisson():
+    """cfg4 in miniature: 4-level MLDA + state-independent AEM on the 1-D Poisson inversion."""
+    rng = np.random.default_rng(4)
+    d, ns, msens = 4, [32, 64, 128, 256], 31
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    truth = prior.rvs(random_state=rng)
+    sig = 1e-3
+    y = Poisson1D(1024, d, msens)(truth) + sig * rng.standard_normal(msens)
+    models = [Poisson1D(n, d, msens) for n in ns]
+
+    def build(tda):
+        posts = []
+        for i, mdl in enumerate(models):
+            lk = (tda.AdaptiveGaussianLogLike(y, sig ** 2 * np.eye(msens)) if i < 3
+                  else tda.GaussianLogLike(y, sig ** 2 * np.eye(msens)))
+            posts.append(tda.Posterior(prior, lk, mdl))
+        prop = tda.GaussianRandomWalk(C=1e-4 * np.eye(d))
+        return posts, prop, dict(subchain_length=[3, 2, 2], adaptive_error_model="state-independent")
+    return dict(build=build, n_chains=2, iterations=15, seed=92, prior=prior)
+
+
+@case
+def mala_rosenbrock():
+    """cfg3: MALA on the 2-D Rosenbrock likelihood (examples/MALA Rosenbrock.ipynb)."""
+    prior = stats.multivariate_normal(np.zeros(2), np.eye(2))
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(np.array([0.0]), np.eye(1)), Rosenbrock(1, 10))
+        return [post], tda.MALA(scaling=0.01, adaptive=True), {}
+    return dict(build=build, n_chains=4, iterations=350, seed=3, prior=prior)
+
+
+@case
+def mala_linear():
+    """MALA on a linear-Gaussian problem with a dense prior covariance."""
+    rng = np.random.default_rng(13)
+    d, m = 4, 9
+    prior = stats.multivariate_normal(0.1 * np.ones(d), _exp_cov(d, 0.7))
+    (G, y), = _linear_levels(rng, d, [m], 0.3, prior)
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.09 * np.eye(m)), LinearModel(G))
+        return [post], tda.MALA(scaling=0.15), {}
+    return dict(build=build, n_chains=3, iterations=100, seed=14, prior=prior)
+
+
+@case
+def am_linear():
+    """Adaptive Metropolis; the covariance factor is refreshed every `period` steps."""
+    rng = np.random.default_rng(15)
+    d, m = 4, 10
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    (G, y), = _linear_levels(rng, d, [m], 0.3, prior)
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.09 * np.eye(m)), LinearModel(G))
+        return [post], tda.AdaptiveMetropolis(C0=0.05 * np.eye(d), period=20, adaptive=True), {}
+    return dict(build=build, n_chains=3, iterations=110, seed=16, prior=prior)
+
+
+@case
+def dreamz_linear():
+    """DREAM(Z) with a per-chain archive."""
+    rng = np.random.default_rng(17)
+    d, m = 4, 10
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    (G, y), = _linear_levels(rng, d, [m], 0.3, prior)
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.09 * np.eye(m)), LinearModel(G))
+        return [post], tda.DREAMZ(M0=8, delta=2, nCR=3), {}
+    return dict(build=build, n_chains=3, iterations=90, seed=18, prior=prior, archive=True)
+
+
+@case
+def dream_shared():
+    """cfg5 in miniature: DREAM with the archive shared by all chains (lock-step visibility)."""
+    rng = np.random.default_rng(5)
+    d, m = 6, 12
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    (G, y), = _linear_levels(rng, d, [m], 0.1, prior)
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.01 * np.eye(m)), LinearModel(G))
+        return [post], tda.DREAM(M0=5, delta=1, nCR=3), {}
+    return dict(build=build, n_chains=4, iterations=70, seed=19, prior=prior, archive=True, shared=True)
+
+
+def stream_sizes(spec, iterations):
+    """Upper bounds for the number of normals / uniforms one chain consumes."""
+    d = spec["d"]
+    base_steps = iterations * int(np.prod(spec["J"])) if spec["J"] else iterations
+    kind = spec["proposal"]["kind"]
+    nz = base_steps * d
+    nu = base_steps
+    mult = 1
+    for j in reversed(spec["J"]):      # upper-level accept tests
+        nu += iterations * mult
+        mult *= j
+    if kind in (4, 5):
+        nu += base_steps * (2 * spec["proposal"]["delta"] + 1 + d + 1 + d)
+    return nz + 8, nu + 8

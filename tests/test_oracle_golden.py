@@ -1,0 +1,28 @@
+"""Pins the oracle (oracle/tinyda_oracle.py) against the reference's own outputs: every
+golden fixture was produced by the unmodified reference under injected streams."""
+import numpy as np
+import pytest
+
+import golden_io
+from oracle import tinyda_oracle as orc
+
+RTOL = 1e-11   # float64 restatement vs reference: only summation-order level differences
+
+
+@pytest.mark.parametrize("name", golden_io.names())
+def test_oracle_matches_reference(name):
+    g = golden_io.load(name)
+    spec = g["spec"]
+    out, chains = orc.run_chains(spec, g["theta0"], g["z"], g["u"], g["iterations"], g["archive0"])
+    for l in range(spec["n_levels"]):
+        ref = g["ref"][l]
+        assert out[l]["acc"].shape == ref["acc"].shape, (name, l)
+        assert np.array_equal(out[l]["acc"], ref["acc"]), "accept/reject decisions differ at level %d" % l
+        np.testing.assert_allclose(out[l]["theta"], ref["theta"], rtol=RTOL, atol=1e-13)
+        np.testing.assert_allclose(out[l]["prior"], ref["prior"], rtol=RTOL, atol=1e-11)
+        np.testing.assert_allclose(out[l]["like"], ref["like"], rtol=1e-9, atol=1e-9)
+        if "F" in ref:
+            np.testing.assert_allclose(out[l]["F"], ref["F"], rtol=1e-10, atol=1e-13)
+    # identical stream consumption (control-flow dependent)
+    consumed = np.array([[ch.S.nz, ch.S.nu] for ch in chains])
+    assert np.array_equal(consumed, g["consumed"])

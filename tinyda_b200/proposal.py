@@ -1,0 +1,158 @@
+"""Proposal descriptors (host side).
+
+Same class names, constructor arguments, defaults, validation errors and class attributes as
+the reference's proposals (tinyDA/proposal.py:132-258 GaussianRandomWalk, :261-369
+CrankNicolson, :372-512 AdaptiveMetropolis, :608-852 DREAMZ, :861-1005 MALA, :1627-1656
+DREAM).  The reference objects carry the per-chain mutable state (scaling, k, t, AM moments,
+DREAM archive) and are deep-copied per chain (tinyDA/sampler.py:176); here that state lives
+in per-chain device arrays and these objects only describe the kernel to run.
+``lower(prior)`` yields the POD parameters + constant buffers for the engine.
+"""
+import numpy as np
+
+PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM = 0, 1, 2, 3, 4, 5
+
+
+def svd_factor(C):
+    """The matrix T for which ``np.random.multivariate_normal(0, C)`` equals ``z @ T``
+    with z ~ N(0, I): numpy's legacy default method factors C by SVD and returns
+    z @ (sqrt(s)[:, None] * Vt).  Feeding the engine this factor (instead of a Cholesky
+    factor) is what makes trajectories identical to the reference under shared streams."""
+    C = np.atleast_2d(np.asarray(C, dtype=np.float64))
+    _, s, vt = np.linalg.svd(C)
+    return np.sqrt(s)[:, None] * vt
+
+
+def _check_square(C, name):
+    # proposal.py:190-196 / :444-450
+    if not isinstance(C, np.ndarray):
+        raise TypeError("%s must be a numpy array" % name)
+    elif C.ndim == 1:
+        if not C.shape[0] == 1:
+            raise ValueError("%s must be an NxN array" % name)
+    elif not C.shape[0] == C.shape[1]:
+        raise ValueError("%s must be an NxN array" % name)
+
+
+class Proposal:
+    is_symmetric = False
+
+
+class GaussianRandomWalk(Proposal):
+    is_symmetric = True
+    alpha_star = 0.24
+    kind = PROP_RWMH
+
+    def __init__(self, C, scaling=1, adaptive=False, gamma=1.01, period=100):
+        _check_square(C, "C")
+        self.C = C
+        self.d = self.C.shape[0]
+        self.scaling = scaling
+        self.adaptive = adaptive
+        self.gamma = gamma
+        self.period = period
+
+    def _common(self):
+        return dict(kind=self.kind, scaling=float(self.scaling), adaptive=bool(self.adaptive),
+                    gamma=float(self.gamma), period=int(self.period),
+                    alpha_star=float(self.alpha_star))
+
+    def lower(self, prior):
+        out = self._common()
+        out["T"] = svd_factor(self.C)
+        return out
+
+
+class CrankNicolson(GaussianRandomWalk):
+    is_symmetric = False
+    kind = PROP_PCN
+
+    def __init__(self, scaling=0.1, adaptive=False, gamma=1.01, period=100):
+        self.scaling = scaling
+        self.adaptive = adaptive
+        self.gamma = gamma
+        self.period = period
+
+    def lower(self, prior):
+        out = self._common()
+        out["T"] = svd_factor(prior["cov"])          # proposal.py:336-347: C <- prior covariance
+        return out
+
+
+class AdaptiveMetropolis(GaussianRandomWalk):
+    kind = PROP_AM
+
+    def __init__(self, C0, sd=None, epsilon=1e-6, t0=0, period=100, adaptive=False, gamma=1.01):
+        _check_square(C0, "C0")
+        self.C = C0
+        self.d = self.C.shape[0]
+        self.scaling = 1
+        self.sd = sd if sd is not None else min(1, 2.4 ** 2 / self.d)   # proposal.py:465-468
+        self.epsilon = epsilon
+        self.t0 = t0
+        self.period = period
+        self.adaptive = adaptive
+        self.gamma = gamma
+
+    def lower(self, prior):
+        out = self._common()
+        out["T"] = svd_factor(self.C)
+        out["C0"] = np.atleast_2d(np.asarray(self.C, dtype=np.float64))
+        out["am_sd"] = float(self.sd)
+        out["am_eps"] = float(self.epsilon)
+        out["am_t0"] = int(self.t0)
+        return out
+
+
+class MALA(GaussianRandomWalk):
+    is_symmetric = False
+    alpha_star = 0.57
+    kind = PROP_MALA
+
+    def __init__(self, scaling=0.1, adaptive=False, gamma=1.01, period=100):
+        self.scaling = scaling
+        self.adaptive = adaptive
+        self.gamma = gamma
+        self.period = period
+
+    def lower(self, prior):
+        return self._common()
+
+
+class DREAMZ(GaussianRandomWalk):
+    kind = PROP_DREAMZ
+
+    def __init__(self, M0, delta=1, b=5e-2, b_star=1e-6, Z_method="random", nCR=3,
+                 adaptive=False, gamma=1.01, period=100):
+        self.M = M0
+        self.scaling = 1
+        self.delta = delta
+        self.b = b
+        self.b_star = b_star
+        self.Z_method = Z_method
+        self.adaptive = adaptive
+        self.nCR = nCR
+        self.gamma = gamma
+        self.period = period
+
+    def lower(self, prior):
+        if self.Z_method != "random":
+            raise NotImplementedError("only Z_method='random' is lowered to the device")
+        out = self._common()
+        out.update(M0=int(self.M), delta=int(self.delta), b=float(self.b), b_star=float(self.b_star),
+                   nCR=int(self.nCR))
+        return out
+
+
+class DREAM(DREAMZ):
+    """DREAM(Z) with an archive shared by all chains (proposal.py:1627-1656).  On one GPU
+    the archive is a single HBM array; across GPUs every step's new rows are all-gathered
+    over NCCL (see sampler.py)."""
+
+    kind = PROP_DREAM
+
+
+def SingleDreamZ(*args, **kwargs):
+    import warnings
+    warnings.warn(" SingleDreamZ has been deprecated. Please use DREAMZ.")
+    return DREAMZ(*args, **kwargs)
