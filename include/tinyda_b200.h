@@ -1,0 +1,212 @@
+/*
+ * tinyda_b200 -- C ABI of the B200-native batched MCMC engine.
+ *
+ * The reference (tinyDA, pure Python) has no FFI of its own: its seams are Python protocols.
+ * This header is the boundary a maintainer would bind (ctypes / cffi / pybind) to replace the
+ * reference's per-chain Python loops with one device engine.  Each entry point names the
+ * reference interface it replaces (file:line into the reference's tinyDA/ package):
+ *
+ *   tda_engine_create     sampler.py:21-290   argument normalisation + chain construction
+ *                         (chain.py:37-76 Chain.__init__, :185-321 DAChain.__init__,
+ *                          :570-678 MLDAChain.__init__, proposal.py:1339-1440 MLDA.__init__)
+ *   tda_upload            the constants those constructors capture (prior, likelihood data /
+ *                         covariance, model operator, proposal covariance factor, initial
+ *                         parameters sampler.py:196-209, DREAM initial archive proposal.py:788)
+ *   tda_engine_init       the initial Links (posterior.py:78-110 create_link on every level),
+ *                         AEM set-up (chain.py:272-305, :644-678, proposal.py:1442-1467)
+ *   tda_engine_run        Chain.sample chain.py:78-129 / DAChain.sample :325-444 /
+ *                         MLDAChain.sample :680-769 with MLDA.make_*_proposal
+ *                         proposal.py:1502-1613, for ALL chains in lock-step (replaces
+ *                         ray.py:12-210, one actor per chain).  Re-entrant: calling it again
+ *                         continues the chains, like calling .sample() again does.
+ *   tda_fetch             the Link lists chain.chain / chain_fine / compress(chain_coarse,
+ *                         is_coarse) / compress(chain, is_local) (sampler.py:305-309,
+ *                         :406-439, :510-547) as structure-of-arrays
+ *   tda_get / tda_set     proposal state the reference keeps on the proposal object
+ *                         (scaling, AM moments, DREAM archive; proposal.py:228-245, :502-512,
+ *                         :790-809) and accept counters (chain.accepted)
+ *   tda_fill_streams      np.random.* (proposal.py:249, :353, :834-848, :958; chain.py:112,
+ *                         :385, :429, :729): exports the engine's counter-based streams so a
+ *                         CPU oracle can be fed the identical draws
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a
+ * negative code on failure, with a message available from tda_last_error(); no C++ exception
+ * crosses the boundary; no host callbacks from inside tda_engine_run.  All host-side constant
+ * uploads are float64 and are converted to the engine dtype on the device side of the call.
+ * The engine owns its device memory; callers own every host pointer they pass.
+ */
+#ifndef TINYDA_B200_H
+#define TINYDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDA_ABI_VERSION 1
+#define TDA_MAX_LEVELS 4
+#define TDA_MAX_D 64
+
+/* dtype */
+#define TDA_F32 0
+#define TDA_F64 1
+/* rng_mode */
+#define TDA_RNG_PHILOX 0    /* per-chain Philox4x32-10 counter streams generated in-kernel  */
+#define TDA_RNG_INJECTED 1  /* normals / uniforms read from uploaded per-chain streams      */
+/* proposal kinds (reference class in parentheses) */
+#define TDA_PROP_RWMH 0     /* GaussianRandomWalk  proposal.py:132  */
+#define TDA_PROP_PCN 1      /* CrankNicolson       proposal.py:261  */
+#define TDA_PROP_AM 2       /* AdaptiveMetropolis  proposal.py:372  */
+#define TDA_PROP_MALA 3     /* MALA                proposal.py:861  */
+#define TDA_PROP_DREAMZ 4   /* DREAMZ              proposal.py:608  */
+#define TDA_PROP_DREAM 5    /* DREAM (shared)      proposal.py:1627 */
+/* likelihood kinds */
+#define TDA_LIK_ISO 0       /* IsotropicGaussianLogLike distributions.py:318 */
+#define TDA_LIK_DIAG 1      /* DiagonalGaussianLogLike  distributions.py:304 */
+#define TDA_LIK_DENSE 2     /* DefaultGaussianLogLike   distributions.py:246 */
+#define TDA_LIK_ADAPTIVE 3  /* AdaptiveGaussianLogLike  distributions.py:332 */
+/* forward model kinds (device-resident replacements of the user's Python callable) */
+#define TDA_MODEL_LINEAR 0
+#define TDA_MODEL_ROSENBROCK 1
+#define TDA_MODEL_POISSON1D 2
+/* history storage flags per level */
+#define TDA_STORE_THETA 1
+#define TDA_STORE_STATS 2   /* log-prior, log-likelihood */
+#define TDA_STORE_OUTPUT 4  /* model output F(theta)     */
+#define TDA_STORE_ACCEPT 8
+
+typedef struct tda_level_config {
+    int32_t model_kind;
+    int32_t m;              /* number of model outputs / observations          */
+    int32_t n_grid;         /* Poisson1D: number of cells                      */
+    int32_t lik_kind;
+    double lik_var;         /* isotropic variance                              */
+    double model_scalars[4];
+    int32_t store;          /* TDA_STORE_* flags                               */
+    int32_t reserved;
+    int64_t hist_capacity;  /* records per chain the level's history can hold  */
+} tda_level_config;
+
+typedef struct tda_config {
+    int32_t abi_version;
+    int32_t dtype;
+    int32_t n_levels;
+    int32_t d;
+    int32_t subchain[TDA_MAX_LEVELS];   /* J[l] for l < n_levels-1                     */
+    int32_t aem;                        /* 0 none, 1 state-independent                 */
+    int32_t rng_mode;
+    uint64_t seed;
+    int64_t n_chains;                   /* chains on THIS device                       */
+    int64_t chain_offset;               /* global index of local chain 0 (Philox key)  */
+    int64_t n_chains_global;            /* DREAM shared archive width                  */
+    /* proposal */
+    int32_t prop_kind;
+    int32_t adaptive;
+    int32_t period;
+    int32_t am_t0;
+    double scaling;
+    double gamma;
+    double alpha_star;
+    double am_sd;
+    double am_eps;
+    int32_t am_device_refactor;         /* 1: Cholesky refactor on device; 0: host uploads factors */
+    int32_t dream_M0;
+    int32_t dream_delta;
+    int32_t dream_nCR;
+    double dream_b;
+    double dream_b_star;
+    int64_t dream_capacity;             /* archive slots per chain (M0 + max steps)    */
+    /* injected streams */
+    int64_t stream_z_len;
+    int64_t stream_u_len;
+    /* prior: logpdf = -0.5*(logconst + |(x-mean) @ LP|^2) */
+    double prior_logconst;
+    tda_level_config level[TDA_MAX_LEVELS];
+} tda_config;
+
+/* tda_upload 'what' */
+#define TDA_UP_PRIOR_MEAN 1     /* [d]                                              */
+#define TDA_UP_PRIOR_LP 2       /* [d][d] whitening matrix                          */
+#define TDA_UP_PRIOR_PREC 3     /* [d][d] inverse covariance (MALA drift)           */
+#define TDA_UP_PROP_T 4         /* [d][d] factor T, xi = z @ T                      */
+#define TDA_UP_MODEL_A 5        /* level: LINEAR G^T [d][m]; POISSON Phi^T [d][n]   */
+#define TDA_UP_MODEL_B 6        /* level: LINEAR offset [m]                         */
+#define TDA_UP_LIK_DATA 7       /* level: [m]                                       */
+#define TDA_UP_LIK_VAR 8        /* level: DIAG variances [m]                        */
+#define TDA_UP_LIK_PREC 9       /* level: DENSE / ADAPTIVE inverse covariance [m][m]*/
+#define TDA_UP_LIK_COV 10       /* level: ADAPTIVE covariance [m][m]                */
+#define TDA_UP_INIT_THETA 11    /* [n_chains][d]                                    */
+#define TDA_UP_STREAM_Z 12      /* [n_chains][stream_z_len] standard normals        */
+#define TDA_UP_STREAM_U 13      /* [n_chains][stream_u_len] U(0,1)                  */
+#define TDA_UP_DREAM_ARCHIVE0 14 /* [n_chains_global][M0][d]                        */
+#define TDA_UP_AM_FACTORS 15    /* [n_chains][d][d] per-chain T                     */
+
+/* tda_fetch 'field' */
+#define TDA_F_THETA 1           /* [nrec][d][n_chains]   engine dtype               */
+#define TDA_F_PRIOR 2           /* [nrec][n_chains]      engine dtype               */
+#define TDA_F_LIKE 3            /* [nrec][n_chains]      engine dtype               */
+#define TDA_F_OUTPUT 4          /* [nrec][m][n_chains]   engine dtype               */
+#define TDA_F_ACCEPT 5          /* [nrec][n_chains]      uint8                      */
+
+/* tda_get / tda_set 'what' (float64 on the host side unless noted) */
+#define TDA_G_SCALING 1         /* [n_chains]                                       */
+#define TDA_G_ACCEPT_COUNTS 2   /* int64 [n_levels][n_chains] accepted local steps  */
+#define TDA_G_CURSORS 3         /* int64 [2][n_chains] consumed normals, uniforms   */
+#define TDA_G_AM_SIGMA 4        /* [n_chains][d][d]                                 */
+#define TDA_G_AM_MU 5           /* [n_chains][d]                                    */
+#define TDA_G_THETA 6           /* level: current state [n_chains][d]               */
+#define TDA_G_NRECORDS 7        /* int64 [n_levels] records written so far          */
+#define TDA_G_MOMENTS 8         /* finest level running sums: [2][d][n_chains] (sum x, sum x^2) */
+
+typedef struct tda_engine tda_engine;
+
+int tda_abi_version(void);
+const char *tda_last_error(void);
+
+int tda_engine_create(const tda_config *cfg, int device, tda_engine **out);
+int tda_engine_destroy(tda_engine *e);
+
+int tda_upload(tda_engine *e, int what, int level, const double *host, size_t count);
+int tda_engine_init(tda_engine *e, void *cuda_stream);
+int tda_engine_run(tda_engine *e, int64_t iterations, void *cuda_stream);
+int tda_engine_sync(tda_engine *e, void *cuda_stream);
+
+/* Copies history records [rec0, rec0+nrec) of one level into host memory (pinned or
+ * pageable), in the device layout documented at TDA_F_*; async on cuda_stream when the host
+ * buffer is pinned.  Returns the number of bytes written through *bytes. */
+int tda_fetch(tda_engine *e, int level, int field, int64_t rec0, int64_t nrec,
+              void *host_dst, size_t dst_bytes, size_t *bytes, void *cuda_stream);
+
+int tda_get(tda_engine *e, int what, int level, void *host_dst, size_t dst_bytes);
+int tda_set(tda_engine *e, int what, int level, const void *host_src, size_t src_bytes);
+
+/* Raw device pointer + byte size of an engine buffer, for zero-copy interop (e.g. wrapping
+ * the DREAM archive in a torch tensor for the NCCL all-gather).  buffer ids: */
+#define TDA_BUF_DREAM_ARCHIVE 1 /* [capacity][n_chains_global][d] engine dtype      */
+#define TDA_BUF_HIST_THETA 2    /* level                                            */
+int tda_device_buffer(tda_engine *e, int buffer, int level, void **dev_ptr, size_t *bytes);
+/* DREAM shared archive: number of filled slots (M0 + steps) */
+int tda_dream_slots(tda_engine *e, int64_t *slots);
+
+/* Fills host arrays z[n_chains][nz], u[n_chains][nu] (float64) with the values the engine's
+ * Philox streams deliver in the engine dtype -- what TDA_RNG_PHILOX mode consumes. */
+int tda_fill_streams(tda_engine *e, double *z, int64_t nz, double *u, int64_t nu);
+
+/* Rewinds the history write position of every level to record 0 (the buffers are reused;
+ * call after the records have been fetched).  The chains themselves are unaffected. */
+int tda_history_reset(tda_engine *e);
+
+/* Kernel selection for tda_engine_run: 0 = automatic, 1 = generic lock-step kernel,
+ * 2 = tcgen05 tensor-core Delayed-Acceptance kernel (fails if the configuration is not
+ * supported by it). */
+int tda_select_kernel(tda_engine *e, int which);
+
+/* Kernel launches issued by this library since load (for bench.py's gpu_launches). */
+int64_t tda_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYDA_B200_H */

@@ -1,0 +1,679 @@
+// Host side of the tinyda_b200 engine: owns device memory, lays constants out for the kernels,
+// launches the lock-step chain kernel, exposes the C ABI declared in include/tinyda_b200.h.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tda_kernels.cuh"
+#include "tda_da_tc.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return fail(-2, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+    } while (0)
+
+inline int round_up(int x, int q) { return (x + q - 1) / q * q; }
+
+}  // namespace
+
+struct tda_engine {
+    virtual ~tda_engine() {}
+    virtual int upload(int what, int level, const double* host, size_t count) = 0;
+    virtual int init(cudaStream_t st) = 0;
+    virtual int run(long long iterations, cudaStream_t st) = 0;
+    virtual int fetch(int level, int field, long long rec0, long long nrec, void* dst, size_t dst_bytes,
+                      size_t* bytes, cudaStream_t st) = 0;
+    virtual int get(int what, int level, void* dst, size_t bytes) = 0;
+    virtual int set(int what, int level, const void* src, size_t bytes) = 0;
+    virtual int device_buffer(int buffer, int level, void** ptr, size_t* bytes) = 0;
+    virtual int fill_streams(double* z, long long nz, double* u, long long nu) = 0;
+    virtual int history_reset() = 0;
+    virtual int select_kernel(int which) = 0;
+    tda_config cfg;
+    int device = 0;
+    long long dream_slots = 0;
+};
+
+namespace {
+
+template <typename R>
+__global__ void fill_kernel(R* dst, R value, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = value;
+}
+
+template <typename R>
+__global__ void broadcast_kernel(R* dst, const R* src, int n, int ld_src, int cols, int Cs) {
+    // dst[(i*cols + j)][c] = src[i*ld_src + j]
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)n * cols * Cs;
+    if (e < total) {
+        size_t ij = e / Cs;
+        int i = (int)(ij / cols), j = (int)(ij - (size_t)i * cols);
+        dst[e] = src[(size_t)i * ld_src + j];
+    }
+}
+
+template <typename R>
+struct EngineT : tda_engine {
+    tda::Params<R> P;
+    std::vector<void*> allocs;
+    int Cs = 0, n_tiles = 0, kt = 0, sm_count = 148;
+    size_t smem_bytes = 0;
+    bool initialised = false;
+    int kernel_choice = 0;     // 0 auto, 1 generic, 2 tensor-core DA
+    std::vector<int> ldA;
+    tda::DaTcState<R> tc;      // tcgen05 fast path (float only; inert for double)
+
+    ~EngineT() override {
+        cudaSetDevice(device);
+        for (void* p : allocs) cudaFree(p);
+        tc.destroy();
+    }
+
+    template <typename T>
+    int dalloc(T** out, size_t n) {
+        void* p = nullptr;
+        size_t bytes = (n ? n : 1) * sizeof(T);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail(-3, std::string("cudaMalloc ") + std::to_string(bytes) + " bytes: " + cudaGetErrorString(e));
+        e = cudaMemset(p, 0, bytes);
+        if (e != cudaSuccess) return fail(-3, std::string("cudaMemset: ") + cudaGetErrorString(e));
+        allocs.push_back(p);
+        *out = reinterpret_cast<T*>(p);
+        return 0;
+    }
+#define DALLOC(ptr, n)                         \
+    do {                                       \
+        int _r = dalloc(&(ptr), (size_t)(n));  \
+        if (_r) return _r;                     \
+    } while (0)
+
+    int create() {
+        const tda_config& c = cfg;
+        CUDA_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        sm_count = prop.multiProcessorCount;
+        memset(&P, 0, sizeof(P));
+        const int L = c.n_levels, d = c.d;
+        P.L = L; P.d = d; P.aem = c.aem; P.rng_mode = c.rng_mode; P.prop_kind = c.prop_kind;
+        P.adaptive = c.adaptive; P.period = c.period > 0 ? c.period : 1; P.am_t0 = c.am_t0;
+        P.am_device_refactor = c.am_device_refactor;
+        for (int l = 0; l < TDA_MAX_LEVELS; l++) P.J[l] = c.subchain[l];
+        P.C = (int)c.n_chains;
+        n_tiles = (P.C + tda::TC - 1) / tda::TC;
+        Cs = n_tiles * tda::TC;
+        P.Cs = Cs; P.n_tiles = n_tiles;
+        P.chain_offset = c.chain_offset;
+        P.Cg = c.n_chains_global > 0 ? c.n_chains_global : c.n_chains;
+        P.seed = c.seed;
+        P.gamma = (R)c.gamma; P.alpha_star = (R)c.alpha_star; P.am_sd = (R)c.am_sd; P.am_eps = (R)c.am_eps;
+        P.dream_b = (R)c.dream_b; P.dream_b_star = (R)c.dream_b_star;
+        P.dream_M0 = c.dream_M0; P.dream_delta = c.dream_delta; P.dream_nCR = c.dream_nCR;
+        P.dream_cap = c.dream_capacity;
+        P.prior_logconst = (R)c.prior_logconst;
+        P.ldD = round_up(d, tda::NB);
+        P.zlen = c.stream_z_len; P.ulen = c.stream_u_len;
+
+        R* tmp;
+        DALLOC(tmp, d); P.prior_mean = tmp;
+        DALLOC(tmp, (size_t)d * P.ldD); P.LP = tmp;
+        DALLOC(tmp, (size_t)d * P.ldD); P.Pprec = tmp;
+        DALLOC(tmp, (size_t)d * P.ldD); P.T = tmp;
+        DALLOC(P.scaling, Cs);
+        DALLOC(P.ucur, Cs);
+        DALLOC(P.sum1, (size_t)d * Cs);
+        DALLOC(P.sum2, (size_t)d * Cs);
+        DALLOC(P.error_flag, 1);
+        if (c.adaptive) { DALLOC(P.win, (size_t)P.period * Cs); DALLOC(P.win_sum, Cs); }
+        if (c.rng_mode == TDA_RNG_INJECTED) {
+            DALLOC(tmp, (size_t)P.C * P.zlen); P.zs = tmp;
+            DALLOC(tmp, (size_t)P.C * P.ulen); P.us = tmp;
+        }
+        if (c.prop_kind == TDA_PROP_AM) {
+            DALLOC(P.am_mu, (size_t)d * Cs);
+            DALLOC(P.am_sigma, (size_t)d * d * Cs);
+            DALLOC(P.am_T, (size_t)d * d * Cs);
+        }
+        if (c.prop_kind == TDA_PROP_MALA) { DALLOC(P.grad, (size_t)d * Cs); DALLOC(P.gradp, (size_t)d * Cs); }
+        if (c.prop_kind >= TDA_PROP_DREAMZ) {
+            DALLOC(P.archive, (size_t)c.dream_capacity * P.Cg * d);
+            dream_slots = c.dream_M0;
+        }
+        kt = d;
+        int n_max = 0;
+        ldA.assign(L, 0);
+        for (int l = 0; l < L; l++) {
+            const tda_level_config& lc = c.level[l];
+            tda::LevelP<R>& v = P.lv[l];
+            const int m = lc.m;
+            v.model_kind = lc.model_kind; v.m = m; v.n_grid = lc.n_grid; v.lik_kind = lc.lik_kind;
+            v.store = lc.store; v.hist_cap = lc.hist_capacity;
+            v.lik_var = (R)lc.lik_var; v.sc0 = (R)lc.model_scalars[0]; v.sc1 = (R)lc.model_scalars[1];
+            v.stride = (int)lc.model_scalars[0];
+            v.need_F = (lc.lik_kind >= TDA_LIK_DENSE) || (lc.model_kind != TDA_MODEL_LINEAR) || c.aem ||
+                       (lc.store & TDA_STORE_OUTPUT) || (c.prop_kind == TDA_PROP_MALA);
+            const int ncols = (lc.model_kind == TDA_MODEL_POISSON1D) ? lc.n_grid : m;
+            v.ldA = round_up(ncols, tda::NB);
+            ldA[l] = v.ldA;
+            if (lc.model_kind == TDA_MODEL_POISSON1D && lc.n_grid > n_max) n_max = lc.n_grid;
+            if (lc.model_kind != TDA_MODEL_ROSENBROCK) { DALLOC(tmp, (size_t)d * v.ldA); v.A = tmp; }
+            if (lc.model_kind == TDA_MODEL_LINEAR && c.prop_kind == TDA_PROP_MALA) {
+                DALLOC(tmp, (size_t)m * P.ldD); v.A2 = tmp;
+                if (m > kt) kt = m;
+            }
+            DALLOC(tmp, m); v.b = tmp;
+            DALLOC(tmp, m); v.data = tmp;
+            DALLOC(tmp, m); v.var = tmp;
+            if (lc.lik_kind >= TDA_LIK_DENSE) { DALLOC(tmp, (size_t)m * m); v.prec = tmp; }
+            if (lc.lik_kind == TDA_LIK_ADAPTIVE) { DALLOC(tmp, (size_t)m * m); v.cov = tmp; }
+            DALLOC(v.theta, (size_t)d * Cs);
+            DALLOC(v.prior, Cs);
+            DALLOC(v.like, Cs);
+            DALLOC(v.sid, Cs);
+            DALLOC(v.n_acc, Cs);
+            DALLOC(v.acc_sub, Cs);
+            if (v.need_F) { DALLOC(v.F, (size_t)m * Cs); DALLOC(v.Fp, (size_t)m * Cs); }
+            for (int a = l + 1; a < L; a++) {
+                DALLOC(v.sv_prior[a], Cs);
+                DALLOC(v.sv_like[a], Cs);
+                if (v.need_F) DALLOC(v.sv_F[a], (size_t)m * Cs);
+            }
+            if (lc.lik_kind == TDA_LIK_ADAPTIVE) {
+                DALLOC(v.lik_bias, (size_t)m * Cs);
+                DALLOC(v.lik_prec, (size_t)m * m * Cs);
+            }
+            if (c.aem && l >= 1) {
+                DALLOC(v.bias_mu, (size_t)m * Cs);
+                DALLOC(v.model_diff, (size_t)m * Cs);
+                DALLOC(v.bias_sigma, (size_t)m * m * Cs);
+            }
+            const size_t cap = (size_t)lc.hist_capacity;
+            if (lc.store & TDA_STORE_THETA) DALLOC(v.h_theta, cap * d * Cs);
+            if (lc.store & TDA_STORE_STATS) { DALLOC(v.h_prior, cap * Cs); DALLOC(v.h_like, cap * Cs); }
+            if (lc.store & TDA_STORE_OUTPUT) DALLOC(v.h_F, cap * m * Cs);
+            if (lc.store & TDA_STORE_ACCEPT) DALLOC(v.h_acc, cap * Cs);
+        }
+        if (kt > tda::MAXD) return fail(-1, "contraction dimension exceeds TDA_MAX_D");
+        if (n_max > 0) { P.n_max = n_max; DALLOC(P.scratch, (size_t)3 * n_max * Cs); }
+        smem_bytes = ((size_t)2 * kt * tda::TC + (size_t)2 * kt * tda::NB + tda::CW * tda::TC + 4 * tda::TC) * sizeof(R) +
+                     tda::TC * sizeof(int);
+        CUDA_TRY(cudaFuncSetAttribute(tda::chain_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        // initial scaling
+        {
+            size_t n = Cs;
+            fill_kernel<R><<<(unsigned)((n + 255) / 256), 256>>>(P.scaling, (R)c.scaling, n);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaDeviceSynchronize());
+        return 0;
+    }
+
+    // ---- uploads ---------------------------------------------------------------------------
+    int put(const R* dst, const std::vector<R>& h) {
+        CUDA_TRY(cudaMemcpy(const_cast<R*>(dst), h.data(), h.size() * sizeof(R), cudaMemcpyHostToDevice));
+        return 0;
+    }
+
+    int put_matrix(const R* dst, const double* src, int rows, int cols, int ld) {
+        std::vector<R> h((size_t)rows * ld, (R)0);
+        for (int i = 0; i < rows; i++)
+            for (int j = 0; j < cols; j++) h[(size_t)i * ld + j] = (R)src[(size_t)i * cols + j];
+        return put(dst, h);
+    }
+
+    int upload(int what, int level, const double* host, size_t count) override {
+        CUDA_TRY(cudaSetDevice(device));
+        const int d = P.d, L = P.L;
+        if (what >= TDA_UP_MODEL_A && what <= TDA_UP_LIK_COV && (level < 0 || level >= L))
+            return fail(-1, "upload: bad level");
+        auto need = [&](size_t n) -> int {
+            if (count != n) return fail(-1, "upload: expected " + std::to_string(n) + " values, got " + std::to_string(count));
+            return 0;
+        };
+        int r;
+        switch (what) {
+        case TDA_UP_PRIOR_MEAN:
+            if ((r = need(d))) return r;
+            return put_matrix(P.prior_mean, host, 1, d, d);
+        case TDA_UP_PRIOR_LP:
+            if ((r = need((size_t)d * d))) return r;
+            return put_matrix(P.LP, host, d, d, P.ldD);
+        case TDA_UP_PRIOR_PREC:
+            if ((r = need((size_t)d * d))) return r;
+            return put_matrix(P.Pprec, host, d, d, P.ldD);
+        case TDA_UP_PROP_T: {
+            if ((r = need((size_t)d * d))) return r;
+            if ((r = put_matrix(P.T, host, d, d, P.ldD))) return r;
+            if (P.prop_kind == TDA_PROP_AM) {
+                size_t total = (size_t)d * d * Cs;
+                broadcast_kernel<R><<<(unsigned)((total + 255) / 256), 256>>>(P.am_T, P.T, d, P.ldD, d, Cs);
+                g_launches++;
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaDeviceSynchronize());
+            }
+            return 0;
+        }
+        case TDA_UP_MODEL_A: {
+            const tda::LevelP<R>& v = P.lv[level];
+            const int ncols = (v.model_kind == TDA_MODEL_POISSON1D) ? v.n_grid : v.m;
+            if ((r = need((size_t)d * ncols))) return r;
+            if ((r = put_matrix(v.A, host, d, ncols, v.ldA))) return r;
+            if (v.A2) {   // G [m][ldD] = transpose of the uploaded G^T
+                std::vector<R> h((size_t)v.m * P.ldD, (R)0);
+                for (int k = 0; k < d; k++)
+                    for (int j = 0; j < v.m; j++) h[(size_t)j * P.ldD + k] = (R)host[(size_t)k * v.m + j];
+                return put(v.A2, h);
+            }
+            return 0;
+        }
+        case TDA_UP_MODEL_B:
+            if ((r = need(P.lv[level].m))) return r;
+            return put_matrix(P.lv[level].b, host, 1, P.lv[level].m, P.lv[level].m);
+        case TDA_UP_LIK_DATA:
+            if ((r = need(P.lv[level].m))) return r;
+            return put_matrix(P.lv[level].data, host, 1, P.lv[level].m, P.lv[level].m);
+        case TDA_UP_LIK_VAR:
+            if ((r = need(P.lv[level].m))) return r;
+            return put_matrix(P.lv[level].var, host, 1, P.lv[level].m, P.lv[level].m);
+        case TDA_UP_LIK_PREC: {
+            const int m = P.lv[level].m;
+            if (!P.lv[level].prec) return fail(-1, "upload: level has no dense precision");
+            if ((r = need((size_t)m * m))) return r;
+            return put_matrix(P.lv[level].prec, host, m, m, m);
+        }
+        case TDA_UP_LIK_COV: {
+            const int m = P.lv[level].m;
+            if (!P.lv[level].cov) return fail(-1, "upload: level is not adaptive");
+            if ((r = need((size_t)m * m))) return r;
+            return put_matrix(P.lv[level].cov, host, m, m, m);
+        }
+        case TDA_UP_INIT_THETA: {
+            if ((r = need((size_t)P.C * d))) return r;
+            std::vector<R> h((size_t)d * Cs, (R)0);
+            for (int c = 0; c < P.C; c++)
+                for (int k = 0; k < d; k++) h[(size_t)k * Cs + c] = (R)host[(size_t)c * d + k];
+            for (int l = 0; l < L; l++)
+                if ((r = put(P.lv[l].theta, h))) return r;
+            return 0;
+        }
+        case TDA_UP_STREAM_Z:
+            if (!P.zs) return fail(-1, "upload: engine is not in injected-stream mode");
+            if ((r = need((size_t)P.C * P.zlen))) return r;
+            return put_matrix(P.zs, host, 1, (int)count, (int)count);
+        case TDA_UP_STREAM_U:
+            if (!P.us) return fail(-1, "upload: engine is not in injected-stream mode");
+            if ((r = need((size_t)P.C * P.ulen))) return r;
+            return put_matrix(P.us, host, 1, (int)count, (int)count);
+        case TDA_UP_DREAM_ARCHIVE0: {
+            if (!P.archive) return fail(-1, "upload: proposal has no archive");
+            const int M0 = P.dream_M0;
+            if ((r = need((size_t)P.Cg * M0 * d))) return r;
+            std::vector<R> h((size_t)M0 * P.Cg * d);
+            for (long long g = 0; g < P.Cg; g++)
+                for (int s = 0; s < M0; s++)
+                    for (int k = 0; k < d; k++)
+                        h[((size_t)s * P.Cg + g) * d + k] = (R)host[((size_t)g * M0 + s) * d + k];
+            return put(P.archive, h);
+        }
+        case TDA_UP_AM_FACTORS: {
+            if (!P.am_T) return fail(-1, "upload: proposal is not AdaptiveMetropolis");
+            if ((r = need((size_t)P.C * d * d))) return r;
+            std::vector<R> h((size_t)d * d * Cs, (R)0);
+            for (int c = 0; c < P.C; c++)
+                for (int e = 0; e < d * d; e++) h[(size_t)e * Cs + c] = (R)host[(size_t)c * d * d + e];
+            return put(P.am_T, h);
+        }
+        default:
+            return fail(-1, "upload: unknown item");
+        }
+    }
+
+    // ---- launches ----------------------------------------------------------------------------
+    int launch(int mode, long long iterations, cudaStream_t st) {
+        CUDA_TRY(cudaSetDevice(device));
+        P.mode = mode;
+        P.iterations = iterations;
+        P.dream_slots = dream_slots;
+        int occ = (sizeof(R) == 4) ? 2 : 1;
+        int grid = n_tiles < sm_count * occ ? n_tiles : sm_count * occ;
+        tda::chain_kernel<R><<<grid, tda::NT, smem_bytes, st>>>(P, kt);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+
+    int init(cudaStream_t st) override {
+        P.t_base = 0; P.wcount = 0;
+        for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = 0; P.lvl_steps[l] = 0; }
+        int r = launch(tda::MODE_INIT, 0, st);
+        if (r) return r;
+        P.rec[P.L - 1] = 1;
+        initialised = true;
+        return 0;
+    }
+
+    bool tc_eligible() const { return tc.eligible(cfg, P); }
+
+    int run(long long iterations, cudaStream_t st) override {
+        if (!initialised) return fail(-1, "run: call tda_engine_init first");
+        if (iterations <= 0) return 0;
+        const int L = P.L;
+        if (P.prop_kind == TDA_PROP_AM && !P.am_device_refactor) {
+            long long to_boundary = P.period - (P.t_base % P.period);
+            if (iterations > to_boundary)
+                return fail(-1, "run: AdaptiveMetropolis with host refactoring must stop at period boundaries");
+        }
+        bool use_tc = (kernel_choice == 2) || (kernel_choice == 0 && tc_eligible());
+        if (kernel_choice == 2 && !tc_eligible()) return fail(-1, "run: tensor-core DA kernel does not support this configuration");
+        int r;
+        if (use_tc) {
+            r = tc.run(P, cfg, iterations, sm_count, st);
+            if (r) return fail(r, tc.err);
+            g_launches++;
+        } else if (P.prop_kind == TDA_PROP_DREAM && iterations > 1) {
+            // shared archive: lock-step visibility (every chain sees all rows through the
+            // previous step) needs a grid-wide boundary per step -> one launch per step
+            for (long long i = 0; i < iterations; i++) {
+                r = run(1, st);
+                if (r) return r;
+            }
+            return 0;
+        } else {
+            r = launch(tda::MODE_RUN, iterations, st);
+            if (r) return r;
+        }
+        // advance the uniform counters exactly like the kernel did
+        long long steps[tda::MAXL];
+        steps[L - 1] = iterations;
+        for (int l = L - 2; l >= 0; l--) steps[l] = steps[l + 1] * P.J[l];
+        P.t_base += steps[0];
+        long long w = steps[0];
+        for (int l = 1; l < L; l++) w += steps[l];
+        P.wcount += (L == 1) ? steps[0] : w;
+        for (int l = 0; l < L; l++) { P.rec[l] += steps[l]; if (l >= 1) P.lvl_steps[l] += steps[l]; }
+        if (P.prop_kind >= TDA_PROP_DREAMZ) dream_slots += steps[0];
+        return 0;
+    }
+
+    int history_reset() override {
+        for (int l = 0; l < P.L; l++) P.rec[l] = 0;
+        return 0;
+    }
+
+    int select_kernel(int which) override {
+        kernel_choice = which;
+        return 0;
+    }
+
+    // ---- downloads ---------------------------------------------------------------------------
+    int fetch(int level, int field, long long rec0, long long nrec, void* dst, size_t dst_bytes, size_t* bytes,
+              cudaStream_t st) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (level < 0 || level >= P.L) return fail(-1, "fetch: bad level");
+        const tda::LevelP<R>& v = P.lv[level];
+        if (rec0 < 0 || nrec < 0 || rec0 + nrec > v.hist_cap) return fail(-1, "fetch: record range outside the history buffer");
+        const void* src = nullptr;
+        size_t rows = 0, esz = sizeof(R);
+        switch (field) {
+        case TDA_F_THETA: src = v.h_theta ? v.h_theta + (size_t)rec0 * P.d * Cs : nullptr; rows = (size_t)nrec * P.d; break;
+        case TDA_F_PRIOR: src = v.h_prior ? v.h_prior + (size_t)rec0 * Cs : nullptr; rows = (size_t)nrec; break;
+        case TDA_F_LIKE: src = v.h_like ? v.h_like + (size_t)rec0 * Cs : nullptr; rows = (size_t)nrec; break;
+        case TDA_F_OUTPUT: src = v.h_F ? v.h_F + (size_t)rec0 * v.m * Cs : nullptr; rows = (size_t)nrec * v.m; break;
+        case TDA_F_ACCEPT: src = v.h_acc ? v.h_acc + (size_t)rec0 * Cs : nullptr; rows = (size_t)nrec; esz = 1; break;
+        default: return fail(-1, "fetch: unknown field");
+        }
+        if (!src) return fail(-1, "fetch: field was not stored for this level");
+        size_t need = rows * (size_t)P.C * esz;
+        if (bytes) *bytes = need;
+        if (dst_bytes < need) return fail(-1, "fetch: destination too small");
+        if (rows == 0) return 0;
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)P.C * esz, src, (size_t)Cs * esz, (size_t)P.C * esz, rows,
+                                   cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+
+    template <typename T>
+    int get_soa(const T* src, int rows, void* dst, size_t bytes, bool as_double, bool transpose) {
+        // device [rows][Cs] -> host [rows][C] or (transpose) [C][rows]; optionally widened to float64
+        std::vector<T> h((size_t)rows * Cs);
+        CUDA_TRY(cudaMemcpy(h.data(), src, h.size() * sizeof(T), cudaMemcpyDeviceToHost));
+        size_t need = (size_t)rows * P.C * (as_double ? sizeof(double) : sizeof(T));
+        if (bytes < need) return fail(-1, "get: destination too small");
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < P.C; c++) {
+                size_t o = transpose ? (size_t)c * rows + r : (size_t)r * P.C + c;
+                if (as_double) reinterpret_cast<double*>(dst)[o] = (double)h[(size_t)r * Cs + c];
+                else reinterpret_cast<T*>(dst)[o] = h[(size_t)r * Cs + c];
+            }
+        return 0;
+    }
+
+    int get(int what, int level, void* dst, size_t bytes) override {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        const int d = P.d;
+        switch (what) {
+        case TDA_G_SCALING: return get_soa(P.scaling, 1, dst, bytes, true, false);
+        case TDA_G_ACCEPT_COUNTS: {
+            if (bytes < (size_t)P.L * P.C * sizeof(long long)) return fail(-1, "get: destination too small");
+            for (int l = 0; l < P.L; l++) {
+                int r = get_soa(P.lv[l].n_acc, 1, reinterpret_cast<long long*>(dst) + (size_t)l * P.C,
+                                (size_t)P.C * sizeof(long long), false, false);
+                if (r) return r;
+            }
+            return 0;
+        }
+        case TDA_G_CURSORS: {
+            if (bytes < (size_t)2 * P.C * sizeof(long long)) return fail(-1, "get: destination too small");
+            long long* o = reinterpret_cast<long long*>(dst);
+            for (int c = 0; c < P.C; c++) o[c] = P.t_base * d;
+            return get_soa(P.ucur, 1, o + P.C, (size_t)P.C * sizeof(long long), false, false);
+        }
+        case TDA_G_AM_SIGMA:
+            if (!P.am_sigma) return fail(-1, "get: proposal is not AdaptiveMetropolis");
+            return get_soa(P.am_sigma, d * d, dst, bytes, true, true);
+        case TDA_G_AM_MU:
+            if (!P.am_mu) return fail(-1, "get: proposal is not AdaptiveMetropolis");
+            return get_soa(P.am_mu, d, dst, bytes, true, true);
+        case TDA_G_THETA:
+            if (level < 0 || level >= P.L) return fail(-1, "get: bad level");
+            return get_soa(P.lv[level].theta, d, dst, bytes, true, true);
+        case TDA_G_NRECORDS: {
+            if (bytes < (size_t)P.L * sizeof(long long)) return fail(-1, "get: destination too small");
+            for (int l = 0; l < P.L; l++) reinterpret_cast<long long*>(dst)[l] = P.rec[l];
+            return 0;
+        }
+        case TDA_G_MOMENTS: {
+            if (bytes < (size_t)2 * d * P.C * sizeof(double)) return fail(-1, "get: destination too small");
+            int r = get_soa(P.sum1, d, dst, (size_t)d * P.C * sizeof(double), true, false);
+            if (r) return r;
+            return get_soa(P.sum2, d, reinterpret_cast<double*>(dst) + (size_t)d * P.C, (size_t)d * P.C * sizeof(double), true, false);
+        }
+        default: return fail(-1, "get: unknown item");
+        }
+    }
+
+    int set(int what, int level, const void* src, size_t bytes) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (what == TDA_G_SCALING) {
+            if (bytes != (size_t)P.C * sizeof(double)) return fail(-1, "set: scaling needs n_chains float64 values");
+            std::vector<R> h(Cs, (R)cfg.scaling);
+            for (int c = 0; c < P.C; c++) h[c] = (R)reinterpret_cast<const double*>(src)[c];
+            return put(P.scaling, h);
+        }
+        return fail(-1, "set: unknown item");
+    }
+
+    int device_buffer(int buffer, int level, void** ptr, size_t* bytes) override {
+        if (buffer == TDA_BUF_DREAM_ARCHIVE) {
+            if (!P.archive) return fail(-1, "device_buffer: proposal has no archive");
+            *ptr = P.archive;
+            *bytes = (size_t)P.dream_cap * P.Cg * P.d * sizeof(R);
+            return 0;
+        }
+        if (buffer == TDA_BUF_HIST_THETA) {
+            if (level < 0 || level >= P.L || !P.lv[level].h_theta) return fail(-1, "device_buffer: no such history");
+            *ptr = P.lv[level].h_theta;
+            *bytes = (size_t)P.lv[level].hist_cap * P.d * Cs * sizeof(R);
+            return 0;
+        }
+        return fail(-1, "device_buffer: unknown buffer");
+    }
+
+    int fill_streams(double* z, long long nz, double* u, long long nu) override {
+        CUDA_TRY(cudaSetDevice(device));
+        double *dz = nullptr, *du = nullptr;
+        size_t tz = (size_t)P.C * nz, tu = (size_t)P.C * nu;
+        CUDA_TRY(cudaMalloc(&dz, (tz ? tz : 1) * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&du, (tu ? tu : 1) * sizeof(double)));
+        size_t n = tz > tu ? tz : tu;
+        if (n) {
+            tda::fill_streams_kernel<R><<<(unsigned)((n + 255) / 256), 256>>>(P.seed, P.chain_offset, P.C, dz, nz, du, nu);
+            g_launches++;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(z, dz, tz * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(u, du, tu * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaFree(dz);
+        cudaFree(du);
+        if (e != cudaSuccess) return fail(-2, std::string("fill_streams: ") + cudaGetErrorString(e));
+        return 0;
+    }
+};
+
+int validate(const tda_config* c) {
+    if (!c) return fail(-1, "null config");
+    if (c->abi_version != TDA_ABI_VERSION) return fail(-1, "ABI version mismatch");
+    if (c->dtype != TDA_F32 && c->dtype != TDA_F64) return fail(-1, "dtype must be TDA_F32 or TDA_F64");
+    if (c->n_levels < 1 || c->n_levels > TDA_MAX_LEVELS) return fail(-1, "n_levels out of range");
+    if (c->d < 1 || c->d > TDA_MAX_D) return fail(-1, "d out of range (1..64)");
+    if (c->n_chains < 1) return fail(-1, "n_chains must be positive");
+    for (int l = 0; l + 1 < c->n_levels; l++)
+        if (c->subchain[l] < 1) return fail(-1, "subchain lengths must be >= 1");
+    if (c->prop_kind < TDA_PROP_RWMH || c->prop_kind > TDA_PROP_DREAM) return fail(-1, "unknown proposal kind");
+    if ((c->prop_kind == TDA_PROP_MALA || c->prop_kind >= TDA_PROP_DREAMZ) && c->n_levels != 1)
+        return fail(-1, "MALA / DREAM(Z) are single-level proposals in this engine");
+    if (c->prop_kind >= TDA_PROP_DREAMZ) {
+        if (c->dream_delta < 1 || c->dream_delta > tda::MAX_DELTA) return fail(-1, "DREAM delta out of range (1..8)");
+        if (c->dream_M0 < 2 || c->dream_capacity < c->dream_M0) return fail(-1, "DREAM archive capacity too small");
+    }
+    if (c->adaptive && c->period < 1) return fail(-1, "period must be >= 1");
+    for (int l = 0; l < c->n_levels; l++) {
+        const tda_level_config& lc = c->level[l];
+        if (lc.m < 1) return fail(-1, "level has no outputs");
+        if (lc.model_kind < TDA_MODEL_LINEAR || lc.model_kind > TDA_MODEL_POISSON1D) return fail(-1, "unknown model kind");
+        if (lc.lik_kind < TDA_LIK_ISO || lc.lik_kind > TDA_LIK_ADAPTIVE) return fail(-1, "unknown likelihood kind");
+        if (lc.model_kind == TDA_MODEL_ROSENBROCK && (c->d != 2 || lc.m != 1)) return fail(-1, "Rosenbrock needs d=2, m=1");
+        if (lc.model_kind == TDA_MODEL_POISSON1D && lc.n_grid < 4) return fail(-1, "Poisson grid too small");
+        if (c->aem && l + 1 < c->n_levels && lc.lik_kind != TDA_LIK_ADAPTIVE)
+            return fail(-1, "adaptive error model needs adaptive likelihoods on the coarse levels");
+        if (c->aem && lc.m != c->level[0].m) return fail(-1, "adaptive error model needs equal output sizes");
+        if (c->prop_kind == TDA_PROP_MALA && lc.lik_kind >= TDA_LIK_DENSE) return fail(-1, "MALA supports isotropic / diagonal likelihoods");
+        if (c->prop_kind == TDA_PROP_MALA && lc.model_kind == TDA_MODEL_POISSON1D) return fail(-1, "MALA needs a model with a gradient");
+        if (c->prop_kind == TDA_PROP_MALA && lc.model_kind == TDA_MODEL_LINEAR && lc.m > TDA_MAX_D)
+            return fail(-1, "MALA with a linear model supports m <= 64");
+    }
+    if (c->rng_mode == TDA_RNG_INJECTED && (c->stream_z_len < 1 || c->stream_u_len < 1)) return fail(-1, "injected streams need lengths");
+    return 0;
+}
+
+}  // namespace
+
+// ---- C ABI -----------------------------------------------------------------------------------
+extern "C" {
+
+int tda_abi_version(void) { return TDA_ABI_VERSION; }
+const char* tda_last_error(void) { return g_err.c_str(); }
+int64_t tda_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int tda_engine_create(const tda_config* cfg, int device, tda_engine** out) {
+    if (!out) return fail(-1, "null output pointer");
+    *out = nullptr;
+    int r = validate(cfg);
+    if (r) return r;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(-4, "no CUDA device available: the tinyda_b200 engine has no CPU path");
+    if (device < 0 || device >= ndev) return fail(-1, "bad device index");
+    tda_engine* e = nullptr;
+    if (cfg->dtype == TDA_F32) {
+        auto* t = new EngineT<float>();
+        t->cfg = *cfg; t->device = device;
+        r = t->create();
+        e = t;
+    } else {
+        auto* t = new EngineT<double>();
+        t->cfg = *cfg; t->device = device;
+        r = t->create();
+        e = t;
+    }
+    if (r) { delete e; return r; }
+    *out = e;
+    return 0;
+}
+
+int tda_engine_destroy(tda_engine* e) {
+    delete e;
+    return 0;
+}
+
+int tda_upload(tda_engine* e, int what, int level, const double* host, size_t count) {
+    if (!e || !host) return fail(-1, "null argument");
+    return e->upload(what, level, host, count);
+}
+int tda_engine_init(tda_engine* e, void* s) { return e ? e->init((cudaStream_t)s) : fail(-1, "null engine"); }
+int tda_engine_run(tda_engine* e, int64_t it, void* s) { return e ? e->run(it, (cudaStream_t)s) : fail(-1, "null engine"); }
+int tda_engine_sync(tda_engine* e, void* s) {
+    if (!e) return fail(-1, "null engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)s));
+    return 0;
+}
+int tda_fetch(tda_engine* e, int level, int field, int64_t rec0, int64_t nrec, void* dst, size_t dst_bytes,
+              size_t* bytes, void* s) {
+    if (!e || !dst) return fail(-1, "null argument");
+    return e->fetch(level, field, rec0, nrec, dst, dst_bytes, bytes, (cudaStream_t)s);
+}
+int tda_get(tda_engine* e, int what, int level, void* dst, size_t bytes) {
+    if (!e || !dst) return fail(-1, "null argument");
+    return e->get(what, level, dst, bytes);
+}
+int tda_set(tda_engine* e, int what, int level, const void* src, size_t bytes) {
+    if (!e || !src) return fail(-1, "null argument");
+    return e->set(what, level, src, bytes);
+}
+int tda_device_buffer(tda_engine* e, int buffer, int level, void** ptr, size_t* bytes) {
+    if (!e || !ptr || !bytes) return fail(-1, "null argument");
+    return e->device_buffer(buffer, level, ptr, bytes);
+}
+int tda_dream_slots(tda_engine* e, int64_t* slots) {
+    if (!e || !slots) return fail(-1, "null argument");
+    *slots = e->dream_slots;
+    return 0;
+}
+int tda_fill_streams(tda_engine* e, double* z, int64_t nz, double* u, int64_t nu) {
+    if (!e || !z || !u) return fail(-1, "null argument");
+    return e->fill_streams(z, nz, u, nu);
+}
+int tda_history_reset(tda_engine* e) { return e ? e->history_reset() : fail(-1, "null engine"); }
+int tda_select_kernel(tda_engine* e, int which) { return e ? e->select_kernel(which) : fail(-1, "null engine"); }
+
+}  // extern "C"

@@ -1,0 +1,956 @@
+// Generic lock-step chain kernel: one launch advances every chain of the engine by
+// `iterations` finest-level iterations of MH / Delayed Acceptance / MLDA, nested coarse
+// subchains included, with no host round trip.  A CTA owns a tile of TC chains for the whole
+// run; per-chain state lives in structure-of-arrays buffers (chain index fastest, so a warp
+// reads 32 consecutive chains = one 128/256-byte line); the dense contractions (proposal
+// factor, prior whitening, linear forward operator, Poisson log-conductivity field) are
+// tile contractions [TC chains x K] @ [K x N] with the shared operand staged through shared
+// memory by cp.async double buffering and the per-chain reductions (|w|^2, |F-data|^2)
+// fused into the epilogue.
+//
+// Reference map (file:line into the reference's tinyDA/ package):
+//   Tile::base_step        chain.py:101-125, :415-444; proposal.py:1583-1613
+//   Tile::upper_step       chain.py:353-402, :708-765; proposal.py:1511-1578
+//   Tile::align            proposal.py:1469-1493 (object identity -> state ids + saved versions)
+//   Tile::eval_level       posterior.py:78-110 (create_link)
+//   Tile::push_bias        chain.py:485-523, :740-765; proposal.py:1442-1467, :1548-1578;
+//                          distributions.py:385-425
+//   Tile::propose_*        proposal.py:247-251 (RWMH/AM), :349-355 (pCN), :811-852 (DREAMZ),
+//                          :948-959 (MALA)
+//   Tile::adapt            proposal.py:228-245, :502-512, :790-795; utils.py:113-124
+#pragma once
+#include "tda_common.cuh"
+
+namespace tda {
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <typename R> struct VecB;
+template <> struct VecB<float> {
+    static constexpr int W = 4;
+    typedef float4 T;
+    static __device__ __forceinline__ void unpack(const T& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+template <> struct VecB<double> {
+    static constexpr int W = 2;
+    typedef double2 T;
+    static __device__ __forceinline__ void unpack(const T& v, double* o) { o[0] = v.x; o[1] = v.y; }
+};
+
+// -------------------------------------------------------------------------------------------
+// Tile contraction: out[c][n] = sum_k (As[k][c] - sub[k]) * Bg[k][n],  c < TC, n < N.
+// Thread (lane, warp): chains c0 = rg*64+lane, c1 = c0+32 (rg = warp/4), columns
+// n0 + cw*RN + j (cw = warp%4).  `epi(r, c, n, value)` is called once per output.
+// -------------------------------------------------------------------------------------------
+template <typename R, typename Epi>
+__device__ __forceinline__ void tile_gemm(const R* __restrict__ As, const R* __restrict__ sub,
+                                          const R* __restrict__ Bg, int K, int N, int ldb,
+                                          R* __restrict__ bs, int KB, Epi& epi) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int cw = w & (CW - 1), rg = w >> 2;
+    const int c0 = rg * 64 + lane, c1 = c0 + 32;
+    const int nchunks = (N + NB - 1) / NB;
+    constexpr int VW = VecB<R>::W;
+    constexpr int VPR = NB / VW;          // 16-byte vectors per staged row
+    const int total = K * VPR;
+    // prefetch chunk 0
+    for (int v = tid; v < total; v += NT) {
+        int k = v / VPR, j = v - k * VPR;
+        cp_async16(bs + k * NB + j * VW, Bg + (size_t)k * ldb + j * VW);
+    }
+    cp_async_commit();
+    for (int ch = 0; ch < nchunks; ch++) {
+        if (ch + 1 < nchunks) {
+            R* dst = bs + ((ch + 1) & 1) * KB * NB;
+            const R* src = Bg + (size_t)(ch + 1) * NB;
+            for (int v = tid; v < total; v += NT) {
+                int k = v / VPR, j = v - k * VPR;
+                cp_async16(dst + k * NB + j * VW, src + (size_t)k * ldb + j * VW);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        R acc0[RN], acc1[RN];
+#pragma unroll
+        for (int j = 0; j < RN; j++) { acc0[j] = (R)0; acc1[j] = (R)0; }
+        const R* bsc = bs + (ch & 1) * KB * NB + cw * RN;
+#pragma unroll 2
+        for (int k = 0; k < K; k++) {
+            R a0 = As[k * TC + c0], a1 = As[k * TC + c1];
+            if (sub != nullptr) { R s = sub[k]; a0 -= s; a1 -= s; }
+            R b[RN];
+            const typename VecB<R>::T* bv = reinterpret_cast<const typename VecB<R>::T*>(bsc + k * NB);
+#pragma unroll
+            for (int j = 0; j < RN / VW; j++) VecB<R>::unpack(bv[j], b + j * VW);
+#pragma unroll
+            for (int j = 0; j < RN; j++) {
+                acc0[j] = fma(a0, b[j], acc0[j]);
+                acc1[j] = fma(a1, b[j], acc1[j]);
+            }
+        }
+        const int nbase = ch * NB + cw * RN;
+#pragma unroll
+        for (int j = 0; j < RN; j++) {
+            int n = nbase + j;
+            if (n < N) {
+                epi(0, c0, n, acc0[j]);
+                epi(1, c1, n, acc1[j]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- epilogues -----------------------------------------------------------------------------
+template <typename R>
+struct EpiSsq {            // sum of squares per chain (prior whitening)
+    R ps[RM];
+    __device__ EpiSsq() { ps[0] = ps[1] = (R)0; }
+    __device__ __forceinline__ void operator()(int r, int, int, R v) { ps[r] = fma(v, v, ps[r]); }
+};
+
+template <typename R>
+struct EpiCombine {        // theta' = a_c * theta_c + b_c * xi   -> proposal tile
+    const R* theta; int Cs; int chain0; R* pt; const R* ca; const R* cb;
+    __device__ __forceinline__ void operator()(int, int c, int n, R v) {
+        pt[n * TC + c] = ca[c] * theta[(size_t)n * Cs + chain0 + c] + cb[c] * v;
+    }
+};
+
+template <typename R>
+struct EpiLinear {         // F = v + b; optional store; residual reduction for ISO / DIAG
+    const R* b; const R* data; const R* var; R* Fp; int Cs; int chain0; int lik_kind; int need_F;
+    R ps[RM];
+    __device__ __forceinline__ void operator()(int r, int c, int n, R v) {
+        R F = v + b[n];
+        if (need_F) Fp[(size_t)n * Cs + chain0 + c] = F;
+        R res = F - data[n];
+        if (lik_kind == TDA_LIK_ISO) ps[r] = fma(res, res, ps[r]);
+        else if (lik_kind == TDA_LIK_DIAG) ps[r] += res * res / var[n];
+    }
+};
+
+template <typename R>
+struct EpiExpStore {       // Poisson: conductivity field k = exp(Phi theta) -> scratch
+    R* kf; int Cs; int chain0;
+    __device__ __forceinline__ void operator()(int, int c, int n, R v) {
+        kf[(size_t)n * Cs + chain0 + c] = texp(v);
+    }
+};
+
+template <typename R>
+struct EpiStoreNeg {       // out[n][c] (+)= -v   (MALA prior gradient P (mu - x))
+    R* out; int Cs; int chain0; int accumulate;
+    __device__ __forceinline__ void operator()(int, int c, int n, R v) {
+        size_t i = (size_t)n * Cs + chain0 + c;
+        out[i] = accumulate ? out[i] - v : -v;
+    }
+};
+
+template <typename R>
+struct EpiStore {          // out[n][c] = v
+    R* out; int Cs; int chain0;
+    __device__ __forceinline__ void operator()(int, int c, int n, R v) {
+        out[(size_t)n * Cs + chain0 + c] = v;
+    }
+};
+
+// -------------------------------------------------------------------------------------------
+template <typename R>
+struct Tile {
+    const Params<R>& p;
+    R *zt, *pt, *bs, *red, *s_prior, *s_like, *s_ca, *s_cb;
+    int* s_acc;
+    int KB;            // rows of a staged operand chunk
+    int chain0;        // first chain of this tile
+    int tid;
+    // run-local counters (uniform across chains)
+    long long t_base, wcount, rec[MAXL], lvl_steps[MAXL], slots;
+
+    __device__ Tile(const Params<R>& p_, unsigned char* smem, int kt) : p(p_) {
+        tid = threadIdx.x;
+        KB = kt;
+        zt = reinterpret_cast<R*>(smem);
+        pt = zt + kt * TC;
+        bs = pt + kt * TC;
+        red = bs + 2 * kt * NB;
+        s_prior = red + CW * TC;
+        s_like = s_prior + TC;
+        s_ca = s_like + TC;
+        s_cb = s_ca + TC;
+        s_acc = reinterpret_cast<int*>(s_cb + TC);
+    }
+
+    __device__ __forceinline__ size_t gi(int k, int c) const { return (size_t)k * p.Cs + chain0 + c; }
+
+    // ---- random streams --------------------------------------------------------------------
+    __device__ __forceinline__ R normal_at(int c, long long idx) const {
+        if (p.rng_mode == TDA_RNG_INJECTED) {
+            int ch = chain0 + c;
+            return (ch < p.C && idx < p.zlen) ? p.zs[(size_t)ch * p.zlen + idx] : (R)0;
+        }
+        return philox_normal<R>(p.seed, p.chain_offset + chain0 + c, idx);
+    }
+    __device__ __forceinline__ R uniform_at(int c, long long idx) const {
+        if (p.rng_mode == TDA_RNG_INJECTED) {
+            int ch = chain0 + c;
+            return (ch < p.C && idx < p.ulen) ? p.us[(size_t)ch * p.ulen + idx] : (R)0.5;
+        }
+        return philox_uniform<R>(p.seed, p.chain_offset + chain0 + c, idx);
+    }
+
+    // d normals per chain for this base step -> zt[k][c]
+    __device__ void fill_normals() {
+        const int d = p.d;
+        const long long z0 = t_base * d;
+        if (p.rng_mode == TDA_RNG_PHILOX && (z0 & 3) == 0) {
+            const int nb4 = (d + 3) >> 2;
+            for (int e = tid; e < nb4 * TC; e += NT) {
+                int q = e / TC, c = e - q * TC;
+                R v[4];
+                normals4<R>(philox_block(p.seed, p.chain_offset + chain0 + c, STREAM_Z,
+                                         (unsigned long long)(z0 >> 2) + q), v);
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (4 * q + i < d) zt[(4 * q + i) * TC + c] = v[i];
+            }
+        } else {
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                zt[k * TC + c] = normal_at(c, z0 + k);
+            }
+        }
+    }
+
+    // cross-column-warp reduction of per-thread partial sums; result valid for tid < TC
+    __device__ __forceinline__ R reduce_cols(R ps0, R ps1) {
+        const int lane = tid & 31, w = tid >> 5, cw = w & (CW - 1), rg = w >> 2;
+        red[cw * TC + rg * 64 + lane] = ps0;
+        red[cw * TC + rg * 64 + 32 + lane] = ps1;
+        __syncthreads();
+        R tot = (R)0;
+        if (tid < TC) tot = (red[tid] + red[TC + tid]) + (red[2 * TC + tid] + red[3 * TC + tid]);
+        __syncthreads();
+        return tot;
+    }
+
+    // ---- likelihoods needing the whole output vector (thread per chain) ----------------------
+    __device__ R loglike_from_F(int l, const R* Fsrc, int c) const {
+        const LevelP<R>& v = p.lv[l];
+        const int m = v.m;
+        if (v.lik_kind == TDA_LIK_ISO || v.lik_kind == TDA_LIK_DIAG) {
+            R s = (R)0;
+            for (int j = 0; j < m; j++) {
+                R r = Fsrc[gi(j, c)] - v.data[j];
+                s += (v.lik_kind == TDA_LIK_ISO) ? r * r : r * r / v.var[j];
+            }
+            return (v.lik_kind == TDA_LIK_ISO) ? (R)-0.5 * s / v.lik_var : (R)-0.5 * s;
+        }
+        R q = (R)0;
+        if (v.lik_kind == TDA_LIK_DENSE) {
+            for (int i = 0; i < m; i++) {
+                R ri = Fsrc[gi(i, c)] - v.data[i];
+                R t = (R)0;
+                for (int j = 0; j < m; j++) t = fma(v.prec[i * m + j], Fsrc[gi(j, c)] - v.data[j], t);
+                q = fma(ri, t, q);
+            }
+        } else {   // ADAPTIVE: r = F + bias - data, per-chain precision
+            for (int i = 0; i < m; i++) {
+                R ri = Fsrc[gi(i, c)] + v.lik_bias[gi(i, c)] - v.data[i];
+                R t = (R)0;
+                for (int j = 0; j < m; j++)
+                    t = fma(v.lik_prec[gi(i * m + j, c)], Fsrc[gi(j, c)] + v.lik_bias[gi(j, c)] - v.data[j], t);
+                q = fma(ri, t, q);
+            }
+        }
+        return (R)-0.5 * q;
+    }
+
+    // ---- create_link: log-prior + forward model + log-likelihood for the tile in pt ----------
+    // results: s_prior[c], s_like[c] (shared), lv[l].Fp (global) when need_F
+    __device__ void eval_level(int l) {
+        const LevelP<R>& v = p.lv[l];
+        const int d = p.d;
+        {   // prior: -0.5*(logconst + |(x-mu) LP|^2)
+            EpiSsq<R> e;
+            tile_gemm<R>(pt, p.prior_mean, p.LP, d, d, p.ldD, bs, KB, e);
+            R tot = reduce_cols(e.ps[0], e.ps[1]);
+            if (tid < TC) s_prior[tid] = (R)-0.5 * (p.prior_logconst + tot);
+        }
+        if (v.model_kind == TDA_MODEL_LINEAR) {
+            EpiLinear<R> e;
+            e.b = v.b; e.data = v.data; e.var = v.var; e.Fp = v.Fp; e.Cs = p.Cs; e.chain0 = chain0;
+            e.lik_kind = v.lik_kind; e.need_F = v.need_F; e.ps[0] = e.ps[1] = (R)0;
+            tile_gemm<R>(pt, (const R*)nullptr, v.A, d, v.m, v.ldA, bs, KB, e);
+            R tot = reduce_cols(e.ps[0], e.ps[1]);
+            if (tid < TC) {
+                if (v.lik_kind == TDA_LIK_ISO) s_like[tid] = (R)-0.5 * tot / v.lik_var;
+                else if (v.lik_kind == TDA_LIK_DIAG) s_like[tid] = (R)-0.5 * tot;
+            }
+            if (v.lik_kind >= TDA_LIK_DENSE) {
+                __syncthreads();     // Fp visible to the owning thread (block-scope global writes)
+                if (tid < TC) s_like[tid] = loglike_from_F(l, v.Fp, tid);
+            }
+        } else if (v.model_kind == TDA_MODEL_ROSENBROCK) {
+            if (tid < TC) {
+                R x = pt[tid], y = pt[TC + tid];
+                R a = v.sc0 - x, b = y - x * x;
+                R F = a * a + v.sc1 * b * b;
+                v.Fp[gi(0, tid)] = F;
+                s_like[tid] = loglike_from_F(l, v.Fp, tid);
+            }
+        } else {   // POISSON1D
+            const int n = v.n_grid;
+            R* kf = p.scratch;
+            R* cp = p.scratch + (size_t)p.n_max * p.Cs;
+            R* dp = p.scratch + (size_t)2 * p.n_max * p.Cs;
+            EpiExpStore<R> e;
+            e.kf = kf; e.Cs = p.Cs; e.chain0 = chain0;
+            tile_gemm<R>(pt, (const R*)nullptr, v.A, d, n, v.ldA, bs, KB, e);
+            __syncthreads();
+            if (tid < TC) {
+                const int c = tid, nn = n - 1;
+                const R h2 = (R)1 / ((R)n * (R)n);
+                R k0 = kf[gi(0, c)], k1 = kf[gi(1, c)];
+                R diag = k0 + k1;
+                R cprev = -k1 / diag, dprev = h2 / diag;
+                cp[gi(0, c)] = cprev; dp[gi(0, c)] = dprev;
+                R ki = k1;
+                for (int i = 1; i < nn; i++) {
+                    R kn = kf[gi(i + 1, c)];
+                    R a = -ki;
+                    diag = (ki + kn) - a * cprev;
+                    cprev = -kn / diag;
+                    dprev = (h2 - a * dprev) / diag;
+                    cp[gi(i, c)] = cprev; dp[gi(i, c)] = dprev;
+                    ki = kn;
+                }
+                R u = dprev;     // u[nn-1]
+                const int stride = v.stride;
+                // sensors sit on nodes (s+1)*stride, i.e. unknown index (s+1)*stride-1
+                if ((nn - 1 + 1) % stride == 0) { int s = (nn) / stride - 1; if (s < v.m) v.Fp[gi(s, c)] = u; }
+                for (int i = nn - 2; i >= 0; i--) {
+                    u = dp[gi(i, c)] - cp[gi(i, c)] * u;
+                    if ((i + 1) % stride == 0) { int s = (i + 1) / stride - 1; if (s < v.m) v.Fp[gi(s, c)] = u; }
+                }
+                s_like[tid] = loglike_from_F(l, v.Fp, tid);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- adaptive error model ------------------------------------------------------------
+    // level l (>=1) pushes bias moments into level l-1's likelihood and re-scores level l-1's
+    // current link.  Thread per chain.
+    __device__ void push_bias(int l) {
+        if (tid < TC) {
+            const int c = tid, L = p.L;
+            const LevelP<R>& lo = p.lv[l - 1];
+            const int m = lo.m;
+            const int kend = (l == L - 1) ? l : L - 1;
+            bool all_small = true;
+            for (int i = 0; i < m; i++) {
+                R mu = (R)0;
+                for (int k = l; k <= kend; k++) mu += p.lv[k].bias_mu[gi(i, c)];
+                lo.lik_bias[gi(i, c)] = mu;
+            }
+            // covariance sum; written into lik_prec as workspace only if it will be inverted
+            for (int e = 0; e < m * m && all_small; e++) {
+                R s = (R)0;
+                for (int k = l; k <= kend; k++) s += p.lv[k].bias_sigma[gi(e, c)];
+                if (!(s < (R)1e-9)) all_small = false;
+            }
+            if (!all_small) {
+                R* W = lo.lik_prec;
+                for (int i = 0; i < m; i++)
+                    for (int j = 0; j <= i; j++) {
+                        R s = (R)0;
+                        for (int k = l; k <= kend; k++) s += p.lv[k].bias_sigma[gi(i * m + j, c)];
+                        W[gi(i * m + j, c)] = lo.cov[i * m + j] + s;
+                    }
+                // Cholesky W = Lc Lc^T (lower, in place)
+                for (int j = 0; j < m; j++) {
+                    R djj = W[gi(j * m + j, c)];
+                    for (int k = 0; k < j; k++) { R t = W[gi(j * m + k, c)]; djj -= t * t; }
+                    djj = tsqrt(djj);
+                    W[gi(j * m + j, c)] = djj;
+                    R inv = (R)1 / djj;
+                    for (int i = j + 1; i < m; i++) {
+                        R s = W[gi(i * m + j, c)];
+                        for (int k = 0; k < j; k++) s -= W[gi(i * m + k, c)] * W[gi(j * m + k, c)];
+                        W[gi(i * m + j, c)] = s * inv;
+                    }
+                }
+                // invert Lc in place (lower triangular)
+                for (int j = 0; j < m; j++) {
+                    R inv = (R)1 / W[gi(j * m + j, c)];
+                    W[gi(j * m + j, c)] = inv;
+                    for (int i = j + 1; i < m; i++) {
+                        R s = (R)0;
+                        for (int k = j; k < i; k++) s -= W[gi(i * m + k, c)] * W[gi(k * m + j, c)];
+                        W[gi(i * m + j, c)] = s / W[gi(i * m + i, c)];
+                    }
+                }
+                // P = Li^T Li : P[i][j] = sum_{k>=max(i,j)} Li[k][i] Li[k][j]; upper part first
+                // (uses only the strictly-lower + diagonal entries, writes the strict upper)
+                for (int i = 0; i < m; i++)
+                    for (int j = i + 1; j < m; j++) {
+                        R s = (R)0;
+                        for (int k = j; k < m; k++) s = fma(W[gi(k * m + i, c)], W[gi(k * m + j, c)], s);
+                        W[gi(i * m + j, c)] = s;
+                    }
+                // diagonal, then mirror the upper part into the lower
+                for (int i = 0; i < m; i++) {
+                    R s = (R)0;
+                    for (int k = i; k < m; k++) { R t = (k == i) ? W[gi(i * m + i, c)] : W[gi(k * m + i, c)]; s = fma(t, t, s); }
+                    W[gi(i * m + i, c)] = s;
+                    for (int k = i + 1; k < m; k++) W[gi(k * m + i, c)] = W[gi(i * m + k, c)];
+                }
+            }
+            // re-score level l-1's current link (posterior.py:112-134)
+            R nl = loglike_from_F(l - 1, lo.F, c);
+            lo.like[chain0 + c] = nl;
+            const int sid = lo.sid[chain0 + c];
+            for (int a = l; a < L; a++)
+                if (p.lv[a].sid[chain0 + c] == sid) lo.sv_like[a][chain0 + c] = nl;
+        }
+        __syncthreads();
+    }
+
+    __device__ void aem_update(int l, long long tcount) {
+        // bias.update(model_diff)  (utils.py:113-124), t = tcount (starts at 1)
+        if (tid < TC) {
+            const int c = tid;
+            const LevelP<R>& v = p.lv[l];
+            const int m = v.m;
+            if (s_acc[c]) {
+                for (int j = 0; j < m; j++)
+                    v.model_diff[gi(j, c)] = v.F[gi(j, c)] - p.lv[l - 1].F[gi(j, c)];
+            }
+            const R t = (R)tcount;
+            const R f1 = (t - (R)1) / t, f2 = (R)1 / t, g1 = (R)1 / (t + (R)1);
+            for (int i = 0; i < m; i++) {
+                R xi = v.model_diff[gi(i, c)];
+                R mpi = v.bias_mu[gi(i, c)];
+                R mni = g1 * (t * mpi + xi);
+                for (int j = 0; j < m; j++) {
+                    R xj = v.model_diff[gi(j, c)];
+                    R mpj = v.bias_mu[gi(j, c)];
+                    R mnj = g1 * (t * mpj + xj);
+                    size_t e = gi(i * m + j, c);
+                    v.bias_sigma[e] = f1 * v.bias_sigma[e] + f2 * (t * mpi * mpj - (t + (R)1) * mni * mnj + xi * xj);
+                }
+            }
+            for (int i = 0; i < m; i++)
+                v.bias_mu[gi(i, c)] = g1 * (t * v.bias_mu[gi(i, c)] + v.model_diff[gi(i, c)]);
+        }
+        __syncthreads();
+    }
+
+    // ---- history ------------------------------------------------------------------------------
+    __device__ void record(int l) {
+        const LevelP<R>& v = p.lv[l];
+        const long long r = rec[l];
+        if (r < v.hist_cap) {
+            const int d = p.d;
+            if (v.store & TDA_STORE_THETA)
+                for (int e = tid; e < d * TC; e += NT) {
+                    int k = e / TC, c = e - k * TC;
+                    v.h_theta[((size_t)r * d + k) * p.Cs + chain0 + c] = v.theta[gi(k, c)];
+                }
+            if ((v.store & TDA_STORE_OUTPUT) && v.need_F)
+                for (int e = tid; e < v.m * TC; e += NT) {
+                    int k = e / TC, c = e - k * TC;
+                    v.h_F[((size_t)r * v.m + k) * p.Cs + chain0 + c] = v.F[gi(k, c)];
+                }
+            if (tid < TC) {
+                size_t o = (size_t)r * p.Cs + chain0 + tid;
+                if (v.store & TDA_STORE_STATS) { v.h_prior[o] = v.prior[chain0 + tid]; v.h_like[o] = v.like[chain0 + tid]; }
+                if (v.store & TDA_STORE_ACCEPT) v.h_acc[o] = (uint8_t)s_acc[tid];
+            }
+        }
+        if (l == p.L - 1) {
+            const int d = p.d;
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                R x = v.theta[gi(k, c)];
+                p.sum1[gi(k, c)] += x;
+                p.sum2[gi(k, c)] += x * x;
+            }
+        }
+        rec[l] = r + 1;
+    }
+
+    // append one entry to the level-0 `accepted` window (thread per chain, tid < TC)
+    __device__ __forceinline__ void window_append(int c, int acc) {
+        if (!p.adaptive) return;
+        const int pos = (int)(wcount % p.period);
+        size_t o = (size_t)pos * p.Cs + chain0 + c;
+        int old = (wcount >= p.period) ? (int)p.win[o] : 0;
+        p.win[o] = (uint8_t)acc;
+        p.win_sum[chain0 + c] += acc - old;
+    }
+
+    // ---- proposals ---------------------------------------------------------------------------
+    __device__ void propose_gaussian() {
+        // RWMH / pCN / AM:  theta' = a*theta + b*(z @ T)
+        const int d = p.d;
+        fill_normals();
+        if (tid < TC) {
+            R s = p.scaling[chain0 + tid];
+            if (p.prop_kind == TDA_PROP_PCN) { s_ca[tid] = tsqrt((R)1 - s * s); s_cb[tid] = s; }
+            else { s_ca[tid] = (R)1; s_cb[tid] = s; }
+        }
+        __syncthreads();
+        if (p.prop_kind == TDA_PROP_AM) {
+            // per-chain factor: thread (c, half) computes half of the output columns
+            const int c = tid & (TC - 1), half = tid / TC;
+            const int j0 = half * ((d + 1) / 2), j1 = min(d, j0 + (d + 1) / 2);
+            for (int j = j0; j < j1; j++) {
+                R s = (R)0;
+                for (int k = 0; k < d; k++) s = fma(zt[k * TC + c], p.am_T[gi(k * d + j, c)], s);
+                pt[j * TC + c] = s_ca[c] * p.lv[0].theta[gi(j, c)] + s_cb[c] * s;
+            }
+        } else {
+            EpiCombine<R> e;
+            e.theta = p.lv[0].theta; e.Cs = p.Cs; e.chain0 = chain0; e.pt = pt; e.ca = s_ca; e.cb = s_cb;
+            tile_gemm<R>(zt, (const R*)nullptr, p.T, d, d, p.ldD, bs, KB, e);
+        }
+        __syncthreads();
+    }
+
+    __device__ void propose_mala() {
+        const int d = p.d;
+        fill_normals();
+        __syncthreads();
+        for (int e = tid; e < d * TC; e += NT) {
+            int k = e / TC, c = e - k * TC;
+            R s = p.scaling[chain0 + c];
+            pt[e] = p.lv[0].theta[gi(k, c)] + (R)0.5 * s * s * p.grad[gi(k, c)] + s * zt[e];
+        }
+        __syncthreads();
+    }
+
+    // gradient of the log-posterior at the tile in pt (F in lv[0].Fp) -> p.gradp   (MALA)
+    __device__ void mala_gradient(R* out) {
+        const LevelP<R>& v = p.lv[0];
+        const int d = p.d;
+        if (v.model_kind == TDA_MODEL_LINEAR) {
+            // sensitivity tile (data - F)/var -> zt[j][c], then  sens @ G  ([m] x [m][d])
+            for (int e = tid; e < v.m * TC; e += NT) {
+                int j = e / TC, c = e - j * TC;
+                R r = v.data[j] - v.Fp[gi(j, c)];
+                zt[e] = (v.lik_kind == TDA_LIK_ISO) ? r / v.lik_var : r / v.var[j];
+            }
+            __syncthreads();
+            EpiStore<R> e1; e1.out = out; e1.Cs = p.Cs; e1.chain0 = chain0;
+            tile_gemm<R>(zt, (const R*)nullptr, v.A2, v.m, d, p.ldD, bs, KB, e1);
+        } else {   // ROSENBROCK
+            if (tid < TC) {
+                const int c = tid;
+                R x = pt[c], y = pt[TC + c];
+                R sens = (v.data[0] - v.Fp[gi(0, c)]) / ((v.lik_kind == TDA_LIK_ISO) ? v.lik_var : v.var[0]);
+                R dFdx = (R)-2 * (v.sc0 - x) - (R)4 * v.sc1 * x * (y - x * x);
+                R dFdy = (R)2 * v.sc1 * (y - x * x);
+                out[gi(0, c)] = sens * dFdx;
+                out[gi(1, c)] = sens * dFdy;
+            }
+        }
+        __syncthreads();
+        EpiStoreNeg<R> e2; e2.out = out; e2.Cs = p.Cs; e2.chain0 = chain0; e2.accumulate = 1;
+        tile_gemm<R>(pt, p.prior_mean, p.Pprec, d, d, p.ldD, bs, KB, e2);
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ const R* archive_row(long long r, int c, long long nslots) const {
+        long long g, slot;
+        if (p.prop_kind == TDA_PROP_DREAM) { g = r / nslots; slot = r - g * nslots; }
+        else { g = p.chain_offset + chain0 + c; slot = r; }
+        return p.archive + ((size_t)slot * p.Cg + g) * p.d;
+    }
+
+    __device__ void propose_dream() {
+        // proposal.py:811-852; integer draws derive from uniforms as documented in DESIGN.md
+        const int d = p.d;
+        if (tid < TC) {
+            const int c = tid, delta = p.dream_delta;
+            const long long nslots = (p.prop_kind == TDA_PROP_DREAM) ? p.dream_slots : slots;
+            const long long M = (p.prop_kind == TDA_PROP_DREAM) ? nslots * p.Cg : nslots;
+            long long uc = p.ucur[chain0 + c];
+            long long r1[MAX_DELTA], r2[MAX_DELTA];
+            for (int i = 0; i < delta; i++) {
+                R u1 = uniform_at(c, uc++), u2 = uniform_at(c, uc++);
+                long long a = (long long)tfloor(u1 * (R)M); if (a > M - 1) a = M - 1;
+                long long b = (long long)tfloor(u2 * (R)(M - 1)); if (b > M - 2) b = M - 2;
+                if (b >= a) b++;
+                r1[i] = a; r2[i] = b;
+            }
+            R ucr = uniform_at(c, uc++);
+            int mCR = 0;
+            {
+                double cs = 0.0;
+                for (int i = 0; i < p.dream_nCR; i++) { cs += 1.0 / p.dream_nCR; if (cs <= (double)ucr) mCR++; }
+                if (mCR > p.dream_nCR - 1) mCR = p.dream_nCR - 1;
+            }
+            const R CR = (R)(mCR + 1) / (R)p.dream_nCR;
+            unsigned long long mask = 0ull;
+            int card = 0;
+            for (int k = 0; k < d; k++) if (uniform_at(c, uc + k) < CR) { mask |= 1ull << k; card++; }
+            uc += d;
+            if (card == 0) {
+                int k = (int)tfloor(uniform_at(c, uc++) * (R)d); if (k > d - 1) k = d - 1;
+                mask = 1ull << k; card = 1;
+            }
+            const R gam = p.scaling[chain0 + c] * (R)2.38 / tsqrt((R)(2 * delta * card));
+            const long long z0 = t_base * d;
+            for (int k = 0; k < d; k++) {
+                R e = -p.dream_b + (p.dream_b + p.dream_b) * uniform_at(c, uc + k);
+                R eps = p.dream_b_star * normal_at(c, z0 + k);
+                R dz = (R)0;
+                R za = (R)0, zb = (R)0;
+                for (int i = 0; i < delta; i++) { za += archive_row(r1[i], c, nslots)[k]; zb += archive_row(r2[i], c, nslots)[k]; }
+                dz = za - zb;
+                R th = p.lv[0].theta[gi(k, c)];
+                pt[k * TC + c] = ((mask >> k) & 1ull) ? th + (((R)1 + e) * gam * dz + eps) : th;
+            }
+            uc += d;
+            p.ucur[chain0 + c] = uc;
+        }
+        __syncthreads();
+    }
+
+    // ---- base level step -----------------------------------------------------------------------
+    __device__ void base_step() {
+        const int d = p.d;
+        const LevelP<R>& v = p.lv[0];
+        if (p.prop_kind == TDA_PROP_MALA) propose_mala();
+        else if (p.prop_kind >= TDA_PROP_DREAMZ) propose_dream();
+        else propose_gaussian();
+        eval_level(0);
+        if (p.prop_kind == TDA_PROP_MALA) mala_gradient(p.gradp);
+        if (tid < TC) {
+            const int c = tid, g = chain0 + c;
+            R pr = s_prior[c], lk = s_like[c];
+            R pr0 = v.prior[g], lk0 = v.like[g];
+            R x;
+            if (p.prop_kind == TDA_PROP_PCN) x = lk - lk0;
+            else x = (pr + lk) - (pr0 + lk0);
+            if (p.prop_kind == TDA_PROP_MALA) {
+                R s = p.scaling[g];
+                R qxy = (R)0, qyx = (R)0;
+                for (int k = 0; k < d; k++) {
+                    R th = v.theta[gi(k, c)], tp = pt[k * TC + c];
+                    R a = th - tp - (R)0.5 * s * s * p.gradp[gi(k, c)];
+                    R b = tp - th - (R)0.5 * s * s * p.grad[gi(k, c)];
+                    qxy = fma(a, a, qxy);
+                    qyx = fma(b, b, qyx);
+                }
+                const R f = (R)-0.5 / (s * s);
+                x = x + f * qxy - f * qyx;
+            }
+            R alpha = tisnan(pr + lk) ? (R)0 : texp(x);
+            long long uc = p.ucur[g];
+            R u = uniform_at(c, uc);
+            p.ucur[g] = uc + 1;
+            int acc = (u < alpha) ? 1 : 0;
+            s_acc[c] = acc;
+            if (acc) {
+                v.prior[g] = pr; v.like[g] = lk;
+                v.sid[g] = (int)(t_base + 1);
+                v.n_acc[g] += 1;
+                v.acc_sub[g] += 1;
+            }
+            window_append(c, acc);
+        }
+        __syncthreads();
+        // accepted chains: proposal -> current state
+        for (int e = tid; e < d * TC; e += NT) {
+            int c = e % TC;
+            if (s_acc[c]) { int k = e / TC; v.theta[gi(k, c)] = pt[e]; }
+        }
+        if (v.need_F)
+            for (int e = tid; e < v.m * TC; e += NT) {
+                int c = e % TC;
+                if (s_acc[c]) { int k = e / TC; v.F[gi(k, c)] = v.Fp[gi(k, c)]; }
+            }
+        if (p.prop_kind == TDA_PROP_MALA)
+            for (int e = tid; e < d * TC; e += NT) {
+                int c = e % TC;
+                if (s_acc[c]) { int k = e / TC; p.grad[gi(k, c)] = p.gradp[gi(k, c)]; }
+            }
+        __syncthreads();
+        wcount += 1;
+        t_base += 1;
+        record(0);
+        adapt();
+        __syncthreads();
+    }
+
+    // proposal.adapt(): global scaling, AM moments / refactor, DREAM archive append
+    __device__ void adapt() {
+        const int d = p.d;
+        const long long t = t_base;     // already incremented: proposal.t after this call
+        if (p.adaptive && (t % p.period) == 0 && tid < TC) {
+            const int g = chain0 + tid;
+            const long long k = t / p.period - 1;
+            R rate = (R)p.win_sum[g] / (R)p.period;
+            R s = p.scaling[g];
+            p.scaling[g] = texp(tlog(s) + tpow(p.gamma, (R)(-(double)k)) * (rate - p.alpha_star));
+        }
+        if (p.prop_kind == TDA_PROP_AM) {
+            // RecursiveSampleMoments.update(theta_cur), recursor.t = t (starts at 1)
+            const R tt = (R)t;
+            const R f1 = (tt - (R)1) / tt, f2 = p.am_sd / tt;
+            for (int e = tid; e < d * d * TC; e += NT) {
+                int c = e % TC, ij = e / TC, i = ij / d, j = ij - i * d;
+                R xi = p.lv[0].theta[gi(i, c)], xj = p.lv[0].theta[gi(j, c)];
+                R mpi = p.am_mu[gi(i, c)], mpj = p.am_mu[gi(j, c)];
+                R mni = ((R)1 / (tt + (R)1)) * (tt * mpi + xi), mnj = ((R)1 / (tt + (R)1)) * (tt * mpj + xj);
+                size_t o = gi(ij, c);
+                p.am_sigma[o] = f1 * p.am_sigma[o] + f2 * (tt * mpi * mpj - (tt + (R)1) * mni * mnj + xi * xj + ((i == j) ? p.am_eps : (R)0));
+            }
+            __syncthreads();
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                p.am_mu[gi(k, c)] = ((R)1 / (tt + (R)1)) * (tt * p.am_mu[gi(k, c)] + p.lv[0].theta[gi(k, c)]);
+            }
+            if (p.am_device_refactor && t >= p.am_t0 && (t % p.period) == 0) {
+                __syncthreads();
+                if (tid < TC) {   // T = chol(sigma)^T so that z @ T = L z
+                    const int c = tid;
+                    R* T = p.am_T;
+                    for (int j = 0; j < d; j++) {
+                        R djj = p.am_sigma[gi(j * d + j, c)];
+                        for (int k = 0; k < j; k++) { R t2 = T[gi(k * d + j, c)]; djj -= t2 * t2; }
+                        djj = tsqrt(djj);
+                        T[gi(j * d + j, c)] = djj;
+                        for (int i = j + 1; i < d; i++) {
+                            R s = p.am_sigma[gi(i * d + j, c)];
+                            for (int k = 0; k < j; k++) s -= T[gi(k * d + i, c)] * T[gi(k * d + j, c)];
+                            T[gi(j * d + i, c)] = s / djj;     // L[i][j] stored at T[j][i]
+                            T[gi(i * d + j, c)] = (R)0;
+                        }
+                    }
+                }
+            }
+        }
+        if (p.prop_kind >= TDA_PROP_DREAMZ) {
+            // archive append of the current state (proposal.py:794 / :1652)
+            if (slots < p.dream_cap)
+                for (int e = tid; e < d * TC; e += NT) {
+                    int c = e / d, k = e - c * d;
+                    if (chain0 + c < p.C)
+                        p.archive[((size_t)slots * p.Cg + p.chain_offset + chain0 + c) * d + k] = p.lv[0].theta[gi(k, c)];
+                }
+            slots += 1;
+        }
+    }
+
+    // ---- alignment of the lower levels after a step of level l --------------------------------
+    __device__ void align(int l) {
+        const int d = p.d;
+        for (int j = l - 1; j >= 0; j--) {
+            const LevelP<R>& lo = p.lv[j];
+            if (tid < TC) {
+                const int c = tid, g = chain0 + c;
+                if (s_acc[c]) {
+                    lo.sv_prior[l][g] = lo.prior[g];
+                    lo.sv_like[l][g] = lo.like[g];
+                } else {
+                    lo.prior[g] = lo.sv_prior[l][g];
+                    lo.like[g] = lo.sv_like[l][g];
+                    lo.sid[g] = p.lv[l].sid[g];
+                    for (int a = j + 1; a < l; a++) { lo.sv_prior[a][g] = lo.sv_prior[l][g]; lo.sv_like[a][g] = lo.sv_like[l][g]; }
+                }
+                lo.acc_sub[g] = 0;
+                if (j == 0) window_append(c, s_acc[c]);
+            }
+            for (int e = tid; e < d * TC; e += NT) {
+                int c = e % TC;
+                if (!s_acc[c]) { int k = e / TC; lo.theta[gi(k, c)] = p.lv[l].theta[gi(k, c)]; }
+            }
+            if (lo.need_F)
+                for (int e = tid; e < lo.m * TC; e += NT) {
+                    int c = e % TC, k = e / TC;
+                    if (s_acc[c]) lo.sv_F[l][gi(k, c)] = lo.F[gi(k, c)];
+                    else {
+                        R f = lo.sv_F[l][gi(k, c)];
+                        lo.F[gi(k, c)] = f;
+                        for (int a = j + 1; a < l; a++) lo.sv_F[a][gi(k, c)] = f;
+                    }
+                }
+        }
+        wcount += 1;
+        __syncthreads();
+    }
+
+    // ---- step of level l >= 1 --------------------------------------------------------------------
+    __device__ void upper_step(int l) {
+        const int d = p.d;
+        const LevelP<R>& v = p.lv[l];
+        const LevelP<R>& lo = p.lv[l - 1];
+        for (int e = tid; e < d * TC; e += NT) {
+            int k = e / TC, c = e - k * TC;
+            pt[e] = lo.theta[gi(k, c)];
+        }
+        __syncthreads();
+        eval_level(l);
+        if (tid < TC) {
+            const int c = tid, g = chain0 + c;
+            int acc = 0;
+            if (lo.acc_sub[g] > 0) {
+                R pr = s_prior[c], lk = s_like[c];
+                R x = (pr + lk) - (v.prior[g] + v.like[g]) + (lo.sv_prior[l][g] + lo.sv_like[l][g]) - (lo.prior[g] + lo.like[g]);
+                R alpha = texp(x);
+                long long uc = p.ucur[g];
+                R u = uniform_at(c, uc);
+                p.ucur[g] = uc + 1;
+                acc = (u < alpha) ? 1 : 0;
+                if (acc) {
+                    v.prior[g] = pr; v.like[g] = lk;
+                    v.sid[g] = lo.sid[g];
+                    v.n_acc[g] += 1;
+                    v.acc_sub[g] += 1;
+                }
+            }
+            s_acc[c] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < d * TC; e += NT) {
+            int c = e % TC;
+            if (s_acc[c]) { int k = e / TC; v.theta[gi(k, c)] = pt[e]; }
+        }
+        if (v.need_F)
+            for (int e = tid; e < v.m * TC; e += NT) {
+                int c = e % TC;
+                if (s_acc[c]) { int k = e / TC; v.F[gi(k, c)] = v.Fp[gi(k, c)]; }
+            }
+        __syncthreads();
+        record(l);
+        align(l);
+        if (p.aem) {
+            lvl_steps[l] += 1;
+            aem_update(l, lvl_steps[l]);
+            push_bias(l);
+        }
+    }
+
+    // ---- initial links, AEM set-up --------------------------------------------------------------
+    __device__ void init() {
+        const int d = p.d, L = p.L;
+        for (int l = 0; l < L; l++) {
+            const LevelP<R>& v = p.lv[l];
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                pt[e] = v.theta[gi(k, c)];
+            }
+            if (v.lik_kind == TDA_LIK_ADAPTIVE)    // per-chain precision starts as inv(cov)
+                for (int e = tid; e < v.m * v.m * TC; e += NT) {
+                    int c = e % TC, ij = e / TC;
+                    v.lik_prec[gi(ij, c)] = v.prec[ij];
+                }
+            __syncthreads();
+            eval_level(l);
+            if (tid < TC) {
+                const int g = chain0 + tid;
+                v.prior[g] = s_prior[tid]; v.like[g] = s_like[tid]; v.sid[g] = 0;
+                v.n_acc[g] = 0; v.acc_sub[g] = 0;
+                for (int a = l + 1; a < L; a++) { v.sv_prior[a][g] = s_prior[tid]; v.sv_like[a][g] = s_like[tid]; }
+                s_acc[tid] = 1;
+            }
+            if (v.need_F)
+                for (int e = tid; e < v.m * TC; e += NT) {
+                    int c = e % TC, k = e / TC;
+                    R f = v.Fp[gi(k, c)];
+                    v.F[gi(k, c)] = f;
+                    for (int a = l + 1; a < L; a++) v.sv_F[a][gi(k, c)] = f;
+                }
+            if (l == 0 && p.prop_kind == TDA_PROP_MALA) { __syncthreads(); mala_gradient(p.grad); }
+            __syncthreads();
+        }
+        if (p.prop_kind == TDA_PROP_AM)
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                p.am_mu[gi(k, c)] = p.lv[0].theta[gi(k, c)];
+            }
+        if (p.aem && L > 1) {
+            for (int l = 1; l < L; l++) {
+                const LevelP<R>& v = p.lv[l];
+                for (int e = tid; e < v.m * TC; e += NT) {
+                    int c = e % TC, k = e / TC;
+                    R df = v.F[gi(k, c)] - p.lv[l - 1].F[gi(k, c)];
+                    v.model_diff[gi(k, c)] = df;
+                    v.bias_mu[gi(k, c)] = df;
+                }
+            }
+            __syncthreads();
+            for (int l = L - 1; l >= 1; l--) push_bias(l);
+        }
+        __syncthreads();
+        record(L - 1);
+    }
+
+    __device__ void run() {
+        const int L = p.L;
+        int cnt[MAXL];
+        for (int l = 0; l < MAXL; l++) cnt[l] = 0;
+        long long it = 0;
+        while (it < p.iterations) {
+            base_step();
+            if (L == 1) { it++; continue; }
+            cnt[0]++;
+            int l = 0;
+            while (l < L - 1 && cnt[l] == p.J[l]) {
+                cnt[l] = 0;
+                upper_step(l + 1);
+                l++;
+                if (l < L - 1) cnt[l]++;
+                else it++;
+            }
+        }
+    }
+};
+
+template <typename R>
+__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 2 : 1))
+chain_kernel(const __grid_constant__ Params<R> p, int kt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        Tile<R> T(p, smem_raw, kt);
+        T.chain0 = tile * TC;
+        T.t_base = p.t_base;
+        T.wcount = p.wcount;
+        T.slots = p.dream_slots;
+        for (int l = 0; l < MAXL; l++) { T.rec[l] = p.rec[l]; T.lvl_steps[l] = p.lvl_steps[l]; }
+        if (p.mode == MODE_INIT) T.init();
+        else T.run();
+        __syncthreads();
+    }
+}
+
+// exports the Philox streams (what TDA_RNG_PHILOX consumes) for the CPU oracle
+template <typename R>
+__global__ void fill_streams_kernel(unsigned long long seed, long long chain_offset, int C,
+                                    double* z, long long nz, double* u, long long nu) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total_z = (long long)C * nz, total_u = (long long)C * nu;
+    if (i < total_z) {
+        long long c = i / nz, k = i - c * nz;
+        z[i] = (double)philox_normal<R>(seed, chain_offset + c, k);
+    }
+    if (i < total_u) {
+        long long c = i / nu, k = i - c * nu;
+        u[i] = (double)philox_uniform<R>(seed, chain_offset + c, k);
+    }
+}
+
+}  // namespace tda

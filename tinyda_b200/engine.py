@@ -1,0 +1,266 @@
+"""Python handle on one device engine (one per GPU / per process).
+
+Turns a lowered problem spec (``lowering.lower_problem``) into the POD ``tda_config`` and
+constant uploads of the C ABI, and exposes run / fetch.  All arithmetic happens in the CUDA
+library behind ``_lib``; importing this module fails loudly if that library is missing.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import lib, check
+from .proposal import PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM
+from .distributions import LIK_ISO, LIK_DIAG, LIK_DENSE, LIK_ADAPTIVE
+from .models import MODEL_LINEAR, MODEL_POISSON1D
+
+STORE_FULL = L.TDA_STORE_THETA | L.TDA_STORE_STATS | L.TDA_STORE_OUTPUT | L.TDA_STORE_ACCEPT
+STORE_STATS = L.TDA_STORE_THETA | L.TDA_STORE_STATS | L.TDA_STORE_ACCEPT
+STORE_NONE = 0
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def steps_per_iteration(spec):
+    """Local steps each level takes per finest-level iteration."""
+    Ln = spec["n_levels"]
+    steps = [1] * Ln
+    for l in range(Ln - 2, -1, -1):
+        steps[l] = steps[l + 1] * int(spec["J"][l])
+    return steps
+
+
+class Engine:
+    def __init__(self, spec, n_chains, dtype="float64", rng="philox", seed=0, store=None,
+                 capacity_iterations=0, streams=None, device=0, chain_offset=0, n_chains_global=None,
+                 archive0=None, am_device_refactor=True, stream=None):
+        self.spec = spec
+        self.C = int(n_chains)
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype("float32"), np.dtype("float64")):
+            raise ValueError("dtype must be float32 or float64")
+        self.Ln = Ln = int(spec["n_levels"])
+        self.d = d = int(spec["d"])
+        self.device = int(device)
+        self.stream = stream
+        prop = spec["proposal"]
+        kind = int(prop["kind"])
+        self.steps = steps_per_iteration(spec)
+        if store is None:
+            store = [STORE_STATS] * Ln
+        elif isinstance(store, int):
+            store = [store] * Ln
+        self.store = list(store)
+
+        cfg = L.Config()
+        cfg.abi_version = L.TDA_ABI_VERSION
+        cfg.dtype = L.TDA_F64 if self.dtype == np.float64 else L.TDA_F32
+        cfg.n_levels = Ln
+        cfg.d = d
+        for i, j in enumerate(spec["J"]):
+            cfg.subchain[i] = int(j)
+        cfg.aem = int(spec.get("aem", 0))
+        cfg.rng_mode = L.TDA_RNG_INJECTED if rng == "injected" else L.TDA_RNG_PHILOX
+        cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        cfg.n_chains = self.C
+        cfg.chain_offset = int(chain_offset)
+        cfg.n_chains_global = int(n_chains_global if n_chains_global is not None else self.C)
+        self.Cg = int(cfg.n_chains_global)
+        cfg.prop_kind = kind
+        cfg.adaptive = int(bool(prop.get("adaptive", False)))
+        cfg.period = int(prop.get("period", 100))
+        cfg.scaling = float(prop.get("scaling", 1.0))
+        cfg.gamma = float(prop.get("gamma", 1.01))
+        cfg.alpha_star = float(prop.get("alpha_star", 0.24))
+        if kind == PROP_AM:
+            cfg.am_sd = float(prop["am_sd"])
+            cfg.am_eps = float(prop["am_eps"])
+            cfg.am_t0 = int(prop["am_t0"])
+            cfg.am_device_refactor = int(bool(am_device_refactor))
+        if kind in (PROP_DREAMZ, PROP_DREAM):
+            cfg.dream_M0 = int(prop["M0"])
+            cfg.dream_delta = int(prop["delta"])
+            cfg.dream_nCR = int(prop["nCR"])
+            cfg.dream_b = float(prop["b"])
+            cfg.dream_b_star = float(prop["b_star"])
+            cfg.dream_capacity = int(prop["M0"]) + int(capacity_iterations) + 1
+        if rng == "injected":
+            z, u = streams
+            z = np.ascontiguousarray(z, dtype=np.float64)
+            u = np.ascontiguousarray(u, dtype=np.float64)
+            cfg.stream_z_len = z.shape[1]
+            cfg.stream_u_len = u.shape[1]
+        cfg.prior_logconst = float(spec["prior"]["logconst"])
+        self.capacity = []
+        for l, lv in enumerate(spec["levels"]):
+            lc = cfg.level[l]
+            lc.model_kind = int(lv["model"]["kind"])
+            lc.m = int(lv["model"]["m"])
+            lc.n_grid = int(lv["model"]["n_grid"])
+            lc.lik_kind = int(lv["lik"]["kind"])
+            lc.lik_var = float(lv["lik"]["var"]) if lc.lik_kind == LIK_ISO else 0.0
+            for i in range(4):
+                lc.model_scalars[i] = float(np.asarray(lv["model"]["scalars"])[i])
+            lc.store = int(self.store[l])
+            cap = int(capacity_iterations) * self.steps[l] + (1 if l == Ln - 1 else 0)
+            lc.hist_capacity = cap if lc.store else 0
+            self.capacity.append(int(lc.hist_capacity))
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        check(lib.tda_engine_create(C.byref(cfg), self.device, C.byref(self._h)))
+
+        # constants
+        pr = spec["prior"]
+        self._up(L.TDA_UP_PRIOR_MEAN, 0, pr["mean"])
+        self._up(L.TDA_UP_PRIOR_LP, 0, pr["LP"])
+        if kind == PROP_MALA:
+            self._up(L.TDA_UP_PRIOR_PREC, 0, np.linalg.inv(pr["cov"]))     # utils.py:272-278
+        if "T" in prop:
+            self._up(L.TDA_UP_PROP_T, 0, prop["T"])
+        for l, lv in enumerate(spec["levels"]):
+            mk = int(lv["model"]["kind"])
+            if mk in (MODEL_LINEAR, MODEL_POISSON1D):
+                self._up(L.TDA_UP_MODEL_A, l, lv["model"]["A"])
+            if mk == MODEL_LINEAR:
+                self._up(L.TDA_UP_MODEL_B, l, lv["model"]["b"])
+            lk = int(lv["lik"]["kind"])
+            self._up(L.TDA_UP_LIK_DATA, l, lv["lik"]["data"])
+            if lk == LIK_DIAG:
+                self._up(L.TDA_UP_LIK_VAR, l, lv["lik"]["var"])
+            if lk in (LIK_DENSE, LIK_ADAPTIVE):
+                self._up(L.TDA_UP_LIK_PREC, l, np.linalg.inv(lv["lik"]["cov"]))   # distributions.py:280
+            if lk == LIK_ADAPTIVE:
+                self._up(L.TDA_UP_LIK_COV, l, lv["lik"]["cov"])
+        if rng == "injected":
+            self._up(L.TDA_UP_STREAM_Z, 0, z)
+            self._up(L.TDA_UP_STREAM_U, 0, u)
+        if kind in (PROP_DREAMZ, PROP_DREAM):
+            if archive0 is None:
+                raise ValueError("DREAM(Z) needs the initial archive [n_chains_global, M0, d]")
+            self._up(L.TDA_UP_DREAM_ARCHIVE0, 0, archive0)
+        self.iterations_done = 0
+
+    # ---- plumbing --------------------------------------------------------------------------
+    def _up(self, what, level, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        check(lib.tda_upload(self._h, what, level, _dptr(a), a.size))
+
+    def _stream_ptr(self):
+        return C.c_void_p(self.stream) if self.stream else C.c_void_p(0)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.tda_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- run ---------------------------------------------------------------------------------
+    def init(self, theta0):
+        theta0 = np.ascontiguousarray(np.atleast_2d(theta0), dtype=np.float64)
+        if theta0.shape != (self.C, self.d):
+            raise ValueError("initial parameters must have shape (n_chains, d)")
+        self._up(L.TDA_UP_INIT_THETA, 0, theta0)
+        check(lib.tda_engine_init(self._h, self._stream_ptr()))
+
+    def run(self, iterations):
+        check(lib.tda_engine_run(self._h, int(iterations), self._stream_ptr()))
+        self.iterations_done += int(iterations)
+
+    def sync(self):
+        check(lib.tda_engine_sync(self._h, self._stream_ptr()))
+
+    def select_kernel(self, which):
+        check(lib.tda_select_kernel(self._h, {"auto": 0, "generic": 1, "tc": 2}[which]))
+
+    def history_reset(self):
+        check(lib.tda_history_reset(self._h))
+
+    def n_records(self):
+        out = np.zeros(self.Ln, dtype=np.int64)
+        check(lib.tda_get(self._h, L.TDA_G_NRECORDS, 0, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    # ---- fetch ---------------------------------------------------------------------------------
+    def fetch(self, level, field, rec0=0, nrec=None, out=None):
+        """History of one level in the device layout: theta [nrec, d, C], prior/like [nrec, C],
+        output [nrec, m, C], accept [nrec, C] (uint8)."""
+        if nrec is None:
+            nrec = int(self.n_records()[level]) - rec0
+        m = int(self.spec["levels"][level]["model"]["m"])
+        fid, shape, dt = {
+            "theta": (L.TDA_F_THETA, (nrec, self.d, self.C), self.dtype),
+            "prior": (L.TDA_F_PRIOR, (nrec, self.C), self.dtype),
+            "like": (L.TDA_F_LIKE, (nrec, self.C), self.dtype),
+            "output": (L.TDA_F_OUTPUT, (nrec, m, self.C), self.dtype),
+            "accept": (L.TDA_F_ACCEPT, (nrec, self.C), np.dtype(np.uint8)),
+        }[field]
+        if out is None:
+            out = np.empty(shape, dtype=dt)
+        nb = C.c_size_t(0)
+        check(lib.tda_fetch(self._h, level, fid, int(rec0), int(nrec), out.ctypes.data_as(C.c_void_p),
+                            out.nbytes, C.byref(nb), self._stream_ptr()))
+        self.sync()
+        return out
+
+    def get(self, what, level=0):
+        Cn, d = self.C, self.d
+        if what == "scaling":
+            out = np.zeros(Cn)
+            code = L.TDA_G_SCALING
+        elif what == "accept_counts":
+            out = np.zeros((self.Ln, Cn), dtype=np.int64)
+            code = L.TDA_G_ACCEPT_COUNTS
+        elif what == "cursors":
+            out = np.zeros((2, Cn), dtype=np.int64)
+            code = L.TDA_G_CURSORS
+        elif what == "am_sigma":
+            out = np.zeros((Cn, d, d))
+            code = L.TDA_G_AM_SIGMA
+        elif what == "am_mu":
+            out = np.zeros((Cn, d))
+            code = L.TDA_G_AM_MU
+        elif what == "theta":
+            out = np.zeros((Cn, d))
+            code = L.TDA_G_THETA
+        elif what == "moments":
+            out = np.zeros((2, d, Cn))
+            code = L.TDA_G_MOMENTS
+        else:
+            raise KeyError(what)
+        check(lib.tda_get(self._h, code, level, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def set_scaling(self, s):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        check(lib.tda_set(self._h, L.TDA_G_SCALING, 0, s.ctypes.data_as(C.c_void_p), s.nbytes))
+
+    def upload_am_factors(self, T):
+        self._up(L.TDA_UP_AM_FACTORS, 0, T)
+
+    def device_buffer(self, which, level=0):
+        ptr, nb = C.c_void_p(), C.c_size_t()
+        code = {"dream_archive": L.TDA_BUF_DREAM_ARCHIVE, "hist_theta": L.TDA_BUF_HIST_THETA}[which]
+        check(lib.tda_device_buffer(self._h, code, level, C.byref(ptr), C.byref(nb)))
+        return ptr.value, nb.value
+
+    def dream_slots(self):
+        s = C.c_int64()
+        check(lib.tda_dream_slots(self._h, C.byref(s)))
+        return s.value
+
+    def fill_streams(self, nz, nu):
+        z = np.zeros((self.C, nz))
+        u = np.zeros((self.C, nu))
+        check(lib.tda_fill_streams(self._h, _dptr(z), nz, _dptr(u), nu))
+        return z, u
+
+
+def launch_count():
+    return int(lib.tda_launch_count())
