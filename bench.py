@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the batched-MCMC hot path (BASELINE.json metric: fine-level MH transitions/sec,
+all chains).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--dtype float32]
+
+Workload (config.workload): BASELINE.json configs[1] -- two-level Delayed Acceptance, pCN,
+linear-Gaussian inverse problem with 64 params / 1024 obs (coarse = 128-obs subset),
+subsampling_rate = 10, 65536 chains PER GPU (weak scaling: chains are independent, no
+data-path collective).  A "step" is one engine run of ITERS fine-level iterations for every
+chain (= ITERS*J coarse proposals + ITERS fine evaluations per chain), one kernel launch.
+
+  value     transitions/s with chain state resident in HBM (CUDA events around the run calls)
+  e2e       the same through the host-buffer path: initial states H2D from pinned memory,
+            init + run, fine-level history (theta, log-prior, log-like, accept) D2H to pinned
+  roofline  the dominant kernel against the measured tensor peak (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference: the CPU port of the reference's chain loop (oracle/),
+            one chain per process on all host cores, like the reference's Ray path does.
+"""
+import argparse
+import json
+import os
+
+# one BLAS thread per process: the CPU baseline runs one chain per process on every core
+# (must be set before numpy loads OpenBLAS)
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CHAINS_PER_GPU = 65536
+ITERS_PER_STEP = 50
+F_ALG = 458752.0       # flop per fine transition
+METRIC = "fine-level MH transitions/sec, all chains"
+UNIT = "transitions/s"
+
+
+def workload_spec():
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da()
+    spec = lower_problem(w["posteriors"], w["proposal"], w["kwargs"]["subchain_length"])
+    return w, spec
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's DAChain loop, one chain per process
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    spec, theta0, seed, iters, faithful = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import tinyda_oracle as orc
+    rng = np.random.default_rng(seed)
+    d, J = spec["d"], spec["J"][0]
+    z = rng.standard_normal(iters * J * d + 8)
+    u = rng.random(iters * (J + 1) + 8)
+    ch = orc.ChainOracle(spec, theta0, z, u, svd_per_proposal=faithful, keep_history=False)
+    t0 = time.perf_counter()
+    ch.run(iters)
+    return time.perf_counter() - t0
+
+
+def cpu_port_rate(spec, prior, iters, faithful, procs=None):
+    import multiprocessing as mp
+    procs = procs or os.cpu_count() or 1
+    rng = np.random.default_rng(123)
+    theta0 = np.atleast_2d(prior.rvs(procs, random_state=rng)).reshape(procs, -1)
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, [(spec, theta0[i], 1000 + i, iters, faithful) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    return procs * iters / wall, procs, wall
+
+
+def cpu_baseline_block(spec, prior, budget_iters_faithful=60, budget_iters_fast=600):
+    rate, procs, wall = cpu_port_rate(spec, prior, budget_iters_faithful, True)
+    rate_fast, _, wall_fast = cpu_port_rate(spec, prior, budget_iters_fast, False)
+    return {
+        "value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+        "sample": "oracle port of tinyDA DAChain.sample, %d processes x 1 chain x %d fine iterations "
+                  "(= %d transitions), SVD of the 64x64 proposal covariance on every draw as "
+                  "np.random.multivariate_normal does inside the reference; %.1f s wall"
+                  % (procs, budget_iters_faithful, procs * budget_iters_faithful, wall),
+        "port_precomputed_factor": {
+            "value": rate_fast, "sample": "same port with the SVD factor computed once, %d x %d iterations, %.1f s"
+                                          % (procs, budget_iters_fast, wall_fast)},
+    }
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return pk, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def run_ours(args):
+    import torch
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE, launch_count
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    w, spec = workload_spec()
+    C = args.chains
+    iters = args.iters
+    dtype = args.dtype
+    d = spec["d"]
+    rng = np.random.default_rng(1000 + rank)
+    theta0 = w["prior"].rvs(C, random_state=rng).astype(np.float64)
+
+    stream = torch.cuda.current_stream().cuda_stream
+    # device-resident arm: stats-only history at the fine level (theta, prior, like, accept)
+    eng = Engine(spec, C, dtype=dtype, rng="philox", seed=2024, store=[STORE_NONE, STORE_STATS],
+                 capacity_iterations=iters, device=local_rank, chain_offset=rank * C,
+                 n_chains_global=world * C, stream=stream)
+    if args.kernel != "auto":
+        eng.select_kernel(args.kernel)
+    eng.init(theta0)
+    eng.run(100 if not args.quick else 10)      # burn-in from the prior draws
+    eng.sync()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        eng.history_reset()
+        eng.run(iters)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                      # L2 flush between timed steps (untimed)
+        ev[k][0].record()
+        one_step()
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = launch_count() - l0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = float(sum(ms_steps))
+
+    # ---- end-to-end arm: host buffers in, host buffers out -------------------------------
+    n_rec = iters
+    np_dt = np.float32 if dtype == "float32" else np.float64
+    pin_theta0 = torch.from_numpy(theta0).pin_memory()
+    h_theta = torch.empty((n_rec, d, C), dtype=torch.float32 if dtype == "float32" else torch.float64).pin_memory()
+    h_prior = torch.empty((n_rec, C), dtype=h_theta.dtype).pin_memory()
+    h_like = torch.empty((n_rec, C), dtype=h_theta.dtype).pin_memory()
+    h_acc = torch.empty((n_rec, C), dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        eng.history_reset()
+        eng.init(pin_theta0.numpy())                     # H2D initial states + initial links
+        eng.run(iters)
+        eng.fetch(1, "theta", 1, n_rec, out=h_theta.numpy())
+        eng.fetch(1, "prior", 1, n_rec, out=h_prior.numpy())
+        eng.fetch(1, "like", 1, n_rec, out=h_like.numpy())
+        eng.fetch(1, "accept", 1, n_rec, out=h_acc.numpy())
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    clock_info = clocks.stop()
+
+    times = torch.tensor([dev_ms, e2e_wall * 1e3, t_wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, wall_ms = [float(x) for x in times.cpu()]
+    total_trans = float(world) * C * iters * args.steps
+    value = total_trans / (dev_ms * 1e-3)
+    e2e_value = float(world) * C * iters * e2e_steps / (e2e_ms * 1e-3)
+    h2d = theta0.nbytes
+    d2h = h_theta.numel() * h_theta.element_size() + 2 * h_prior.numel() * h_prior.element_size() + h_acc.numel()
+
+    if rank == 0:
+        pk, src = measured_peaks()
+        per_gpu_rate = C * iters / (np.mean(ms_steps) * 1e-3)
+        achieved = per_gpu_rate * F_ALG / 1e12
+        peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+        acc = eng.get("accept_counts")
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == "float32" else "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": w["name"], "chains_per_gpu": C, "fine_iterations_per_step": iters,
+                "transitions_per_step": world * C * iters, "rng": "philox4x32-10 in-kernel",
+                "history": "fine level theta+log-prior+log-like+accept (265 B/transition f32)",
+                "l2": "256 MiB buffer written between timed steps (L2 flush); chain state is kept "
+                      "L2/SMEM-resident by design", "kernel": eng_kernel_name(args, dtype),
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "what": "pinned initial states H2D + init + run + fine history D2H to pinned"},
+            "gpu_launches": int(launches),
+            "clocks": clock_info,
+            "roofline": {
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "note": "achieved = 458752 algorithmic flop/transition x per-GPU transitions/s "
+                        "(CUDA events, mean over timed launches); peak = bf16 dense sustained, " + src +
+                        " (MEASURED_PEAKS.json); a 3xTF32 split (fp32-grade accuracy) caps at peak/6",
+            },
+            "accept_rate": {"coarse": float(acc[0].mean() / max(1, eng.iterations_done * spec["J"][0])),
+                            "fine": float(acc[1].mean() / max(1, eng.iterations_done))},
+            "wall_ms_timed_region": wall_ms,
+        }
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline_block(spec, w["prior"],
+                                                     6 if args.quick else 60, 60 if args.quick else 600)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def eng_kernel_name(args, dtype):
+    return "%s (%s)" % (args.kernel, dtype)
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path: tinyDA is pure Python and does not
+    travel to the GPU box, so this times the oracle port of its DAChain loop (one chain per
+    process on all host cores, as tinyDA/ray.py does)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, spec = workload_spec()
+    iters = 6 if args.quick else 40
+    steps_done = []
+    t_all0 = time.perf_counter()
+    for _ in range(args.warmup):
+        cpu_port_rate(spec, w["prior"], max(2, iters // 10), True)
+    for _ in range(args.steps):
+        rate, procs, wall = cpu_port_rate(spec, w["prior"], iters, True)
+        steps_done.append((rate, procs, wall))
+        if time.perf_counter() - t_all0 > 240:
+            break
+    n = len(steps_done)
+    procs = steps_done[0][1]
+    total_wall = sum(s[2] for s in steps_done)
+    value = procs * iters * n / total_wall
+    sample = ("oracle port of tinyDA DAChain.sample (per-draw SVD like np.random.multivariate_normal), "
+              "%d processes x 1 chain x %d fine iterations per step" % (procs, iters))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": n, "warmup": args.warmup, "ms_per_step": total_wall / n * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "chains": procs, "fine_iterations_per_step": iters},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tc"])
+    ap.add_argument("--chains", type=int, default=N_CHAINS_PER_GPU)
+    ap.add_argument("--iters", type=int, default=ITERS_PER_STEP)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not args.quick:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -214,7 +214,8 @@ class ChainOracle:
                      am_sd, am_eps, am_t0, C0, M0, delta, b, b_star, nCR)
     """
 
-    def __init__(self, spec, theta0, z, u, archive0=None, am_refactor="svd"):
+    def __init__(self, spec, theta0, z, u, archive0=None, am_refactor="svd", svd_per_proposal=False,
+                 keep_history=True):
         self.spec = spec
         self.L = int(spec["n_levels"])
         self.d = int(spec["d"])
@@ -227,6 +228,11 @@ class ChainOracle:
         self.P = dict(spec["proposal"])
         self.kind = int(self.P["kind"])
         self.am_refactor = am_refactor
+        # svd_per_proposal=True re-factors the proposal covariance on every draw exactly like
+        # np.random.multivariate_normal does inside the reference (proposal.py:249, :353) -- same
+        # result, the reference's cost profile (used by the timed CPU baseline only)
+        self.svd_per_proposal = svd_per_proposal
+        self.keep_history = keep_history
         L = self.L
         self.next_sid = 1
         theta0 = np.array(theta0, dtype=np.float64)
@@ -289,6 +295,8 @@ class ChainOracle:
         return _State(theta, prior, like, F, sid)
 
     def _record(self, level, acc):
+        if not self.keep_history:
+            return
         h = self.hist[level]
         c = self.cur[level]
         h["theta"].append(c.theta.copy())
@@ -331,9 +339,11 @@ class ChainOracle:
         c = self.cur[0]
         d = self.d
         if self.kind in (PROP_RWMH, PROP_AM):                    # proposal.py:247-251
-            return c.theta + self.scaling * (self.S.normals(d) @ self.T)
+            T = svd_factor(self.P["C"]) if (self.svd_per_proposal and self.kind == PROP_RWMH) else self.T
+            return c.theta + self.scaling * (self.S.normals(d) @ T)
         if self.kind == PROP_PCN:                                # proposal.py:349-355
-            return np.sqrt(1 - self.scaling ** 2) * c.theta + self.scaling * (self.S.normals(d) @ self.T)
+            T = svd_factor(self.prior["cov"]) if self.svd_per_proposal else self.T
+            return np.sqrt(1 - self.scaling ** 2) * c.theta + self.scaling * (self.S.normals(d) @ T)
         if self.kind == PROP_MALA:                               # proposal.py:948-959
             return c.theta + 0.5 * self.scaling ** 2 * c.grad + self.scaling * self.S.normals(d)
         # DREAMZ / DREAM                                         # proposal.py:811-852

@@ -168,6 +168,7 @@ class Engine:
             raise ValueError("initial parameters must have shape (n_chains, d)")
         self._up(L.TDA_UP_INIT_THETA, 0, theta0)
         check(lib.tda_engine_init(self._h, self._stream_ptr()))
+        self.iterations_done = 0
 
     def run(self, iterations):
         check(lib.tda_engine_run(self._h, int(iterations), self._stream_ptr()))

@@ -60,6 +60,7 @@ class GaussianRandomWalk(Proposal):
     def lower(self, prior):
         out = self._common()
         out["T"] = svd_factor(self.C)
+        out["C"] = np.atleast_2d(np.asarray(self.C, dtype=np.float64))
         return out
 
 
