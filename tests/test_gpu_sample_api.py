@@ -1,0 +1,180 @@
+"""GPU tests through the public drop-in API (tinyda_b200.sample) and size-independent
+properties at BASELINE.json's full sizes."""
+import warnings
+
+import numpy as np
+import pytest
+
+import golden_io
+import problems
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(name):
+    import tinyda_b200 as tda
+    defn = problems.CASES[name]()
+    posts, prop, kw = defn["build"](tda)
+    return tda, defn, posts, prop, kw
+
+
+@pytest.mark.parametrize("name", ["mh_rwmh_linreg", "da_pcn_small", "mlda3_linear", "mlda4_aem_poisson"])
+def test_sample_result_dict_matches_reference_trajectories(name):
+    """tda.sample(...) with injected streams: same dict keys / lengths as tinyDA.sample and the
+    same Links as the reference produced (golden fixture)."""
+    tda, defn, posts, prop, kw = _build(name)
+    g = golden_io.load(name)
+    C, iters = g["theta0"].shape[0], g["iterations"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = tda.sample(posts if len(posts) > 1 else posts[0], prop, iters, n_chains=C,
+                         initial_parameters=[t for t in g["theta0"]], rng="injected",
+                         streams=(g["z"], g["u"]), **kw)
+    L = len(posts)
+    assert res["n_chains"] == C and res["iterations"] == iters + 1
+    if L == 1:
+        assert res["sampler"] == "MH"
+        keys = ["chain_%d"]
+    elif L == 2:
+        assert res["sampler"] == "DA" and res["subchain_length"] == kw["subchain_length"]
+        keys = ["chain_coarse_%d", "chain_fine_%d"]
+    else:
+        assert res["sampler"] == "MLDA" and res["levels"] == L and res["subchain_lengths"] == list(kw["subchain_length"])
+        keys = ["chain_l%d_%%d" % l for l in range(L)]
+    for l, key in enumerate(keys):
+        ref = g["ref"][l]
+        for c in range(C):
+            seq = res[key % c]
+            assert len(seq) == ref["theta"].shape[1]
+            np.testing.assert_allclose(seq.parameters, ref["theta"][c], rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(seq.likelihood, ref["like"][c], rtol=1e-9, atol=1e-8)
+            np.testing.assert_allclose(seq.model_output, ref["F"][c], rtol=1e-9, atol=1e-10)
+            link = seq[len(seq) // 2]
+            assert link.posterior == link.prior + link.likelihood
+    # reference-style post-processing on the result
+    s = tda.get_samples(res, "parameters", level={1: "fine", 2: "fine"}.get(L, L - 1), burnin=3)
+    assert s["chain_0"].shape == (iters + 1 - 3, g["spec"]["d"])
+
+
+def test_store_coarse_chain_false_returns_none_like_the_reference():
+    tda, defn, posts, prop, kw = _build("da_pcn_small")
+    res = tda.sample(posts, prop, 10, n_chains=3, store_coarse_chain=False, seed=1, **kw)
+    assert res["chain_coarse_0"] is None and len(res["chain_fine_2"]) == 11
+
+
+@pytest.mark.parametrize("name,dtype", [("da_pcn_small", "float64"), ("mh_pcn_diag", "float64"),
+                                        ("mala_rosenbrock", "float64"), ("dreamz_linear", "float64"),
+                                        ("mlda3_aem_linear", "float64")])
+def test_philox_mode_equals_oracle_fed_the_exported_streams(name, dtype):
+    """Production RNG mode: the engine's in-kernel Philox draws, exported with tda_fill_streams
+    and fed to the CPU oracle, give the engine's own trajectories -> the counter-based streams
+    are consumed exactly like the reference consumes np.random."""
+    from tinyda_b200.engine import Engine, STORE_FULL
+    from oracle import tinyda_oracle as orc
+    g = golden_io.load(name)
+    spec, theta0, iters = g["spec"], g["theta0"], g["iterations"]
+    C = theta0.shape[0]
+    eng = Engine(spec, C, dtype=dtype, rng="philox", seed=77, store=STORE_FULL, capacity_iterations=iters,
+                 archive0=g["archive0"], chain_offset=5)
+    eng.init(theta0)
+    eng.run(iters)
+    z, u = eng.fill_streams(g["z"].shape[1], g["u"].shape[1])
+    out, chains = orc.run_chains(spec, theta0, z, u, iters, g["archive0"])
+    for l in range(spec["n_levels"]):
+        acc = eng.fetch(l, "accept").T.astype(bool)
+        th = np.transpose(eng.fetch(l, "theta"), (2, 0, 1))
+        assert np.array_equal(acc, out[l]["acc"])
+        np.testing.assert_allclose(th, out[l]["theta"], rtol=1e-10, atol=1e-12)
+    cur = eng.get("cursors")
+    assert np.array_equal(cur.T, np.array([[ch.S.nz, ch.S.nu] for ch in chains]))
+    # the streams themselves look like N(0,1) / U(0,1)
+    assert abs(z.mean()) < 0.05 and abs(z.std() - 1) < 0.05 and abs(u.mean() - 0.5) < 0.02
+
+
+def test_conjugate_posterior_within_3_mcse_rwmh():
+    """cfg1 (README linear regression, adaptive RWMH): posterior mean / covariance against the
+    closed-form conjugate posterior, 4096 independent chains -> MCSE from across-chain spread."""
+    import tinyda_b200 as tda
+    from tinyda_b200.workloads import cfg1_linreg, conjugate_posterior
+    w = cfg1_linreg()
+    mu, S = conjugate_posterior(w["G"], w["y"], w["sigma2"], w["prior"])
+    C, burn, iters = 4096, 1500, 2500
+    res, eng = tda.sample(w["posteriors"][0], w["proposal"], burn + iters, n_chains=C, seed=5,
+                          store_model_output=False, return_engine=True)
+    th = np.transpose(eng.fetch(0, "theta", burn + 1, iters), (2, 0, 1))       # [C, iters, d]
+    cm = th.mean(axis=1)
+    mcse = cm.std(axis=0, ddof=1) / np.sqrt(C)
+    assert np.all(np.abs(cm.mean(axis=0) - mu) < 3 * mcse + 1e-12), (cm.mean(axis=0), mu, mcse)
+    second = (th[:, :, :, None] * th[:, :, None, :]).mean(axis=1)                # E[x x^T] per chain
+    e2 = second.mean(axis=0)
+    e2_mcse = second.std(axis=0, ddof=1) / np.sqrt(C)
+    target = S + np.outer(mu, mu)
+    assert np.all(np.abs(e2 - target) < 3 * e2_mcse + 1e-12), (e2, target, e2_mcse)
+    sc = eng.get("scaling")
+    assert np.all(sc > 0) and sc.std() > 0          # per-chain adaptive scaling really adapted
+    eng.close()
+
+
+def test_conjugate_posterior_da_pcn_fp32_full_shape():
+    """cfg2 at its real shape (64 params, 1024/128 obs, J=10), float32 production mode, 8192 chains:
+    fine-chain mean within 3 MCSE (+ float32 slack) of the closed-form posterior mean, checked
+    from the on-device running moments (no history stored)."""
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.engine import Engine, STORE_NONE
+    from tinyda_b200.workloads import cfg2_da, conjugate_posterior
+    w = cfg2_da()
+    mu, S = conjugate_posterior(w["G"], w["y"], w["sigma2"], w["prior"])
+    spec = lower_problem(w["posteriors"], w["proposal"], 10)
+    C = 8192
+    rng = np.random.default_rng(0)
+    # start in the posterior bulk so that no long burn-in is needed
+    theta0 = rng.multivariate_normal(mu, S, size=C)
+    eng = Engine(spec, C, dtype="float32", seed=3, store=STORE_NONE)
+    eng.init(theta0)
+    eng.run(150)
+    m0 = eng.get("moments")
+    n0 = 151
+    eng.run(600)
+    m1 = eng.get("moments")
+    n = 600
+    cm = ((m1[0] - m0[0]) / n).T                      # [C, d] chain means over the last 600 draws
+    mcse = cm.std(axis=0, ddof=1) / np.sqrt(C)
+    err = np.abs(cm.mean(axis=0) - mu)
+    assert np.all(err < 3 * mcse + 2e-4 * (np.abs(mu) + np.sqrt(np.diag(S)))), (err / mcse).max()
+    acc = eng.get("accept_counts")
+    rate_c, rate_f = acc[0].mean() / (750 * 10), acc[1].mean() / 750
+    # at stationarity pCN with beta=0.05 on this 64-dim posterior accepts ~1-2% of coarse proposals
+    assert 0.002 < rate_c < 0.9 and 0.002 < rate_f < 0.99, (rate_c, rate_f)
+    eng.close()
+
+
+def test_resume_and_sharding_are_exact():
+    """Size-independent properties on cfg2's shape: (1) run(a); run(b) equals run(a+b) bit for
+    bit; (2) an engine holding chains [lo, hi) of a larger job (chain_offset = lo) reproduces
+    those chains bit for bit -> sharding over GPUs changes nothing."""
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da()
+    spec = lower_problem(w["posteriors"], w["proposal"], 10)
+    C = 512
+    rng = np.random.default_rng(1)
+    theta0 = w["prior"].rvs(C, random_state=rng)
+
+    def run(lo, hi, splits, dtype):
+        eng = Engine(spec, hi - lo, dtype=dtype, seed=9, store=[STORE_NONE, STORE_STATS],
+                     capacity_iterations=sum(splits), chain_offset=lo, n_chains_global=C)
+        eng.init(theta0[lo:hi])
+        for s in splits:
+            eng.run(s)
+        th = eng.fetch(1, "theta")
+        lk = eng.fetch(1, "like")
+        eng.close()
+        return th, lk
+
+    for dtype in ("float32", "float64"):
+        th_a, lk_a = run(0, C, [12], dtype)
+        th_b, lk_b = run(0, C, [5, 7], dtype)
+        assert np.array_equal(th_a, th_b) and np.array_equal(lk_a, lk_b)
+        th_c, lk_c = run(128, 384, [12], dtype)
+        assert np.array_equal(th_a[:, :, 128:384], th_c) and np.array_equal(lk_a[:, 128:384], lk_c)

@@ -1,0 +1,208 @@
+"""CPU-side tests: the host mirror of the reference's API (validation, factories, result
+containers), the C-ABI library's symbol table, and the loud failure without a GPU."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+import scipy.stats as stats
+
+import tinyda_b200 as tda
+from tinyda_b200.link import LinkSequence
+from tinyda_b200.lowering import spec_to_flat, spec_from_flat
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _post(d=3, m=5, prior=None):
+    rng = np.random.default_rng(0)
+    G = rng.standard_normal((m, d))
+    prior = prior or stats.multivariate_normal(np.zeros(d), np.eye(d))
+    return tda.Posterior(prior, tda.GaussianLogLike(rng.standard_normal(m), 0.1 * np.eye(m)), tda.LinearModel(G))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "tinyda_b200.h")).read()
+    declared = set(re.findall(r"\b(tda_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"tda_engine", "tda_config", "tda_level_config"}
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(os.path.join(ROOT, "tinyda_b200", "libtinyda_b200.so"))
+    for name in sorted(declared):
+        assert hasattr(lib, name), "library does not export %s" % name
+    from tinyda_b200 import _lib
+    assert set(_lib.EXPORTS) == declared
+    assert lib.tda_abi_version() == 1
+
+
+def test_config_struct_layout_matches_header(tmp_path):
+    """ctypes mirror of tda_config vs the C compiler's layout of include/tinyda_b200.h."""
+    import subprocess
+    from tinyda_b200 import _lib
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "tinyda_b200.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tda_level_config), sizeof(tda_config),'
+        ' offsetof(tda_config, seed), offsetof(tda_config, scaling), offsetof(tda_config, prior_logconst),'
+        ' offsetof(tda_config, level)); return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    C = _lib.Config
+    assert got == [ctypes.sizeof(_lib.LevelConfig), ctypes.sizeof(C), C.seed.offset, C.scaling.offset,
+                   C.prior_logconst.offset, C.level.offset]
+
+
+def test_gaussian_loglike_factory_rule():
+    y = np.arange(4.0)
+    assert isinstance(tda.GaussianLogLike(y, 0.5 * np.eye(4)), tda.IsotropicGaussianLogLike)
+    assert isinstance(tda.GaussianLogLike(y, np.diag([1.0, 2, 3, 4])), tda.DiagonalGaussianLogLike)
+    C = np.eye(4)
+    C[0, 1] = C[1, 0] = 0.1
+    lk = tda.GaussianLogLike(y, C)
+    assert type(lk) is tda.DefaultGaussianLogLike
+    with pytest.raises(TypeError):
+        tda.GaussianLogLike(y, [[1.0]])
+    with pytest.raises(ValueError):
+        tda.GaussianLogLike(y, np.eye(3))
+    with pytest.raises(TypeError):
+        tda.AdaptiveGaussianLogLike(y, np.ones(4))
+    assert tda.AdaptiveLogLike is tda.AdaptiveGaussianLogLike
+
+
+def test_proposal_validation_matches_reference():
+    with pytest.raises(TypeError):
+        tda.GaussianRandomWalk([[1.0]])
+    with pytest.raises(ValueError):
+        tda.GaussianRandomWalk(np.ones((2, 3)))
+    with pytest.raises(TypeError):
+        tda.AdaptiveMetropolis(C0=1.0)
+    am = tda.AdaptiveMetropolis(C0=np.eye(10))
+    assert am.sd == min(1, 2.4 ** 2 / 10) and am.scaling == 1
+    assert tda.GaussianRandomWalk.alpha_star == 0.24 and tda.MALA.alpha_star == 0.57
+    assert tda.GaussianRandomWalk.is_symmetric and not tda.CrankNicolson.is_symmetric
+
+
+def test_sample_rejects_what_the_reference_rejects():
+    post = _post(prior=stats.norm(0, 1))
+    with pytest.raises(TypeError, match="scipy.stats.multivariate_normal"):
+        tda.sample(post, tda.CrankNicolson(), 10)
+    post = _post()
+    with pytest.raises(TypeError, match="list, numpy array or None"):
+        tda.sample(post, tda.GaussianRandomWalk(np.eye(3)), 10, initial_parameters=(0, 0, 0))
+    with pytest.raises(AssertionError):
+        tda.sample(post, tda.GaussianRandomWalk(np.eye(3)), 10, n_chains=2, initial_parameters=[np.zeros(3)])
+    with pytest.raises(AssertionError):
+        tda.sample(post, tda.GaussianRandomWalk(np.eye(3)), 10, initial_parameters=np.zeros(4))
+
+
+def test_python_callable_model_is_rejected_not_run_on_cpu():
+    prior = stats.multivariate_normal(np.zeros(2), np.eye(2))
+    post = tda.Posterior(prior, tda.GaussianLogLike(np.zeros(3), np.eye(3)), lambda th: np.zeros(3))
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        tda.sample(post, tda.GaussianRandomWalk(np.eye(2)), 10)
+
+
+def test_sample_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from tinyda_b200._lib import EngineError
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(EngineError, match="no CPU path"):
+            tda.sample(_post(), tda.GaussianRandomWalk(np.eye(3)), 5, n_chains=2, subsampling_rate=3)
+
+
+def test_subsampling_rate_warns():
+    import torch
+    post = _post()
+    with pytest.warns(UserWarning, match="subsampling_rate has been deprecated"):
+        try:
+            tda.sample([post, post], tda.GaussianRandomWalk(np.eye(3)), 2, subsampling_rate=2)
+        except Exception:
+            if torch.cuda.is_available():
+                raise
+
+
+def test_lowering_roundtrip_and_checks():
+    p = _post()
+    spec = tda.lower_problem([p, p, p], tda.GaussianRandomWalk(0.1 * np.eye(3)), [3, 2])
+    assert spec["n_levels"] == 3 and spec["J"] == [3, 2] and spec["d"] == 3
+    back = spec_from_flat(spec_to_flat(spec))
+    assert back["J"] == [3, 2]
+    np.testing.assert_array_equal(back["levels"][1]["model"]["A"], spec["levels"][1]["model"]["A"])
+    with pytest.raises(TypeError):      # AEM needs adaptive likelihoods on the coarse levels
+        tda.lower_problem([p, p], tda.GaussianRandomWalk(np.eye(3)), 2, "state-independent")
+    with pytest.raises(ValueError):
+        tda.lower_problem([p, p], tda.GaussianRandomWalk(np.eye(3)), [2, 2])
+    # scipy's own whitening reproduces scipy's logpdf
+    prior = stats.multivariate_normal(np.array([0.3, -0.2, 0.1]), np.array([[2, .3, 0], [.3, 1, .1], [0, .1, .5]]))
+    lp = tda.posterior.lower_prior(prior)
+    x = np.array([0.5, 0.1, -1.0])
+    val = -0.5 * (lp["logconst"] + np.sum(((x - lp["mean"]) @ lp["LP"]) ** 2))
+    assert abs(val - prior.logpdf(x)) < 1e-12
+
+
+def test_link_sequence_behaves_like_a_list_of_links():
+    n, d, m = 7, 3, 4
+    rng = np.random.default_rng(1)
+    seq = LinkSequence(rng.standard_normal((n, d)), rng.standard_normal(n), rng.standard_normal(n),
+                       rng.standard_normal((n, m)), np.ones(n, bool))
+    assert len(seq) == n
+    l = seq[-1]
+    assert l.posterior == l.prior + l.likelihood and l.parameters.shape == (d,) and l.qoi is None
+    tail = seq[2:]
+    assert len(tail) == n - 2 and np.array_equal(tail[0].parameters, seq[2].parameters)
+    both = seq[5:] + seq[:1]
+    assert len(both) == 3
+    assert np.array([lk.parameters for lk in both]).shape == (3, d)
+    with pytest.raises(IndexError):
+        seq[n]
+
+
+def test_get_samples_matches_reference_layout():
+    n, d, m = 9, 2, 3
+    rng = np.random.default_rng(2)
+    mk = lambda: LinkSequence(rng.standard_normal((n, d)), rng.standard_normal(n), rng.standard_normal(n),
+                              rng.standard_normal((n, m)), np.ones(n, bool))
+    res = {"sampler": "DA", "n_chains": 2, "iterations": n, "subchain_length": 3,
+           "chain_fine_0": mk(), "chain_fine_1": mk(), "chain_coarse_0": mk(), "chain_coarse_1": mk()}
+    s = tda.get_samples(res, "parameters", "fine", burnin=2)
+    assert s["iterations"] == n - 2 and s["dimension"] == d and s["chain_1"].shape == (n - 2, d)
+    st = tda.get_samples(res, "stats", "coarse")
+    assert st["dimension"] == 3
+    np.testing.assert_allclose(st["chain_0"][:, 2], st["chain_0"][:, 0] + st["chain_0"][:, 1])
+    mo = tda.get_samples(res, "model_output")
+    assert mo["dimension"] == m
+
+
+def test_ess_and_rhat_on_ar1_chains():
+    rng = np.random.default_rng(3)
+    n, m, rho = 20000, 4, 0.8
+    x = np.zeros((m, n))
+    e = rng.standard_normal((m, n))
+    for i in range(1, n):
+        x[:, i] = rho * x[:, i - 1] + e[:, i]
+    expected = m * n * (1 - rho) / (1 + rho)
+    assert abs(tda.ess_bulk(x) / expected - 1) < 0.2
+    assert abs(tda.rhat(x) - 1) < 0.01
+    x[0] += 3.0
+    assert tda.rhat(x) > 1.2
+
+
+def test_model_classes_keep_the_reference_model_protocol():
+    mdl = tda.Poisson1D(64, 4, 31)
+    out = mdl(np.array([0.1, -0.2, 0.05, 0.0]))
+    assert out.shape == (31,) and np.all(out > 0)
+    # constant conductivity k=1: u = x(1-x)/2 exactly at the nodes
+    u = tda.Poisson1D(32, 2, 31)(np.zeros(2))
+    x = np.arange(1, 32) / 32
+    np.testing.assert_allclose(u, x * (1 - x) / 2, rtol=1e-12)
+    r = tda.Rosenbrock(1, 10)
+    th = np.array([0.3, -0.4])
+    g = r.gradient(th, np.array([1.0]))
+    h = 1e-6
+    fd = np.array([(r(th + h * np.eye(2)[i])[0] - r(th - h * np.eye(2)[i])[0]) / (2 * h) for i in range(2)])
+    np.testing.assert_allclose(g, fd, rtol=1e-6)

@@ -69,7 +69,7 @@ struct Params {
     int mode, L, d, aem, rng_mode, prop_kind, adaptive, period, am_t0, am_device_refactor;
     int J[MAXL];
     int C, Cs, n_tiles;
-    long long chain_offset, Cg;
+    long long chain_offset, Cg, arch_off;   // arch_off: first archive column owned by this engine
     unsigned long long seed;
     long long iterations;
     // resumable counters (uniform over chains because chains advance in lock-step)

@@ -120,7 +120,8 @@ struct EngineT : tda_engine {
         Cs = n_tiles * tda::TC;
         P.Cs = Cs; P.n_tiles = n_tiles;
         P.chain_offset = c.chain_offset;
-        P.Cg = c.n_chains_global > 0 ? c.n_chains_global : c.n_chains;
+        P.Cg = (c.prop_kind == TDA_PROP_DREAM && c.n_chains_global > 0) ? c.n_chains_global : c.n_chains;
+        P.arch_off = (c.prop_kind == TDA_PROP_DREAM) ? c.chain_offset : 0;
         P.seed = c.seed;
         P.gamma = (R)c.gamma; P.alpha_star = (R)c.alpha_star; P.am_sd = (R)c.am_sd; P.am_eps = (R)c.am_eps;
         P.dream_b = (R)c.dream_b; P.dream_b_star = (R)c.dream_b_star;

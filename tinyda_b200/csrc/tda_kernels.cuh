@@ -574,7 +574,7 @@ struct Tile {
     __device__ __forceinline__ const R* archive_row(long long r, int c, long long nslots) const {
         long long g, slot;
         if (p.prop_kind == TDA_PROP_DREAM) { g = r / nslots; slot = r - g * nslots; }
-        else { g = p.chain_offset + chain0 + c; slot = r; }
+        else { g = chain0 + c; slot = r; }     // DREAMZ: own (local) archive column
         return p.archive + ((size_t)slot * p.Cg + g) * p.d;
     }
 
@@ -749,7 +749,7 @@ struct Tile {
                 for (int e = tid; e < d * TC; e += NT) {
                     int c = e / d, k = e - c * d;
                     if (chain0 + c < p.C)
-                        p.archive[((size_t)slots * p.Cg + p.chain_offset + chain0 + c) * d + k] = p.lv[0].theta[gi(k, c)];
+                        p.archive[((size_t)slots * p.Cg + p.arch_off + chain0 + c) * d + k] = p.lv[0].theta[gi(k, c)];
                 }
             slots += 1;
         }

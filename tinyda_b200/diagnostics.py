@@ -1,3 +1,162 @@
-def to_inference_data(*a, **k):
-    raise NotImplementedError
-get_samples = to_xarray = ess_bulk = rhat = to_inference_data
+"""Post-processing: ``get_samples`` / ``to_xarray`` / ``to_inference_data`` with the reference's
+signatures and naming (tinyDA/diagnostics.py:6-209), reading the array-backed LinkSequence
+directly instead of one Python object per sample, plus rank-normalised split-R-hat and bulk
+ESS (Vehtari et al. 2021, what ArviZ computes on the reference's output) in NumPy so that
+the benchmark's min-ESS/sec needs neither ArviZ nor the reference.
+"""
+import numpy as np
+
+from .link import LinkSequence
+
+
+def _attr_array(seq, attribute):
+    if isinstance(seq, LinkSequence):
+        if attribute == "parameters":
+            return np.asarray(seq.parameters)
+        if attribute == "model_output":
+            if seq.model_output is None:
+                raise ValueError("model outputs were not stored (store_model_output=False)")
+            return np.asarray(seq.model_output)
+        if attribute == "stats":
+            return np.stack([seq.prior, seq.likelihood, seq.prior + seq.likelihood], axis=1)
+        if attribute == "qoi":
+            return np.array([None] * len(seq))
+    if attribute == "stats":
+        return np.array([[l.prior, l.likelihood, l.posterior] for l in seq])
+    return np.array([getattr(l, attribute) for l in seq])
+
+
+def get_samples(chain, attribute="parameters", level="fine", burnin=0):
+    """diagnostics.py:114-209: dict with 'chain_i' arrays (samples as rows), 'iterations',
+    'dimension' plus the sampler info copied across."""
+    samples = {"sampler": chain["sampler"], "n_chains": chain["n_chains"], "attribute": attribute}
+    if chain["sampler"] == "MH":
+        key = "chain_{}"
+    elif chain["sampler"] == "DA":
+        samples["subchain_length"] = chain["subchain_length"]
+        samples["level"] = level
+        key = "chain_" + str(level) + "_{}"
+    elif chain["sampler"] == "MLDA":
+        samples["subchain_lengths"] = chain["subchain_lengths"]
+        samples["level"] = level
+        key = "chain_l" + str(level) + "_{}"
+    else:
+        raise ValueError("unknown sampler %r" % chain["sampler"])
+    for i in range(chain["n_chains"]):
+        x = _attr_array(chain[key.format(i)][burnin:], attribute)
+        if x.ndim == 1:
+            x = x[..., np.newaxis]
+        samples["chain_{}".format(i)] = x
+    samples["iterations"] = samples["chain_0"].shape[0]
+    samples["dimension"] = samples["chain_0"].shape[1]
+    return samples
+
+
+def to_xarray(samples, keys):
+    """diagnostics.py:72-111 (needs xarray)."""
+    import xarray as xr
+    data_vars = {}
+    for i in range(samples["dimension"]):
+        x = np.array([samples["chain_{}".format(j)][:, i] for j in range(samples["n_chains"])])
+        data_vars[keys[i]] = (["chain", "draw"], x)
+    return xr.Dataset(
+        data_vars=data_vars,
+        coords=dict(chain=("chain", list(range(samples["n_chains"]))),
+                    draw=("draw", list(range(samples["iterations"])))),
+    )
+
+
+def to_inference_data(chain, level="fine", burnin=0, parameter_names=None):
+    """diagnostics.py:6-69 (needs arviz + xarray): groups posterior, posterior_predictive, qoi,
+    sample_stats; variables x{i}, obs_{i}, qoi_{i}, prior / likelihood / posterior."""
+    import arviz as az
+    arrays = []
+    for attr in ["parameters", "model_output", "qoi", "stats"]:
+        samples = get_samples(chain, attr, level, burnin)
+        if attr == "parameters":
+            keys = (["x{}".format(i) for i in range(samples["dimension"])]
+                    if parameter_names is None else parameter_names)
+        elif attr == "model_output":
+            keys = ["obs_{}".format(i) for i in range(samples["dimension"])]
+        elif attr == "qoi":
+            keys = ["qoi_{}".format(i) for i in range(samples["dimension"])]
+        else:
+            keys = ["prior", "likelihood", "posterior"]
+        arrays.append(to_xarray(samples, keys))
+    return az.InferenceData(posterior=arrays[0], posterior_predictive=arrays[1], qoi=arrays[2],
+                            sample_stats=arrays[3])
+
+
+# ---- R-hat / ESS ---------------------------------------------------------------------------
+def _split(x):
+    n = x.shape[1] // 2
+    return np.concatenate([x[:, :n], x[:, x.shape[1] - n:]], axis=0)
+
+
+def _rank_normalise(x):
+    from scipy.stats import rankdata, norm
+    r = rankdata(x.reshape(-1), method="average").reshape(x.shape)
+    return norm.ppf((r - 0.375) / (x.size + 0.25))
+
+
+def _autocov(x):
+    n = x.shape[1]
+    m = 1 << int(np.ceil(np.log2(2 * n)))
+    xc = x - x.mean(axis=1, keepdims=True)
+    f = np.fft.rfft(xc, n=m, axis=1)
+    ac = np.fft.irfft(f * np.conj(f), n=m, axis=1)[:, :n]
+    return ac / n
+
+
+def _rhat_plain(x):
+    m, n = x.shape
+    W = x.var(axis=1, ddof=1).mean()
+    B = n * x.mean(axis=1).var(ddof=1)
+    return np.sqrt(((n - 1) / n * W + B / n) / W)
+
+
+def _ess_plain(x):
+    m, n = x.shape
+    acov = _autocov(x)
+    chain_var = acov[:, 0] * n / (n - 1.0)
+    mean_var = chain_var.mean()
+    var_plus = mean_var * (n - 1.0) / n
+    if m > 1:
+        var_plus += x.mean(axis=1).var(ddof=1)
+    rho = np.zeros(n)
+    rho[0] = 1.0
+    t = 1
+    rho_even, rho_odd = 1.0, 1.0 - (mean_var - acov[:, 1].mean()) / var_plus
+    rho[1] = rho_odd
+    while t < n - 3 and (rho_even + rho_odd) > 0:       # Geyer's initial positive sequence
+        rho_even = 1.0 - (mean_var - acov[:, t + 1].mean()) / var_plus
+        rho_odd = 1.0 - (mean_var - acov[:, t + 2].mean()) / var_plus
+        if rho_even + rho_odd >= 0:
+            rho[t + 1], rho[t + 2] = rho_even, rho_odd
+        t += 2
+    max_t = t - 2
+    if rho_even > 0:
+        rho[max_t + 1] = rho_even
+    t = 1
+    while t <= max_t - 2:                                # initial monotone sequence
+        if rho[t + 1] + rho[t + 2] > rho[t - 1] + rho[t]:
+            rho[t + 1] = (rho[t - 1] + rho[t]) / 2.0
+            rho[t + 2] = rho[t + 1]
+        t += 2
+    tau = -1.0 + 2.0 * rho[:max_t + 1].sum() + rho[max_t + 1]
+    tau = max(tau, 1.0 / np.log10(m * n))
+    return m * n / tau
+
+
+def rhat(x):
+    """Rank-normalised split-R-hat of draws x [n_chains, n_draws]."""
+    x = np.asarray(x, dtype=np.float64)
+    z = _rank_normalise(_split(x))
+    zf = _rank_normalise(np.abs(_split(x) - np.median(x)))
+    return max(_rhat_plain(z), _rhat_plain(zf))
+
+
+def ess_bulk(x):
+    """Bulk effective sample size of draws x [n_chains, n_draws] (rank-normalised, split)."""
+    x = np.asarray(x, dtype=np.float64)
+    return _ess_plain(_rank_normalise(_split(x)))
