@@ -203,6 +203,12 @@ int tda_history_reset(tda_engine *e);
  * supported by it). */
 int tda_select_kernel(tda_engine *e, int which);
 
+/* Diagnostic: D[128][N] = A[128][64] @ B[64][N] (row-major float32 host arrays) computed by one
+ * CTA on the tcgen05 tensor cores with the conventions of the tensor-core DA kernel
+ * (A operand in TMEM when a_in_tmem != 0, else in shared memory; B K-major in shared memory;
+ * 3xTF32 split when split != 0, a single TF32 pass on B otherwise).  N: multiple of 8, <= 256. */
+int tda_tc_gemm_selftest(const float *A, const float *B, int N, float *D, int a_in_tmem, int split);
+
 /* Kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t tda_launch_count(void);
 

@@ -28,7 +28,7 @@ EXPORTS = [
     "tda_abi_version", "tda_last_error", "tda_engine_create", "tda_engine_destroy", "tda_upload",
     "tda_engine_init", "tda_engine_run", "tda_engine_sync", "tda_fetch", "tda_get", "tda_set",
     "tda_device_buffer", "tda_dream_slots", "tda_fill_streams", "tda_history_reset",
-    "tda_select_kernel", "tda_launch_count",
+    "tda_select_kernel", "tda_launch_count", "tda_tc_gemm_selftest",
 ]
 
 
@@ -81,6 +81,7 @@ def _load():
     lib.tda_fill_streams.argtypes = [vp, C.POINTER(C.c_double), i64, C.POINTER(C.c_double), i64]
     lib.tda_history_reset.argtypes = [vp]
     lib.tda_select_kernel.argtypes = [vp, i32]
+    lib.tda_tc_gemm_selftest.argtypes = [vp, vp, i32, vp, i32, i32]
     for name in EXPORTS:
         if getattr(lib, name).restype is C.c_int and name not in ("tda_abi_version",):
             getattr(lib, name).restype = i32

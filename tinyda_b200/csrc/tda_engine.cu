@@ -674,6 +674,14 @@ int tda_fill_streams(tda_engine* e, double* z, int64_t nz, double* u, int64_t nu
     if (!e || !z || !u) return fail(-1, "null argument");
     return e->fill_streams(z, nz, u, nu);
 }
+int tda_tc_gemm_selftest(const float* A, const float* B, int N, float* D, int a_in_tmem, int split) {
+    if (!A || !B || !D) return fail(-1, "null argument");
+    std::string err;
+    int r = tda::tc_gemm_selftest_host(A, B, N, D, a_in_tmem, split, err);
+    g_launches++;
+    if (r) return fail(r, err);
+    return 0;
+}
 int tda_history_reset(tda_engine* e) { return e ? e->history_reset() : fail(-1, "null engine"); }
 int tda_select_kernel(tda_engine* e, int which) { return e ? e->select_kernel(which) : fail(-1, "null engine"); }
 
