@@ -33,3 +33,98 @@ def test_tf32x3_gemm_matches_fp64(a_in_tmem, N):
     D1 = _gemm(A, B, a_in_tmem, 0)
     err1 = np.abs(D1 - ref).max()
     assert err1 < 5e-3 * scale and err1 > 5 * err
+
+
+# ---- tensor-core Delayed-Acceptance kernel ---------------------------------------------------
+def _cfg2_engine(C, kernel, seed=9, rng="philox", streams=None, iters=30, theta0=None, chain_offset=0):
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da()
+    spec = lower_problem(w["posteriors"], w["proposal"], 10)
+    if theta0 is None:
+        theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1))
+    eng = Engine(spec, C, dtype="float32", rng=rng, seed=seed, streams=streams, store=[STORE_NONE, STORE_STATS],
+                 capacity_iterations=iters, chain_offset=chain_offset)
+    eng.select_kernel(kernel)
+    eng.init(theta0)
+    return eng, w
+
+
+def test_tc_kernel_matches_reference_trajectory_until_near_tie():
+    """cfg2 golden fixture (unmodified reference, injected streams) vs the tcgen05 kernel."""
+    import golden_io
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    g = golden_io.load("da_pcn_cfg2")
+    C, iters = g["theta0"].shape[0], g["iterations"]
+    eng = Engine(g["spec"], C, dtype="float32", rng="injected", streams=(g["z"], g["u"]),
+                 store=[STORE_NONE, STORE_STATS], capacity_iterations=iters)
+    eng.select_kernel("tc")
+    eng.init(g["theta0"])
+    eng.run(iters)
+    acc = eng.fetch(1, "accept").T.astype(bool)
+    th = np.transpose(eng.fetch(1, "theta"), (2, 0, 1)).astype(np.float64)
+    lk = eng.fetch(1, "like").T.astype(np.float64)
+    ref = g["ref"][1]
+    diff = acc != ref["acc"]
+    first = np.where(diff.any(axis=1), diff.argmax(axis=1), acc.shape[1])
+    assert first.min() >= 10, first            # long common prefix on both chains
+    for c in range(C):
+        k = int(first[c])
+        scale = np.abs(ref["theta"][c, :k]).max()
+        np.testing.assert_allclose(th[c, :k], ref["theta"][c, :k], rtol=1e-4, atol=1e-4 * scale)
+        np.testing.assert_allclose(lk[c, :k], ref["like"][c, :k], rtol=2e-4, atol=2e-2)
+
+
+def test_tc_kernel_agrees_with_generic_fp32_kernel():
+    C, iters = 512, 30
+    a, _ = _cfg2_engine(C, "tc", iters=iters)
+    b, _ = _cfg2_engine(C, "generic", iters=iters)
+    a.run(iters)
+    b.run(iters)
+    acc_a, acc_b = a.fetch(1, "accept"), b.fetch(1, "accept")
+    th_a, th_b = a.fetch(1, "theta"), b.fetch(1, "theta")
+    same = (acc_a == acc_b)
+    assert same.mean() > 0.97, same.mean()
+    # chains whose decisions all agree follow the same trajectory to float32 accuracy
+    ok = same.all(axis=0)
+    assert ok.mean() > 0.6
+    scale = np.abs(th_b).max()
+    assert np.abs(th_a[:, :, ok] - th_b[:, :, ok]).max() < 2e-3 * scale
+    assert np.array_equal(a.get("cursors")[0], b.get("cursors")[0])
+    ca, cb = a.get("accept_counts"), b.get("accept_counts")
+    assert abs(ca[0].mean() - cb[0].mean()) < 0.05 * cb[0].mean() + 1
+
+
+def test_tc_kernel_resume_and_sharding_exact():
+    C = 512
+    def run(lo, hi, splits):
+        from tinyda_b200.workloads import cfg2_da
+        theta0 = cfg2_da()["prior"].rvs(C, random_state=np.random.default_rng(1))
+        eng, _ = _cfg2_engine(hi - lo, "tc", iters=sum(splits), theta0=theta0[lo:hi], chain_offset=lo)
+        for s in splits:
+            eng.run(s)
+        return eng.fetch(1, "theta"), eng.fetch(1, "like")
+    th_a, lk_a = run(0, C, [12])
+    th_b, lk_b = run(0, C, [5, 7])
+    assert np.array_equal(th_a, th_b) and np.array_equal(lk_a, lk_b)
+    th_c, lk_c = run(256, 512, [12])
+    assert np.array_equal(th_a[:, :, 256:512], th_c)
+
+
+def test_tc_kernel_conjugate_posterior_mean():
+    from tinyda_b200.workloads import conjugate_posterior
+    C = 8192
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da()
+    mu, S = conjugate_posterior(w["G"], w["y"], w["sigma2"], w["prior"])
+    theta0 = np.random.default_rng(0).multivariate_normal(mu, S, size=C)
+    eng, _ = _cfg2_engine(C, "tc", seed=3, iters=0, theta0=theta0)
+    eng.run(150)
+    m0 = eng.get("moments")
+    eng.run(600)
+    m1 = eng.get("moments")
+    cm = ((m1[0] - m0[0]) / 600).T
+    mcse = cm.std(axis=0, ddof=1) / np.sqrt(C)
+    err = np.abs(cm.mean(axis=0) - mu)
+    assert np.all(err < 3 * mcse + 2e-4 * (np.abs(mu) + np.sqrt(np.diag(S)))), (err / mcse).max()

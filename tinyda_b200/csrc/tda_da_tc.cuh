@@ -152,12 +152,474 @@ inline int tc_gemm_selftest_host(const float* A, const float* B, int N, float* D
     return err.empty() ? 0 : -2;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core Delayed-Acceptance kernel.
+//
+// One CTA = 2 tiles x 128 chains (thread = chain = TMEM lane) + one MMA-issuing warp + one
+// bulk-copy producer warp.  Per tile, TMEM holds the A operand (hi | lo, 2 x 64 columns) and a
+// 128-column accumulator; all B operands live in shared memory in the canonical K-major
+// no-swizzle layout, pre-split into hi / lo on the host: the proposal factor T and the coarse
+// operator G_c^T stay resident, the fine operator [G_f^T | LP] streams through a ring of
+// 64-column chunks filled by cp.async.bulk.  Row threads and the MMA thread hand jobs back and
+// forth through two mbarriers per tile (req: "A written / D consumed", resp: tcgen05.commit);
+// the two tiles interleave so that one tile's CUDA-core work (Philox, Box-Muller, splits,
+// residual reductions) overlaps the other tile's MMAs.
+//
+// Reference semantics are those of Tile::base_step / Tile::upper_step in tda_kernels.cuh
+// (chain.py:325-444) specialised to pCN + isotropic likelihoods + linear models; the state
+// buffers are shared with the generic kernel, so runs of the two kernels can be interleaved.
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_K = 64;                    // parameters (contraction length)
+constexpr int TC_CH = 64;                   // columns per streamed chunk
+constexpr int TC_NST = 3;                   // ring stages
+constexpr int TC_MAX_MC = 128;
+constexpr int TC_MAX_MF = 4096;
+constexpr int TC_THREADS = 320;
+constexpr int TC_CHUNK_BYTES = TC_CH * TC_K * 4 * 2;   // hi + lo
+
+__constant__ float c_yc[TC_MAX_MC];         // coarse data - offset
+__constant__ float c_yf[TC_MAX_MF];         // fine data - offset
+__constant__ float c_lp[TC_K];              // prior_mean @ LP
+
+struct DaTcParams {
+    const float* T_hl;       // canonical [hi 64x64 | lo 64x64]
+    const float* Gc_hl;      // canonical [hi mc x 64 | lo mc x 64]
+    const float* F_chunks;   // n_chunks x [hi 64x64 | lo 64x64]   (fine operator columns, then LP)
+    int mc, mf, n_chunks, J;
+    float var_c, var_f, prior_logconst;
+    int n_pairs;
+};
+
+__device__ __forceinline__ void tc_issue_job(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi_saddr, uint32_t b_lo_saddr, int N) {
+    const uint32_t idesc = tc::idesc_tf32(128, N);
+    uint32_t accumulate = 0;
+#pragma unroll
+    for (int pass = 0; pass < 3; pass++) {
+        const uint32_t a = a_tmem + (pass == 1 ? TC_K : 0);
+        const uint64_t b0 = tc::smem_desc_kmajor(pass == 2 ? b_lo_saddr : b_hi_saddr, 128, (TC_K / 4) * 128);
+#pragma unroll
+        for (int ks = 0; ks < TC_K / 8; ks++) {
+            tc::mma_tf32_ts(d_tmem, a + ks * 8, b0 + (uint64_t)(ks * 16), idesc, accumulate);
+            accumulate = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ DaTcParams q) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* sT = reinterpret_cast<float*>(smem);                         // 32 KB (hi | lo)
+    float* sGc = sT + 2 * 64 * TC_K;                                    // 64 KB (hi | lo), sized for mc = 128
+    unsigned char* ring = reinterpret_cast<unsigned char*>(sGc + 2 * TC_MAX_MC * TC_K);   // NST x 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + TC_NST * TC_CHUNK_BYTES);
+    uint64_t* bar_res = bars;            // resident operands landed
+    uint64_t* bar_req = bars + 1;        // [2]
+    uint64_t* bar_resp = bars + 3;       // [2]
+    uint64_t* bar_full = bars + 5;       // [NST]
+    uint64_t* bar_empty = bars + 5 + TC_NST;   // [NST]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5 + 2 * TC_NST);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 8) tc::tmem_alloc(s_tmem, 512);
+    if (tid == 288) {
+        tc::mbar_init(bar_res, 1);
+        for (int t = 0; t < 2; t++) { tc::mbar_init(bar_req + t, 128); tc::mbar_init(bar_resp + t, 1); }
+        for (int s = 0; s < TC_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 1); }
+        tc::fence_mbar_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = *s_tmem;
+
+    const int J = q.J, mc = q.mc, NCH = q.n_chunks;
+    const int my_pairs = (q.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long iters = p.iterations;
+    const long long total_chunks = (long long)my_pairs * iters * NCH;
+
+    if (warp == 9) {
+        // ===== producer: resident operands once, then the fine-operator chunk ring =====
+        if (lane == 0) {
+            const uint32_t bT = 2u * 64 * TC_K * 4, bG = 2u * (uint32_t)mc * TC_K * 4;
+            tc::mbar_expect_tx(bar_res, bT + bG);
+            tc::bulk_g2s(sT, q.T_hl, bT, bar_res);
+            // hi part and lo part of G_c are stored back to back in global; in shared memory the lo
+            // part starts at the fixed offset used by the MMA warp (mc rows each)
+            tc::bulk_g2s(sGc, q.Gc_hl, bG / 2, bar_res);
+            tc::bulk_g2s(sGc + TC_MAX_MC * TC_K, q.Gc_hl + (size_t)mc * TC_K, bG / 2, bar_res);
+            for (long long g = 0; g < total_chunks; g++) {
+                const int st = (int)(g % TC_NST);
+                if (g >= TC_NST) tc::mbar_wait(bar_empty + st, (uint32_t)(((g / TC_NST) - 1) & 1));
+                const int c = (int)(g % NCH);
+                tc::mbar_expect_tx(bar_full + st, TC_CHUNK_BYTES);
+                tc::bulk_g2s(ring + (size_t)st * TC_CHUNK_BYTES, q.F_chunks + (size_t)c * (TC_CHUNK_BYTES / 4), TC_CHUNK_BYTES, bar_full + st);
+            }
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            tc::mbar_wait(bar_res, 0);
+            uint32_t rph[2] = {0, 0};
+            const uint32_t sT_hi = tc::smem_u32(sT), sT_lo = sT_hi + 64 * TC_K * 4;
+            const uint32_t sG_hi = tc::smem_u32(sGc), sG_lo = sG_hi + TC_MAX_MC * TC_K * 4;
+            long long g = 0;
+            for (int pr = 0; pr < my_pairs; pr++) {
+                for (long long it = 0; it < iters; it++) {
+                    for (int j = 0; j < J; j++) {
+                        for (int t = 0; t < 2; t++) {       // xi = z @ T
+                            tc::mbar_wait(bar_req + t, rph[t]); rph[t] ^= 1;
+                            tc::fence_after_sync();
+                            tc_issue_job(tbase + t * 256 + 128, tbase + t * 256, sT_hi, sT_lo, 64);
+                            tc::mma_commit(bar_resp + t);
+                        }
+                        for (int t = 0; t < 2; t++) {       // F_c = theta' @ G_c^T
+                            tc::mbar_wait(bar_req + t, rph[t]); rph[t] ^= 1;
+                            tc::fence_after_sync();
+                            tc_issue_job(tbase + t * 256 + 128, tbase + t * 256, sG_hi, sG_lo, mc);
+                            tc::mma_commit(bar_resp + t);
+                        }
+                    }
+                    for (int c = 0; c < NCH; c++, g++) {    // fine operator chunks, then the prior chunk
+                        const int st = (int)(g % TC_NST);
+                        tc::mbar_wait(bar_full + st, (uint32_t)((g / TC_NST) & 1));
+                        const uint32_t b_hi = tc::smem_u32(ring + (size_t)st * TC_CHUNK_BYTES), b_lo = b_hi + TC_CH * TC_K * 4;
+                        for (int t = 0; t < 2; t++) {
+                            tc::mbar_wait(bar_req + t, rph[t]); rph[t] ^= 1;
+                            tc::fence_after_sync();
+                            tc_issue_job(tbase + t * 256 + 128, tbase + t * 256, b_hi, b_lo, TC_CH);
+                            tc::mma_commit(bar_resp + t);
+                        }
+                        tc::mma_commit(bar_empty + st);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== row threads: one chain each =====
+        const int t = warp >> 2;                       // tile within the pair
+        const int wq = warp & 3;                       // TMEM lane quarter
+        const uint32_t tA = tbase + ((uint32_t)(wq * 32) << 16) + t * 256;
+        const uint32_t tD = tA + 128;
+        uint64_t* req = bar_req + t;
+        uint64_t* resp = bar_resp + t;
+        uint32_t ph = 0;
+        const LevelP<float>& l0 = p.lv[0];
+        const LevelP<float>& l1 = p.lv[1];
+        const float inv2vc = -0.5f / q.var_c, inv2vf = -0.5f / q.var_f;
+
+        for (int pr = 0; pr < my_pairs; pr++) {
+            const int pair = (int)blockIdx.x + pr * (int)gridDim.x;
+            const int g = pair * 256 + t * 128 + wq * 32 + lane;       // chain slot (padded arrays)
+            const long long gchain = p.chain_offset + g;
+            const bool inj = p.rng_mode == TDA_RNG_INJECTED;
+            const bool live = g < p.C;
+            float th[TC_K], tp[TC_K];
+#pragma unroll
+            for (int k = 0; k < TC_K; k++) th[k] = l1.theta[(size_t)k * p.Cs + g];
+            float like_c = l0.like[g], like_cs = like_c, like_f = l1.like[g], prior_f = l1.prior[g];
+            long long ucur = p.ucur[g];
+            long long nacc_c = 0, nacc_f = 0;
+            int acc_any = 0;
+            const float s = p.scaling[g];
+            const float ca = sqrtf(1.0f - s * s), cb = s;
+            long long tb = p.t_base;
+
+            for (long long it = 0; it < iters; it++) {
+                for (int j = 0; j < J; j++) {
+                    // ---- proposal draws -> A (hi | lo) ----
+                    const long long z0 = tb * TC_K;
+#pragma unroll
+                    for (int c0 = 0; c0 < TC_K; c0 += 16) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; b4++) {
+                            float v[4];
+                            if (inj) {
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    long long idx = z0 + c0 + b4 * 4 + i;
+                                    v[i] = (live && idx < p.zlen) ? p.zs[(size_t)g * p.zlen + idx] : 0.0f;
+                                }
+                            } else {
+                                normals4<float>(philox_block(p.seed, gchain, STREAM_Z, (unsigned long long)(z0 >> 2) + (c0 >> 2) + b4), v);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                float h = tc::tf32_hi(v[i]);
+                                hi[b4 * 4 + i] = __float_as_uint(h);
+                                lo[b4 * 4 + i] = __float_as_uint(v[i] - h);
+                            }
+                        }
+                        tc::tmem_st16(tA + c0, hi);
+                        tc::tmem_st16(tA + TC_K + c0, lo);
+                    }
+                    tc::tmem_wait_st();
+                    tc::fence_before_sync();
+                    tc::mbar_arrive(req);
+                    // ---- xi -> theta' -> A ----
+                    tc::mbar_wait(resp, ph); ph ^= 1;
+                    tc::fence_after_sync();
+#pragma unroll
+                    for (int c0 = 0; c0 < TC_K; c0 += 16) {
+                        uint32_t v[16], hi[16], lo[16];
+                        tc::tmem_ld16(tD + c0, v);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            float x = ca * th[c0 + i] + cb * __uint_as_float(v[i]);
+                            tp[c0 + i] = x;
+                            float h = tc::tf32_hi(x);
+                            hi[i] = __float_as_uint(h);
+                            lo[i] = __float_as_uint(x - h);
+                        }
+                        tc::tmem_st16(tA + c0, hi);
+                        tc::tmem_st16(tA + TC_K + c0, lo);
+                    }
+                    tc::tmem_wait_st();
+                    tc::fence_before_sync();
+                    tc::mbar_arrive(req);
+                    // ---- coarse residual, accept / reject ----
+                    tc::mbar_wait(resp, ph); ph ^= 1;
+                    tc::fence_after_sync();
+                    float ssq = 0.0f;
+                    for (int c0 = 0; c0 < mc; c0 += 16) {
+                        uint32_t v[16];
+                        tc::tmem_ld16(tD + c0, v);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            float r = __uint_as_float(v[i]) - c_yc[c0 + i];
+                            ssq = fmaf(r, r, ssq);
+                        }
+                    }
+                    const float like_p = inv2vc * ssq;
+                    const float alpha = isnan(like_p) ? 0.0f : expf(like_p - like_c);
+                    float u;
+                    if (inj) u = (live && ucur < p.ulen) ? p.us[(size_t)g * p.ulen + ucur] : 0.5f;
+                    else u = philox_uniform<float>(p.seed, gchain, ucur);
+                    ucur++;
+                    if (u < alpha) {
+#pragma unroll
+                        for (int k = 0; k < TC_K; k++) th[k] = tp[k];
+                        like_c = like_p;
+                        acc_any = 1;
+                        nacc_c++;
+                    }
+                    tb++;
+                }
+                // ---- fine level: A <- current coarse state ----
+#pragma unroll
+                for (int c0 = 0; c0 < TC_K; c0 += 16) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        float h = tc::tf32_hi(th[c0 + i]);
+                        hi[i] = __float_as_uint(h);
+                        lo[i] = __float_as_uint(th[c0 + i] - h);
+                    }
+                    tc::tmem_st16(tA + c0, hi);
+                    tc::tmem_st16(tA + TC_K + c0, lo);
+                }
+                tc::tmem_wait_st();
+                tc::fence_before_sync();
+                tc::mbar_arrive(req);
+                float ssq_f = 0.0f, ssq_p = 0.0f;
+                for (int c = 0; c < NCH; c++) {
+                    tc::mbar_wait(resp, ph); ph ^= 1;
+                    tc::fence_after_sync();
+#pragma unroll
+                    for (int c0 = 0; c0 < TC_CH; c0 += 16) {
+                        uint32_t v[16];
+                        tc::tmem_ld16(tD + c0, v);
+                        tc::tmem_wait_ld();
+                        if (c < NCH - 1) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                float r = __uint_as_float(v[i]) - c_yf[c * TC_CH + c0 + i];
+                                ssq_f = fmaf(r, r, ssq_f);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                float w = __uint_as_float(v[i]) - c_lp[c0 + i];
+                                ssq_p = fmaf(w, w, ssq_p);
+                            }
+                        }
+                    }
+                    if (c < NCH - 1) {
+                        tc::fence_before_sync();
+                        tc::mbar_arrive(req);
+                    }
+                }
+                const float like_fp = inv2vf * ssq_f;
+                const float prior_p = -0.5f * (q.prior_logconst + ssq_p);
+                int accf = 0;
+                if (acc_any) {
+                    const float alpha2 = expf(like_fp - like_f + like_cs - like_c);
+                    float u;
+                    if (inj) u = (live && ucur < p.ulen) ? p.us[(size_t)g * p.ulen + ucur] : 0.5f;
+                    else u = philox_uniform<float>(p.seed, gchain, ucur);
+                    ucur++;
+                    accf = (u < alpha2) ? 1 : 0;
+                }
+                if (accf) {
+                    like_f = like_fp; prior_f = prior_p; like_cs = like_c; nacc_f++;
+#pragma unroll
+                    for (int k = 0; k < TC_K; k++) l1.theta[(size_t)k * p.Cs + g] = th[k];
+                } else {
+                    like_c = like_cs;
+#pragma unroll
+                    for (int k = 0; k < TC_K; k++) th[k] = l1.theta[(size_t)k * p.Cs + g];
+                }
+                acc_any = 0;
+                // ---- fine-level record (coalesced: consecutive lanes = consecutive chains) ----
+                const long long r = p.rec[1] + it;
+                if (r < l1.hist_cap) {
+                    if (l1.store & TDA_STORE_THETA) {
+#pragma unroll
+                        for (int k = 0; k < TC_K; k++) l1.h_theta[((size_t)r * TC_K + k) * p.Cs + g] = th[k];
+                    }
+                    if (l1.store & TDA_STORE_STATS) { l1.h_prior[(size_t)r * p.Cs + g] = prior_f; l1.h_like[(size_t)r * p.Cs + g] = like_f; }
+                    if (l1.store & TDA_STORE_ACCEPT) l1.h_acc[(size_t)r * p.Cs + g] = (uint8_t)accf;
+                }
+#pragma unroll
+                for (int k = 0; k < TC_K; k++) {
+                    p.sum1[(size_t)k * p.Cs + g] += th[k];
+                    p.sum2[(size_t)k * p.Cs + g] += th[k] * th[k];
+                }
+            }
+            // ---- write the chain state back (layout shared with the generic kernel) ----
+#pragma unroll
+            for (int k = 0; k < TC_K; k++) l0.theta[(size_t)k * p.Cs + g] = th[k];
+            l0.like[g] = like_c; l0.prior[g] = prior_f; l1.like[g] = like_f; l1.prior[g] = prior_f;
+            l0.sv_like[1][g] = like_c; l0.sv_prior[1][g] = prior_f;
+            l0.acc_sub[g] = 0;
+            l0.n_acc[g] += nacc_c; l1.n_acc[g] += nacc_f;
+            p.ucur[g] = ucur;
+        }
+        tc::fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tbase, 512);
+}
+
 template <typename R>
 struct DaTcState {
     std::string err;
     bool eligible(const tda_config&, const Params<R>&) const { return false; }
-    int run(Params<R>&, const tda_config&, long long, int, cudaStream_t) { err = "tensor-core path not built"; return -5; }
+    int run(Params<R>&, const tda_config&, long long, int, cudaStream_t) { err = "tensor-core DA kernel is float32 only"; return -5; }
     void destroy() {}
+};
+
+template <>
+struct DaTcState<float> {
+    std::string err;
+    float *dT = nullptr, *dGc = nullptr, *dF = nullptr;
+    bool prepared = false;
+    DaTcParams q{};
+    std::vector<float> yc, yf, clp;
+
+    bool eligible(const tda_config& c, const Params<float>& P) const {
+        if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.prop_kind != TDA_PROP_PCN || c.adaptive) return false;
+        if (c.d != TC_K) return false;
+        for (int l = 0; l < 2; l++)
+            if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
+        if (c.level[0].m > TC_MAX_MC || (c.level[0].m % 16) != 0) return false;
+        if (c.level[1].m > TC_MAX_MF || (c.level[1].m % TC_CH) != 0) return false;
+        if (c.level[0].store != 0 || (c.level[1].store & TDA_STORE_OUTPUT)) return false;
+        if ((P.Cs % 256) != 0) return false;
+        return true;
+    }
+
+    void destroy() {
+        if (dT) cudaFree(dT);
+        if (dGc) cudaFree(dGc);
+        if (dF) cudaFree(dF);
+        dT = dGc = dF = nullptr;
+    }
+
+    // canonical K-major hi / lo images of B[n][k] = W[k][n] (W row-major [K][ldw])
+    static void canon_split(const std::vector<float>& W, int ldw, int n0, int rows, float* hi, float* lo) {
+        for (int n = 0; n < rows; n++)
+            for (int k = 0; k < TC_K; k++) {
+                float x = W[(size_t)k * ldw + n0 + n];
+                float h = tc::tf32_hi(x);
+                size_t o = tc::canon_offset_f32(n, k, TC_K) / 4;
+                hi[o] = h;
+                lo[o] = x - h;
+            }
+    }
+
+    int prepare(const Params<float>& P, const tda_config& c) {
+        auto fetch = [&](const float* dev, size_t n, std::vector<float>& h) {
+            h.resize(n);
+            return cudaMemcpy(h.data(), dev, n * sizeof(float), cudaMemcpyDeviceToHost);
+        };
+        const int mc = c.level[0].m, mf = c.level[1].m;
+        std::vector<float> T, LP, Ac, Af, bc, bf, dc, df, mu;
+        cudaError_t e = cudaSuccess;
+        if (e == cudaSuccess) e = fetch(P.T, (size_t)TC_K * P.ldD, T);
+        if (e == cudaSuccess) e = fetch(P.LP, (size_t)TC_K * P.ldD, LP);
+        if (e == cudaSuccess) e = fetch(P.lv[0].A, (size_t)TC_K * P.lv[0].ldA, Ac);
+        if (e == cudaSuccess) e = fetch(P.lv[1].A, (size_t)TC_K * P.lv[1].ldA, Af);
+        if (e == cudaSuccess) e = fetch(P.lv[0].b, mc, bc);
+        if (e == cudaSuccess) e = fetch(P.lv[1].b, mf, bf);
+        if (e == cudaSuccess) e = fetch(P.lv[0].data, mc, dc);
+        if (e == cudaSuccess) e = fetch(P.lv[1].data, mf, df);
+        if (e == cudaSuccess) e = fetch(P.prior_mean, TC_K, mu);
+        if (e != cudaSuccess) { err = std::string("tc prepare: ") + cudaGetErrorString(e); return -2; }
+        const int nfc = mf / TC_CH, nch = nfc + 1;
+        std::vector<float> hT((size_t)2 * 64 * TC_K), hG((size_t)2 * mc * TC_K), hF((size_t)nch * 2 * TC_CH * TC_K);
+        canon_split(T, P.ldD, 0, 64, hT.data(), hT.data() + 64 * TC_K);
+        canon_split(Ac, P.lv[0].ldA, 0, mc, hG.data(), hG.data() + (size_t)mc * TC_K);
+        for (int ch = 0; ch < nfc; ch++)
+            canon_split(Af, P.lv[1].ldA, ch * TC_CH, TC_CH, hF.data() + (size_t)ch * 2 * TC_CH * TC_K,
+                        hF.data() + (size_t)ch * 2 * TC_CH * TC_K + TC_CH * TC_K);
+        canon_split(LP, P.ldD, 0, TC_CH, hF.data() + (size_t)nfc * 2 * TC_CH * TC_K, hF.data() + (size_t)nfc * 2 * TC_CH * TC_K + TC_CH * TC_K);
+        destroy();
+        if (e == cudaSuccess) e = cudaMalloc(&dT, hT.size() * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&dGc, hG.size() * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&dF, hF.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(dT, hT.data(), hT.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dGc, hG.data(), hG.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dF, hF.data(), hF.size() * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { err = std::string("tc prepare: ") + cudaGetErrorString(e); return -2; }
+        yc.assign(TC_MAX_MC, 0.f); yf.assign(TC_MAX_MF, 0.f); clp.assign(TC_K, 0.f);
+        for (int j = 0; j < mc; j++) yc[j] = dc[j] - bc[j];
+        for (int j = 0; j < mf; j++) yf[j] = df[j] - bf[j];
+        for (int n = 0; n < TC_K; n++) {
+            double a = 0;
+            for (int k = 0; k < TC_K; k++) a += (double)mu[k] * (double)LP[(size_t)k * P.ldD + n];
+            clp[n] = (float)a;
+        }
+        q.T_hl = dT; q.Gc_hl = dGc; q.F_chunks = dF;
+        q.mc = mc; q.mf = mf; q.n_chunks = nch; q.J = c.subchain[0];
+        q.var_c = (float)c.level[0].lik_var; q.var_f = (float)c.level[1].lik_var;
+        q.prior_logconst = (float)c.prior_logconst;
+        prepared = true;
+        return 0;
+    }
+
+    int run(Params<float>& P, const tda_config& c, long long iterations, int sm_count, cudaStream_t st) {
+        if (!prepared) { int r = prepare(P, c); if (r) return r; }
+        cudaError_t e;
+        e = cudaMemcpyToSymbolAsync(c_yc, yc.data(), TC_MAX_MC * 4, 0, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_yf, yf.data(), TC_MAX_MF * 4, 0, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_lp, clp.data(), TC_K * 4, 0, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { err = std::string("tc constants: ") + cudaGetErrorString(e); return -2; }
+        q.n_pairs = P.Cs / 256;
+        const size_t smem = (size_t)(2 * 64 * TC_K + 2 * TC_MAX_MC * TC_K) * 4 + (size_t)TC_NST * TC_CHUNK_BYTES + 256;
+        e = cudaFuncSetAttribute(da_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { err = std::string("tc attr: ") + cudaGetErrorString(e); return -2; }
+        P.mode = MODE_RUN;
+        P.iterations = iterations;
+        int grid = q.n_pairs < sm_count ? q.n_pairs : sm_count;
+        da_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P, q);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { err = std::string("tc launch: ") + cudaGetErrorString(e); return -2; }
+        return 0;
+    }
 };
 
 }  // namespace tda

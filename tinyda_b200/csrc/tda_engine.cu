@@ -116,8 +116,9 @@ struct EngineT : tda_engine {
         P.am_device_refactor = c.am_device_refactor;
         for (int l = 0; l < TDA_MAX_LEVELS; l++) P.J[l] = c.subchain[l];
         P.C = (int)c.n_chains;
-        n_tiles = (P.C + tda::TC - 1) / tda::TC;
-        Cs = n_tiles * tda::TC;
+        // padded to whole pairs of 128-chain tiles (the tensor-core kernel processes tile pairs)
+        Cs = (P.C + 2 * tda::TC - 1) / (2 * tda::TC) * (2 * tda::TC);
+        n_tiles = Cs / tda::TC;
         P.Cs = Cs; P.n_tiles = n_tiles;
         P.chain_offset = c.chain_offset;
         P.Cg = (c.prop_kind == TDA_PROP_DREAM && c.n_chains_global > 0) ? c.n_chains_global : c.n_chains;
