@@ -155,15 +155,22 @@ inline int tc_gemm_selftest_host(const float* A, const float* B, int N, float* D
 // ---------------------------------------------------------------------------------------------
 // Tensor-core Delayed-Acceptance kernel.
 //
-// One CTA = 2 tiles x 128 chains (thread = chain = TMEM lane) + one MMA-issuing warp + one
-// bulk-copy producer warp.  Per tile, TMEM holds the A operand (hi | lo, 2 x 64 columns) and a
-// 128-column accumulator; all B operands live in shared memory in the canonical K-major
-// no-swizzle layout, pre-split into hi / lo on the host: the proposal factor T and the coarse
-// operator G_c^T stay resident, the fine operator [G_f^T | LP] streams through a ring of
-// 64-column chunks filled by cp.async.bulk.  Row threads and the MMA thread hand jobs back and
-// forth through two mbarriers per tile (req: "A written / D consumed", resp: tcgen05.commit);
-// the two tiles interleave so that one tile's CUDA-core work (Philox, Box-Muller, splits,
-// residual reductions) overlaps the other tile's MMAs.
+// One CTA = 2 tiles x 128 chains.  A chain is a TMEM lane; TWO threads serve each chain (16 row
+// warps: warp w -> tile w/8, column half (w/4)%2, TMEM lane quarter w%4), each owning half of
+// the columns of every row-wise operation (proposal draws, theta', residual sums) so that four
+// row warps per scheduler hide each other's latencies; the two partial sums of a chain meet in
+// shared memory across one named barrier per step, and both threads then take the identical
+// accept decision.  Warp 16 lane 0 issues every tcgen05.mma; warp 17 lane 0 runs the bulk-copy
+// producer.  Per tile, TMEM holds the A operand (hi | lo, 2 x 64 columns) and 128 accumulator
+// columns (one 128-column buffer for the coarse jobs, two 64-column buffers for the streamed
+// fine-operator chunks so that the MMA of chunk c+1 overlaps the residual reduction of chunk c).
+// All B operands live in shared memory in the canonical K-major no-swizzle layout, pre-split
+// into hi / lo on the host: the proposal factor T and the coarse operator G_c^T stay resident,
+// the fine operator [G_f^T | LP] streams through a ring of 64-column chunks filled by
+// cp.async.bulk.  Row warps and the MMA thread hand jobs over through mbarriers (req: "A
+// written / D buffer free", resp: tcgen05.commit); the MMA thread polls both tiles and serves
+// whichever is ready, so one tile's CUDA-core work (Philox, Box-Muller, splits, residual
+// reductions) overlaps the other tile's MMAs.
 //
 // Reference semantics are those of Tile::base_step / Tile::upper_step in tda_kernels.cuh
 // (chain.py:325-444) specialised to pCN + isotropic likelihoods + linear models; the state
@@ -174,8 +181,14 @@ constexpr int TC_CH = 64;                   // columns per streamed chunk
 constexpr int TC_NST = 3;                   // ring stages
 constexpr int TC_MAX_MC = 128;
 constexpr int TC_MAX_MF = 4096;
-constexpr int TC_THREADS = 320;
+constexpr int TC_ROW_WARPS = 16;
+constexpr int TC_MMA_WARP = 16;
+constexpr int TC_PROD_WARP = 17;
+constexpr int TC_THREADS = 32 * 18;
+constexpr int TC_HK = TC_K / 2;             // theta columns per thread
 constexpr int TC_CHUNK_BYTES = TC_CH * TC_K * 4 * 2;   // hi + lo
+constexpr size_t TC_SMEM_BYTES = (size_t)(2 * 64 * TC_K + 2 * TC_MAX_MC * TC_K) * 4 + (size_t)TC_NST * TC_CHUNK_BYTES +
+                                 (size_t)(2 * 2 * 2 * 128 + 2 * 2 * 2 * 128) * 4 + 256;
 
 __constant__ float c_yc[TC_MAX_MC];         // coarse data - offset
 __constant__ float c_yf[TC_MAX_MF];         // fine data - offset
@@ -205,26 +218,54 @@ __device__ __forceinline__ void tc_issue_job(uint32_t d_tmem, uint32_t a_tmem, u
     }
 }
 
+// split 8 fp32 values into tf32 hi / lo and store them as A-operand columns [col, col+8)
+__device__ __forceinline__ void tc_store_split8(uint32_t tA, int col, const float* x) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = __float_as_uint(tc::tf32_hi(x[i]));
+    tc::tmem_st8(tA + col, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = __float_as_uint(x[i] - __uint_as_float(w[i]));
+    tc::tmem_st8(tA + TC_K + col, w);
+}
+
+// hides a pointer's provenance from the optimiser so that the 32 per-column addresses derived
+// from it are recomputed at the use site instead of being hoisted out of the run loop (and spilled)
+template <typename T>
+__device__ __forceinline__ T* tc_opaque(T* ptr) {
+    asm volatile("" : "+l"(ptr));
+    return ptr;
+}
+
+// row warps: "my TMEM writes / reads are done" -> one arrival per warp
+__device__ __forceinline__ void tc_warp_arrive(uint64_t* bar, int lane) {
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(bar);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ DaTcParams q) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sT = reinterpret_cast<float*>(smem);                         // 32 KB (hi | lo)
     float* sGc = sT + 2 * 64 * TC_K;                                    // 64 KB (hi | lo), sized for mc = 128
     unsigned char* ring = reinterpret_cast<unsigned char*>(sGc + 2 * TC_MAX_MC * TC_K);   // NST x 32 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + TC_NST * TC_CHUNK_BYTES);
+    float* s_part = reinterpret_cast<float*>(ring + TC_NST * TC_CHUNK_BYTES);   // [buf 2][tile 2][half 2][128]
+    float* s_pf = s_part + 2 * 2 * 2 * 128;                                      // [tile 2][half 2][val 2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_pf + 2 * 2 * 2 * 128);
     uint64_t* bar_res = bars;            // resident operands landed
-    uint64_t* bar_req = bars + 1;        // [2]
-    uint64_t* bar_resp = bars + 3;       // [2]
-    uint64_t* bar_full = bars + 5;       // [NST]
-    uint64_t* bar_empty = bars + 5 + TC_NST;   // [NST]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5 + 2 * TC_NST);
+    uint64_t* bar_req = bars + 1;        // [tile 2][buffer 2]
+    uint64_t* bar_resp = bars + 5;       // [tile 2][buffer 2]
+    uint64_t* bar_full = bars + 9;       // [NST]
+    uint64_t* bar_empty = bars + 9 + TC_NST;   // [NST]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 9 + 2 * TC_NST);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 8) tc::tmem_alloc(s_tmem, 512);
-    if (tid == 288) {
+    if (warp == TC_MMA_WARP) tc::tmem_alloc(s_tmem, 512);
+    if (tid == TC_PROD_WARP * 32) {
         tc::mbar_init(bar_res, 1);
-        for (int t = 0; t < 2; t++) { tc::mbar_init(bar_req + t, 128); tc::mbar_init(bar_resp + t, 1); }
-        for (int s = 0; s < TC_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 1); }
+        for (int i = 0; i < 4; i++) { tc::mbar_init(bar_req + i, 8); tc::mbar_init(bar_resp + i, 1); }
+        for (int s = 0; s < TC_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 2); }
         tc::fence_mbar_init();
     }
     tc::fence_before_sync();
@@ -235,11 +276,11 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
     const int J = q.J, mc = q.mc, NCH = q.n_chunks;
     const int my_pairs = (q.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const long long iters = p.iterations;
-    const long long total_chunks = (long long)my_pairs * iters * NCH;
 
-    if (warp == 9) {
+    if (warp == TC_PROD_WARP) {
         // ===== producer: resident operands once, then the fine-operator chunk ring =====
         if (lane == 0) {
+            const long long total_chunks = (long long)my_pairs * iters * NCH;
             const uint32_t bT = 2u * 64 * TC_K * 4, bG = 2u * (uint32_t)mc * TC_K * 4;
             tc::mbar_expect_tx(bar_res, bT + bG);
             tc::bulk_g2s(sT, q.T_hl, bT, bar_res);
@@ -255,71 +296,86 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                 tc::bulk_g2s(ring + (size_t)st * TC_CHUNK_BYTES, q.F_chunks + (size_t)c * (TC_CHUNK_BYTES / 4), TC_CHUNK_BYTES, bar_full + st);
             }
         }
-    } else if (warp == 8) {
-        // ===== MMA issuer =====
+    } else if (warp == TC_MMA_WARP) {
+        // ===== MMA issuer: serves whichever tile has its next job ready =====
         if (lane == 0) {
             tc::mbar_wait(bar_res, 0);
-            uint32_t rph[2] = {0, 0};
             const uint32_t sT_hi = tc::smem_u32(sT), sT_lo = sT_hi + 64 * TC_K * 4;
             const uint32_t sG_hi = tc::smem_u32(sGc), sG_lo = sG_hi + TC_MAX_MC * TC_K * 4;
-            long long g = 0;
-            for (int pr = 0; pr < my_pairs; pr++) {
-                for (long long it = 0; it < iters; it++) {
-                    for (int j = 0; j < J; j++) {
-                        for (int t = 0; t < 2; t++) {       // xi = z @ T
-                            tc::mbar_wait(bar_req + t, rph[t]); rph[t] ^= 1;
-                            tc::fence_after_sync();
-                            tc_issue_job(tbase + t * 256 + 128, tbase + t * 256, sT_hi, sT_lo, 64);
-                            tc::mma_commit(bar_resp + t);
-                        }
-                        for (int t = 0; t < 2; t++) {       // F_c = theta' @ G_c^T
-                            tc::mbar_wait(bar_req + t, rph[t]); rph[t] ^= 1;
-                            tc::fence_after_sync();
-                            tc_issue_job(tbase + t * 256 + 128, tbase + t * 256, sG_hi, sG_lo, mc);
-                            tc::mma_commit(bar_resp + t);
-                        }
-                    }
-                    for (int c = 0; c < NCH; c++, g++) {    // fine operator chunks, then the prior chunk
-                        const int st = (int)(g % TC_NST);
-                        tc::mbar_wait(bar_full + st, (uint32_t)((g / TC_NST) & 1));
+            const int JOBS = 2 * J + NCH;
+            const long long total = (long long)my_pairs * iters * JOBS;
+            long long n0 = 0, n1 = 0, g0 = 0, g1 = 0;      // jobs done / chunks consumed per tile
+            int q0 = 0, q1 = 0;                             // position inside the iteration
+            uint32_t rph = 0;                               // bit (t*2+b): parity of req[t][b]
+            while (n0 < total || n1 < total) {
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    long long& n = t ? n1 : n0;
+                    long long& gch = t ? g1 : g0;
+                    int& qq = t ? q1 : q0;
+                    if (n >= total) continue;
+                    const uint32_t tA = tbase + t * 256, tD = tA + 128;
+                    if (qq < 2 * J) {
+                        uint64_t* rq = bar_req + t * 2;
+                        if (!tc::mbar_test(rq, (rph >> (t * 2)) & 1u)) continue;
+                        rph ^= 1u << (t * 2);
+                        tc::fence_after_sync();
+                        if (qq & 1) tc_issue_job(tD, tA, sG_hi, sG_lo, mc);      // F_c = theta' @ G_c^T
+                        else tc_issue_job(tD, tA, sT_hi, sT_lo, 64);            // xi = z @ T
+                        tc::mma_commit(bar_resp + t * 2);
+                    } else {
+                        const int c = qq - 2 * J, b = c & 1;
+                        const int st = (int)(gch % TC_NST);
+                        uint64_t* rq = bar_req + t * 2 + b;
+                        if (!tc::mbar_test(rq, (rph >> (t * 2 + b)) & 1u)) continue;
+                        if (!tc::mbar_test(bar_full + st, (uint32_t)((gch / TC_NST) & 1))) continue;
+                        rph ^= 1u << (t * 2 + b);
+                        tc::fence_after_sync();
                         const uint32_t b_hi = tc::smem_u32(ring + (size_t)st * TC_CHUNK_BYTES), b_lo = b_hi + TC_CH * TC_K * 4;
-                        for (int t = 0; t < 2; t++) {
-                            tc::mbar_wait(bar_req + t, rph[t]); rph[t] ^= 1;
-                            tc::fence_after_sync();
-                            tc_issue_job(tbase + t * 256 + 128, tbase + t * 256, b_hi, b_lo, TC_CH);
-                            tc::mma_commit(bar_resp + t);
-                        }
+                        tc_issue_job(tD + b * TC_CH, tA, b_hi, b_lo, TC_CH);
+                        tc::mma_commit(bar_resp + t * 2 + b);
                         tc::mma_commit(bar_empty + st);
+                        gch++;
                     }
+                    n++;
+                    qq = (qq + 1 == JOBS) ? 0 : qq + 1;
                 }
             }
         }
         __syncwarp();
     } else {
-        // ===== row threads: one chain each =====
-        const int t = warp >> 2;                       // tile within the pair
+        // ===== row threads: two per chain =====
+        const int t = warp >> 3;                       // tile within the pair
+        const int h = (warp >> 2) & 1;                 // column half
         const int wq = warp & 3;                       // TMEM lane quarter
+        const int cl = wq * 32 + lane;                 // chain within the tile
+        const int col0 = h * TC_HK;                    // first theta column of this thread
         const uint32_t tA = tbase + ((uint32_t)(wq * 32) << 16) + t * 256;
         const uint32_t tD = tA + 128;
-        uint64_t* req = bar_req + t;
-        uint64_t* resp = bar_resp + t;
-        uint32_t ph = 0;
+        uint64_t* req = bar_req + t * 2;
+        uint64_t* resp = bar_resp + t * 2;
+        uint32_t ph0 = 0, ph1 = 0;
+        int sbuf = 0;
         const LevelP<float>& l0 = p.lv[0];
         const LevelP<float>& l1 = p.lv[1];
         const float inv2vc = -0.5f / q.var_c, inv2vf = -0.5f / q.var_f;
+        // coarse residual columns of this thread: 16-column groups [gc0, gc1)
+        const int ngc = mc >> 4, gc0 = h ? (ngc + 1) / 2 : 0, gc1 = h ? ngc : (ngc + 1) / 2;
+        const bool inj = p.rng_mode == TDA_RNG_INJECTED;
 
         for (int pr = 0; pr < my_pairs; pr++) {
             const int pair = (int)blockIdx.x + pr * (int)gridDim.x;
-            const int g = pair * 256 + t * 128 + wq * 32 + lane;       // chain slot (padded arrays)
+            const int g = pair * 256 + t * 128 + cl;                   // chain slot (padded arrays)
             const long long gchain = p.chain_offset + g;
-            const bool inj = p.rng_mode == TDA_RNG_INJECTED;
             const bool live = g < p.C;
-            float th[TC_K], tp[TC_K];
+            float th[TC_HK];
 #pragma unroll
-            for (int k = 0; k < TC_K; k++) th[k] = l1.theta[(size_t)k * p.Cs + g];
+            for (int k = 0; k < TC_HK; k++) th[k] = l1.theta[(size_t)(col0 + k) * p.Cs + g];
+            const size_t cs = (size_t)p.Cs;
+            const size_t off0 = (size_t)col0 * cs + g;      // this thread's first column, this chain
             float like_c = l0.like[g], like_cs = like_c, like_f = l1.like[g], prior_f = l1.prior[g];
             long long ucur = p.ucur[g];
-            long long nacc_c = 0, nacc_f = 0;
+            int nacc_c = 0, nacc_f = 0;
             int acc_any = 0;
             const float s = p.scaling[g];
             const float ca = sqrtf(1.0f - s * s), cb = s;
@@ -327,133 +383,125 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
 
             for (long long it = 0; it < iters; it++) {
                 for (int j = 0; j < J; j++) {
-                    // ---- proposal draws -> A (hi | lo) ----
-                    const long long z0 = tb * TC_K;
+                    // ---- proposal draws (this thread's 32 of the 64 normals) -> A (hi | lo) ----
+                    const long long z0 = tb * TC_K + col0;
 #pragma unroll
-                    for (int c0 = 0; c0 < TC_K; c0 += 16) {
-                        uint32_t hi[16], lo[16];
+                    for (int c0 = 0; c0 < TC_HK; c0 += 8) {
+                        float v[8];
 #pragma unroll
-                        for (int b4 = 0; b4 < 4; b4++) {
-                            float v[4];
+                        for (int b4 = 0; b4 < 2; b4++) {
                             if (inj) {
 #pragma unroll
                                 for (int i = 0; i < 4; i++) {
                                     long long idx = z0 + c0 + b4 * 4 + i;
-                                    v[i] = (live && idx < p.zlen) ? p.zs[(size_t)g * p.zlen + idx] : 0.0f;
+                                    v[b4 * 4 + i] = (live && idx < p.zlen) ? p.zs[(size_t)g * p.zlen + idx] : 0.0f;
                                 }
                             } else {
-                                normals4<float>(philox_block(p.seed, gchain, STREAM_Z, (unsigned long long)(z0 >> 2) + (c0 >> 2) + b4), v);
-                            }
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                float h = tc::tf32_hi(v[i]);
-                                hi[b4 * 4 + i] = __float_as_uint(h);
-                                lo[b4 * 4 + i] = __float_as_uint(v[i] - h);
+                                normals4<float>(philox_block(p.seed, gchain, STREAM_Z, (unsigned long long)(z0 >> 2) + (c0 >> 2) + b4), v + b4 * 4);
                             }
                         }
-                        tc::tmem_st16(tA + c0, hi);
-                        tc::tmem_st16(tA + TC_K + c0, lo);
+                        tc_store_split8(tA, col0 + c0, v);
                     }
                     tc::tmem_wait_st();
-                    tc::fence_before_sync();
-                    tc::mbar_arrive(req);
+                    tc_warp_arrive(req, lane);
                     // ---- xi -> theta' -> A ----
-                    tc::mbar_wait(resp, ph); ph ^= 1;
+                    tc::mbar_wait(resp, ph0); ph0 ^= 1;
                     tc::fence_after_sync();
 #pragma unroll
-                    for (int c0 = 0; c0 < TC_K; c0 += 16) {
-                        uint32_t v[16], hi[16], lo[16];
-                        tc::tmem_ld16(tD + c0, v);
+                    for (int c0 = 0; c0 < TC_HK; c0 += 8) {
+                        uint32_t v[8];
+                        float x[8];
+                        tc::tmem_ld8(tD + col0 + c0, v);
                         tc::tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            float x = ca * th[c0 + i] + cb * __uint_as_float(v[i]);
-                            tp[c0 + i] = x;
-                            float h = tc::tf32_hi(x);
-                            hi[i] = __float_as_uint(h);
-                            lo[i] = __float_as_uint(x - h);
-                        }
-                        tc::tmem_st16(tA + c0, hi);
-                        tc::tmem_st16(tA + TC_K + c0, lo);
+                        for (int i = 0; i < 8; i++) x[i] = ca * th[c0 + i] + cb * __uint_as_float(v[i]);
+                        tc_store_split8(tA, col0 + c0, x);
                     }
                     tc::tmem_wait_st();
-                    tc::fence_before_sync();
-                    tc::mbar_arrive(req);
-                    // ---- coarse residual, accept / reject ----
-                    tc::mbar_wait(resp, ph); ph ^= 1;
+                    tc_warp_arrive(req, lane);
+                    // ---- coarse residual (this thread's column groups), accept / reject ----
+                    tc::mbar_wait(resp, ph0); ph0 ^= 1;
                     tc::fence_after_sync();
                     float ssq = 0.0f;
-                    for (int c0 = 0; c0 < mc; c0 += 16) {
+                    for (int gc = gc0; gc < gc1; gc++) {
                         uint32_t v[16];
-                        tc::tmem_ld16(tD + c0, v);
+                        tc::tmem_ld16(tD + gc * 16, v);
                         tc::tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
-                            float r = __uint_as_float(v[i]) - c_yc[c0 + i];
+                            float r = __uint_as_float(v[i]) - c_yc[gc * 16 + i];
                             ssq = fmaf(r, r, ssq);
                         }
                     }
-                    const float like_p = inv2vc * ssq;
+                    float* sp = s_part + ((sbuf * 2 + t) * 2) * 128;
+                    sp[h * 128 + cl] = ssq;
+                    sbuf ^= 1;
+                    tc::named_bar_sync(1 + t, 256);
+                    const float like_p = inv2vc * (sp[cl] + sp[128 + cl]);
                     const float alpha = isnan(like_p) ? 0.0f : expf(like_p - like_c);
                     float u;
                     if (inj) u = (live && ucur < p.ulen) ? p.us[(size_t)g * p.ulen + ucur] : 0.5f;
                     else u = philox_uniform<float>(p.seed, gchain, ucur);
                     ucur++;
-                    if (u < alpha) {
+                    const bool acc = u < alpha;
+                    if (__any_sync(0xffffffffu, acc)) {
+                        // theta' = hi + lo exactly: read it back from the A operand
 #pragma unroll
-                        for (int k = 0; k < TC_K; k++) th[k] = tp[k];
-                        like_c = like_p;
-                        acc_any = 1;
-                        nacc_c++;
+                        for (int c0 = 0; c0 < TC_HK; c0 += 8) {
+                            uint32_t vh[8], vl[8];
+                            tc::tmem_ld8(tA + col0 + c0, vh);
+                            tc::tmem_ld8(tA + TC_K + col0 + c0, vl);
+                            tc::tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                th[c0 + i] = acc ? __uint_as_float(vh[i]) + __uint_as_float(vl[i]) : th[c0 + i];
+                        }
                     }
+                    if (acc) { like_c = like_p; acc_any = 1; nacc_c++; }
                     tb++;
                 }
                 // ---- fine level: A <- current coarse state ----
 #pragma unroll
-                for (int c0 = 0; c0 < TC_K; c0 += 16) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        float h = tc::tf32_hi(th[c0 + i]);
-                        hi[i] = __float_as_uint(h);
-                        lo[i] = __float_as_uint(th[c0 + i] - h);
-                    }
-                    tc::tmem_st16(tA + c0, hi);
-                    tc::tmem_st16(tA + TC_K + c0, lo);
-                }
+                for (int c0 = 0; c0 < TC_HK; c0 += 8) tc_store_split8(tA, col0 + c0, th + c0);
                 tc::tmem_wait_st();
                 tc::fence_before_sync();
-                tc::mbar_arrive(req);
+                __syncwarp();
+                if (lane == 0) { tc::mbar_arrive(req); tc::mbar_arrive(req + 1); }
                 float ssq_f = 0.0f, ssq_p = 0.0f;
                 for (int c = 0; c < NCH; c++) {
-                    tc::mbar_wait(resp, ph); ph ^= 1;
+                    const int b = c & 1;
+                    if (b) { tc::mbar_wait(resp + 1, ph1); ph1 ^= 1; }
+                    else { tc::mbar_wait(resp, ph0); ph0 ^= 1; }
                     tc::fence_after_sync();
+                    uint32_t v0[16], v1[16];
+                    tc::tmem_ld16(tD + b * TC_CH + col0, v0);
+                    tc::tmem_ld16(tD + b * TC_CH + col0 + 16, v1);
+                    tc::tmem_wait_ld();
+                    if (c + 2 < NCH) tc_warp_arrive(req + b, lane);
+                    if (c < NCH - 1) {
 #pragma unroll
-                    for (int c0 = 0; c0 < TC_CH; c0 += 16) {
-                        uint32_t v[16];
-                        tc::tmem_ld16(tD + c0, v);
-                        tc::tmem_wait_ld();
-                        if (c < NCH - 1) {
+                        for (int i = 0; i < 16; i++) {
+                            float r0 = __uint_as_float(v0[i]) - c_yf[c * TC_CH + col0 + i];
+                            float r1 = __uint_as_float(v1[i]) - c_yf[c * TC_CH + col0 + 16 + i];
+                            ssq_f = fmaf(r0, r0, ssq_f);
+                            ssq_f = fmaf(r1, r1, ssq_f);
+                        }
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 16; i++) {
-                                float r = __uint_as_float(v[i]) - c_yf[c * TC_CH + c0 + i];
-                                ssq_f = fmaf(r, r, ssq_f);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; i++) {
-                                float w = __uint_as_float(v[i]) - c_lp[c0 + i];
-                                ssq_p = fmaf(w, w, ssq_p);
-                            }
+                        for (int i = 0; i < 16; i++) {
+                            float w0 = __uint_as_float(v0[i]) - c_lp[col0 + i];
+                            float w1 = __uint_as_float(v1[i]) - c_lp[col0 + 16 + i];
+                            ssq_p = fmaf(w0, w0, ssq_p);
+                            ssq_p = fmaf(w1, w1, ssq_p);
                         }
                     }
-                    if (c < NCH - 1) {
-                        tc::fence_before_sync();
-                        tc::mbar_arrive(req);
-                    }
                 }
-                const float like_fp = inv2vf * ssq_f;
-                const float prior_p = -0.5f * (q.prior_logconst + ssq_p);
+                float* sf = s_pf + (t * 2) * 256;
+                sf[h * 256 + cl] = ssq_f;
+                sf[h * 256 + 128 + cl] = ssq_p;
+                tc::named_bar_sync(1 + t, 256);
+                const float like_fp = inv2vf * (sf[cl] + sf[256 + cl]);
+                const float prior_p = -0.5f * (q.prior_logconst + (sf[128 + cl] + sf[256 + 128 + cl]));
                 int accf = 0;
                 if (acc_any) {
                     const float alpha2 = expf(like_fp - like_f + like_cs - like_c);
@@ -466,42 +514,59 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                 if (accf) {
                     like_f = like_fp; prior_f = prior_p; like_cs = like_c; nacc_f++;
 #pragma unroll
-                    for (int k = 0; k < TC_K; k++) l1.theta[(size_t)k * p.Cs + g] = th[k];
+                    float* dst = tc_opaque(l1.theta + off0);
+#pragma unroll
+                    for (int k = 0; k < TC_HK; k++) dst[k * cs] = th[k];
                 } else {
                     like_c = like_cs;
+                    const float* src = tc_opaque(l1.theta + off0);
 #pragma unroll
-                    for (int k = 0; k < TC_K; k++) th[k] = l1.theta[(size_t)k * p.Cs + g];
+                    for (int k = 0; k < TC_HK; k++) th[k] = src[k * cs];
                 }
                 acc_any = 0;
                 // ---- fine-level record (coalesced: consecutive lanes = consecutive chains) ----
                 const long long r = p.rec[1] + it;
                 if (r < l1.hist_cap) {
                     if (l1.store & TDA_STORE_THETA) {
+                        float* dst = tc_opaque(l1.h_theta + (size_t)r * TC_K * cs + off0);
 #pragma unroll
-                        for (int k = 0; k < TC_K; k++) l1.h_theta[((size_t)r * TC_K + k) * p.Cs + g] = th[k];
+                        for (int k = 0; k < TC_HK; k++) dst[k * cs] = th[k];
                     }
-                    if (l1.store & TDA_STORE_STATS) { l1.h_prior[(size_t)r * p.Cs + g] = prior_f; l1.h_like[(size_t)r * p.Cs + g] = like_f; }
-                    if (l1.store & TDA_STORE_ACCEPT) l1.h_acc[(size_t)r * p.Cs + g] = (uint8_t)accf;
+                    if (h == 0) {
+                        if (l1.store & TDA_STORE_STATS) { l1.h_prior[(size_t)r * p.Cs + g] = prior_f; l1.h_like[(size_t)r * p.Cs + g] = like_f; }
+                        if (l1.store & TDA_STORE_ACCEPT) l1.h_acc[(size_t)r * p.Cs + g] = (uint8_t)accf;
+                    }
                 }
+                {
+                    float* s1 = tc_opaque(p.sum1 + off0);
+                    float* s2 = tc_opaque(p.sum2 + off0);
 #pragma unroll
-                for (int k = 0; k < TC_K; k++) {
-                    p.sum1[(size_t)k * p.Cs + g] += th[k];
-                    p.sum2[(size_t)k * p.Cs + g] += th[k] * th[k];
+                    for (int k = 0; k < TC_HK; k++) {
+                        s1[k * cs] += th[k];
+                        s2[k * cs] += th[k] * th[k];
+                    }
                 }
             }
             // ---- write the chain state back (layout shared with the generic kernel) ----
+            {
+                float* dst = tc_opaque(l0.theta + off0);
 #pragma unroll
-            for (int k = 0; k < TC_K; k++) l0.theta[(size_t)k * p.Cs + g] = th[k];
-            l0.like[g] = like_c; l0.prior[g] = prior_f; l1.like[g] = like_f; l1.prior[g] = prior_f;
-            l0.sv_like[1][g] = like_c; l0.sv_prior[1][g] = prior_f;
-            l0.acc_sub[g] = 0;
-            l0.n_acc[g] += nacc_c; l1.n_acc[g] += nacc_f;
-            p.ucur[g] = ucur;
+                for (int k = 0; k < TC_HK; k++) dst[k * cs] = th[k];
+            }
+            if (h == 0) {
+                l0.like[g] = like_c; l0.prior[g] = prior_f; l1.like[g] = like_f; l1.prior[g] = prior_f;
+                l0.sv_like[1][g] = like_c; l0.sv_prior[1][g] = prior_f;
+                l0.acc_sub[g] = 0;
+                l0.n_acc[g] += nacc_c; l1.n_acc[g] += nacc_f;
+                p.ucur[g] = ucur;
+            }
+            // both halves must have read the pair's scalars before anyone starts the next pair's
+            // loads only matters for p.ucur / like arrays of THIS pair, which are per chain: no hazard
         }
         tc::fence_before_sync();
     }
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tbase, 512);
+    if (warp == TC_MMA_WARP) tc::tmem_dealloc(tbase, 512);
 }
 
 template <typename R>
@@ -609,7 +674,7 @@ struct DaTcState<float> {
         if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_lp, clp.data(), TC_K * 4, 0, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) { err = std::string("tc constants: ") + cudaGetErrorString(e); return -2; }
         q.n_pairs = P.Cs / 256;
-        const size_t smem = (size_t)(2 * 64 * TC_K + 2 * TC_MAX_MC * TC_K) * 4 + (size_t)TC_NST * TC_CHUNK_BYTES + 256;
+        const size_t smem = TC_SMEM_BYTES;
         e = cudaFuncSetAttribute(da_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { err = std::string("tc attr: ") + cudaGetErrorString(e); return -2; }
         P.mode = MODE_RUN;
