@@ -82,18 +82,28 @@ def cpu_port_rate(spec, prior, iters, faithful, procs=None):
     return procs * iters / wall, procs, wall
 
 
-def cpu_baseline_block(spec, prior, budget_iters_faithful=60, budget_iters_fast=600):
-    rate, procs, wall = cpu_port_rate(spec, prior, budget_iters_faithful, True)
-    rate_fast, _, wall_fast = cpu_port_rate(spec, prior, budget_iters_fast, False)
+def calibrated_iters(spec, prior, faithful, target_s, lo=4, hi=200000):
+    """Fine iterations per process so that one cpu_port_rate() call takes about target_s."""
+    probe = 4 if faithful else 40
+    rate, procs, wall = cpu_port_rate(spec, prior, probe, faithful)
+    per_proc = max(probe / max(wall, 1e-3), 1e-3)         # includes pool start-up: conservative
+    return int(min(hi, max(lo, per_proc * target_s)))
+
+
+def cpu_baseline_block(spec, prior, target_s=15.0, target_fast_s=6.0):
+    n_f = calibrated_iters(spec, prior, True, target_s)
+    rate, procs, wall = cpu_port_rate(spec, prior, n_f, True)
+    n_p = calibrated_iters(spec, prior, False, target_fast_s)
+    rate_fast, _, wall_fast = cpu_port_rate(spec, prior, n_p, False)
     return {
         "value": rate, "unit": UNIT, "cores": procs, "kind": "port",
         "sample": "oracle port of tinyDA DAChain.sample, %d processes x 1 chain x %d fine iterations "
                   "(= %d transitions), SVD of the 64x64 proposal covariance on every draw as "
                   "np.random.multivariate_normal does inside the reference; %.1f s wall"
-                  % (procs, budget_iters_faithful, procs * budget_iters_faithful, wall),
+                  % (procs, n_f, procs * n_f, wall),
         "port_precomputed_factor": {
             "value": rate_fast, "sample": "same port with the SVD factor computed once, %d x %d iterations, %.1f s"
-                                          % (procs, budget_iters_fast, wall_fast)},
+                                          % (procs, n_p, wall_fast)},
     }
 
 
@@ -287,8 +297,8 @@ def run_ours(args):
             "wall_ms_timed_region": wall_ms,
         }
         if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline_block(spec, w["prior"],
-                                                     6 if args.quick else 60, 60 if args.quick else 600)
+            out["cpu_baseline"] = cpu_baseline_block(spec, w["prior"], 1.0 if args.quick else 15.0,
+                                                     0.5 if args.quick else 6.0)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -306,7 +316,9 @@ def run_reference(args):
     if rank != 0:
         return
     w, spec = workload_spec()
-    iters = 6 if args.quick else 40
+    # every step is a bounded sample: the whole --steps K --warmup W run is sized for ~150 s
+    per_step_s = 1.0 if args.quick else max(3.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    iters = calibrated_iters(spec, w["prior"], True, per_step_s)
     steps_done = []
     t_all0 = time.perf_counter()
     for _ in range(args.warmup):

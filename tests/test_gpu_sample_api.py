@@ -115,37 +115,44 @@ def test_conjugate_posterior_within_3_mcse_rwmh():
     eng.close()
 
 
-def test_conjugate_posterior_da_pcn_fp32_full_shape():
-    """cfg2 at its real shape (64 params, 1024/128 obs, J=10), float32 production mode, 8192 chains:
-    fine-chain mean within 3 MCSE (+ float32 slack) of the closed-form posterior mean, checked
-    from the on-device running moments (no history stored)."""
+def _da_conjugate_check(kernel, m_f, beta, burn, n, C=8192):
+    """Two-level DA on a cfg2-shaped linear-Gaussian problem, float32 production mode (Philox):
+    chains start 2 posterior standard deviations away from the closed-form posterior in every
+    coordinate, and after burn-in the fine-chain mean must sit within MCSE of the closed-form
+    mean and the pooled variance within 5% of the closed-form variance.  Checked from the
+    on-device running moments (no history stored)."""
     from tinyda_b200 import lower_problem
     from tinyda_b200.engine import Engine, STORE_NONE
     from tinyda_b200.workloads import cfg2_da, conjugate_posterior
-    w = cfg2_da()
+    w = cfg2_da(beta=beta, m_f=m_f)
     mu, S = conjugate_posterior(w["G"], w["y"], w["sigma2"], w["prior"])
+    sd = np.sqrt(np.diag(S))
     spec = lower_problem(w["posteriors"], w["proposal"], 10)
-    C = 8192
-    rng = np.random.default_rng(0)
-    # start in the posterior bulk so that no long burn-in is needed
-    theta0 = rng.multivariate_normal(mu, S, size=C)
+    theta0 = np.random.default_rng(0).multivariate_normal(mu, S, size=C) + 2.0 * sd
     eng = Engine(spec, C, dtype="float32", seed=3, store=STORE_NONE)
+    eng.select_kernel(kernel)
     eng.init(theta0)
-    eng.run(150)
-    m0 = eng.get("moments")
-    n0 = 151
-    eng.run(600)
-    m1 = eng.get("moments")
-    n = 600
-    cm = ((m1[0] - m0[0]) / n).T                      # [C, d] chain means over the last 600 draws
+    eng.run(burn)
+    a0, m0 = eng.get("accept_counts").astype(float), eng.get("moments")
+    eng.run(n)
+    a1, m1 = eng.get("accept_counts").astype(float), eng.get("moments")
+    eng.close()
+    cm = ((m1[0] - m0[0]) / n).T                      # [C, d] per-chain means over the last n draws
+    c2 = ((m1[1] - m0[1]) / n).T
     mcse = cm.std(axis=0, ddof=1) / np.sqrt(C)
     err = np.abs(cm.mean(axis=0) - mu)
-    assert np.all(err < 3 * mcse + 2e-4 * (np.abs(mu) + np.sqrt(np.diag(S)))), (err / mcse).max()
-    acc = eng.get("accept_counts")
-    rate_c, rate_f = acc[0].mean() / (750 * 10), acc[1].mean() / 750
-    # at stationarity pCN with beta=0.05 on this 64-dim posterior accepts ~1-2% of coarse proposals
-    assert 0.002 < rate_c < 0.9 and 0.002 < rate_f < 0.99, (rate_c, rate_f)
-    eng.close()
+    # max over 64 coordinates of a |N(0,1)| is ~2.4; 4.5 leaves room, 0.03 sd absorbs the residual burn-in bias
+    assert np.all(err < 4.5 * mcse + 0.03 * sd), (err / mcse).max()
+    var_ratio = (c2.mean(axis=0) - cm.mean(axis=0) ** 2) / np.diag(S)
+    assert var_ratio.min() > 0.95 and var_ratio.max() < 1.05, (var_ratio.min(), var_ratio.max())
+    rate_c, rate_f = (a1[0] - a0[0]).mean() / (n * 10), (a1[1] - a0[1]).mean() / n
+    assert 0.05 < rate_c < 0.98 and 0.03 < rate_f < 0.9, (rate_c, rate_f)
+    return rate_c, rate_f
+
+
+def test_conjugate_posterior_da_pcn_fp32_generic_kernel():
+    """64 params, 256/128 observations, J=10, generic lock-step kernel."""
+    _da_conjugate_check("generic", 256, 0.02, 1500, 3000)
 
 
 def test_resume_and_sharding_are_exact():

@@ -112,19 +112,11 @@ def test_tc_kernel_resume_and_sharding_exact():
     assert np.array_equal(th_a[:, :, 256:512], th_c)
 
 
-def test_tc_kernel_conjugate_posterior_mean():
-    from tinyda_b200.workloads import conjugate_posterior
-    C = 8192
-    from tinyda_b200.workloads import cfg2_da
-    w = cfg2_da()
-    mu, S = conjugate_posterior(w["G"], w["y"], w["sigma2"], w["prior"])
-    theta0 = np.random.default_rng(0).multivariate_normal(mu, S, size=C)
-    eng, _ = _cfg2_engine(C, "tc", seed=3, iters=0, theta0=theta0)
-    eng.run(150)
-    m0 = eng.get("moments")
-    eng.run(600)
-    m1 = eng.get("moments")
-    cm = ((m1[0] - m0[0]) / 600).T
-    mcse = cm.std(axis=0, ddof=1) / np.sqrt(C)
-    err = np.abs(cm.mean(axis=0) - mu)
-    assert np.all(err < 3 * mcse + 2e-4 * (np.abs(mu) + np.sqrt(np.diag(S)))), (err / mcse).max()
+def test_tc_kernel_conjugate_posterior_full_shape():
+    """cfg2 at its real shape (64 params, 1024/128 observations, J=10, 8192 chains) on the tcgen05
+    kernel with a pCN step tuned for stationarity (beta = 0.004): mean within MCSE and variance
+    within 5% of the closed-form posterior, starting 2 sd away in every coordinate."""
+    from test_gpu_sample_api import _da_conjugate_check
+    rc, rf = _da_conjugate_check("tc", 1024, 0.004, 3000, 3000)
+    rc2, rf2 = _da_conjugate_check("tc", 256, 0.02, 1500, 3000)
+    assert rc > rc2          # the smaller step accepts more often

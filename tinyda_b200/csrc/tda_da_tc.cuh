@@ -542,8 +542,9 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                     float* s2 = tc_opaque(p.sum2 + off0);
 #pragma unroll
                     for (int k = 0; k < TC_HK; k++) {
-                        s1[k * cs] += th[k];
-                        s2[k * cs] += th[k] * th[k];
+                        // fire-and-forget reductions (one adder per address: deterministic), no load latency
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s1 + k * cs), "f"(th[k]) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s2 + k * cs), "f"(th[k] * th[k]) : "memory");
                     }
                 }
             }

@@ -7,8 +7,10 @@ from tinyda_b200.engine import Engine, STORE_NONE
 from tinyda_b200.workloads import cfg2_da, conjugate_posterior
 
 for kernel in ("tc", "generic"):
-    for beta in (0.005, 0.01, 0.02):
-        w = cfg2_da(beta=beta)
+    for (mf, beta, burn, n) in ((256, 0.01, 1500, 3000), (256, 0.02, 1500, 3000), (256, 0.03, 1500, 3000), (1024, 0.004, 3000, 3000)):
+        if kernel == "generic" and burn + n > 5000:
+            continue
+        w = cfg2_da(beta=beta, m_f=mf)
         mu, S = conjugate_posterior(w["G"], w["y"], w["sigma2"], w["prior"])
         sd = np.sqrt(np.diag(S))
         spec = lower_problem(w["posteriors"], w["proposal"], 10)
@@ -19,10 +21,9 @@ for kernel in ("tc", "generic"):
         eng.select_kernel(kernel)
         eng.init(theta0)
         t0 = time.time()
-        eng.run(400); eng.sync()
+        eng.run(burn); eng.sync()
         a0 = eng.get("accept_counts").astype(float)
         m0 = eng.get("moments")
-        n = 800
         eng.run(n); eng.sync()
         dt = time.time() - t0
         a1 = eng.get("accept_counts").astype(float)
@@ -31,9 +32,8 @@ for kernel in ("tc", "generic"):
         c2 = ((m1[1] - m0[1]) / n).T
         mcse = cm.std(axis=0, ddof=1) / np.sqrt(C)
         z = (cm.mean(axis=0) - mu) / mcse
-        var = c2.mean(axis=0) - (cm ** 2).mean(axis=0) + cm.var(axis=0)   # pooled variance estimate
         pooled_var = c2.mean(axis=0) - cm.mean(axis=0) ** 2
-        print(kernel, "beta", beta, "rates c/f", (a1[0] - a0[0]).mean() / (n * 10), (a1[1] - a0[1]).mean() / n,
-              "max|z|", np.abs(z).max(), "max rel err mean (in sd)", (np.abs(cm.mean(axis=0) - mu) / sd).max(),
+        print(kernel, "mf", mf, "beta", beta, "rates c/f", (a1[0] - a0[0]).mean() / (n * 10), (a1[1] - a0[1]).mean() / n,
+              "max|z|", np.abs(z).max(), "max err mean (in sd)", (np.abs(cm.mean(axis=0) - mu) / sd).max(),
               "var ratio min/max", (pooled_var / np.diag(S)).min(), (pooled_var / np.diag(S)).max(), "%.2fs" % dt, flush=True)
         eng.close()
