@@ -446,8 +446,11 @@ struct EngineT : tda_engine {
         if (bytes) *bytes = need;
         if (dst_bytes < need) return fail(-1, "fetch: destination too small");
         if (rows == 0) return 0;
-        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)P.C * esz, src, (size_t)Cs * esz, (size_t)P.C * esz, rows,
-                                   cudaMemcpyDeviceToHost, st));
+        if (P.C == Cs)
+            CUDA_TRY(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, st));
+        else
+            CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)P.C * esz, src, (size_t)Cs * esz, (size_t)P.C * esz, rows,
+                                       cudaMemcpyDeviceToHost, st));
         return 0;
     }
 

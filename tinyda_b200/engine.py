@@ -147,8 +147,9 @@ class Engine:
         a = np.ascontiguousarray(arr, dtype=np.float64)
         check(lib.tda_upload(self._h, what, level, _dptr(a), a.size))
 
-    def _stream_ptr(self):
-        return C.c_void_p(self.stream) if self.stream else C.c_void_p(0)
+    def _stream_ptr(self, stream=None):
+        st = self.stream if stream is None else stream
+        return C.c_void_p(st) if st else C.c_void_p(0)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -170,12 +171,14 @@ class Engine:
         check(lib.tda_engine_init(self._h, self._stream_ptr()))
         self.iterations_done = 0
 
-    def run(self, iterations):
-        check(lib.tda_engine_run(self._h, int(iterations), self._stream_ptr()))
+    def run(self, iterations, stream=None):
+        """Advances every chain by `iterations` finest-level iterations; asynchronous on the CUDA
+        stream (raw handle) given here or at construction."""
+        check(lib.tda_engine_run(self._h, int(iterations), self._stream_ptr(stream)))
         self.iterations_done += int(iterations)
 
-    def sync(self):
-        check(lib.tda_engine_sync(self._h, self._stream_ptr()))
+    def sync(self, stream=None):
+        check(lib.tda_engine_sync(self._h, self._stream_ptr(stream)))
 
     def select_kernel(self, which):
         check(lib.tda_select_kernel(self._h, {"auto": 0, "generic": 1, "tc": 2}[which]))
@@ -189,9 +192,10 @@ class Engine:
         return out
 
     # ---- fetch ---------------------------------------------------------------------------------
-    def fetch(self, level, field, rec0=0, nrec=None, out=None):
+    def fetch(self, level, field, rec0=0, nrec=None, out=None, stream=None, sync=True):
         """History of one level in the device layout: theta [nrec, d, C], prior/like [nrec, C],
-        output [nrec, m, C], accept [nrec, C] (uint8)."""
+        output [nrec, m, C], accept [nrec, C] (uint8).  With sync=False the copy is only enqueued
+        on `stream` (pinned `out` required for it to be asynchronous)."""
         if nrec is None:
             nrec = int(self.n_records()[level]) - rec0
         m = int(self.spec["levels"][level]["model"]["m"])
@@ -206,8 +210,9 @@ class Engine:
             out = np.empty(shape, dtype=dt)
         nb = C.c_size_t(0)
         check(lib.tda_fetch(self._h, level, fid, int(rec0), int(nrec), out.ctypes.data_as(C.c_void_p),
-                            out.nbytes, C.byref(nb), self._stream_ptr()))
-        self.sync()
+                            out.nbytes, C.byref(nb), self._stream_ptr(stream)))
+        if sync:
+            self.sync(stream)
         return out
 
     def get(self, what, level=0):
