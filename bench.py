@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tc"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tc", "tc16"])
     ap.add_argument("--chains", type=int, default=N_CHAINS_PER_GPU)
     ap.add_argument("--iters", type=int, default=ITERS_PER_STEP)
     ap.add_argument("--no-cpu", action="store_true")

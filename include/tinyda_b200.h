@@ -159,6 +159,8 @@ typedef struct tda_config {
 #define TDA_G_THETA 6           /* level: current state [n_chains][d]               */
 #define TDA_G_NRECORDS 7        /* int64 [n_levels] records written so far          */
 #define TDA_G_MOMENTS 8         /* finest level running sums: [2][d][n_chains] (sum x, sum x^2) */
+#define TDA_G_ZROUND 9          /* set only: one float64 flag; non-zero = Philox normals on the fp16 grid
+                                 * ("z16" stream) also for the generic / 3xTF32 kernels (float32 engine) */
 
 typedef struct tda_engine tda_engine;
 
@@ -199,8 +201,11 @@ int tda_fill_streams(tda_engine *e, double *z, int64_t nz, double *u, int64_t nu
 int tda_history_reset(tda_engine *e);
 
 /* Kernel selection for tda_engine_run: 0 = automatic, 1 = generic lock-step kernel,
- * 2 = tcgen05 tensor-core Delayed-Acceptance kernel (fails if the configuration is not
- * supported by it). */
+ * 2 = tcgen05 tensor-core Delayed-Acceptance kernel with 3xTF32 operands, 3 = tcgen05
+ * Delayed-Acceptance kernel with two-term fp16-split operands and normals produced by dedicated
+ * warps (2 and 3 fail if the configuration is not supported).  Kernel 3 consumes the "z16"
+ * Philox normal stream (normals rounded to the fp16 grid at scale 4096); tda_fill_streams
+ * exports whatever stream the selected kernel consumes. */
 int tda_select_kernel(tda_engine *e, int which);
 
 /* Diagnostic: D[128][N] = A[128][64] @ B[64][N] (row-major float32 host arrays) computed by one
@@ -208,6 +213,11 @@ int tda_select_kernel(tda_engine *e, int which);
  * (A operand in TMEM when a_in_tmem != 0, else in shared memory; B K-major in shared memory;
  * 3xTF32 split when split != 0, a single TF32 pass on B otherwise).  N: multiple of 8, <= 256. */
 int tda_tc_gemm_selftest(const float *A, const float *B, int N, float *D, int a_in_tmem, int split);
+
+/* Same diagnostic for the fp16-split conventions of kernel 3 (kind::f16 MMAs, two-term split of
+ * both operands at power-of-two scales, A packed in TMEM or canonical in shared memory).
+ * N: multiple of 16, <= 256. */
+int tda_tc16_gemm_selftest(const float *A, const float *B, int N, float *D, int a_in_tmem);
 
 /* Kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t tda_launch_count(void);

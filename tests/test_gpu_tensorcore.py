@@ -35,7 +35,38 @@ def test_tf32x3_gemm_matches_fp64(a_in_tmem, N):
     assert err1 < 5e-3 * scale and err1 > 5 * err
 
 
-# ---- tensor-core Delayed-Acceptance kernel ---------------------------------------------------
+def _gemm16(A, B, a_in_tmem):
+    from tinyda_b200._lib import lib, check
+    N = B.shape[1]
+    D = np.zeros((128, N), dtype=np.float32)
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    check(lib.tda_tc16_gemm_selftest(A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), N,
+                                     D.ctypes.data_as(C.c_void_p), a_in_tmem))
+    return D
+
+
+@pytest.mark.parametrize("a_in_tmem", [1, 0])
+@pytest.mark.parametrize("N", [64, 128, 16, 256])
+def test_fp16_split_gemm_matches_fp64(a_in_tmem, N):
+    """kind::f16 MMAs on two-term fp16 splits at power-of-two scales: fp32-grade accuracy, with the
+    A operand packed in TMEM (theta) or canonical in shared memory (the normals)."""
+    rng = np.random.default_rng(100 + N + a_in_tmem)
+    A = rng.standard_normal((128, 64)).astype(np.float32)
+    A[:, 3] *= 1e-3                                  # a column far below the matrix scale
+    B = (rng.standard_normal((64, N)) / 8).astype(np.float32)
+    B[5, :] *= 1e-4
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    D = _gemm16(A, B, a_in_tmem)
+    err = np.abs(D - ref).max()
+    scale = np.abs(ref).max()
+    assert err < 2e-6 * scale + 1e-6, (err, scale)
+
+
+# ---- tensor-core Delayed-Acceptance kernels --------------------------------------------------
+KERNELS = ["tc", "tc16"]
+
+
 def _cfg2_engine(C, kernel, seed=9, rng="philox", streams=None, iters=30, theta0=None, chain_offset=0):
     from tinyda_b200 import lower_problem
     from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
@@ -51,15 +82,16 @@ def _cfg2_engine(C, kernel, seed=9, rng="philox", streams=None, iters=30, theta0
     return eng, w
 
 
-def test_tc_kernel_matches_reference_trajectory_until_near_tie():
-    """cfg2 golden fixture (unmodified reference, injected streams) vs the tcgen05 kernel."""
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_tc_kernel_matches_reference_trajectory_until_near_tie(kernel):
+    """cfg2 golden fixture (unmodified reference, injected streams) vs the tcgen05 kernels."""
     import golden_io
     from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
     g = golden_io.load("da_pcn_cfg2")
     C, iters = g["theta0"].shape[0], g["iterations"]
     eng = Engine(g["spec"], C, dtype="float32", rng="injected", streams=(g["z"], g["u"]),
                  store=[STORE_NONE, STORE_STATS], capacity_iterations=iters)
-    eng.select_kernel("tc")
+    eng.select_kernel(kernel)
     eng.init(g["theta0"])
     eng.run(iters)
     acc = eng.fetch(1, "accept").T.astype(bool)
@@ -76,10 +108,13 @@ def test_tc_kernel_matches_reference_trajectory_until_near_tie():
         np.testing.assert_allclose(lk[c, :k], ref["like"][c, :k], rtol=2e-4, atol=2e-2)
 
 
-def test_tc_kernel_agrees_with_generic_fp32_kernel():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_tc_kernel_agrees_with_generic_fp32_kernel(kernel):
     C, iters = 512, 30
-    a, _ = _cfg2_engine(C, "tc", iters=iters)
+    a, _ = _cfg2_engine(C, kernel, iters=iters)
     b, _ = _cfg2_engine(C, "generic", iters=iters)
+    if kernel == "tc16":
+        b.set_z_round(True)            # same normal stream (fp16 grid) for the generic kernel
     a.run(iters)
     b.run(iters)
     acc_a, acc_b = a.fetch(1, "accept"), b.fetch(1, "accept")
@@ -96,12 +131,13 @@ def test_tc_kernel_agrees_with_generic_fp32_kernel():
     assert abs(ca[0].mean() - cb[0].mean()) < 0.05 * cb[0].mean() + 1
 
 
-def test_tc_kernel_resume_and_sharding_exact():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_tc_kernel_resume_and_sharding_exact(kernel):
     C = 512
     def run(lo, hi, splits):
         from tinyda_b200.workloads import cfg2_da
         theta0 = cfg2_da()["prior"].rvs(C, random_state=np.random.default_rng(1))
-        eng, _ = _cfg2_engine(hi - lo, "tc", iters=sum(splits), theta0=theta0[lo:hi], chain_offset=lo)
+        eng, _ = _cfg2_engine(hi - lo, kernel, iters=sum(splits), theta0=theta0[lo:hi], chain_offset=lo)
         for s in splits:
             eng.run(s)
         return eng.fetch(1, "theta"), eng.fetch(1, "like")
@@ -112,11 +148,40 @@ def test_tc_kernel_resume_and_sharding_exact():
     assert np.array_equal(th_a[:, :, 256:512], th_c)
 
 
-def test_tc_kernel_conjugate_posterior_full_shape():
+def test_tc16_philox_streams_fed_to_the_oracle():
+    """Production mode of the fp16-split kernel: its z16 / uniform streams exported with
+    tda_fill_streams and fed to the CPU oracle reproduce the accept decisions and (to float32
+    accuracy) the states, chain by chain until the first near-tie."""
+    from oracle import tinyda_oracle as orc
+    C, iters = 64, 12
+    eng, w = _cfg2_engine(C, "tc16", iters=iters, chain_offset=7)
+    theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1))
+    eng.run(iters)
+    z, u = eng.fill_streams(iters * 10 * 64, iters * 11)
+    zh = (z * 4096).astype(np.float16).astype(np.float64) / 4096
+    assert np.array_equal(zh, z)                                  # the stream lies on the fp16 grid
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+    from tinyda_b200 import lower_problem
+    spec = lower_problem(w["posteriors"], w["proposal"], 10)
+    out, _ = orc.run_chains(spec, theta0, z, u, iters)
+    acc = eng.fetch(1, "accept").T.astype(bool)
+    th = np.transpose(eng.fetch(1, "theta"), (2, 0, 1)).astype(np.float64)
+    ref_acc, ref_th = out[1]["acc"], out[1]["theta"]
+    assert acc.shape == ref_acc.shape
+    diff = acc != ref_acc
+    assert diff.mean() < 0.02, diff.mean()
+    ok = ~diff.any(axis=1)
+    assert ok.mean() > 0.7
+    scale = np.abs(ref_th).max()
+    assert np.abs(th[ok] - ref_th[ok]).max() < 2e-4 * scale
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_tc_kernel_conjugate_posterior_full_shape(kernel):
     """cfg2 at its real shape (64 params, 1024/128 observations, J=10, 8192 chains) on the tcgen05
     kernel with a pCN step tuned for stationarity (beta = 0.004): mean within MCSE and variance
     within 5% of the closed-form posterior, starting 2 sd away in every coordinate."""
     from test_gpu_sample_api import _da_conjugate_check
-    rc, rf = _da_conjugate_check("tc", 1024, 0.004, 3000, 3000)
-    rc2, rf2 = _da_conjugate_check("tc", 256, 0.02, 1500, 3000)
+    rc, rf = _da_conjugate_check(kernel, 1024, 0.004, 3000, 3000)
+    rc2, rf2 = _da_conjugate_check(kernel, 256, 0.02, 1500, 3000)
     assert rc > rc2          # the smaller step accepts more often

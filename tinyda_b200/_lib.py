@@ -21,14 +21,14 @@ TDA_STORE_THETA, TDA_STORE_STATS, TDA_STORE_OUTPUT, TDA_STORE_ACCEPT = 1, 2, 4, 
  TDA_UP_STREAM_U, TDA_UP_DREAM_ARCHIVE0, TDA_UP_AM_FACTORS) = range(1, 16)
 TDA_F_THETA, TDA_F_PRIOR, TDA_F_LIKE, TDA_F_OUTPUT, TDA_F_ACCEPT = 1, 2, 3, 4, 5
 (TDA_G_SCALING, TDA_G_ACCEPT_COUNTS, TDA_G_CURSORS, TDA_G_AM_SIGMA, TDA_G_AM_MU, TDA_G_THETA,
- TDA_G_NRECORDS, TDA_G_MOMENTS) = range(1, 9)
+ TDA_G_NRECORDS, TDA_G_MOMENTS, TDA_G_ZROUND) = range(1, 10)
 TDA_BUF_DREAM_ARCHIVE, TDA_BUF_HIST_THETA = 1, 2
 
 EXPORTS = [
     "tda_abi_version", "tda_last_error", "tda_engine_create", "tda_engine_destroy", "tda_upload",
     "tda_engine_init", "tda_engine_run", "tda_engine_sync", "tda_fetch", "tda_get", "tda_set",
     "tda_device_buffer", "tda_dream_slots", "tda_fill_streams", "tda_history_reset",
-    "tda_select_kernel", "tda_launch_count", "tda_tc_gemm_selftest",
+    "tda_select_kernel", "tda_launch_count", "tda_tc_gemm_selftest", "tda_tc16_gemm_selftest",
 ]
 
 
@@ -82,6 +82,7 @@ def _load():
     lib.tda_history_reset.argtypes = [vp]
     lib.tda_select_kernel.argtypes = [vp, i32]
     lib.tda_tc_gemm_selftest.argtypes = [vp, vp, i32, vp, i32, i32]
+    lib.tda_tc16_gemm_selftest.argtypes = [vp, vp, i32, vp, i32]
     for name in EXPORTS:
         if getattr(lib, name).restype is C.c_int and name not in ("tda_abi_version",):
             getattr(lib, name).restype = i32

@@ -67,6 +67,7 @@ struct LevelP {
 template <typename R>
 struct Params {
     int mode, L, d, aem, rng_mode, prop_kind, adaptive, period, am_t0, am_device_refactor;
+    int z_round;               // Philox normals on the fp16 grid ("z16" stream, float engine)
     int J[MAXL];
     int C, Cs, n_tiles;
     long long chain_offset, Cg, arch_off;   // arch_off: first archive column owned by this engine
@@ -125,11 +126,16 @@ __device__ __forceinline__ bool tisnan(float x) { return isnan(x); }
 __device__ __forceinline__ bool tisnan(double x) { return isnan(x); }
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: random access by draw index --------
-__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+// 32 x 32 -> 64-bit product split into halves: one IMAD.WIDE on the device
+__host__ __device__ __forceinline__ void mulwide32(uint32_t a, uint32_t m, uint32_t& hi, uint32_t& lo) {
 #ifdef __CUDA_ARCH__
-    return __umulhi(a, b);
+    uint64_t p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(m));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
 #else
-    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+    const uint64_t p = (uint64_t)a * (uint64_t)m;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
 #endif
 }
 
@@ -137,8 +143,9 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int i = 0; i < 10; i++) {
-        uint32_t hi0 = mulhi32(M0, ctr.x), lo0 = M0 * ctr.x;
-        uint32_t hi1 = mulhi32(M1, ctr.z), lo1 = M1 * ctr.z;
+        uint32_t hi0, lo0, hi1, lo1;
+        mulwide32(ctr.x, M0, hi0, lo0);
+        mulwide32(ctr.z, M1, hi1, lo1);
         ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
         key.x += W0;
         key.y += W1;
@@ -177,32 +184,67 @@ __device__ __forceinline__ void normals4(uint4 b, R out[4]) {
 }
 
 // float engine: Box-Muller on the special-function unit (lg2 / sqrt / sin / cos .approx, absolute
-// error ~1e-6 on a N(0,1) variate, far below float32 MCMC noise) -- 7 instructions per normal
-// instead of ~45 for the correctly-rounded logf / sincospif versions.  This IS the definition of
-// the float engine's normal stream: every kernel and tda_fill_streams go through this function.
+// error ~1e-6 on a N(0,1) variate, far below float32 MCMC noise).  Both uniforms are built from the
+// low 23 bits of a Philox word with one logic op (no int->float conversion): f = 1.mantissa in
+// [1, 2); radius uniform u = 2 - f in (0, 1], angle = (f - 1.5) * 2 pi in [-pi, pi).
+// This IS the definition of the float engine's normal stream: every kernel and tda_fill_streams go
+// through bm_pair().
 __device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+constexpr float BM_C_PLAIN = -1.3862943611198906f;                 // -2 ln 2        -> r
+constexpr float BM_C_X4096 = -1.3862943611198906f * 16777216.0f;   // -2 ln 2 * 2^24 -> 4096 r
+constexpr float Z16_SCALE = 4096.0f, Z16_UNSCALE = 1.0f / 4096.0f;
+
+// two normals (times sqrt(c / (-2 ln 2))) from two Philox words
+__device__ __forceinline__ void bm_pair(uint32_t w_radius, uint32_t w_angle, float c, float& n0, float& n1) {
+    const float f = __uint_as_float((w_radius & 0x007FFFFFu) | 0x3F800000u);
+    const float g = __uint_as_float((w_angle & 0x007FFFFFu) | 0x3F800000u);
+    const float r = mufu_sqrt(c * mufu_lg2(2.0f - f));
+    const float a = fmaf(g, 6.283185307179586f, -9.42477796076938f);
+    n0 = r * mufu_cos(a);
+    n1 = r * mufu_sin(a);
+}
+
 template <>
 __device__ __forceinline__ void normals4<float>(uint4 b, float out[4]) {
-    const float TWO_PI_24 = 6.283185307179586f * 5.9604644775390625e-08f;   // 2 pi / 2^24
-    const float A0 = -3.141592653589793f + 0.5f * TWO_PI_24;                // angle in (-pi, pi)
-    float r0 = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u01<float>(b.x)));  // sqrt(-2 ln u)
-    float r1 = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u01<float>(b.z)));
-    float a0 = fmaf((float)(b.y >> 8), TWO_PI_24, A0);
-    float a1 = fmaf((float)(b.w >> 8), TWO_PI_24, A0);
-    out[0] = r0 * mufu_cos(a0);
-    out[1] = r0 * mufu_sin(a0);
-    out[2] = r1 * mufu_cos(a1);
-    out[3] = r1 * mufu_sin(a1);
+    bm_pair(b.x, b.y, BM_C_PLAIN, out[0], out[1]);
+    bm_pair(b.z, b.w, BM_C_PLAIN, out[2], out[3]);
+}
+
+// "z16" normal stream of the float engine (used by the fp16-split tensor-core kernel and by every
+// other kernel / tda_fill_streams when Params::z_round is set): the normal is generated at scale
+// 4096, rounded to the nearest fp16 and scaled back, i.e. it lies on an 11-bit-mantissa grid so
+// that it is ONE exact fp16 tensor-core operand (rounding is unbiased, relative step 2^-11).
+__device__ __forceinline__ float z16_round(float scaled) {
+    unsigned short h;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(scaled));
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+    return f * Z16_UNSCALE;
+}
+__device__ __forceinline__ void normals4_z16(uint4 b, float out[4]) {
+    float s[4];
+    bm_pair(b.x, b.y, BM_C_X4096, s[0], s[1]);
+    bm_pair(b.z, b.w, BM_C_X4096, s[2], s[3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = z16_round(s[i]);
+}
+__device__ __forceinline__ void normals4_z16(uint4 b, double out[4]) {
+    float f[4];
+    normals4_z16(b, f);
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = (double)f[i];
 }
 
 template <typename R>
-__device__ __forceinline__ R philox_normal(unsigned long long seed, long long chain, long long idx) {
+__device__ __forceinline__ R philox_normal(unsigned long long seed, long long chain, long long idx, int z_round = 0) {
     R v[4];
-    normals4<R>(philox_block(seed, chain, STREAM_Z, (unsigned long long)idx >> 2), v);
+    const uint4 b = philox_block(seed, chain, STREAM_Z, (unsigned long long)idx >> 2);
+    if (z_round) normals4_z16(b, v);
+    else normals4<R>(b, v);
     return v[idx & 3];
 }
 

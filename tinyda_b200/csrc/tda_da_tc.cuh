@@ -513,7 +513,6 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                 }
                 if (accf) {
                     like_f = like_fp; prior_f = prior_p; like_cs = like_c; nacc_f++;
-#pragma unroll
                     float* dst = tc_opaque(l1.theta + off0);
 #pragma unroll
                     for (int k = 0; k < TC_HK; k++) dst[k * cs] = th[k];

@@ -1,0 +1,844 @@
+// Tensor-core (tcgen05 / TMEM) Delayed-Acceptance kernel, third generation ("tc16"): two-level DA,
+// pCN proposal, linear forward operators, isotropic likelihoods (BASELINE cfg2), float32 engine.
+//
+// What changed against tda_da_tc.cuh (3xTF32, draws on the row threads):
+//
+//  * Arithmetic: every operand is a TWO-TERM FP16 SPLIT at a power-of-two scale chosen on the host
+//    (x * 2^s = hi + lo, hi = fp16(x 2^s), lo = fp16(x 2^s - hi)); products are
+//    hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM.  fp16 carries the same 11 significant
+//    bits as tf32, so the accuracy is that of the 3xTF32 scheme (~2^-22 per element), but
+//    kind::f16 runs at twice the tf32 rate.  The scales keep every hi part in [2^3, 2^15) so the
+//    lo parts stay in fp16's normal range; an overflowing proposal yields NaN -> alpha = 0.
+//  * Normals: Philox4x32-10 + Box-Muller run on DEDICATED warps that stay one coarse step ahead
+//    and write z straight into shared memory as an MMA A operand.  The stream is the "z16"
+//    stream of tda_common.cuh (normals on the fp16 grid), so z is ONE exact operand image.
+//  * One MMA hop per coarse step: with theta' = a theta + b z T (pCN), the coarse model output is
+//        F_c(theta') = theta @ (a G_c^T)  +  z @ (b T G_c^T)
+//    i.e. two accumulating MMA groups into the same TMEM columns (A = theta from TMEM, 3 products;
+//    A = z from shared memory, 2 products) with the composed operator b T G_c^T built once on the
+//    host; xi = z @ T goes to 64 more columns and is only read when a chain accepts
+//    (theta <- a theta + b xi).  The row threads keep A_theta = split(theta) up to date.
+//  * One MMA-issuing warp per tile (blocking mbarrier waits instead of a polling loop).
+//  * Register budget moved between warpgroups with setmaxnreg.
+//
+// Reference semantics: chain.py:325-444 (DAChain), proposal.py:261-369 (pCN), exactly as
+// Tile::base_step / Tile::upper_step in tda_kernels.cuh; the state buffers are shared with the other
+// kernels, so runs can be interleaved.
+#pragma once
+#include <cuda_fp16.h>
+#include <cmath>
+#include <string>
+#include <vector>
+#include "tda_common.cuh"
+#include "tda_tc_prims.cuh"
+
+namespace tda {
+
+constexpr int T16_K = 64;                       // parameters (contraction length)
+constexpr int T16_CH = 64;                      // columns per streamed fine-operator chunk
+constexpr int T16_NST = 4;                      // ring stages
+constexpr int T16_MAX_MC = 128;
+constexpr int T16_MAX_MF = 4096;
+constexpr int T16_RNG_WARPS = 8;                // warps 0..7   (warpgroups 0-1)
+constexpr int T16_ROW_WARP0 = 8;                // warps 8..23  (warpgroups 2-5)
+constexpr int T16_MMA_WARP0 = 24;               // warps 24, 25 (one per tile)
+constexpr int T16_PROD_WARP = 26;               // warp 27 idles (completes warpgroup 6)
+constexpr int T16_THREADS = 28 * 32;
+constexpr int T16_HK = T16_K / 2;               // theta columns per row thread
+constexpr int T16_IMG = 128 * T16_K * 2;        // one [128 x 64] fp16 image: 16 KB
+constexpr int T16_TIMG = 64 * T16_K * 2;        // one [64 x 64] fp16 image: 8 KB
+constexpr int T16_CHUNK_BYTES = 2 * T16_TIMG;   // hi + lo
+constexpr int T16_REGS_ROW = 96, T16_REGS_RNG = 40, T16_REGS_AUX = 40;   // 512*24 taken = 256*32 + 128*32 released (launch: 72)
+
+constexpr int T16_OFF_G = 0;                                   // a G_c^T   (hi | lo)
+constexpr int T16_OFF_M = T16_OFF_G + 2 * T16_IMG;             // b T G_c^T (hi | lo)
+constexpr int T16_OFF_T = T16_OFF_M + 2 * T16_IMG;             // T         (hi | lo)
+constexpr int T16_OFF_RING = T16_OFF_T + 2 * T16_TIMG;
+constexpr int T16_OFF_Z = T16_OFF_RING + T16_NST * T16_CHUNK_BYTES;   // [tile 2][buffer 2] images
+constexpr int T16_OFF_PART = T16_OFF_Z + 4 * T16_IMG;          // [buf 2][tile 2][half 2][128] f32
+constexpr int T16_OFF_U = T16_OFF_PART + 2 * 2 * 2 * 128 * 4;  // [buf 2][tile 2][128] f32
+constexpr int T16_OFF_PF = T16_OFF_U + 2 * 2 * 128 * 4;        // [tile 2][half 2][val 2][128] f32
+constexpr int T16_OFF_BARS = T16_OFF_PF + 2 * 2 * 2 * 128 * 4;
+constexpr size_t T16_SMEM_BYTES = T16_OFF_BARS + 256;
+
+__constant__ float c16_nyc[T16_MAX_MC];     // -(coarse data - offset)
+__constant__ float c16_nyf[T16_MAX_MF];     // -(fine data - offset)
+__constant__ float c16_nlp[T16_K];          // -(prior_mean @ LP)
+
+struct DaTc16Params {
+    const __half* G_hl;       // [hi mc x 64 | lo mc x 64] canonical K-major, a G_c^T  * 2^sG
+    const __half* M_hl;       // [hi mc x 64 | lo mc x 64]                  b T G_c^T * 2^sM
+    const __half* T_hl;       // [hi 64 x 64 | lo 64 x 64]                  T         * 2^sT
+    const __half* F_chunks;   // n_chunks x [hi 64 x 64 | lo 64 x 64]  fine operator columns, then LP
+    int mc, mf, n_chunks, J;
+    float var_c, var_f, prior_logconst;
+    float ca;                 // sqrt(1 - beta^2)
+    float cxi;                // beta * 2^s_theta / 2^(s_z + s_T): scaled-theta increment per unit of D_xi
+    float sc_c, sc_f, sc_p;   // accumulator -> model output: 2^-(s_theta + s_G), 2^-(s_theta + s_Gf), 2^-(s_theta + s_LP)
+    float th_scale, th_unscale;
+    int n_pairs;
+};
+
+// ---------------------------------------------------------------------------------------------
+// self-test: D[128][N] = A[128][64] @ B[64][N], fp16 two-term split, the conventions of the DA
+// kernel (A packed in TMEM or canonical in shared memory, B canonical in shared memory).
+// A is scaled by sA in the kernel; B arrives pre-scaled / pre-split; D is unscaled by the host.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160, 1)
+tc16_gemm_selftest_kernel(const float* __restrict__ A, const __half* __restrict__ B_hl, int N, float sA,
+                          float* __restrict__ D, int a_in_tmem) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int K = T16_K;
+    unsigned char* sB_hi = smem;                       // up to 256 x 64 halves = 32 KB
+    unsigned char* sB_lo = smem + 256 * K * 2;
+    unsigned char* sA_hi = smem + 2 * 256 * K * 2;     // 16 KB each
+    unsigned char* sA_lo = sA_hi + T16_IMG;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA_lo + T16_IMG);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t *bar_b = bars, *bar_req = bars + 1, *bar_resp = bars + 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 4) tc::tmem_alloc(s_tmem, 512);
+    if (tid == 128) {
+        tc::mbar_init(bar_b, 1);
+        tc::mbar_init(bar_req, 128);
+        tc::mbar_init(bar_resp, 1);
+        tc::fence_mbar_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = *s_tmem;
+    const uint32_t bytes_b = (uint32_t)N * K * 2;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tc::mbar_expect_tx(bar_b, 2 * bytes_b);
+            tc::bulk_g2s(sB_hi, B_hl, bytes_b, bar_b);
+            tc::bulk_g2s(sB_lo, B_hl + (size_t)N * K, bytes_b, bar_b);
+            tc::mbar_wait(bar_b, 0);
+            tc::mbar_wait(bar_req, 0);
+            tc::fence_after_sync();
+            const uint32_t idesc = tc::idesc_f16(128, N);
+            const uint32_t d_t = tbase + 128;
+            uint32_t accumulate = 0;
+            for (int pass = 0; pass < 3; pass++) {
+                const int a_lo = (pass == 1);
+                const unsigned char* sb = (pass == 2) ? sB_lo : sB_hi;
+                const unsigned char* sa = a_lo ? sA_lo : sA_hi;
+                for (int ks = 0; ks < K / 16; ks++) {
+                    const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(sb) + ks * 256, 128, (K / 8) * 128);
+                    if (a_in_tmem) {
+                        tc::mma_f16_ts(d_t, tbase + a_lo * 32 + ks * 8, bdesc, idesc, accumulate);
+                    } else {
+                        const uint64_t adesc = tc::smem_desc_kmajor(tc::smem_u32(sa) + ks * 256, 128, (K / 8) * 128);
+                        tc::mma_f16_ss(d_t, adesc, bdesc, idesc, accumulate);
+                    }
+                    accumulate = 1;
+                }
+            }
+            tc::mma_commit(bar_resp);
+        }
+        __syncwarp();
+    } else {
+        const int r = tid;
+        const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
+        uint32_t hi[16], lo[16];
+        for (int c0 = 0; c0 < K; c0 += 32) {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                tc::split_f16x2(A[r * K + c0 + 2 * j] * sA, A[r * K + c0 + 2 * j + 1] * sA, hi[j], lo[j]);
+            if (a_in_tmem) {
+                tc::tmem_st16(lane_base + c0 / 2, hi);
+                tc::tmem_st16(lane_base + 32 + c0 / 2, lo);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    *reinterpret_cast<uint32_t*>(sA_hi + tc::canon_offset_f16(r, c0 + 2 * j, K)) = hi[j];
+                    *reinterpret_cast<uint32_t*>(sA_lo + tc::canon_offset_f16(r, c0 + 2 * j, K)) = lo[j];
+                }
+            }
+        }
+        if (a_in_tmem) tc::tmem_wait_st();
+        else tc::fence_proxy_async_smem();
+        tc::fence_before_sync();
+        tc::mbar_arrive(bar_req);
+        tc::mbar_wait(bar_resp, 0);
+        tc::fence_after_sync();
+        uint32_t v[16];
+        for (int c0 = 0; c0 < N; c0 += 16) {
+            tc::tmem_ld16(lane_base + 128 + c0, v);
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (c0 + j < N) D[r * N + c0 + j] = __uint_as_float(v[j]);
+        }
+        tc::fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tbase, 512);
+}
+
+// power-of-two scale that brings `maxabs` into [2^(top-1), 2^top)
+inline int pow2_scale_for(double maxabs, int top) {
+    if (!(maxabs > 0.0) || !std::isfinite(maxabs)) return 0;
+    int e;
+    std::frexp(maxabs, &e);          // maxabs = f * 2^e, f in [0.5, 1)
+    return top - e;
+}
+
+// canonical K-major fp16 hi / lo images of B[n][k] = factor * W[k][n0 + n] * 2^s   (W row-major [K][ldw])
+inline void canon_split16(const std::vector<double>& W, int ldw, int n0, int rows, double factor, int s, __half* hi, __half* lo) {
+    for (int n = 0; n < rows; n++)
+        for (int k = 0; k < T16_K; k++) {
+            const float x = (float)std::ldexp(factor * W[(size_t)k * ldw + n0 + n], s);
+            const __half h = __float2half_rn(x);
+            const __half l = __float2half_rn(x - __half2float(h));
+            const size_t o = tc::canon_offset_f16(n, k, T16_K) / 2;
+            hi[o] = h;
+            lo[o] = l;
+        }
+}
+
+inline int tc16_gemm_selftest_host(const float* A, const float* B, int N, float* D, int a_in_tmem, std::string& err) {
+    constexpr int K = T16_K;
+    if (N < 16 || N > 256 || (N % 16) != 0) { err = "selftest16: N must be a multiple of 16 in [16, 256]"; return -1; }
+    double ma = 0, mb = 0;
+    for (int i = 0; i < 128 * K; i++) ma = std::fmax(ma, std::fabs((double)A[i]));
+    for (int i = 0; i < K * N; i++) mb = std::fmax(mb, std::fabs((double)B[i]));
+    const int sa = pow2_scale_for(ma, 14), sb = pow2_scale_for(mb, 14);
+    std::vector<double> W((size_t)K * N);
+    for (size_t i = 0; i < W.size(); i++) W[i] = B[i];
+    std::vector<__half> bhl((size_t)2 * N * K);
+    canon_split16(W, N, 0, N, 1.0, sb, bhl.data(), bhl.data() + (size_t)N * K);
+    float *dA = nullptr, *dD = nullptr;
+    __half* dB = nullptr;
+    auto chk = [&](cudaError_t c, const char* what) { if (c != cudaSuccess && err.empty()) err = std::string(what) + ": " + cudaGetErrorString(c); return c; };
+    chk(cudaMalloc(&dA, 128 * K * 4), "malloc");
+    chk(cudaMalloc(&dB, bhl.size() * 2), "malloc");
+    chk(cudaMalloc(&dD, (size_t)128 * N * 4), "malloc");
+    chk(cudaMemcpy(dA, A, 128 * K * 4, cudaMemcpyHostToDevice), "h2d");
+    chk(cudaMemcpy(dB, bhl.data(), bhl.size() * 2, cudaMemcpyHostToDevice), "h2d");
+    const size_t smem = (size_t)2 * 256 * K * 2 + 2 * T16_IMG + 64;
+    chk(cudaFuncSetAttribute(tc16_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr");
+    if (err.empty()) {
+        tc16_gemm_selftest_kernel<<<1, 160, smem>>>(dA, dB, N, (float)std::ldexp(1.0, sa), dD, a_in_tmem);
+        chk(cudaGetLastError(), "launch");
+        chk(cudaDeviceSynchronize(), "sync");
+        chk(cudaMemcpy(D, dD, (size_t)128 * N * 4, cudaMemcpyDeviceToHost), "d2h");
+        const float un = (float)std::ldexp(1.0, -(sa + sb));
+        for (size_t i = 0; i < (size_t)128 * N; i++) D[i] *= un;
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    return err.empty() ? 0 : -2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the DA kernel
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T* t16_opaque(T* ptr) {
+    asm volatile("" : "+l"(ptr));
+    return ptr;
+}
+
+// "my TMEM / shared-memory accesses are done" -> one arrival per warp
+__device__ __forceinline__ void t16_warp_arrive(uint64_t* bar, int lane) {
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(bar);
+}
+
+// 3 products (A = theta hi | lo in TMEM, B hi | lo in shared memory), N columns, K = 64
+__device__ __forceinline__ void t16_issue_theta(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+#pragma unroll
+    for (int pass = 0; pass < 3; pass++) {
+        const uint32_t a = a_tmem + (pass == 1 ? 32 : 0);
+        const uint64_t b0 = tc::smem_desc_kmajor(pass == 2 ? b_lo : b_hi, 128, (T16_K / 8) * 128);
+#pragma unroll
+        for (int ks = 0; ks < T16_K / 16; ks++) {
+            tc::mma_f16_ts(d_tmem, a + ks * 8, b0 + (uint64_t)(ks * 16), idesc, accumulate);
+            accumulate = 1;
+        }
+    }
+}
+
+// z-operand products: z @ B_hi + z @ B_lo (+ z_lo @ B_hi when the stream is injected)
+__device__ __forceinline__ void t16_issue_z(uint32_t d_tmem, uint32_t z_hi, uint32_t z_lo, bool with_lo, uint32_t b_hi, uint32_t b_lo,
+                                            uint32_t idesc, uint32_t accumulate) {
+    const int npass = with_lo ? 3 : 2;
+    for (int pass = 0; pass < npass; pass++) {
+        const uint64_t a0 = tc::smem_desc_kmajor(pass == 2 ? z_lo : z_hi, 128, (T16_K / 8) * 128);
+        const uint64_t b0 = tc::smem_desc_kmajor(pass == 1 ? b_lo : b_hi, 128, (T16_K / 8) * 128);
+#pragma unroll
+        for (int ks = 0; ks < T16_K / 16; ks++) {
+            tc::mma_f16_ss(d_tmem, a0 + (uint64_t)(ks * 16), b0 + (uint64_t)(ks * 16), idesc, accumulate);
+            accumulate = 1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(T16_THREADS, 1)
+da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ DaTc16Params q) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sG = smem + T16_OFF_G;
+    unsigned char* sM = smem + T16_OFF_M;
+    unsigned char* sT = smem + T16_OFF_T;
+    unsigned char* ring = smem + T16_OFF_RING;
+    unsigned char* zbuf = smem + T16_OFF_Z;
+    float* s_part = reinterpret_cast<float*>(smem + T16_OFF_PART);
+    float* s_u = reinterpret_cast<float*>(smem + T16_OFF_U);
+    float* s_pf = reinterpret_cast<float*>(smem + T16_OFF_PF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T16_OFF_BARS);
+    uint64_t* bar_res = bars;                       // resident operands landed
+    uint64_t* bar_req = bars + 1;                   // [tile 2][buffer 2]  rows -> MMA
+    uint64_t* bar_resp = bars + 5;                  // [tile 2][buffer 2]  MMA  -> rows
+    uint64_t* bar_zfull = bars + 9;                 // [tile 2][buffer 2]  RNG  -> MMA
+    uint64_t* bar_zfree = bars + 13;                // [tile 2][buffer 2]  MMA  -> RNG
+    uint64_t* bar_full = bars + 17;                 // [NST]
+    uint64_t* bar_empty = bars + 17 + T16_NST;      // [NST]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 17 + 2 * T16_NST);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == T16_MMA_WARP0) tc::tmem_alloc(s_tmem, 512);
+    if (tid == T16_PROD_WARP * 32) {
+        tc::mbar_init(bar_res, 1);
+        for (int i = 0; i < 4; i++) {
+            tc::mbar_init(bar_req + i, 8);
+            tc::mbar_init(bar_resp + i, 1);
+            tc::mbar_init(bar_zfull + i, 4);
+            tc::mbar_init(bar_zfree + i, 1);
+        }
+        for (int s = 0; s < T16_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 2); }
+        tc::fence_mbar_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = *s_tmem;
+
+    const int J = q.J, mc = q.mc, NCH = q.n_chunks;
+    const int my_pairs = (q.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long iters = p.iterations;
+    const bool inj = p.rng_mode == TDA_RNG_INJECTED;
+
+    if (warp < T16_RNG_WARPS) {
+        // =====================================================================================
+        // RNG warps: thread = one chain of one tile; 64 normals per coarse step -> z image(s)
+        // =====================================================================================
+        tc::setmaxnreg_dec<T16_REGS_RNG>();
+        const int t = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        unsigned char* zt = zbuf + (size_t)t * 2 * T16_IMG + (row >> 3) * ((T16_K / 8) * 128) + (row & 7) * 16;
+        uint64_t* zfull = bar_zfull + t * 2;
+        uint64_t* zfree = bar_zfree + t * 2;
+        long long n = 0;                                   // coarse steps produced
+        for (int pr = 0; pr < my_pairs; pr++) {
+            const int pair = (int)blockIdx.x + pr * (int)gridDim.x;
+            const int g = pair * 256 + t * 128 + row;
+            const long long gchain = p.chain_offset + g;
+            const bool live = g < p.C;
+            long long tb = p.t_base;
+            const long long nsteps = iters * J;
+            for (long long st = 0; st < nsteps; st++, n++, tb++) {
+                const int b = inj ? 0 : (int)(n & 1);
+                const long long use = inj ? n : (n >> 1);
+                if (use >= 1) tc::mbar_wait(zfree + b, (uint32_t)((use - 1) & 1));
+                unsigned char* dst = zt + (size_t)b * T16_IMG;
+                if (!inj) {
+                    const unsigned long long blk0 = (unsigned long long)(tb * (T16_K / 4));
+#pragma unroll 2
+                    for (int kg = 0; kg < T16_K / 8; kg++) {
+                        const uint4 b0 = philox_block(p.seed, gchain, STREAM_Z, blk0 + 2 * kg);
+                        const uint4 b1 = philox_block(p.seed, gchain, STREAM_Z, blk0 + 2 * kg + 1);
+                        float s[8];
+                        bm_pair(b0.x, b0.y, BM_C_X4096, s[0], s[1]);
+                        bm_pair(b0.z, b0.w, BM_C_X4096, s[2], s[3]);
+                        bm_pair(b1.x, b1.y, BM_C_X4096, s[4], s[5]);
+                        bm_pair(b1.z, b1.w, BM_C_X4096, s[6], s[7]);
+                        uint4 w;
+                        w.x = tc::pack_f16x2(s[0], s[1]);
+                        w.y = tc::pack_f16x2(s[2], s[3]);
+                        w.z = tc::pack_f16x2(s[4], s[5]);
+                        w.w = tc::pack_f16x2(s[6], s[7]);
+                        *reinterpret_cast<uint4*>(dst + kg * 128) = w;
+                    }
+                } else {
+                    const long long z0 = tb * T16_K;
+                    for (int kg = 0; kg < T16_K / 8; kg++) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const long long idx = z0 + kg * 8 + 2 * i;
+                            const float x0 = (live && idx < p.zlen) ? p.zs[(size_t)g * p.zlen + idx] * Z16_SCALE : 0.0f;
+                            const float x1 = (live && idx + 1 < p.zlen) ? p.zs[(size_t)g * p.zlen + idx + 1] * Z16_SCALE : 0.0f;
+                            tc::split_f16x2(x0, x1, hi[i], lo[i]);
+                        }
+                        *reinterpret_cast<uint4*>(dst + kg * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(dst + T16_IMG + kg * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                tc::fence_proxy_async_smem();          // generic-proxy writes -> visible to the MMA (async proxy)
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(zfull + b);
+            }
+        }
+    } else if (warp >= T16_MMA_WARP0) {
+        tc::setmaxnreg_dec<T16_REGS_AUX>();
+        if (warp == T16_PROD_WARP) {
+            // ===== producer: resident operands once, then the fine-operator chunk ring =====
+            if (lane == 0) {
+                const long long total_chunks = (long long)my_pairs * iters * NCH;
+                const uint32_t bI = (uint32_t)mc * T16_K * 2;       // one mc-row image
+                tc::mbar_expect_tx(bar_res, 4 * bI + 2 * T16_TIMG);
+                tc::bulk_g2s(sG, q.G_hl, bI, bar_res);
+                tc::bulk_g2s(sG + T16_IMG, q.G_hl + (size_t)mc * T16_K, bI, bar_res);
+                tc::bulk_g2s(sM, q.M_hl, bI, bar_res);
+                tc::bulk_g2s(sM + T16_IMG, q.M_hl + (size_t)mc * T16_K, bI, bar_res);
+                tc::bulk_g2s(sT, q.T_hl, 2 * T16_TIMG, bar_res);
+                for (long long g = 0; g < total_chunks; g++) {
+                    const int st = (int)(g % T16_NST);
+                    if (g >= T16_NST) tc::mbar_wait(bar_empty + st, (uint32_t)(((g / T16_NST) - 1) & 1));
+                    const int c = (int)(g % NCH);
+                    tc::mbar_expect_tx(bar_full + st, T16_CHUNK_BYTES);
+                    tc::bulk_g2s(ring + (size_t)st * T16_CHUNK_BYTES, q.F_chunks + (size_t)c * (T16_CHUNK_BYTES / 2), T16_CHUNK_BYTES, bar_full + st);
+                }
+            }
+        } else if (warp < T16_PROD_WARP) {
+            // ===== MMA issuer of tile t =====
+            const int t = warp - T16_MMA_WARP0;
+            if (lane == 0) {
+                tc::mbar_wait(bar_res, 0);
+                const uint32_t tA = tbase + t * 256, tD = tA + 64;
+                const uint32_t sG_hi = tc::smem_u32(sG), sG_lo = sG_hi + T16_IMG;
+                const uint32_t sM_hi = tc::smem_u32(sM), sM_lo = sM_hi + T16_IMG;
+                const uint32_t sT_hi = tc::smem_u32(sT), sT_lo = sT_hi + T16_TIMG;
+                const uint32_t z_base = tc::smem_u32(zbuf) + t * 2 * T16_IMG;
+                const uint32_t idesc_c = tc::idesc_f16(128, mc), idesc_64 = tc::idesc_f16(128, 64);
+                uint64_t* req = bar_req + t * 2;
+                uint64_t* resp = bar_resp + t * 2;
+                uint32_t rq0 = 0, rq1 = 0;
+                long long n = 0, gch = 0;
+                const long long total_it = (long long)my_pairs * iters;
+                for (long long itg = 0; itg < total_it; itg++) {
+                    for (int j = 0; j < J; j++, n++) {
+                        const int b = inj ? 0 : (int)(n & 1);
+                        const long long use = inj ? n : (n >> 1);
+                        tc::mbar_wait(req, rq0); rq0 ^= 1;
+                        tc::fence_after_sync();
+                        // theta part first: it does not need this step's normals
+                        t16_issue_theta(tD, tA, sG_hi, sG_lo, idesc_c, 0);
+                        tc::mbar_wait(bar_zfull + t * 2 + b, (uint32_t)(use & 1));
+                        tc::fence_after_sync();
+                        const uint32_t z_hi = z_base + b * T16_IMG, z_lo = z_base + T16_IMG;
+                        t16_issue_z(tD, z_hi, z_lo, inj, sM_hi, sM_lo, idesc_c, 1);
+                        t16_issue_z(tD + 128, z_hi, z_lo, inj, sT_hi, sT_lo, idesc_64, 0);
+                        tc::mma_commit(resp);
+                        tc::mma_commit(bar_zfree + t * 2 + b);
+                    }
+                    for (int c = 0; c < NCH; c++, gch++) {
+                        const int b = c & 1;
+                        const int st = (int)(gch % T16_NST);
+                        if (b) { tc::mbar_wait(req + 1, rq1); rq1 ^= 1; }
+                        else { tc::mbar_wait(req, rq0); rq0 ^= 1; }
+                        tc::mbar_wait(bar_full + st, (uint32_t)((gch / T16_NST) & 1));
+                        tc::fence_after_sync();
+                        const uint32_t b_hi = tc::smem_u32(ring + (size_t)st * T16_CHUNK_BYTES), b_lo = b_hi + T16_TIMG;
+                        t16_issue_theta(tD + b * T16_CH, tA, b_hi, b_lo, idesc_64, 0);
+                        tc::mma_commit(resp + b);
+                        tc::mma_commit(bar_empty + st);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =====================================================================================
+        // row threads: two per chain (column halves)
+        // =====================================================================================
+        tc::setmaxnreg_inc<T16_REGS_ROW>();
+        const int rw = warp - T16_ROW_WARP0;
+        const int t = rw >> 3;                         // tile within the pair
+        const int h = (rw >> 2) & 1;                   // column half
+        const int wq = rw & 3;                         // TMEM lane quarter (= warp % 4)
+        const int cl = wq * 32 + lane;                 // chain within the tile
+        const int col0 = h * T16_HK;                   // first theta column of this thread
+        const uint32_t tA = tbase + ((uint32_t)(wq * 32) << 16) + t * 256;
+        const uint32_t tD = tA + 64;
+        uint64_t* req = bar_req + t * 2;
+        uint64_t* resp = bar_resp + t * 2;
+        uint32_t ph0 = 0, ph1 = 0;
+        int sbuf = 0;
+        const LevelP<float>& l0 = p.lv[0];
+        const LevelP<float>& l1 = p.lv[1];
+        const float inv2vc = -0.5f / q.var_c, inv2vf = -0.5f / q.var_f;
+        const float ca = q.ca, cxi = q.cxi, sc_c = q.sc_c, sc_f = q.sc_f, sc_p = q.sc_p;
+        const float th_scale = q.th_scale, th_unscale = q.th_unscale;
+        const int ngc = mc >> 4, gc0 = h ? (ngc + 1) / 2 : 0, gc1 = h ? ngc : (ngc + 1) / 2;
+
+        for (int pr = 0; pr < my_pairs; pr++) {
+            const int pair = (int)blockIdx.x + pr * (int)gridDim.x;
+            const int g = pair * 256 + t * 128 + cl;                   // chain slot (padded arrays)
+            const long long gchain = p.chain_offset + g;
+            const bool live = g < p.C;
+            const size_t cs = (size_t)p.Cs;
+            const size_t off0 = (size_t)col0 * cs + g;      // this thread's first column, this chain
+            float th[T16_HK];                                // current coarse state, scaled by 2^s_theta
+            {
+                const float* src = t16_opaque(l1.theta + off0);
+#pragma unroll
+                for (int k = 0; k < T16_HK; k++) th[k] = src[k * cs] * th_scale;
+            }
+            float like_c = l0.like[g], like_cs = like_c, like_f = l1.like[g], prior_f = l1.prior[g];
+            long long ucur = p.ucur[g];
+            int nacc_c = 0, nacc_f = 0;
+            int acc_any = 0;
+
+            auto store_A = [&]() {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) tc::split_f16x2(th[2 * i], th[2 * i + 1], hi[i], lo[i]);
+                tc::tmem_st16(tA + h * 16, hi);
+                tc::tmem_st16(tA + 32 + h * 16, lo);
+                tc::tmem_wait_st();
+            };
+            auto draw_u = [&]() -> float {
+                if (inj) return (live && ucur < p.ulen) ? p.us[(size_t)g * p.ulen + ucur] : 0.5f;
+                return philox_uniform<float>(p.seed, gchain, ucur);
+            };
+
+            store_A();
+            t16_warp_arrive(req, lane);
+
+            for (long long it = 0; it < iters; it++) {
+                for (int j = 0; j < J; j++) {
+                    // the accept-test uniform does not depend on the MMA: draw it while waiting
+                    float u_mine = 0.0f;
+                    if (h == 0) u_mine = draw_u();
+                    ucur++;
+                    tc::mbar_wait(resp, ph0); ph0 ^= 1;
+                    tc::fence_after_sync();
+                    float ssq = 0.0f;
+                    for (int gc = gc0; gc < gc1; gc++) {
+                        uint32_t v[16];
+                        tc::tmem_ld16(tD + gc * 16, v);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float r = fmaf(__uint_as_float(v[i]), sc_c, c16_nyc[gc * 16 + i]);
+                            ssq = fmaf(r, r, ssq);
+                        }
+                    }
+                    float* sp = s_part + ((sbuf * 2 + t) * 2) * 128;
+                    float* su = s_u + (sbuf * 2 + t) * 128;
+                    sp[h * 128 + cl] = ssq;
+                    if (h == 0) su[cl] = u_mine;
+                    sbuf ^= 1;
+                    tc::named_bar_sync(1 + t, 256);
+                    const float like_p = inv2vc * (sp[cl] + sp[128 + cl]);
+                    const float u = su[cl];
+                    const float alpha = isnan(like_p) ? 0.0f : expf(like_p - like_c);
+                    const bool acc = u < alpha;
+                    if (__any_sync(0xffffffffu, acc)) {
+                        uint32_t x0[16], x1[16];
+                        tc::tmem_ld16(tD + 128 + col0, x0);
+                        tc::tmem_ld16(tD + 128 + col0 + 16, x1);
+                        tc::tmem_wait_ld();
+                        if (acc) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                th[i] = fmaf(__uint_as_float(x0[i]), cxi, ca * th[i]);
+                                th[16 + i] = fmaf(__uint_as_float(x1[i]), cxi, ca * th[16 + i]);
+                            }
+                        }
+                        store_A();
+                    }
+                    if (acc) { like_c = like_p; acc_any = 1; nacc_c++; }
+                    // D consumed, A_theta current -> next job (the last coarse step also frees the
+                    // second fine-chunk accumulator)
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tc::mbar_arrive(req);
+                        if (j == J - 1) tc::mbar_arrive(req + 1);
+                    }
+                }
+                // ---- fine level: F_f = theta @ G_f^T streamed in 64-column chunks, then theta @ LP ----
+                float u2 = 0.0f;
+                if (h == 0) u2 = draw_u();
+                float ssq_f = 0.0f, ssq_p = 0.0f;
+                for (int c = 0; c < NCH; c++) {
+                    const int b = c & 1;
+                    if (b) { tc::mbar_wait(resp + 1, ph1); ph1 ^= 1; }
+                    else { tc::mbar_wait(resp, ph0); ph0 ^= 1; }
+                    tc::fence_after_sync();
+                    uint32_t v0[16], v1[16];
+                    tc::tmem_ld16(tD + b * T16_CH + col0, v0);
+                    tc::tmem_ld16(tD + b * T16_CH + col0 + 16, v1);
+                    tc::tmem_wait_ld();
+                    if (c + 2 < NCH) t16_warp_arrive(req + b, lane);
+                    if (c < NCH - 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float r0 = fmaf(__uint_as_float(v0[i]), sc_f, c16_nyf[c * T16_CH + col0 + i]);
+                            const float r1 = fmaf(__uint_as_float(v1[i]), sc_f, c16_nyf[c * T16_CH + col0 + 16 + i]);
+                            ssq_f = fmaf(r0, r0, ssq_f);
+                            ssq_f = fmaf(r1, r1, ssq_f);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float w0 = fmaf(__uint_as_float(v0[i]), sc_p, c16_nlp[col0 + i]);
+                            const float w1 = fmaf(__uint_as_float(v1[i]), sc_p, c16_nlp[col0 + 16 + i]);
+                            ssq_p = fmaf(w0, w0, ssq_p);
+                            ssq_p = fmaf(w1, w1, ssq_p);
+                        }
+                    }
+                }
+                float* sf = s_pf + (t * 2) * 256;
+                sf[h * 256 + cl] = ssq_f;
+                sf[h * 256 + 128 + cl] = ssq_p;
+                float* su = s_u + (sbuf * 2 + t) * 128;
+                if (h == 0) su[cl] = u2;
+                sbuf ^= 1;
+                tc::named_bar_sync(1 + t, 256);
+                const float like_fp = inv2vf * (sf[cl] + sf[256 + cl]);
+                const float prior_p = -0.5f * (q.prior_logconst + (sf[128 + cl] + sf[256 + 128 + cl]));
+                int accf = 0;
+                if (acc_any) {
+                    const float alpha2 = expf(like_fp - like_f + like_cs - like_c);
+                    accf = (su[cl] < alpha2) ? 1 : 0;
+                    ucur++;
+                }
+                if (accf) {
+                    like_f = like_fp; prior_f = prior_p; like_cs = like_c; nacc_f++;
+                    float* dst = t16_opaque(l1.theta + off0);
+#pragma unroll
+                    for (int k = 0; k < T16_HK; k++) dst[k * cs] = th[k] * th_unscale;
+                } else {
+                    like_c = like_cs;
+                    const float* src = t16_opaque(l1.theta + off0);
+#pragma unroll
+                    for (int k = 0; k < T16_HK; k++) th[k] = src[k * cs] * th_scale;
+                }
+                acc_any = 0;
+                // the A operand must hold the (possibly rewound) state before the next coarse job
+                if (!__all_sync(0xffffffffu, accf)) store_A();
+                if (it + 1 < iters) t16_warp_arrive(req, lane);
+                // ---- fine-level record (coalesced: consecutive lanes = consecutive chains) ----
+                const long long r = p.rec[1] + it;
+                if (r < l1.hist_cap) {
+                    if (l1.store & TDA_STORE_THETA) {
+                        float* dst = t16_opaque(l1.h_theta + (size_t)r * T16_K * cs + off0);
+#pragma unroll
+                        for (int k = 0; k < T16_HK; k++) dst[k * cs] = th[k] * th_unscale;
+                    }
+                    if (h == 0) {
+                        if (l1.store & TDA_STORE_STATS) { l1.h_prior[(size_t)r * p.Cs + g] = prior_f; l1.h_like[(size_t)r * p.Cs + g] = like_f; }
+                        if (l1.store & TDA_STORE_ACCEPT) l1.h_acc[(size_t)r * p.Cs + g] = (uint8_t)accf;
+                    }
+                }
+                {
+                    float* s1 = t16_opaque(p.sum1 + off0);
+                    float* s2 = t16_opaque(p.sum2 + off0);
+#pragma unroll
+                    for (int k = 0; k < T16_HK; k++) {
+                        const float x = th[k] * th_unscale;
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s1 + k * cs), "f"(x) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s2 + k * cs), "f"(x * x) : "memory");
+                    }
+                }
+            }
+            // ---- write the chain state back (layout shared with the other kernels) ----
+            {
+                float* dst = t16_opaque(l0.theta + off0);
+#pragma unroll
+                for (int k = 0; k < T16_HK; k++) dst[k * cs] = th[k] * th_unscale;
+            }
+            if (h == 0) {
+                l0.like[g] = like_c; l0.prior[g] = prior_f; l1.like[g] = like_f; l1.prior[g] = prior_f;
+                l0.sv_like[1][g] = like_c; l0.sv_prior[1][g] = prior_f;
+                l0.acc_sub[g] = 0;
+                l0.n_acc[g] += nacc_c; l1.n_acc[g] += nacc_f;
+                p.ucur[g] = ucur;
+            }
+        }
+        tc::fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == T16_MMA_WARP0) tc::tmem_dealloc(tbase, 512);
+}
+
+template <typename R>
+struct DaTc16State {
+    std::string err;
+    bool prepared = false;
+    bool eligible(const tda_config&, const Params<R>&) const { return false; }
+    int prepare(const Params<R>&, const tda_config&) { err = "fp16-split tensor-core DA kernel is float32 only"; return 1; }
+    int run(Params<R>&, const tda_config&, long long, int, cudaStream_t) { err = "fp16-split tensor-core DA kernel is float32 only"; return -5; }
+    void destroy() {}
+};
+
+template <>
+struct DaTc16State<float> {
+    std::string err;
+    __half *dG = nullptr, *dM = nullptr, *dT = nullptr, *dF = nullptr;
+    bool prepared = false;
+    DaTc16Params q{};
+    std::vector<float> nyc, nyf, nlp;
+
+    bool eligible(const tda_config& c, const Params<float>& P) const {
+        if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.prop_kind != TDA_PROP_PCN || c.adaptive) return false;
+        if (c.d != T16_K) return false;
+        for (int l = 0; l < 2; l++)
+            if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
+        if (c.level[0].m > T16_MAX_MC || (c.level[0].m % 16) != 0) return false;
+        if (c.level[1].m > T16_MAX_MF || (c.level[1].m % T16_CH) != 0) return false;
+        if (c.level[0].store != 0 || (c.level[1].store & TDA_STORE_OUTPUT)) return false;
+        if ((P.Cs % 256) != 0) return false;
+        if (!(c.scaling > 0.0 && c.scaling < 1.0)) return false;
+        return true;
+    }
+
+    void destroy() {
+        if (dG) cudaFree(dG);
+        if (dM) cudaFree(dM);
+        if (dT) cudaFree(dT);
+        if (dF) cudaFree(dF);
+        dG = dM = dT = dF = nullptr;
+        prepared = false;
+    }
+
+    static double maxabs(const std::vector<double>& W, int ldw, int n0, int rows, double factor) {
+        double m = 0;
+        for (int k = 0; k < T16_K; k++)
+            for (int n = 0; n < rows; n++) m = std::fmax(m, std::fabs(factor * W[(size_t)k * ldw + n0 + n]));
+        return m;
+    }
+
+    // returns 1 when the problem cannot be scaled into fp16 (caller falls back to another kernel)
+    int prepare(const Params<float>& P, const tda_config& c) {
+        auto fetch = [&](const float* dev, size_t n, std::vector<double>& h) {
+            std::vector<float> f(n);
+            cudaError_t e = cudaMemcpy(f.data(), dev, n * sizeof(float), cudaMemcpyDeviceToHost);
+            h.assign(f.begin(), f.end());
+            return e;
+        };
+        const int mc = c.level[0].m, mf = c.level[1].m;
+        std::vector<double> T, LP, Ac, Af, bc, bf, dc, df, mu, sc;
+        cudaError_t e = cudaSuccess;
+        if (e == cudaSuccess) e = fetch(P.T, (size_t)T16_K * P.ldD, T);
+        if (e == cudaSuccess) e = fetch(P.LP, (size_t)T16_K * P.ldD, LP);
+        if (e == cudaSuccess) e = fetch(P.lv[0].A, (size_t)T16_K * P.lv[0].ldA, Ac);
+        if (e == cudaSuccess) e = fetch(P.lv[1].A, (size_t)T16_K * P.lv[1].ldA, Af);
+        if (e == cudaSuccess) e = fetch(P.lv[0].b, mc, bc);
+        if (e == cudaSuccess) e = fetch(P.lv[1].b, mf, bf);
+        if (e == cudaSuccess) e = fetch(P.lv[0].data, mc, dc);
+        if (e == cudaSuccess) e = fetch(P.lv[1].data, mf, df);
+        if (e == cudaSuccess) e = fetch(P.prior_mean, T16_K, mu);
+        if (e == cudaSuccess) e = fetch(P.scaling, (size_t)P.Cs, sc);
+        if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
+        // the pCN step is folded into the operators: it must be the same for every chain
+        const double beta = sc[0];
+        for (int i = 0; i < P.C; i++)
+            if (sc[i] != beta) { err = "tc16: per-chain pCN step sizes"; return 1; }
+        if (!(beta > 0.0 && beta < 1.0)) { err = "tc16: pCN step outside (0, 1)"; return 1; }
+        const double a = std::sqrt(1.0 - (double)(float)beta * (double)(float)beta);
+        const int ldD = P.ldD, ldc = P.lv[0].ldA, ldf = P.lv[1].ldA;
+
+        // composed coarse operator M[k][n] = sum_j T[k][j] * G_c^T[j][n]
+        std::vector<double> M((size_t)T16_K * mc);
+        for (int k = 0; k < T16_K; k++)
+            for (int n = 0; n < mc; n++) {
+                double s = 0;
+                for (int j = 0; j < T16_K; j++) s += T[(size_t)k * ldD + j] * Ac[(size_t)j * ldc + n];
+                M[(size_t)k * mc + n] = s;
+            }
+        // scales: theta from the prior (mean +- 12 sd must stay below 2^15), operators to [2^13, 2^14)
+        double th_max = 0;
+        for (int k = 0; k < T16_K; k++) {
+            double var = 0;     // prior covariance diagonal = sum_j T[j][k]^2  (xi = z @ T ~ N(0, C))
+            for (int j = 0; j < T16_K; j++) var += T[(size_t)j * ldD + k] * T[(size_t)j * ldD + k];
+            th_max = std::fmax(th_max, std::fabs(mu[k]) + 12.0 * std::sqrt(var));
+        }
+        const int s_th = pow2_scale_for(th_max, 15);
+        const int s_z = 12;
+        int s_G = pow2_scale_for(maxabs(Ac, ldc, 0, mc, a), 14);
+        int s_M = s_th + s_G - s_z;
+        const double mM = maxabs(M, mc, 0, mc, beta);
+        const int s_M_max = pow2_scale_for(mM, 15);
+        if (s_M > s_M_max) { s_G -= (s_M - s_M_max); s_M = s_M_max; }
+        const int s_T = pow2_scale_for(maxabs(T, ldD, 0, 64, 1.0), 14);
+        const int s_Gf = pow2_scale_for(maxabs(Af, ldf, 0, mf, 1.0), 14);
+        const int s_LP = pow2_scale_for(maxabs(LP, ldD, 0, 64, 1.0), 14);
+        auto bad = [](int s) { return s < -20 || s > 40; };
+        if (bad(s_th) || bad(s_G) || bad(s_M) || bad(s_T) || bad(s_Gf) || bad(s_LP)) { err = "tc16: operands do not fit the fp16 range"; return 1; }
+        if (maxabs(Ac, ldc, 0, mc, a) * std::ldexp(1.0, s_G) < 64.0) { err = "tc16: coarse operator and composed operator differ too much in scale"; return 1; }
+
+        const int nfc = mf / T16_CH, nch = nfc + 1;
+        std::vector<__half> hG((size_t)2 * mc * T16_K), hM((size_t)2 * mc * T16_K), hT((size_t)2 * 64 * T16_K),
+            hF((size_t)nch * 2 * T16_CH * T16_K);
+        canon_split16(Ac, ldc, 0, mc, a, s_G, hG.data(), hG.data() + (size_t)mc * T16_K);
+        canon_split16(M, mc, 0, mc, beta, s_M, hM.data(), hM.data() + (size_t)mc * T16_K);
+        canon_split16(T, ldD, 0, 64, 1.0, s_T, hT.data(), hT.data() + (size_t)64 * T16_K);
+        for (int ch = 0; ch < nfc; ch++)
+            canon_split16(Af, ldf, ch * T16_CH, T16_CH, 1.0, s_Gf, hF.data() + (size_t)ch * 2 * T16_CH * T16_K,
+                          hF.data() + (size_t)ch * 2 * T16_CH * T16_K + T16_CH * T16_K);
+        canon_split16(LP, ldD, 0, T16_CH, 1.0, s_LP, hF.data() + (size_t)nfc * 2 * T16_CH * T16_K,
+                      hF.data() + (size_t)nfc * 2 * T16_CH * T16_K + T16_CH * T16_K);
+        destroy();
+        if (e == cudaSuccess) e = cudaMalloc(&dG, hG.size() * 2);
+        if (e == cudaSuccess) e = cudaMalloc(&dM, hM.size() * 2);
+        if (e == cudaSuccess) e = cudaMalloc(&dT, hT.size() * 2);
+        if (e == cudaSuccess) e = cudaMalloc(&dF, hF.size() * 2);
+        if (e == cudaSuccess) e = cudaMemcpy(dG, hG.data(), hG.size() * 2, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dM, hM.data(), hM.size() * 2, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dT, hT.data(), hT.size() * 2, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dF, hF.data(), hF.size() * 2, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
+        nyc.assign(T16_MAX_MC, 0.f); nyf.assign(T16_MAX_MF, 0.f); nlp.assign(T16_K, 0.f);
+        for (int j = 0; j < mc; j++) nyc[j] = -(float)(dc[j] - bc[j]);
+        for (int j = 0; j < mf; j++) nyf[j] = -(float)(df[j] - bf[j]);
+        for (int n = 0; n < T16_K; n++) {
+            double s = 0;
+            for (int k = 0; k < T16_K; k++) s += mu[k] * LP[(size_t)k * ldD + n];
+            nlp[n] = -(float)s;
+        }
+        q.G_hl = dG; q.M_hl = dM; q.T_hl = dT; q.F_chunks = dF;
+        q.mc = mc; q.mf = mf; q.n_chunks = nch; q.J = c.subchain[0];
+        q.var_c = (float)c.level[0].lik_var; q.var_f = (float)c.level[1].lik_var;
+        q.prior_logconst = (float)c.prior_logconst;
+        q.ca = (float)a;
+        q.cxi = (float)(beta * std::ldexp(1.0, s_th - s_z - s_T));
+        q.sc_c = (float)std::ldexp(1.0, -(s_th + s_G));
+        q.sc_f = (float)std::ldexp(1.0, -(s_th + s_Gf));
+        q.sc_p = (float)std::ldexp(1.0, -(s_th + s_LP));
+        q.th_scale = (float)std::ldexp(1.0, s_th);
+        q.th_unscale = (float)std::ldexp(1.0, -s_th);
+        prepared = true;
+        return 0;
+    }
+
+    int run(Params<float>& P, const tda_config& c, long long iterations, int sm_count, cudaStream_t st) {
+        if (!prepared) { int r = prepare(P, c); if (r) return r; }
+        cudaError_t e;
+        e = cudaMemcpyToSymbolAsync(c16_nyc, nyc.data(), T16_MAX_MC * 4, 0, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c16_nyf, nyf.data(), T16_MAX_MF * 4, 0, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c16_nlp, nlp.data(), T16_K * 4, 0, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { err = std::string("tc16 constants: ") + cudaGetErrorString(e); return -2; }
+        q.n_pairs = P.Cs / 256;
+        const size_t smem = T16_SMEM_BYTES;
+        e = cudaFuncSetAttribute(da_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { err = std::string("tc16 attr: ") + cudaGetErrorString(e); return -2; }
+        P.mode = MODE_RUN;
+        P.iterations = iterations;
+        P.z_round = 1;
+        int grid = q.n_pairs < sm_count ? q.n_pairs : sm_count;
+        da_tc16_kernel<<<grid, T16_THREADS, smem, st>>>(P, q);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { err = std::string("tc16 launch: ") + cudaGetErrorString(e); return -2; }
+        return 0;
+    }
+};
+
+}  // namespace tda

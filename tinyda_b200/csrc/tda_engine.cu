@@ -8,6 +8,7 @@
 
 #include "tda_kernels.cuh"
 #include "tda_da_tc.cuh"
+#include "tda_da_tc16.cuh"
 
 namespace {
 
@@ -75,14 +76,18 @@ struct EngineT : tda_engine {
     int Cs = 0, n_tiles = 0, kt = 0, sm_count = 148;
     size_t smem_bytes = 0;
     bool initialised = false;
-    int kernel_choice = 0;     // 0 auto, 1 generic, 2 tensor-core DA
+    int kernel_choice = 0;     // 0 auto, 1 generic, 2 tensor-core DA (3xTF32), 3 tensor-core DA (fp16 split)
+    int z_round_user = 0;      // generic / TF32 kernels: use the z16 normal stream (tda_set TDA_G_ZROUND)
     std::vector<int> ldA;
     tda::DaTcState<R> tc;      // tcgen05 fast path (float only; inert for double)
+    tda::DaTc16State<R> tc16;  // fp16-split tcgen05 fast path (float only)
+    bool tc16_unfit = false;   // prepare() found operands that do not fit the fp16 range
 
     ~EngineT() override {
         cudaSetDevice(device);
         for (void* p : allocs) cudaFree(p);
         tc.destroy();
+        tc16.destroy();
     }
 
     template <typename T>
@@ -372,6 +377,19 @@ struct EngineT : tda_engine {
     }
 
     bool tc_eligible() const { return tc.eligible(cfg, P); }
+    bool tc16_eligible() const { return !tc16_unfit && tc16.eligible(cfg, P); }
+    // which kernel tda_engine_run launches: 1 generic, 2 tensor-core 3xTF32, 3 tensor-core fp16 split
+    int resolved_kernel() const {
+        if (kernel_choice == 1 || kernel_choice == 2 || kernel_choice == 3) return kernel_choice;
+        if (tc16_eligible()) return 3;
+        if (tc_eligible()) return 2;
+        return 1;
+    }
+    // the fp16-split kernel consumes the z16 normal stream; the others do on request
+    int z_round_effective() const {
+        if (cfg.dtype != TDA_F32 || P.rng_mode != TDA_RNG_PHILOX) return 0;
+        return (resolved_kernel() == 3 || z_round_user) ? 1 : 0;
+    }
 
     int run(long long iterations, cudaStream_t st) override {
         if (!initialised) return fail(-1, "run: call tda_engine_init first");
@@ -382,10 +400,26 @@ struct EngineT : tda_engine {
             if (iterations > to_boundary)
                 return fail(-1, "run: AdaptiveMetropolis with host refactoring must stop at period boundaries");
         }
-        bool use_tc = (kernel_choice == 2) || (kernel_choice == 0 && tc_eligible());
         if (kernel_choice == 2 && !tc_eligible()) return fail(-1, "run: tensor-core DA kernel does not support this configuration");
+        if (kernel_choice == 3 && !tc16.eligible(cfg, P)) return fail(-1, "run: fp16-split tensor-core DA kernel does not support this configuration");
+        int which = resolved_kernel();
+        if (which == 3 && !tc16.prepared) {
+            // operand scaling happens on first use; a problem that does not fit fp16 falls back
+            int r = tc16.prepare(P, cfg);
+            if (r < 0) return fail(r, tc16.err);
+            if (r > 0) {
+                if (kernel_choice == 3) return fail(-1, "run: " + tc16.err);
+                tc16_unfit = true;
+                which = resolved_kernel();
+            }
+        }
+        P.z_round = z_round_effective();
         int r;
-        if (use_tc) {
+        if (which == 3) {
+            r = tc16.run(P, cfg, iterations, sm_count, st);
+            if (r) return fail(r, tc16.err);
+            g_launches++;
+        } else if (which == 2) {
             r = tc.run(P, cfg, iterations, sm_count, st);
             if (r) return fail(r, tc.err);
             g_launches++;
@@ -521,7 +555,14 @@ struct EngineT : tda_engine {
             if (bytes != (size_t)P.C * sizeof(double)) return fail(-1, "set: scaling needs n_chains float64 values");
             std::vector<R> h(Cs, (R)cfg.scaling);
             for (int c = 0; c < P.C; c++) h[c] = (R)reinterpret_cast<const double*>(src)[c];
+            tc16.prepared = false;     // the pCN step is folded into its operators
+            tc16_unfit = false;
             return put(P.scaling, h);
+        }
+        if (what == TDA_G_ZROUND) {
+            if (bytes != sizeof(double)) return fail(-1, "set: z-round flag is one float64");
+            z_round_user = *reinterpret_cast<const double*>(src) != 0.0;
+            return 0;
         }
         return fail(-1, "set: unknown item");
     }
@@ -550,7 +591,7 @@ struct EngineT : tda_engine {
         CUDA_TRY(cudaMalloc(&du, (tu ? tu : 1) * sizeof(double)));
         size_t n = tz > tu ? tz : tu;
         if (n) {
-            tda::fill_streams_kernel<R><<<(unsigned)((n + 255) / 256), 256>>>(P.seed, P.chain_offset, P.C, dz, nz, du, nu);
+            tda::fill_streams_kernel<R><<<(unsigned)((n + 255) / 256), 256>>>(P.seed, P.chain_offset, P.C, dz, nz, du, nu, z_round_effective());
             g_launches++;
         }
         cudaError_t e = cudaGetLastError();
@@ -687,6 +728,15 @@ int tda_tc_gemm_selftest(const float* A, const float* B, int N, float* D, int a_
     return 0;
 }
 int tda_history_reset(tda_engine* e) { return e ? e->history_reset() : fail(-1, "null engine"); }
+int tda_tc16_gemm_selftest(const float* A, const float* B, int N, float* D, int a_in_tmem) {
+    if (!A || !B || !D) return fail(-1, "null argument");
+    std::string err;
+    int r = tda::tc16_gemm_selftest_host(A, B, N, D, a_in_tmem, err);
+    if (r) return fail(r, err);
+    g_launches++;
+    return 0;
+}
+
 int tda_select_kernel(tda_engine* e, int which) { return e ? e->select_kernel(which) : fail(-1, "null engine"); }
 
 }  // extern "C"

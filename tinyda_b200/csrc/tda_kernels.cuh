@@ -198,7 +198,7 @@ struct Tile {
             int ch = chain0 + c;
             return (ch < p.C && idx < p.zlen) ? p.zs[(size_t)ch * p.zlen + idx] : (R)0;
         }
-        return philox_normal<R>(p.seed, p.chain_offset + chain0 + c, idx);
+        return philox_normal<R>(p.seed, p.chain_offset + chain0 + c, idx, p.z_round);
     }
     __device__ __forceinline__ R uniform_at(int c, long long idx) const {
         if (p.rng_mode == TDA_RNG_INJECTED) {
@@ -217,8 +217,9 @@ struct Tile {
             for (int e = tid; e < nb4 * TC; e += NT) {
                 int q = e / TC, c = e - q * TC;
                 R v[4];
-                normals4<R>(philox_block(p.seed, p.chain_offset + chain0 + c, STREAM_Z,
-                                         (unsigned long long)(z0 >> 2) + q), v);
+                const uint4 blk = philox_block(p.seed, p.chain_offset + chain0 + c, STREAM_Z, (unsigned long long)(z0 >> 2) + q);
+                if (p.z_round) normals4_z16(blk, v);
+                else normals4<R>(blk, v);
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                     if (4 * q + i < d) zt[(4 * q + i) * TC + c] = v[i];
@@ -940,12 +941,12 @@ chain_kernel(const __grid_constant__ Params<R> p, int kt) {
 // exports the Philox streams (what TDA_RNG_PHILOX consumes) for the CPU oracle
 template <typename R>
 __global__ void fill_streams_kernel(unsigned long long seed, long long chain_offset, int C,
-                                    double* z, long long nz, double* u, long long nu) {
+                                    double* z, long long nz, double* u, long long nu, int z_round) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total_z = (long long)C * nz, total_u = (long long)C * nu;
     if (i < total_z) {
         long long c = i / nz, k = i - c * nz;
-        z[i] = (double)philox_normal<R>(seed, chain_offset + c, k);
+        z[i] = (double)philox_normal<R>(seed, chain_offset + c, k, z_round);
     }
     if (i < total_u) {
         long long c = i / nu, k = i - c * nu;

@@ -168,5 +168,65 @@ __host__ __device__ __forceinline__ float tf32_hi(float x) {
 #endif
 }
 
+
+// ---- kind::f16 (fp16 operands, fp32 accumulate) ---------------------------------------------
+// Instruction descriptor, kind::f16 with fp16 A and B (a_format = b_format = 0), fp32 accumulate,
+// both operands K-major.  One instruction contracts K = 16.
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4)                     // c_format  = F32
+           | ((uint32_t)(N >> 3) << 17)  // n_dim
+           | ((uint32_t)(M >> 4) << 24); // m_dim
+}
+// canonical no-swizzle K-major placement of element (row, k) of a [rows x K] fp16 operand:
+// core matrix = 8 rows x 8 halves (16 bytes per row), K-adjacent core matrices 128 bytes apart,
+// 8-row groups (K/8)*128 bytes apart
+__host__ __device__ constexpr uint32_t canon_offset_f16(int row, int k, int K) {
+    return (uint32_t)((row >> 3) * (K / 8) * 128 + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T   (A: 128 x 16 fp16 = 8 packed 32-bit TMEM columns)
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// two fp32 -> packed fp16x2 (round to nearest even): low half = x0, high half = x1
+__device__ __forceinline__ uint32_t pack_f16x2(float x0, float x1) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x1), "f"(x0));
+    return d;
+}
+__device__ __forceinline__ float f16lo_to_f32(uint32_t p) {
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(p));
+    return f;
+}
+__device__ __forceinline__ float f16hi_to_f32(uint32_t p) {
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(p));
+    return f;
+}
+// two-term fp16 split of a pair of (pre-scaled) fp32 values: hi = fp16(x), lo = fp16(x - hi);
+// x*y ~= hi_x*hi_y + lo_x*hi_y + hi_x*lo_y with fp32 accumulation keeps ~22 mantissa bits
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_f16x2(x0, x1);
+    lo = pack_f16x2(x0 - f16lo_to_f32(hi), x1 - f16hi_to_f32(hi));
+}
+
+// ---- register re-allocation between warpgroups (all 4 warps of a warpgroup execute it) ---------
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 }  // namespace tc
 }  // namespace tda

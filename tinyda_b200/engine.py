@@ -181,7 +181,14 @@ class Engine:
         check(lib.tda_engine_sync(self._h, self._stream_ptr(stream)))
 
     def select_kernel(self, which):
-        check(lib.tda_select_kernel(self._h, {"auto": 0, "generic": 1, "tc": 2}[which]))
+        """"auto" | "generic" | "tc" (tcgen05, 3xTF32) | "tc16" (tcgen05, fp16 split + RNG warps)."""
+        check(lib.tda_select_kernel(self._h, {"auto": 0, "generic": 1, "tc": 2, "tc16": 3}[which]))
+
+    def set_z_round(self, on=True):
+        """Philox normals on the fp16 grid (the "z16" stream the tc16 kernel consumes) also for the
+        generic / tc kernels -- lets the kernels be compared on identical streams."""
+        v = np.array([1.0 if on else 0.0])
+        check(lib.tda_set(self._h, L.TDA_G_ZROUND, 0, v.ctypes.data_as(C.c_void_p), v.nbytes))
 
     def history_reset(self):
         check(lib.tda_history_reset(self._h))
