@@ -38,9 +38,13 @@ constexpr int T16_K = 64;                       // parameters (contraction lengt
 constexpr int T16_CH = 64;                      // columns per streamed fine-operator chunk
 constexpr int T16_NST = 4;                      // ring stages
 constexpr int T16_MAX_MC = 128;
-constexpr int T16_MAX_MF = 4096;
-constexpr int T16_RNG_WARPS = 8;                // warps 0..7   (warpgroups 0-1)
-constexpr int T16_ROW_WARP0 = 8;                // warps 8..23  (warpgroups 2-5)
+constexpr int T16_MAX_MF = 1920;                // the negated data vector stays resident in shared memory
+// The warp scheduler prefers the highest warp id among ready warps: the MMA issuers come first,
+// then the RNG warps (the throughput-critical producers; alone they need ~4400 cycles per coarse
+// step of both tiles), then the row warps, which fill the remaining issue slots.
+constexpr int T16_ROW_WARP0 = 0;                // warps 0..15  (warpgroups 0-3)
+constexpr int T16_RNG_WARP0 = 16;               // warps 16..23 (warpgroups 4-5)
+constexpr int T16_RNG_WARPS = 8;
 constexpr int T16_MMA_WARP0 = 24;               // warps 24, 25 (one per tile)
 constexpr int T16_PROD_WARP = 26;               // warp 27 idles (completes warpgroup 6)
 constexpr int T16_THREADS = 28 * 32;
@@ -58,18 +62,19 @@ constexpr int T16_OFF_Z = T16_OFF_RING + T16_NST * T16_CHUNK_BYTES;   // [tile 2
 constexpr int T16_OFF_PART = T16_OFF_Z + 4 * T16_IMG;          // [buf 2][tile 2][half 2][128] f32
 constexpr int T16_OFF_U = T16_OFF_PART + 2 * 2 * 2 * 128 * 4;  // [buf 2][tile 2][128] f32
 constexpr int T16_OFF_PF = T16_OFF_U + 2 * 2 * 128 * 4;        // [tile 2][half 2][val 2][128] f32
-constexpr int T16_OFF_BARS = T16_OFF_PF + 2 * 2 * 2 * 128 * 4;
+constexpr int T16_OFF_NY = T16_OFF_PF + 2 * 2 * 2 * 128 * 4;   // f32: [-y_c 128 | -(mu @ LP) 64 | -y_f mf]
+constexpr int T16_NY_FLOATS = T16_MAX_MC + T16_K + T16_MAX_MF;
+constexpr int T16_OFF_BARS = T16_OFF_NY + T16_NY_FLOATS * 4;
 constexpr size_t T16_SMEM_BYTES = T16_OFF_BARS + 256;
+static_assert(T16_SMEM_BYTES <= 232448, "shared memory budget");
 
-__constant__ float c16_nyc[T16_MAX_MC];     // -(coarse data - offset)
-__constant__ float c16_nyf[T16_MAX_MF];     // -(fine data - offset)
-__constant__ float c16_nlp[T16_K];          // -(prior_mean @ LP)
 
 struct DaTc16Params {
     const __half* G_hl;       // [hi mc x 64 | lo mc x 64] canonical K-major, a G_c^T  * 2^sG
     const __half* M_hl;       // [hi mc x 64 | lo mc x 64]                  b T G_c^T * 2^sM
     const __half* T_hl;       // [hi 64 x 64 | lo 64 x 64]                  T         * 2^sT
     const __half* F_chunks;   // n_chunks x [hi 64 x 64 | lo 64 x 64]  fine operator columns, then LP
+    const float* ny;          // [-(y_c - b_c) 128 | -(mu @ LP) 64 | -(y_f - b_f) mf]
     int mc, mf, n_chunks, J;
     float var_c, var_f, prior_logconst;
     float ca;                 // sqrt(1 - beta^2)
@@ -289,6 +294,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     float* s_part = reinterpret_cast<float*>(smem + T16_OFF_PART);
     float* s_u = reinterpret_cast<float*>(smem + T16_OFF_U);
     float* s_pf = reinterpret_cast<float*>(smem + T16_OFF_PF);
+    const float* s_ny = reinterpret_cast<const float*>(smem + T16_OFF_NY);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T16_OFF_BARS);
     uint64_t* bar_res = bars;                       // resident operands landed
     uint64_t* bar_req = bars + 1;                   // [tile 2][buffer 2]  rows -> MMA
@@ -322,12 +328,12 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     const long long iters = p.iterations;
     const bool inj = p.rng_mode == TDA_RNG_INJECTED;
 
-    if (warp < T16_RNG_WARPS) {
+    if (warp >= T16_RNG_WARP0 && warp < T16_RNG_WARP0 + T16_RNG_WARPS) {
         // =====================================================================================
         // RNG warps: thread = one chain of one tile; 64 normals per coarse step -> z image(s)
         // =====================================================================================
         tc::setmaxnreg_dec<T16_REGS_RNG>();
-        const int t = warp >> 2;
+        const int t = (warp - T16_RNG_WARP0) >> 2;
         const int row = (warp & 3) * 32 + lane;
         unsigned char* zt = zbuf + (size_t)t * 2 * T16_IMG + (row >> 3) * ((T16_K / 8) * 128) + (row & 7) * 16;
         uint64_t* zfull = bar_zfull + t * 2;
@@ -390,7 +396,9 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             if (lane == 0) {
                 const long long total_chunks = (long long)my_pairs * iters * NCH;
                 const uint32_t bI = (uint32_t)mc * T16_K * 2;       // one mc-row image
-                tc::mbar_expect_tx(bar_res, 4 * bI + 2 * T16_TIMG);
+                const uint32_t bNY = (uint32_t)(T16_MAX_MC + T16_K + q.mf) * 4;
+                tc::mbar_expect_tx(bar_res, 4 * bI + 2 * T16_TIMG + bNY);
+                tc::bulk_g2s(smem + T16_OFF_NY, q.ny, bNY, bar_res);
                 tc::bulk_g2s(sG, q.G_hl, bI, bar_res);
                 tc::bulk_g2s(sG + T16_IMG, q.G_hl + (size_t)mc * T16_K, bI, bar_res);
                 tc::bulk_g2s(sM, q.M_hl, bI, bar_res);
@@ -405,49 +413,56 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 }
             }
         } else if (warp < T16_PROD_WARP) {
-            // ===== MMA issuer of tile t =====
+            // ===== MMA issuer of tile t: the whole warp runs the (uniform) control flow so that
+            // descriptors live in uniform registers; one elected lane issues =====
             const int t = warp - T16_MMA_WARP0;
-            if (lane == 0) {
-                tc::mbar_wait(bar_res, 0);
-                const uint32_t tA = tbase + t * 256, tD = tA + 64;
-                const uint32_t sG_hi = tc::smem_u32(sG), sG_lo = sG_hi + T16_IMG;
-                const uint32_t sM_hi = tc::smem_u32(sM), sM_lo = sM_hi + T16_IMG;
-                const uint32_t sT_hi = tc::smem_u32(sT), sT_lo = sT_hi + T16_TIMG;
-                const uint32_t z_base = tc::smem_u32(zbuf) + t * 2 * T16_IMG;
-                const uint32_t idesc_c = tc::idesc_f16(128, mc), idesc_64 = tc::idesc_f16(128, 64);
-                uint64_t* req = bar_req + t * 2;
-                uint64_t* resp = bar_resp + t * 2;
-                uint32_t rq0 = 0, rq1 = 0;
-                long long n = 0, gch = 0;
-                const long long total_it = (long long)my_pairs * iters;
-                for (long long itg = 0; itg < total_it; itg++) {
-                    for (int j = 0; j < J; j++, n++) {
-                        const int b = inj ? 0 : (int)(n & 1);
-                        const long long use = inj ? n : (n >> 1);
-                        tc::mbar_wait(req, rq0); rq0 ^= 1;
-                        tc::fence_after_sync();
-                        // theta part first: it does not need this step's normals
-                        t16_issue_theta(tD, tA, sG_hi, sG_lo, idesc_c, 0);
-                        tc::mbar_wait(bar_zfull + t * 2 + b, (uint32_t)(use & 1));
-                        tc::fence_after_sync();
+            tc::mbar_wait(bar_res, 0);
+            const uint32_t tA = tbase + t * 256, tD = tA + 64;
+            const uint32_t sG_hi = tc::smem_u32(sG), sG_lo = sG_hi + T16_IMG;
+            const uint32_t sM_hi = tc::smem_u32(sM), sM_lo = sM_hi + T16_IMG;
+            const uint32_t sT_hi = tc::smem_u32(sT), sT_lo = sT_hi + T16_TIMG;
+            const uint32_t z_base = tc::smem_u32(zbuf) + t * 2 * T16_IMG;
+            const uint32_t ring_base = tc::smem_u32(ring);
+            const uint32_t idesc_c = tc::idesc_f16(128, mc), idesc_64 = tc::idesc_f16(128, 64);
+            uint64_t* req = bar_req + t * 2;
+            uint64_t* resp = bar_resp + t * 2;
+            uint32_t rq0 = 0, rq1 = 0;
+            long long n = 0, gch = 0;
+            const long long total_it = (long long)my_pairs * iters;
+            for (long long itg = 0; itg < total_it; itg++) {
+                for (int j = 0; j < J; j++, n++) {
+                    const int b = inj ? 0 : (int)(n & 1);
+                    const long long use = inj ? n : (n >> 1);
+                    tc::mbar_wait(req, rq0); rq0 ^= 1;
+                    tc::fence_after_sync();
+                    // theta part first: it does not need this step's normals
+                    if (tc::elect_one()) t16_issue_theta(tD, tA, sG_hi, sG_lo, idesc_c, 0);
+                    __syncwarp();
+                    tc::mbar_wait(bar_zfull + t * 2 + b, (uint32_t)(use & 1));
+                    tc::fence_after_sync();
+                    if (tc::elect_one()) {
                         const uint32_t z_hi = z_base + b * T16_IMG, z_lo = z_base + T16_IMG;
                         t16_issue_z(tD, z_hi, z_lo, inj, sM_hi, sM_lo, idesc_c, 1);
                         t16_issue_z(tD + 128, z_hi, z_lo, inj, sT_hi, sT_lo, idesc_64, 0);
                         tc::mma_commit(resp);
                         tc::mma_commit(bar_zfree + t * 2 + b);
                     }
-                    for (int c = 0; c < NCH; c++, gch++) {
-                        const int b = c & 1;
-                        const int st = (int)(gch % T16_NST);
-                        if (b) { tc::mbar_wait(req + 1, rq1); rq1 ^= 1; }
-                        else { tc::mbar_wait(req, rq0); rq0 ^= 1; }
-                        tc::mbar_wait(bar_full + st, (uint32_t)((gch / T16_NST) & 1));
-                        tc::fence_after_sync();
-                        const uint32_t b_hi = tc::smem_u32(ring + (size_t)st * T16_CHUNK_BYTES), b_lo = b_hi + T16_TIMG;
+                    __syncwarp();
+                }
+                for (int c = 0; c < NCH; c++, gch++) {
+                    const int b = c & 1;
+                    const int st = (int)(gch % T16_NST);
+                    if (b) { tc::mbar_wait(req + 1, rq1); rq1 ^= 1; }
+                    else { tc::mbar_wait(req, rq0); rq0 ^= 1; }
+                    tc::mbar_wait(bar_full + st, (uint32_t)((gch / T16_NST) & 1));
+                    tc::fence_after_sync();
+                    if (tc::elect_one()) {
+                        const uint32_t b_hi = ring_base + st * T16_CHUNK_BYTES, b_lo = b_hi + T16_TIMG;
                         t16_issue_theta(tD + b * T16_CH, tA, b_hi, b_lo, idesc_64, 0);
                         tc::mma_commit(resp + b);
                         tc::mma_commit(bar_empty + st);
                     }
+                    __syncwarp();
                 }
             }
         }
@@ -475,6 +490,16 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         const float ca = q.ca, cxi = q.cxi, sc_c = q.sc_c, sc_f = q.sc_f, sc_p = q.sc_p;
         const float th_scale = q.th_scale, th_unscale = q.th_unscale;
         const int ngc = mc >> 4, gc0 = h ? (ngc + 1) / 2 : 0, gc1 = h ? ngc : (ngc + 1) / 2;
+        // One warp per tile waits on the MMA's mbarrier; the other seven block in a named barrier
+        // (blocked warps take no issue slots, spinning mbarrier waiters do).
+        const bool leader = (h == 0 && wq == 0);
+        auto wait_mma = [&](uint64_t* bar, uint32_t& ph) {
+            if (leader) tc::mbar_wait(bar, ph);
+            ph ^= 1;
+            tc::named_bar_sync(3 + t, 256);
+            tc::fence_after_sync();
+        };
+        tc::mbar_wait(bar_res, 0);                     // the data vector arrives with the resident operands
 
         for (int pr = 0; pr < my_pairs; pr++) {
             const int pair = (int)blockIdx.x + pr * (int)gridDim.x;
@@ -516,16 +541,33 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     float u_mine = 0.0f;
                     if (h == 0) u_mine = draw_u();
                     ucur++;
-                    tc::mbar_wait(resp, ph0); ph0 ^= 1;
-                    tc::fence_after_sync();
+                    wait_mma(resp, ph0);
                     float ssq = 0.0f;
-                    for (int gc = gc0; gc < gc1; gc++) {
+                    int gc = gc0;
+                    for (; gc + 1 < gc1; gc += 2) {
+                        uint32_t v0[16], v1[16];
+                        tc::tmem_ld16(tD + gc * 16, v0);
+                        tc::tmem_ld16(tD + gc * 16 + 16, v1);
+                        const float4* ny4 = reinterpret_cast<const float4*>(s_ny + gc * 16);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; i4++) {
+                            const float4 y0 = ny4[i4], y1 = ny4[4 + i4];
+                            const float r0 = fmaf(__uint_as_float(v0[4 * i4 + 0]), sc_c, y0.x), r1 = fmaf(__uint_as_float(v0[4 * i4 + 1]), sc_c, y0.y);
+                            const float r2 = fmaf(__uint_as_float(v0[4 * i4 + 2]), sc_c, y0.z), r3 = fmaf(__uint_as_float(v0[4 * i4 + 3]), sc_c, y0.w);
+                            const float r4 = fmaf(__uint_as_float(v1[4 * i4 + 0]), sc_c, y1.x), r5 = fmaf(__uint_as_float(v1[4 * i4 + 1]), sc_c, y1.y);
+                            const float r6 = fmaf(__uint_as_float(v1[4 * i4 + 2]), sc_c, y1.z), r7 = fmaf(__uint_as_float(v1[4 * i4 + 3]), sc_c, y1.w);
+                            ssq = fmaf(r0, r0, ssq); ssq = fmaf(r1, r1, ssq); ssq = fmaf(r2, r2, ssq); ssq = fmaf(r3, r3, ssq);
+                            ssq = fmaf(r4, r4, ssq); ssq = fmaf(r5, r5, ssq); ssq = fmaf(r6, r6, ssq); ssq = fmaf(r7, r7, ssq);
+                        }
+                    }
+                    if (gc < gc1) {
                         uint32_t v[16];
                         tc::tmem_ld16(tD + gc * 16, v);
                         tc::tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
-                            const float r = fmaf(__uint_as_float(v[i]), sc_c, c16_nyc[gc * 16 + i]);
+                            const float r = fmaf(__uint_as_float(v[i]), sc_c, s_ny[gc * 16 + i]);
                             ssq = fmaf(r, r, ssq);
                         }
                     }
@@ -569,31 +611,30 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 float ssq_f = 0.0f, ssq_p = 0.0f;
                 for (int c = 0; c < NCH; c++) {
                     const int b = c & 1;
-                    if (b) { tc::mbar_wait(resp + 1, ph1); ph1 ^= 1; }
-                    else { tc::mbar_wait(resp, ph0); ph0 ^= 1; }
-                    tc::fence_after_sync();
+                    if (b) wait_mma(resp + 1, ph1);
+                    else wait_mma(resp, ph0);
                     uint32_t v0[16], v1[16];
                     tc::tmem_ld16(tD + b * T16_CH + col0, v0);
                     tc::tmem_ld16(tD + b * T16_CH + col0 + 16, v1);
+                    const bool last = (c == NCH - 1);
+                    const float4* ny4 = reinterpret_cast<const float4*>(last ? s_ny + T16_MAX_MC + col0
+                                                                             : s_ny + T16_MAX_MC + T16_K + c * T16_CH + col0);
+                    const float scl = last ? sc_p : sc_f;
                     tc::tmem_wait_ld();
                     if (c + 2 < NCH) t16_warp_arrive(req + b, lane);
-                    if (c < NCH - 1) {
+                    float acc2 = 0.0f;
 #pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            const float r0 = fmaf(__uint_as_float(v0[i]), sc_f, c16_nyf[c * T16_CH + col0 + i]);
-                            const float r1 = fmaf(__uint_as_float(v1[i]), sc_f, c16_nyf[c * T16_CH + col0 + 16 + i]);
-                            ssq_f = fmaf(r0, r0, ssq_f);
-                            ssq_f = fmaf(r1, r1, ssq_f);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            const float w0 = fmaf(__uint_as_float(v0[i]), sc_p, c16_nlp[col0 + i]);
-                            const float w1 = fmaf(__uint_as_float(v1[i]), sc_p, c16_nlp[col0 + 16 + i]);
-                            ssq_p = fmaf(w0, w0, ssq_p);
-                            ssq_p = fmaf(w1, w1, ssq_p);
-                        }
+                    for (int i4 = 0; i4 < 4; i4++) {
+                        const float4 y0 = ny4[i4], y1 = ny4[4 + i4];
+                        const float r0 = fmaf(__uint_as_float(v0[4 * i4 + 0]), scl, y0.x), r1 = fmaf(__uint_as_float(v0[4 * i4 + 1]), scl, y0.y);
+                        const float r2 = fmaf(__uint_as_float(v0[4 * i4 + 2]), scl, y0.z), r3 = fmaf(__uint_as_float(v0[4 * i4 + 3]), scl, y0.w);
+                        const float r4 = fmaf(__uint_as_float(v1[4 * i4 + 0]), scl, y1.x), r5 = fmaf(__uint_as_float(v1[4 * i4 + 1]), scl, y1.y);
+                        const float r6 = fmaf(__uint_as_float(v1[4 * i4 + 2]), scl, y1.z), r7 = fmaf(__uint_as_float(v1[4 * i4 + 3]), scl, y1.w);
+                        acc2 = fmaf(r0, r0, acc2); acc2 = fmaf(r1, r1, acc2); acc2 = fmaf(r2, r2, acc2); acc2 = fmaf(r3, r3, acc2);
+                        acc2 = fmaf(r4, r4, acc2); acc2 = fmaf(r5, r5, acc2); acc2 = fmaf(r6, r6, acc2); acc2 = fmaf(r7, r7, acc2);
                     }
+                    if (last) ssq_p += acc2;
+                    else ssq_f += acc2;
                 }
                 float* sf = s_pf + (t * 2) * 256;
                 sf[h * 256 + cl] = ssq_f;
@@ -683,9 +724,9 @@ template <>
 struct DaTc16State<float> {
     std::string err;
     __half *dG = nullptr, *dM = nullptr, *dT = nullptr, *dF = nullptr;
+    float* dNY = nullptr;
     bool prepared = false;
     DaTc16Params q{};
-    std::vector<float> nyc, nyf, nlp;
 
     bool eligible(const tda_config& c, const Params<float>& P) const {
         if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.prop_kind != TDA_PROP_PCN || c.adaptive) return false;
@@ -705,7 +746,9 @@ struct DaTc16State<float> {
         if (dM) cudaFree(dM);
         if (dT) cudaFree(dT);
         if (dF) cudaFree(dF);
+        if (dNY) cudaFree(dNY);
         dG = dM = dT = dF = nullptr;
+        dNY = nullptr;
         prepared = false;
     }
 
@@ -796,15 +839,18 @@ struct DaTc16State<float> {
         if (e == cudaSuccess) e = cudaMemcpy(dT, hT.data(), hT.size() * 2, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(dF, hF.data(), hF.size() * 2, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
-        nyc.assign(T16_MAX_MC, 0.f); nyf.assign(T16_MAX_MF, 0.f); nlp.assign(T16_K, 0.f);
-        for (int j = 0; j < mc; j++) nyc[j] = -(float)(dc[j] - bc[j]);
-        for (int j = 0; j < mf; j++) nyf[j] = -(float)(df[j] - bf[j]);
+        std::vector<float> ny((size_t)T16_MAX_MC + T16_K + mf, 0.f);
+        for (int j = 0; j < mc; j++) ny[j] = -(float)(dc[j] - bc[j]);
         for (int n = 0; n < T16_K; n++) {
             double s = 0;
             for (int k = 0; k < T16_K; k++) s += mu[k] * LP[(size_t)k * ldD + n];
-            nlp[n] = -(float)s;
+            ny[T16_MAX_MC + n] = -(float)s;
         }
-        q.G_hl = dG; q.M_hl = dM; q.T_hl = dT; q.F_chunks = dF;
+        for (int j = 0; j < mf; j++) ny[T16_MAX_MC + T16_K + j] = -(float)(df[j] - bf[j]);
+        e = cudaMalloc(&dNY, ny.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(dNY, ny.data(), ny.size() * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
+        q.G_hl = dG; q.M_hl = dM; q.T_hl = dT; q.F_chunks = dF; q.ny = dNY;
         q.mc = mc; q.mf = mf; q.n_chunks = nch; q.J = c.subchain[0];
         q.var_c = (float)c.level[0].lik_var; q.var_f = (float)c.level[1].lik_var;
         q.prior_logconst = (float)c.prior_logconst;
@@ -822,10 +868,7 @@ struct DaTc16State<float> {
     int run(Params<float>& P, const tda_config& c, long long iterations, int sm_count, cudaStream_t st) {
         if (!prepared) { int r = prepare(P, c); if (r) return r; }
         cudaError_t e;
-        e = cudaMemcpyToSymbolAsync(c16_nyc, nyc.data(), T16_MAX_MC * 4, 0, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c16_nyf, nyf.data(), T16_MAX_MF * 4, 0, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c16_nlp, nlp.data(), T16_K * 4, 0, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) { err = std::string("tc16 constants: ") + cudaGetErrorString(e); return -2; }
+        (void)st;
         q.n_pairs = P.Cs / 256;
         const size_t smem = T16_SMEM_BYTES;
         e = cudaFuncSetAttribute(da_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
