@@ -125,6 +125,26 @@ __device__ __forceinline__ void tsincospi(double x, double* s, double* c) { sinc
 __device__ __forceinline__ bool tisnan(float x) { return isnan(x); }
 __device__ __forceinline__ bool tisnan(double x) { return isnan(x); }
 
+// ---- packed fp32 pairs (FFMA2 / FMUL2 on sm_100): two lanes of fp32 math per instruction -------
+__device__ __forceinline__ unsigned long long f2pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long f2mul(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: random access by draw index --------
 // 32 x 32 -> 64-bit product split into halves: one IMAD.WIDE on the device
 __host__ __device__ __forceinline__ void mulwide32(uint32_t a, uint32_t m, uint32_t& hi, uint32_t& lo) {
@@ -215,9 +235,13 @@ __device__ __forceinline__ void normals4<float>(uint4 b, float out[4]) {
 }
 
 // "z16" normal stream of the float engine (used by the fp16-split tensor-core kernel and by every
-// other kernel / tda_fill_streams when Params::z_round is set): the normal is generated at scale
-// 4096, rounded to the nearest fp16 and scaled back, i.e. it lies on an 11-bit-mantissa grid so
-// that it is ONE exact fp16 tensor-core operand (rounding is unbiased, relative step 2^-11).
+// other kernel / tda_fill_streams when Params::z_round is set).
+//  * bits: normals 16g .. 16g+15 of a chain come from Philox blocks 3g, 3g+1, 3g+2 of its Z stream;
+//    their 384 bits are cut into sixteen 24-bit fields (bm_pair uses the low 23 bits of a field),
+//    pair p of the group takes field 2p (radius) and 2p+1 (angle) -> normals 2p (cos), 2p+1 (sin).
+//    12 blocks per 64 normals instead of 16: the Philox multiplies dominate the generator's cost.
+//  * value: generated at scale 4096, rounded to the nearest fp16 and scaled back, i.e. on an
+//    11-bit-mantissa grid, so that it is ONE exact fp16 tensor-core operand (rounding is unbiased).
 __device__ __forceinline__ float z16_round(float scaled) {
     unsigned short h;
     asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(scaled));
@@ -225,26 +249,38 @@ __device__ __forceinline__ float z16_round(float scaled) {
     asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
     return f * Z16_UNSCALE;
 }
-__device__ __forceinline__ void normals4_z16(uint4 b, float out[4]) {
-    float s[4];
-    bm_pair(b.x, b.y, BM_C_X4096, s[0], s[1]);
-    bm_pair(b.z, b.w, BM_C_X4096, s[2], s[3]);
-#pragma unroll
-    for (int i = 0; i < 4; i++) out[i] = z16_round(s[i]);
+__device__ __forceinline__ void z16_fields4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t f[4]) {
+    f[0] = w0;
+    f[1] = __funnelshift_r(w0, w1, 24);
+    f[2] = __funnelshift_r(w1, w2, 16);
+    f[3] = w2 >> 8;
 }
-__device__ __forceinline__ void normals4_z16(uint4 b, double out[4]) {
-    float f[4];
-    normals4_z16(b, f);
+// sixteen normals at scale 4096 (not yet rounded) from the three blocks of a group
+__device__ __forceinline__ void z16_group_scaled(uint4 b0, uint4 b1, uint4 b2, float s[16]) {
+    uint32_t f[16];
+    z16_fields4(b0.x, b0.y, b0.z, f);
+    z16_fields4(b0.w, b1.x, b1.y, f + 4);
+    z16_fields4(b1.z, b1.w, b2.x, f + 8);
+    z16_fields4(b2.y, b2.z, b2.w, f + 12);
 #pragma unroll
-    for (int i = 0; i < 4; i++) out[i] = (double)f[i];
+    for (int pr = 0; pr < 8; pr++) bm_pair(f[2 * pr], f[2 * pr + 1], BM_C_X4096, s[2 * pr], s[2 * pr + 1]);
+}
+__device__ __forceinline__ float philox_normal_z16(unsigned long long seed, long long chain, long long idx) {
+    const unsigned long long g = (unsigned long long)idx >> 4;
+    float s[16];
+    z16_group_scaled(philox_block(seed, chain, STREAM_Z, 3 * g), philox_block(seed, chain, STREAM_Z, 3 * g + 1),
+                     philox_block(seed, chain, STREAM_Z, 3 * g + 2), s);
+    float v = s[0];
+#pragma unroll
+    for (int i = 1; i < 16; i++) v = ((int)(idx & 15) == i) ? s[i] : v;
+    return z16_round(v);
 }
 
 template <typename R>
 __device__ __forceinline__ R philox_normal(unsigned long long seed, long long chain, long long idx, int z_round = 0) {
+    if (z_round) return (R)philox_normal_z16(seed, chain, idx);
     R v[4];
-    const uint4 b = philox_block(seed, chain, STREAM_Z, (unsigned long long)idx >> 2);
-    if (z_round) normals4_z16(b, v);
-    else normals4<R>(b, v);
+    normals4<R>(philox_block(seed, chain, STREAM_Z, (unsigned long long)idx >> 2), v);
     return v[idx & 3];
 }
 

@@ -65,7 +65,7 @@ constexpr int T16_OFF_PF = T16_OFF_U + 2 * 2 * 128 * 4;        // [tile 2][half 
 constexpr int T16_OFF_NY = T16_OFF_PF + 2 * 2 * 2 * 128 * 4;   // f32: [-y_c 128 | -(mu @ LP) 64 | -y_f mf]
 constexpr int T16_NY_FLOATS = T16_MAX_MC + T16_K + T16_MAX_MF;
 constexpr int T16_OFF_BARS = T16_OFF_NY + T16_NY_FLOATS * 4;
-constexpr size_t T16_SMEM_BYTES = T16_OFF_BARS + 256;
+constexpr size_t T16_SMEM_BYTES = T16_OFF_BARS + 512;
 static_assert(T16_SMEM_BYTES <= 232448, "shared memory budget");
 
 
@@ -297,21 +297,31 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     const float* s_ny = reinterpret_cast<const float*>(smem + T16_OFF_NY);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T16_OFF_BARS);
     uint64_t* bar_res = bars;                       // resident operands landed
-    uint64_t* bar_req = bars + 1;                   // [tile 2][buffer 2]  rows -> MMA
-    uint64_t* bar_resp = bars + 5;                  // [tile 2][buffer 2]  MMA  -> rows
-    uint64_t* bar_zfull = bars + 9;                 // [tile 2][buffer 2]  RNG  -> MMA
-    uint64_t* bar_zfree = bars + 13;                // [tile 2][buffer 2]  MMA  -> RNG
-    uint64_t* bar_full = bars + 17;                 // [NST]
-    uint64_t* bar_empty = bars + 17 + T16_NST;      // [NST]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 17 + 2 * T16_NST);
+    uint64_t* bar_reqA = bars + 1;                  // [tile]     rows -> MMA: D[0:128) consumed
+    uint64_t* bar_reqB = bars + 3;                  // [tile]     rows -> MMA: A_theta current, D_xi consumed
+    uint64_t* bar_respA = bars + 5;                 // [tile]     MMA  -> rows: F_c(theta') complete in D[0:128)
+    uint64_t* bar_respB = bars + 7;                 // [tile]     MMA  -> rows: xi complete in D[128:192)
+    uint64_t* bar_reqF = bars + 9;                  // [tile][buffer] rows -> MMA: fine-chunk accumulator consumed
+    uint64_t* bar_respF = bars + 13;                // [tile][buffer] MMA  -> rows: fine chunk complete
+    uint64_t* bar_zfull = bars + 17;                // [tile][buffer] RNG  -> MMA
+    uint64_t* bar_zfree = bars + 21;                // [tile][buffer] MMA  -> RNG
+    uint64_t* bar_full = bars + 25;                 // [NST]
+    uint64_t* bar_empty = bars + 25 + T16_NST;      // [NST]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 25 + 2 * T16_NST);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == T16_MMA_WARP0) tc::tmem_alloc(s_tmem, 512);
     if (tid == T16_PROD_WARP * 32) {
         tc::mbar_init(bar_res, 1);
+        for (int i = 0; i < 2; i++) {
+            tc::mbar_init(bar_reqA + i, 8);
+            tc::mbar_init(bar_reqB + i, 8);
+            tc::mbar_init(bar_respA + i, 1);
+            tc::mbar_init(bar_respB + i, 1);
+        }
         for (int i = 0; i < 4; i++) {
-            tc::mbar_init(bar_req + i, 8);
-            tc::mbar_init(bar_resp + i, 1);
+            tc::mbar_init(bar_reqF + i, 8);
+            tc::mbar_init(bar_respF + i, 1);
             tc::mbar_init(bar_zfull + i, 4);
             tc::mbar_init(bar_zfree + i, 1);
         }
@@ -352,22 +362,21 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 if (use >= 1) tc::mbar_wait(zfree + b, (uint32_t)((use - 1) & 1));
                 unsigned char* dst = zt + (size_t)b * T16_IMG;
                 if (!inj) {
-                    const unsigned long long blk0 = (unsigned long long)(tb * (T16_K / 4));
-#pragma unroll 2
-                    for (int kg = 0; kg < T16_K / 8; kg++) {
-                        const uint4 b0 = philox_block(p.seed, gchain, STREAM_Z, blk0 + 2 * kg);
-                        const uint4 b1 = philox_block(p.seed, gchain, STREAM_Z, blk0 + 2 * kg + 1);
-                        float s[8];
-                        bm_pair(b0.x, b0.y, BM_C_X4096, s[0], s[1]);
-                        bm_pair(b0.z, b0.w, BM_C_X4096, s[2], s[3]);
-                        bm_pair(b1.x, b1.y, BM_C_X4096, s[4], s[5]);
-                        bm_pair(b1.z, b1.w, BM_C_X4096, s[6], s[7]);
-                        uint4 w;
-                        w.x = tc::pack_f16x2(s[0], s[1]);
-                        w.y = tc::pack_f16x2(s[2], s[3]);
-                        w.z = tc::pack_f16x2(s[4], s[5]);
-                        w.w = tc::pack_f16x2(s[6], s[7]);
-                        *reinterpret_cast<uint4*>(dst + kg * 128) = w;
+                    // z16 stream: 64 normals = 4 groups of 3 Philox blocks (24-bit fields)
+                    const unsigned long long grp0 = (unsigned long long)(tb * (T16_K / 16));
+#pragma unroll 1
+                    for (int q4 = 0; q4 < T16_K / 16; q4++) {
+                        const unsigned long long b3 = 3 * (grp0 + q4);
+                        float s[16];
+                        z16_group_scaled(philox_block(p.seed, gchain, STREAM_Z, b3), philox_block(p.seed, gchain, STREAM_Z, b3 + 1),
+                                         philox_block(p.seed, gchain, STREAM_Z, b3 + 2), s);
+                        uint4 w0, w1;
+                        w0.x = tc::pack_f16x2(s[0], s[1]);   w0.y = tc::pack_f16x2(s[2], s[3]);
+                        w0.z = tc::pack_f16x2(s[4], s[5]);   w0.w = tc::pack_f16x2(s[6], s[7]);
+                        w1.x = tc::pack_f16x2(s[8], s[9]);   w1.y = tc::pack_f16x2(s[10], s[11]);
+                        w1.z = tc::pack_f16x2(s[12], s[13]); w1.w = tc::pack_f16x2(s[14], s[15]);
+                        *reinterpret_cast<uint4*>(dst + (2 * q4) * 128) = w0;
+                        *reinterpret_cast<uint4*>(dst + (2 * q4 + 1) * 128) = w1;
                     }
                 } else {
                     const long long z0 = tb * T16_K;
@@ -424,42 +433,58 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             const uint32_t z_base = tc::smem_u32(zbuf) + t * 2 * T16_IMG;
             const uint32_t ring_base = tc::smem_u32(ring);
             const uint32_t idesc_c = tc::idesc_f16(128, mc), idesc_64 = tc::idesc_f16(128, 64);
-            uint64_t* req = bar_req + t * 2;
-            uint64_t* resp = bar_resp + t * 2;
-            uint32_t rq0 = 0, rq1 = 0;
+            uint64_t* reqA = bar_reqA + t;
+            uint64_t* reqB = bar_reqB + t;
+            uint64_t* respA = bar_respA + t;
+            uint64_t* respB = bar_respB + t;
+            uint64_t* reqF = bar_reqF + t * 2;
+            uint64_t* respF = bar_respF + t * 2;
+            uint32_t pa = 0, pb = 0, pf0 = 0, pf1 = 0;
             long long n = 0, gch = 0;
             const long long total_it = (long long)my_pairs * iters;
             for (long long itg = 0; itg < total_it; itg++) {
+                // Per coarse step three MMA groups with their own dependencies:
+                //   G1  z @ (b T G_c^T) -> D[0:128)   needs the normals and the rows' residual pass of the
+                //                                      previous step -- it runs WHILE the rows still update theta
+                //   G2  theta @ (a G_c^T), accumulating on G1   needs the updated A_theta
+                //   G3  xi = z @ T      -> D[128:192) needs the rows' previous xi read (same signal as G2)
                 for (int j = 0; j < J; j++, n++) {
                     const int b = inj ? 0 : (int)(n & 1);
                     const long long use = inj ? n : (n >> 1);
-                    tc::mbar_wait(req, rq0); rq0 ^= 1;
-                    tc::fence_after_sync();
-                    // theta part first: it does not need this step's normals
-                    if (tc::elect_one()) t16_issue_theta(tD, tA, sG_hi, sG_lo, idesc_c, 0);
-                    __syncwarp();
+                    const uint32_t z_hi = z_base + b * T16_IMG, z_lo = z_base + T16_IMG;
+                    tc::mbar_wait(reqA, pa); pa ^= 1;
                     tc::mbar_wait(bar_zfull + t * 2 + b, (uint32_t)(use & 1));
                     tc::fence_after_sync();
+                    if (tc::elect_one()) t16_issue_z(tD, z_hi, z_lo, inj, sM_hi, sM_lo, idesc_c, 0);
+                    __syncwarp();
+                    tc::mbar_wait(reqB, pb); pb ^= 1;
+                    tc::fence_after_sync();
                     if (tc::elect_one()) {
-                        const uint32_t z_hi = z_base + b * T16_IMG, z_lo = z_base + T16_IMG;
-                        t16_issue_z(tD, z_hi, z_lo, inj, sM_hi, sM_lo, idesc_c, 1);
+                        t16_issue_theta(tD, tA, sG_hi, sG_lo, idesc_c, 1);
+                        tc::mma_commit(respA);
                         t16_issue_z(tD + 128, z_hi, z_lo, inj, sT_hi, sT_lo, idesc_64, 0);
-                        tc::mma_commit(resp);
+                        tc::mma_commit(respB);
                         tc::mma_commit(bar_zfree + t * 2 + b);
                     }
                     __syncwarp();
                 }
+                // fine stage: both chunk accumulators are free and A_theta is current once the rows
+                // have signalled the end of the last coarse step
+                tc::mbar_wait(reqA, pa); pa ^= 1;
+                tc::mbar_wait(reqB, pb); pb ^= 1;
                 for (int c = 0; c < NCH; c++, gch++) {
                     const int b = c & 1;
                     const int st = (int)(gch % T16_NST);
-                    if (b) { tc::mbar_wait(req + 1, rq1); rq1 ^= 1; }
-                    else { tc::mbar_wait(req, rq0); rq0 ^= 1; }
+                    if (c >= 2) {
+                        if (b) { tc::mbar_wait(reqF + 1, pf1); pf1 ^= 1; }
+                        else { tc::mbar_wait(reqF, pf0); pf0 ^= 1; }
+                    }
                     tc::mbar_wait(bar_full + st, (uint32_t)((gch / T16_NST) & 1));
                     tc::fence_after_sync();
                     if (tc::elect_one()) {
                         const uint32_t b_hi = ring_base + st * T16_CHUNK_BYTES, b_lo = b_hi + T16_TIMG;
                         t16_issue_theta(tD + b * T16_CH, tA, b_hi, b_lo, idesc_64, 0);
-                        tc::mma_commit(resp + b);
+                        tc::mma_commit(respF + b);
                         tc::mma_commit(bar_empty + st);
                     }
                     __syncwarp();
@@ -480,14 +505,19 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         const int col0 = h * T16_HK;                   // first theta column of this thread
         const uint32_t tA = tbase + ((uint32_t)(wq * 32) << 16) + t * 256;
         const uint32_t tD = tA + 64;
-        uint64_t* req = bar_req + t * 2;
-        uint64_t* resp = bar_resp + t * 2;
-        uint32_t ph0 = 0, ph1 = 0;
+        uint64_t* reqA = bar_reqA + t;
+        uint64_t* reqB = bar_reqB + t;
+        uint64_t* respA = bar_respA + t;
+        uint64_t* respB = bar_respB + t;
+        uint64_t* reqF = bar_reqF + t * 2;
+        uint64_t* respF = bar_respF + t * 2;
+        uint32_t phA = 0, phB = 0, ph0 = 0, ph1 = 0;
         int sbuf = 0;
         const LevelP<float>& l0 = p.lv[0];
         const LevelP<float>& l1 = p.lv[1];
         const float inv2vc = -0.5f / q.var_c, inv2vf = -0.5f / q.var_f;
         const float ca = q.ca, cxi = q.cxi, sc_c = q.sc_c, sc_f = q.sc_f, sc_p = q.sc_p;
+        const unsigned long long sc_c2 = f2pack(sc_c, sc_c);
         const float th_scale = q.th_scale, th_unscale = q.th_unscale;
         const int ngc = mc >> 4, gc0 = h ? (ngc + 1) / 2 : 0, gc1 = h ? ngc : (ngc + 1) / 2;
         // One warp per tile waits on the MMA's mbarrier; the other seven block in a named barrier
@@ -533,7 +563,9 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             };
 
             store_A();
-            t16_warp_arrive(req, lane);
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(reqA); tc::mbar_arrive(reqB); }
 
             for (long long it = 0; it < iters; it++) {
                 for (int j = 0; j < J; j++) {
@@ -541,8 +573,9 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     float u_mine = 0.0f;
                     if (h == 0) u_mine = draw_u();
                     ucur++;
-                    wait_mma(resp, ph0);
+                    wait_mma(respA, phA);
                     float ssq = 0.0f;
+                    unsigned long long ssq2a = 0ull, ssq2b = 0ull;      // packed (even, odd) partial sums
                     int gc = gc0;
                     for (; gc + 1 < gc1; gc += 2) {
                         uint32_t v0[16], v1[16];
@@ -553,12 +586,12 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
 #pragma unroll
                         for (int i4 = 0; i4 < 4; i4++) {
                             const float4 y0 = ny4[i4], y1 = ny4[4 + i4];
-                            const float r0 = fmaf(__uint_as_float(v0[4 * i4 + 0]), sc_c, y0.x), r1 = fmaf(__uint_as_float(v0[4 * i4 + 1]), sc_c, y0.y);
-                            const float r2 = fmaf(__uint_as_float(v0[4 * i4 + 2]), sc_c, y0.z), r3 = fmaf(__uint_as_float(v0[4 * i4 + 3]), sc_c, y0.w);
-                            const float r4 = fmaf(__uint_as_float(v1[4 * i4 + 0]), sc_c, y1.x), r5 = fmaf(__uint_as_float(v1[4 * i4 + 1]), sc_c, y1.y);
-                            const float r6 = fmaf(__uint_as_float(v1[4 * i4 + 2]), sc_c, y1.z), r7 = fmaf(__uint_as_float(v1[4 * i4 + 3]), sc_c, y1.w);
-                            ssq = fmaf(r0, r0, ssq); ssq = fmaf(r1, r1, ssq); ssq = fmaf(r2, r2, ssq); ssq = fmaf(r3, r3, ssq);
-                            ssq = fmaf(r4, r4, ssq); ssq = fmaf(r5, r5, ssq); ssq = fmaf(r6, r6, ssq); ssq = fmaf(r7, r7, ssq);
+                            const unsigned long long r0 = f2fma(f2pack(__uint_as_float(v0[4 * i4 + 0]), __uint_as_float(v0[4 * i4 + 1])), sc_c2, f2pack(y0.x, y0.y));
+                            const unsigned long long r1 = f2fma(f2pack(__uint_as_float(v0[4 * i4 + 2]), __uint_as_float(v0[4 * i4 + 3])), sc_c2, f2pack(y0.z, y0.w));
+                            const unsigned long long r2 = f2fma(f2pack(__uint_as_float(v1[4 * i4 + 0]), __uint_as_float(v1[4 * i4 + 1])), sc_c2, f2pack(y1.x, y1.y));
+                            const unsigned long long r3 = f2fma(f2pack(__uint_as_float(v1[4 * i4 + 2]), __uint_as_float(v1[4 * i4 + 3])), sc_c2, f2pack(y1.z, y1.w));
+                            ssq2a = f2fma(r0, r0, ssq2a); ssq2b = f2fma(r1, r1, ssq2b);
+                            ssq2a = f2fma(r2, r2, ssq2a); ssq2b = f2fma(r3, r3, ssq2b);
                         }
                     }
                     if (gc < gc1) {
@@ -571,6 +604,13 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                             ssq = fmaf(r, r, ssq);
                         }
                     }
+                    t16_warp_arrive(reqA, lane);           // D[0:128) consumed: the next step's z products may start
+                    {
+                        float e0, e1, e2, e3;
+                        f2unpack(ssq2a, e0, e1);
+                        f2unpack(ssq2b, e2, e3);
+                        ssq += (e0 + e1) + (e2 + e3);
+                    }
                     float* sp = s_part + ((sbuf * 2 + t) * 2) * 128;
                     float* su = s_u + (sbuf * 2 + t) * 128;
                     sp[h * 128 + cl] = ssq;
@@ -581,29 +621,26 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     const float u = su[cl];
                     const float alpha = isnan(like_p) ? 0.0f : expf(like_p - like_c);
                     const bool acc = u < alpha;
+                    wait_mma(respB, phB);
                     if (__any_sync(0xffffffffu, acc)) {
                         uint32_t x0[16], x1[16];
                         tc::tmem_ld16(tD + 128 + col0, x0);
                         tc::tmem_ld16(tD + 128 + col0 + 16, x1);
                         tc::tmem_wait_ld();
                         if (acc) {
+                            const unsigned long long ca2 = f2pack(ca, ca), cxi2 = f2pack(cxi, cxi);
 #pragma unroll
-                            for (int i = 0; i < 16; i++) {
-                                th[i] = fmaf(__uint_as_float(x0[i]), cxi, ca * th[i]);
-                                th[16 + i] = fmaf(__uint_as_float(x1[i]), cxi, ca * th[16 + i]);
+                            for (int i = 0; i < 8; i++) {
+                                const unsigned long long a0 = f2mul(f2pack(th[2 * i], th[2 * i + 1]), ca2);
+                                const unsigned long long a1 = f2mul(f2pack(th[16 + 2 * i], th[16 + 2 * i + 1]), ca2);
+                                f2unpack(f2fma(f2pack(__uint_as_float(x0[2 * i]), __uint_as_float(x0[2 * i + 1])), cxi2, a0), th[2 * i], th[2 * i + 1]);
+                                f2unpack(f2fma(f2pack(__uint_as_float(x1[2 * i]), __uint_as_float(x1[2 * i + 1])), cxi2, a1), th[16 + 2 * i], th[16 + 2 * i + 1]);
                             }
                         }
                         store_A();
                     }
                     if (acc) { like_c = like_p; acc_any = 1; nacc_c++; }
-                    // D consumed, A_theta current -> next job (the last coarse step also frees the
-                    // second fine-chunk accumulator)
-                    tc::fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tc::mbar_arrive(req);
-                        if (j == J - 1) tc::mbar_arrive(req + 1);
-                    }
+                    t16_warp_arrive(reqB, lane);           // A_theta current, xi consumed
                 }
                 // ---- fine level: F_f = theta @ G_f^T streamed in 64-column chunks, then theta @ LP ----
                 float u2 = 0.0f;
@@ -611,8 +648,8 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 float ssq_f = 0.0f, ssq_p = 0.0f;
                 for (int c = 0; c < NCH; c++) {
                     const int b = c & 1;
-                    if (b) wait_mma(resp + 1, ph1);
-                    else wait_mma(resp, ph0);
+                    if (b) wait_mma(respF + 1, ph1);
+                    else wait_mma(respF, ph0);
                     uint32_t v0[16], v1[16];
                     tc::tmem_ld16(tD + b * T16_CH + col0, v0);
                     tc::tmem_ld16(tD + b * T16_CH + col0 + 16, v1);
@@ -621,17 +658,25 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                                                                              : s_ny + T16_MAX_MC + T16_K + c * T16_CH + col0);
                     const float scl = last ? sc_p : sc_f;
                     tc::tmem_wait_ld();
-                    if (c + 2 < NCH) t16_warp_arrive(req + b, lane);
-                    float acc2 = 0.0f;
+                    if (c + 2 < NCH) t16_warp_arrive(reqF + b, lane);
+                    unsigned long long a2 = 0ull, b2 = 0ull;
+                    const unsigned long long scl2 = f2pack(scl, scl);
 #pragma unroll
                     for (int i4 = 0; i4 < 4; i4++) {
                         const float4 y0 = ny4[i4], y1 = ny4[4 + i4];
-                        const float r0 = fmaf(__uint_as_float(v0[4 * i4 + 0]), scl, y0.x), r1 = fmaf(__uint_as_float(v0[4 * i4 + 1]), scl, y0.y);
-                        const float r2 = fmaf(__uint_as_float(v0[4 * i4 + 2]), scl, y0.z), r3 = fmaf(__uint_as_float(v0[4 * i4 + 3]), scl, y0.w);
-                        const float r4 = fmaf(__uint_as_float(v1[4 * i4 + 0]), scl, y1.x), r5 = fmaf(__uint_as_float(v1[4 * i4 + 1]), scl, y1.y);
-                        const float r6 = fmaf(__uint_as_float(v1[4 * i4 + 2]), scl, y1.z), r7 = fmaf(__uint_as_float(v1[4 * i4 + 3]), scl, y1.w);
-                        acc2 = fmaf(r0, r0, acc2); acc2 = fmaf(r1, r1, acc2); acc2 = fmaf(r2, r2, acc2); acc2 = fmaf(r3, r3, acc2);
-                        acc2 = fmaf(r4, r4, acc2); acc2 = fmaf(r5, r5, acc2); acc2 = fmaf(r6, r6, acc2); acc2 = fmaf(r7, r7, acc2);
+                        const unsigned long long r0 = f2fma(f2pack(__uint_as_float(v0[4 * i4 + 0]), __uint_as_float(v0[4 * i4 + 1])), scl2, f2pack(y0.x, y0.y));
+                        const unsigned long long r1 = f2fma(f2pack(__uint_as_float(v0[4 * i4 + 2]), __uint_as_float(v0[4 * i4 + 3])), scl2, f2pack(y0.z, y0.w));
+                        const unsigned long long r2 = f2fma(f2pack(__uint_as_float(v1[4 * i4 + 0]), __uint_as_float(v1[4 * i4 + 1])), scl2, f2pack(y1.x, y1.y));
+                        const unsigned long long r3 = f2fma(f2pack(__uint_as_float(v1[4 * i4 + 2]), __uint_as_float(v1[4 * i4 + 3])), scl2, f2pack(y1.z, y1.w));
+                        a2 = f2fma(r0, r0, a2); b2 = f2fma(r1, r1, b2);
+                        a2 = f2fma(r2, r2, a2); b2 = f2fma(r3, r3, b2);
+                    }
+                    float acc2;
+                    {
+                        float e0, e1, e2, e3;
+                        f2unpack(a2, e0, e1);
+                        f2unpack(b2, e2, e3);
+                        acc2 = (e0 + e1) + (e2 + e3);
                     }
                     if (last) ssq_p += acc2;
                     else ssq_f += acc2;
@@ -665,7 +710,11 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 acc_any = 0;
                 // the A operand must hold the (possibly rewound) state before the next coarse job
                 if (!__all_sync(0xffffffffu, accf)) store_A();
-                if (it + 1 < iters) t16_warp_arrive(req, lane);
+                if (it + 1 < iters) {
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) { tc::mbar_arrive(reqA); tc::mbar_arrive(reqB); }
+                }
                 // ---- fine-level record (coalesced: consecutive lanes = consecutive chains) ----
                 const long long r = p.rec[1] + it;
                 if (r < l1.hist_cap) {

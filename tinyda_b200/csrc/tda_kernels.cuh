@@ -212,14 +212,12 @@ struct Tile {
     __device__ void fill_normals() {
         const int d = p.d;
         const long long z0 = t_base * d;
-        if (p.rng_mode == TDA_RNG_PHILOX && (z0 & 3) == 0) {
+        if (p.rng_mode == TDA_RNG_PHILOX && (z0 & 3) == 0 && !p.z_round) {
             const int nb4 = (d + 3) >> 2;
             for (int e = tid; e < nb4 * TC; e += NT) {
                 int q = e / TC, c = e - q * TC;
                 R v[4];
-                const uint4 blk = philox_block(p.seed, p.chain_offset + chain0 + c, STREAM_Z, (unsigned long long)(z0 >> 2) + q);
-                if (p.z_round) normals4_z16(blk, v);
-                else normals4<R>(blk, v);
+                normals4<R>(philox_block(p.seed, p.chain_offset + chain0 + c, STREAM_Z, (unsigned long long)(z0 >> 2) + q), v);
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                     if (4 * q + i < d) zt[(4 * q + i) * TC + c] = v[i];
