@@ -159,6 +159,7 @@ typedef struct tda_config {
 #define TDA_G_THETA 6           /* level: current state [n_chains][d]               */
 #define TDA_G_NRECORDS 7        /* int64 [n_levels] records written so far          */
 #define TDA_G_MOMENTS 8         /* finest level running sums: [2][d][n_chains] (sum x, sum x^2) */
+#define TDA_G_TC16_TIMELINE 10  /* get only, diagnostic: int64 [4][256] clock64 stamps of CTA 0 of kernel 3 (first call arms the probe) */
 #define TDA_G_ZROUND 9          /* set only: one float64 flag; non-zero = Philox normals on the fp16 grid
                                  * ("z16" stream) also for the generic / 3xTF32 kernels (float32 engine) */
 

@@ -82,6 +82,7 @@ struct DaTc16Params {
     float sc_c, sc_f, sc_p;   // accumulator -> model output: 2^-(s_theta + s_G), 2^-(s_theta + s_Gf), 2^-(s_theta + s_LP)
     float th_scale, th_unscale;
     int n_pairs;
+    long long* dbg;           // optional timeline probe (tools/tc16_timeline.py): [role 4][256] clock64 stamps of CTA 0
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -283,6 +284,29 @@ __device__ __forceinline__ void t16_issue_z(uint32_t d_tmem, uint32_t z_hi, uint
     }
 }
 
+// One 16-normal group (z16 stream) of one chain, packed to fp16 and stored into the chain's row of
+// a canonical K-major z image (row_ptr = image + row offset; columns 16 q4 .. 16 q4 + 15).
+__device__ __forceinline__ void t16_z_group(unsigned long long seed, long long gchain, unsigned long long group, unsigned char* row_ptr, int q4) {
+    const unsigned long long b3 = 3 * group;
+    float s[16];
+    z16_group_scaled(philox_block(seed, gchain, STREAM_Z, b3), philox_block(seed, gchain, STREAM_Z, b3 + 1),
+                     philox_block(seed, gchain, STREAM_Z, b3 + 2), s);
+    uint4 w0, w1;
+    w0.x = tc::pack_f16x2(s[0], s[1]);   w0.y = tc::pack_f16x2(s[2], s[3]);
+    w0.z = tc::pack_f16x2(s[4], s[5]);   w0.w = tc::pack_f16x2(s[6], s[7]);
+    w1.x = tc::pack_f16x2(s[8], s[9]);   w1.y = tc::pack_f16x2(s[10], s[11]);
+    w1.z = tc::pack_f16x2(s[12], s[13]); w1.w = tc::pack_f16x2(s[14], s[15]);
+    *reinterpret_cast<uint4*>(row_ptr + (2 * q4) * 128) = w0;
+    *reinterpret_cast<uint4*>(row_ptr + (2 * q4 + 1) * 128) = w1;
+}
+
+// Share of the normals generated by the RNG warps: groups [0, T16_RNG_GROUPS) of the 4 groups of a
+// coarse step.  With T16_RNG_GROUPS = 2 the two row threads of a chain generate groups 2 and 3 for
+// the NEXT coarse step while they wait for the MMA (measured on B200: slower -- the row threads are
+// the critical path once the normals are ahead -- so the RNG warps keep all 4 groups).
+constexpr int T16_RNG_GROUPS = 4;
+constexpr bool T16_ROW_SHARE = T16_RNG_GROUPS < 4;
+
 __global__ void __launch_bounds__(T16_THREADS, 1)
 da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ DaTc16Params q) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -309,7 +333,9 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     uint64_t* bar_empty = bars + 25 + T16_NST;      // [NST]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 25 + 2 * T16_NST);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the shuffle tells the compiler that the warp index (and everything derived from it: tile,
+    // TMEM / shared-memory bases, MMA descriptors) is warp-uniform -> uniform registers
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (warp == T16_MMA_WARP0) tc::tmem_alloc(s_tmem, 512);
     if (tid == T16_PROD_WARP * 32) {
         tc::mbar_init(bar_res, 1);
@@ -322,7 +348,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         for (int i = 0; i < 4; i++) {
             tc::mbar_init(bar_reqF + i, 8);
             tc::mbar_init(bar_respF + i, 1);
-            tc::mbar_init(bar_zfull + i, 4);
+            tc::mbar_init(bar_zfull + i, T16_ROW_SHARE ? 12 : 4);   // 4 RNG warps (+ 8 row warps of the tile)
             tc::mbar_init(bar_zfree + i, 1);
         }
         for (int s = 0; s < T16_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 2); }
@@ -331,7 +357,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tbase = *s_tmem;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, *s_tmem, 0);
 
     const int J = q.J, mc = q.mc, NCH = q.n_chunks;
     const int my_pairs = (q.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -359,25 +385,16 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             for (long long st = 0; st < nsteps; st++, n++, tb++) {
                 const int b = inj ? 0 : (int)(n & 1);
                 const long long use = inj ? n : (n >> 1);
+                const bool dbg_on = q.dbg && blockIdx.x == 0 && warp == T16_RNG_WARP0 && lane == 0 && n < 64;
+                if (dbg_on) q.dbg[0 * 256 + 3 * n] = clock64();
                 if (use >= 1) tc::mbar_wait(zfree + b, (uint32_t)((use - 1) & 1));
+                if (dbg_on) q.dbg[0 * 256 + 3 * n + 1] = clock64();
                 unsigned char* dst = zt + (size_t)b * T16_IMG;
                 if (!inj) {
-                    // z16 stream: 64 normals = 4 groups of 3 Philox blocks (24-bit fields)
+                    // z16 stream: 64 normals = 4 groups of 3 Philox blocks; the row threads add groups 2, 3
                     const unsigned long long grp0 = (unsigned long long)(tb * (T16_K / 16));
 #pragma unroll 1
-                    for (int q4 = 0; q4 < T16_K / 16; q4++) {
-                        const unsigned long long b3 = 3 * (grp0 + q4);
-                        float s[16];
-                        z16_group_scaled(philox_block(p.seed, gchain, STREAM_Z, b3), philox_block(p.seed, gchain, STREAM_Z, b3 + 1),
-                                         philox_block(p.seed, gchain, STREAM_Z, b3 + 2), s);
-                        uint4 w0, w1;
-                        w0.x = tc::pack_f16x2(s[0], s[1]);   w0.y = tc::pack_f16x2(s[2], s[3]);
-                        w0.z = tc::pack_f16x2(s[4], s[5]);   w0.w = tc::pack_f16x2(s[6], s[7]);
-                        w1.x = tc::pack_f16x2(s[8], s[9]);   w1.y = tc::pack_f16x2(s[10], s[11]);
-                        w1.z = tc::pack_f16x2(s[12], s[13]); w1.w = tc::pack_f16x2(s[14], s[15]);
-                        *reinterpret_cast<uint4*>(dst + (2 * q4) * 128) = w0;
-                        *reinterpret_cast<uint4*>(dst + (2 * q4 + 1) * 128) = w1;
-                    }
+                    for (int q4 = 0; q4 < T16_RNG_GROUPS; q4++) t16_z_group(p.seed, gchain, grp0 + q4, dst, q4);
                 } else {
                     const long long z0 = tb * T16_K;
                     for (int kg = 0; kg < T16_K / 8; kg++) {
@@ -395,7 +412,9 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 }
                 tc::fence_proxy_async_smem();          // generic-proxy writes -> visible to the MMA (async proxy)
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(zfull + b);
+                // (injected streams: the RNG warps write everything and also stand in for the row warps' arrivals)
+                if (lane == 0 || (T16_ROW_SHARE && inj && lane < 3)) tc::mbar_arrive(zfull + b);
+                if (dbg_on) q.dbg[0 * 256 + 3 * n + 2] = clock64();
             }
         }
     } else if (warp >= T16_MMA_WARP0) {
@@ -452,13 +471,19 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     const int b = inj ? 0 : (int)(n & 1);
                     const long long use = inj ? n : (n >> 1);
                     const uint32_t z_hi = z_base + b * T16_IMG, z_lo = z_base + T16_IMG;
+                    const bool dbg_on = q.dbg && blockIdx.x == 0 && t == 0 && lane == 0 && n < 40;
+                    if (dbg_on) q.dbg[1 * 256 + 6 * n] = clock64();
                     tc::mbar_wait(reqA, pa); pa ^= 1;
+                    if (dbg_on) q.dbg[1 * 256 + 6 * n + 1] = clock64();
                     tc::mbar_wait(bar_zfull + t * 2 + b, (uint32_t)(use & 1));
                     tc::fence_after_sync();
+                    if (dbg_on) q.dbg[1 * 256 + 6 * n + 2] = clock64();
                     if (tc::elect_one()) t16_issue_z(tD, z_hi, z_lo, inj, sM_hi, sM_lo, idesc_c, 0);
                     __syncwarp();
+                    if (dbg_on) q.dbg[1 * 256 + 6 * n + 3] = clock64();
                     tc::mbar_wait(reqB, pb); pb ^= 1;
                     tc::fence_after_sync();
+                    if (dbg_on) q.dbg[1 * 256 + 6 * n + 4] = clock64();
                     if (tc::elect_one()) {
                         t16_issue_theta(tD, tA, sG_hi, sG_lo, idesc_c, 1);
                         tc::mma_commit(respA);
@@ -467,6 +492,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                         tc::mma_commit(bar_zfree + t * 2 + b);
                     }
                     __syncwarp();
+                    if (dbg_on) q.dbg[1 * 256 + 6 * n + 5] = clock64();
                 }
                 // fine stage: both chunk accumulators are free and A_theta is current once the rows
                 // have signalled the end of the last coarse step
@@ -530,6 +556,29 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             tc::fence_after_sync();
         };
         tc::mbar_wait(bar_res, 0);                     // the data vector arrives with the resident operands
+        // Row threads' share of the z16 normals: thread (chain, half h) generates group 2 + h of coarse
+        // step n (global count over this CTA's pairs / iterations / subchain steps) into z buffer n & 1.
+        // The buffer is free by program order: its previous user, step n - 2, was fully consumed
+        // (G1 and G3 complete) before this thread passed that step's respA / respB waits.
+        const long long steps_per_pair = iters * J;
+        const long long total_steps = (long long)my_pairs * steps_per_pair;
+        unsigned char* z_row = zbuf + (size_t)t * 2 * T16_IMG + (cl >> 3) * ((T16_K / 8) * 128) + (cl & 7) * 16;
+        uint64_t* zfull = bar_zfull + t * 2;
+        auto z_share = [&](long long n) {
+            if (!T16_ROW_SHARE || inj || n >= total_steps) return;
+            const int b = inj ? 0 : (int)(n & 1);
+            if (!inj) {
+                const long long prn = n / steps_per_pair, stn = n - prn * steps_per_pair;
+                const int pairn = (int)blockIdx.x + (int)prn * (int)gridDim.x;
+                const long long gch = p.chain_offset + pairn * 256 + t * 128 + cl;
+                const unsigned long long grp = (unsigned long long)((p.t_base + stn) * (T16_K / 16)) + T16_RNG_GROUPS + h;
+                t16_z_group(p.seed, gch, grp, z_row + (size_t)b * T16_IMG, T16_RNG_GROUPS + h);
+                tc::fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(zfull + b);
+        };
+        long long zn = 0;                              // global coarse-step count of this thread
 
         for (int pr = 0; pr < my_pairs; pr++) {
             const int pair = (int)blockIdx.x + pr * (int)gridDim.x;
@@ -566,6 +615,9 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(reqA); tc::mbar_arrive(reqB); }
+            // this thread's share of the normals of the pair's first coarse step (later steps are
+            // produced one step ahead, while waiting for the MMA)
+            if (pr == 0) z_share(0);
 
             for (long long it = 0; it < iters; it++) {
                 for (int j = 0; j < J; j++) {
@@ -573,7 +625,14 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     float u_mine = 0.0f;
                     if (h == 0) u_mine = draw_u();
                     ucur++;
+                    const long long dn = it * J + j;
+                    const bool dbg_on = q.dbg && blockIdx.x == 0 && pr == 0 && t == 0 && lane == 0 && dn < 40 && (leader || (h == 1 && wq == 3));
+                    long long* dbg = q.dbg + (leader ? 2 : 3) * 256 + 6 * dn;
+                    if (dbg_on) dbg[0] = clock64();
+                    z_share(zn + 1);                       // next step's normals, generated in the MMA's shadow
+                    zn++;
                     wait_mma(respA, phA);
+                    if (dbg_on) dbg[1] = clock64();
                     float ssq = 0.0f;
                     unsigned long long ssq2a = 0ull, ssq2b = 0ull;      // packed (even, odd) partial sums
                     int gc = gc0;
@@ -605,6 +664,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                         }
                     }
                     t16_warp_arrive(reqA, lane);           // D[0:128) consumed: the next step's z products may start
+                    if (dbg_on) dbg[2] = clock64();
                     {
                         float e0, e1, e2, e3;
                         f2unpack(ssq2a, e0, e1);
@@ -621,7 +681,9 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     const float u = su[cl];
                     const float alpha = isnan(like_p) ? 0.0f : expf(like_p - like_c);
                     const bool acc = u < alpha;
+                    if (dbg_on) dbg[3] = clock64();
                     wait_mma(respB, phB);
+                    if (dbg_on) dbg[4] = clock64();
                     if (__any_sync(0xffffffffu, acc)) {
                         uint32_t x0[16], x1[16];
                         tc::tmem_ld16(tD + 128 + col0, x0);
@@ -641,6 +703,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     }
                     if (acc) { like_c = like_p; acc_any = 1; nacc_c++; }
                     t16_warp_arrive(reqB, lane);           // A_theta current, xi consumed
+                    if (dbg_on) dbg[5] = clock64();
                 }
                 // ---- fine level: F_f = theta @ G_f^T streamed in 64-column chunks, then theta @ LP ----
                 float u2 = 0.0f;
@@ -765,6 +828,7 @@ struct DaTc16State {
     bool prepared = false;
     bool eligible(const tda_config&, const Params<R>&) const { return false; }
     int prepare(const Params<R>&, const tda_config&) { err = "fp16-split tensor-core DA kernel is float32 only"; return 1; }
+    int timeline(long long*) { return -5; }
     int run(Params<R>&, const tda_config&, long long, int, cudaStream_t) { err = "fp16-split tensor-core DA kernel is float32 only"; return -5; }
     void destroy() {}
 };
@@ -774,6 +838,7 @@ struct DaTc16State<float> {
     std::string err;
     __half *dG = nullptr, *dM = nullptr, *dT = nullptr, *dF = nullptr;
     float* dNY = nullptr;
+    long long* dDbg = nullptr;
     bool prepared = false;
     DaTc16Params q{};
 
@@ -790,7 +855,20 @@ struct DaTc16State<float> {
         return true;
     }
 
+    // timeline probe: allocate the stamp buffer (subsequent runs fill it), or read it back
+    int timeline(long long* host_out) {
+        if (!dDbg) {
+            if (cudaMalloc(&dDbg, 4 * 256 * sizeof(long long)) != cudaSuccess) return -3;
+            cudaMemset(dDbg, 0, 4 * 256 * sizeof(long long));
+            return 0;
+        }
+        cudaDeviceSynchronize();
+        return cudaMemcpy(host_out, dDbg, 4 * 256 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+    }
+
     void destroy() {
+        if (dDbg) cudaFree(dDbg);
+        dDbg = nullptr;
         if (dG) cudaFree(dG);
         if (dM) cudaFree(dM);
         if (dT) cudaFree(dT);
@@ -919,6 +997,7 @@ struct DaTc16State<float> {
         cudaError_t e;
         (void)st;
         q.n_pairs = P.Cs / 256;
+        q.dbg = dDbg;
         const size_t smem = T16_SMEM_BYTES;
         e = cudaFuncSetAttribute(da_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { err = std::string("tc16 attr: ") + cudaGetErrorString(e); return -2; }

@@ -539,6 +539,12 @@ struct EngineT : tda_engine {
             for (int l = 0; l < P.L; l++) reinterpret_cast<long long*>(dst)[l] = P.rec[l];
             return 0;
         }
+        case TDA_G_TC16_TIMELINE: {
+            // diagnostic: first call arms the probe, later calls return [4][256] clock64 stamps
+            if (bytes < 4 * 256 * sizeof(long long)) return fail(-1, "get: destination too small");
+            int r = tc16.timeline(reinterpret_cast<long long*>(dst));
+            return r ? fail(r, "tc16 timeline probe unavailable") : 0;
+        }
         case TDA_G_MOMENTS: {
             if (bytes < (size_t)2 * d * P.C * sizeof(double)) return fail(-1, "get: destination too small");
             int r = get_soa(P.sum1, d, dst, (size_t)d * P.C * sizeof(double), true, false);
