@@ -148,6 +148,29 @@ def test_tc_kernel_resume_and_sharding_exact(kernel):
     assert np.array_equal(th_a[:, :, 256:512], th_c)
 
 
+def test_tc16_iteration_blocks_hand_chains_between_sms_exactly(monkeypatch):
+    """tc16 cuts a launch into (tile pair, iteration block) units dealt round-robin over the SMs; with
+    more pairs than SMs consecutive blocks of a pair run on different SMs and the state travels through
+    global memory.  The result must not depend on the block count, bit for bit."""
+    import os
+    from tinyda_b200.workloads import cfg2_da
+    C, iters = 150 * 256 + 40, 7                      # 151 tile pairs > 148 SMs, ragged last pair
+    theta0 = cfg2_da()["prior"].rvs(C, random_state=np.random.default_rng(4))
+    outs = []
+    for blocks in ("1", "3", "7"):
+        monkeypatch.setenv("TDA_TC16_BLOCKS", blocks)
+        eng, _ = _cfg2_engine(C, "tc16", iters=iters, theta0=theta0)
+        eng.run(3)
+        eng.run(iters - 3)
+        outs.append((eng.fetch(1, "theta"), eng.fetch(1, "like"), eng.fetch(1, "accept"), eng.get("accept_counts"),
+                     eng.get("cursors"), eng.get("moments")))
+        eng.close()
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    assert outs[0][2][1:].mean() > 0.3
+
+
 def test_tc16_philox_streams_fed_to_the_oracle():
     """Production mode of the fp16-split kernel: its z16 / uniform streams exported with
     tda_fill_streams and fed to the CPU oracle reproduce the accept decisions and (to float32

@@ -27,6 +27,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "tda_common.cuh"
@@ -82,6 +83,8 @@ struct DaTc16Params {
     float sc_c, sc_f, sc_p;   // accumulator -> model output: 2^-(s_theta + s_G), 2^-(s_theta + s_Gf), 2^-(s_theta + s_LP)
     float th_scale, th_unscale;
     int n_pairs;
+    int ib, nb;               // work units: iterations per block, blocks per launch (unit = tile pair x block)
+    int* progress;            // [n_pairs] tile completions of this launch (2 per finished block)
     long long* dbg;           // optional timeline probe (tools/tc16_timeline.py): [role 4][256] clock64 stamps of CTA 0
 };
 
@@ -300,12 +303,37 @@ __device__ __forceinline__ void t16_z_group(unsigned long long seed, long long g
     *reinterpret_cast<uint4*>(row_ptr + (2 * q4 + 1) * 128) = w1;
 }
 
-// Share of the normals generated by the RNG warps: groups [0, T16_RNG_GROUPS) of the 4 groups of a
-// coarse step.  With T16_RNG_GROUPS = 2 the two row threads of a chain generate groups 2 and 3 for
-// the NEXT coarse step while they wait for the MMA (measured on B200: slower -- the row threads are
-// the critical path once the normals are ahead -- so the RNG warps keep all 4 groups).
-constexpr int T16_RNG_GROUPS = 4;
-constexpr bool T16_ROW_SHARE = T16_RNG_GROUPS < 4;
+// Work distribution.  A launch advances n_pairs tile pairs by `iterations`; 256 pairs on 148 SMs would
+// leave 27 % of the machine idle in the second wave, so the iterations are cut into nb blocks and the
+// units (pair, block) are dealt round-robin, block-major: CTA c runs units c, c + grid, c + 2 grid, ...
+// Consecutive blocks of a pair generally run on different SMs; the chain state travels through global
+// memory (as it does between launches) and `progress[pair]` orders the hand-off.  Unit u depends only
+// on unit u - n_pairs, every CTA walks its units in increasing order and all CTAs are co-resident
+// (grid <= #SMs, one CTA per SM), so the wait cannot deadlock.
+struct T16Unit {
+    int pair, blk, it0, it1;       // 32-bit on purpose: the RNG / MMA warps run on 40 registers
+};
+__device__ __forceinline__ bool t16_unit(const DaTc16Params& q, int iters, int k, T16Unit& u) {
+    const int idx = (int)blockIdx.x + k * (int)gridDim.x;
+    if (idx >= q.n_pairs * q.nb) return false;
+    u.blk = idx / q.n_pairs;
+    u.pair = idx - u.blk * q.n_pairs;
+    u.it0 = u.blk * q.ib;
+    u.it1 = min(u.it0 + q.ib, iters);
+    return true;
+}
+__device__ __forceinline__ int t16_ld_acquire(const int* ptr) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void t16_red_release_add(int* ptr, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+
+// (Measured on B200 and rejected: letting the row threads generate a quarter or a half of the
+// normals one step ahead, in the shadow of the MMA -- 678 M / 636 M transitions/s against 701 M with
+// the RNG warps alone; the row threads are the critical path as soon as the normals are ahead.)
 
 __global__ void __launch_bounds__(T16_THREADS, 1)
 da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ DaTc16Params q) {
@@ -348,7 +376,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         for (int i = 0; i < 4; i++) {
             tc::mbar_init(bar_reqF + i, 8);
             tc::mbar_init(bar_respF + i, 1);
-            tc::mbar_init(bar_zfull + i, T16_ROW_SHARE ? 12 : 4);   // 4 RNG warps (+ 8 row warps of the tile)
+            tc::mbar_init(bar_zfull + i, 4);
             tc::mbar_init(bar_zfree + i, 1);
         }
         for (int s = 0; s < T16_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 2); }
@@ -360,8 +388,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     const uint32_t tbase = __shfl_sync(0xffffffffu, *s_tmem, 0);
 
     const int J = q.J, mc = q.mc, NCH = q.n_chunks;
-    const int my_pairs = (q.n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const long long iters = p.iterations;
+    const int iters = (int)p.iterations;          // per launch; checked on the host
     const bool inj = p.rng_mode == TDA_RNG_INJECTED;
 
     if (warp >= T16_RNG_WARP0 && warp < T16_RNG_WARP0 + T16_RNG_WARPS) {
@@ -374,27 +401,27 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         unsigned char* zt = zbuf + (size_t)t * 2 * T16_IMG + (row >> 3) * ((T16_K / 8) * 128) + (row & 7) * 16;
         uint64_t* zfull = bar_zfull + t * 2;
         uint64_t* zfree = bar_zfree + t * 2;
-        long long n = 0;                                   // coarse steps produced
-        for (int pr = 0; pr < my_pairs; pr++) {
-            const int pair = (int)blockIdx.x + pr * (int)gridDim.x;
-            const int g = pair * 256 + t * 128 + row;
+        unsigned n = 0;                                    // coarse steps produced
+        T16Unit un;
+        for (int uk = 0; t16_unit(q, iters, uk, un); uk++) {
+            const int g = un.pair * 256 + t * 128 + row;
             const long long gchain = p.chain_offset + g;
             const bool live = g < p.C;
-            long long tb = p.t_base;
-            const long long nsteps = iters * J;
-            for (long long st = 0; st < nsteps; st++, n++, tb++) {
+            long long tb = p.t_base + (long long)un.it0 * J;
+            const int nsteps = (un.it1 - un.it0) * J;
+            for (int st = 0; st < nsteps; st++, n++, tb++) {
                 const int b = inj ? 0 : (int)(n & 1);
-                const long long use = inj ? n : (n >> 1);
+                const unsigned use = inj ? n : (n >> 1);
                 const bool dbg_on = q.dbg && blockIdx.x == 0 && warp == T16_RNG_WARP0 && lane == 0 && n < 64;
                 if (dbg_on) q.dbg[0 * 256 + 3 * n] = clock64();
                 if (use >= 1) tc::mbar_wait(zfree + b, (uint32_t)((use - 1) & 1));
                 if (dbg_on) q.dbg[0 * 256 + 3 * n + 1] = clock64();
                 unsigned char* dst = zt + (size_t)b * T16_IMG;
                 if (!inj) {
-                    // z16 stream: 64 normals = 4 groups of 3 Philox blocks; the row threads add groups 2, 3
+                    // z16 stream: 64 normals = 4 groups of 3 Philox blocks
                     const unsigned long long grp0 = (unsigned long long)(tb * (T16_K / 16));
 #pragma unroll 1
-                    for (int q4 = 0; q4 < T16_RNG_GROUPS; q4++) t16_z_group(p.seed, gchain, grp0 + q4, dst, q4);
+                    for (int q4 = 0; q4 < T16_K / 16; q4++) t16_z_group(p.seed, gchain, grp0 + q4, dst, q4);
                 } else {
                     const long long z0 = tb * T16_K;
                     for (int kg = 0; kg < T16_K / 8; kg++) {
@@ -412,8 +439,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 }
                 tc::fence_proxy_async_smem();          // generic-proxy writes -> visible to the MMA (async proxy)
                 __syncwarp();
-                // (injected streams: the RNG warps write everything and also stand in for the row warps' arrivals)
-                if (lane == 0 || (T16_ROW_SHARE && inj && lane < 3)) tc::mbar_arrive(zfull + b);
+                if (lane == 0) tc::mbar_arrive(zfull + b);
                 if (dbg_on) q.dbg[0 * 256 + 3 * n + 2] = clock64();
             }
         }
@@ -422,7 +448,11 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         if (warp == T16_PROD_WARP) {
             // ===== producer: resident operands once, then the fine-operator chunk ring =====
             if (lane == 0) {
-                const long long total_chunks = (long long)my_pairs * iters * NCH;
+                unsigned total_chunks = 0;
+                {
+                    T16Unit un;
+                    for (int uk = 0; t16_unit(q, iters, uk, un); uk++) total_chunks += (unsigned)(un.it1 - un.it0) * NCH;
+                }
                 const uint32_t bI = (uint32_t)mc * T16_K * 2;       // one mc-row image
                 const uint32_t bNY = (uint32_t)(T16_MAX_MC + T16_K + q.mf) * 4;
                 tc::mbar_expect_tx(bar_res, 4 * bI + 2 * T16_TIMG + bNY);
@@ -432,7 +462,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 tc::bulk_g2s(sM, q.M_hl, bI, bar_res);
                 tc::bulk_g2s(sM + T16_IMG, q.M_hl + (size_t)mc * T16_K, bI, bar_res);
                 tc::bulk_g2s(sT, q.T_hl, 2 * T16_TIMG, bar_res);
-                for (long long g = 0; g < total_chunks; g++) {
+                for (unsigned g = 0; g < total_chunks; g++) {
                     const int st = (int)(g % T16_NST);
                     if (g >= T16_NST) tc::mbar_wait(bar_empty + st, (uint32_t)(((g / T16_NST) - 1) & 1));
                     const int c = (int)(g % NCH);
@@ -459,9 +489,13 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             uint64_t* reqF = bar_reqF + t * 2;
             uint64_t* respF = bar_respF + t * 2;
             uint32_t pa = 0, pb = 0, pf0 = 0, pf1 = 0;
-            long long n = 0, gch = 0;
-            const long long total_it = (long long)my_pairs * iters;
-            for (long long itg = 0; itg < total_it; itg++) {
+            unsigned n = 0, gch = 0;
+            int total_it = 0;
+            {
+                T16Unit un;
+                for (int uk = 0; t16_unit(q, iters, uk, un); uk++) total_it += un.it1 - un.it0;
+            }
+            for (int itg = 0; itg < total_it; itg++) {
                 // Per coarse step three MMA groups with their own dependencies:
                 //   G1  z @ (b T G_c^T) -> D[0:128)   needs the normals and the rows' residual pass of the
                 //                                      previous step -- it runs WHILE the rows still update theta
@@ -469,7 +503,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 //   G3  xi = z @ T      -> D[128:192) needs the rows' previous xi read (same signal as G2)
                 for (int j = 0; j < J; j++, n++) {
                     const int b = inj ? 0 : (int)(n & 1);
-                    const long long use = inj ? n : (n >> 1);
+                    const unsigned use = inj ? n : (n >> 1);
                     const uint32_t z_hi = z_base + b * T16_IMG, z_lo = z_base + T16_IMG;
                     const bool dbg_on = q.dbg && blockIdx.x == 0 && t == 0 && lane == 0 && n < 40;
                     if (dbg_on) q.dbg[1 * 256 + 6 * n] = clock64();
@@ -556,45 +590,29 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             tc::fence_after_sync();
         };
         tc::mbar_wait(bar_res, 0);                     // the data vector arrives with the resident operands
-        // Row threads' share of the z16 normals: thread (chain, half h) generates group 2 + h of coarse
-        // step n (global count over this CTA's pairs / iterations / subchain steps) into z buffer n & 1.
-        // The buffer is free by program order: its previous user, step n - 2, was fully consumed
-        // (G1 and G3 complete) before this thread passed that step's respA / respB waits.
-        const long long steps_per_pair = iters * J;
-        const long long total_steps = (long long)my_pairs * steps_per_pair;
-        unsigned char* z_row = zbuf + (size_t)t * 2 * T16_IMG + (cl >> 3) * ((T16_K / 8) * 128) + (cl & 7) * 16;
-        uint64_t* zfull = bar_zfull + t * 2;
-        auto z_share = [&](long long n) {
-            if (!T16_ROW_SHARE || inj || n >= total_steps) return;
-            const int b = inj ? 0 : (int)(n & 1);
-            if (!inj) {
-                const long long prn = n / steps_per_pair, stn = n - prn * steps_per_pair;
-                const int pairn = (int)blockIdx.x + (int)prn * (int)gridDim.x;
-                const long long gch = p.chain_offset + pairn * 256 + t * 128 + cl;
-                const unsigned long long grp = (unsigned long long)((p.t_base + stn) * (T16_K / 16)) + T16_RNG_GROUPS + h;
-                t16_z_group(p.seed, gch, grp, z_row + (size_t)b * T16_IMG, T16_RNG_GROUPS + h);
-                tc::fence_proxy_async_smem();
-            }
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(zfull + b);
-        };
-        long long zn = 0;                              // global coarse-step count of this thread
 
-        for (int pr = 0; pr < my_pairs; pr++) {
-            const int pair = (int)blockIdx.x + pr * (int)gridDim.x;
+        T16Unit un;
+        for (int uk = 0; t16_unit(q, iters, uk, un); uk++) {
+            const int pair = un.pair;
             const int g = pair * 256 + t * 128 + cl;                   // chain slot (padded arrays)
+            if (un.blk > 0) {
+                // the previous block of this pair ran on another SM: wait for both of its tiles
+                if (leader) while (t16_ld_acquire(q.progress + pair) < 2 * un.blk) __nanosleep(200);
+                tc::named_bar_sync(3 + t, 256);
+            }
             const long long gchain = p.chain_offset + g;
             const bool live = g < p.C;
             const size_t cs = (size_t)p.Cs;
             const size_t off0 = (size_t)col0 * cs + g;      // this thread's first column, this chain
             float th[T16_HK];                                // current coarse state, scaled by 2^s_theta
             {
+                // (.cg loads: the state may have been written by another SM during this launch)
                 const float* src = t16_opaque(l1.theta + off0);
 #pragma unroll
-                for (int k = 0; k < T16_HK; k++) th[k] = src[k * cs] * th_scale;
+                for (int k = 0; k < T16_HK; k++) th[k] = __ldcg(src + k * cs) * th_scale;
             }
-            float like_c = l0.like[g], like_cs = like_c, like_f = l1.like[g], prior_f = l1.prior[g];
-            long long ucur = p.ucur[g];
+            float like_c = __ldcg(l0.like + g), like_cs = like_c, like_f = __ldcg(l1.like + g), prior_f = __ldcg(l1.prior + g);
+            long long ucur = __ldcg(p.ucur + g);
             int nacc_c = 0, nacc_f = 0;
             int acc_any = 0;
 
@@ -615,22 +633,17 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) { tc::mbar_arrive(reqA); tc::mbar_arrive(reqB); }
-            // this thread's share of the normals of the pair's first coarse step (later steps are
-            // produced one step ahead, while waiting for the MMA)
-            if (pr == 0) z_share(0);
 
-            for (long long it = 0; it < iters; it++) {
+            for (int it = un.it0; it < un.it1; it++) {
                 for (int j = 0; j < J; j++) {
                     // the accept-test uniform does not depend on the MMA: draw it while waiting
                     float u_mine = 0.0f;
                     if (h == 0) u_mine = draw_u();
                     ucur++;
-                    const long long dn = it * J + j;
-                    const bool dbg_on = q.dbg && blockIdx.x == 0 && pr == 0 && t == 0 && lane == 0 && dn < 40 && (leader || (h == 1 && wq == 3));
+                    const int dn = it * J + j;
+                    const bool dbg_on = q.dbg && blockIdx.x == 0 && uk == 0 && t == 0 && lane == 0 && dn < 40 && (leader || (h == 1 && wq == 3));
                     long long* dbg = q.dbg + (leader ? 2 : 3) * 256 + 6 * dn;
                     if (dbg_on) dbg[0] = clock64();
-                    z_share(zn + 1);                       // next step's normals, generated in the MMA's shadow
-                    zn++;
                     wait_mma(respA, phA);
                     if (dbg_on) dbg[1] = clock64();
                     float ssq = 0.0f;
@@ -768,12 +781,12 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     like_c = like_cs;
                     const float* src = t16_opaque(l1.theta + off0);
 #pragma unroll
-                    for (int k = 0; k < T16_HK; k++) th[k] = src[k * cs] * th_scale;
+                    for (int k = 0; k < T16_HK; k++) th[k] = __ldcg(src + k * cs) * th_scale;
                 }
                 acc_any = 0;
                 // the A operand must hold the (possibly rewound) state before the next coarse job
                 if (!__all_sync(0xffffffffu, accf)) store_A();
-                if (it + 1 < iters) {
+                if (it + 1 < un.it1) {
                     tc::fence_before_sync();
                     __syncwarp();
                     if (lane == 0) { tc::mbar_arrive(reqA); tc::mbar_arrive(reqB); }
@@ -812,8 +825,15 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 l0.like[g] = like_c; l0.prior[g] = prior_f; l1.like[g] = like_f; l1.prior[g] = prior_f;
                 l0.sv_like[1][g] = like_c; l0.sv_prior[1][g] = prior_f;
                 l0.acc_sub[g] = 0;
-                l0.n_acc[g] += nacc_c; l1.n_acc[g] += nacc_f;
+                l0.n_acc[g] = __ldcg(l0.n_acc + g) + nacc_c;
+                l1.n_acc[g] = __ldcg(l1.n_acc + g) + nacc_f;
                 p.ucur[g] = ucur;
+            }
+            if (q.nb > 1) {
+                // publish the block: state stores -> fence -> tile barrier -> release increment
+                __threadfence();
+                tc::named_bar_sync(3 + t, 256);
+                if (leader && lane == 0) t16_red_release_add(q.progress + pair, 1);
             }
         }
         tc::fence_before_sync();
@@ -839,6 +859,8 @@ struct DaTc16State<float> {
     __half *dG = nullptr, *dM = nullptr, *dT = nullptr, *dF = nullptr;
     float* dNY = nullptr;
     long long* dDbg = nullptr;
+    int* dProgress = nullptr;
+    int progress_len = 0;
     bool prepared = false;
     DaTc16Params q{};
 
@@ -869,6 +891,9 @@ struct DaTc16State<float> {
     void destroy() {
         if (dDbg) cudaFree(dDbg);
         dDbg = nullptr;
+        if (dProgress) cudaFree(dProgress);
+        dProgress = nullptr;
+        progress_len = 0;
         if (dG) cudaFree(dG);
         if (dM) cudaFree(dM);
         if (dT) cudaFree(dT);
@@ -994,17 +1019,46 @@ struct DaTc16State<float> {
 
     int run(Params<float>& P, const tda_config& c, long long iterations, int sm_count, cudaStream_t st) {
         if (!prepared) { int r = prepare(P, c); if (r) return r; }
-        cudaError_t e;
-        (void)st;
+        cudaError_t e = cudaSuccess;
         q.n_pairs = P.Cs / 256;
         q.dbg = dDbg;
+        const int grid = q.n_pairs < sm_count ? q.n_pairs : sm_count;
+        // iteration blocks: the smallest block count (<= 16) whose round-robin deal of the
+        // (pair, block) units fills at least 97 % of the last wave, else the best one
+        int nb = 1;
+        if (q.n_pairs > grid) {
+            double best = 0.0;
+            const int nb_max = iterations < 16 ? (int)iterations : 16;
+            for (int cand = 1; cand <= nb_max; cand++) {
+                const long long units = (long long)q.n_pairs * cand;
+                const double eff = (double)units / (double)(((units + grid - 1) / grid) * grid);
+                if (eff > best + 1e-9) { best = eff; nb = cand; }
+                if (eff >= 0.97) { nb = cand; break; }
+            }
+        }
+        if (const char* forced = getenv("TDA_TC16_BLOCKS")) {     // test hook: force the block count
+            const int f = atoi(forced);
+            if (f >= 1) nb = f < iterations ? f : (int)iterations;
+        }
+        q.ib = (int)((iterations + nb - 1) / nb);
+        q.nb = (int)((iterations + q.ib - 1) / q.ib);
+        if (q.nb > 1) {
+            if (progress_len < q.n_pairs) {
+                if (dProgress) cudaFree(dProgress);
+                dProgress = nullptr;
+                if (cudaMalloc(&dProgress, (size_t)q.n_pairs * sizeof(int)) != cudaSuccess) { err = "tc16: cudaMalloc progress"; return -3; }
+                progress_len = q.n_pairs;
+            }
+            e = cudaMemsetAsync(dProgress, 0, (size_t)q.n_pairs * sizeof(int), st);
+            if (e != cudaSuccess) { err = std::string("tc16 progress: ") + cudaGetErrorString(e); return -2; }
+        }
+        q.progress = dProgress;
         const size_t smem = T16_SMEM_BYTES;
         e = cudaFuncSetAttribute(da_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { err = std::string("tc16 attr: ") + cudaGetErrorString(e); return -2; }
         P.mode = MODE_RUN;
         P.iterations = iterations;
         P.z_round = 1;
-        int grid = q.n_pairs < sm_count ? q.n_pairs : sm_count;
         da_tc16_kernel<<<grid, T16_THREADS, smem, st>>>(P, q);
         e = cudaGetLastError();
         if (e != cudaSuccess) { err = std::string("tc16 launch: ") + cudaGetErrorString(e); return -2; }

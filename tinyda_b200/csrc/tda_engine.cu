@@ -415,6 +415,16 @@ struct EngineT : tda_engine {
         }
         P.z_round = z_round_effective();
         int r;
+        if (which == 3 && iterations > (1 << 20)) {
+            // the fp16-split kernel counts its coarse steps per launch in 32 bits
+            for (long long done = 0; done < iterations;) {
+                const long long n = iterations - done < (1 << 20) ? iterations - done : (1 << 20);
+                r = run(n, st);
+                if (r) return r;
+                done += n;
+            }
+            return 0;
+        }
         if (which == 3) {
             r = tc16.run(P, cfg, iterations, sm_count, st);
             if (r) return fail(r, tc16.err);
