@@ -38,7 +38,10 @@ sys.path.insert(0, ROOT)
 
 N_CHAINS_PER_GPU = 65536
 ITERS_PER_STEP = 50
-F_ALG = 458752.0       # flop per fine transition
+F_ALG = 458752.0       # algorithmic flop per fine transition
+# tensor-core flop the fp16-split kernel EXECUTES per fine transition: per coarse step
+# theta @ aG_c^T (3 products) + z @ bTG_c^T (2) + z @ T (2), per fine step theta @ [G_f^T | LP] (3)
+F_EXEC_TC16 = 2.0 * (10 * 64 * (3 * 128 + 2 * 128 + 2 * 64) + 3 * 64 * (1024 + 64))
 METRIC = "fine-level MH transitions/sec, all chains"
 UNIT = "transitions/s"
 
@@ -284,6 +287,7 @@ def run_ours(args):
     h2d = theta0.nbytes
     d2h = h_theta.numel() * h_theta.element_size() + 2 * h_prior.numel() * h_prior.element_size() + h_acc.numel()
 
+    kernel_used = args.kernel if args.kernel != "auto" else ("tc16" if dtype == "float32" else "generic")
     if rank == 0:
         pk, src = measured_peaks()
         per_gpu_rate = C * iters / (np.mean(ms_steps) * 1e-3)
@@ -309,9 +313,13 @@ def run_ours(args):
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None,
+                "executed_tflops": per_gpu_rate * F_EXEC_TC16 / 1e12 if kernel_used == "tc16" else None,
+                "executed_frac": per_gpu_rate * F_EXEC_TC16 / 1e12 / peak if kernel_used == "tc16" else None,
                 "note": "achieved = 458752 algorithmic flop/transition x per-GPU transitions/s "
                         "(CUDA events, mean over timed launches); peak = bf16 dense sustained, " + src +
-                        " (MEASURED_PEAKS.json); a 3xTF32 split (fp32-grade accuracy) caps at peak/6",
+                        " (MEASURED_PEAKS.json). fp32-grade accuracy on 16-bit tensor cores needs a two-term "
+                        "fp16 split (3 products per contraction), so the algorithmic figure caps near peak/3; "
+                        "executed_* counts the fp16 tensor flop the kernel really issues (1.40 MFLOP/transition)",
             },
             "accept_rate": {"coarse": float(acc[0].mean() / max(1, eng.iterations_done * spec["J"][0])),
                             "fine": float(acc[1].mean() / max(1, eng.iterations_done))},
@@ -326,7 +334,8 @@ def run_ours(args):
 
 
 def eng_kernel_name(args, dtype):
-    return "%s (%s)" % (args.kernel, dtype)
+    k = args.kernel if args.kernel != "auto" else ("auto -> tc16" if dtype == "float32" else "auto -> generic")
+    return "%s (%s)" % (k, dtype)
 
 
 def run_reference(args):

@@ -69,6 +69,30 @@ __global__ void broadcast_kernel(R* dst, const R* src, int n, int ld_src, int co
     }
 }
 
+// initial states: host layout [C][d] float64 -> device SoA [d][Cs] of the engine dtype, for every
+// level at once (shared-memory tile transpose: coalesced on both sides)
+template <typename R>
+__global__ void init_theta_kernel(const double* __restrict__ src, int C, int d, int Cs, R* t0, R* t1, R* t2, R* t3) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, k = k0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && k < d) ? src[(size_t)c * d + k] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int k = k0 + i, c = c0 + threadIdx.x;
+        if (k < d && c < Cs) {
+            const R v = (R)tile[threadIdx.x][i];
+            const size_t o = (size_t)k * Cs + c;
+            t0[o] = v;
+            if (t1) t1[o] = v;
+            if (t2) t2[o] = v;
+            if (t3) t3[o] = v;
+        }
+    }
+}
+
 template <typename R>
 struct EngineT : tda_engine {
     tda::Params<R> P;
@@ -79,6 +103,7 @@ struct EngineT : tda_engine {
     int kernel_choice = 0;     // 0 auto, 1 generic, 2 tensor-core DA (3xTF32), 3 tensor-core DA (fp16 split)
     int z_round_user = 0;      // generic / TF32 kernels: use the z16 normal stream (tda_set TDA_G_ZROUND)
     std::vector<int> ldA;
+    double* stage_theta = nullptr;   // device staging for the initial states ([C][d] float64)
     tda::DaTcState<R> tc;      // tcgen05 fast path (float only; inert for double)
     tda::DaTc16State<R> tc16;  // fp16-split tcgen05 fast path (float only)
     bool tc16_unfit = false;   // prepare() found operands that do not fit the fp16 range
@@ -313,11 +338,17 @@ struct EngineT : tda_engine {
         }
         case TDA_UP_INIT_THETA: {
             if ((r = need((size_t)P.C * d))) return r;
-            std::vector<R> h((size_t)d * Cs, (R)0);
-            for (int c = 0; c < P.C; c++)
-                for (int k = 0; k < d; k++) h[(size_t)k * Cs + c] = (R)host[(size_t)c * d + k];
-            for (int l = 0; l < L; l++)
-                if ((r = put(P.lv[l].theta, h))) return r;
+            // one H2D copy of the caller's [C][d] float64 array (asynchronous when it is pinned),
+            // transposed / converted on the device
+            if (!stage_theta) DALLOC(stage_theta, (size_t)P.C * d);
+            CUDA_TRY(cudaMemcpyAsync(stage_theta, host, (size_t)P.C * d * sizeof(double), cudaMemcpyHostToDevice, 0));
+            R* t[4] = {nullptr, nullptr, nullptr, nullptr};
+            for (int l = 0; l < L && l < 4; l++) t[l] = P.lv[l].theta;
+            dim3 grid((unsigned)((Cs + 31) / 32), (unsigned)((d + 31) / 32)), block(32, 8);
+            init_theta_kernel<R><<<grid, block>>>(stage_theta, P.C, d, Cs, t[0], t[1], t[2], t[3]);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(0));
             return 0;
         }
         case TDA_UP_STREAM_Z:
