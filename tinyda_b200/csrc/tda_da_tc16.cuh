@@ -353,13 +353,13 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     uint64_t* bar_reqB = bars + 3;                  // [tile]     rows -> MMA: A_theta current, D_xi consumed
     uint64_t* bar_respA = bars + 5;                 // [tile]     MMA  -> rows: F_c(theta') complete in D[0:128)
     uint64_t* bar_respB = bars + 7;                 // [tile]     MMA  -> rows: xi complete in D[128:192)
-    uint64_t* bar_reqF = bars + 9;                  // [tile][buffer] rows -> MMA: fine-chunk accumulator consumed
-    uint64_t* bar_respF = bars + 13;                // [tile][buffer] MMA  -> rows: fine chunk complete
-    uint64_t* bar_zfull = bars + 17;                // [tile][buffer] RNG  -> MMA
-    uint64_t* bar_zfree = bars + 21;                // [tile][buffer] MMA  -> RNG
-    uint64_t* bar_full = bars + 25;                 // [NST]
-    uint64_t* bar_empty = bars + 25 + T16_NST;      // [NST]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 25 + 2 * T16_NST);
+    uint64_t* bar_reqF = bars + 9;                  // [tile][3] rows -> MMA: fine-chunk accumulator consumed
+    uint64_t* bar_respF = bars + 15;                // [tile][3] MMA  -> rows: fine chunk complete
+    uint64_t* bar_zfull = bars + 21;                // [tile][buffer] RNG  -> MMA
+    uint64_t* bar_zfree = bars + 25;                // [tile][buffer] MMA  -> RNG
+    uint64_t* bar_full = bars + 29;                 // [NST]
+    uint64_t* bar_empty = bars + 29 + T16_NST;      // [NST]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 29 + 2 * T16_NST);
 
     // the shuffle tells the compiler that the warp index (and everything derived from it: tile,
     // TMEM / shared-memory bases, MMA descriptors) is warp-uniform -> uniform registers
@@ -373,9 +373,11 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             tc::mbar_init(bar_respA + i, 1);
             tc::mbar_init(bar_respB + i, 1);
         }
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 6; i++) {
             tc::mbar_init(bar_reqF + i, 8);
             tc::mbar_init(bar_respF + i, 1);
+        }
+        for (int i = 0; i < 4; i++) {
             tc::mbar_init(bar_zfull + i, 4);
             tc::mbar_init(bar_zfree + i, 1);
         }
@@ -486,9 +488,9 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             uint64_t* reqB = bar_reqB + t;
             uint64_t* respA = bar_respA + t;
             uint64_t* respB = bar_respB + t;
-            uint64_t* reqF = bar_reqF + t * 2;
-            uint64_t* respF = bar_respF + t * 2;
-            uint32_t pa = 0, pb = 0, pf0 = 0, pf1 = 0;
+            uint64_t* reqF = bar_reqF + t * 3;
+            uint64_t* respF = bar_respF + t * 3;
+            uint32_t pa = 0, pb = 0, pf = 0;              // pf: bit b = parity of reqF[b]
             unsigned n = 0, gch = 0;
             int total_it = 0;
             {
@@ -532,12 +534,13 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 // have signalled the end of the last coarse step
                 tc::mbar_wait(reqA, pa); pa ^= 1;
                 tc::mbar_wait(reqB, pb); pb ^= 1;
-                for (int c = 0; c < NCH; c++, gch++) {
-                    const int b = c & 1;
+                // three 64-column accumulators (the xi columns are idle during the fine stage): the
+                // MMAs run up to two chunks ahead of the rows' residual pass
+                for (int c = 0, b = 0; c < NCH; c++, gch++, b = (b == 2 ? 0 : b + 1)) {
                     const int st = (int)(gch % T16_NST);
-                    if (c >= 2) {
-                        if (b) { tc::mbar_wait(reqF + 1, pf1); pf1 ^= 1; }
-                        else { tc::mbar_wait(reqF, pf0); pf0 ^= 1; }
+                    if (c >= 3) {
+                        tc::mbar_wait(reqF + b, (pf >> b) & 1u);
+                        pf ^= 1u << b;
                     }
                     tc::mbar_wait(bar_full + st, (uint32_t)((gch / T16_NST) & 1));
                     tc::fence_after_sync();
@@ -569,9 +572,9 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         uint64_t* reqB = bar_reqB + t;
         uint64_t* respA = bar_respA + t;
         uint64_t* respB = bar_respB + t;
-        uint64_t* reqF = bar_reqF + t * 2;
-        uint64_t* respF = bar_respF + t * 2;
-        uint32_t phA = 0, phB = 0, ph0 = 0, ph1 = 0;
+        uint64_t* reqF = bar_reqF + t * 3;
+        uint64_t* respF = bar_respF + t * 3;
+        uint32_t phA = 0, phB = 0, phF = 0;           // phF: bit b = parity of respF[b]
         int sbuf = 0;
         const LevelP<float>& l0 = p.lv[0];
         const LevelP<float>& l1 = p.lv[1];
@@ -722,10 +725,12 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 float u2 = 0.0f;
                 if (h == 0) u2 = draw_u();
                 float ssq_f = 0.0f, ssq_p = 0.0f;
-                for (int c = 0; c < NCH; c++) {
-                    const int b = c & 1;
-                    if (b) wait_mma(respF + 1, ph1);
-                    else wait_mma(respF, ph0);
+                for (int c = 0, b = 0; c < NCH; c++, b = (b == 2 ? 0 : b + 1)) {
+                    {
+                        uint32_t phb = (phF >> b) & 1u;
+                        wait_mma(respF + b, phb);
+                        phF ^= 1u << b;
+                    }
                     uint32_t v0[16], v1[16];
                     tc::tmem_ld16(tD + b * T16_CH + col0, v0);
                     tc::tmem_ld16(tD + b * T16_CH + col0 + 16, v1);
@@ -734,7 +739,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                                                                              : s_ny + T16_MAX_MC + T16_K + c * T16_CH + col0);
                     const float scl = last ? sc_p : sc_f;
                     tc::tmem_wait_ld();
-                    if (c + 2 < NCH) t16_warp_arrive(reqF + b, lane);
+                    if (c + 3 < NCH) t16_warp_arrive(reqF + b, lane);
                     unsigned long long a2 = 0ull, b2 = 0ull;
                     const unsigned long long scl2 = f2pack(scl, scl);
 #pragma unroll
