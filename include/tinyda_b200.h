@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define TDA_ABI_VERSION 1
+#define TDA_ABI_VERSION 2
 #define TDA_MAX_LEVELS 4
 #define TDA_MAX_D 64
 
@@ -95,8 +95,11 @@ typedef struct tda_config {
     int32_t n_levels;
     int32_t d;
     int32_t subchain[TDA_MAX_LEVELS];   /* J[l] for l < n_levels-1                     */
-    int32_t aem;                        /* 0 none, 1 state-independent                 */
+    int32_t aem;                        /* 0 none, 1 state-independent (chain.py:485-499, proposal.py:1442-1467),
+                                         * 2 state-dependent (two levels; chain.py:446-473, :501-522) */
     int32_t rng_mode;
+    int32_t randomize_subchain;         /* DAChain randomize_subchain_length, chain.py:310-321, :369, :525-527 */
+    int32_t reserved0;
     uint64_t seed;
     int64_t n_chains;                   /* chains on THIS device                       */
     int64_t chain_offset;               /* global index of local chain 0 (Philox key)  */

@@ -19,9 +19,13 @@ Reference map (file:line are into /root/reference/tinyDA/):
   eval_model           posterior.py:95 (user model; here the device-resident model classes)
   LogLike.*            distributions.py:246-449
   Moments              utils.py:9-124 (RecursiveSampleMoments)
+  ZeroMeanMoments      utils.py:127-201 (ZeroMeanRecursiveSampleMoments, state-dependent AEM)
   ChainOracle.base_step    chain.py:101-125 / chain.py:415-444 / proposal.py:1583-1613
   ChainOracle.upper_step   chain.py:353-402 / chain.py:708-765 / proposal.py:1511-1578
   ChainOracle._align       proposal.py:1469-1493 (object identity replaced by saved versions)
+  ChainOracle._alpha_state_dependent   chain.py:446-473, distributions.py:427-446,
+                                       proposal.py:364-369 (CrankNicolson.get_q)
+  randomize_subchain_length            chain.py:310-321, :369-375, :525-527
   proposals            proposal.py:132-258 (RWMH), 261-369 (pCN), 372-512 (AM),
                        608-852 (DREAMZ), 861-1005 (MALA), 1627-1656 + ray.py:366-384 (DREAM)
 """
@@ -123,6 +127,10 @@ class LogLike:
         if not np.all(sigma < 1e-9):
             self.cov_inverse = np.linalg.inv(self.cov + sigma)
 
+    def loglike_custom_bias(self, F, bias):                      # distributions.py:427-446
+        r = F + bias - self.data
+        return -0.5 * (r @ self.cov_inverse @ r)
+
     def grad_loglike(self, F):                                   # distributions.py:300-329,448
         if self.kind == LIK_ISO:
             return 1.0 / self.var * (self.data - F)
@@ -154,6 +162,18 @@ class Moments:
             + np.outer(x, x)
             + self.epsilon * np.eye(self.d)
         )
+        self.t += 1
+
+
+class ZeroMeanMoments:
+    """ZeroMeanRecursiveSampleMoments, utils.py:127-201 (t starts at 1)."""
+
+    def __init__(self, m):
+        self.sigma = np.zeros((m, m))
+        self.t = 1
+
+    def update(self, x):                                         # utils.py:190-201
+        self.sigma = (self.t - 1) / self.t * self.sigma + 1 / self.t * np.outer(x, x)
         self.t += 1
 
 
@@ -207,7 +227,9 @@ class ChainOracle:
     """One (ML)DA / MH chain.  spec is the plain dict produced by
     tinyda_b200.lowering.lower_problem (or loaded from a golden fixture):
 
-      n_levels, d, J (list, len n_levels-1), aem (0/1),
+      n_levels, d, J (list, len n_levels-1),
+      aem (0 none / 1 state-independent / 2 state-dependent, two levels only),
+      randomize (0/1: DAChain randomize_subchain_length, two levels only),
       prior: dict(mean, LP, logconst, cov)
       levels: list of dict(lik=dict(kind, data, var|cov), model=dict(kind, A, b, scalars, m))
       proposal: dict(kind, T, scaling, adaptive, gamma, period, alpha_star,
@@ -221,6 +243,8 @@ class ChainOracle:
         self.d = int(spec["d"])
         self.J = [int(j) for j in spec.get("J", [])]
         self.aem = int(spec.get("aem", 0))
+        self.randomize = int(spec.get("randomize", 0))
+        self.sub_states = []                                     # coarse links of the running subchain
         self.prior = spec["prior"]
         self.models = [lv["model"] for lv in spec["levels"]]
         self.liks = [LogLike(lv["lik"]) for lv in spec["levels"]]
@@ -279,7 +303,7 @@ class ChainOracle:
             self.bias = [None] * L
             for l in range(1, L):
                 self.model_diff[l] = self.cur[l].F - self.cur[l - 1].F
-                self.bias[l] = Moments(self.model_diff[l], m)
+                self.bias[l] = ZeroMeanMoments(m) if self.aem == 2 else Moments(self.model_diff[l], m)
             for l in range(L - 1, 0, -1):
                 self._push_bias(l)
 
@@ -311,7 +335,9 @@ class ChainOracle:
         l-1's last link.  Top level: own bias only (chain.py:659-661, 753-756); lower
         levels: sums over all finer biases, current values (proposal.py:1454-1458, 1563-1569)."""
         L = self.L
-        if l == L - 1:
+        if self.aem == 2:                                        # chain.py:296-300, 517-522
+            mu, sigma = self.model_diff[l], self.bias[l].sigma
+        elif l == L - 1:
             mu, sigma = self.bias[l].mu, self.bias[l].sigma
         else:
             mu = np.sum([self.bias[k].mu for k in range(l, L)], axis=0)
@@ -422,7 +448,29 @@ class ChainOracle:
         self._record(0, acc)
         self.last_alpha = alpha
         self.last_u = u
+        if self.randomize:
+            self.sub_states.append(self.cur[0])
         self._adapt(self.cur[0].theta, old.theta)
+
+    def _get_q_pcn(self, x, y):
+        """CrankNicolson.get_q (proposal.py:364-369) without the normalising constant, which is
+        the same in every term of the state-dependent acceptance and cancels exactly."""
+        s = self.scaling
+        w = (y.theta - np.sqrt(1 - s ** 2) * x.theta) @ self.prior["LP"]
+        return -0.5 * np.sum(np.square(w)) / s ** 2
+
+    def _alpha_state_dependent(self, l, new, below, start_below):   # chain.py:446-473
+        bias_next = new.F - below.F
+        biased_post = start_below.prior + self.liks[l - 1].loglike_custom_bias(start_below.F, bias_next)
+        if self.kind in (PROP_RWMH, PROP_AM):                    # is_symmetric, proposal.py:168
+            q_x_y = q_y_x = 0.0
+        elif self.kind == PROP_PCN:
+            q_x_y = self._get_q_pcn(self.cur[l], new)
+            q_y_x = self._get_q_pcn(new, self.cur[l])
+        else:
+            raise NotImplementedError("the reference has no usable get_q for this proposal")
+        return np.exp(min(new.post + q_y_x, biased_post + q_x_y)
+                      - min(self.cur[l].post + q_x_y, below.post + q_y_x))
 
     def upper_step(self, l):
         Jb = self.J[l - 1]
@@ -430,18 +478,31 @@ class ChainOracle:
         if sum(self.accepted[l - 1][-Jb:]) == 0:                 # chain.py:357, 711; proposal.py:1516
             acc = False
         else:
+            if self.randomize:                                   # chain.py:369, 525-527
+                k = min(int(np.floor(self.S.uniform() * Jb)), Jb - 1)
+                below = self.sub_states[-Jb + k]
             new = self._create(l, below.theta, below.sid)
             start_below = self.saved[l - 1][l]
             with np.errstate(over="ignore", invalid="ignore"):
-                alpha = np.exp(new.post - self.cur[l].post + start_below.post - below.post)
+                if self.aem == 2:
+                    alpha = self._alpha_state_dependent(l, new, below, start_below)
+                else:
+                    alpha = np.exp(new.post - self.cur[l].post + start_below.post - below.post)
             u = self.S.uniform()
             acc = bool(u < alpha)
             if acc:
                 self.cur[l] = new
+                self.cur[l - 1] = below                          # chain.py:383 (the promoted link)
+        self.sub_states = []
         self.accepted[l].append(acc)
         self._record(l, acc)
         self._align(l, acc)
-        if self.aem:
+        if self.aem == 2:                                        # chain.py:501-522
+            corrected = self.cur[l].F - (self.cur[l - 1].F + self.model_diff[l])
+            self.model_diff[l] = self.cur[l].F - self.cur[l - 1].F
+            self.bias[l].update(corrected)
+            self._push_bias(l)
+        elif self.aem:
             if acc:
                 self.model_diff[l] = self.cur[l].F - self.cur[l - 1].F
             self.bias[l].update(self.model_diff[l])

@@ -52,7 +52,8 @@ def run_reference_chain(tda, posts, prop, kw, theta0, iterations, store_F):
         ch.sample(iterations, progressbar=False)
         return [_hist(ch.chain, ch.accepted, store_F)], ch
     if L == 2:
-        ch = tda.DAChain(posts[0], posts[1], prop, kw["subchain_length"], False, theta0,
+        ch = tda.DAChain(posts[0], posts[1], prop, kw["subchain_length"],
+                         kw.get("randomize_subchain_length", False), theta0,
                          kw.get("adaptive_error_model"), True)
         ch.sample(iterations, progressbar=False)
         coarse = _hist(list(compress(ch.chain_coarse, ch.is_coarse)),
@@ -139,7 +140,7 @@ def make(name):
     posts_ref, prop_ref, kw = defn["build"](tda)
     posts_our, prop_our, kw2 = defn["build"](ours)
     spec = ours.lower_problem(posts_our, prop_our, kw2.get("subchain_length"),
-                              kw2.get("adaptive_error_model"))
+                              kw2.get("adaptive_error_model"), kw2.get("randomize_subchain_length", False))
     C, iters, seed = defn["n_chains"], defn["iterations"], defn["seed"]
     store_F = defn.get("store_F", True)
     rng = np.random.default_rng(seed)

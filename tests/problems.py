@@ -166,6 +166,77 @@ def da_aem_linear():
 
 
 @case
+def da_sdaem_rwmh():
+    """DA + STATE-DEPENDENT adaptive error model (chain.py:446-473, 501-522) with a symmetric
+    proposal and the recommended subchain length 1."""
+    rng = np.random.default_rng(61)
+    d, m = 4, 10
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    (Gc, yc), (Gf, yf) = _linear_levels(rng, d, [m, m], 0.1, prior, coarse_mode="same", perturb=0.05)
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.AdaptiveGaussianLogLike(yc, 0.01 * np.eye(m)), LinearModel(Gc))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(yf, 0.01 * np.eye(m)), LinearModel(Gf))
+        prop = tda.GaussianRandomWalk(C=0.01 * np.eye(d))
+        return [pc, pf], prop, dict(subchain_length=1, adaptive_error_model="state-dependent")
+    return dict(build=build, n_chains=3, iterations=120, seed=63, prior=prior)
+
+
+@case
+def da_sdaem_pcn():
+    """State-dependent error model with the non-symmetric pCN proposal: the transition densities
+    CrankNicolson.get_q (proposal.py:364-369) enter the second-stage acceptance; J = 3."""
+    rng = np.random.default_rng(64)
+    d, m = 6, 9
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d, 0.4))
+    (Gc, yc), (Gf, yf) = _linear_levels(rng, d, [m, m], 0.15, prior, coarse_mode="same", perturb=0.04)
+    B = rng.standard_normal((m, m))
+    cov = 0.0225 * (np.eye(m) + 0.03 * (B @ B.T))
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.AdaptiveGaussianLogLike(yc, cov), LinearModel(Gc))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(yf, cov), LinearModel(Gf))
+        prop = tda.CrankNicolson(scaling=0.15, adaptive=True, period=30)
+        return [pc, pf], prop, dict(subchain_length=3, adaptive_error_model="state-dependent")
+    return dict(build=build, n_chains=3, iterations=70, seed=65, prior=prior)
+
+
+@case
+def da_randomize_pcn():
+    """DA with randomize_subchain_length (chain.py:369, 525-527): a uniformly chosen link of the
+    coarse subchain is promoted; J = 5."""
+    rng = np.random.default_rng(66)
+    d = 8
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d))
+    (Gc, yc), (Gf, yf) = _linear_levels(rng, d, [8, 32], 0.1, prior)
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.GaussianLogLike(yc, 0.01 * np.eye(8)), LinearModel(Gc))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(yf, 0.01 * np.eye(32)), LinearModel(Gf))
+        return [pc, pf], tda.CrankNicolson(scaling=0.1), dict(subchain_length=5, randomize_subchain_length=True)
+    return dict(build=build, n_chains=4, iterations=80, seed=67, prior=prior)
+
+
+@case
+def da_randomize_aem():
+    """randomize_subchain_length together with the state-independent error model and an
+    adaptively scaled random walk (the promoted link re-enters the coarse chain and is the one
+    the bias update and the re-scoring see)."""
+    rng = np.random.default_rng(68)
+    d, m = 4, 10
+    prior = stats.multivariate_normal(0.1 * np.ones(d), np.eye(d))
+    (Gc, yc), (Gf, yf) = _linear_levels(rng, d, [m, m], 0.1, prior, coarse_mode="same", perturb=0.05)
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.AdaptiveGaussianLogLike(yc, 0.01 * np.eye(m)), LinearModel(Gc))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(yf, 0.01 * np.eye(m)), LinearModel(Gf))
+        prop = tda.GaussianRandomWalk(C=0.01 * np.eye(d), adaptive=True, period=20)
+        return [pc, pf], prop, dict(subchain_length=4, adaptive_error_model="state-independent",
+                                    randomize_subchain_length=True)
+    return dict(build=build, n_chains=3, iterations=60, seed=69, prior=prior)
+
+
+@case
 def mlda3_linear():
     """3-level MLDA without error model, J=[3,2], different output sizes per level."""
     rng = np.random.default_rng(7)
@@ -299,6 +370,8 @@ def stream_sizes(spec, iterations):
     for j in reversed(spec["J"]):      # upper-level accept tests
         nu += iterations * mult
         mult *= j
+    if spec.get("randomize"):          # one index draw per fine iteration
+        nu += iterations
     if kind in (4, 5):
         nu += base_steps * (2 * spec["proposal"]["delta"] + 1 + d + 1 + d)
     return nz + 8, nu + 8

@@ -18,7 +18,8 @@ def _build(name):
     return tda, defn, posts, prop, kw
 
 
-@pytest.mark.parametrize("name", ["mh_rwmh_linreg", "da_pcn_small", "mlda3_linear", "mlda4_aem_poisson"])
+@pytest.mark.parametrize("name", ["mh_rwmh_linreg", "da_pcn_small", "mlda3_linear", "mlda4_aem_poisson",
+                                  "da_sdaem_pcn", "da_randomize_aem"])
 def test_sample_result_dict_matches_reference_trajectories(name):
     """tda.sample(...) with injected streams: same dict keys / lengths as tinyDA.sample and the
     same Links as the reference produced (golden fixture)."""
@@ -64,7 +65,9 @@ def test_store_coarse_chain_false_returns_none_like_the_reference():
 
 @pytest.mark.parametrize("name,dtype", [("da_pcn_small", "float64"), ("mh_pcn_diag", "float64"),
                                         ("mala_rosenbrock", "float64"), ("dreamz_linear", "float64"),
-                                        ("mlda3_aem_linear", "float64")])
+                                        ("mlda3_aem_linear", "float64"), ("da_sdaem_rwmh", "float64"),
+                                        ("da_sdaem_pcn", "float64"), ("da_randomize_pcn", "float64"),
+                                        ("da_randomize_aem", "float64")])
 def test_philox_mode_equals_oracle_fed_the_exported_streams(name, dtype):
     """Production RNG mode: the engine's in-kernel Philox draws, exported with tda_fill_streams
     and fed to the CPU oracle, give the engine's own trajectories -> the counter-based streams

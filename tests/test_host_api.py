@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "library does not export %s" % name
     from tinyda_b200 import _lib
     assert set(_lib.EXPORTS) == declared
-    assert lib.tda_abi_version() == 1
+    assert lib.tda_abi_version() == 2
 
 
 def test_config_struct_layout_matches_header(tmp_path):
@@ -95,6 +95,35 @@ def test_sample_rejects_what_the_reference_rejects():
         tda.sample(post, tda.GaussianRandomWalk(np.eye(3)), 10, n_chains=2, initial_parameters=[np.zeros(3)])
     with pytest.raises(AssertionError):
         tda.sample(post, tda.GaussianRandomWalk(np.eye(3)), 10, initial_parameters=np.zeros(4))
+
+
+def test_error_model_and_randomize_options_are_checked_like_the_reference():
+    """chain.py:305 (unknown error model), :310-314 (randomize needs J > 1 and the coarse chain),
+    sampler.py:184-193 (warnings); plus what the device lowering cannot honour."""
+    post = _post()
+    rw = tda.GaussianRandomWalk(np.eye(3))
+    with pytest.raises(ValueError, match="state-dependent, state-independent or None"):
+        tda.sample([post, post], rw, 5, adaptive_error_model="sometimes")
+    with pytest.raises(ValueError, match="subchain_length > 1"):
+        tda.sample([post, post], rw, 5, subchain_length=1, randomize_subchain_length=True)
+    with pytest.raises(ValueError, match="requires storing the coarse chain"):
+        tda.sample([post, post], rw, 5, subchain_length=3, randomize_subchain_length=True,
+                   store_coarse_chain=False)
+    with pytest.raises(TypeError, match="AdaptiveGaussianLogLike"):
+        with pytest.warns(UserWarning, match="not guaranteed to be ergodic"):
+            tda.sample([post, post], rw, 5, subchain_length=3, adaptive_error_model="state-dependent")
+    # lowering: aem code 2, randomize flag; the state-dependent model is two-level only
+    prior = stats.multivariate_normal(np.zeros(3), np.eye(3))
+    G = np.arange(12.0).reshape(4, 3) / 10
+    pc = tda.Posterior(prior, tda.AdaptiveGaussianLogLike(np.zeros(4), 0.1 * np.eye(4)), tda.LinearModel(G))
+    pf = tda.Posterior(prior, tda.GaussianLogLike(np.zeros(4), 0.1 * np.eye(4)), tda.LinearModel(G))
+    spec = tda.lower_problem([pc, pf], tda.CrankNicolson(0.2), 3, "state-dependent", True)
+    assert spec["aem"] == 2 and spec["randomize"] == 1
+    assert tda.lower_problem([pc, pf], rw, 3, "state-independent")["aem"] == 1
+    with pytest.raises(ValueError, match="two-level"):
+        tda.lower_problem([pc, pc, pf], rw, [2, 2], "state-dependent")
+    with pytest.raises(ValueError, match="two-level"):
+        tda.lower_problem([pc, pc, pf], rw, [2, 2], None, True)
 
 
 def test_python_callable_model_is_rejected_not_run_on_cpu():

@@ -68,6 +68,7 @@ template <typename R>
 struct Params {
     int mode, L, d, aem, rng_mode, prop_kind, adaptive, period, am_t0, am_device_refactor;
     int z_round;               // Philox normals on the fp16 grid ("z16" stream, float engine)
+    int randomize;             // DA: randomize_subchain_length (chain.py:310-321)
     int J[MAXL];
     int C, Cs, n_tiles;
     long long chain_offset, Cg, arch_off;   // arch_off: first archive column owned by this engine
@@ -103,6 +104,13 @@ struct Params {
     R* archive;            // DREAM: [cap][Cg][d]
     R* sum1;               // [d][Cs] running sum of finest-level states
     R* sum2;               // [d][Cs] running sum of squares
+    // randomize_subchain_length: the link of the running coarse subchain that will be promoted
+    int* promo_j;          // [Cs] 1-based coarse step after which it is taken
+    R* pm_theta;           // [d][Cs]
+    R* pm_prior;           // [Cs]
+    R* pm_like;            // [Cs]
+    R* pm_F;               // [m0][Cs] (need_F)
+    int* pm_sid;           // [Cs]
     R* scratch;            // POISSON: [3][n_max][Cs]  (k-field, c', d')
     int n_max;
     int* error_flag;

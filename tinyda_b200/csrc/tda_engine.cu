@@ -144,6 +144,7 @@ struct EngineT : tda_engine {
         P.L = L; P.d = d; P.aem = c.aem; P.rng_mode = c.rng_mode; P.prop_kind = c.prop_kind;
         P.adaptive = c.adaptive; P.period = c.period > 0 ? c.period : 1; P.am_t0 = c.am_t0;
         P.am_device_refactor = c.am_device_refactor;
+        P.randomize = c.randomize_subchain;
         for (int l = 0; l < TDA_MAX_LEVELS; l++) P.J[l] = c.subchain[l];
         P.C = (int)c.n_chains;
         // padded to whole pairs of 128-chain tiles (the tensor-core kernel processes tile pairs)
@@ -240,6 +241,14 @@ struct EngineT : tda_engine {
             if (lc.store & TDA_STORE_STATS) { DALLOC(v.h_prior, cap * Cs); DALLOC(v.h_like, cap * Cs); }
             if (lc.store & TDA_STORE_OUTPUT) DALLOC(v.h_F, cap * m * Cs);
             if (lc.store & TDA_STORE_ACCEPT) DALLOC(v.h_acc, cap * Cs);
+        }
+        if (c.randomize_subchain) {
+            DALLOC(P.promo_j, Cs);
+            DALLOC(P.pm_theta, (size_t)d * Cs);
+            DALLOC(P.pm_prior, Cs);
+            DALLOC(P.pm_like, Cs);
+            DALLOC(P.pm_sid, Cs);
+            if (P.lv[0].need_F) DALLOC(P.pm_F, (size_t)P.lv[0].m * Cs);
         }
         if (kt > tda::MAXD) return fail(-1, "contraction dimension exceeds TDA_MAX_D");
         if (n_max > 0) { P.n_max = n_max; DALLOC(P.scratch, (size_t)3 * n_max * Cs); }
@@ -668,6 +677,12 @@ int validate(const tda_config* c) {
         if (c->dream_M0 < 2 || c->dream_capacity < c->dream_M0) return fail(-1, "DREAM archive capacity too small");
     }
     if (c->adaptive && c->period < 1) return fail(-1, "period must be >= 1");
+    if (c->aem < 0 || c->aem > 2) return fail(-1, "aem must be 0, 1 (state-independent) or 2 (state-dependent)");
+    if (c->aem == 2 && c->n_levels != 2) return fail(-1, "the state-dependent error model is a two-level method");
+    if (c->aem == 2 && c->prop_kind != TDA_PROP_RWMH && c->prop_kind != TDA_PROP_AM && c->prop_kind != TDA_PROP_PCN)
+        return fail(-1, "the state-dependent error model needs a symmetric proposal or pCN");
+    if (c->randomize_subchain && (c->n_levels != 2 || c->subchain[0] < 2))
+        return fail(-1, "randomize_subchain needs two levels and a subchain length > 1");
     for (int l = 0; l < c->n_levels; l++) {
         const tda_level_config& lc = c->level[l];
         if (lc.m < 1) return fail(-1, "level has no outputs");

@@ -18,6 +18,9 @@
 //   Tile::propose_*        proposal.py:247-251 (RWMH/AM), :349-355 (pCN), :811-852 (DREAMZ),
 //                          :948-959 (MALA)
 //   Tile::adapt            proposal.py:228-245, :502-512, :790-795; utils.py:113-124
+//   Tile::sd_terms / aem_update_sd   state-dependent error model chain.py:446-473, :501-522;
+//                          utils.py:190-201; distributions.py:427-446; proposal.py:364-369
+//   Tile::draw_promoted / snapshot_promoted   randomize_subchain_length chain.py:369, :525-527
 #pragma once
 #include "tda_common.cuh"
 
@@ -359,7 +362,8 @@ struct Tile {
             bool all_small = true;
             for (int i = 0; i < m; i++) {
                 R mu = (R)0;
-                for (int k = l; k <= kend; k++) mu += p.lv[k].bias_mu[gi(i, c)];
+                if (p.aem == 2) mu = p.lv[l].model_diff[gi(i, c)];     // chain.py:296-300, :519-522
+                else for (int k = l; k <= kend; k++) mu += p.lv[k].bias_mu[gi(i, c)];
                 lo.lik_bias[gi(i, c)] = mu;
             }
             // covariance sum; written into lik_prec as workspace only if it will be inverted
@@ -451,6 +455,99 @@ struct Tile {
             }
             for (int i = 0; i < m; i++)
                 v.bias_mu[gi(i, c)] = g1 * (t * v.bias_mu[gi(i, c)] + v.model_diff[gi(i, c)]);
+        }
+        __syncthreads();
+    }
+
+    // state-dependent error model (two levels): ZeroMeanRecursiveSampleMoments.update with the
+    // difference corrected by the previous offset, then the offset itself (chain.py:501-522)
+    __device__ void aem_update_sd(int l, long long tcount) {
+        if (tid < TC) {
+            const int c = tid;
+            const LevelP<R>& v = p.lv[l];
+            const LevelP<R>& lo = p.lv[l - 1];
+            const int m = v.m;
+            R* corr = v.bias_mu;      // scratch: the mean is not used by this error model
+            for (int j = 0; j < m; j++) {
+                R ff = v.F[gi(j, c)], fc = lo.F[gi(j, c)];
+                corr[gi(j, c)] = ff - (fc + v.model_diff[gi(j, c)]);
+                v.model_diff[gi(j, c)] = ff - fc;
+            }
+            const R t = (R)tcount;
+            const R f1 = (t - (R)1) / t, f2 = (R)1 / t;
+            for (int i = 0; i < m; i++) {
+                R xi = corr[gi(i, c)];
+                for (int j = 0; j < m; j++) {
+                    size_t e = gi(i * m + j, c);
+                    v.bias_sigma[e] = f1 * v.bias_sigma[e] + f2 * (xi * corr[gi(j, c)]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // state-dependent second stage: q(x,y) = log N(y; sqrt(1-s^2) x, s^2 C) up to the constant
+    // that every term of chain.py:463-471 shares -> s_ca = q_x_y, s_cb = q_y_x (0 if symmetric).
+    // x = the level's current state, y = the promoted state in pt.
+    __device__ void sd_terms(int l) {
+        const int d = p.d;
+        const LevelP<R>& v = p.lv[l];
+        if (p.prop_kind != TDA_PROP_PCN) {
+            if (tid < TC) { s_ca[tid] = (R)0; s_cb[tid] = (R)0; }
+            __syncthreads();
+            return;
+        }
+        for (int pass = 0; pass < 2; pass++) {
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                R s = p.scaling[chain0 + c];
+                R a = tsqrt((R)1 - s * s);
+                R x = v.theta[gi(k, c)], y = pt[e];
+                zt[e] = pass == 0 ? y - a * x : x - a * y;
+            }
+            __syncthreads();
+            EpiSsq<R> e;
+            tile_gemm<R>(zt, (const R*)nullptr, p.LP, d, d, p.ldD, bs, KB, e);
+            R tot = reduce_cols(e.ps[0], e.ps[1]);
+            if (tid < TC) {
+                R s = p.scaling[chain0 + tid];
+                R q = (R)-0.5 * tot / (s * s);
+                if (pass == 0) s_ca[tid] = q; else s_cb[tid] = q;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- randomize_subchain_length (two levels) -------------------------------------------------
+    // np.random.randint(-J, 0) is drawn after the subchain (chain.py:369) from the uniform that
+    // follows the J accept-test uniforms; every base step of the proposals allowed here consumes
+    // exactly one uniform, so that value can be read before the subchain starts and the chosen
+    // link snapshotted when the subchain passes it.
+    __device__ void draw_promoted() {
+        if (tid < TC) {
+            const int g = chain0 + tid, J = p.J[0];
+            R u = uniform_at(tid, p.ucur[g] + J);
+            int k = (int)tfloor(u * (R)J);
+            if (k > J - 1) k = J - 1;
+            p.promo_j[g] = k + 1;          // index -J+k = the link after coarse step k+1
+        }
+        __syncthreads();
+    }
+    __device__ void snapshot_promoted(int j) {
+        const int d = p.d;
+        const LevelP<R>& lo = p.lv[0];
+        for (int e = tid; e < d * TC; e += NT) {
+            int k = e / TC, c = e - k * TC;
+            if (p.promo_j[chain0 + c] == j) p.pm_theta[gi(k, c)] = lo.theta[gi(k, c)];
+        }
+        if (lo.need_F)
+            for (int e = tid; e < lo.m * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                if (p.promo_j[chain0 + c] == j) p.pm_F[gi(k, c)] = lo.F[gi(k, c)];
+            }
+        if (tid < TC) {
+            const int g = chain0 + tid;
+            if (p.promo_j[g] == j) { p.pm_prior[g] = lo.prior[g]; p.pm_like[g] = lo.like[g]; p.pm_sid[g] = lo.sid[g]; }
         }
         __syncthreads();
     }
@@ -797,28 +894,61 @@ struct Tile {
         const int d = p.d;
         const LevelP<R>& v = p.lv[l];
         const LevelP<R>& lo = p.lv[l - 1];
+        const bool rnd = p.randomize != 0;
+        // the promoted link: the subchain's last one, or the randomly chosen one
+        const R* b_theta = rnd ? p.pm_theta : lo.theta;
+        const R* b_prior = rnd ? p.pm_prior : lo.prior;
+        const R* b_like = rnd ? p.pm_like : lo.like;
+        const R* b_F = rnd ? p.pm_F : lo.F;
+        const int* b_sid = rnd ? p.pm_sid : lo.sid;
         for (int e = tid; e < d * TC; e += NT) {
             int k = e / TC, c = e - k * TC;
-            pt[e] = lo.theta[gi(k, c)];
+            pt[e] = b_theta[gi(k, c)];
         }
         __syncthreads();
         eval_level(l);
+        if (p.aem == 2) sd_terms(l);
         if (tid < TC) {
             const int c = tid, g = chain0 + c;
             int acc = 0;
             if (lo.acc_sub[g] > 0) {
                 R pr = s_prior[c], lk = s_like[c];
-                R x = (pr + lk) - (v.prior[g] + v.like[g]) + (lo.sv_prior[l][g] + lo.sv_like[l][g]) - (lo.prior[g] + lo.like[g]);
+                const R post_new = pr + lk, post_cur = v.prior[g] + v.like[g];
+                const R post_below = b_prior[g] + b_like[g];
+                R x;
+                if (p.aem == 2) {
+                    // chain.py:446-473: the subchain start re-scored with the bias at the proposal
+                    const int m = lo.m;
+                    R q = (R)0;
+                    for (int i = 0; i < m; i++) {
+                        R ri = lo.sv_F[l][gi(i, c)] + (v.Fp[gi(i, c)] - b_F[gi(i, c)]) - lo.data[i];
+                        R t = (R)0;
+                        for (int j = 0; j < m; j++)
+                            t = fma(lo.lik_prec[gi(i * m + j, c)],
+                                    lo.sv_F[l][gi(j, c)] + (v.Fp[gi(j, c)] - b_F[gi(j, c)]) - lo.data[j], t);
+                        q = fma(ri, t, q);
+                    }
+                    const R post_biased = lo.sv_prior[l][g] + (R)-0.5 * q;
+                    const R qxy = s_ca[c], qyx = s_cb[c];
+                    // Python's min(a, b): a unless b < a (so a NaN in `a` survives, like the reference)
+                    const R n1 = post_new + qyx, n2 = post_biased + qxy;
+                    const R d1 = post_cur + qxy, d2 = post_below + qyx;
+                    x = ((n2 < n1) ? n2 : n1) - ((d2 < d1) ? d2 : d1);
+                } else {
+                    x = post_new - post_cur + (lo.sv_prior[l][g] + lo.sv_like[l][g]) - post_below;
+                }
                 R alpha = texp(x);
                 long long uc = p.ucur[g];
+                if (rnd) uc += 1;          // the index draw (read ahead by draw_promoted)
                 R u = uniform_at(c, uc);
                 p.ucur[g] = uc + 1;
                 acc = (u < alpha) ? 1 : 0;
                 if (acc) {
                     v.prior[g] = pr; v.like[g] = lk;
-                    v.sid[g] = lo.sid[g];
+                    v.sid[g] = b_sid[g];
                     v.n_acc[g] += 1;
                     v.acc_sub[g] += 1;
+                    if (rnd) { lo.prior[g] = b_prior[g]; lo.like[g] = b_like[g]; lo.sid[g] = b_sid[g]; }
                 }
             }
             s_acc[c] = acc;
@@ -826,19 +956,29 @@ struct Tile {
         __syncthreads();
         for (int e = tid; e < d * TC; e += NT) {
             int c = e % TC;
-            if (s_acc[c]) { int k = e / TC; v.theta[gi(k, c)] = pt[e]; }
+            if (s_acc[c]) {
+                int k = e / TC;
+                v.theta[gi(k, c)] = pt[e];
+                if (rnd) lo.theta[gi(k, c)] = pt[e];      // chain.py:383: the promoted link re-enters the coarse chain
+            }
         }
         if (v.need_F)
             for (int e = tid; e < v.m * TC; e += NT) {
                 int c = e % TC;
                 if (s_acc[c]) { int k = e / TC; v.F[gi(k, c)] = v.Fp[gi(k, c)]; }
             }
+        if (rnd && lo.need_F)
+            for (int e = tid; e < lo.m * TC; e += NT) {
+                int c = e % TC;
+                if (s_acc[c]) { int k = e / TC; lo.F[gi(k, c)] = b_F[gi(k, c)]; }
+            }
         __syncthreads();
         record(l);
         align(l);
         if (p.aem) {
             lvl_steps[l] += 1;
-            aem_update(l, lvl_steps[l]);
+            if (p.aem == 2) aem_update_sd(l, lvl_steps[l]);
+            else aem_update(l, lvl_steps[l]);
             push_bias(l);
         }
     }
@@ -890,6 +1030,10 @@ struct Tile {
                     v.model_diff[gi(k, c)] = df;
                     v.bias_mu[gi(k, c)] = df;
                 }
+                for (int e = tid; e < v.m * v.m * TC; e += NT) {
+                    int c = e % TC, ij = e / TC;
+                    v.bias_sigma[gi(ij, c)] = (R)0;
+                }
             }
             __syncthreads();
             for (int l = L - 1; l >= 1; l--) push_bias(l);
@@ -904,9 +1048,11 @@ struct Tile {
         for (int l = 0; l < MAXL; l++) cnt[l] = 0;
         long long it = 0;
         while (it < p.iterations) {
+            if (p.randomize && cnt[0] == 0) draw_promoted();
             base_step();
             if (L == 1) { it++; continue; }
             cnt[0]++;
+            if (p.randomize) snapshot_promoted(cnt[0]);
             int l = 0;
             while (l < L - 1 && cnt[l] == p.J[l]) {
                 cnt[l] = 0;

@@ -62,6 +62,7 @@ class Engine:
         for i, j in enumerate(spec["J"]):
             cfg.subchain[i] = int(j)
         cfg.aem = int(spec.get("aem", 0))
+        cfg.randomize_subchain = int(spec.get("randomize", 0))
         cfg.rng_mode = L.TDA_RNG_INJECTED if rng == "injected" else L.TDA_RNG_PHILOX
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.n_chains = self.C

@@ -16,7 +16,8 @@ MAX_LEVELS = 4
 MAX_D = 64
 
 
-def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_model=None):
+def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_model=None,
+                  randomize_subchain_length=False):
     if isinstance(posteriors, Posterior):
         posteriors = [posteriors]
     L = len(posteriors)
@@ -44,9 +45,13 @@ def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_mo
         J = []
     aem = 0
     if adaptive_error_model is not None and L > 1:
-        if adaptive_error_model != "state-independent":
-            raise NotImplementedError("only the state-independent adaptive error model runs on the device")
+        if adaptive_error_model not in ("state-independent", "state-dependent"):
+            raise ValueError("Adaptive error model can only be state-dependent, state-independent or None.")
         aem = 1
+        if adaptive_error_model == "state-dependent":
+            if L != 2:       # sampler.py:184-188 falls back before this point
+                raise ValueError("the state-dependent error model is a two-level method")
+            aem = 2
         ms = {lv["model"]["m"] for lv in levels}
         if len(ms) != 1:
             raise ValueError("the adaptive error model needs equal output sizes on all levels")
@@ -55,6 +60,17 @@ def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_mo
                 raise TypeError("coarse likelihoods must be AdaptiveGaussianLogLike when an "
                                 "adaptive error model is used")
     prop = proposal.lower(prior)
+    if aem == 2 and prop["kind"] not in (PROP_RWMH, PROP_AM, PROP_PCN):
+        # chain.py:456-460 needs is_symmetric or a working get_q(fine link, fine link): MALA's get_q
+        # reads a gradient the fine links do not carry and DREAM(Z) inherits a get_q that returns None
+        raise TypeError("the state-dependent error model needs a symmetric proposal or CrankNicolson")
+    randomize = 0
+    if randomize_subchain_length:
+        if L != 2:
+            raise ValueError("randomize_subchain_length is a two-level (Delayed Acceptance) option")
+        if J[0] == 1:                                                # chain.py:311-312
+            raise ValueError("Randomize subchain length requires a subchain_length > 1.")
+        randomize = 1
     if prop["kind"] == PROP_MALA:
         if L != 1:
             raise NotImplementedError("MALA is lowered for single-level sampling only")
@@ -62,7 +78,8 @@ def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_mo
             raise TypeError("MALA needs a model with an analytic gradient")
     if prop["kind"] in (PROP_DREAMZ, PROP_DREAM) and L != 1:
         raise NotImplementedError("DREAM(Z) is lowered for single-level sampling only")
-    return dict(n_levels=L, d=d, J=J, aem=aem, prior=prior, levels=levels, proposal=prop)
+    return dict(n_levels=L, d=d, J=J, aem=aem, randomize=randomize, prior=prior, levels=levels,
+                proposal=prop)
 
 
 # ---- (de)serialisation for golden fixtures ------------------------------------------------

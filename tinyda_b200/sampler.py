@@ -97,10 +97,11 @@ def sample(
         )
     if adaptive_error_model not in (None, "state-independent", "state-dependent"):
         raise ValueError("Adaptive error model can only be state-dependent, state-independent or None.")
-    if adaptive_error_model == "state-dependent":
-        raise NotImplementedError("the state-dependent adaptive error model is not lowered to the device yet")
-    if randomize_subchain_length:
-        raise NotImplementedError("randomize_subchain_length is not lowered to the device yet")
+    if n_levels == 2 and randomize_subchain_length:                   # chain.py:310-314
+        if subchain_length == 1:
+            raise ValueError("Randomize subchain length requires a subchain_length > 1.")
+        if not store_coarse_chain:
+            raise ValueError("Randomize subchain length requires storing the coarse chain.")
 
     # sharding: one process per GPU, contiguous chain ranges (ray.py:68-74 -> chain sharding)
     rank, world = parallel.rank_world()
@@ -127,7 +128,8 @@ def sample(
         theta0 = np.atleast_2d(posteriors[0].prior.rvs(n_chains, random_state=host_rng)).reshape(n_chains, -1)[lo:hi]
 
     spec = lower_problem(posteriors, proposal, subchain_length if n_levels > 1 else None,
-                         adaptive_error_model if n_levels > 1 else None)
+                         adaptive_error_model if n_levels > 1 else None,
+                         randomize_subchain_length if n_levels == 2 else False)
     kind = int(spec["proposal"]["kind"])
 
     archive0 = None
