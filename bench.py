@@ -333,6 +333,173 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------
+# Secondary workloads (BASELINE.json configs[2..4]); not the headline line, same timing rules
+# ------------------------------------------------------------------------------------------
+def _other_workload(name, world):
+    from tinyda_b200 import lower_problem, workloads
+    w = workloads.WORKLOADS[name]()
+    kw = w["kwargs"]
+    spec = lower_problem(w["posteriors"], w["proposal"], kw.get("subchain_length"), kw.get("adaptive_error_model"))
+    d = spec["d"]
+    s = 4
+    if name == "cfg3":     # theta, prior, loglike, F + accept byte
+        cfgd = dict(chains=1 << 20, iters=100, bytes_unit=(d + 3) * s + 1, flop_unit=120.0, bound="hbm",
+                    store="full")
+    elif name == "cfg4":
+        ns = [lv["model"]["n_grid"] for lv in spec["levels"]]
+        J = spec["J"]
+        evals = [J[0] * J[1] * J[2], J[1] * J[2], J[2], 1]
+        flop = sum(e * (2 * d + 9) * n for e, n in zip(evals, ns))
+        cfgd = dict(chains=16384, iters=4, bytes_unit=(d + 2) * s + 1, flop_unit=float(flop), bound="fp32", store="stats")
+    elif name == "cfg5":
+        m = spec["levels"][0]["model"]["m"]
+        cfgd = dict(chains=8192 // world, iters=50, bytes_unit=(d + 2) * s + 1 + 3 * d * s, flop_unit=2.0 * d * m,
+                    bound="latency", store="stats")
+    else:
+        raise SystemExit("unknown workload " + name)
+    return w, spec, cfgd
+
+
+def run_other(args):
+    """configs[2..4] through the generic lock-step kernel: device-timed value, e2e with the
+    finest-level history copied to pinned host memory, and the SURVEY 8(d) roofline figure."""
+    import torch
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_FULL, STORE_NONE, launch_count
+    from tinyda_b200 import parallel
+    from tinyda_b200.proposal import PROP_DREAM
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w, spec, cd = _other_workload(args.workload, world)
+    C = args.chains if args.chains != N_CHAINS_PER_GPU else cd["chains"]
+    iters = args.iters if args.iters != ITERS_PER_STEP else cd["iters"]
+    L, d = spec["n_levels"], spec["d"]
+    shared = int(spec["proposal"]["kind"]) == PROP_DREAM
+    rng = np.random.default_rng(1000 + rank)
+    theta0 = np.atleast_2d(w["prior"].rvs(C, random_state=rng)).reshape(C, -1).astype(np.float64)
+    archive0 = None
+    total_runs = args.warmup + args.steps + 2 + max(2, min(args.steps, 5))
+    if shared:
+        M0 = int(spec["proposal"]["M0"])
+        arng = np.random.default_rng(77)
+        archive0 = np.atleast_2d(w["prior"].rvs(world * C * M0, random_state=arng)).reshape(world * C, M0, d)
+    store = [STORE_NONE] * (L - 1) + [STORE_FULL if cd["store"] == "full" else STORE_STATS]
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = Engine(spec, C, dtype=args.dtype, rng="philox", seed=2024, store=store,
+                 capacity_iterations=iters if not shared else iters * total_runs + 64, device=local_rank,
+                 chain_offset=rank * C, n_chains_global=world * C if shared else C, archive0=archive0, stream=stream)
+    eng.init(theta0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        eng.history_reset()
+        if shared and world > 1:
+            parallel.run_dream_shared(eng, iters, rank, world)
+        else:
+            eng.run(iters)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    acc0 = eng.get("accept_counts").astype(np.float64)
+    l0 = launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        one_step()
+        ev[k][1].record()
+    barrier()
+    launches = launch_count() - l0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = float(sum(ms_steps))
+    acc1 = eng.get("accept_counts").astype(np.float64)
+    accept_rate = [float((b - a).mean() / (iters * args.steps * st)) for a, b, st in zip(acc0, acc1, eng.steps)]
+
+    # e2e: initial states from pinned host memory, run, finest-level history to pinned host memory
+    tdt = torch.float32 if args.dtype == "float32" else torch.float64
+    top = L - 1
+    m_top = int(spec["levels"][top]["model"]["m"])
+    pin_theta0 = torch.from_numpy(theta0).pin_memory()
+    h_theta = torch.empty((iters, d, C), dtype=tdt).pin_memory()
+    h_prior = torch.empty((iters, C), dtype=tdt).pin_memory()
+    h_like = torch.empty((iters, C), dtype=tdt).pin_memory()
+    h_acc = torch.empty((iters, C), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty((iters, m_top, C), dtype=tdt).pin_memory() if cd["store"] == "full" else None
+
+    def e2e_step():
+        eng.history_reset()
+        if not shared:                                   # DREAM keeps its archive: states continue
+            eng.init(pin_theta0.numpy())
+        one_rec0 = int(eng.n_records()[top])
+        if shared and world > 1:
+            parallel.run_dream_shared(eng, iters, rank, world)
+        else:
+            eng.run(iters)
+        eng.fetch(top, "theta", one_rec0, iters, out=h_theta.numpy(), sync=False)
+        eng.fetch(top, "prior", one_rec0, iters, out=h_prior.numpy(), sync=False)
+        eng.fetch(top, "like", one_rec0, iters, out=h_like.numpy(), sync=False)
+        eng.fetch(top, "accept", one_rec0, iters, out=h_acc.numpy(), sync=False)
+        if h_out is not None:
+            eng.fetch(top, "output", one_rec0, iters, out=h_out.numpy(), sync=False)
+        eng.sync()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    clock_info = clocks.stop()
+    times = torch.tensor([dev_ms, e2e_wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = [float(x) for x in times.cpu()]
+    if rank == 0:
+        pk, src = measured_peaks()
+        value = float(world) * C * iters * args.steps / (dev_ms * 1e-3)
+        per_gpu = C * iters / (np.mean(ms_steps) * 1e-3)
+        d2h = sum(t.numel() * t.element_size() for t in (h_theta, h_prior, h_like, h_acc) + ((h_out,) if h_out is not None else ()))
+        if cd["bound"] == "hbm":
+            roof = {"bound": "hbm", "achieved": per_gpu * cd["bytes_unit"] / 1e9, "peak": float(pk["hbm_gbs"]), "unit": "GB/s",
+                    "note": "%d B/transition (SURVEY 8d) x per-GPU transitions/s; peak = copy bandwidth, %s" % (cd["bytes_unit"], src)}
+        else:
+            peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            roof = {"bound": cd["bound"], "achieved": per_gpu * cd["flop_unit"] / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "note": "%.0f algorithmic flop/unit (SURVEY 8d) x per-GPU units/s; peak = fp32 FMA, computed 148 SM x 128 lanes x 2 x 1.965 GHz (not measured)" % cd["flop_unit"]}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["traffic"] = None
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if shared else "weak",
+            "vs_baseline": None, "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "chains_per_gpu": C, "finest_iterations_per_step": iters,
+                       "kernel": "%s (%s)" % (eng.kernel(), args.dtype), "l2": "256 MiB buffer written between timed steps"},
+            "e2e": {"value": float(world) * C * iters * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(theta0.nbytes) if not shared else 0, "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof,
+            "accept_rate_timed_region": accept_rate,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def eng_kernel_name(args, dtype):
     k = args.kernel if args.kernel != "auto" else ("auto -> tc16" if dtype == "float32" else "auto -> generic")
     return "%s (%s)" % (k, dtype)
@@ -388,11 +555,15 @@ def main():
     ap.add_argument("--iters", type=int, default=ITERS_PER_STEP)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 = the headline line (BASELINE.json configs[1]); the others are secondary measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.quick:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "cfg2":
+        run_other(args)
     else:
         run_ours(args)
 

@@ -163,6 +163,7 @@ typedef struct tda_config {
 #define TDA_G_NRECORDS 7        /* int64 [n_levels] records written so far          */
 #define TDA_G_MOMENTS 8         /* finest level running sums: [2][d][n_chains] (sum x, sum x^2) */
 #define TDA_G_TC16_TIMELINE 10  /* get only, diagnostic: int64 [4][256] clock64 stamps of CTA 0 of kernel 3 (first call arms the probe) */
+#define TDA_G_KERNEL 11         /* get only: int64 [1], the kernel tda_engine_run would launch now (ids of tda_select_kernel) */
 #define TDA_G_ZROUND 9          /* set only: one float64 flag; non-zero = Philox normals on the fp16 grid
                                  * ("z16" stream) also for the generic / 3xTF32 kernels (float32 engine) */
 
@@ -205,6 +206,9 @@ int tda_fill_streams(tda_engine *e, double *z, int64_t nz, double *u, int64_t nu
 int tda_history_reset(tda_engine *e);
 
 /* Kernel selection for tda_engine_run: 0 = automatic, 1 = generic lock-step kernel,
+ * 4 = register-resident single-level kernel (one thread per chain; d <= 8, RWMH / pCN / MALA,
+ * isotropic or diagonal likelihood, Rosenbrock or a linear model with m <= 256 and no model-output
+ * history; fails otherwise),
  * 2 = tcgen05 tensor-core Delayed-Acceptance kernel with 3xTF32 operands, 3 = tcgen05
  * Delayed-Acceptance kernel with two-term fp16-split operands and normals produced by dedicated
  * warps (2 and 3 fail if the configuration is not supported).  Kernel 3 consumes the "z16"

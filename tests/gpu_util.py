@@ -6,7 +6,7 @@ from tinyda_b200.engine import Engine, STORE_FULL
 from tinyda_b200.proposal import PROP_AM, svd_factor
 
 
-def run_engine(g, dtype="float64", iterations=None, store_F=True):
+def run_engine(g, dtype="float64", iterations=None, store_F=True, kernel=None):
     spec = g["spec"]
     C = g["theta0"].shape[0]
     iters = g["iterations"] if iterations is None else iterations
@@ -14,6 +14,8 @@ def run_engine(g, dtype="float64", iterations=None, store_F=True):
     store = STORE_FULL if store_F else (STORE_FULL & ~4)
     eng = Engine(spec, C, dtype=dtype, rng="injected", streams=(g["z"], g["u"]), store=store,
                  capacity_iterations=iters, archive0=g["archive0"], am_device_refactor=False)
+    if kernel is not None:
+        eng.select_kernel(kernel)
     eng.init(g["theta0"])
     if kind == PROP_AM:
         # parity mode for Adaptive Metropolis: the covariance factor is refreshed on the host

@@ -21,7 +21,7 @@ TDA_STORE_THETA, TDA_STORE_STATS, TDA_STORE_OUTPUT, TDA_STORE_ACCEPT = 1, 2, 4, 
  TDA_UP_STREAM_U, TDA_UP_DREAM_ARCHIVE0, TDA_UP_AM_FACTORS) = range(1, 16)
 TDA_F_THETA, TDA_F_PRIOR, TDA_F_LIKE, TDA_F_OUTPUT, TDA_F_ACCEPT = 1, 2, 3, 4, 5
 (TDA_G_SCALING, TDA_G_ACCEPT_COUNTS, TDA_G_CURSORS, TDA_G_AM_SIGMA, TDA_G_AM_MU, TDA_G_THETA,
- TDA_G_NRECORDS, TDA_G_MOMENTS, TDA_G_ZROUND, TDA_G_TC16_TIMELINE) = range(1, 11)
+ TDA_G_NRECORDS, TDA_G_MOMENTS, TDA_G_ZROUND, TDA_G_TC16_TIMELINE, TDA_G_KERNEL) = range(1, 12)
 TDA_BUF_DREAM_ARCHIVE, TDA_BUF_HIST_THETA = 1, 2
 
 EXPORTS = [

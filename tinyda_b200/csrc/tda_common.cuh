@@ -81,6 +81,7 @@ struct Params {
     long long lvl_steps[MAXL]; // steps done per level (bias.t - 1 for levels >= 1)
     // proposal
     R gamma, alpha_star, am_sd, am_eps, dream_b, dream_b_star;
+    R scaling0;                // proposal.scaling at construction (restored by init)
     int dream_M0, dream_delta, dream_nCR;
     long long dream_cap, dream_slots;
     R prior_logconst;

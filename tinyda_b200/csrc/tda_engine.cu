@@ -9,6 +9,7 @@
 #include "tda_kernels.cuh"
 #include "tda_da_tc.cuh"
 #include "tda_da_tc16.cuh"
+#include "tda_mh_reg.cuh"
 
 namespace {
 
@@ -100,7 +101,8 @@ struct EngineT : tda_engine {
     int Cs = 0, n_tiles = 0, kt = 0, sm_count = 148;
     size_t smem_bytes = 0;
     bool initialised = false;
-    int kernel_choice = 0;     // 0 auto, 1 generic, 2 tensor-core DA (3xTF32), 3 tensor-core DA (fp16 split)
+    int kernel_choice = 0;     // 0 auto, 1 generic, 2 tensor-core DA (3xTF32), 3 tensor-core DA (fp16 split),
+                               // 4 register-resident single-level MH
     int z_round_user = 0;      // generic / TF32 kernels: use the z16 normal stream (tda_set TDA_G_ZROUND)
     std::vector<int> ldA;
     double* stage_theta = nullptr;   // device staging for the initial states ([C][d] float64)
@@ -160,6 +162,7 @@ struct EngineT : tda_engine {
         P.dream_M0 = c.dream_M0; P.dream_delta = c.dream_delta; P.dream_nCR = c.dream_nCR;
         P.dream_cap = c.dream_capacity;
         P.prior_logconst = (R)c.prior_logconst;
+        P.scaling0 = (R)c.scaling;
         P.ldD = round_up(d, tda::NB);
         P.zlen = c.stream_z_len; P.ulen = c.stream_u_len;
 
@@ -408,6 +411,7 @@ struct EngineT : tda_engine {
 
     int init(cudaStream_t st) override {
         P.t_base = 0; P.wcount = 0;
+        if (P.prop_kind >= TDA_PROP_DREAMZ) dream_slots = cfg.dream_M0;
         for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = 0; P.lvl_steps[l] = 0; }
         int r = launch(tda::MODE_INIT, 0, st);
         if (r) return r;
@@ -418,11 +422,14 @@ struct EngineT : tda_engine {
 
     bool tc_eligible() const { return tc.eligible(cfg, P); }
     bool tc16_eligible() const { return !tc16_unfit && tc16.eligible(cfg, P); }
-    // which kernel tda_engine_run launches: 1 generic, 2 tensor-core 3xTF32, 3 tensor-core fp16 split
+    bool reg_eligible() const { return tda::mh_reg_eligible(cfg, P.lv[0].need_F != 0) && !z_round_user; }
+    // which kernel tda_engine_run launches: 1 generic, 2 tensor-core 3xTF32, 3 tensor-core fp16 split,
+    // 4 register-resident single-level
     int resolved_kernel() const {
-        if (kernel_choice == 1 || kernel_choice == 2 || kernel_choice == 3) return kernel_choice;
+        if (kernel_choice >= 1 && kernel_choice <= 4) return kernel_choice;
         if (tc16_eligible()) return 3;
         if (tc_eligible()) return 2;
+        if (reg_eligible()) return 4;
         return 1;
     }
     // the fp16-split kernel consumes the z16 normal stream; the others do on request
@@ -442,6 +449,7 @@ struct EngineT : tda_engine {
         }
         if (kernel_choice == 2 && !tc_eligible()) return fail(-1, "run: tensor-core DA kernel does not support this configuration");
         if (kernel_choice == 3 && !tc16.eligible(cfg, P)) return fail(-1, "run: fp16-split tensor-core DA kernel does not support this configuration");
+        if (kernel_choice == 4 && !reg_eligible()) return fail(-1, "run: register-resident kernel does not support this configuration");
         int which = resolved_kernel();
         if (which == 3 && !tc16.prepared) {
             // operand scaling happens on first use; a problem that does not fit fp16 falls back
@@ -472,6 +480,12 @@ struct EngineT : tda_engine {
         } else if (which == 2) {
             r = tc.run(P, cfg, iterations, sm_count, st);
             if (r) return fail(r, tc.err);
+            g_launches++;
+        } else if (which == 4) {
+            CUDA_TRY(cudaSetDevice(device));
+            P.mode = tda::MODE_RUN;
+            P.iterations = iterations;
+            CUDA_TRY(tda::mh_reg_launch<R>(P, st));
             g_launches++;
         } else if (P.prop_kind == TDA_PROP_DREAM && iterations > 1) {
             // shared archive: lock-step visibility (every chain sees all rows through the
@@ -587,6 +601,11 @@ struct EngineT : tda_engine {
         case TDA_G_NRECORDS: {
             if (bytes < (size_t)P.L * sizeof(long long)) return fail(-1, "get: destination too small");
             for (int l = 0; l < P.L; l++) reinterpret_cast<long long*>(dst)[l] = P.rec[l];
+            return 0;
+        }
+        case TDA_G_KERNEL: {
+            if (bytes < sizeof(long long)) return fail(-1, "get: destination too small");
+            reinterpret_cast<long long*>(dst)[0] = resolved_kernel();
             return 0;
         }
         case TDA_G_TC16_TIMELINE: {

@@ -986,6 +986,14 @@ struct Tile {
     // ---- initial links, AEM set-up --------------------------------------------------------------
     __device__ void init() {
         const int d = p.d, L = p.L;
+        // a fresh proposal object per sample() call (sampler.py:176 deep-copies it): step size,
+        // adaptation window and stream cursors start over
+        if (tid < TC) {
+            const int g = chain0 + tid;
+            p.scaling[g] = p.scaling0;
+            p.ucur[g] = 0;
+            if (p.adaptive) p.win_sum[g] = 0;
+        }
         for (int l = 0; l < L; l++) {
             const LevelP<R>& v = p.lv[l];
             for (int e = tid; e < d * TC; e += NT) {
