@@ -46,36 +46,45 @@ struct PairGen<double> {
     }
 };
 
-// per-thread view of the chain's two streams with the last Philox block / Box-Muller pair cached
-// (consecutive draws of a chain share blocks: 4 normals or 4 uniforms per block)
+// per-thread view of the chain's two streams.  The kernel consumes both strictly sequentially, so
+// the generator keeps a cursor per stream and decides from its low bits when a new Philox block
+// (4 normals or 4 uniforms) or Box-Muller pair is due; seek_*() primes the cached block when the
+// launch starts in the middle of one.
 template <typename R>
 struct ChainStreams {
     const Params<R>& p;
     long long chain;       // global chain id (Philox counter word)
     int local;             // chain index on this engine (injected streams)
     uint4 zb, ub;
-    long long zb_id, ub_id, pair_id;
+    unsigned long long zi, ui;     // next normal / uniform index
     R n0, n1;
-    __device__ ChainStreams(const Params<R>& p_, int local_) : p(p_), chain(p_.chain_offset + local_), local(local_),
-                                                              zb_id(-1), ub_id(-1), pair_id(-1) {}
-    __device__ __forceinline__ R normal(long long idx) {
-        if (p.rng_mode == TDA_RNG_INJECTED)
-            return (local < p.C && idx < p.zlen) ? p.zs[(size_t)local * p.zlen + idx] : (R)0;
-        const long long pid = idx >> 1;
-        if (pid != pair_id) {
-            const long long b = pid >> 1;
-            if (b != zb_id) { zb = philox_block(p.seed, chain, STREAM_Z, (unsigned long long)b); zb_id = b; }
-            PairGen<R>::pair(zb, (int)(pid & 1), n0, n1);
-            pair_id = pid;
-        }
-        return (idx & 1) ? n1 : n0;
+    __device__ ChainStreams(const Params<R>& p_, int local_) : p(p_), chain(p_.chain_offset + local_), local(local_) {}
+    __device__ __forceinline__ void seek_normal(long long idx) {
+        zi = (unsigned long long)idx;
+        if (p.rng_mode == TDA_RNG_INJECTED) return;
+        if (zi & 3) zb = philox_block(p.seed, chain, STREAM_Z, zi >> 2);
+        if (zi & 1) PairGen<R>::pair(zb, (int)((zi >> 1) & 1), n0, n1);
     }
-    __device__ __forceinline__ R uniform(long long idx) {
+    __device__ __forceinline__ void seek_uniform(long long idx) {
+        ui = (unsigned long long)idx;
+        if (p.rng_mode == TDA_RNG_INJECTED) return;
+        if (ui & 3) ub = philox_block(p.seed, chain, STREAM_U, ui >> 2);
+    }
+    __device__ __forceinline__ R normal() {
+        const unsigned long long idx = zi++;
         if (p.rng_mode == TDA_RNG_INJECTED)
-            return (local < p.C && idx < p.ulen) ? p.us[(size_t)local * p.ulen + idx] : (R)0.5;
-        const long long b = idx >> 2;
-        if (b != ub_id) { ub = philox_block(p.seed, chain, STREAM_U, (unsigned long long)b); ub_id = b; }
-        const int o = (int)(idx & 3);
+            return (local < p.C && (long long)idx < p.zlen) ? p.zs[(size_t)local * p.zlen + idx] : (R)0;
+        const unsigned o = (unsigned)idx & 3u;
+        if (o == 0) zb = philox_block(p.seed, chain, STREAM_Z, idx >> 2);
+        if ((o & 1u) == 0) PairGen<R>::pair(zb, (int)(o >> 1), n0, n1);
+        return (o & 1u) ? n1 : n0;
+    }
+    __device__ __forceinline__ R uniform() {
+        const unsigned long long idx = ui++;
+        if (p.rng_mode == TDA_RNG_INJECTED)
+            return (local < p.C && (long long)idx < p.ulen) ? p.us[(size_t)local * p.ulen + idx] : (R)0.5;
+        const unsigned o = (unsigned)idx & 3u;
+        if (o == 0) ub = philox_block(p.seed, chain, STREAM_U, idx >> 2);
         const uint32_t x = o == 0 ? ub.x : o == 1 ? ub.y : o == 2 ? ub.z : ub.w;
         return u01<R>(x);
     }
@@ -203,7 +212,7 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
     R prior = v.prior[g], like = v.like[g];
     R F0 = v.need_F ? v.F[g] : (R)0;             // Rosenbrock output (m = 1)
     R scal = p.scaling[g];
-    long long uc = p.ucur[g];
+    const long long uc0 = p.ucur[g];
     long long n_acc = v.n_acc[g];
     // accepts since the last period boundary: at a boundary the reference's window
     // accepted[-period:] (proposal.py:234) is exactly the period that just ended, so no ring read
@@ -211,6 +220,16 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
     int win_cnt = 0;
     int sid = v.sid[g];
     ChainStreams<R> rs(p, g);
+    rs.seek_normal(p.t_base * d);
+    rs.seek_uniform(uc0);
+    // history cursors: record r of field f lives at f + r * stride; advanced by one record per step
+    R* hp_theta = v.h_theta + ((size_t)p.rec[0] * d) * Cs + g;
+    R* hp_prior = v.h_prior + (size_t)p.rec[0] * Cs + g;
+    R* hp_like = v.h_like + (size_t)p.rec[0] * Cs + g;
+    R* hp_F = v.h_F + (size_t)p.rec[0] * Cs + g;
+    uint8_t* hp_acc = v.h_acc + (size_t)p.rec[0] * Cs + g;
+    uint8_t* wp = p.win + (size_t)(p.t_base % p.period) * Cs + g;
+    const size_t theta_stride = (size_t)d * Cs;
     // position in the adaptation period, kept incrementally (no 64-bit division per step)
     int wpos = (int)(p.t_base % p.period);
     long long kk = p.t_base / p.period;          // adaptations done so far
@@ -227,7 +246,7 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
         // ---- proposal --------------------------------------------------------------------------
         R z[D], tp[D];
 #pragma unroll
-        for (int k = 0; k < D; k++) z[k] = (k < d) ? rs.normal(t * d + k) : (R)0;
+        for (int k = 0; k < D; k++) z[k] = (k < d) ? rs.normal() : (R)0;
         if (mala) {
 #pragma unroll
             for (int k = 0; k < D; k++) tp[k] = th[k] + hs2 * grad[k] + scal * z[k];
@@ -263,8 +282,7 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
             x = x + qf * qxy - qf * qyx;
         }
         const R alpha = tisnan(pr + lk) ? (R)0 : texp(x);
-        const R u = rs.uniform(uc);
-        uc += 1;
+        const R u = rs.uniform();
         const int acc = (u < alpha) ? 1 : 0;
         if (acc) {
 #pragma unroll
@@ -274,7 +292,8 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
             n_acc += 1;
         }
         if (p.adaptive) {        // the `accepted` window of proposal.adapt (proposal.py:234)
-            p.win[(size_t)wpos * Cs + g] = (uint8_t)acc;
+            *wp = (uint8_t)acc;
+            wp += Cs;
             win_cnt += acc;
         }
         // ---- Link write-out (lane = chain: one 128-byte line per store instruction) ---------------
@@ -283,17 +302,19 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
             if (store & TDA_STORE_THETA) {
 #pragma unroll
                 for (int k = 0; k < D; k++)
-                    if (k < d) v.h_theta[((size_t)r * d + k) * Cs + g] = th[k];
+                    if (k < d) hp_theta[k * Cs] = th[k];
+                hp_theta += theta_stride;
             }
-            if (store_F) v.h_F[(size_t)r * Cs + g] = F0;
-            if (store & TDA_STORE_STATS) { v.h_prior[(size_t)r * Cs + g] = prior; v.h_like[(size_t)r * Cs + g] = like; }
-            if (store & TDA_STORE_ACCEPT) v.h_acc[(size_t)r * Cs + g] = (uint8_t)acc;
+            if (store_F) { *hp_F = F0; hp_F += Cs; }
+            if (store & TDA_STORE_STATS) { *hp_prior = prior; *hp_like = like; hp_prior += Cs; hp_like += Cs; }
+            if (store & TDA_STORE_ACCEPT) { *hp_acc = (uint8_t)acc; hp_acc += Cs; }
         }
 #pragma unroll
         for (int k = 0; k < D; k++) { s1[k] += th[k]; s2[k] += th[k] * th[k]; }
         // ---- adaptive global scaling -------------------------------------------------------------
         if (++wpos == p.period) {                // (t + 1) % period == 0
             wpos = 0;
+            wp = p.win + g;
             if (p.adaptive) {
                 const R rate = (R)win_cnt / (R)p.period;
                 scal = texp(tlog(scal) + tpow(p.gamma, (R)(-(double)kk)) * (rate - p.alpha_star));
@@ -317,7 +338,7 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
     v.prior[g] = prior; v.like[g] = like;
     if (v.need_F && MODEL == TDA_MODEL_ROSENBROCK) v.F[g] = F0;
     p.scaling[g] = scal;
-    p.ucur[g] = uc;
+    p.ucur[g] = (long long)rs.ui;
     v.n_acc[g] = n_acc;
     v.sid[g] = sid;
     if (p.adaptive) {
