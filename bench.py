@@ -288,6 +288,29 @@ def run_ours(args):
     d2h = h_theta.numel() * h_theta.element_size() + 2 * h_prior.numel() * h_prior.element_size() + h_acc.numel()
 
     kernel_used = args.kernel if args.kernel != "auto" else ("tc16" if dtype == "float32" else "generic")
+    ess = None
+    if rank == 0 and not args.no_ess:
+        # second half of BASELINE.json's metric: min over parameters of the bulk ESS per second.
+        # Sampling efficiency (ESS per transition) is measured on a side run of the same workload
+        # and kernel -- 256 chains, 300 burn-in + 1500 kept fine iterations, rank-normalised split
+        # bulk ESS (Vehtari et al. 2021, tinyda_b200.diagnostics.ess_bulk) -- and scaled by `value`.
+        from tinyda_b200.diagnostics import ess_bulk
+        Ce, burn, keep = 256, 300, 1500
+        th0 = w["prior"].rvs(Ce, random_state=np.random.default_rng(7)).astype(np.float64)
+        e2 = Engine(spec, Ce, dtype=dtype, rng="philox", seed=4048, store=[STORE_NONE, STORE_STATS],
+                    capacity_iterations=keep, device=local_rank, stream=stream)
+        if args.kernel != "auto":
+            e2.select_kernel(args.kernel)
+        e2.init(th0)
+        e2.run(burn)
+        e2.history_reset()
+        e2.run(keep)
+        th = np.transpose(e2.fetch(1, "theta", 0, keep), (2, 0, 1))          # [chains, draws, d]
+        e2.close()
+        per_param = np.array([ess_bulk(th[:, :, k]) for k in range(d)])
+        ess = {"min_ess_per_transition": float(per_param.min() / (Ce * keep)),
+               "median_ess_per_transition": float(np.median(per_param) / (Ce * keep)),
+               "sample": "%d chains x %d fine iterations after %d burn-in, bulk ESS per parameter" % (Ce, keep, burn)}
     if rank == 0:
         pk, src = measured_peaks()
         per_gpu_rate = C * iters / (np.mean(ms_steps) * 1e-3)
@@ -325,6 +348,10 @@ def run_ours(args):
                             "fine": float(acc[1].mean() / max(1, eng.iterations_done))},
             "wall_ms_timed_region": wall_ms,
         }
+        if ess is not None:
+            ess["min_ess_per_s"] = ess["min_ess_per_transition"] * value
+            out["min_ess_per_s"] = ess["min_ess_per_s"]
+            out["ess"] = ess
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline_block(spec, w["prior"], 1.0 if args.quick else 15.0,
                                                      0.5 if args.quick else 6.0)
@@ -554,6 +581,7 @@ def main():
     ap.add_argument("--chains", type=int, default=N_CHAINS_PER_GPU)
     ap.add_argument("--iters", type=int, default=ITERS_PER_STEP)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2 = the headline line (BASELINE.json configs[1]); the others are secondary measurements")

@@ -138,7 +138,8 @@ typedef struct tda_config {
 #define TDA_UP_MODEL_B 6        /* level: LINEAR offset [m]                         */
 #define TDA_UP_LIK_DATA 7       /* level: [m]                                       */
 #define TDA_UP_LIK_VAR 8        /* level: DIAG variances [m]                        */
-#define TDA_UP_LIK_PREC 9       /* level: DENSE / ADAPTIVE inverse covariance [m][m]*/
+#define TDA_UP_LIK_PREC 9       /* level: DENSE inverse covariance [m][m]; ADAPTIVE: Li = inv(chol(cov)),
+                                 * lower triangular [m][m] (Li^T Li = inv(cov))     */
 #define TDA_UP_LIK_COV 10       /* level: ADAPTIVE covariance [m][m]                */
 #define TDA_UP_INIT_THETA 11    /* [n_chains][d]                                    */
 #define TDA_UP_STREAM_Z 12      /* [n_chains][stream_z_len] standard normals        */

@@ -50,7 +50,7 @@ struct LevelP {
     R* sv_F[MAXL];
     // adaptive error model
     R* lik_bias;       // [m][Cs]     bias currently set on this level's likelihood
-    R* lik_prec;       // [m][m][Cs]  per-chain inverse of (cov + bias covariance)
+    R* lik_prec;       // [m][m][Cs]  per-chain Li = inv(chol(cov + bias covariance)), lower triangular
     R* bias_mu;        // [m][Cs]     moments of F_l - F_{l-1}  (levels >= 1)
     R* bias_sigma;     // [m][m][Cs]
     R* model_diff;     // [m][Cs]
@@ -69,6 +69,8 @@ struct Params {
     int mode, L, d, aem, rng_mode, prop_kind, adaptive, period, am_t0, am_device_refactor;
     int z_round;               // Philox normals on the fp16 grid ("z16" stream, float engine)
     int randomize;             // DA: randomize_subchain_length (chain.py:310-321)
+    int aem_G;                 // chains per group of the cooperative bias-covariance factorisation
+    int m_adapt;               // largest output count of a level with an adaptive likelihood (0 if none)
     int J[MAXL];
     int C, Cs, n_tiles;
     long long chain_offset, Cg, arch_off;   // arch_off: first archive column owned by this engine

@@ -256,7 +256,20 @@ struct EngineT : tda_engine {
         if (kt > tda::MAXD) return fail(-1, "contraction dimension exceeds TDA_MAX_D");
         if (n_max > 0) { P.n_max = n_max; DALLOC(P.scratch, (size_t)3 * n_max * Cs); }
         smem_bytes = ((size_t)2 * kt * tda::TC + (size_t)2 * kt * tda::NB + tda::CW * tda::TC + 4 * tda::TC) * sizeof(R) +
-                     tda::TC * sizeof(int);
+                     2 * tda::TC * sizeof(int);
+        for (int l = 0; l < L; l++)
+            if (c.level[l].lik_kind == TDA_LIK_ADAPTIVE && c.level[l].m > P.m_adapt) P.m_adapt = c.level[l].m;
+        smem_bytes += (size_t)P.m_adapt * tda::TC * sizeof(R);
+        if (c.aem) {
+            // workspace of the cooperative factorisation: (m*m + m) values per chain of a group; the
+            // largest power-of-two group that stays within 64 KB
+            const size_t m = (size_t)c.level[0].m;
+            int G = 16;
+            while (G > 1 && (m * m + m) * G * sizeof(R) > 64 * 1024) G /= 2;
+            if ((m * m + m) * G * sizeof(R) > 96 * 1024) return fail(-1, "adaptive error model supports up to 128 outputs (float) / 96 (double)");
+            P.aem_G = G;
+            smem_bytes += (m * m + m) * G * sizeof(R);
+        }
         CUDA_TRY(cudaFuncSetAttribute(tda::chain_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         // initial scaling
         {

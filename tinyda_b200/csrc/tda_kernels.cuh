@@ -173,6 +173,9 @@ struct Tile {
     const Params<R>& p;
     R *zt, *pt, *bs, *red, *s_prior, *s_like, *s_ca, *s_cb;
     int* s_acc;
+    int* s_inv;        // [TC] chains whose bias covariance must be re-factorised (push_bias)
+    R* aem_w;          // [m*m][aem_G] workspace of the cooperative Cholesky (adaptive error model)
+    R* s_r;            // [m][TC] residual tile of the adaptive likelihood
     int KB;            // rows of a staged operand chunk
     int chain0;        // first chain of this tile
     int tid;
@@ -191,6 +194,9 @@ struct Tile {
         s_ca = s_like + TC;
         s_cb = s_ca + TC;
         s_acc = reinterpret_cast<int*>(s_cb + TC);
+        s_inv = s_acc + TC;
+        s_r = reinterpret_cast<R*>(s_inv + TC);
+        aem_w = s_r + p_.m_adapt * TC;
     }
 
     __device__ __forceinline__ size_t gi(int k, int c) const { return (size_t)k * p.Cs + chain0 + c; }
@@ -265,16 +271,53 @@ struct Tile {
                 for (int j = 0; j < m; j++) t = fma(v.prec[i * m + j], Fsrc[gi(j, c)] - v.data[j], t);
                 q = fma(ri, t, q);
             }
-        } else {   // ADAPTIVE: r = F + bias - data, per-chain precision
+        } else {   // ADAPTIVE: r = F + bias - data; r^T inv(cov + cov_bias) r = |Li r|^2 with the
+                   // per-chain inverse Cholesky factor Li (lower triangular) kept in lik_prec
             for (int i = 0; i < m; i++) {
-                R ri = Fsrc[gi(i, c)] + v.lik_bias[gi(i, c)] - v.data[i];
                 R t = (R)0;
-                for (int j = 0; j < m; j++)
+                for (int j = 0; j <= i; j++)
                     t = fma(v.lik_prec[gi(i * m + j, c)], Fsrc[gi(j, c)] + v.lik_bias[gi(j, c)] - v.data[j], t);
-                q = fma(ri, t, q);
+                q = fma(t, t, q);
             }
         }
         return (R)-0.5 * q;
+    }
+
+    // AdaptiveGaussianLogLike for the whole tile, all NT threads: r = F + bias - data staged in
+    // shared memory, then |Li r|^2 with the per-chain triangular factor, the rows of Li dealt
+    // alternately to the two threads of a chain.  out[c] (shared) valid after the call.
+    __device__ void loglike_adaptive_tile(int l, const R* Fsrc, R* out) {
+        const LevelP<R>& v = p.lv[l];
+        const int m = v.m;
+        for (int e = tid; e < m * TC; e += NT) {
+            int j = e / TC, c = e - j * TC;
+            s_r[e] = Fsrc[gi(j, c)] + v.lik_bias[gi(j, c)] - v.data[j];
+        }
+        __syncthreads();
+        const int c = tid & (TC - 1), h = tid / TC;
+        const R* __restrict__ Li = v.lik_prec + chain0 + c;
+        const size_t Cs = (size_t)p.Cs;
+        R q = (R)0;
+        for (int i = h; i < m; i += NT / TC) {
+            const R* row = Li + (size_t)i * m * Cs;
+            R t0 = (R)0, t1 = (R)0;
+            int j = 0;
+            for (; j + 1 <= i; j += 2) {
+                t0 = fma(row[(size_t)j * Cs], s_r[j * TC + c], t0);
+                t1 = fma(row[(size_t)(j + 1) * Cs], s_r[(j + 1) * TC + c], t1);
+            }
+            if (j <= i) t0 = fma(row[(size_t)j * Cs], s_r[j * TC + c], t0);
+            const R t = t0 + t1;
+            q = fma(t, t, q);
+        }
+        red[h * TC + c] = q;
+        __syncthreads();
+        if (tid < TC) {
+            R tot = (R)0;
+            for (int k = 0; k < NT / TC; k++) tot += red[k * TC + tid];
+            out[tid] = (R)-0.5 * tot;
+        }
+        __syncthreads();
     }
 
     // ---- create_link: log-prior + forward model + log-likelihood for the tile in pt ----------
@@ -300,7 +343,8 @@ struct Tile {
             }
             if (v.lik_kind >= TDA_LIK_DENSE) {
                 __syncthreads();     // Fp visible to the owning thread (block-scope global writes)
-                if (tid < TC) s_like[tid] = loglike_from_F(l, v.Fp, tid);
+                if (v.lik_kind == TDA_LIK_ADAPTIVE) loglike_adaptive_tile(l, v.Fp, s_like);
+                else if (tid < TC) s_like[tid] = loglike_from_F(l, v.Fp, tid);
             }
         } else if (v.model_kind == TDA_MODEL_ROSENBROCK) {
             if (tid < TC) {
@@ -308,8 +352,9 @@ struct Tile {
                 R a = v.sc0 - x, b = y - x * x;
                 R F = a * a + v.sc1 * b * b;
                 v.Fp[gi(0, tid)] = F;
-                s_like[tid] = loglike_from_F(l, v.Fp, tid);
+                if (v.lik_kind != TDA_LIK_ADAPTIVE) s_like[tid] = loglike_from_F(l, v.Fp, tid);
             }
+            if (v.lik_kind == TDA_LIK_ADAPTIVE) { __syncthreads(); loglike_adaptive_tile(l, v.Fp, s_like); }
         } else {   // POISSON1D
             const int n = v.n_grid;
             R* kf = p.scratch;
@@ -344,8 +389,9 @@ struct Tile {
                     u = dp[gi(i, c)] - cp[gi(i, c)] * u;
                     if ((i + 1) % stride == 0) { int s = (i + 1) / stride - 1; if (s < v.m) v.Fp[gi(s, c)] = u; }
                 }
-                s_like[tid] = loglike_from_F(l, v.Fp, tid);
+                if (v.lik_kind != TDA_LIK_ADAPTIVE) s_like[tid] = loglike_from_F(l, v.Fp, tid);
             }
+            if (v.lik_kind == TDA_LIK_ADAPTIVE) { __syncthreads(); loglike_adaptive_tile(l, v.Fp, s_like); }
         }
         __syncthreads();
     }
@@ -354,73 +400,82 @@ struct Tile {
     // level l (>=1) pushes bias moments into level l-1's likelihood and re-scores level l-1's
     // current link.  Thread per chain.
     __device__ void push_bias(int l) {
-        if (tid < TC) {
-            const int c = tid, L = p.L;
-            const LevelP<R>& lo = p.lv[l - 1];
-            const int m = lo.m;
-            const int kend = (l == L - 1) ? l : L - 1;
-            bool all_small = true;
-            for (int i = 0; i < m; i++) {
-                R mu = (R)0;
-                if (p.aem == 2) mu = p.lv[l].model_diff[gi(i, c)];     // chain.py:296-300, :519-522
-                else for (int k = l; k <= kend; k++) mu += p.lv[k].bias_mu[gi(i, c)];
-                lo.lik_bias[gi(i, c)] = mu;
+        const int L = p.L;
+        const LevelP<R>& lo = p.lv[l - 1];
+        const int m = lo.m;
+        const int kend = (l == L - 1) ? l : L - 1;
+        // (1) bias mean; does any entry of the summed bias covariance reach 1e-9 (distributions.py:399)?
+        for (int e = tid; e < m * TC; e += NT) {
+            int i = e / TC, c = e - i * TC;
+            R mu = (R)0;
+            if (p.aem == 2) mu = p.lv[l].model_diff[gi(i, c)];     // chain.py:296-300, :519-522
+            else for (int k = l; k <= kend; k++) mu += p.lv[k].bias_mu[gi(i, c)];
+            lo.lik_bias[gi(i, c)] = mu;
+        }
+        if (tid < TC) s_inv[tid] = 0;
+        __syncthreads();
+        {   // every entry independent: both threads of a chain scan half of the m*m entries
+            const int c = tid & (TC - 1), h = tid / TC;
+            int big = 0;
+            for (int e = h; e < m * m; e += NT / TC) {
+                R sg = (R)0;
+                for (int k = l; k <= kend; k++) sg += p.lv[k].bias_sigma[gi(e, c)];
+                if (!(sg < (R)1e-9)) big = 1;
             }
-            // covariance sum; written into lik_prec as workspace only if it will be inverted
-            for (int e = 0; e < m * m && all_small; e++) {
-                R s = (R)0;
-                for (int k = l; k <= kend; k++) s += p.lv[k].bias_sigma[gi(e, c)];
-                if (!(s < (R)1e-9)) all_small = false;
-            }
-            if (!all_small) {
-                R* W = lo.lik_prec;
-                for (int i = 0; i < m; i++)
+            if (big) s_inv[c] = 1;
+        }
+        __syncthreads();
+        // (2) W = cov + cov_bias = Lc Lc^T, Li = inv(Lc) -> lik_prec.  G chains at a time in shared
+        // memory, NT/G threads per chain: the trailing rows of a Cholesky column and the columns of
+        // the triangular inverse are dealt round-robin to a chain's threads.
+        const int G = p.aem_G, NW = NT / G;
+        const int cg = tid % G, wk = tid / G;
+        R* Wm = aem_w;                 // [m*m][G]
+        R* dg = aem_w + m * m * G;     // [m][G] diagonal of Lc
+        for (int g0 = 0; g0 < TC; g0 += G) {
+            const int c = g0 + cg;
+            const bool on = s_inv[c] != 0;
+            if (on)
+                for (int i = wk; i < m; i += NW)
                     for (int j = 0; j <= i; j++) {
-                        R s = (R)0;
-                        for (int k = l; k <= kend; k++) s += p.lv[k].bias_sigma[gi(i * m + j, c)];
-                        W[gi(i * m + j, c)] = lo.cov[i * m + j] + s;
+                        R sg = (R)0;
+                        for (int k = l; k <= kend; k++) sg += p.lv[k].bias_sigma[gi(i * m + j, c)];
+                        Wm[(i * m + j) * G + cg] = lo.cov[i * m + j] + sg;
                     }
-                // Cholesky W = Lc Lc^T (lower, in place)
-                for (int j = 0; j < m; j++) {
-                    R djj = W[gi(j * m + j, c)];
-                    for (int k = 0; k < j; k++) { R t = W[gi(j * m + k, c)]; djj -= t * t; }
+            __syncthreads();
+            for (int j = 0; j < m; j++) {
+                if (on) {
+                    R djj = Wm[(j * m + j) * G + cg];
+                    for (int k = 0; k < j; k++) { R t = Wm[(j * m + k) * G + cg]; djj -= t * t; }
                     djj = tsqrt(djj);
-                    W[gi(j * m + j, c)] = djj;
-                    R inv = (R)1 / djj;
-                    for (int i = j + 1; i < m; i++) {
-                        R s = W[gi(i * m + j, c)];
-                        for (int k = 0; k < j; k++) s -= W[gi(i * m + k, c)] * W[gi(j * m + k, c)];
-                        W[gi(i * m + j, c)] = s * inv;
+                    const R inv = (R)1 / djj;
+                    if (wk == 0) dg[j * G + cg] = djj;
+                    for (int i = j + 1 + wk; i < m; i += NW) {
+                        R sv = Wm[(i * m + j) * G + cg];
+                        for (int k = 0; k < j; k++) sv -= Wm[(i * m + k) * G + cg] * Wm[(j * m + k) * G + cg];
+                        Wm[(i * m + j) * G + cg] = sv * inv;
                     }
                 }
-                // invert Lc in place (lower triangular)
-                for (int j = 0; j < m; j++) {
-                    R inv = (R)1 / W[gi(j * m + j, c)];
-                    W[gi(j * m + j, c)] = inv;
+                __syncthreads();
+            }
+            if (on) {
+                R* Li = lo.lik_prec;
+                for (int j = wk; j < m; j += NW) {     // column j of inv(Lc); a thread re-reads only its own writes
+                    Li[gi(j * m + j, c)] = (R)1 / dg[j * G + cg];
                     for (int i = j + 1; i < m; i++) {
-                        R s = (R)0;
-                        for (int k = j; k < i; k++) s -= W[gi(i * m + k, c)] * W[gi(k * m + j, c)];
-                        W[gi(i * m + j, c)] = s / W[gi(i * m + i, c)];
+                        R sv = (R)0;
+                        for (int k = j; k < i; k++) sv -= Wm[(i * m + k) * G + cg] * Li[gi(k * m + j, c)];
+                        Li[gi(i * m + j, c)] = sv / dg[i * G + cg];
                     }
-                }
-                // P = Li^T Li : P[i][j] = sum_{k>=max(i,j)} Li[k][i] Li[k][j]; upper part first
-                // (uses only the strictly-lower + diagonal entries, writes the strict upper)
-                for (int i = 0; i < m; i++)
-                    for (int j = i + 1; j < m; j++) {
-                        R s = (R)0;
-                        for (int k = j; k < m; k++) s = fma(W[gi(k * m + i, c)], W[gi(k * m + j, c)], s);
-                        W[gi(i * m + j, c)] = s;
-                    }
-                // diagonal, then mirror the upper part into the lower
-                for (int i = 0; i < m; i++) {
-                    R s = (R)0;
-                    for (int k = i; k < m; k++) { R t = (k == i) ? W[gi(i * m + i, c)] : W[gi(k * m + i, c)]; s = fma(t, t, s); }
-                    W[gi(i * m + i, c)] = s;
-                    for (int k = i + 1; k < m; k++) W[gi(k * m + i, c)] = W[gi(i * m + k, c)];
                 }
             }
-            // re-score level l-1's current link (posterior.py:112-134)
-            R nl = loglike_from_F(l - 1, lo.F, c);
+            __syncthreads();
+        }
+        // (3) re-score level l-1's current link (posterior.py:112-134)
+        loglike_adaptive_tile(l - 1, lo.F, s_like);
+        if (tid < TC) {
+            const int c = tid;
+            R nl = s_like[c];
             lo.like[chain0 + c] = nl;
             const int sid = lo.sid[chain0 + c];
             for (int a = l; a < L; a++)
@@ -430,31 +485,33 @@ struct Tile {
     }
 
     __device__ void aem_update(int l, long long tcount) {
-        // bias.update(model_diff)  (utils.py:113-124), t = tcount (starts at 1)
-        if (tid < TC) {
-            const int c = tid;
-            const LevelP<R>& v = p.lv[l];
-            const int m = v.m;
-            if (s_acc[c]) {
-                for (int j = 0; j < m; j++)
-                    v.model_diff[gi(j, c)] = v.F[gi(j, c)] - p.lv[l - 1].F[gi(j, c)];
+        // bias.update(model_diff)  (utils.py:113-124), t = tcount (starts at 1); element-parallel
+        const LevelP<R>& v = p.lv[l];
+        const int m = v.m;
+        for (int e = tid; e < m * TC; e += NT) {
+            int j = e / TC, c = e - j * TC;
+            if (s_acc[c]) v.model_diff[gi(j, c)] = v.F[gi(j, c)] - p.lv[l - 1].F[gi(j, c)];
+        }
+        __syncthreads();
+        const R t = (R)tcount;
+        const R f1 = (t - (R)1) / t, f2 = (R)1 / t, g1 = (R)1 / (t + (R)1);
+        {
+            const R* __restrict__ md = v.model_diff;
+            const R* __restrict__ bm = v.bias_mu;
+            R* __restrict__ sg = v.bias_sigma;
+            for (int e = tid; e < m * m * TC; e += NT) {
+                int c = e & (TC - 1), ij = e / TC, i = ij / m, j = ij - i * m;
+                R xi = md[gi(i, c)], xj = md[gi(j, c)];
+                R mpi = bm[gi(i, c)], mpj = bm[gi(j, c)];
+                R mni = g1 * (t * mpi + xi), mnj = g1 * (t * mpj + xj);
+                size_t o = gi(ij, c);
+                sg[o] = f1 * sg[o] + f2 * (t * mpi * mpj - (t + (R)1) * mni * mnj + xi * xj);
             }
-            const R t = (R)tcount;
-            const R f1 = (t - (R)1) / t, f2 = (R)1 / t, g1 = (R)1 / (t + (R)1);
-            for (int i = 0; i < m; i++) {
-                R xi = v.model_diff[gi(i, c)];
-                R mpi = v.bias_mu[gi(i, c)];
-                R mni = g1 * (t * mpi + xi);
-                for (int j = 0; j < m; j++) {
-                    R xj = v.model_diff[gi(j, c)];
-                    R mpj = v.bias_mu[gi(j, c)];
-                    R mnj = g1 * (t * mpj + xj);
-                    size_t e = gi(i * m + j, c);
-                    v.bias_sigma[e] = f1 * v.bias_sigma[e] + f2 * (t * mpi * mpj - (t + (R)1) * mni * mnj + xi * xj);
-                }
-            }
-            for (int i = 0; i < m; i++)
-                v.bias_mu[gi(i, c)] = g1 * (t * v.bias_mu[gi(i, c)] + v.model_diff[gi(i, c)]);
+        }
+        __syncthreads();
+        for (int e = tid; e < m * TC; e += NT) {
+            int i = e / TC, c = e - i * TC;
+            v.bias_mu[gi(i, c)] = g1 * (t * v.bias_mu[gi(i, c)] + v.model_diff[gi(i, c)]);
         }
         __syncthreads();
     }
@@ -921,12 +978,11 @@ struct Tile {
                     const int m = lo.m;
                     R q = (R)0;
                     for (int i = 0; i < m; i++) {
-                        R ri = lo.sv_F[l][gi(i, c)] + (v.Fp[gi(i, c)] - b_F[gi(i, c)]) - lo.data[i];
                         R t = (R)0;
-                        for (int j = 0; j < m; j++)
+                        for (int j = 0; j <= i; j++)
                             t = fma(lo.lik_prec[gi(i * m + j, c)],
                                     lo.sv_F[l][gi(j, c)] + (v.Fp[gi(j, c)] - b_F[gi(j, c)]) - lo.data[j], t);
-                        q = fma(ri, t, q);
+                        q = fma(t, t, q);
                     }
                     const R post_biased = lo.sv_prior[l][g] + (R)-0.5 * q;
                     const R qxy = s_ca[c], qyx = s_cb[c];
@@ -1000,7 +1056,7 @@ struct Tile {
                 int k = e / TC, c = e - k * TC;
                 pt[e] = v.theta[gi(k, c)];
             }
-            if (v.lik_kind == TDA_LIK_ADAPTIVE)    // per-chain precision starts as inv(cov)
+            if (v.lik_kind == TDA_LIK_ADAPTIVE)    // per-chain factor starts as inv(chol(cov)) (uploaded)
                 for (int e = tid; e < v.m * v.m * TC; e += NT) {
                     int c = e % TC, ij = e / TC;
                     v.lik_prec[gi(ij, c)] = v.prec[ij];

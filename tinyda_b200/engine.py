@@ -130,8 +130,12 @@ class Engine:
             self._up(L.TDA_UP_LIK_DATA, l, lv["lik"]["data"])
             if lk == LIK_DIAG:
                 self._up(L.TDA_UP_LIK_VAR, l, lv["lik"]["var"])
-            if lk in (LIK_DENSE, LIK_ADAPTIVE):
+            if lk == LIK_DENSE:
                 self._up(L.TDA_UP_LIK_PREC, l, np.linalg.inv(lv["lik"]["cov"]))   # distributions.py:280
+            if lk == LIK_ADAPTIVE:
+                # r^T inv(cov) r = |Li r|^2 with Li = inv(chol(cov)); the device re-factorises
+                # cov + cov_bias per chain whenever set_bias would re-invert (distributions.py:399-402)
+                self._up(L.TDA_UP_LIK_PREC, l, np.linalg.inv(np.linalg.cholesky(lv["lik"]["cov"])))
             if lk == LIK_ADAPTIVE:
                 self._up(L.TDA_UP_LIK_COV, l, lv["lik"]["cov"])
         if rng == "injected":
