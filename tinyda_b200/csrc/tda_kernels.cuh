@@ -414,35 +414,30 @@ struct Tile {
         }
         if (tid < TC) s_inv[tid] = 0;
         __syncthreads();
-        {   // every entry independent: both threads of a chain scan half of the m*m entries
-            const int c = tid & (TC - 1), h = tid / TC;
-            int big = 0;
-            for (int e = h; e < m * m; e += NT / TC) {
-                R sg = (R)0;
-                for (int k = l; k <= kend; k++) sg += p.lv[k].bias_sigma[gi(e, c)];
-                if (!(sg < (R)1e-9)) big = 1;
-            }
-            if (big) s_inv[c] = 1;
-        }
-        __syncthreads();
         // (2) W = cov + cov_bias = Lc Lc^T, Li = inv(Lc) -> lik_prec.  G chains at a time in shared
-        // memory, NT/G threads per chain: the trailing rows of a Cholesky column and the columns of
-        // the triangular inverse are dealt round-robin to a chain's threads.
+        // memory, NT/G threads per chain: the rows of W, the trailing rows of a Cholesky column and
+        // the columns of the triangular inverse are dealt round-robin to a chain's threads.  The
+        // "is any entry of cov_bias >= 1e-9" test of set_bias (distributions.py:399) rides on the
+        // assembly of W (the matrices are symmetric: the lower triangle decides).
         const int G = p.aem_G, NW = NT / G;
         const int cg = tid % G, wk = tid / G;
         R* Wm = aem_w;                 // [m*m][G]
         R* dg = aem_w + m * m * G;     // [m][G] diagonal of Lc
         for (int g0 = 0; g0 < TC; g0 += G) {
             const int c = g0 + cg;
-            const bool on = s_inv[c] != 0;
-            if (on)
+            {
+                int big = 0;
                 for (int i = wk; i < m; i += NW)
                     for (int j = 0; j <= i; j++) {
                         R sg = (R)0;
                         for (int k = l; k <= kend; k++) sg += p.lv[k].bias_sigma[gi(i * m + j, c)];
+                        if (!(sg < (R)1e-9)) big = 1;
                         Wm[(i * m + j) * G + cg] = lo.cov[i * m + j] + sg;
                     }
+                if (big) s_inv[c] = 1;
+            }
             __syncthreads();
+            const bool on = s_inv[c] != 0;
             for (int j = 0; j < m; j++) {
                 if (on) {
                     R djj = Wm[(j * m + j) * G + cg];
