@@ -335,7 +335,10 @@ def run_ours(args):
             "clocks": clock_info,
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one da_tc16_kernel launch of this very
+                # command (ncu --set full, profiles/r01_ncu_tc16_summary.txt): 0.164 + 1.148 GB against
+                # 0.868 GB of algorithmic history bytes (265 B x 3,276,800 transitions)
+                "traffic": 1.312e9 if (kernel_used == "tc16" and C == N_CHAINS_PER_GPU and iters == ITERS_PER_STEP) else None,
                 "executed_tflops": per_gpu_rate * F_EXEC_TC16 / 1e12 if kernel_used == "tc16" else None,
                 "executed_frac": per_gpu_rate * F_EXEC_TC16 / 1e12 / peak if kernel_used == "tc16" else None,
                 "note": "achieved = 458752 algorithmic flop/transition x per-GPU transitions/s "
@@ -378,7 +381,7 @@ def _other_workload(name, world):
         J = spec["J"]
         evals = [J[0] * J[1] * J[2], J[1] * J[2], J[2], 1]
         flop = sum(e * (2 * d + 9) * n for e, n in zip(evals, ns))
-        cfgd = dict(chains=16384, iters=4, bytes_unit=(d + 2) * s + 1, flop_unit=float(flop), bound="fp32", store="stats")
+        cfgd = dict(chains=32768, iters=4, bytes_unit=(d + 2) * s + 1, flop_unit=float(flop), bound="fp32", store="stats")
     elif name == "cfg5":
         m = spec["levels"][0]["model"]["m"]
         cfgd = dict(chains=8192 // world, iters=50, bytes_unit=(d + 2) * s + 1 + 3 * d * s, flop_unit=2.0 * d * m,
