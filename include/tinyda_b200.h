@@ -62,6 +62,7 @@ extern "C" {
 #define TDA_PROP_MALA 3     /* MALA                proposal.py:861  */
 #define TDA_PROP_DREAMZ 4   /* DREAMZ              proposal.py:608  */
 #define TDA_PROP_DREAM 5    /* DREAM (shared)      proposal.py:1627 */
+#define TDA_PROP_OWPCN 6    /* OperatorWeightedCrankNicolson proposal.py:515 (non-adaptive) */
 /* likelihood kinds */
 #define TDA_LIK_ISO 0       /* IsotropicGaussianLogLike distributions.py:318 */
 #define TDA_LIK_DIAG 1      /* DiagonalGaussianLogLike  distributions.py:304 */
@@ -146,6 +147,8 @@ typedef struct tda_config {
 #define TDA_UP_STREAM_U 13      /* [n_chains][stream_u_len] U(0,1)                  */
 #define TDA_UP_DREAM_ARCHIVE0 14 /* [n_chains_global][M0][d]                        */
 #define TDA_UP_AM_FACTORS 15    /* [n_chains][d][d] per-chain T                     */
+#define TDA_UP_PROP_S 16        /* OWPCN: [d][d] state operator, transposed: theta' = theta @ S + z @ T,
+                                 * S = sqrtm(I - scaling*B)^T, T = svd_factor(prior cov) @ sqrtm(scaling*B)^T */
 
 /* tda_fetch 'field' */
 #define TDA_F_THETA 1           /* [nrec][d][n_chains]   engine dtype               */
@@ -208,8 +211,7 @@ int tda_history_reset(tda_engine *e);
 
 /* Kernel selection for tda_engine_run: 0 = automatic, 1 = generic lock-step kernel,
  * 4 = register-resident single-level kernel (one thread per chain; d <= 8, RWMH / pCN / MALA,
- * isotropic or diagonal likelihood, Rosenbrock or a linear model with m <= 256 and no model-output
- * history; fails otherwise),
+ * isotropic or diagonal likelihood, Rosenbrock or a linear model with m <= 256; fails otherwise),
  * 2 = tcgen05 tensor-core Delayed-Acceptance kernel with 3xTF32 operands, 3 = tcgen05
  * Delayed-Acceptance kernel with two-term fp16-split operands and normals produced by dedicated
  * warps (2 and 3 fail if the configuration is not supported).  Kernel 3 consumes the "z16"

@@ -27,12 +27,13 @@ Reference map (file:line are into /root/reference/tinyDA/):
                                        proposal.py:364-369 (CrankNicolson.get_q)
   randomize_subchain_length            chain.py:310-321, :369-375, :525-527
   proposals            proposal.py:132-258 (RWMH), 261-369 (pCN), 372-512 (AM),
-                       608-852 (DREAMZ), 861-1005 (MALA), 1627-1656 + ray.py:366-384 (DREAM)
+                       515-605 (operator-weighted pCN), 608-852 (DREAMZ), 861-1005 (MALA),
+                       1627-1656 + ray.py:366-384 (DREAM)
 """
 import numpy as np
 
 # ---- kinds (kept numerically identical to include/tinyda_b200.h) -------------------------
-PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM = 0, 1, 2, 3, 4, 5
+PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM, PROP_OWPCN = 0, 1, 2, 3, 4, 5, 6
 LIK_ISO, LIK_DIAG, LIK_DENSE, LIK_ADAPTIVE = 0, 1, 2, 3
 MODEL_LINEAR, MODEL_ROSENBROCK, MODEL_POISSON1D = 0, 1, 2
 
@@ -280,6 +281,10 @@ class ChainOracle:
         self.t = 0
         if self.kind in (PROP_RWMH, PROP_PCN, PROP_AM):
             self.T = np.array(self.P["T"], dtype=np.float64)
+        if self.kind == PROP_OWPCN:                              # proposal.py:575-579
+            self.state_operator = np.array(self.P["state_operator"], dtype=np.float64)
+            self.noise_operator = np.array(self.P["noise_operator"], dtype=np.float64)
+            self.T = np.array(self.P["T_prior"], dtype=np.float64)
         if self.kind == PROP_AM:
             self.am = Moments(theta0, self.d, sd=float(self.P["am_sd"]), epsilon=float(self.P["am_eps"]))
             self.am_t0 = int(self.P["am_t0"])
@@ -291,6 +296,8 @@ class ChainOracle:
             self.b_star = float(self.P["b_star"])
             self.nCR = int(self.P["nCR"])
             self.pCR = np.array(self.nCR * [1 / self.nCR])
+            self.LCR = np.zeros(self.nCR)                        # proposal.py:752-754
+            self.DeltaCR = np.ones(self.nCR)
             self.shared_view = None                              # set by DreamEnsemble
         if self.kind == PROP_MALA:
             self.prior_cov_inv = np.linalg.inv(self.prior["cov"])    # utils.py:275
@@ -370,6 +377,8 @@ class ChainOracle:
         if self.kind == PROP_PCN:                                # proposal.py:349-355
             T = svd_factor(self.prior["cov"]) if self.svd_per_proposal else self.T
             return np.sqrt(1 - self.scaling ** 2) * c.theta + self.scaling * (self.S.normals(d) @ T)
+        if self.kind == PROP_OWPCN:                              # proposal.py:593-598
+            return np.dot(self.state_operator, c.theta) + np.dot(self.noise_operator, self.S.normals(d) @ self.T)
         if self.kind == PROP_MALA:                               # proposal.py:948-959
             return c.theta + 0.5 * self.scaling ** 2 * c.grad + self.scaling * self.S.normals(d)
         # DREAMZ / DREAM                                         # proposal.py:811-852
@@ -407,7 +416,7 @@ class ChainOracle:
         if np.isnan(new.post):                                   # proposal.py:254, 358, 963
             return 0.0
         with np.errstate(over="ignore"):
-            if self.kind == PROP_PCN:
+            if self.kind in (PROP_PCN, PROP_OWPCN):
                 return np.exp(new.like - old.like)               # proposal.py:362
             if self.kind == PROP_MALA:
                 new.grad = self._gradient(new)                   # proposal.py:968-969
@@ -432,6 +441,13 @@ class ChainOracle:
                 self.n_refactor += 1
         if self.kind in (PROP_DREAMZ, PROP_DREAM):               # proposal.py:790-795
             self.Z = np.vstack((self.Z, theta_cur))
+            if self.adaptive and self.t % self.period == 0:      # proposal.py:797-809
+                jump = theta_cur - theta_prev
+                self.DeltaCR[self.mCR] = self.DeltaCR[self.mCR] + (jump ** 2 / np.var(self.Z, axis=0)).sum()
+                self.LCR[self.mCR] = self.LCR[self.mCR] + 1
+                if np.all(self.LCR > 0):
+                    mean = self.DeltaCR / self.LCR
+                    self.pCR = mean / mean.sum()
 
     # -- steps -----------------------------------------------------------------------------
     def base_step(self):

@@ -100,6 +100,38 @@ def mh_pcn_diag():
 
 
 @case
+def mh_owpcn():
+    """Operator-weighted pCN (proposal.py:515-605): state and noise operators from sqrtm."""
+    rng = np.random.default_rng(33)
+    d, m = 6, 14
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d, 0.3))
+    (G, y), = _linear_levels(rng, d, [m], 0.2, prior)
+    Q = rng.standard_normal((d, d))
+    B = 0.5 * (np.eye(d) + 0.2 * (Q @ Q.T) / d)           # SPD with scaling*B < I
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.04 * np.eye(m)), LinearModel(G))
+        return [post], tda.OperatorWeightedCrankNicolson(B, scaling=0.08), {}
+    return dict(build=build, n_chains=3, iterations=130, seed=34, prior=prior)
+
+
+@case
+def da_owpcn():
+    """Two-level DA with the operator-weighted pCN as the coarse proposal."""
+    rng = np.random.default_rng(35)
+    d = 6
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d, 0.3))
+    (Gc, yc), (Gf, yf) = _linear_levels(rng, d, [6, 24], 0.15, prior)
+    B = np.diag(np.linspace(0.5, 1.5, d))
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.GaussianLogLike(yc, 0.0225 * np.eye(6)), LinearModel(Gc))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(yf, 0.0225 * np.eye(24)), LinearModel(Gf))
+        return [pc, pf], tda.OperatorWeightedCrankNicolson(B, scaling=0.05), dict(subchain_length=3)
+    return dict(build=build, n_chains=3, iterations=60, seed=36, prior=prior)
+
+
+@case
 def da_pcn_small():
     """cfg2 in miniature: two-level DA, pCN, coarse = strided observation subset, J=3."""
     rng = np.random.default_rng(2)
@@ -343,6 +375,21 @@ def dreamz_linear():
         post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.09 * np.eye(m)), LinearModel(G))
         return [post], tda.DREAMZ(M0=8, delta=2, nCR=3), {}
     return dict(build=build, n_chains=3, iterations=90, seed=18, prior=prior, archive=True)
+
+
+@case
+def dreamz_adaptive():
+    """DREAM(Z) with adaptive=True: global scaling AND the crossover distribution pCR adapt
+    (proposal.py:790-809: DeltaCR / LCR updated with the jump normalised by the archive variance)."""
+    rng = np.random.default_rng(23)
+    d, m = 5, 10
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    (G, y), = _linear_levels(rng, d, [m], 0.3, prior)
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.09 * np.eye(m)), LinearModel(G))
+        return [post], tda.DREAMZ(M0=8, delta=1, nCR=3, adaptive=True, period=8), {}
+    return dict(build=build, n_chains=3, iterations=200, seed=24, prior=prior, archive=True)
 
 
 @case

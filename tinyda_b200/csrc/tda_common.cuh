@@ -17,6 +17,11 @@ constexpr int NB = CW * RN;  // columns per staged chunk of the shared operand (
 constexpr int MAXL = TDA_MAX_LEVELS;
 constexpr int MAXD = TDA_MAX_D;
 constexpr int MAX_DELTA = 8;
+constexpr int MAX_NCR = 8;
+
+__host__ __device__ __forceinline__ bool is_dream(int kind) { return kind == TDA_PROP_DREAMZ || kind == TDA_PROP_DREAM; }
+// proposals whose acceptance is the likelihood ratio (proposal.py:357-362, inherited by :515)
+__host__ __device__ __forceinline__ bool is_pcn_like(int kind) { return kind == TDA_PROP_PCN || kind == TDA_PROP_OWPCN; }
 
 constexpr int MODE_INIT = 0;
 constexpr int MODE_RUN = 1;
@@ -91,6 +96,7 @@ struct Params {
     const R* LP;           // [d][ldD]
     const R* Pprec;        // [d][ldD]
     const R* T;            // [d][ldD]  shared proposal factor
+    const R* Sop;          // [d][ldD]  OWPCN state operator (transposed)
     int ldD;
     R* scaling;            // [Cs]
     uint8_t* win;          // [period][Cs] ring of the last `period` accept flags
@@ -105,6 +111,13 @@ struct Params {
     R* grad;               // [d][Cs] MALA: gradient at the current state
     R* gradp;              // [d][Cs] MALA: gradient at the proposal
     R* archive;            // DREAM: [cap][Cg][d]
+    // DREAM(Z) with adaptive=True: crossover distribution (proposal.py:797-809), per chain
+    R* dream_pCR;          // [nCR][Cs]
+    R* dream_DeltaCR;      // [nCR][Cs]
+    R* dream_LCR;          // [nCR][Cs]
+    int* dream_mCR;        // [Cs] crossover index of the last proposal
+    R* arch_s1;            // [d][Cs] column sums of the chain's local archive (for np.var(Z, axis=0))
+    R* arch_s2;            // [d][Cs] column sums of squares
     R* sum1;               // [d][Cs] running sum of finest-level states
     R* sum2;               // [d][Cs] running sum of squares
     // randomize_subchain_length: the link of the running coarse subchain that will be promoted

@@ -171,6 +171,7 @@ struct EngineT : tda_engine {
         DALLOC(tmp, (size_t)d * P.ldD); P.LP = tmp;
         DALLOC(tmp, (size_t)d * P.ldD); P.Pprec = tmp;
         DALLOC(tmp, (size_t)d * P.ldD); P.T = tmp;
+        if (c.prop_kind == TDA_PROP_OWPCN) { DALLOC(tmp, (size_t)d * P.ldD); P.Sop = tmp; }
         DALLOC(P.scaling, Cs);
         DALLOC(P.ucur, Cs);
         DALLOC(P.sum1, (size_t)d * Cs);
@@ -187,9 +188,17 @@ struct EngineT : tda_engine {
             DALLOC(P.am_T, (size_t)d * d * Cs);
         }
         if (c.prop_kind == TDA_PROP_MALA) { DALLOC(P.grad, (size_t)d * Cs); DALLOC(P.gradp, (size_t)d * Cs); }
-        if (c.prop_kind >= TDA_PROP_DREAMZ) {
+        if (tda::is_dream(c.prop_kind)) {
             DALLOC(P.archive, (size_t)c.dream_capacity * P.Cg * d);
             dream_slots = c.dream_M0;
+            if (c.adaptive) {
+                DALLOC(P.dream_pCR, (size_t)tda::MAX_NCR * Cs);
+                DALLOC(P.dream_DeltaCR, (size_t)tda::MAX_NCR * Cs);
+                DALLOC(P.dream_LCR, (size_t)tda::MAX_NCR * Cs);
+                DALLOC(P.dream_mCR, Cs);
+                DALLOC(P.arch_s1, (size_t)d * Cs);
+                DALLOC(P.arch_s2, (size_t)d * Cs);
+            }
         }
         kt = d;
         int n_max = 0;
@@ -327,6 +336,10 @@ struct EngineT : tda_engine {
             }
             return 0;
         }
+        case TDA_UP_PROP_S:
+            if (!P.Sop) return fail(-1, "upload: proposal has no state operator");
+            if ((r = need((size_t)d * d))) return r;
+            return put_matrix(P.Sop, host, d, d, P.ldD);
         case TDA_UP_MODEL_A: {
             const tda::LevelP<R>& v = P.lv[level];
             const int ncols = (v.model_kind == TDA_MODEL_POISSON1D) ? v.n_grid : v.m;
@@ -424,7 +437,7 @@ struct EngineT : tda_engine {
 
     int init(cudaStream_t st) override {
         P.t_base = 0; P.wcount = 0;
-        if (P.prop_kind >= TDA_PROP_DREAMZ) dream_slots = cfg.dream_M0;
+        if (tda::is_dream(P.prop_kind)) dream_slots = cfg.dream_M0;
         for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = 0; P.lvl_steps[l] = 0; }
         int r = launch(tda::MODE_INIT, 0, st);
         if (r) return r;
@@ -521,7 +534,7 @@ struct EngineT : tda_engine {
         for (int l = 1; l < L; l++) w += steps[l];
         P.wcount += (L == 1) ? steps[0] : w;
         for (int l = 0; l < L; l++) { P.rec[l] += steps[l]; if (l >= 1) P.lvl_steps[l] += steps[l]; }
-        if (P.prop_kind >= TDA_PROP_DREAMZ) dream_slots += steps[0];
+        if (tda::is_dream(P.prop_kind)) dream_slots += steps[0];
         return 0;
     }
 
@@ -701,14 +714,17 @@ int validate(const tda_config* c) {
     if (c->n_chains < 1) return fail(-1, "n_chains must be positive");
     for (int l = 0; l + 1 < c->n_levels; l++)
         if (c->subchain[l] < 1) return fail(-1, "subchain lengths must be >= 1");
-    if (c->prop_kind < TDA_PROP_RWMH || c->prop_kind > TDA_PROP_DREAM) return fail(-1, "unknown proposal kind");
-    if ((c->prop_kind == TDA_PROP_MALA || c->prop_kind >= TDA_PROP_DREAMZ) && c->n_levels != 1)
+    if (c->prop_kind < TDA_PROP_RWMH || c->prop_kind > TDA_PROP_OWPCN) return fail(-1, "unknown proposal kind");
+    if ((c->prop_kind == TDA_PROP_MALA || tda::is_dream(c->prop_kind)) && c->n_levels != 1)
         return fail(-1, "MALA / DREAM(Z) are single-level proposals in this engine");
-    if (c->prop_kind >= TDA_PROP_DREAMZ) {
+    if (tda::is_dream(c->prop_kind)) {
         if (c->dream_delta < 1 || c->dream_delta > tda::MAX_DELTA) return fail(-1, "DREAM delta out of range (1..8)");
         if (c->dream_M0 < 2 || c->dream_capacity < c->dream_M0) return fail(-1, "DREAM archive capacity too small");
+        if (c->dream_nCR < 1 || c->dream_nCR > tda::MAX_NCR) return fail(-1, "DREAM nCR out of range (1..8)");
     }
     if (c->adaptive && c->period < 1) return fail(-1, "period must be >= 1");
+    if (c->prop_kind == TDA_PROP_OWPCN && c->adaptive)
+        return fail(-1, "operator-weighted pCN: the operators depend on the step size; adaptive scaling is not supported");
     if (c->aem < 0 || c->aem > 2) return fail(-1, "aem must be 0, 1 (state-independent) or 2 (state-dependent)");
     if (c->aem == 2 && c->n_levels != 2) return fail(-1, "the state-dependent error model is a two-level method");
     if (c->aem == 2 && c->prop_kind != TDA_PROP_RWMH && c->prop_kind != TDA_PROP_AM && c->prop_kind != TDA_PROP_PCN)

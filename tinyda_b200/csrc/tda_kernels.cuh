@@ -160,6 +160,14 @@ struct EpiStoreNeg {       // out[n][c] (+)= -v   (MALA prior gradient P (mu - x
 };
 
 template <typename R>
+struct EpiTile {           // shared-memory tile: t[n][c] (+)= v
+    R* t; int accumulate;
+    __device__ __forceinline__ void operator()(int, int c, int n, R v) {
+        t[n * TC + c] = accumulate ? t[n * TC + c] + v : v;
+    }
+};
+
+template <typename R>
 struct EpiStore {          // out[n][c] = v
     R* out; int Cs; int chain0;
     __device__ __forceinline__ void operator()(int, int c, int n, R v) {
@@ -659,7 +667,19 @@ struct Tile {
             else { s_ca[tid] = (R)1; s_cb[tid] = s; }
         }
         __syncthreads();
-        if (p.prop_kind == TDA_PROP_AM) {
+        if (p.prop_kind == TDA_PROP_OWPCN) {
+            // theta' = S theta + N xi  (proposal.py:593-598) = theta @ S^T + z @ (T N^T)
+            EpiTile<R> e1; e1.t = pt; e1.accumulate = 0;
+            tile_gemm<R>(zt, (const R*)nullptr, p.T, d, d, p.ldD, bs, KB, e1);
+            __syncthreads();
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                zt[e] = p.lv[0].theta[gi(k, c)];
+            }
+            __syncthreads();
+            EpiTile<R> e2; e2.t = pt; e2.accumulate = 1;
+            tile_gemm<R>(zt, (const R*)nullptr, p.Sop, d, d, p.ldD, bs, KB, e2);
+        } else if (p.prop_kind == TDA_PROP_AM) {
             // per-chain factor: thread (c, half) computes half of the output columns
             const int c = tid & (TC - 1), half = tid / TC;
             const int j0 = half * ((d + 1) / 2), j1 = min(d, j0 + (d + 1) / 2);
@@ -746,9 +766,13 @@ struct Tile {
             int mCR = 0;
             {
                 double cs = 0.0;
-                for (int i = 0; i < p.dream_nCR; i++) { cs += 1.0 / p.dream_nCR; if (cs <= (double)ucr) mCR++; }
+                for (int i = 0; i < p.dream_nCR; i++) {
+                    cs += p.adaptive ? (double)p.dream_pCR[gi(i, c)] : 1.0 / p.dream_nCR;
+                    if (cs <= (double)ucr) mCR++;
+                }
                 if (mCR > p.dream_nCR - 1) mCR = p.dream_nCR - 1;
             }
+            if (p.adaptive) p.dream_mCR[chain0 + c] = mCR;
             const R CR = (R)(mCR + 1) / (R)p.dream_nCR;
             unsigned long long mask = 0ull;
             int card = 0;
@@ -781,7 +805,7 @@ struct Tile {
         const int d = p.d;
         const LevelP<R>& v = p.lv[0];
         if (p.prop_kind == TDA_PROP_MALA) propose_mala();
-        else if (p.prop_kind >= TDA_PROP_DREAMZ) propose_dream();
+        else if (is_dream(p.prop_kind)) propose_dream();
         else propose_gaussian();
         eval_level(0);
         if (p.prop_kind == TDA_PROP_MALA) mala_gradient(p.gradp);
@@ -790,7 +814,7 @@ struct Tile {
             R pr = s_prior[c], lk = s_like[c];
             R pr0 = v.prior[g], lk0 = v.like[g];
             R x;
-            if (p.prop_kind == TDA_PROP_PCN) x = lk - lk0;
+            if (is_pcn_like(p.prop_kind)) x = lk - lk0;
             else x = (pr + lk) - (pr0 + lk0);
             if (p.prop_kind == TDA_PROP_MALA) {
                 R s = p.scaling[g];
@@ -820,6 +844,14 @@ struct Tile {
             window_append(c, acc);
         }
         __syncthreads();
+        // DREAM(Z) crossover adaptation needs the squared jump of this step (proposal.py:799)
+        const bool cr_adapt = is_dream(p.prop_kind) && p.adaptive && ((t_base + 1) % p.period) == 0;
+        if (cr_adapt)
+            for (int e = tid; e < d * TC; e += NT) {
+                int c = e % TC, k = e / TC;
+                R jd = s_acc[c] ? pt[e] - v.theta[gi(k, c)] : (R)0;
+                zt[e] = jd * jd;
+            }
         // accepted chains: proposal -> current state
         for (int e = tid; e < d * TC; e += NT) {
             int c = e % TC;
@@ -891,7 +923,7 @@ struct Tile {
                 }
             }
         }
-        if (p.prop_kind >= TDA_PROP_DREAMZ) {
+        if (is_dream(p.prop_kind)) {
             // archive append of the current state (proposal.py:794 / :1652)
             if (slots < p.dream_cap)
                 for (int e = tid; e < d * TC; e += NT) {
@@ -900,6 +932,40 @@ struct Tile {
                         p.archive[((size_t)slots * p.Cg + p.arch_off + chain0 + c) * d + k] = p.lv[0].theta[gi(k, c)];
                 }
             slots += 1;
+            if (p.adaptive) {
+                // local archive moments (the shared-archive variant keeps a local Z too, proposal.py:794)
+                for (int e = tid; e < d * TC; e += NT) {
+                    int k = e / TC, c = e - k * TC;
+                    R x = p.lv[0].theta[gi(k, c)];
+                    p.arch_s1[gi(k, c)] += x;
+                    p.arch_s2[gi(k, c)] += x * x;
+                }
+                if ((t % p.period) == 0) {
+                    __syncthreads();
+                    if (tid < TC) {
+                        const int c = tid, nCR = p.dream_nCR;
+                        const R M = (R)(p.dream_M0 + t);          // rows of the local archive
+                        R acc = (R)0;
+                        for (int k = 0; k < d; k++) {
+                            R mean = p.arch_s1[gi(k, c)] / M;
+                            R var = p.arch_s2[gi(k, c)] / M - mean * mean;      // np.var(Z, axis=0)
+                            acc += zt[k * TC + c] / var;
+                        }
+                        const int mCR = p.dream_mCR[chain0 + c];
+                        p.dream_DeltaCR[gi(mCR, c)] += acc;
+                        p.dream_LCR[gi(mCR, c)] += (R)1;
+                        bool all_pos = true;
+                        R tot = (R)0;
+                        for (int i = 0; i < nCR; i++) {
+                            if (!(p.dream_LCR[gi(i, c)] > (R)0)) all_pos = false;
+                            else tot += p.dream_DeltaCR[gi(i, c)] / p.dream_LCR[gi(i, c)];
+                        }
+                        if (all_pos)
+                            for (int i = 0; i < nCR; i++)
+                                p.dream_pCR[gi(i, c)] = p.dream_DeltaCR[gi(i, c)] / p.dream_LCR[gi(i, c)] / tot;
+                    }
+                }
+            }
         }
     }
 
@@ -1080,6 +1146,25 @@ struct Tile {
                 int k = e / TC, c = e - k * TC;
                 p.am_mu[gi(k, c)] = p.lv[0].theta[gi(k, c)];
             }
+        if (is_dream(p.prop_kind) && p.adaptive) {
+            if (tid < TC)
+                for (int i = 0; i < p.dream_nCR; i++) {
+                    p.dream_pCR[gi(i, tid)] = (R)(1.0 / p.dream_nCR);
+                    p.dream_DeltaCR[gi(i, tid)] = (R)1;
+                    p.dream_LCR[gi(i, tid)] = (R)0;
+                }
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                R a1 = (R)0, a2 = (R)0;
+                if (chain0 + c < p.C)
+                    for (int sl = 0; sl < p.dream_M0; sl++) {
+                        R x = p.archive[((size_t)sl * p.Cg + p.arch_off + chain0 + c) * d + k];
+                        a1 += x; a2 += x * x;
+                    }
+                p.arch_s1[gi(k, c)] = a1;
+                p.arch_s2[gi(k, c)] = a2;
+            }
+        }
         if (p.aem && L > 1) {
             for (int l = 1; l < L; l++) {
                 const LevelP<R>& v = p.lv[l];

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
     R* hp_theta = v.h_theta + ((size_t)p.rec[0] * d) * Cs + g;
     R* hp_prior = v.h_prior + (size_t)p.rec[0] * Cs + g;
     R* hp_like = v.h_like + (size_t)p.rec[0] * Cs + g;
-    R* hp_F = v.h_F + (size_t)p.rec[0] * Cs + g;
+    R* hp_F = v.h_F + (size_t)p.rec[0] * v.m * Cs + g;
     uint8_t* hp_acc = v.h_acc + (size_t)p.rec[0] * Cs + g;
     uint8_t* wp = p.win + (size_t)(p.t_base % p.period) * Cs + g;
     const size_t theta_stride = (size_t)d * Cs;
@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
     if (p.adaptive)
         for (int q = 0; q < wpos; q++) win_cnt += (int)p.win[(size_t)q * Cs + g];
     const bool store_F = (v.store & TDA_STORE_OUTPUT) && v.need_F && MODEL == TDA_MODEL_ROSENBROCK;
+    const bool store_lin_F = (v.store & TDA_STORE_OUTPUT) && MODEL == TDA_MODEL_LINEAR;
     const bool pcn = p.prop_kind == TDA_PROP_PCN;
     const int store = v.store;
     const long long rec0 = p.rec[0], hist_cap = v.hist_cap;
@@ -306,6 +307,18 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
                 hp_theta += theta_stride;
             }
             if (store_F) { *hp_F = F0; hp_F += Cs; }
+            if (store_lin_F) {
+                // Link.model_output of a linear model: recomputed from the current state with the
+                // expression create_link used (same bits), m coalesced stores
+                for (int j = 0; j < v.m; j++) {
+                    R acc_f = (R)0;
+#pragma unroll
+                    for (int k = 0; k < D; k++)
+                        if (k < d) acc_f = fma(th[k], S.A[k * RG_MAXM + j], acc_f);
+                    hp_F[(size_t)j * Cs] = acc_f + S.b[j];
+                }
+                hp_F += (size_t)v.m * Cs;
+            }
             if (store & TDA_STORE_STATS) { *hp_prior = prior; *hp_like = like; hp_prior += Cs; hp_like += Cs; }
             if (store & TDA_STORE_ACCEPT) { *hp_acc = (uint8_t)acc; hp_acc += Cs; }
         }
@@ -358,8 +371,6 @@ inline bool mh_reg_eligible(const tda_config& c, bool need_F_level0) {
     if (lc.lik_kind != TDA_LIK_ISO && lc.lik_kind != TDA_LIK_DIAG) return false;
     if (lc.model_kind == TDA_MODEL_ROSENBROCK) return true;
     if (lc.model_kind != TDA_MODEL_LINEAR || lc.m > RG_MAXM) return false;
-    // a linear model's output vector is not kept per chain: no model-output history
-    if (lc.store & TDA_STORE_OUTPUT) return false;
     (void)need_F_level0;
     return true;
 }

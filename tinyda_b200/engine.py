@@ -120,6 +120,8 @@ class Engine:
             self._up(L.TDA_UP_PRIOR_PREC, 0, np.linalg.inv(pr["cov"]))     # utils.py:272-278
         if "T" in prop:
             self._up(L.TDA_UP_PROP_T, 0, prop["T"])
+        if "S" in prop:
+            self._up(L.TDA_UP_PROP_S, 0, prop["S"])
         for l, lv in enumerate(spec["levels"]):
             mk = int(lv["model"]["kind"])
             if mk in (MODEL_LINEAR, MODEL_POISSON1D):

@@ -10,7 +10,7 @@ in per-chain device arrays and these objects only describe the kernel to run.
 """
 import numpy as np
 
-PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM = 0, 1, 2, 3, 4, 5
+PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM, PROP_OWPCN = 0, 1, 2, 3, 4, 5, 6
 
 
 def svd_factor(C):
@@ -77,6 +77,36 @@ class CrankNicolson(GaussianRandomWalk):
     def lower(self, prior):
         out = self._common()
         out["T"] = svd_factor(prior["cov"])          # proposal.py:336-347: C <- prior covariance
+        return out
+
+
+class OperatorWeightedCrankNicolson(CrankNicolson):
+    """Operator-weighted pCN (Law 2014), tinyDA/proposal.py:515-605:
+    theta' = sqrtm(I - scaling*B) theta + sqrtm(scaling*B) xi,  xi ~ N(0, prior cov).  The two matrix
+    square roots are taken once on the host (proposal.py:578-579); with adaptive=True the reference
+    re-takes them per chain every period from the adapted step size, which is not lowered."""
+
+    kind = PROP_OWPCN
+
+    def __init__(self, B, scaling=1.0, adaptive=False, gamma=1.01, period=100):
+        self.B = B
+        super().__init__(scaling, adaptive, gamma, period)
+
+    def lower(self, prior):
+        from scipy.linalg import sqrtm
+        if self.adaptive:
+            raise NotImplementedError("adaptive OperatorWeightedCrankNicolson is not lowered to the device")
+        d = prior["cov"].shape[0]
+        B = np.atleast_2d(np.asarray(self.B, dtype=np.float64))
+        state_operator = np.real(sqrtm(np.eye(d) - self.scaling * B))
+        noise_operator = np.real(sqrtm(self.scaling * B))
+        T_prior = svd_factor(prior["cov"])
+        out = self._common()
+        out["state_operator"] = state_operator
+        out["noise_operator"] = noise_operator
+        out["T_prior"] = T_prior
+        out["T"] = T_prior @ noise_operator.T        # z @ T = noise_operator @ (z @ T_prior)
+        out["S"] = state_operator.T                  # theta @ S = state_operator @ theta
         return out
 
 
