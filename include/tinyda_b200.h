@@ -100,7 +100,8 @@ typedef struct tda_config {
                                          * 2 state-dependent (two levels; chain.py:446-473, :501-522) */
     int32_t rng_mode;
     int32_t randomize_subchain;         /* DAChain randomize_subchain_length, chain.py:310-321, :369, :525-527 */
-    int32_t reserved0;
+    int32_t mtm_k;                      /* > 0: MultipleTry with k tries around the proposal kernel (ray.py:213-354;
+                                         * RWMH / AM / pCN kernels, 2 <= k <= 16) */
     uint64_t seed;
     int64_t n_chains;                   /* chains on THIS device                       */
     int64_t chain_offset;               /* global index of local chain 0 (Philox key)  */

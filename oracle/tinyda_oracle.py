@@ -26,6 +26,7 @@ Reference map (file:line are into /root/reference/tinyDA/):
   ChainOracle._alpha_state_dependent   chain.py:446-473, distributions.py:427-446,
                                        proposal.py:364-369 (CrankNicolson.get_q)
   randomize_subchain_length            chain.py:310-321, :369-375, :525-527
+  ChainOracle._mtm_propose / _mtm_acceptance   MultipleTry ray.py:213-354
   proposals            proposal.py:132-258 (RWMH), 261-369 (pCN), 372-512 (AM),
                        515-605 (operator-weighted pCN), 608-852 (DREAMZ), 861-1005 (MALA),
                        1627-1656 + ray.py:366-384 (DREAM)
@@ -234,7 +235,8 @@ class ChainOracle:
       prior: dict(mean, LP, logconst, cov)
       levels: list of dict(lik=dict(kind, data, var|cov), model=dict(kind, A, b, scalars, m))
       proposal: dict(kind, T, scaling, adaptive, gamma, period, alpha_star,
-                     am_sd, am_eps, am_t0, C0, M0, delta, b, b_star, nCR)
+                     am_sd, am_eps, am_t0, C0, M0, delta, b, b_star, nCR,
+                     mtm_k: > 0 wraps the kernel in MultipleTry with k tries)
     """
 
     def __init__(self, spec, theta0, z, u, archive0=None, am_refactor="svd", svd_per_proposal=False,
@@ -279,6 +281,7 @@ class ChainOracle:
         self.alpha_star = float(self.P.get("alpha_star", 0.24))
         self.k = 0
         self.t = 0
+        self.mtm_k = int(self.P.get("mtm_k", 0))
         if self.kind in (PROP_RWMH, PROP_PCN, PROP_AM):
             self.T = np.array(self.P["T"], dtype=np.float64)
         if self.kind == PROP_OWPCN:                              # proposal.py:575-579
@@ -368,8 +371,56 @@ class ChainOracle:
         s = self.scaling
         return -0.5 / s ** 2 * np.linalg.norm(x.theta - y.theta - 0.5 * s ** 2 * y.grad) ** 2
 
-    def _propose(self):
+    def _logsumexp(self, a):
+        """scipy.special.logsumexp for a 1-D array (ray.py:316, :350-352)."""
+        a = np.asarray(a, dtype=np.float64)
+        if a.size == 0:
+            return -np.inf
+        a_max = a.max()
+        if not np.isfinite(a_max):
+            a_max = 0.0
+        with np.errstate(divide="ignore"):
+            return np.log(np.sum(np.exp(a - a_max))) + a_max
+
+    def _mtm_propose(self):                                      # ray.py:279-317
         c = self.cur[0]
+        k = self.mtm_k
+        links = [self._create(0, self._propose_from(c), self.next_sid) for _ in range(k)]
+        if self.kind in (PROP_RWMH, PROP_AM):                    # kernel.is_symmetric -> MTM(II)
+            q = np.zeros(k)
+        else:
+            q = np.array([self._get_q_pcn(c, l) for l in links])
+        w = np.array([l.post + qi for l, qi in zip(links, q)])
+        w[np.isnan(w)] = -np.inf
+        self.mtm_weights = w
+        u = self.S.uniform()
+        if np.isinf(w).all():
+            idx = min(int(np.floor(u * k)), k - 1)
+        else:
+            with np.errstate(over="ignore"):
+                pr = np.exp(w - self._logsumexp(w))
+            idx = int(min(np.searchsorted(np.cumsum(pr), u, side="right"), k - 1))
+        return links[idx].theta
+
+    def _mtm_acceptance(self, new, old):                         # ray.py:319-354
+        if np.isnan(new.post) or np.isinf(self.mtm_weights).all():
+            return 0.0
+        refs = [self._create(0, self._propose_from(new), 0) for _ in range(self.mtm_k - 1)]
+        if self.kind in (PROP_RWMH, PROP_AM):
+            q = np.zeros(len(refs))
+        else:
+            q = np.array([self._get_q_pcn(new, r) for r in refs])
+        wr = np.array([r.post + qi for r, qi in zip(refs, q)])
+        wr[np.isnan(wr)] = -np.inf
+        with np.errstate(over="ignore", invalid="ignore"):
+            return np.exp(self._logsumexp(self.mtm_weights) - self._logsumexp(wr))
+
+    def _propose(self):
+        if self.mtm_k:
+            return self._mtm_propose()
+        return self._propose_from(self.cur[0])
+
+    def _propose_from(self, c):
         d = self.d
         if self.kind in (PROP_RWMH, PROP_AM):                    # proposal.py:247-251
             T = svd_factor(self.P["C"]) if (self.svd_per_proposal and self.kind == PROP_RWMH) else self.T
@@ -413,6 +464,8 @@ class ChainOracle:
         return Z.shape[0], (lambda r: Z[r, :])
 
     def _acceptance(self, new, old):
+        if self.mtm_k:
+            return self._mtm_acceptance(new, old)
         if np.isnan(new.post):                                   # proposal.py:254, 358, 963
             return 0.0
         with np.errstate(over="ignore"):

@@ -22,6 +22,7 @@ What it does
     choice(M, 2, replace=False)    r1=floor(u1*M); r2=floor(u2*(M-1)); r2 += (r2>=r1)
     choice(n, p=p)                 first k with cumsum(p)[k] > u   (k clipped to n-1)
     choice(n)                      floor(u*n)
+    choice(seq[, p=p])             seq[choice(len(seq)[, p=p])]
     randint(lo, hi)                lo + floor(u*(hi-lo))
   The integer maps are OUR definition of how integers derive from uniforms (numpy's own
   integer draws are not reproducible from a uniform stream); the engine uses the same maps.
@@ -148,6 +149,10 @@ def injected(streams):
         return float(S.take_u(1)[0])
 
     def choice(a, size=None, replace=True, p=None):
+        if not isinstance(a, (int, np.integer)):
+            # choice over a sequence of objects (MultipleTry, ray.py:309-316): pick the index
+            seq = list(a)
+            return seq[choice(len(seq), size=size, replace=replace, p=p)]
         n = int(a)
         if size is None and p is None:
             return min(int(np.floor(S.take_u(1)[0] * n)), n - 1)

@@ -132,6 +132,35 @@ def da_owpcn():
 
 
 @case
+def mh_mtm_rwmh():
+    """MultipleTry (ray.py:213-354) around a symmetric random walk: MTM(II), k = 3."""
+    rng = np.random.default_rng(37)
+    d, m = 4, 10
+    prior = stats.multivariate_normal(0.1 * np.ones(d), np.eye(d))
+    (G, y), = _linear_levels(rng, d, [m], 0.3, prior)
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.09 * np.eye(m)), LinearModel(G))
+        return [post], tda.MultipleTry(tda.GaussianRandomWalk(C=0.08 * np.eye(d)), 3), {}
+    return dict(build=build, n_chains=3, iterations=90, seed=38, prior=prior)
+
+
+@case
+def mh_mtm_pcn():
+    """MultipleTry around pCN: MTM(I), the transition densities CrankNicolson.get_q enter the
+    candidate and reference weights; k = 4."""
+    rng = np.random.default_rng(39)
+    d, m = 6, 12
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d, 0.4))
+    (G, y), = _linear_levels(rng, d, [m], 0.2, prior)
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.04 * np.eye(m)), LinearModel(G))
+        return [post], tda.MultipleTry(tda.CrankNicolson(scaling=0.25), 4), {}
+    return dict(build=build, n_chains=3, iterations=80, seed=40, prior=prior)
+
+
+@case
 def da_pcn_small():
     """cfg2 in miniature: two-level DA, pCN, coarse = strided observation subset, J=3."""
     rng = np.random.default_rng(2)
@@ -421,4 +450,8 @@ def stream_sizes(spec, iterations):
         nu += iterations
     if kind in (4, 5):
         nu += base_steps * (2 * spec["proposal"]["delta"] + 1 + d + 1 + d)
+    k = int(spec["proposal"].get("mtm_k", 0))
+    if k:
+        nz = base_steps * d * (2 * k - 1)
+        nu += base_steps
     return nz + 8, nu + 8

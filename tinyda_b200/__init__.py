@@ -14,7 +14,7 @@ from .distributions import (GaussianLogLike, AdaptiveGaussianLogLike, AdaptiveLo
 from .posterior import Posterior
 from .link import Link, LinkSequence
 from .proposal import (Proposal, GaussianRandomWalk, CrankNicolson, OperatorWeightedCrankNicolson,
-                       AdaptiveMetropolis, MALA, DREAMZ, DREAM, SingleDreamZ)
+                       AdaptiveMetropolis, MALA, DREAMZ, DREAM, SingleDreamZ, MultipleTry)
 from .lowering import lower_problem
 from .sampler import sample
 from .diagnostics import to_inference_data, get_samples, to_xarray, ess_bulk, rhat

@@ -18,6 +18,7 @@ constexpr int MAXL = TDA_MAX_LEVELS;
 constexpr int MAXD = TDA_MAX_D;
 constexpr int MAX_DELTA = 8;
 constexpr int MAX_NCR = 8;
+constexpr int MAX_MTM = 16;
 
 __host__ __device__ __forceinline__ bool is_dream(int kind) { return kind == TDA_PROP_DREAMZ || kind == TDA_PROP_DREAM; }
 // proposals whose acceptance is the likelihood ratio (proposal.py:357-362, inherited by :515)
@@ -120,6 +121,17 @@ struct Params {
     R* arch_s2;            // [d][Cs] column sums of squares
     R* sum1;               // [d][Cs] running sum of finest-level states
     R* sum2;               // [d][Cs] running sum of squares
+    // MultipleTry (ray.py:213-354): k candidates per base-level step
+    int mtm_k;
+    long long* zcur;       // [Cs] normal cursor (consumption depends on the chain's control flow)
+    R* mt_theta;           // [k][d][Cs] candidates
+    R* mt_prior;           // [k][Cs]
+    R* mt_like;            // [k][Cs]
+    R* mt_w;               // [k][Cs] log-weights of the candidates, then of the reference points
+    R* mt_F;               // [k][m0][Cs] (need_F)
+    R* mt_y;               // [d][Cs] the chosen candidate (source of the reference points)
+    int* mt_sel;           // [Cs] its index; -1: all weights were -inf / NaN posterior (alpha = 0)
+    R* mt_lse;             // [Cs] logsumexp of the candidate weights
     // randomize_subchain_length: the link of the running coarse subchain that will be promoted
     int* promo_j;          // [Cs] 1-based coarse step after which it is taken
     R* pm_theta;           // [d][Cs]

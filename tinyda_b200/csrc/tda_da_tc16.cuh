@@ -870,7 +870,7 @@ struct DaTc16State<float> {
     DaTc16Params q{};
 
     bool eligible(const tda_config& c, const Params<float>& P) const {
-        if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.prop_kind != TDA_PROP_PCN || c.adaptive) return false;
+        if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.mtm_k || c.prop_kind != TDA_PROP_PCN || c.adaptive) return false;
         if (c.d != T16_K) return false;
         for (int l = 0; l < 2; l++)
             if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;

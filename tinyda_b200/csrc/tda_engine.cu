@@ -147,6 +147,7 @@ struct EngineT : tda_engine {
         P.adaptive = c.adaptive; P.period = c.period > 0 ? c.period : 1; P.am_t0 = c.am_t0;
         P.am_device_refactor = c.am_device_refactor;
         P.randomize = c.randomize_subchain;
+        P.mtm_k = c.mtm_k;
         for (int l = 0; l < TDA_MAX_LEVELS; l++) P.J[l] = c.subchain[l];
         P.C = (int)c.n_chains;
         // padded to whole pairs of 128-chain tiles (the tensor-core kernel processes tile pairs)
@@ -253,6 +254,18 @@ struct EngineT : tda_engine {
             if (lc.store & TDA_STORE_STATS) { DALLOC(v.h_prior, cap * Cs); DALLOC(v.h_like, cap * Cs); }
             if (lc.store & TDA_STORE_OUTPUT) DALLOC(v.h_F, cap * m * Cs);
             if (lc.store & TDA_STORE_ACCEPT) DALLOC(v.h_acc, cap * Cs);
+        }
+        if (c.mtm_k) {
+            const size_t K = (size_t)c.mtm_k;
+            DALLOC(P.zcur, Cs);
+            DALLOC(P.mt_theta, K * d * Cs);
+            DALLOC(P.mt_prior, K * Cs);
+            DALLOC(P.mt_like, K * Cs);
+            DALLOC(P.mt_w, K * Cs);
+            if (P.lv[0].need_F) DALLOC(P.mt_F, K * P.lv[0].m * Cs);
+            DALLOC(P.mt_y, (size_t)d * Cs);
+            DALLOC(P.mt_sel, Cs);
+            DALLOC(P.mt_lse, Cs);
         }
         if (c.randomize_subchain) {
             DALLOC(P.promo_j, Cs);
@@ -613,6 +626,7 @@ struct EngineT : tda_engine {
             if (bytes < (size_t)2 * P.C * sizeof(long long)) return fail(-1, "get: destination too small");
             long long* o = reinterpret_cast<long long*>(dst);
             for (int c = 0; c < P.C; c++) o[c] = P.t_base * d;
+            if (P.zcur) { int r0 = get_soa(P.zcur, 1, o, (size_t)P.C * sizeof(long long), false, false); if (r0) return r0; }
             return get_soa(P.ucur, 1, o + P.C, (size_t)P.C * sizeof(long long), false, false);
         }
         case TDA_G_AM_SIGMA:
@@ -723,6 +737,10 @@ int validate(const tda_config* c) {
         if (c->dream_nCR < 1 || c->dream_nCR > tda::MAX_NCR) return fail(-1, "DREAM nCR out of range (1..8)");
     }
     if (c->adaptive && c->period < 1) return fail(-1, "period must be >= 1");
+    if (c->mtm_k < 0 || c->mtm_k == 1 || c->mtm_k > tda::MAX_MTM) return fail(-1, "mtm_k must be 0 or 2..16");
+    if (c->mtm_k && c->prop_kind != TDA_PROP_RWMH && c->prop_kind != TDA_PROP_AM && c->prop_kind != TDA_PROP_PCN)
+        return fail(-1, "MultipleTry needs an RWMH, AM or pCN kernel");
+    if (c->mtm_k && (c->randomize_subchain || c->aem == 2)) return fail(-1, "MultipleTry cannot be combined with randomize_subchain / state-dependent AEM");
     if (c->prop_kind == TDA_PROP_OWPCN && c->adaptive)
         return fail(-1, "operator-weighted pCN: the operators depend on the step size; adaptive scaling is not supported");
     if (c->aem < 0 || c->aem > 2) return fail(-1, "aem must be 0, 1 (state-independent) or 2 (state-dependent)");

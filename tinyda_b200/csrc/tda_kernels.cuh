@@ -189,6 +189,8 @@ struct Tile {
     int tid;
     // run-local counters (uniform across chains)
     long long t_base, wcount, rec[MAXL], lvl_steps[MAXL], slots;
+    long long mtm_zoff;          // MultipleTry: normals drawn so far within the current step
+    const R* prop_src;           // state the Gaussian proposals start from (default: level 0's current state)
 
     __device__ Tile(const Params<R>& p_, unsigned char* smem, int kt) : p(p_) {
         tid = threadIdx.x;
@@ -228,6 +230,13 @@ struct Tile {
     // d normals per chain for this base step -> zt[k][c]
     __device__ void fill_normals() {
         const int d = p.d;
+        if (p.mtm_k) {      // per-chain cursor: offset by the draws this chain has consumed so far
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                zt[k * TC + c] = normal_at(c, p.zcur[chain0 + c] + mtm_zoff + k);
+            }
+            return;
+        }
         const long long z0 = t_base * d;
         if (p.rng_mode == TDA_RNG_PHILOX && (z0 & 3) == 0 && !p.z_round) {
             const int nb4 = (d + 3) >> 2;
@@ -674,7 +683,7 @@ struct Tile {
             __syncthreads();
             for (int e = tid; e < d * TC; e += NT) {
                 int k = e / TC, c = e - k * TC;
-                zt[e] = p.lv[0].theta[gi(k, c)];
+                zt[e] = prop_src[gi(k, c)];
             }
             __syncthreads();
             EpiTile<R> e2; e2.t = pt; e2.accumulate = 1;
@@ -686,11 +695,11 @@ struct Tile {
             for (int j = j0; j < j1; j++) {
                 R s = (R)0;
                 for (int k = 0; k < d; k++) s = fma(zt[k * TC + c], p.am_T[gi(k * d + j, c)], s);
-                pt[j * TC + c] = s_ca[c] * p.lv[0].theta[gi(j, c)] + s_cb[c] * s;
+                pt[j * TC + c] = s_ca[c] * prop_src[gi(j, c)] + s_cb[c] * s;
             }
         } else {
             EpiCombine<R> e;
-            e.theta = p.lv[0].theta; e.Cs = p.Cs; e.chain0 = chain0; e.pt = pt; e.ca = s_ca; e.cb = s_cb;
+            e.theta = prop_src; e.Cs = p.Cs; e.chain0 = chain0; e.pt = pt; e.ca = s_ca; e.cb = s_cb;
             tile_gemm<R>(zt, (const R*)nullptr, p.T, d, d, p.ldD, bs, KB, e);
         }
         __syncthreads();
@@ -800,14 +809,145 @@ struct Tile {
         __syncthreads();
     }
 
+    // ---- MultipleTry (ray.py:213-354) ---------------------------------------------------------------
+    // log q(x, y) of the pCN kernel up to its constant for the tile y in pt -> red-free result in
+    // s_cb (valid for tid < TC); x = src.  Zero for symmetric kernels (MTM(II)).
+    __device__ void mtm_q(const R* src) {
+        const int d = p.d;
+        if (p.prop_kind != TDA_PROP_PCN) {
+            if (tid < TC) s_cb[tid] = (R)0;
+            __syncthreads();
+            return;
+        }
+        for (int e = tid; e < d * TC; e += NT) {
+            int k = e / TC, c = e - k * TC;
+            R s = p.scaling[chain0 + c];
+            zt[e] = pt[e] - tsqrt((R)1 - s * s) * src[gi(k, c)];
+        }
+        __syncthreads();
+        EpiSsq<R> e;
+        tile_gemm<R>(zt, (const R*)nullptr, p.LP, d, d, p.ldD, bs, KB, e);
+        R tot = reduce_cols(e.ps[0], e.ps[1]);
+        if (tid < TC) { R s = p.scaling[chain0 + tid]; s_cb[tid] = (R)-0.5 * tot / (s * s); }
+        __syncthreads();
+    }
+
+    // scipy.special.logsumexp of w[0..n) (stride Cs) for chain c
+    __device__ R mtm_logsumexp(const R* w, int n, int c) const {
+        if (n == 0) return -INFINITY;
+        R a_max = w[gi(0, c)];
+        for (int i = 1; i < n; i++) a_max = fmax(a_max, w[gi(i, c)]);
+        if (!isfinite(a_max)) a_max = (R)0;
+        R s = (R)0;
+        for (int i = 0; i < n; i++) s += texp(w[gi(i, c)] - a_max);
+        return tlog(s) + a_max;
+    }
+
+    // make_proposal + get_acceptance of MultipleTry: leaves the chosen candidate in pt / s_prior /
+    // s_like / Fp and the acceptance probability in s_ca
+    __device__ void mtm_step() {
+        const int d = p.d, K = p.mtm_k;
+        const LevelP<R>& v = p.lv[0];
+        mtm_zoff = 0;
+        prop_src = v.theta;
+        for (int i = 0; i < K; i++) {                  // ray.py:281-303: k candidates and their weights
+            propose_gaussian();
+            mtm_zoff += d;
+            eval_level(0);
+            mtm_q(v.theta);
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                p.mt_theta[((size_t)i * d + k) * p.Cs + chain0 + c] = pt[e];
+            }
+            if (v.need_F)
+                for (int e = tid; e < v.m * TC; e += NT) {
+                    int k = e / TC, c = e - k * TC;
+                    p.mt_F[((size_t)i * v.m + k) * p.Cs + chain0 + c] = v.Fp[gi(k, c)];
+                }
+            if (tid < TC) {
+                const int c = tid;
+                R w = (s_prior[c] + s_like[c]) + s_cb[c];
+                if (tisnan(w)) w = -INFINITY;
+                p.mt_prior[gi(i, c)] = s_prior[c];
+                p.mt_like[gi(i, c)] = s_like[c];
+                p.mt_w[gi(i, c)] = w;
+            }
+            __syncthreads();
+        }
+        if (tid < TC) {                                // ray.py:305-317: choose one
+            const int c = tid, g = chain0 + c;
+            bool all_inf = true;
+            for (int i = 0; i < K; i++) if (!isinf(p.mt_w[gi(i, c)])) all_inf = false;
+            long long uc = p.ucur[g];
+            const R u = uniform_at(c, uc);
+            p.ucur[g] = uc + 1;
+            int idx;
+            const R lse = mtm_logsumexp(p.mt_w, K, c);
+            if (all_inf) {
+                idx = (int)tfloor(u * (R)K);
+                if (idx > K - 1) idx = K - 1;
+            } else {
+                R cs = (R)0;
+                idx = 0;
+                for (int i = 0; i < K; i++) { cs += texp(p.mt_w[gi(i, c)] - lse); if (cs <= u) idx++; }
+                if (idx > K - 1) idx = K - 1;
+            }
+            const R post = p.mt_prior[gi(idx, c)] + p.mt_like[gi(idx, c)];
+            const bool dead = all_inf || tisnan(post);          // ray.py:321: acceptance 0, no reference draws
+            p.mt_sel[g] = idx;
+            s_acc[c] = dead ? 1 : 0;
+            p.mt_lse[g] = lse;
+        }
+        __syncthreads();
+        for (int e = tid; e < d * TC; e += NT) {
+            int k = e / TC, c = e - k * TC;
+            p.mt_y[gi(k, c)] = p.mt_theta[((size_t)p.mt_sel[chain0 + c] * d + k) * p.Cs + chain0 + c];
+        }
+        __syncthreads();
+        prop_src = p.mt_y;
+        for (int i = 0; i < K - 1; i++) {              // ray.py:325-347: k-1 reference points
+            propose_gaussian();
+            mtm_zoff += d;
+            eval_level(0);
+            mtm_q(p.mt_y);
+            if (tid < TC) {
+                const int c = tid;
+                R w = (s_prior[c] + s_like[c]) + s_cb[c];
+                if (tisnan(w)) w = -INFINITY;
+                p.mt_w[gi(i, c)] = w;
+            }
+            __syncthreads();
+        }
+        prop_src = v.theta;
+        // the chosen candidate becomes the proposal link (chain.py:105)
+        for (int e = tid; e < d * TC; e += NT) pt[e] = p.mt_y[gi(e / TC, e % TC)];
+        if (v.need_F)
+            for (int e = tid; e < v.m * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                v.Fp[gi(k, c)] = p.mt_F[((size_t)p.mt_sel[chain0 + c] * v.m + k) * p.Cs + chain0 + c];
+            }
+        if (tid < TC) {
+            const int c = tid, g = chain0 + c, idx = p.mt_sel[g];
+            s_prior[c] = p.mt_prior[gi(idx, c)];
+            s_like[c] = p.mt_like[gi(idx, c)];
+            s_ca[c] = s_acc[c] ? (R)0 : texp(p.mt_lse[g] - mtm_logsumexp(p.mt_w, K - 1, c));   // ray.py:350-353
+            // a chain whose candidates were all invalid draws no reference points (ray.py:321-323)
+            p.zcur[g] += s_acc[c] ? (long long)K * d : (long long)(2 * K - 1) * d;
+        }
+        __syncthreads();
+    }
+
     // ---- base level step -----------------------------------------------------------------------
     __device__ void base_step() {
         const int d = p.d;
         const LevelP<R>& v = p.lv[0];
-        if (p.prop_kind == TDA_PROP_MALA) propose_mala();
-        else if (is_dream(p.prop_kind)) propose_dream();
-        else propose_gaussian();
-        eval_level(0);
+        if (p.mtm_k) mtm_step();
+        else {
+            if (p.prop_kind == TDA_PROP_MALA) propose_mala();
+            else if (is_dream(p.prop_kind)) propose_dream();
+            else propose_gaussian();
+            eval_level(0);
+        }
         if (p.prop_kind == TDA_PROP_MALA) mala_gradient(p.gradp);
         if (tid < TC) {
             const int c = tid, g = chain0 + c;
@@ -830,6 +970,7 @@ struct Tile {
                 x = x + f * qxy - f * qyx;
             }
             R alpha = tisnan(pr + lk) ? (R)0 : texp(x);
+            if (p.mtm_k) alpha = s_ca[c];
             long long uc = p.ucur[g];
             R u = uniform_at(c, uc);
             p.ucur[g] = uc + 1;
@@ -1109,6 +1250,7 @@ struct Tile {
             const int g = chain0 + tid;
             p.scaling[g] = p.scaling0;
             p.ucur[g] = 0;
+            if (p.mtm_k) p.zcur[g] = 0;
             if (p.adaptive) p.win_sum[g] = 0;
         }
         for (int l = 0; l < L; l++) {
@@ -1219,6 +1361,8 @@ chain_kernel(const __grid_constant__ Params<R> p, int kt) {
         T.t_base = p.t_base;
         T.wcount = p.wcount;
         T.slots = p.dream_slots;
+        T.mtm_zoff = 0;
+        T.prop_src = p.lv[0].theta;
         for (int l = 0; l < MAXL; l++) { T.rec[l] = p.rec[l]; T.lvl_steps[l] = p.lvl_steps[l]; }
         if (p.mode == MODE_INIT) T.init();
         else T.run();

@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(RG_NT) mh_reg_kernel(const __grid_constant__ P
 
 // which configurations the register kernel advances
 inline bool mh_reg_eligible(const tda_config& c, bool need_F_level0) {
-    if (c.n_levels != 1 || c.d > 8) return false;
+    if (c.n_levels != 1 || c.d > 8 || c.mtm_k) return false;
     if (c.prop_kind != TDA_PROP_RWMH && c.prop_kind != TDA_PROP_PCN && c.prop_kind != TDA_PROP_MALA) return false;
     const tda_level_config& lc = c.level[0];
     if (lc.lik_kind != TDA_LIK_ISO && lc.lik_kind != TDA_LIK_DIAG) return false;

@@ -8,7 +8,7 @@ import numpy as np
 
 from .posterior import Posterior, lower_prior
 from .proposal import (PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM,
-                       GaussianRandomWalk)
+                       GaussianRandomWalk, MultipleTry)
 from .distributions import LIK_ADAPTIVE
 from .models import MODEL_LINEAR, MODEL_ROSENBROCK
 
@@ -23,7 +23,7 @@ def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_mo
     L = len(posteriors)
     if L < 1 or L > MAX_LEVELS:
         raise ValueError("the engine supports 1..%d levels" % MAX_LEVELS)
-    if not isinstance(proposal, GaussianRandomWalk):
+    if not isinstance(proposal, (GaussianRandomWalk, MultipleTry)):
         raise TypeError("proposal %s cannot be lowered to the device engine"
                         % type(proposal).__name__)
     prior = lower_prior(posteriors[0].prior)
@@ -64,6 +64,8 @@ def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_mo
         # chain.py:456-460 needs is_symmetric or a working get_q(fine link, fine link): MALA's get_q
         # reads a gradient the fine links do not carry and DREAM(Z) inherits a get_q that returns None
         raise TypeError("the state-dependent error model needs a symmetric proposal or CrankNicolson")
+    if prop.get("mtm_k", 0) and aem == 2:
+        raise NotImplementedError("MultipleTry with the state-dependent error model is not lowered")
     randomize = 0
     if randomize_subchain_length:
         if L != 2:

@@ -183,6 +183,35 @@ class DREAM(DREAMZ):
     kind = PROP_DREAM
 
 
+class MultipleTry(Proposal):
+    """Multiple-Try Metropolis (Liu et al. 2000) around another proposal, tinyDA/ray.py:213-354:
+    k candidates from the kernel, one chosen with probability proportional to its posterior
+    weight, k-1 reference points drawn from the chosen one, acceptance = ratio of the summed
+    weights.  MTM(II) for symmetric kernels, MTM(I) with the kernel's transition density
+    otherwise.  The reference evaluates the k links on k Ray actors; here the candidates of all
+    chains are evaluated by the same lock-step kernel."""
+
+    is_symmetric = True
+
+    def __init__(self, kernel, k):
+        import warnings
+        self.kernel = kernel
+        self.k = k
+        if self.kernel.adaptive:                                   # ray.py:258-261
+            warnings.warn(" Using global adaptive scaling with MultipleTry proposal can be unstable.\n")
+
+    def lower(self, prior):
+        out = self.kernel.lower(prior)
+        if out["kind"] not in (PROP_RWMH, PROP_AM, PROP_PCN):
+            # MTM(I) needs kernel.get_q on plain links: MALA's reads a cached gradient the candidate
+            # links do not have, DREAM(Z) inherits one that returns None (proposal.py:40, :977-988)
+            raise TypeError("MultipleTry needs a GaussianRandomWalk, AdaptiveMetropolis or CrankNicolson kernel")
+        if int(self.k) < 2 or int(self.k) > 16:
+            raise ValueError("MultipleTry is lowered for 2 <= k <= 16 tries")
+        out["mtm_k"] = int(self.k)
+        return out
+
+
 def SingleDreamZ(*args, **kwargs):
     import warnings
     warnings.warn(" SingleDreamZ has been deprecated. Please use DREAMZ.")

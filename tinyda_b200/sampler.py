@@ -82,6 +82,11 @@ def sample(
         posteriors[0].prior, stats._multivariate.multivariate_normal_frozen
     ):
         raise TypeError("Prior must be of type scipy.stats.multivariate_normal for pCN proposal")
+    elif hasattr(proposal, "kernel"):                                  # sampler.py:146-152
+        if isinstance(proposal.kernel, CrankNicolson) and not isinstance(
+            posteriors[0].prior, stats._multivariate.multivariate_normal_frozen
+        ):
+            raise TypeError("Prior must be of type scipy.stats.multivariate_normal for pCN kernel")
 
     # sampler.py:184-193
     if n_levels > 2 and adaptive_error_model == "state-dependent":
