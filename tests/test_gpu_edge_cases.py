@@ -1,0 +1,100 @@
+"""Edge cases of the hot path on the GPU: empty runs, a single chain, chain counts that do not fill
+a tile, the smallest and largest shapes the tensor-core kernel accepts, and what it must refuse."""
+import numpy as np
+import pytest
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+
+def test_zero_iterations_returns_only_the_initial_links():
+    import tinyda_b200 as tda
+    import problems
+    defn = problems.CASES["da_pcn_small"]()
+    posts, prop, kw = defn["build"](tda)
+    res = tda.sample(posts, prop, 0, n_chains=3, seed=1, **kw)
+    assert res["iterations"] == 1
+    assert len(res["chain_fine_0"]) == 1 and len(res["chain_coarse_2"]) == 0
+    link = res["chain_fine_1"][0]
+    assert np.isfinite(link.posterior) and link.parameters.shape == (8,)
+
+
+@pytest.mark.parametrize("name", ["mh_pcn_diag", "da_aem_linear", "mlda3_linear"])
+@pytest.mark.parametrize("C", [1, 129, 257])
+def test_ragged_chain_counts_do_not_change_any_chain(name, C):
+    """Chains are independent: chain i of a C-chain engine equals chain i of any other engine fed
+    the same stream, whatever the padding of the last tile (here: the golden chain 0 replicated)."""
+    from tinyda_b200.engine import Engine, STORE_FULL
+    g = golden_io.load(name)
+    spec, iters = g["spec"], g["iterations"]
+    theta0 = np.repeat(g["theta0"][:1], C, axis=0)
+    z = np.repeat(g["z"][:1], C, axis=0)
+    u = np.repeat(g["u"][:1], C, axis=0)
+    eng = Engine(spec, C, dtype="float64", rng="injected", streams=(z, u), store=STORE_FULL,
+                 capacity_iterations=iters)
+    eng.init(theta0)
+    eng.run(iters)
+    for l in range(spec["n_levels"]):
+        ref = g["ref"][l]
+        th = np.transpose(eng.fetch(l, "theta"), (2, 0, 1))
+        acc = eng.fetch(l, "accept").T.astype(bool)
+        for c in (0, C - 1):
+            assert np.array_equal(acc[c], ref["acc"][0])
+            np.testing.assert_allclose(th[c], ref["theta"][0], rtol=1e-10, atol=1e-12)
+    eng.close()
+
+
+@pytest.mark.parametrize("m_c,m_f", [(16, 64), (128, 1920)])
+def test_tc16_extreme_shapes_agree_with_the_generic_kernel(m_c, m_f):
+    """Smallest and largest observation counts the fp16-split tensor-core kernel accepts, against
+    the generic fp32 kernel on the same (z16) Philox streams."""
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.engine import Engine, STORE_NONE, STORE_STATS
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da(m_f=m_f, m_c=m_c, beta=0.05 if m_f > 100 else 0.2)
+    spec = lower_problem(w["posteriors"], w["proposal"], 10)
+    C, iters = 256, 12
+    theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(3))
+    out = {}
+    for kern in ("tc16", "generic"):
+        eng = Engine(spec, C, dtype="float32", seed=5, store=[STORE_NONE, STORE_STATS], capacity_iterations=iters)
+        eng.select_kernel(kern)
+        if kern == "generic":
+            eng.set_z_round(True)
+        eng.init(theta0)
+        eng.run(iters)
+        out[kern] = (eng.fetch(1, "accept"), eng.fetch(1, "theta"), eng.fetch(1, "like"))
+        eng.close()
+    acc_a, th_a, lk_a = out["tc16"]
+    acc_b, th_b, lk_b = out["generic"]
+    same = acc_a == acc_b
+    assert same.mean() > 0.95, same.mean()
+    ok = same.all(axis=0)
+    assert ok.mean() > 0.5
+    scale = np.abs(th_b).max()
+    assert np.abs(th_a[:, :, ok] - th_b[:, :, ok]).max() < 2e-3 * scale
+    assert np.abs(lk_a[:, ok] - lk_b[:, ok]).max() < 2e-3 * np.abs(lk_b).max() + 0.05
+
+
+def test_tensor_core_kernel_refuses_what_it_cannot_run():
+    """Explicit kernel selection fails loudly (no silent fallback) on unsupported configurations;
+    automatic selection falls back to the generic kernel."""
+    from tinyda_b200._lib import EngineError
+    from tinyda_b200.engine import Engine, STORE_STATS
+    g = golden_io.load("da_pcn_small")            # d = 8: not a tensor-core shape
+    eng = Engine(g["spec"], 4, dtype="float32", seed=1, store=STORE_STATS, capacity_iterations=4)
+    eng.init(g["theta0"])
+    assert eng.kernel() == "generic"
+    for kern in ("tc16", "tc", "reg"):
+        eng.select_kernel(kern)
+        with pytest.raises(EngineError, match="does not support"):
+            eng.run(1)
+    eng.select_kernel("auto")
+    eng.run(2)
+    eng.close()
+    # float64 engines never take the float32 tensor-core path
+    g2 = golden_io.load("da_pcn_cfg2")
+    e2 = Engine(g2["spec"], 256, dtype="float64", seed=1, store=STORE_STATS, capacity_iterations=2)
+    assert e2.kernel() == "generic"
+    e2.close()
