@@ -327,4 +327,71 @@ __device__ __forceinline__ R philox_uniform(unsigned long long seed, long long c
     return u01<R>(x);
 }
 
+// ---- sequential per-chain stream cursors (shared by the register-resident kernel and the DREAM
+// proposal of the lock-step kernel) -------------------------------------------------------------
+template <typename R>
+struct PairGen;
+template <>
+struct PairGen<float> {
+    static __device__ __forceinline__ void pair(const uint4& b, int half, float& n0, float& n1) {
+        if (half == 0) bm_pair(b.x, b.y, BM_C_PLAIN, n0, n1);
+        else bm_pair(b.z, b.w, BM_C_PLAIN, n0, n1);
+    }
+};
+template <>
+struct PairGen<double> {
+    static __device__ __forceinline__ void pair(const uint4& b, int half, double& n0, double& n1) {
+        const uint32_t wr = half == 0 ? b.x : b.z, wa = half == 0 ? b.y : b.w;
+        double r = tsqrt(-2.0 * tlog(u01<double>(wr)));
+        double s, c;
+        tsincospi(2.0 * u01<double>(wa), &s, &c);
+        n0 = r * c;
+        n1 = r * s;
+    }
+};
+
+// per-thread view of the chain's two streams.  The kernel consumes both strictly sequentially, so
+// the generator keeps a cursor per stream and decides from its low bits when a new Philox block
+// (4 normals or 4 uniforms) or Box-Muller pair is due; seek_*() primes the cached block when the
+// launch starts in the middle of one.
+template <typename R>
+struct ChainStreams {
+    const Params<R>& p;
+    long long chain;       // global chain id (Philox counter word)
+    int local;             // chain index on this engine (injected streams)
+    uint4 zb, ub;
+    unsigned long long zi, ui;     // next normal / uniform index
+    R n0, n1;
+    __device__ ChainStreams(const Params<R>& p_, int local_) : p(p_), chain(p_.chain_offset + local_), local(local_) {}
+    __device__ __forceinline__ void seek_normal(long long idx) {
+        zi = (unsigned long long)idx;
+        if (p.rng_mode == TDA_RNG_INJECTED) return;
+        if (zi & 3) zb = philox_block(p.seed, chain, STREAM_Z, zi >> 2);
+        if (zi & 1) PairGen<R>::pair(zb, (int)((zi >> 1) & 1), n0, n1);
+    }
+    __device__ __forceinline__ void seek_uniform(long long idx) {
+        ui = (unsigned long long)idx;
+        if (p.rng_mode == TDA_RNG_INJECTED) return;
+        if (ui & 3) ub = philox_block(p.seed, chain, STREAM_U, ui >> 2);
+    }
+    __device__ __forceinline__ R normal() {
+        const unsigned long long idx = zi++;
+        if (p.rng_mode == TDA_RNG_INJECTED)
+            return (local < p.C && (long long)idx < p.zlen) ? p.zs[(size_t)local * p.zlen + idx] : (R)0;
+        const unsigned o = (unsigned)idx & 3u;
+        if (o == 0) zb = philox_block(p.seed, chain, STREAM_Z, idx >> 2);
+        if ((o & 1u) == 0) PairGen<R>::pair(zb, (int)(o >> 1), n0, n1);
+        return (o & 1u) ? n1 : n0;
+    }
+    __device__ __forceinline__ R uniform() {
+        const unsigned long long idx = ui++;
+        if (p.rng_mode == TDA_RNG_INJECTED)
+            return (local < p.C && (long long)idx < p.ulen) ? p.us[(size_t)local * p.ulen + idx] : (R)0.5;
+        const unsigned o = (unsigned)idx & 3u;
+        if (o == 0) ub = philox_block(p.seed, chain, STREAM_U, idx >> 2);
+        const uint32_t x = o == 0 ? ub.x : o == 1 ? ub.y : o == 2 ? ub.z : ub.w;
+        return u01<R>(x);
+    }
+};
+
 }  // namespace tda

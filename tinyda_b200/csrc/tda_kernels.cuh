@@ -756,22 +756,28 @@ struct Tile {
     }
 
     __device__ void propose_dream() {
-        // proposal.py:811-852; integer draws derive from uniforms as documented in DESIGN.md
+        // proposal.py:811-852; integer draws derive from uniforms as documented in DESIGN.md.
+        // The ~2*delta + 2 + 2d uniforms and d normals of a proposal are consecutive stream entries:
+        // sequential cursors reuse each Philox block for 4 draws.
         const int d = p.d;
         if (tid < TC) {
             const int c = tid, delta = p.dream_delta;
             const long long nslots = (p.prop_kind == TDA_PROP_DREAM) ? p.dream_slots : slots;
             const long long M = (p.prop_kind == TDA_PROP_DREAM) ? nslots * p.Cg : nslots;
-            long long uc = p.ucur[chain0 + c];
+            const bool seq_z = !p.z_round;
+            ChainStreams<R> rs(p, chain0 + c);
+            rs.seek_uniform(p.ucur[chain0 + c]);
+            const long long z0 = t_base * d;
+            if (seq_z) rs.seek_normal(z0);
             long long r1[MAX_DELTA], r2[MAX_DELTA];
             for (int i = 0; i < delta; i++) {
-                R u1 = uniform_at(c, uc++), u2 = uniform_at(c, uc++);
+                R u1 = rs.uniform(), u2 = rs.uniform();
                 long long a = (long long)tfloor(u1 * (R)M); if (a > M - 1) a = M - 1;
                 long long b = (long long)tfloor(u2 * (R)(M - 1)); if (b > M - 2) b = M - 2;
                 if (b >= a) b++;
                 r1[i] = a; r2[i] = b;
             }
-            R ucr = uniform_at(c, uc++);
+            R ucr = rs.uniform();
             int mCR = 0;
             {
                 double cs = 0.0;
@@ -785,26 +791,25 @@ struct Tile {
             const R CR = (R)(mCR + 1) / (R)p.dream_nCR;
             unsigned long long mask = 0ull;
             int card = 0;
-            for (int k = 0; k < d; k++) if (uniform_at(c, uc + k) < CR) { mask |= 1ull << k; card++; }
-            uc += d;
+            for (int k = 0; k < d; k++) if (rs.uniform() < CR) { mask |= 1ull << k; card++; }
             if (card == 0) {
-                int k = (int)tfloor(uniform_at(c, uc++) * (R)d); if (k > d - 1) k = d - 1;
+                int k = (int)tfloor(rs.uniform() * (R)d); if (k > d - 1) k = d - 1;
                 mask = 1ull << k; card = 1;
             }
             const R gam = p.scaling[chain0 + c] * (R)2.38 / tsqrt((R)(2 * delta * card));
-            const long long z0 = t_base * d;
+            const R* ra[MAX_DELTA];
+            const R* rb[MAX_DELTA];
+            for (int i = 0; i < delta; i++) { ra[i] = archive_row(r1[i], c, nslots); rb[i] = archive_row(r2[i], c, nslots); }
             for (int k = 0; k < d; k++) {
-                R e = -p.dream_b + (p.dream_b + p.dream_b) * uniform_at(c, uc + k);
-                R eps = p.dream_b_star * normal_at(c, z0 + k);
-                R dz = (R)0;
+                R e = -p.dream_b + (p.dream_b + p.dream_b) * rs.uniform();
+                R eps = p.dream_b_star * (seq_z ? rs.normal() : normal_at(c, z0 + k));
                 R za = (R)0, zb = (R)0;
-                for (int i = 0; i < delta; i++) { za += archive_row(r1[i], c, nslots)[k]; zb += archive_row(r2[i], c, nslots)[k]; }
-                dz = za - zb;
+                for (int i = 0; i < delta; i++) { za += ra[i][k]; zb += rb[i][k]; }
+                R dz = za - zb;
                 R th = p.lv[0].theta[gi(k, c)];
                 pt[k * TC + c] = ((mask >> k) & 1ull) ? th + (((R)1 + e) * gam * dz + eps) : th;
             }
-            uc += d;
-            p.ucur[chain0 + c] = uc;
+            p.ucur[chain0 + c] = (long long)rs.ui;
         }
         __syncthreads();
     }
