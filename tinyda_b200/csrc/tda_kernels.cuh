@@ -383,28 +383,41 @@ struct Tile {
             __syncthreads();
             if (tid < TC) {
                 const int c = tid, nn = n - 1;
+                // the three scratch arrays never alias: telling the compiler lets it issue the loads of
+                // a sweep ahead of the recurrence (only the divide / FMA chain stays serial)
+                const size_t Cs = (size_t)p.Cs;
+                const R* __restrict__ kfc = kf + chain0 + c;
+                R* __restrict__ cpc = cp + chain0 + c;
+                R* __restrict__ dpc = dp + chain0 + c;
                 const R h2 = (R)1 / ((R)n * (R)n);
-                R k0 = kf[gi(0, c)], k1 = kf[gi(1, c)];
+                R k0 = kfc[0], k1 = kfc[Cs];
                 R diag = k0 + k1;
                 R cprev = -k1 / diag, dprev = h2 / diag;
-                cp[gi(0, c)] = cprev; dp[gi(0, c)] = dprev;
+                cpc[0] = cprev; dpc[0] = dprev;
                 R ki = k1;
+#pragma unroll 4
                 for (int i = 1; i < nn; i++) {
-                    R kn = kf[gi(i + 1, c)];
+                    R kn = kfc[(size_t)(i + 1) * Cs];
                     R a = -ki;
                     diag = (ki + kn) - a * cprev;
                     cprev = -kn / diag;
                     dprev = (h2 - a * dprev) / diag;
-                    cp[gi(i, c)] = cprev; dp[gi(i, c)] = dprev;
+                    cpc[(size_t)i * Cs] = cprev; dpc[(size_t)i * Cs] = dprev;
                     ki = kn;
                 }
                 R u = dprev;     // u[nn-1]
                 const int stride = v.stride;
                 // sensors sit on nodes (s+1)*stride, i.e. unknown index (s+1)*stride-1
                 if ((nn - 1 + 1) % stride == 0) { int s = (nn) / stride - 1; if (s < v.m) v.Fp[gi(s, c)] = u; }
+                int next_sensor = ((nn - 1) / stride) * stride - 1;      // largest sensor index <= nn-2
+#pragma unroll 4
                 for (int i = nn - 2; i >= 0; i--) {
-                    u = dp[gi(i, c)] - cp[gi(i, c)] * u;
-                    if ((i + 1) % stride == 0) { int s = (i + 1) / stride - 1; if (s < v.m) v.Fp[gi(s, c)] = u; }
+                    u = dpc[(size_t)i * Cs] - cpc[(size_t)i * Cs] * u;
+                    if (i == next_sensor) {
+                        int s = (i + 1) / stride - 1;
+                        if (s < v.m) v.Fp[gi(s, c)] = u;
+                        next_sensor -= stride;
+                    }
                 }
                 if (v.lik_kind != TDA_LIK_ADAPTIVE) s_like[tid] = loglike_from_F(l, v.Fp, tid);
             }
