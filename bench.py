@@ -373,7 +373,10 @@ def _other_workload(name, world):
     spec = lower_problem(w["posteriors"], w["proposal"], kw.get("subchain_length"), kw.get("adaptive_error_model"))
     d = spec["d"]
     s = 4
-    if name == "cfg3":     # theta, prior, loglike, F + accept byte
+    if name == "cfg1":     # README linear regression: theta, prior, loglike + accept byte (stats-only history)
+        cfgd = dict(chains=2, iters=12000, bytes_unit=(d + 2) * s + 1, flop_unit=2.0 * d * 100 + 4.0 * d * d,
+                    bound="latency", store="stats")
+    elif name == "cfg3":   # theta, prior, loglike, F + accept byte
         cfgd = dict(chains=1 << 20, iters=100, bytes_unit=(d + 3) * s + 1, flop_unit=120.0, bound="hbm",
                     store="full")
     elif name == "cfg4":
@@ -586,7 +589,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="cfg2 = the headline line (BASELINE.json configs[1]); the others are secondary measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.quick:

@@ -207,6 +207,44 @@ def test_get_samples_matches_reference_layout():
     assert mo["dimension"] == m
 
 
+def test_to_inference_data_builds_the_reference_groups(monkeypatch):
+    """diagnostics.py:6-69: groups posterior / posterior_predictive / qoi / sample_stats with the
+    variables x{i}, obs_{i}, qoi_{i}, prior / likelihood / posterior and dims (chain, draw).
+    arviz and xarray are not installed in this image: two recording stand-ins take their place."""
+    import sys
+    import types
+    xr = types.ModuleType("xarray")
+    az = types.ModuleType("arviz")
+
+    class Dataset:
+        def __init__(self, data_vars, coords):
+            self.data_vars, self.coords = data_vars, coords
+
+    class InferenceData:
+        def __init__(self, **groups):
+            self.groups = groups
+
+    xr.Dataset, az.InferenceData = Dataset, InferenceData
+    monkeypatch.setitem(sys.modules, "xarray", xr)
+    monkeypatch.setitem(sys.modules, "arviz", az)
+    n, d, m = 12, 2, 3
+    rng = np.random.default_rng(4)
+    mk = lambda: LinkSequence(rng.standard_normal((n, d)), rng.standard_normal(n), rng.standard_normal(n),
+                              rng.standard_normal((n, m)), np.ones(n, bool))
+    res = {"sampler": "MH", "n_chains": 3, "iterations": n, "chain_0": mk(), "chain_1": mk(), "chain_2": mk()}
+    idata = tda.to_inference_data(res, burnin=4, parameter_names=["b", "m"])
+    assert set(idata.groups) == {"posterior", "posterior_predictive", "qoi", "sample_stats"}
+    post = idata.groups["posterior"]
+    assert list(post.data_vars) == ["b", "m"]
+    dims, arr = post.data_vars["m"]
+    assert dims == ["chain", "draw"] and arr.shape == (3, n - 4)
+    np.testing.assert_array_equal(arr[1], res["chain_1"].parameters[4:, 1])
+    assert list(idata.groups["posterior_predictive"].data_vars) == ["obs_0", "obs_1", "obs_2"]
+    assert list(idata.groups["sample_stats"].data_vars) == ["prior", "likelihood", "posterior"]
+    assert list(idata.groups["qoi"].data_vars) == ["qoi_0"]
+    assert post.coords["draw"][1] == list(range(n - 4))
+
+
 def test_ess_and_rhat_on_ar1_chains():
     rng = np.random.default_rng(3)
     n, m, rho = 20000, 4, 0.8
