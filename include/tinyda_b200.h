@@ -231,6 +231,16 @@ int tda_tc_gemm_selftest(const float *A, const float *B, int N, float *D, int a_
  * N: multiple of 16, <= 256. */
 int tda_tc16_gemm_selftest(const float *A, const float *B, int N, float *D, int a_in_tmem);
 
+/* Checkpoint / resume across processes.  The reference's chain objects are resumable only in
+ * memory (calling .sample() again, chain.py:78-129); here the complete sampler state -- constants,
+ * the current Links of every level, proposal state (step sizes, adaptation windows, AM moments,
+ * DREAM archive), error-model moments and factors, stream cursors -- can be written to a host blob
+ * and loaded into an engine created with the same configuration; the run continues bit for bit.
+ * The stored history is not part of the blob (fetch it first); the history position restarts at 0. */
+int tda_state_size(tda_engine *e, size_t *bytes);
+int tda_state_save(tda_engine *e, void *host_dst, size_t dst_bytes);
+int tda_state_load(tda_engine *e, const void *host_src, size_t src_bytes);
+
 /* Kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t tda_launch_count(void);
 

@@ -98,3 +98,50 @@ def test_tensor_core_kernel_refuses_what_it_cannot_run():
     e2 = Engine(g2["spec"], 256, dtype="float64", seed=1, store=STORE_STATS, capacity_iterations=2)
     assert e2.kernel() == "generic"
     e2.close()
+
+
+@pytest.mark.parametrize("name,dtype,kernel", [("da_pcn_cfg2", "float32", "tc16"), ("mlda3_aem_linear", "float64", "generic"),
+                                               ("dreamz_adaptive", "float64", "generic"), ("mala_rosenbrock", "float32", "reg"),
+                                               ("am_linear", "float64", "generic")])
+def test_checkpoint_resume_is_exact(name, dtype, kernel):
+    """tda_state_save / tda_state_load: an engine restored from a checkpoint continues the chains
+    bit for bit (constants, Links of every level, proposal and error-model state, stream cursors
+    are all in the blob; the history is not)."""
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    g = golden_io.load(name)
+    spec = g["spec"]
+    store = [STORE_NONE] * (spec["n_levels"] - 1) + [STORE_STATS]
+    C = 256
+    theta0 = np.resize(g["theta0"], (C, g["theta0"].shape[1]))
+    arch = None if g["archive0"] is None else np.resize(g["archive0"], (C,) + g["archive0"].shape[1:])
+    a, b = 7, 9
+
+    def make():
+        e = Engine(spec, C, dtype=dtype, seed=21, store=store, capacity_iterations=a + b, archive0=arch)
+        e.select_kernel(kernel)
+        return e
+
+    e1 = make()
+    e1.init(theta0)
+    e1.run(a)
+    blob = e1.save_state()
+    e1.history_reset()
+    e1.run(b)
+    top = spec["n_levels"] - 1
+    want = (e1.fetch(top, "theta", 0, b), e1.fetch(top, "like", 0, b), e1.get("scaling"), e1.get("cursors"))
+    e1.close()
+    e2 = make()                       # fresh engine: never initialised, state comes from the blob
+    e2.load_state(blob, iterations_done=a)
+    assert e2.kernel() == kernel
+    e2.run(b)
+    got = (e2.fetch(top, "theta", 0, b), e2.fetch(top, "like", 0, b), e2.get("scaling"), e2.get("cursors"))
+    e2.close()
+    for w, x in zip(want, got):
+        assert np.array_equal(w, x)
+    # a blob from a different configuration is refused
+    other = golden_io.load("mh_pcn_diag")
+    e3 = Engine(other["spec"], C, dtype="float64", seed=1, store=STORE_STATS, capacity_iterations=2)
+    from tinyda_b200._lib import EngineError
+    with pytest.raises(EngineError, match="different configuration|too small"):
+        e3.load_state(blob)
+    e3.close()

@@ -29,6 +29,7 @@ EXPORTS = [
     "tda_engine_init", "tda_engine_run", "tda_engine_sync", "tda_fetch", "tda_get", "tda_set",
     "tda_device_buffer", "tda_dream_slots", "tda_fill_streams", "tda_history_reset",
     "tda_select_kernel", "tda_launch_count", "tda_tc_gemm_selftest", "tda_tc16_gemm_selftest",
+    "tda_state_size", "tda_state_save", "tda_state_load",
 ]
 
 
@@ -82,6 +83,9 @@ def _load():
     lib.tda_fill_streams.argtypes = [vp, C.POINTER(C.c_double), i64, C.POINTER(C.c_double), i64]
     lib.tda_history_reset.argtypes = [vp]
     lib.tda_select_kernel.argtypes = [vp, i32]
+    lib.tda_state_size.argtypes = [vp, C.POINTER(sz)]
+    lib.tda_state_save.argtypes = [vp, vp, sz]
+    lib.tda_state_load.argtypes = [vp, vp, sz]
     lib.tda_tc_gemm_selftest.argtypes = [vp, vp, i32, vp, i32, i32]
     lib.tda_tc16_gemm_selftest.argtypes = [vp, vp, i32, vp, i32]
     for name in EXPORTS:

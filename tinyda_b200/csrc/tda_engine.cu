@@ -45,6 +45,7 @@ struct tda_engine {
     virtual int fill_streams(double* z, long long nz, double* u, long long nu) = 0;
     virtual int history_reset() = 0;
     virtual int select_kernel(int which) = 0;
+    virtual int state_io(void* host, size_t bytes, size_t* needed, int load) = 0;
     tda_config cfg;
     int device = 0;
     long long dream_slots = 0;
@@ -98,6 +99,9 @@ template <typename R>
 struct EngineT : tda_engine {
     tda::Params<R> P;
     std::vector<void*> allocs;
+    std::vector<size_t> alloc_bytes;
+    std::vector<char> alloc_is_state;   // 0: history buffer (not part of a checkpoint)
+    bool alloc_history = false;
     int Cs = 0, n_tiles = 0, kt = 0, sm_count = 148;
     size_t smem_bytes = 0;
     bool initialised = false;
@@ -126,6 +130,8 @@ struct EngineT : tda_engine {
         e = cudaMemset(p, 0, bytes);
         if (e != cudaSuccess) return fail(-3, std::string("cudaMemset: ") + cudaGetErrorString(e));
         allocs.push_back(p);
+        alloc_bytes.push_back(bytes);
+        alloc_is_state.push_back(alloc_history ? 0 : 1);
         *out = reinterpret_cast<T*>(p);
         return 0;
     }
@@ -250,10 +256,12 @@ struct EngineT : tda_engine {
                 DALLOC(v.bias_sigma, (size_t)m * m * Cs);
             }
             const size_t cap = (size_t)lc.hist_capacity;
+            alloc_history = true;
             if (lc.store & TDA_STORE_THETA) DALLOC(v.h_theta, cap * d * Cs);
             if (lc.store & TDA_STORE_STATS) { DALLOC(v.h_prior, cap * Cs); DALLOC(v.h_like, cap * Cs); }
             if (lc.store & TDA_STORE_OUTPUT) DALLOC(v.h_F, cap * m * Cs);
             if (lc.store & TDA_STORE_ACCEPT) DALLOC(v.h_acc, cap * Cs);
+            alloc_history = false;
         }
         if (c.mtm_k) {
             const size_t K = (size_t)c.mtm_k;
@@ -558,6 +566,57 @@ struct EngineT : tda_engine {
 
     int select_kernel(int which) override {
         kernel_choice = which;
+        return 0;
+    }
+
+    // Checkpoint: the host-side counters + every device buffer except the history (constants, chain
+    // state of every level, proposal state, stream cursors).  load == 0: engine -> host blob,
+    // load == 1: host blob -> engine (created with the same configuration).
+    struct StateHeader {
+        unsigned long long magic;
+        tda_config cfg;
+        long long t_base, wcount, rec[tda::MAXL], lvl_steps[tda::MAXL], dream_slots;
+        int initialised, n_buffers;
+        unsigned long long payload;
+    };
+    int state_io(void* host, size_t bytes, size_t* needed, int load) override {
+        CUDA_TRY(cudaSetDevice(device));
+        size_t payload = 0;
+        int nb = 0;
+        for (size_t i = 0; i < allocs.size(); i++)
+            if (alloc_is_state[i] && allocs[i] != (void*)stage_theta) { payload += alloc_bytes[i]; nb++; }
+        const size_t total = sizeof(StateHeader) + payload;
+        if (needed) *needed = total;
+        if (!host) return 0;
+        if (bytes < total) return fail(-1, "state: buffer too small");
+        CUDA_TRY(cudaDeviceSynchronize());
+        StateHeader h;
+        char* q = reinterpret_cast<char*>(host) + sizeof(StateHeader);
+        if (!load) {
+            memset(&h, 0, sizeof(h));
+            h.magic = 0x7464615f73746174ull;
+            h.cfg = cfg;
+            h.t_base = P.t_base; h.wcount = P.wcount; h.dream_slots = dream_slots;
+            for (int l = 0; l < tda::MAXL; l++) { h.rec[l] = P.rec[l]; h.lvl_steps[l] = P.lvl_steps[l]; }
+            h.initialised = initialised ? 1 : 0; h.n_buffers = nb; h.payload = payload;
+            memcpy(host, &h, sizeof(h));
+        } else {
+            memcpy(&h, host, sizeof(h));
+            tda_config a = h.cfg, b = cfg;
+            // the history capacity may differ between the engine that saved and the one that loads
+            for (int l = 0; l < TDA_MAX_LEVELS; l++) { a.level[l].hist_capacity = 0; b.level[l].hist_capacity = 0; a.level[l].store = b.level[l].store; }
+            if (h.magic != 0x7464615f73746174ull || h.n_buffers != nb || h.payload != payload || memcmp(&a, &b, sizeof(a)) != 0)
+                return fail(-1, "state: blob was saved by an engine with a different configuration");
+            P.t_base = h.t_base; P.wcount = h.wcount; dream_slots = h.dream_slots;
+            for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = 0; P.lvl_steps[l] = h.lvl_steps[l]; }
+            initialised = h.initialised != 0;
+        }
+        for (size_t i = 0; i < allocs.size(); i++) {
+            if (!alloc_is_state[i] || allocs[i] == (void*)stage_theta) continue;
+            if (!load) CUDA_TRY(cudaMemcpy(q, allocs[i], alloc_bytes[i], cudaMemcpyDeviceToHost));
+            else CUDA_TRY(cudaMemcpy(allocs[i], q, alloc_bytes[i], cudaMemcpyHostToDevice));
+            q += alloc_bytes[i];
+        }
         return 0;
     }
 
@@ -866,5 +925,18 @@ int tda_tc16_gemm_selftest(const float* A, const float* B, int N, float* D, int 
 }
 
 int tda_select_kernel(tda_engine* e, int which) { return e ? e->select_kernel(which) : fail(-1, "null engine"); }
+
+int tda_state_size(tda_engine* e, size_t* bytes) {
+    if (!e || !bytes) return fail(-1, "null argument");
+    return e->state_io(nullptr, 0, bytes, 0);
+}
+int tda_state_save(tda_engine* e, void* host_dst, size_t dst_bytes) {
+    if (!e || !host_dst) return fail(-1, "null argument");
+    return e->state_io(host_dst, dst_bytes, nullptr, 0);
+}
+int tda_state_load(tda_engine* e, const void* host_src, size_t src_bytes) {
+    if (!e || !host_src) return fail(-1, "null argument");
+    return e->state_io(const_cast<void*>(host_src), src_bytes, nullptr, 1);
+}
 
 }  // extern "C"

@@ -205,6 +205,22 @@ class Engine:
         v = np.array([1.0 if on else 0.0])
         check(lib.tda_set(self._h, L.TDA_G_ZROUND, 0, v.ctypes.data_as(C.c_void_p), v.nbytes))
 
+    def save_state(self):
+        """Checkpoint: the whole sampler state (no history) as a bytes-like NumPy array."""
+        n = C.c_size_t(0)
+        check(lib.tda_state_size(self._h, C.byref(n)))
+        blob = np.empty(n.value, dtype=np.uint8)
+        check(lib.tda_state_save(self._h, blob.ctypes.data_as(C.c_void_p), blob.nbytes))
+        self._saved_iterations = self.iterations_done
+        return blob
+
+    def load_state(self, blob, iterations_done=0):
+        """Restores a checkpoint made by an engine with the same configuration; `run` continues the
+        chains exactly where the saved engine stood."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        check(lib.tda_state_load(self._h, blob.ctypes.data_as(C.c_void_p), blob.nbytes))
+        self.iterations_done = int(iterations_done)
+
     def history_reset(self):
         check(lib.tda_history_reset(self._h))
 
