@@ -187,8 +187,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
 
     w, spec = workload_spec()
-    C = args.chains
-    iters = args.iters
+    C = args.chains if args.chains is not None else N_CHAINS_PER_GPU
+    iters = args.iters if args.iters is not None else ITERS_PER_STEP
     dtype = args.dtype
     d = spec["d"]
     rng = np.random.default_rng(1000 + rank)
@@ -411,8 +411,8 @@ def run_other(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     w, spec, cd = _other_workload(args.workload, world)
-    C = args.chains if args.chains != N_CHAINS_PER_GPU else cd["chains"]
-    iters = args.iters if args.iters != ITERS_PER_STEP else cd["iters"]
+    C = args.chains if args.chains is not None else cd["chains"]
+    iters = args.iters if args.iters is not None else cd["iters"]
     L, d = spec["n_levels"], spec["d"]
     shared = int(spec["proposal"]["kind"]) == PROP_DREAM
     rng = np.random.default_rng(1000 + rank)
@@ -584,8 +584,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tc", "tc16"])
-    ap.add_argument("--chains", type=int, default=N_CHAINS_PER_GPU)
-    ap.add_argument("--iters", type=int, default=ITERS_PER_STEP)
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--iters", type=int, default=None, help="finest-level iterations per step (default: the workload's)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--quick", action="store_true")
