@@ -145,3 +145,37 @@ def test_checkpoint_resume_is_exact(name, dtype, kernel):
     with pytest.raises(EngineError, match="different configuration|too small"):
         e3.load_state(blob)
     e3.close()
+
+
+def test_the_binding_stub_of_integration_md_runs_as_written():
+    """INTEGRATION.md section B shows the ctypes stub a tinyDA maintainer would add.  This executes
+    that very code block (only the library path is made absolute) on a small DA problem and
+    compares its output with the package's own engine wrapper."""
+    import os
+    import re
+    import ctypes as C
+    from tinyda_b200 import _lib
+    from tinyda_b200.engine import Engine, STORE_FULL
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n# tinyDA/_b200.py.*?\n(.*?)```", text, re.S).group(1)
+    block = block.replace('C.CDLL("libtinyda_b200.so")', 'C.CDLL(%r)' % _lib.LIB_PATH)
+    ns = {}
+    exec(block, ns)
+
+    g = golden_io.load("da_pcn_small")
+    spec, theta0, iters = g["spec"], g["theta0"], 12
+    # the package's engine fills the POD config; constants are collected from its upload calls
+    ups = []
+    orig = Engine._up
+    Engine._up = lambda self, what, level, arr: (ups.append((what, level, np.array(arr, dtype=np.float64))), orig(self, what, level, arr))[1]
+    try:
+        eng = Engine(spec, theta0.shape[0], dtype="float64", rng="philox", seed=3, store=STORE_FULL, capacity_iterations=iters)
+    finally:
+        Engine._up = orig
+    eng.init(theta0)
+    eng.run(iters)
+    want = eng.fetch(1, "theta")
+    theta = ns["sample_da_b200"](eng.cfg, ups, theta0, iters)
+    eng.close()
+    assert theta.shape == want.shape and np.array_equal(theta, want)
