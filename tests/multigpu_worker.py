@@ -76,6 +76,12 @@ def main(outdir):
     e2.close()
     np.testing.assert_allclose(red["rhat"], full, rtol=1e-9)
     assert red["n_chains"] == C2
+    # ---- ESS reduction over NCCL: sharded == all chains in one process -----------------------------
+    from tinyda_b200.diagnostics import _ess_plain
+    sub = one2[:64, :, :4].astype(np.float64)                  # 64 chains, 4 parameters
+    a, b = parallel.shard_range(64, rank, world)
+    ess = parallel.allreduce_ess(sub[a:b])
+    np.testing.assert_allclose(ess, [_ess_plain(sub[:, :, k]) for k in range(4)], rtol=1e-9)
     dist.barrier()
     dist.destroy_process_group()
 

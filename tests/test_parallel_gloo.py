@@ -21,6 +21,17 @@ def test_shard_ranges_partition_the_chains():
     assert parallel.archive_row_to_chain_slot(17, 5) == (3, 2)
 
 
+def _ar1_chains():
+    rng = np.random.default_rng(5)
+    C, n, d = 6, 4000, 2
+    y = np.zeros((C, n, d))
+    e = rng.standard_normal((C, n, d))
+    for t in range(1, n):
+        y[:, t, 0] = 0.7 * y[:, t - 1, 0] + e[:, t, 0]
+        y[:, t, 1] = 0.95 * y[:, t - 1, 1] + e[:, t, 1]
+    return y
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -42,7 +53,10 @@ def _worker(rank, world, port, q):
         s1 = x[lo:hi].sum(axis=1).T
         s2 = (x[lo:hi] ** 2).sum(axis=1).T
         out = parallel.allreduce_chain_moments(s1, s2, n)
-        q.put((rank, out["rhat"], out["mean"], out["n_chains"]))
+        # ESS over both ranks' chains: AR(1) series, 3 chains per rank
+        y = _ar1_chains()
+        ess = parallel.allreduce_ess(y[lo:hi])
+        q.put((rank, out["rhat"], out["mean"], out["n_chains"], ess))
     finally:
         dist.destroy_process_group()
 
@@ -64,7 +78,14 @@ def test_two_rank_allgather_and_moment_reduction():
     W = x.var(axis=1, ddof=1).mean(axis=0)
     B_over_n = x.mean(axis=1).var(axis=0, ddof=1)
     rhat = np.sqrt(((n - 1) / n * W + B_over_n) / W)
-    for rank, r, mean, m in res:
+    from tinyda_b200.diagnostics import _ess_plain
+    y = _ar1_chains()
+    ess_one = np.array([_ess_plain(y[:, :, k]) for k in range(y.shape[2])])
+    for rank, r, mean, m, ess in res:
         assert m == C
         np.testing.assert_allclose(r, rhat, rtol=1e-12)
         np.testing.assert_allclose(mean, x.mean(axis=(0, 1)), rtol=1e-12)
+        np.testing.assert_allclose(ess, ess_one, rtol=1e-9)          # sharded == single process
+    # and the estimate is right: ESS/N of an AR(1) chain is (1 - rho) / (1 + rho)
+    N = y.shape[0] * y.shape[1]
+    assert abs(ess_one[0] / N - 0.3 / 1.7) < 0.03 and abs(ess_one[1] / N - 0.05 / 1.95) < 0.01

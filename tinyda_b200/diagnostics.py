@@ -118,11 +118,20 @@ def _rhat_plain(x):
 def _ess_plain(x):
     m, n = x.shape
     acov = _autocov(x)
-    chain_var = acov[:, 0] * n / (n - 1.0)
-    mean_var = chain_var.mean()
+    means = x.mean(axis=1)
+    return _ess_from_sums(m, n, acov.sum(axis=0), means.sum(), (means ** 2).sum())
+
+
+def _ess_from_sums(m, n, acov_sum, mean_sum, mean_sq_sum):
+    """Multi-chain ESS (Geyer's initial sequences, as in Stan / ArviZ) from quantities that are
+    plain sums over chains -- so they can be all-reduced across GPUs: acov_sum[t] = sum over chains
+    of the biased autocovariance at lag t, and the sums of the chain means and of their squares."""
+    acov_mean = acov_sum / m
+    mean_var = acov_mean[0] * n / (n - 1.0)
     var_plus = mean_var * (n - 1.0) / n
     if m > 1:
-        var_plus += x.mean(axis=1).var(ddof=1)
+        var_plus += (mean_sq_sum - mean_sum ** 2 / m) / (m - 1.0)
+    acov = acov_mean[None, :]
     rho = np.zeros(n)
     rho[0] = 1.0
     t = 1

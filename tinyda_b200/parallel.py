@@ -122,3 +122,34 @@ def allreduce_chain_moments(sum1, sum2, n_draws):
     W = s_var / m
     var_plus = (n - 1.0) / n * W + B_over_n
     return dict(mean=grand, var_within=W, var_between=B_over_n * n, rhat=np.sqrt(var_plus / W), n_chains=int(m))
+
+
+def allreduce_ess(x_local):
+    """Multi-chain effective sample size per parameter over ALL ranks' chains.  x_local:
+    [n_chains_local, n_draws, d] draws held by this rank.  Each rank reduces its chains to
+    per-parameter sums (autocovariances by FFT, chain means, squared chain means) and one
+    all-reduce of (n_draws + 3) * d numbers finishes the job; the result equals the single-process
+    estimate on the concatenated chains (``diagnostics._ess_plain``, the non-rank-normalised ESS of
+    Stan / ArviZ).  Returns ess[d]."""
+    import torch
+    from .diagnostics import _autocov, _ess_from_sums
+    x = np.asarray(x_local, dtype=np.float64)
+    m, n, d = x.shape
+    pack = np.zeros((d, n + 3))
+    for k in range(d):
+        xk = x[:, :, k]
+        means = xk.mean(axis=1)
+        pack[k, :n] = _autocov(xk).sum(axis=0)
+        pack[k, n] = means.sum()
+        pack[k, n + 1] = (means ** 2).sum()
+        pack[k, n + 2] = m
+    t = torch.from_numpy(pack)
+    dist = _dist()
+    if dist is not None:
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t)
+        t = t.cpu()
+    pack = t.numpy()
+    return np.array([_ess_from_sums(int(round(pack[k, n + 2])), n, pack[k, :n], pack[k, n], pack[k, n + 1])
+                     for k in range(d)])
