@@ -810,15 +810,20 @@ struct Tile {
                 mask = 1ull << k; card = 1;
             }
             const R gam = p.scaling[chain0 + c] * (R)2.38 / tsqrt((R)(2 * delta * card));
-            const R* ra[MAX_DELTA];
-            const R* rb[MAX_DELTA];
-            for (int i = 0; i < delta; i++) { ra[i] = archive_row(r1[i], c, nslots); rb[i] = archive_row(r2[i], c, nslots); }
+            // jump direction sum(Z[r1]) - sum(Z[r2]) first, on its own: the two gathered archive rows of
+            // a chain are scattered 4d-byte reads, and a loop with nothing but loads lets them overlap
+            // (sums kept separately, zt = sum Z[r1], pt = sum Z[r2], like Z_r1 / Z_r2 in proposal.py:818-826)
+            for (int k = 0; k < d; k++) { zt[k * TC + c] = (R)0; pt[k * TC + c] = (R)0; }
+            for (int i = 0; i < delta; i++) {
+                const R* __restrict__ ra = archive_row(r1[i], c, nslots);
+                const R* __restrict__ rb = archive_row(r2[i], c, nslots);
+#pragma unroll 8
+                for (int k = 0; k < d; k++) { zt[k * TC + c] += ra[k]; pt[k * TC + c] += rb[k]; }
+            }
             for (int k = 0; k < d; k++) {
                 R e = -p.dream_b + (p.dream_b + p.dream_b) * rs.uniform();
                 R eps = p.dream_b_star * (seq_z ? rs.normal() : normal_at(c, z0 + k));
-                R za = (R)0, zb = (R)0;
-                for (int i = 0; i < delta; i++) { za += ra[i][k]; zb += rb[i][k]; }
-                R dz = za - zb;
+                R dz = zt[k * TC + c] - pt[k * TC + c];
                 R th = p.lv[0].theta[gi(k, c)];
                 pt[k * TC + c] = ((mask >> k) & 1ull) ? th + (((R)1 + e) * gam * dz + eps) : th;
             }
