@@ -657,12 +657,19 @@ struct Tile {
             }
         }
         if (l == p.L - 1) {
+            // running moments of the finest level; the three arrays never alias, which lets the
+            // read-modify-writes of different elements overlap instead of serialising on each load
             const int d = p.d;
+            const R* __restrict__ th = v.theta;
+            R* __restrict__ s1 = p.sum1;
+            R* __restrict__ s2 = p.sum2;
+#pragma unroll 4
             for (int e = tid; e < d * TC; e += NT) {
                 int k = e / TC, c = e - k * TC;
-                R x = v.theta[gi(k, c)];
-                p.sum1[gi(k, c)] += x;
-                p.sum2[gi(k, c)] += x * x;
+                const size_t o = gi(k, c);
+                R x = th[o];
+                s1[o] += x;
+                s2[o] += x * x;
             }
         }
         rec[l] = r + 1;
