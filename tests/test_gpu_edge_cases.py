@@ -179,3 +179,14 @@ def test_the_binding_stub_of_integration_md_runs_as_written():
     theta = ns["sample_da_b200"](eng.cfg, ups, theta0, iters)
     eng.close()
     assert theta.shape == want.shape and np.array_equal(theta, want)
+
+
+@pytest.mark.parametrize("script,args", [("basic_sampler.py", ["8", "3000"]), ("delayed_acceptance.py", ["512", "40"])])
+def test_example_scripts_run(script, args):
+    """The examples are the reference's notebooks with the import swapped; they must run as written."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", script)] + args, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
