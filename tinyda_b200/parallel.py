@@ -14,6 +14,11 @@ import numpy as np
 
 
 def _dist():
+    # a process group can only exist if the caller has already imported torch: do not pay for the
+    # import (about a second) in single-process use
+    import sys
+    if "torch" not in sys.modules:
+        return None
     try:
         import torch.distributed as dist
     except Exception:
