@@ -161,6 +161,21 @@ def mh_mtm_pcn():
 
 
 @case
+def da_mtm_rwmh():
+    """Delayed Acceptance whose coarse proposal is a MultipleTry random walk (k = 3)."""
+    rng = np.random.default_rng(41)
+    d = 4
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    (Gc, yc), (Gf, yf) = _linear_levels(rng, d, [6, 24], 0.2, prior, perturb=0.02)
+
+    def build(tda):
+        pc = tda.Posterior(prior, tda.GaussianLogLike(yc, 0.04 * np.eye(6)), LinearModel(Gc))
+        pf = tda.Posterior(prior, tda.GaussianLogLike(yf, 0.04 * np.eye(24)), LinearModel(Gf))
+        return [pc, pf], tda.MultipleTry(tda.GaussianRandomWalk(C=0.03 * np.eye(d)), 3), dict(subchain_length=3)
+    return dict(build=build, n_chains=3, iterations=40, seed=42, prior=prior)
+
+
+@case
 def da_pcn_small():
     """cfg2 in miniature: two-level DA, pCN, coarse = strided observation subset, J=3."""
     rng = np.random.default_rng(2)
