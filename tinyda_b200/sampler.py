@@ -160,10 +160,20 @@ def sample(
     if device is None:
         device = parallel.local_device()
     shared = kind == PROP_DREAM
-    eng = Engine(spec, n_local, dtype=dtype, rng=rng, seed=0 if seed is None else seed, store=store,
-                 capacity_iterations=iterations, streams=streams, device=device,
-                 chain_offset=lo, n_chains_global=n_chains if shared else n_local,
-                 archive0=archive0, am_device_refactor=True)
+    from ._lib import EngineError
+    try:
+        eng = Engine(spec, n_local, dtype=dtype, rng=rng, seed=0 if seed is None else seed, store=store,
+                     capacity_iterations=iterations, streams=streams, device=device,
+                     chain_offset=lo, n_chains_global=n_chains if shared else n_local,
+                     archive0=archive0, am_device_refactor=True)
+    except EngineError as exc:
+        if "cudaMalloc" in str(exc):
+            # the reference keeps every Link (with its model output) of every level in host lists;
+            # here that history lives in HBM until it is fetched
+            raise EngineError(str(exc) + " -- the Link history of %d chains x %d iterations does not fit in device "
+                              "memory: pass store_model_output=False and/or store_coarse_chain=False, or "
+                              "sample in several calls" % (n_local, iterations)) from None
+        raise
     if kind == PROP_DREAMZ:
         # per-chain archives live in the same [slot][chain][d] array, indexed by the local chain
         pass
