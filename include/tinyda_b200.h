@@ -102,6 +102,9 @@ typedef struct tda_config {
     int32_t randomize_subchain;         /* DAChain randomize_subchain_length, chain.py:310-321, :369, :525-527 */
     int32_t mtm_k;                      /* > 0: MultipleTry with k tries around the proposal kernel (ray.py:213-354;
                                          * RWMH / AM / pCN kernels, 2 <= k <= 16) */
+    int32_t mtm_include_current;        /* 0 = the reference's k-1 reference points; 1 = the current state is
+                                         * the k-th reference point (Liu et al. 2000; detailed balance)      */
+    int32_t reserved0;
     uint64_t seed;
     int64_t n_chains;                   /* chains on THIS device                       */
     int64_t chain_offset;               /* global index of local chain 0 (Philox key)  */

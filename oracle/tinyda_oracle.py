@@ -282,6 +282,9 @@ class ChainOracle:
         self.k = 0
         self.t = 0
         self.mtm_k = int(self.P.get("mtm_k", 0))
+        # engine extension (default off = the reference): the current state joins the reference
+        # points, as Liu et al. (2000) prescribe
+        self.mtm_include_current = bool(self.P.get("mtm_include_current", 0))
         if self.kind in (PROP_RWMH, PROP_PCN, PROP_AM):
             self.T = np.array(self.P["T"], dtype=np.float64)
         if self.kind == PROP_OWPCN:                              # proposal.py:575-579
@@ -388,7 +391,9 @@ class ChainOracle:
         links = [self._create(0, self._propose_from(c), self.next_sid) for _ in range(k)]
         if self.kind in (PROP_RWMH, PROP_AM):                    # kernel.is_symmetric -> MTM(II)
             q = np.zeros(k)
-        else:
+        elif self.mtm_include_current:                           # MTM(I) of Liu et al.: w(y, x) = pi(y) T(y, x)
+            q = np.array([self._get_q_pcn(l, c) for l in links])
+        else:                                                    # the reference: pi(y) T(x, y), ray.py:292-296
             q = np.array([self._get_q_pcn(c, l) for l in links])
         w = np.array([l.post + qi for l, qi in zip(links, q)])
         w[np.isnan(w)] = -np.inf
@@ -408,9 +413,14 @@ class ChainOracle:
         refs = [self._create(0, self._propose_from(new), 0) for _ in range(self.mtm_k - 1)]
         if self.kind in (PROP_RWMH, PROP_AM):
             q = np.zeros(len(refs))
+        elif self.mtm_include_current:
+            q = np.array([self._get_q_pcn(r, new) for r in refs])
         else:
             q = np.array([self._get_q_pcn(new, r) for r in refs])
         wr = np.array([r.post + qi for r, qi in zip(refs, q)])
+        if self.mtm_include_current:
+            q_old = 0.0 if self.kind in (PROP_RWMH, PROP_AM) else self._get_q_pcn(old, new)
+            wr = np.append(wr, old.post + q_old)
         wr[np.isnan(wr)] = -np.inf
         with np.errstate(over="ignore", invalid="ignore"):
             return np.exp(self._logsumexp(self.mtm_weights) - self._logsumexp(wr))

@@ -122,7 +122,7 @@ struct Params {
     R* sum1;               // [d][Cs] running sum of finest-level states
     R* sum2;               // [d][Cs] running sum of squares
     // MultipleTry (ray.py:213-354): k candidates per base-level step
-    int mtm_k;
+    int mtm_k, mtm_include_current;
     long long* zcur;       // [Cs] normal cursor (consumption depends on the chain's control flow)
     R* mt_theta;           // [k][d][Cs] candidates
     R* mt_prior;           // [k][Cs]

@@ -154,6 +154,7 @@ struct EngineT : tda_engine {
         P.am_device_refactor = c.am_device_refactor;
         P.randomize = c.randomize_subchain;
         P.mtm_k = c.mtm_k;
+        P.mtm_include_current = c.mtm_include_current;
         for (int l = 0; l < TDA_MAX_LEVELS; l++) P.J[l] = c.subchain[l];
         P.C = (int)c.n_chains;
         // padded to whole pairs of 128-chain tiles (the tensor-core kernel processes tile pairs)
@@ -269,7 +270,7 @@ struct EngineT : tda_engine {
             DALLOC(P.mt_theta, K * d * Cs);
             DALLOC(P.mt_prior, K * Cs);
             DALLOC(P.mt_like, K * Cs);
-            DALLOC(P.mt_w, K * Cs);
+            DALLOC(P.mt_w, (K + 1) * Cs);
             if (P.lv[0].need_F) DALLOC(P.mt_F, K * P.lv[0].m * Cs);
             DALLOC(P.mt_y, (size_t)d * Cs);
             DALLOC(P.mt_sel, Cs);

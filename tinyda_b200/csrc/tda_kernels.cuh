@@ -840,9 +840,11 @@ struct Tile {
     }
 
     // ---- MultipleTry (ray.py:213-354) ---------------------------------------------------------------
-    // log q(x, y) of the pCN kernel up to its constant for the tile y in pt -> red-free result in
-    // s_cb (valid for tid < TC); x = src.  Zero for symmetric kernels (MTM(II)).
-    __device__ void mtm_q(const R* src) {
+    // log-density of the pCN kernel up to its constant between the tile in pt and the state src
+    // -> s_cb (valid for tid < TC): q(src -> pt), the direction the reference uses (ray.py:292-296,
+    // :337-342), or q(pt -> src) when `reverse` (the weights w(y, x) = pi(y) T(y, x) of Liu et al.'s
+    // MTM(I), used by the detailed-balance mode).  Zero for symmetric kernels (MTM(II)).
+    __device__ void mtm_q(const R* src, bool reverse) {
         const int d = p.d;
         if (p.prop_kind != TDA_PROP_PCN) {
             if (tid < TC) s_cb[tid] = (R)0;
@@ -852,7 +854,8 @@ struct Tile {
         for (int e = tid; e < d * TC; e += NT) {
             int k = e / TC, c = e - k * TC;
             R s = p.scaling[chain0 + c];
-            zt[e] = pt[e] - tsqrt((R)1 - s * s) * src[gi(k, c)];
+            const R a = tsqrt((R)1 - s * s);
+            zt[e] = reverse ? src[gi(k, c)] - a * pt[e] : pt[e] - a * src[gi(k, c)];
         }
         __syncthreads();
         EpiSsq<R> e;
@@ -884,7 +887,7 @@ struct Tile {
             propose_gaussian();
             mtm_zoff += d;
             eval_level(0);
-            mtm_q(v.theta);
+            mtm_q(v.theta, p.mtm_include_current != 0);
             for (int e = tid; e < d * TC; e += NT) {
                 int k = e / TC, c = e - k * TC;
                 p.mt_theta[((size_t)i * d + k) * p.Cs + chain0 + c] = pt[e];
@@ -939,7 +942,7 @@ struct Tile {
             propose_gaussian();
             mtm_zoff += d;
             eval_level(0);
-            mtm_q(p.mt_y);
+            mtm_q(p.mt_y, p.mtm_include_current != 0);
             if (tid < TC) {
                 const int c = tid;
                 R w = (s_prior[c] + s_like[c]) + s_cb[c];
@@ -949,6 +952,21 @@ struct Tile {
             __syncthreads();
         }
         prop_src = v.theta;
+        int n_ref = K - 1;
+        if (p.mtm_include_current) {
+            // Liu et al. (2000): the current state x is the k-th reference point, weight pi(x) q(y, x)
+            for (int e = tid; e < d * TC; e += NT) pt[e] = v.theta[gi(e / TC, e % TC)];
+            __syncthreads();
+            mtm_q(p.mt_y, true);          // pt = x, src = y: q(x -> y)
+            if (tid < TC) {
+                const int c = tid, g = chain0 + c;
+                R w = (v.prior[g] + v.like[g]) + s_cb[c];
+                if (tisnan(w)) w = -INFINITY;
+                p.mt_w[gi(K - 1, c)] = w;
+            }
+            n_ref = K;
+            __syncthreads();
+        }
         // the chosen candidate becomes the proposal link (chain.py:105)
         for (int e = tid; e < d * TC; e += NT) pt[e] = p.mt_y[gi(e / TC, e % TC)];
         if (v.need_F)
@@ -960,7 +978,7 @@ struct Tile {
             const int c = tid, g = chain0 + c, idx = p.mt_sel[g];
             s_prior[c] = p.mt_prior[gi(idx, c)];
             s_like[c] = p.mt_like[gi(idx, c)];
-            s_ca[c] = s_acc[c] ? (R)0 : texp(p.mt_lse[g] - mtm_logsumexp(p.mt_w, K - 1, c));   // ray.py:350-353
+            s_ca[c] = s_acc[c] ? (R)0 : texp(p.mt_lse[g] - mtm_logsumexp(p.mt_w, n_ref, c));   // ray.py:350-353
             // a chain whose candidates were all invalid draws no reference points (ray.py:321-323)
             p.zcur[g] += s_acc[c] ? (long long)K * d : (long long)(2 * K - 1) * d;
         }

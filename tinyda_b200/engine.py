@@ -64,6 +64,7 @@ class Engine:
         cfg.aem = int(spec.get("aem", 0))
         cfg.randomize_subchain = int(spec.get("randomize", 0))
         cfg.mtm_k = int(prop.get("mtm_k", 0))
+        cfg.mtm_include_current = int(prop.get("mtm_include_current", 0))
         cfg.rng_mode = L.TDA_RNG_INJECTED if rng == "injected" else L.TDA_RNG_PHILOX
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.n_chains = self.C
