@@ -62,7 +62,8 @@ extern "C" {
 #define TDA_PROP_MALA 3     /* MALA                proposal.py:861  */
 #define TDA_PROP_DREAMZ 4   /* DREAMZ              proposal.py:608  */
 #define TDA_PROP_DREAM 5    /* DREAM (shared)      proposal.py:1627 */
-#define TDA_PROP_OWPCN 6    /* OperatorWeightedCrankNicolson proposal.py:515 (non-adaptive) */
+#define TDA_PROP_OWPCN 6    /* OperatorWeightedCrankNicolson proposal.py:515; with adaptive != 0 the operators
+                             * follow each chain's step size through the eigen-decomposition of B     */
 /* likelihood kinds */
 #define TDA_LIK_ISO 0       /* IsotropicGaussianLogLike distributions.py:318 */
 #define TDA_LIK_DIAG 1      /* DiagonalGaussianLogLike  distributions.py:304 */
@@ -152,7 +153,10 @@ typedef struct tda_config {
 #define TDA_UP_DREAM_ARCHIVE0 14 /* [n_chains_global][M0][d]                        */
 #define TDA_UP_AM_FACTORS 15    /* [n_chains][d][d] per-chain T                     */
 #define TDA_UP_PROP_S 16        /* OWPCN: [d][d] state operator, transposed: theta' = theta @ S + z @ T,
-                                 * S = sqrtm(I - scaling*B)^T, T = svd_factor(prior cov) @ sqrtm(scaling*B)^T */
+                                 * S = sqrtm(I - scaling*B)^T, T = svd_factor(prior cov) @ sqrtm(scaling*B)^T.
+                                 * Adaptive OWPCN (B = V diag(lambda) V^T): S = V, T = svd_factor(prior cov) @ V */
+#define TDA_UP_PROP_S2 17       /* adaptive OWPCN: [d][d] V^T                        */
+#define TDA_UP_PROP_LAMBDA 18   /* adaptive OWPCN: [d] eigenvalues of B              */
 
 /* tda_fetch 'field' */
 #define TDA_F_THETA 1           /* [nrec][d][n_chains]   engine dtype               */

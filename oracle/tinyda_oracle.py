@@ -494,6 +494,11 @@ class ChainOracle:
             rate = np.mean(self.accepted[0][-self.period:])
             self.scaling = np.exp(np.log(self.scaling) + self.gamma ** -self.k * (rate - self.alpha_star))
             self.k += 1
+        if self.kind == PROP_OWPCN and self.adaptive and self.t % self.period == 0:   # proposal.py:581-591
+            from scipy.linalg import sqrtm
+            B = np.asarray(self.P["B"], dtype=np.float64)
+            self.state_operator = np.real(sqrtm(np.eye(self.d) - self.scaling * B))
+            self.noise_operator = np.real(sqrtm(self.scaling * B))
         if self.kind == PROP_AM:                                 # proposal.py:502-512
             self.am.update(theta_cur)
             if self.t >= self.am_t0 and self.t % self.period == 0:

@@ -116,6 +116,23 @@ def mh_owpcn():
 
 
 @case
+def mh_owpcn_adaptive():
+    """Operator-weighted pCN with adaptive=True, the way examples/Operator-weighted pCN.ipynb uses it:
+    both operators are re-derived from the adapted step size every period (proposal.py:581-591)."""
+    rng = np.random.default_rng(43)
+    d, m = 5, 12
+    prior = stats.multivariate_normal(np.zeros(d), _exp_cov(d, 0.3))
+    (G, y), = _linear_levels(rng, d, [m], 0.2, prior)
+    Q = rng.standard_normal((d, d))
+    B = 0.6 * (np.eye(d) + 0.3 * (Q @ Q.T) / d)
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.04 * np.eye(m)), LinearModel(G))
+        return [post], tda.OperatorWeightedCrankNicolson(B, scaling=0.05, adaptive=True, period=20), {}
+    return dict(build=build, n_chains=3, iterations=150, seed=44, prior=prior)
+
+
+@case
 def da_owpcn():
     """Two-level DA with the operator-weighted pCN as the coarse proposal."""
     rng = np.random.default_rng(35)

@@ -18,7 +18,8 @@ TDA_RNG_PHILOX, TDA_RNG_INJECTED = 0, 1
 TDA_STORE_THETA, TDA_STORE_STATS, TDA_STORE_OUTPUT, TDA_STORE_ACCEPT = 1, 2, 4, 8
 (TDA_UP_PRIOR_MEAN, TDA_UP_PRIOR_LP, TDA_UP_PRIOR_PREC, TDA_UP_PROP_T, TDA_UP_MODEL_A, TDA_UP_MODEL_B,
  TDA_UP_LIK_DATA, TDA_UP_LIK_VAR, TDA_UP_LIK_PREC, TDA_UP_LIK_COV, TDA_UP_INIT_THETA, TDA_UP_STREAM_Z,
- TDA_UP_STREAM_U, TDA_UP_DREAM_ARCHIVE0, TDA_UP_AM_FACTORS, TDA_UP_PROP_S) = range(1, 17)
+ TDA_UP_STREAM_U, TDA_UP_DREAM_ARCHIVE0, TDA_UP_AM_FACTORS, TDA_UP_PROP_S, TDA_UP_PROP_S2,
+ TDA_UP_PROP_LAMBDA) = range(1, 19)
 TDA_F_THETA, TDA_F_PRIOR, TDA_F_LIKE, TDA_F_OUTPUT, TDA_F_ACCEPT = 1, 2, 3, 4, 5
 (TDA_G_SCALING, TDA_G_ACCEPT_COUNTS, TDA_G_CURSORS, TDA_G_AM_SIGMA, TDA_G_AM_MU, TDA_G_THETA,
  TDA_G_NRECORDS, TDA_G_MOMENTS, TDA_G_ZROUND, TDA_G_TC16_TIMELINE, TDA_G_KERNEL) = range(1, 12)

@@ -97,7 +97,9 @@ struct Params {
     const R* LP;           // [d][ldD]
     const R* Pprec;        // [d][ldD]
     const R* T;            // [d][ldD]  shared proposal factor
-    const R* Sop;          // [d][ldD]  OWPCN state operator (transposed)
+    const R* Sop;          // [d][ldD]  OWPCN state operator (transposed); adaptive OWPCN: V
+    const R* Sop2;         // [d][ldD]  adaptive OWPCN: V^T
+    const R* ow_lambda;    // [d]       adaptive OWPCN: eigenvalues of B
     int ldD;
     R* scaling;            // [Cs]
     uint8_t* win;          // [period][Cs] ring of the last `period` accept flags

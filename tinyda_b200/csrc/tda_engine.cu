@@ -179,7 +179,11 @@ struct EngineT : tda_engine {
         DALLOC(tmp, (size_t)d * P.ldD); P.LP = tmp;
         DALLOC(tmp, (size_t)d * P.ldD); P.Pprec = tmp;
         DALLOC(tmp, (size_t)d * P.ldD); P.T = tmp;
-        if (c.prop_kind == TDA_PROP_OWPCN) { DALLOC(tmp, (size_t)d * P.ldD); P.Sop = tmp; }
+        if (c.prop_kind == TDA_PROP_OWPCN) {
+            DALLOC(tmp, (size_t)d * P.ldD); P.Sop = tmp;
+            DALLOC(tmp, (size_t)d * P.ldD); P.Sop2 = tmp;
+            DALLOC(tmp, d); P.ow_lambda = tmp;
+        }
         DALLOC(P.scaling, Cs);
         DALLOC(P.ucur, Cs);
         DALLOC(P.sum1, (size_t)d * Cs);
@@ -362,6 +366,14 @@ struct EngineT : tda_engine {
             if (!P.Sop) return fail(-1, "upload: proposal has no state operator");
             if ((r = need((size_t)d * d))) return r;
             return put_matrix(P.Sop, host, d, d, P.ldD);
+        case TDA_UP_PROP_S2:
+            if (!P.Sop2) return fail(-1, "upload: proposal has no state operator");
+            if ((r = need((size_t)d * d))) return r;
+            return put_matrix(P.Sop2, host, d, d, P.ldD);
+        case TDA_UP_PROP_LAMBDA:
+            if (!P.ow_lambda) return fail(-1, "upload: proposal has no operator spectrum");
+            if ((r = need((size_t)d))) return r;
+            return put_matrix(P.ow_lambda, host, 1, d, d);
         case TDA_UP_MODEL_A: {
             const tda::LevelP<R>& v = P.lv[level];
             const int ncols = (v.model_kind == TDA_MODEL_POISSON1D) ? v.n_grid : v.m;
@@ -801,8 +813,6 @@ int validate(const tda_config* c) {
     if (c->mtm_k && c->prop_kind != TDA_PROP_RWMH && c->prop_kind != TDA_PROP_AM && c->prop_kind != TDA_PROP_PCN)
         return fail(-1, "MultipleTry needs an RWMH, AM or pCN kernel");
     if (c->mtm_k && (c->randomize_subchain || c->aem == 2)) return fail(-1, "MultipleTry cannot be combined with randomize_subchain / state-dependent AEM");
-    if (c->prop_kind == TDA_PROP_OWPCN && c->adaptive)
-        return fail(-1, "operator-weighted pCN: the operators depend on the step size; adaptive scaling is not supported");
     if (c->aem < 0 || c->aem > 2) return fail(-1, "aem must be 0, 1 (state-independent) or 2 (state-dependent)");
     if (c->aem == 2 && c->n_levels != 2) return fail(-1, "the state-dependent error model is a two-level method");
     if (c->aem == 2 && c->prop_kind != TDA_PROP_RWMH && c->prop_kind != TDA_PROP_AM && c->prop_kind != TDA_PROP_PCN)

@@ -168,6 +168,15 @@ struct EpiTile {           // shared-memory tile: t[n][c] (+)= v
 };
 
 template <typename R>
+struct EpiOw {             // adaptive OWPCN: t[n][c] = sqrt(s_c lam_n) t[n][c] + sqrt(1 - s_c lam_n) v
+    R* t; const R* s; const R* lam;
+    __device__ __forceinline__ void operator()(int, int c, int n, R v) {
+        const R sl = s[c] * lam[n];
+        t[n * TC + c] = tsqrt(sl) * t[n * TC + c] + tsqrt((R)1 - sl) * v;
+    }
+};
+
+template <typename R>
 struct EpiStore {          // out[n][c] = v
     R* out; int Cs; int chain0;
     __device__ __forceinline__ void operator()(int, int c, int n, R v) {
@@ -696,7 +705,25 @@ struct Tile {
             else { s_ca[tid] = (R)1; s_cb[tid] = s; }
         }
         __syncthreads();
-        if (p.prop_kind == TDA_PROP_OWPCN) {
+        if (p.prop_kind == TDA_PROP_OWPCN && p.adaptive) {
+            // per-chain step size s: S = V diag(sqrt(1 - s lam)) V^T, N = V diag(sqrt(s lam)) V^T
+            // (proposal.py:578-591)  ->  theta' = [ sqrt(s lam) (V^T xi) + sqrt(1 - s lam) (V^T theta) ] V^T
+            EpiTile<R> e1; e1.t = pt; e1.accumulate = 0;
+            tile_gemm<R>(zt, (const R*)nullptr, p.T, d, d, p.ldD, bs, KB, e1);        // V^T xi
+            __syncthreads();
+            for (int e = tid; e < d * TC; e += NT) {
+                int k = e / TC, c = e - k * TC;
+                zt[e] = prop_src[gi(k, c)];
+            }
+            __syncthreads();
+            EpiOw<R> e2; e2.t = pt; e2.s = s_cb; e2.lam = p.ow_lambda;
+            tile_gemm<R>(zt, (const R*)nullptr, p.Sop, d, d, p.ldD, bs, KB, e2);      // combine with V^T theta
+            __syncthreads();
+            for (int e = tid; e < d * TC; e += NT) zt[e] = pt[e];
+            __syncthreads();
+            EpiTile<R> e3; e3.t = pt; e3.accumulate = 0;
+            tile_gemm<R>(zt, (const R*)nullptr, p.Sop2, d, d, p.ldD, bs, KB, e3);     // back: @ V^T
+        } else if (p.prop_kind == TDA_PROP_OWPCN) {
             // theta' = S theta + N xi  (proposal.py:593-598) = theta @ S^T + z @ (T N^T)
             EpiTile<R> e1; e1.t = pt; e1.accumulate = 0;
             tile_gemm<R>(zt, (const R*)nullptr, p.T, d, d, p.ldD, bs, KB, e1);

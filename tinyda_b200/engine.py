@@ -124,6 +124,9 @@ class Engine:
             self._up(L.TDA_UP_PROP_T, 0, prop["T"])
         if "S" in prop:
             self._up(L.TDA_UP_PROP_S, 0, prop["S"])
+        if "S2" in prop:
+            self._up(L.TDA_UP_PROP_S2, 0, prop["S2"])
+            self._up(L.TDA_UP_PROP_LAMBDA, 0, prop["ow_lambda"])
         for l, lv in enumerate(spec["levels"]):
             mk = int(lv["model"]["kind"])
             if mk in (MODEL_LINEAR, MODEL_POISSON1D):

@@ -84,7 +84,8 @@ class OperatorWeightedCrankNicolson(CrankNicolson):
     """Operator-weighted pCN (Law 2014), tinyDA/proposal.py:515-605:
     theta' = sqrtm(I - scaling*B) theta + sqrtm(scaling*B) xi,  xi ~ N(0, prior cov).  The two matrix
     square roots are taken once on the host (proposal.py:578-579); with adaptive=True the reference
-    re-takes them per chain every period from the adapted step size, which is not lowered."""
+    re-takes them every period from the adapted step size (proposal.py:581-591) and the device
+    follows each chain's step size through the eigen-decomposition of a symmetric B."""
 
     kind = PROP_OWPCN
 
@@ -94,19 +95,28 @@ class OperatorWeightedCrankNicolson(CrankNicolson):
 
     def lower(self, prior):
         from scipy.linalg import sqrtm
-        if self.adaptive:
-            raise NotImplementedError("adaptive OperatorWeightedCrankNicolson is not lowered to the device")
         d = prior["cov"].shape[0]
         B = np.atleast_2d(np.asarray(self.B, dtype=np.float64))
-        state_operator = np.real(sqrtm(np.eye(d) - self.scaling * B))
-        noise_operator = np.real(sqrtm(self.scaling * B))
         T_prior = svd_factor(prior["cov"])
         out = self._common()
-        out["state_operator"] = state_operator
-        out["noise_operator"] = noise_operator
+        out["B"] = B
         out["T_prior"] = T_prior
-        out["T"] = T_prior @ noise_operator.T        # z @ T = noise_operator @ (z @ T_prior)
-        out["S"] = state_operator.T                  # theta @ S = state_operator @ theta
+        out["state_operator"] = np.real(sqrtm(np.eye(d) - self.scaling * B))      # proposal.py:578-579
+        out["noise_operator"] = np.real(sqrtm(self.scaling * B))
+        if self.adaptive:
+            # the reference re-takes both matrix square roots from every chain's adapted step size
+            # (proposal.py:581-591); for a symmetric B = V diag(lam) V^T they are
+            # V diag(sqrt(1 - s lam)) V^T and V diag(sqrt(s lam)) V^T, which the device forms per chain
+            if not np.allclose(B, B.T, rtol=1e-12, atol=1e-14):
+                raise NotImplementedError("adaptive OperatorWeightedCrankNicolson needs a symmetric operator B")
+            lam, V = np.linalg.eigh(B)
+            out["ow_lambda"] = lam
+            out["T"] = T_prior @ V                       # z @ T = V^T xi
+            out["S"] = V                                 # theta @ S = V^T theta
+            out["S2"] = V.T
+        else:
+            out["T"] = T_prior @ out["noise_operator"].T     # z @ T = noise_operator @ (z @ T_prior)
+            out["S"] = out["state_operator"].T               # theta @ S = state_operator @ theta
         return out
 
 
