@@ -190,3 +190,33 @@ def test_example_scripts_run(script, args):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "examples", script)] + args, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+
+
+def test_create_link_and_get_map_run_on_the_device():
+    """Posterior.create_link (posterior.py:78-110) and get_MAP / get_ML (utils.py:204-269), used by
+    three of the reference's example notebooks for `initial_parameters=MAP`: Links come from the
+    CUDA engine; on a linear-Gaussian problem the MAP is the closed-form posterior mean and the ML
+    estimate the least-squares solution."""
+    import scipy.stats as stats
+    import tinyda_b200 as tda
+    from tinyda_b200.workloads import conjugate_posterior
+    from oracle import tinyda_oracle as orc
+    rng = np.random.default_rng(3)
+    d, m, sig2 = 5, 12, 0.05
+    prior = stats.multivariate_normal(0.1 * np.ones(d), np.eye(d) + 0.2)
+    G = rng.standard_normal((m, d))
+    y = G @ prior.rvs(random_state=rng) + np.sqrt(sig2) * rng.standard_normal(m)
+    post = tda.Posterior(prior, tda.GaussianLogLike(y, sig2 * np.eye(m)), tda.LinearModel(G, offset=0.3 * np.ones(m)))
+    x = prior.rvs(random_state=rng)
+    link = post.create_link(x)
+    np.testing.assert_allclose(link.prior, prior.logpdf(x), rtol=1e-12)
+    np.testing.assert_allclose(link.model_output, G @ x + 0.3, rtol=1e-12)
+    np.testing.assert_allclose(link.likelihood, -0.5 * np.sum((G @ x + 0.3 - y) ** 2) / sig2, rtol=1e-12)
+    assert link.posterior == link.prior + link.likelihood
+    mu, S = conjugate_posterior(G, y - 0.3, sig2, prior)
+    MAP = tda.get_MAP(post, initial_parameters=np.zeros(d))
+    np.testing.assert_allclose(MAP, mu, atol=2e-4)
+    ML = tda.get_ML(post, initial_parameters=np.zeros(d), method="L-BFGS-B")
+    np.testing.assert_allclose(ML, np.linalg.lstsq(G, y - 0.3, rcond=None)[0], atol=2e-4)
+    MAP2 = tda.get_MAP(post, method="differential_evolution", bounds=[(-4, 4)] * d, seed=1, maxiter=300, tol=1e-10)
+    np.testing.assert_allclose(MAP2, mu, atol=5e-3)

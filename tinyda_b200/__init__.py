@@ -17,4 +17,5 @@ from .proposal import (Proposal, GaussianRandomWalk, CrankNicolson, OperatorWeig
                        AdaptiveMetropolis, MALA, DREAMZ, DREAM, SingleDreamZ, MultipleTry)
 from .lowering import lower_problem
 from .sampler import sample
+from .utils import get_MAP, get_ML, LinkEvaluator
 from .diagnostics import to_inference_data, get_samples, to_xarray, ess_bulk, rhat

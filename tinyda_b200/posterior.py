@@ -37,6 +37,20 @@ class Posterior:
         self.likelihood = likelihood
         self.model = model
 
+    def create_link(self, parameters):
+        """posterior.py:78-110: the Link of one parameter vector -- log-prior, model output and
+        log-likelihood -- evaluated by the CUDA engine (the fused stage that also creates the
+        chains' initial Links).  The per-sample calls of the reference's chain loop never come
+        here: they run inside the kernels."""
+        from .utils import LinkEvaluator
+        from .link import Link
+        ev = getattr(self, "_evaluator", None)
+        if ev is None:
+            ev = self._evaluator = LinkEvaluator(self, batch=1)
+        parameters = np.atleast_1d(np.asarray(parameters, dtype=np.float64))
+        prior, out, like = ev(parameters[None, :])
+        return Link(parameters, float(prior[0]), out[0], float(like[0]), None)
+
     def lower(self):
         if not is_device_model(self.model):
             raise TypeError(
