@@ -166,7 +166,10 @@ def make(name):
             hists.append(h)
             consumed.append([S.nz, S.nu])
             if defn.get("archive"):
-                archive0.append(np.array(ch.proposal.Z[:spec["proposal"]["M0"]]))
+                base = ch.proposal                      # MLDA nests the base proposal (proposal.py:1395-1440)
+                while not hasattr(base, "Z"):
+                    base = base.proposal
+                archive0.append(np.array(base.Z[:spec["proposal"]["M0"]]))
         consumed = np.array(consumed)
         if defn.get("archive"):
             out["archive0"] = np.array(archive0)

@@ -364,6 +364,22 @@ def mlda3_aem_linear():
 
 
 @case
+def mlda3_dreamz():
+    """3-level MLDA whose base proposal is adaptive DREAM(Z), as in the reference's
+    examples/Multilevel Delayed Acceptance.ipynb (there with M0 = 1000 and an LHS archive)."""
+    rng = np.random.default_rng(45)
+    d = 5
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    lv = _linear_levels(rng, d, [5, 10, 20], 0.2, prior, perturb=0.02)
+
+    def build(tda):
+        posts = [tda.Posterior(prior, tda.GaussianLogLike(y, 0.04 * np.eye(len(y))), LinearModel(G))
+                 for G, y in lv]
+        return posts, tda.DREAMZ(M0=12, delta=1, nCR=3, adaptive=True, period=10), dict(subchain_length=[3, 2])
+    return dict(build=build, n_chains=3, iterations=40, seed=46, prior=prior, archive=True)
+
+
+@case
 def mlda4_aem_poisson():
     """cfg4 in miniature: 4-level MLDA + state-independent AEM on the 1-D Poisson inversion."""
     rng = np.random.default_rng(4)

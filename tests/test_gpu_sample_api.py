@@ -69,6 +69,7 @@ def test_store_coarse_chain_false_returns_none_like_the_reference():
                                         ("da_sdaem_pcn", "float64"), ("da_randomize_pcn", "float64"),
                                         ("da_randomize_aem", "float64"), ("dreamz_adaptive", "float64"),
                                         ("mh_owpcn", "float64"), ("da_owpcn", "float64"), ("mh_owpcn_adaptive", "float64"),
+                                        ("mlda3_dreamz", "float64"),
                                         ("mh_mtm_rwmh", "float64"), ("mh_mtm_pcn", "float64")])
 def test_philox_mode_equals_oracle_fed_the_exported_streams(name, dtype):
     """Production RNG mode: the engine's in-kernel Philox draws, exported with tda_fill_streams
@@ -319,3 +320,27 @@ def test_mtm_detailed_balance_mode_equals_the_oracle(name):
     np.testing.assert_allclose(np.transpose(eng.fetch(0, "theta"), (2, 0, 1)), out[0]["theta"], rtol=1e-10, atol=1e-12)
     assert np.array_equal(eng.get("cursors").T, np.array([[ch.S.nz, ch.S.nu] for ch in chains]))
     eng.close()
+
+
+def test_mlda_notebook_configuration_runs_through_sample():
+    """examples/Multilevel Delayed Acceptance.ipynb as written: three levels, DREAMZ(M0=1000, delta=1,
+    Z_method='lhs', adaptive=True) as the base proposal, subchain_length=5, initial_parameters=MAP."""
+    import scipy.stats as stats
+    import tinyda_b200 as tda
+    rng = np.random.default_rng(11)
+    d = 4
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    G = rng.standard_normal((32, d)) / 2
+    y = G @ prior.rvs(random_state=rng) + 0.1 * rng.standard_normal(32)
+    posts = [tda.Posterior(prior, tda.GaussianLogLike(y[::s], 0.01 * np.eye(len(y[::s]))), tda.LinearModel(G[::s]))
+             for s in (4, 2, 1)]
+    MAP = tda.get_MAP(posts[2], initial_parameters=np.zeros(d))
+    prop = tda.DREAMZ(M0=1000, delta=1, Z_method="lhs", adaptive=True)
+    res = tda.sample(posts, prop, iterations=300, n_chains=2, initial_parameters=MAP, subchain_length=5, seed=2)
+    assert res["sampler"] == "MLDA" and res["levels"] == 3 and res["subchain_lengths"] == [5, 5]
+    s = tda.get_samples(res, "parameters", level=2, burnin=50)
+    pooled = np.concatenate([s["chain_0"], s["chain_1"]])
+    Spost = np.linalg.inv(np.eye(d) + G.T @ G / 0.01)
+    mu = Spost @ (G.T @ y / 0.01)
+    assert np.all(np.abs(pooled.mean(axis=0) - mu) < 6 * np.sqrt(np.diag(Spost)))
+    assert len(res["chain_l0_0"]) == 300 * 25 and len(res["chain_l2_1"]) == 301

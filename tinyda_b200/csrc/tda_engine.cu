@@ -507,6 +507,12 @@ struct EngineT : tda_engine {
             if (iterations > to_boundary)
                 return fail(-1, "run: AdaptiveMetropolis with host refactoring must stop at period boundaries");
         }
+        if (tda::is_dream(P.prop_kind)) {
+            long long base_steps = iterations;
+            for (int l = 0; l + 1 < L; l++) base_steps *= P.J[l];
+            if (dream_slots + base_steps > P.dream_cap)
+                return fail(-1, "run: the DREAM(Z) archive (dream_capacity slots) cannot hold one row per base-level step of this run");
+        }
         if (kernel_choice == 2 && !tc_eligible()) return fail(-1, "run: tensor-core DA kernel does not support this configuration");
         if (kernel_choice == 3 && !tc16.eligible(cfg, P)) return fail(-1, "run: fp16-split tensor-core DA kernel does not support this configuration");
         if (kernel_choice == 4 && !reg_eligible()) return fail(-1, "run: register-resident kernel does not support this configuration");
@@ -801,8 +807,8 @@ int validate(const tda_config* c) {
     for (int l = 0; l + 1 < c->n_levels; l++)
         if (c->subchain[l] < 1) return fail(-1, "subchain lengths must be >= 1");
     if (c->prop_kind < TDA_PROP_RWMH || c->prop_kind > TDA_PROP_OWPCN) return fail(-1, "unknown proposal kind");
-    if ((c->prop_kind == TDA_PROP_MALA || tda::is_dream(c->prop_kind)) && c->n_levels != 1)
-        return fail(-1, "MALA / DREAM(Z) are single-level proposals in this engine");
+    if ((c->prop_kind == TDA_PROP_MALA || c->prop_kind == TDA_PROP_DREAM) && c->n_levels != 1)
+        return fail(-1, "MALA / DREAM (shared archive) are single-level proposals in this engine");
     if (tda::is_dream(c->prop_kind)) {
         if (c->dream_delta < 1 || c->dream_delta > tda::MAX_DELTA) return fail(-1, "DREAM delta out of range (1..8)");
         if (c->dream_M0 < 2 || c->dream_capacity < c->dream_M0) return fail(-1, "DREAM archive capacity too small");
@@ -817,6 +823,8 @@ int validate(const tda_config* c) {
     if (c->aem == 2 && c->n_levels != 2) return fail(-1, "the state-dependent error model is a two-level method");
     if (c->aem == 2 && c->prop_kind != TDA_PROP_RWMH && c->prop_kind != TDA_PROP_AM && c->prop_kind != TDA_PROP_PCN)
         return fail(-1, "the state-dependent error model needs a symmetric proposal or pCN");
+    if (c->randomize_subchain && tda::is_dream(c->prop_kind))
+        return fail(-1, "randomize_subchain needs a proposal with a fixed number of uniform draws per step");
     if (c->randomize_subchain && (c->n_levels != 2 || c->subchain[0] < 2))
         return fail(-1, "randomize_subchain needs two levels and a subchain length > 1");
     for (int l = 0; l < c->n_levels; l++) {

@@ -72,14 +72,19 @@ def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_mo
             raise ValueError("randomize_subchain_length is a two-level (Delayed Acceptance) option")
         if J[0] == 1:                                                # chain.py:311-312
             raise ValueError("Randomize subchain length requires a subchain_length > 1.")
+        if prop["kind"] in (PROP_DREAMZ, PROP_DREAM):
+            raise NotImplementedError("randomize_subchain_length with a DREAM(Z) base proposal is not lowered "
+                                      "(the index draw is read ahead of a fixed number of uniforms per step)")
         randomize = 1
     if prop["kind"] == PROP_MALA:
         if L != 1:
             raise NotImplementedError("MALA is lowered for single-level sampling only")
         if levels[0]["model"]["kind"] not in (MODEL_LINEAR, MODEL_ROSENBROCK):
             raise TypeError("MALA needs a model with an analytic gradient")
-    if prop["kind"] in (PROP_DREAMZ, PROP_DREAM) and L != 1:
-        raise NotImplementedError("DREAM(Z) is lowered for single-level sampling only")
+    if prop["kind"] == PROP_DREAM and L != 1:
+        # the shared archive needs a grid-wide boundary after every base-level step
+        raise NotImplementedError("DREAM with the shared archive is lowered for single-level sampling only "
+                                  "(use DREAMZ as the base proposal of DA / MLDA)")
     return dict(n_levels=L, d=d, J=J, aem=aem, randomize=randomize, prior=prior, levels=levels,
                 proposal=prop)
 

@@ -177,12 +177,27 @@ class DREAMZ(GaussianRandomWalk):
         self.period = period
 
     def lower(self, prior):
-        if self.Z_method != "random":
-            raise NotImplementedError("only Z_method='random' is lowered to the device")
+        if self.Z_method not in ("random", "lhs"):
+            raise ValueError("Z_method must be 'random' or 'lhs'")
         out = self._common()
         out.update(M0=int(self.M), delta=int(self.delta), b=float(self.b), b_star=float(self.b_star),
                    nCR=int(self.nCR))
         return out
+
+    def initial_archive(self, prior, rng):
+        """The chain's initial archive Z (proposal.py:756-788): M0 prior draws, or for
+        Z_method='lhs' a Latin hypercube pushed through the prior's marginal normal quantiles (the
+        reference's fallback for a multivariate normal prior, which has no .ppf)."""
+        import scipy.stats as stats
+        d = np.atleast_1d(prior.mean).shape[0]
+        if self.Z_method == "lhs":
+            Z = stats.qmc.LatinHypercube(d=d, seed=rng).random(n=int(self.M))
+            var = np.diag(np.atleast_2d(prior.cov))
+            mean = np.atleast_1d(prior.mean)
+            for i in range(d):
+                Z[:, i] = stats.norm(loc=mean[i], scale=np.sqrt(var[i])).ppf(Z[:, i])
+            return Z
+        return np.atleast_2d(prior.rvs(int(self.M), random_state=rng)).reshape(int(self.M), -1)
 
 
 class DREAM(DREAMZ):

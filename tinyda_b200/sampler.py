@@ -144,8 +144,8 @@ def sample(
             archive0 = np.asarray(initial_archive, dtype=np.float64)
         else:                                                           # proposal.py:788, per chain
             host_rng = np.random.default_rng(None if seed is None else [int(seed), 11])
-            archive0 = np.stack([np.atleast_2d(posteriors[0].prior.rvs(M0, random_state=host_rng)).reshape(M0, -1)
-                                 for _ in range(n_chains)])
+            base = proposal.kernel if hasattr(proposal, "kernel") else proposal
+            archive0 = np.stack([base.initial_archive(posteriors[0].prior, host_rng) for _ in range(n_chains)])
         if kind == PROP_DREAMZ:
             archive0 = archive0[lo:hi]
 
