@@ -21,6 +21,12 @@
 //   Tile::sd_terms / aem_update_sd   state-dependent error model chain.py:446-473, :501-522;
 //                          utils.py:190-201; distributions.py:427-446; proposal.py:364-369
 //   Tile::draw_promoted / snapshot_promoted   randomize_subchain_length chain.py:369, :525-527
+//   Tile::mtm_step / mtm_q / mtm_logsumexp    MultipleTry ray.py:279-354 (k candidate Links, the
+//                          choice, k-1 reference Links, ratio of summed weights)
+//   Tile::propose_gaussian (OWPCN branches)   OperatorWeightedCrankNicolson proposal.py:575-598
+//   Tile::propose_dream + the crossover part of Tile::adapt   DREAMZ proposal.py:790-852
+//   Tile::loglike_adaptive_tile, the cooperative factorisation in Tile::push_bias
+//                          AdaptiveGaussianLogLike distributions.py:385-446
 #pragma once
 #include "tda_common.cuh"
 
