@@ -344,3 +344,51 @@ def test_mlda_notebook_configuration_runs_through_sample():
     mu = Spost @ (G.T @ y / 0.01)
     assert np.all(np.abs(pooled.mean(axis=0) - mu) < 6 * np.sqrt(np.diag(Spost)))
     assert len(res["chain_l0_0"]) == 300 * 25 and len(res["chain_l2_1"]) == 301
+
+
+@pytest.mark.parametrize("config", ["basic_am", "basic_pcn_adaptive", "da_aem_am", "da_aem_pcn_adaptive", "mtm_pcn_adaptive",
+                                    "owpcn_adaptive_map", "mlda_am"])
+def test_reference_notebook_configurations_run(config):
+    """Every proposal / option combination the reference's example notebooks offer (commented-in
+    alternatives included) runs through sample() and yields finite, moving chains."""
+    import warnings
+    import scipy.stats as stats
+    import tinyda_b200 as tda
+    rng = np.random.default_rng(5)
+    d, m = 4, 16
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    G = rng.standard_normal((m, d)) / 2
+    y = G @ prior.rvs(random_state=rng) + 0.1 * rng.standard_normal(m)
+    cov = 0.01 * np.eye(m)
+    fine = tda.Posterior(prior, tda.GaussianLogLike(y, cov), tda.LinearModel(G))
+    coarse_adaptive = tda.Posterior(prior, tda.AdaptiveGaussianLogLike(y, cov), tda.LinearModel(G + 0.02 * rng.standard_normal((m, d))))
+    am = tda.AdaptiveMetropolis(C0=0.01 * np.eye(d), t0=100, sd=None, epsilon=1e-6)
+    kw, posts = {}, fine
+    if config == "basic_am":
+        prop = am
+    elif config == "basic_pcn_adaptive":
+        prop = tda.CrankNicolson(scaling=0.1, adaptive=True)
+    elif config in ("da_aem_am", "da_aem_pcn_adaptive"):
+        posts = [coarse_adaptive, fine]
+        prop = am if config == "da_aem_am" else tda.CrankNicolson(scaling=0.1, adaptive=True)
+        kw = dict(subchain_length=5, adaptive_error_model="state-independent", initial_parameters=tda.get_MAP(fine, initial_parameters=np.zeros(d)))
+    elif config == "mtm_pcn_adaptive":
+        with pytest.warns(UserWarning, match="can be unstable"):
+            prop = tda.MultipleTry(tda.CrankNicolson(scaling=0.1, adaptive=True), 3)
+    elif config == "owpcn_adaptive_map":
+        H_inv = np.linalg.inv(np.eye(d) + G.T @ G / 0.01)          # prior-preconditioned inverse Hessian, as in the notebook
+        prop = tda.OperatorWeightedCrankNicolson(H_inv, adaptive=True)
+        kw = dict(initial_parameters=tda.get_MAP(fine, initial_parameters=np.zeros(d)), force_sequential=True)
+    else:
+        posts = [tda.Posterior(prior, tda.GaussianLogLike(y[::s], 0.01 * np.eye(len(y[::s]))), tda.LinearModel(G[::s])) for s in (4, 2, 1)]
+        prop = am
+        kw = dict(subchain_length=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = tda.sample(posts, prop, iterations=250, n_chains=2, seed=3, **kw)
+    level = {"MH": None, "DA": "fine", "MLDA": 2}[res["sampler"]]
+    s = tda.get_samples(res, "parameters", level=level if level is not None else "fine", burnin=50)
+    for c in range(2):
+        x = s["chain_%d" % c]
+        assert np.isfinite(x).all() and x.shape == (201, d)
+        assert np.unique(x[:, 0]).size > 10          # the chain moves
