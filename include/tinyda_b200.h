@@ -155,6 +155,8 @@ typedef struct tda_config {
 #define TDA_UP_PROP_S 16        /* OWPCN: [d][d] state operator, transposed: theta' = theta @ S + z @ T,
                                  * S = sqrtm(I - scaling*B)^T, T = svd_factor(prior cov) @ sqrtm(scaling*B)^T.
                                  * Adaptive OWPCN (B = V diag(lambda) V^T): S = V, T = svd_factor(prior cov) @ V */
+#define TDA_PROP_INDEP 7    /* IndependenceSampler proposal.py:64 with a multivariate normal q: upload its SVD factor
+                             * as TDA_UP_PROP_T, its whitening matrix as TDA_UP_PROP_S, its mean as TDA_UP_PROP_LAMBDA */
 #define TDA_UP_PROP_S2 17       /* adaptive OWPCN: [d][d] V^T                        */
 #define TDA_UP_PROP_LAMBDA 18   /* adaptive OWPCN: [d] eigenvalues of B              */
 

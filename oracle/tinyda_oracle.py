@@ -28,13 +28,13 @@ Reference map (file:line are into /root/reference/tinyDA/):
   randomize_subchain_length            chain.py:310-321, :369-375, :525-527
   ChainOracle._mtm_propose / _mtm_acceptance   MultipleTry ray.py:213-354
   proposals            proposal.py:132-258 (RWMH), 261-369 (pCN), 372-512 (AM),
-                       515-605 (operator-weighted pCN), 608-852 (DREAMZ), 861-1005 (MALA),
+                       64-131 (IndependenceSampler), 515-605 (operator-weighted pCN), 608-852 (DREAMZ), 861-1005 (MALA),
                        1627-1656 + ray.py:366-384 (DREAM)
 """
 import numpy as np
 
 # ---- kinds (kept numerically identical to include/tinyda_b200.h) -------------------------
-PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM, PROP_OWPCN = 0, 1, 2, 3, 4, 5, 6
+PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM, PROP_OWPCN, PROP_INDEP = 0, 1, 2, 3, 4, 5, 6, 7
 LIK_ISO, LIK_DIAG, LIK_DENSE, LIK_ADAPTIVE = 0, 1, 2, 3
 MODEL_LINEAR, MODEL_ROSENBROCK, MODEL_POISSON1D = 0, 1, 2
 
@@ -285,7 +285,7 @@ class ChainOracle:
         # engine extension (default off = the reference): the current state joins the reference
         # points, as Liu et al. (2000) prescribe
         self.mtm_include_current = bool(self.P.get("mtm_include_current", 0))
-        if self.kind in (PROP_RWMH, PROP_PCN, PROP_AM):
+        if self.kind in (PROP_RWMH, PROP_PCN, PROP_AM, PROP_INDEP):
             self.T = np.array(self.P["T"], dtype=np.float64)
         if self.kind == PROP_OWPCN:                              # proposal.py:575-579
             self.state_operator = np.array(self.P["state_operator"], dtype=np.float64)
@@ -438,6 +438,8 @@ class ChainOracle:
         if self.kind == PROP_PCN:                                # proposal.py:349-355
             T = svd_factor(self.prior["cov"]) if self.svd_per_proposal else self.T
             return np.sqrt(1 - self.scaling ** 2) * c.theta + self.scaling * (self.S.normals(d) @ T)
+        if self.kind == PROP_INDEP:                              # proposal.py:117-119: q.rvs(1)
+            return np.asarray(self.P["q_mean"], dtype=np.float64) + self.S.normals(d) @ self.T
         if self.kind == PROP_OWPCN:                              # proposal.py:593-598
             return np.dot(self.state_operator, c.theta) + np.dot(self.noise_operator, self.S.normals(d) @ self.T)
         if self.kind == PROP_MALA:                               # proposal.py:948-959
@@ -476,6 +478,11 @@ class ChainOracle:
     def _acceptance(self, new, old):
         if self.mtm_k:
             return self._mtm_acceptance(new, old)
+        if self.kind == PROP_INDEP:                              # proposal.py:121-131 (no NaN guard there)
+            mu, LP = np.asarray(self.P["q_mean"]), np.asarray(self.P["S"])
+            logq = lambda st: -0.5 * np.sum(np.square((st.theta - mu) @ LP))     # constant cancels
+            with np.errstate(over="ignore", invalid="ignore"):
+                return np.exp(new.post - old.post + logq(old) - logq(new))
         if np.isnan(new.post):                                   # proposal.py:254, 358, 963
             return 0.0
         with np.errstate(over="ignore"):

@@ -99,6 +99,39 @@ def mh_pcn_diag():
     return dict(build=build, n_chains=3, iterations=130, seed=32, prior=prior)
 
 
+class _NormalQ:
+    """A multivariate normal q for IndependenceSampler whose draws go through
+    np.random.multivariate_normal (so that the golden harness can inject them); the reference only
+    asks for .rvs() and .logpdf(), the device lowering for .mean and .cov."""
+
+    def __init__(self, mean, cov):
+        self.mean, self.cov = np.asarray(mean, dtype=np.float64), np.asarray(cov, dtype=np.float64)
+        self._frozen = stats.multivariate_normal(self.mean, self.cov)
+
+    def rvs(self, size=1):
+        return np.array([np.random.multivariate_normal(self.mean, self.cov) for _ in range(size)])
+
+    def logpdf(self, x):
+        return self._frozen.logpdf(x)
+
+
+@case
+def mh_independence():
+    """IndependenceSampler (proposal.py:64-131) with a normal q roughly matched to the posterior."""
+    rng = np.random.default_rng(47)
+    d, m = 3, 8
+    prior = stats.multivariate_normal(np.zeros(d), np.eye(d))
+    (G, y), = _linear_levels(rng, d, [m], 0.4, prior)
+    S = np.linalg.inv(np.eye(d) + G.T @ G / 0.16)
+    mu = S @ (G.T @ y / 0.16)
+    q = _NormalQ(mu + 0.1, 1.8 * S + 0.02 * np.eye(d))
+
+    def build(tda):
+        post = tda.Posterior(prior, tda.GaussianLogLike(y, 0.16 * np.eye(m)), LinearModel(G))
+        return [post], tda.IndependenceSampler(q), {}
+    return dict(build=build, n_chains=3, iterations=150, seed=48, prior=prior)
+
+
 @case
 def mh_owpcn():
     """Operator-weighted pCN (proposal.py:515-605): state and noise operators from sqrtm."""

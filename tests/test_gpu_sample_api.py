@@ -69,7 +69,7 @@ def test_store_coarse_chain_false_returns_none_like_the_reference():
                                         ("da_sdaem_pcn", "float64"), ("da_randomize_pcn", "float64"),
                                         ("da_randomize_aem", "float64"), ("dreamz_adaptive", "float64"),
                                         ("mh_owpcn", "float64"), ("da_owpcn", "float64"), ("mh_owpcn_adaptive", "float64"),
-                                        ("mlda3_dreamz", "float64"),
+                                        ("mlda3_dreamz", "float64"), ("mh_independence", "float64"),
                                         ("mh_mtm_rwmh", "float64"), ("mh_mtm_pcn", "float64")])
 def test_philox_mode_equals_oracle_fed_the_exported_streams(name, dtype):
     """Production RNG mode: the engine's in-kernel Philox draws, exported with tda_fill_streams

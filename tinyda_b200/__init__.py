@@ -13,7 +13,7 @@ from .distributions import (GaussianLogLike, AdaptiveGaussianLogLike, AdaptiveLo
                             IsotropicGaussianLogLike)
 from .posterior import Posterior
 from .link import Link, LinkSequence
-from .proposal import (Proposal, GaussianRandomWalk, CrankNicolson, OperatorWeightedCrankNicolson,
+from .proposal import (Proposal, IndependenceSampler, GaussianRandomWalk, CrankNicolson, OperatorWeightedCrankNicolson,
                        AdaptiveMetropolis, MALA, DREAMZ, DREAM, SingleDreamZ, MultipleTry)
 from .lowering import lower_problem
 from .sampler import sample

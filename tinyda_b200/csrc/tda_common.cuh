@@ -111,6 +111,7 @@ struct Params {
     R* am_mu;              // [d][Cs]
     R* am_sigma;           // [d][d][Cs]
     R* am_T;               // [d][d][Cs]  per-chain factor
+    R* qcur;               // [Cs] IndependenceSampler: log q (up to its constant) of the current state
     R* grad;               // [d][Cs] MALA: gradient at the current state
     R* gradp;              // [d][Cs] MALA: gradient at the proposal
     R* archive;            // DREAM: [cap][Cg][d]

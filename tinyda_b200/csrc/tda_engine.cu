@@ -179,6 +179,11 @@ struct EngineT : tda_engine {
         DALLOC(tmp, (size_t)d * P.ldD); P.LP = tmp;
         DALLOC(tmp, (size_t)d * P.ldD); P.Pprec = tmp;
         DALLOC(tmp, (size_t)d * P.ldD); P.T = tmp;
+        if (c.prop_kind == TDA_PROP_INDEP) {
+            DALLOC(tmp, (size_t)d * P.ldD); P.Sop = tmp;
+            DALLOC(tmp, d); P.ow_lambda = tmp;
+            DALLOC(P.qcur, Cs);
+        }
         if (c.prop_kind == TDA_PROP_OWPCN) {
             DALLOC(tmp, (size_t)d * P.ldD); P.Sop = tmp;
             DALLOC(tmp, (size_t)d * P.ldD); P.Sop2 = tmp;
@@ -806,9 +811,10 @@ int validate(const tda_config* c) {
     if (c->n_chains < 1) return fail(-1, "n_chains must be positive");
     for (int l = 0; l + 1 < c->n_levels; l++)
         if (c->subchain[l] < 1) return fail(-1, "subchain lengths must be >= 1");
-    if (c->prop_kind < TDA_PROP_RWMH || c->prop_kind > TDA_PROP_OWPCN) return fail(-1, "unknown proposal kind");
-    if ((c->prop_kind == TDA_PROP_MALA || c->prop_kind == TDA_PROP_DREAM) && c->n_levels != 1)
-        return fail(-1, "MALA / DREAM (shared archive) are single-level proposals in this engine");
+    if (c->prop_kind < TDA_PROP_RWMH || c->prop_kind > TDA_PROP_INDEP) return fail(-1, "unknown proposal kind");
+    if ((c->prop_kind == TDA_PROP_MALA || c->prop_kind == TDA_PROP_DREAM || c->prop_kind == TDA_PROP_INDEP) && c->n_levels != 1)
+        return fail(-1, "MALA / DREAM (shared archive) / IndependenceSampler are single-level proposals in this engine");
+    if (c->prop_kind == TDA_PROP_INDEP && (c->adaptive || c->mtm_k)) return fail(-1, "IndependenceSampler is neither adaptive nor a MultipleTry kernel");
     if (tda::is_dream(c->prop_kind)) {
         if (c->dream_delta < 1 || c->dream_delta > tda::MAX_DELTA) return fail(-1, "DREAM delta out of range (1..8)");
         if (c->dream_M0 < 2 || c->dream_capacity < c->dream_M0) return fail(-1, "DREAM archive capacity too small");

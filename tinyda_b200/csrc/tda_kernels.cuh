@@ -136,6 +136,12 @@ struct EpiCombine {        // theta' = a_c * theta_c + b_c * xi   -> proposal ti
 };
 
 template <typename R>
+struct EpiAffine {         // independence proposal: pt[n][c] = mu[n] + v
+    R* pt; const R* mu;
+    __device__ __forceinline__ void operator()(int, int c, int n, R v) { pt[n * TC + c] = mu[n] + v; }
+};
+
+template <typename R>
 struct EpiLinear {         // F = v + b; optional store; residual reduction for ISO / DIAG
     const R* b; const R* data; const R* var; R* Fp; int Cs; int chain0; int lik_kind; int need_F;
     R ps[RM];
@@ -711,7 +717,11 @@ struct Tile {
             else { s_ca[tid] = (R)1; s_cb[tid] = s; }
         }
         __syncthreads();
-        if (p.prop_kind == TDA_PROP_OWPCN && p.adaptive) {
+        if (p.prop_kind == TDA_PROP_INDEP) {
+            // q.rvs(): mu_q + z @ T_q, independent of the current state (proposal.py:117-119)
+            EpiAffine<R> e; e.pt = pt; e.mu = p.ow_lambda;
+            tile_gemm<R>(zt, (const R*)nullptr, p.T, d, d, p.ldD, bs, KB, e);
+        } else if (p.prop_kind == TDA_PROP_OWPCN && p.adaptive) {
             // per-chain step size s: S = V diag(sqrt(1 - s lam)) V^T, N = V diag(sqrt(s lam)) V^T
             // (proposal.py:578-591)  ->  theta' = [ sqrt(s lam) (V^T xi) + sqrt(1 - s lam) (V^T theta) ] V^T
             EpiTile<R> e1; e1.t = pt; e1.accumulate = 0;
@@ -869,6 +879,15 @@ struct Tile {
             }
             p.ucur[chain0 + c] = (long long)rs.ui;
         }
+        __syncthreads();
+    }
+
+    // log q(pt) of the IndependenceSampler's normal q, up to its constant -> s_cb (tid < TC)
+    __device__ void indep_logq() {
+        EpiSsq<R> e;
+        tile_gemm<R>(pt, p.ow_lambda, p.Sop, p.d, p.d, p.ldD, bs, KB, e);
+        R tot = reduce_cols(e.ps[0], e.ps[1]);
+        if (tid < TC) s_cb[tid] = (R)-0.5 * tot;
         __syncthreads();
     }
 
@@ -1030,6 +1049,7 @@ struct Tile {
             eval_level(0);
         }
         if (p.prop_kind == TDA_PROP_MALA) mala_gradient(p.gradp);
+        if (p.prop_kind == TDA_PROP_INDEP) indep_logq();
         if (tid < TC) {
             const int c = tid, g = chain0 + c;
             R pr = s_prior[c], lk = s_like[c];
@@ -1037,6 +1057,7 @@ struct Tile {
             R x;
             if (is_pcn_like(p.prop_kind)) x = lk - lk0;
             else x = (pr + lk) - (pr0 + lk0);
+            if (p.prop_kind == TDA_PROP_INDEP) x = x + p.qcur[g] - s_cb[c];     // proposal.py:121-127
             if (p.prop_kind == TDA_PROP_MALA) {
                 R s = p.scaling[g];
                 R qxy = (R)0, qyx = (R)0;
@@ -1059,6 +1080,7 @@ struct Tile {
             s_acc[c] = acc;
             if (acc) {
                 v.prior[g] = pr; v.like[g] = lk;
+                if (p.prop_kind == TDA_PROP_INDEP) p.qcur[g] = s_cb[c];
                 v.sid[g] = (int)(t_base + 1);
                 v.n_acc[g] += 1;
                 v.acc_sub[g] += 1;
@@ -1362,6 +1384,11 @@ struct Tile {
                     for (int a = l + 1; a < L; a++) v.sv_F[a][gi(k, c)] = f;
                 }
             if (l == 0 && p.prop_kind == TDA_PROP_MALA) { __syncthreads(); mala_gradient(p.grad); }
+            if (l == 0 && p.prop_kind == TDA_PROP_INDEP) {
+                __syncthreads();
+                indep_logq();
+                if (tid < TC) p.qcur[chain0 + tid] = s_cb[tid];
+            }
             __syncthreads();
         }
         if (p.prop_kind == TDA_PROP_AM)

@@ -125,6 +125,8 @@ class Engine:
             self._up(L.TDA_UP_PROP_T, 0, prop["T"])
         if "S" in prop:
             self._up(L.TDA_UP_PROP_S, 0, prop["S"])
+        if "S2" not in prop and "ow_lambda" in prop:
+            self._up(L.TDA_UP_PROP_LAMBDA, 0, prop["ow_lambda"])
         if "S2" in prop:
             self._up(L.TDA_UP_PROP_S2, 0, prop["S2"])
             self._up(L.TDA_UP_PROP_LAMBDA, 0, prop["ow_lambda"])

@@ -8,7 +8,7 @@ import numpy as np
 
 from .posterior import Posterior, lower_prior
 from .proposal import (PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM,
-                       GaussianRandomWalk, MultipleTry)
+                       GaussianRandomWalk, MultipleTry, IndependenceSampler, PROP_INDEP)
 from .distributions import LIK_ADAPTIVE
 from .models import MODEL_LINEAR, MODEL_ROSENBROCK
 
@@ -23,7 +23,7 @@ def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_mo
     L = len(posteriors)
     if L < 1 or L > MAX_LEVELS:
         raise ValueError("the engine supports 1..%d levels" % MAX_LEVELS)
-    if not isinstance(proposal, (GaussianRandomWalk, MultipleTry)):
+    if not isinstance(proposal, (GaussianRandomWalk, MultipleTry, IndependenceSampler)):
         raise TypeError("proposal %s cannot be lowered to the device engine"
                         % type(proposal).__name__)
     prior = lower_prior(posteriors[0].prior)
@@ -81,6 +81,8 @@ def lower_problem(posteriors, proposal, subchain_lengths=None, adaptive_error_mo
             raise NotImplementedError("MALA is lowered for single-level sampling only")
         if levels[0]["model"]["kind"] not in (MODEL_LINEAR, MODEL_ROSENBROCK):
             raise TypeError("MALA needs a model with an analytic gradient")
+    if prop["kind"] == PROP_INDEP and L != 1:
+        raise NotImplementedError("IndependenceSampler is lowered for single-level sampling only")
     if prop["kind"] == PROP_DREAM and L != 1:
         # the shared archive needs a grid-wide boundary after every base-level step
         raise NotImplementedError("DREAM with the shared archive is lowered for single-level sampling only "

@@ -10,7 +10,7 @@ in per-chain device arrays and these objects only describe the kernel to run.
 """
 import numpy as np
 
-PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM, PROP_OWPCN = 0, 1, 2, 3, 4, 5, 6
+PROP_RWMH, PROP_PCN, PROP_AM, PROP_MALA, PROP_DREAMZ, PROP_DREAM, PROP_OWPCN, PROP_INDEP = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 def svd_factor(C):
@@ -36,6 +36,37 @@ def _check_square(C, name):
 
 class Proposal:
     is_symmetric = False
+
+
+class IndependenceSampler(Proposal):
+    """Independence sampler (tinyDA/proposal.py:64-131): proposals are draws of a fixed distribution
+    q, acceptance exp(pi(y) - pi(x) + log q(x) - log q(y)).  The reference takes any object with
+    .rvs() / .logpdf(); the device needs a multivariate normal q (a scipy frozen
+    multivariate_normal, or any object that also exposes .mean and .cov)."""
+
+    is_symmetric = False
+    adaptive = False
+    kind = PROP_INDEP
+
+    def __init__(self, q):
+        self.q = q
+        try:                                            # proposal.py:102-105
+            self.q.logpdf(self.q.rvs(1))
+        except AttributeError:
+            raise
+
+    def lower(self, prior):
+        import scipy.stats as stats
+        if not (hasattr(self.q, "mean") and hasattr(self.q, "cov")):
+            raise TypeError("the device engine needs a multivariate normal proposal distribution q "
+                            "(an object with .mean and .cov); there is no CPU fallback")
+        mean = np.atleast_1d(np.asarray(self.q.mean, dtype=np.float64))
+        cov = np.atleast_2d(np.asarray(self.q.cov, dtype=np.float64))
+        if mean.shape[0] != prior["mean"].shape[0]:
+            raise ValueError("q has a different dimension than the prior")
+        co = stats.multivariate_normal(mean, cov).cov_object       # scipy's own whitening, as in logpdf
+        return dict(kind=self.kind, scaling=1.0, adaptive=False, gamma=1.01, period=100, alpha_star=0.24,
+                    T=svd_factor(cov), S=np.ascontiguousarray(co._LP), ow_lambda=mean, q_mean=mean, q_cov=cov)
 
 
 class GaussianRandomWalk(Proposal):
