@@ -392,3 +392,29 @@ def test_reference_notebook_configurations_run(config):
         x = s["chain_%d" % c]
         assert np.isfinite(x).all() and x.shape == (201, d)
         assert np.unique(x[:, 0]).size > 10          # the chain moves
+
+
+def test_sample_defaults_on_cfg2_run_on_the_tensor_core_kernel():
+    """The reference's own call -- tda.sample([coarse, fine], pCN, iterations, n_chains,
+    subsampling_rate) with its default storage (coarse chain kept, Link.model_output kept) -- takes the
+    tcgen05 kernel in float32 mode and returns complete Links at both levels."""
+    import tinyda_b200 as tda
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da()
+    C, iters, J = 256, 8, 10
+    res, eng = tda.sample(w["posteriors"], w["proposal"], iters, n_chains=C, subsampling_rate=J, seed=3,
+                          dtype="float32", return_engine=True)
+    assert eng.kernel() == "tc16"
+    assert res["sampler"] == "DA" and res["iterations"] == iters + 1 and res["subchain_length"] == J
+    coarse, fine = res["chain_coarse_5"], res["chain_fine_5"]
+    assert len(coarse) == J * iters and len(fine) == iters + 1
+    idx = np.arange(0, 1024, 8)
+    for seq, G, y in ((coarse, w["G"][idx], w["y"][idx]), (fine, w["G"], w["y"])):
+        for link in (seq[0], seq[len(seq) // 2], seq[-1]):
+            th = np.asarray(link.parameters, dtype=np.float64)
+            F = G @ th
+            np.testing.assert_allclose(link.model_output, F, rtol=1e-4, atol=1e-5 * np.abs(F).max())
+            np.testing.assert_allclose(link.likelihood, -0.5 * ((F - y) ** 2).sum() / w["sigma2"], rtol=2e-4, atol=2e-2)
+            np.testing.assert_allclose(link.prior, w["prior"].logpdf(th), rtol=2e-4, atol=2e-2)
+            np.testing.assert_allclose(link.posterior, link.prior + link.likelihood, rtol=1e-6)
+    eng.close()

@@ -67,7 +67,7 @@ def test_fp16_split_gemm_matches_fp64(a_in_tmem, N):
 KERNELS = ["tc", "tc16"]
 
 
-def _cfg2_engine(C, kernel, seed=9, rng="philox", streams=None, iters=30, theta0=None, chain_offset=0):
+def _cfg2_engine(C, kernel, seed=9, rng="philox", streams=None, iters=30, theta0=None, chain_offset=0, store=None):
     from tinyda_b200 import lower_problem
     from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
     from tinyda_b200.workloads import cfg2_da
@@ -75,7 +75,8 @@ def _cfg2_engine(C, kernel, seed=9, rng="philox", streams=None, iters=30, theta0
     spec = lower_problem(w["posteriors"], w["proposal"], 10)
     if theta0 is None:
         theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1))
-    eng = Engine(spec, C, dtype="float32", rng=rng, seed=seed, streams=streams, store=[STORE_NONE, STORE_STATS],
+    eng = Engine(spec, C, dtype="float32", rng=rng, seed=seed, streams=streams,
+                 store=[STORE_NONE, STORE_STATS] if store is None else store,
                  capacity_iterations=iters, chain_offset=chain_offset)
     eng.select_kernel(kernel)
     eng.init(theta0)
@@ -208,3 +209,79 @@ def test_tc_kernel_conjugate_posterior_full_shape(kernel):
     rc, rf = _da_conjugate_check(kernel, 1024, 0.004, 3000, 3000)
     rc2, rf2 = _da_conjugate_check(kernel, 256, 0.02, 1500, 3000)
     assert rc > rc2          # the smaller step accepts more often
+
+
+# ---- tc16 with the reference's default storage: chain_coarse_i and Link.model_output ---------------
+def _link_fields(eng, level):
+    f = {k: eng.fetch(level, k).astype(np.float64) for k in ("theta", "prior", "like", "output")}
+    f["accept"] = eng.fetch(level, "accept")
+    return f
+
+
+def test_tc16_full_storage_is_consistent_and_does_not_change_the_chain():
+    """tda.sample's defaults (store_coarse_chain=True, Link.model_output kept, sampler.py:421-436) on the
+    fp16-split kernel: the kernel records the coarse parameters, log-likelihood and accept flag of every
+    coarse step; Link.prior of the coarse records and Link.model_output of both levels are rebuilt from
+    the recorded parameters when fetched.  Every record must be a consistent Link (posterior.py:78-110),
+    and storing more must not move the chain by a bit."""
+    from tinyda_b200.engine import STORE_FULL
+    C, iters, J = 512, 12, 10
+    a, w = _cfg2_engine(C, "tc16", iters=iters, store=[STORE_FULL, STORE_FULL])
+    b, _ = _cfg2_engine(C, "tc16", iters=iters)
+    assert a.kernel() == "tc16"
+    a.run(5); a.run(7)                       # two launches: the pending-record range must extend
+    b.run(iters)
+    assert np.array_equal(a.fetch(1, "theta"), b.fetch(1, "theta"))
+    assert np.array_equal(a.fetch(1, "like"), b.fetch(1, "like"))
+    assert np.array_equal(a.fetch(1, "accept"), b.fetch(1, "accept"))
+    assert list(a.n_records()[:2]) == [J * iters, iters + 1]
+    G, y, s2, prior = w["G"], w["y"], w["sigma2"], w["prior"]
+    idx = np.arange(0, 1024, 8)
+    for level, (Gl, yl) in enumerate([(G[idx], y[idx]), (G, y)]):
+        f = _link_fields(a, level)
+        th = np.transpose(f["theta"], (0, 2, 1))                    # [rec, chain, d]
+        F = np.transpose(f["output"], (0, 2, 1))                    # [rec, chain, m]
+        F_ref = th @ Gl.T
+        assert np.abs(F - F_ref).max() < 1e-5 * np.abs(F_ref).max()
+        like_ref = -0.5 * ((F_ref - yl) ** 2).sum(axis=2) / s2
+        np.testing.assert_allclose(f["like"], like_ref, rtol=2e-4, atol=2e-2)
+        prior_ref = prior.logpdf(th.reshape(-1, 64)).reshape(th.shape[:2])
+        np.testing.assert_allclose(f["prior"], prior_ref, rtol=2e-4, atol=2e-2)
+    # coarse accept flags describe the recorded coarse states: a rejected step repeats the previous record
+    f0 = _link_fields(a, 0)
+    rej = f0["accept"][1:] == 0
+    same = (f0["theta"][1:] == f0["theta"][:-1]).all(axis=1)
+    within = (np.arange(1, J * iters) % J != 0)[:, None]             # not the first step of a subchain
+    assert np.array_equal((rej & within), (same & within))
+    acc = a.get("accept_counts")
+    assert np.array_equal(acc[0], f0["accept"].sum(axis=0))
+
+
+def test_tc16_full_storage_agrees_with_generic_kernel_and_alternates_with_it():
+    from tinyda_b200.engine import STORE_FULL
+    C, iters, J = 512, 10, 10
+    a, w = _cfg2_engine(C, "tc16", iters=2 * iters, store=[STORE_FULL, STORE_FULL])
+    b, _ = _cfg2_engine(C, "generic", iters=2 * iters, store=[STORE_FULL, STORE_FULL])
+    b.set_z_round(True)
+    a.run(iters)
+    b.run(iters)
+    fa, fb = _link_fields(a, 0), _link_fields(b, 0)
+    ok = (fa["accept"] == fb["accept"]).all(axis=0) & (a.fetch(1, "accept") == b.fetch(1, "accept")).all(axis=0)
+    assert ok.mean() > 0.6
+    for k, tol in (("theta", 2e-3), ("output", 2e-3)):
+        scale = np.abs(fb[k]).max()
+        assert np.abs(fa[k][:, :, ok] - fb[k][:, :, ok]).max() < tol * scale, k
+    for k in ("prior", "like"):
+        np.testing.assert_allclose(fa[k][:, ok], fb[k][:, ok], rtol=1e-3, atol=0.3)
+    # the generic kernel continues the tc16 run on the same buffers: its records carry the model
+    # output of the current state, which tc16 does not keep -- the engine rebuilds it before the launch
+    a.select_kernel("generic")
+    a.set_z_round(True)
+    a.run(iters)
+    G = w["G"]
+    idx = np.arange(0, 1024, 8)
+    for level, Gl in enumerate([G[idx], G]):
+        th = np.transpose(a.fetch(level, "theta").astype(np.float64), (0, 2, 1))
+        F = np.transpose(a.fetch(level, "output").astype(np.float64), (0, 2, 1))
+        F_ref = th @ Gl.T
+        assert np.abs(F - F_ref).max() < 1e-5 * np.abs(F_ref).max(), level

@@ -720,6 +720,24 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     if (acc) { like_c = like_p; acc_any = 1; nacc_c++; }
                     t16_warp_arrive(reqB, lane);           // A_theta current, xi consumed
                     if (dbg_on) dbg[5] = clock64();
+                    // ---- coarse-level record (chain_coarse_i, sampler.py:421-436): the state after this
+                    // step with its log-likelihood and accept flag; Link.prior / Link.model_output of
+                    // these records are filled from the stored parameters when they are first fetched
+                    // (engine: fill_lazy_history) ----
+                    if (l0.store) {
+                        const long long r0 = p.rec[0] + (long long)it * J + j;
+                        if (r0 < l0.hist_cap) {
+                            if (l0.store & TDA_STORE_THETA) {
+                                float* dst = t16_opaque(l0.h_theta + (size_t)r0 * T16_K * cs + off0);
+#pragma unroll
+                                for (int k = 0; k < T16_HK; k++) __stcs(dst + k * cs, th[k] * th_unscale);
+                            }
+                            if (h == 0) {
+                                if (l0.store & TDA_STORE_STATS) __stcs(l0.h_like + (size_t)r0 * cs + g, like_c);
+                                if (l0.store & TDA_STORE_ACCEPT) l0.h_acc[(size_t)r0 * cs + g] = (uint8_t)acc;
+                            }
+                        }
+                    }
                 }
                 // ---- fine level: F_f = theta @ G_f^T streamed in 64-column chunks, then theta @ LP ----
                 float u2 = 0.0f;
@@ -876,7 +894,10 @@ struct DaTc16State<float> {
             if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
         if (c.level[0].m > T16_MAX_MC || (c.level[0].m % 16) != 0) return false;
         if (c.level[1].m > T16_MAX_MF || (c.level[1].m % T16_CH) != 0) return false;
-        if (c.level[0].store != 0 || (c.level[1].store & TDA_STORE_OUTPUT)) return false;
+        // Link.prior of the coarse records and Link.model_output of both levels are rebuilt from the
+        // stored parameters when first fetched (engine: fill_lazy_history): they need the parameters
+        if ((c.level[0].store & (TDA_STORE_STATS | TDA_STORE_OUTPUT)) && !(c.level[0].store & TDA_STORE_THETA)) return false;
+        if ((c.level[1].store & TDA_STORE_OUTPUT) && !(c.level[1].store & TDA_STORE_THETA)) return false;
         if ((P.Cs % 256) != 0) return false;
         if (!(c.scaling > 0.0 && c.scaling < 1.0)) return false;
         return true;

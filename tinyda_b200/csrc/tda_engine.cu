@@ -95,6 +95,55 @@ __global__ void init_theta_kernel(const double* __restrict__ src, int C, int d, 
     }
 }
 
+// Derived Link fields of history records written by the tensor-core DA kernel, which stores the
+// parameters, the log-likelihood and the accept flag of a record only:
+//   mode 0  Link.model_output  F[r][n][c] = b[n] + sum_k theta[r][k][c] * A[k][n]   (posterior.py:95-105, LinearModel)
+//   mode 1  Link.prior         prior[r][c] = -0.5 * (logconst + |(theta[r][:, c] - mu) @ LP|^2)   (posterior.py:92)
+// One thread = one (record, chain): the parameter row sits in registers, the operator comes through
+// the read-only cache at warp-uniform addresses, stores are coalesced (lane = chain).  Runs when the
+// fields are first fetched, i.e. next to a PCIe copy of the same records, never inside the sampling loop.
+template <typename R, int D>
+__global__ void __launch_bounds__(256) hist_fill_kernel(const R* __restrict__ theta, const R* __restrict__ W, int ldW, int ncol,
+                                                        const R* __restrict__ off, const R* __restrict__ mu, R* __restrict__ out,
+                                                        int Cs, int mode, R logconst) {
+    const int cblocks = Cs / 256;
+    const size_t r = blockIdx.x / cblocks;
+    const int c = (int)(blockIdx.x - r * cblocks) * 256 + threadIdx.x;
+    const R* th_src = theta + r * (size_t)D * Cs + c;
+    R th[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) th[k] = th_src[(size_t)k * Cs] - (mu ? mu[k] : (R)0);
+    R ssq = 0;
+    R* dst = out + (mode == 0 ? r * (size_t)ncol * Cs : r * (size_t)Cs) + c;
+    for (int n = 0; n < ncol; n += 4) {
+        R a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        if (n + 3 < ncol) {
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const R* w = W + (size_t)k * ldW + n;
+                a0 = fma(th[k], __ldg(w), a0); a1 = fma(th[k], __ldg(w + 1), a1);
+                a2 = fma(th[k], __ldg(w + 2), a2); a3 = fma(th[k], __ldg(w + 3), a3);
+            }
+        } else {
+            for (int k = 0; k < D; k++) {
+                const R* w = W + (size_t)k * ldW + n;
+                a0 = fma(th[k], __ldg(w), a0);
+                if (n + 1 < ncol) a1 = fma(th[k], __ldg(w + 1), a1);
+                if (n + 2 < ncol) a2 = fma(th[k], __ldg(w + 2), a2);
+            }
+        }
+        if (mode == 0) {
+            dst[(size_t)n * Cs] = a0 + (off ? off[n] : (R)0);
+            if (n + 1 < ncol) dst[(size_t)(n + 1) * Cs] = a1 + (off ? off[n + 1] : (R)0);
+            if (n + 2 < ncol) dst[(size_t)(n + 2) * Cs] = a2 + (off ? off[n + 2] : (R)0);
+            if (n + 3 < ncol) dst[(size_t)(n + 3) * Cs] = a3 + (off ? off[n + 3] : (R)0);
+        } else {
+            ssq += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        }
+    }
+    if (mode == 1) *dst = (R)-0.5 * (logconst + ssq);
+}
+
 template <typename R>
 struct EngineT : tda_engine {
     tda::Params<R> P;
@@ -113,6 +162,10 @@ struct EngineT : tda_engine {
     tda::DaTcState<R> tc;      // tcgen05 fast path (float only; inert for double)
     tda::DaTc16State<R> tc16;  // fp16-split tcgen05 fast path (float only)
     bool tc16_unfit = false;   // prepare() found operands that do not fit the fp16 range
+    // records written by the fp16-split kernel whose derived fields (coarse Link.prior, Link.model_output)
+    // have not been filled yet, per level; and: the levels' current model outputs lag behind theta
+    long long lazy_lo[tda::MAXL] = {0, 0, 0, 0}, lazy_hi[tda::MAXL] = {0, 0, 0, 0};
+    bool state_F_stale = false;
 
     ~EngineT() override {
         cudaSetDevice(device);
@@ -474,10 +527,64 @@ struct EngineT : tda_engine {
         return 0;
     }
 
+    int hist_fill(int l, const R* theta, long long nrec, R* out, int mode, cudaStream_t st) {
+        if (P.d != 64) return fail(-1, "history fill: d != 64");
+        const tda::LevelP<R>& v = P.lv[l];
+        const long long per = Cs / 256;
+        for (long long r0 = 0; r0 < nrec;) {
+            const long long n = nrec - r0 < (1 << 20) ? nrec - r0 : (1 << 20);
+            const R* th = theta + (size_t)r0 * P.d * Cs;
+            if (mode == 0)
+                hist_fill_kernel<R, 64><<<(unsigned)(n * per), 256, 0, st>>>(th, v.A, v.ldA, v.m, v.b, (const R*)nullptr,
+                                                                          out + (size_t)r0 * v.m * Cs, Cs, 0, (R)0);
+            else
+                hist_fill_kernel<R, 64><<<(unsigned)(n * per), 256, 0, st>>>(th, P.LP, P.ldD, P.d, (const R*)nullptr, P.prior_mean,
+                                                                          out + (size_t)r0 * Cs, Cs, 1, P.prior_logconst);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+            r0 += n;
+        }
+        return 0;
+    }
+    // fills Link.prior (levels below the finest) and Link.model_output of the records the fp16-split
+    // kernel wrote since the last call
+    int fill_lazy_history(cudaStream_t st) {
+        CUDA_TRY(cudaSetDevice(device));
+        for (int l = 0; l < P.L; l++) {
+            const tda::LevelP<R>& v = P.lv[l];
+            const long long lo = lazy_lo[l], hi = lazy_hi[l] < v.hist_cap ? lazy_hi[l] : v.hist_cap;
+            lazy_lo[l] = lazy_hi[l];
+            if (hi <= lo || !v.h_theta) continue;
+            const R* th = v.h_theta + (size_t)lo * P.d * Cs;
+            int r = 0;
+            if (l < P.L - 1 && (v.store & TDA_STORE_STATS)) r = hist_fill(l, th, hi - lo, v.h_prior + (size_t)lo * Cs, 1, st);
+            if (!r && (v.store & TDA_STORE_OUTPUT)) r = hist_fill(l, th, hi - lo, v.h_F + (size_t)lo * v.m * Cs, 0, st);
+            if (r) return r;
+        }
+        return 0;
+    }
+    // the fp16-split kernel keeps no model outputs: rebuild the levels' current F from theta before
+    // another kernel (or a checkpoint) reads them
+    int refresh_state_outputs(cudaStream_t st) {
+        if (!state_F_stale) return 0;
+        CUDA_TRY(cudaSetDevice(device));
+        state_F_stale = false;
+        for (int l = 0; l < P.L; l++) {
+            tda::LevelP<R>& v = P.lv[l];
+            if (!v.need_F || !v.F || v.model_kind != TDA_MODEL_LINEAR) continue;
+            int r = hist_fill(l, v.theta, 1, v.F, 0, st);
+            if (r) return r;
+            for (int a = 0; a < tda::MAXL; a++)
+                if (v.sv_F[a]) CUDA_TRY(cudaMemcpyAsync(v.sv_F[a], v.F, (size_t)v.m * Cs * sizeof(R), cudaMemcpyDeviceToDevice, st));
+        }
+        return 0;
+    }
+
     int init(cudaStream_t st) override {
         P.t_base = 0; P.wcount = 0;
         if (tda::is_dream(P.prop_kind)) dream_slots = cfg.dream_M0;
-        for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = 0; P.lvl_steps[l] = 0; }
+        for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = 0; P.lvl_steps[l] = 0; lazy_lo[l] = lazy_hi[l] = 0; }
+        state_F_stale = false;
         int r = launch(tda::MODE_INIT, 0, st);
         if (r) return r;
         P.rec[P.L - 1] = 1;
@@ -534,6 +641,11 @@ struct EngineT : tda_engine {
         }
         P.z_round = z_round_effective();
         int r;
+        if (which != 3) {
+            r = fill_lazy_history(st);
+            if (!r) r = refresh_state_outputs(st);
+            if (r) return r;
+        }
         if (which == 3 && iterations > (1 << 20)) {
             // the fp16-split kernel counts its coarse steps per launch in 32 bits
             for (long long done = 0; done < iterations;) {
@@ -578,13 +690,20 @@ struct EngineT : tda_engine {
         long long w = steps[0];
         for (int l = 1; l < L; l++) w += steps[l];
         P.wcount += (L == 1) ? steps[0] : w;
+        if (which == 3) {
+            for (int l = 0; l < L; l++) {
+                if (lazy_lo[l] == lazy_hi[l]) lazy_lo[l] = P.rec[l];
+                lazy_hi[l] = P.rec[l] + steps[l];
+            }
+            state_F_stale = true;
+        }
         for (int l = 0; l < L; l++) { P.rec[l] += steps[l]; if (l >= 1) P.lvl_steps[l] += steps[l]; }
         if (tda::is_dream(P.prop_kind)) dream_slots += steps[0];
         return 0;
     }
 
     int history_reset() override {
-        for (int l = 0; l < P.L; l++) P.rec[l] = 0;
+        for (int l = 0; l < P.L; l++) { P.rec[l] = 0; lazy_lo[l] = lazy_hi[l] = 0; }
         return 0;
     }
 
@@ -613,6 +732,13 @@ struct EngineT : tda_engine {
         if (needed) *needed = total;
         if (!host) return 0;
         if (bytes < total) return fail(-1, "state: buffer too small");
+        if (!load) {
+            int r = refresh_state_outputs(0);
+            if (r) return r;
+        } else {
+            state_F_stale = false;
+            for (int l = 0; l < tda::MAXL; l++) lazy_lo[l] = lazy_hi[l] = 0;
+        }
         CUDA_TRY(cudaDeviceSynchronize());
         StateHeader h;
         char* q = reinterpret_cast<char*>(host) + sizeof(StateHeader);
@@ -651,6 +777,10 @@ struct EngineT : tda_engine {
         if (level < 0 || level >= P.L) return fail(-1, "fetch: bad level");
         const tda::LevelP<R>& v = P.lv[level];
         if (rec0 < 0 || nrec < 0 || rec0 + nrec > v.hist_cap) return fail(-1, "fetch: record range outside the history buffer");
+        if (field == TDA_F_PRIOR || field == TDA_F_OUTPUT) {
+            int r = fill_lazy_history(st);
+            if (r) return r;
+        }
         const void* src = nullptr;
         size_t rows = 0, esz = sizeof(R);
         switch (field) {
