@@ -196,7 +196,9 @@ def run_ours(args):
 
     stream = torch.cuda.current_stream().cuda_stream
     # device-resident arm: stats-only history at the fine level (theta, prior, like, accept)
-    eng = Engine(spec, C, dtype=dtype, rng="philox", seed=2024, store=[STORE_NONE, STORE_STATS],
+    coarse_hist = args.history == "coarse"
+    J0 = int(spec["J"][0])
+    eng = Engine(spec, C, dtype=dtype, rng="philox", seed=2024, store=[STORE_STATS if coarse_hist else STORE_NONE, STORE_STATS],
                  capacity_iterations=iters, device=local_rank, chain_offset=rank * C,
                  n_chains_global=world * C, stream=stream)
     if args.kernel != "auto":
@@ -242,6 +244,11 @@ def run_ours(args):
     h_prior = torch.empty((n_rec, C), dtype=h_theta.dtype).pin_memory()
     h_like = torch.empty((n_rec, C), dtype=h_theta.dtype).pin_memory()
     h_acc = torch.empty((n_rec, C), dtype=torch.uint8).pin_memory()
+    if coarse_hist:
+        c_theta = torch.empty((n_rec * J0, d, C), dtype=h_theta.dtype).pin_memory()
+        c_prior = torch.empty((n_rec * J0, C), dtype=h_theta.dtype).pin_memory()
+        c_like = torch.empty((n_rec * J0, C), dtype=h_theta.dtype).pin_memory()
+        c_acc = torch.empty((n_rec * J0, C), dtype=torch.uint8).pin_memory()
 
     # the run is cut into chunks; the history of chunk k travels to the host on a second stream
     # while chunk k+1 computes (the user-facing pattern for long runs: tda_engine_run is
@@ -265,6 +272,12 @@ def run_ours(args):
             eng.fetch(1, "prior", 1 + a, b - a, out=h_prior.numpy()[a:b], stream=cs, sync=False)
             eng.fetch(1, "like", 1 + a, b - a, out=h_like.numpy()[a:b], stream=cs, sync=False)
             eng.fetch(1, "accept", 1 + a, b - a, out=h_acc.numpy()[a:b], stream=cs, sync=False)
+            if coarse_hist:
+                ca, cb = a * J0, b * J0
+                eng.fetch(0, "theta", ca, cb - ca, out=c_theta.numpy()[ca:cb], stream=cs, sync=False)
+                eng.fetch(0, "prior", ca, cb - ca, out=c_prior.numpy()[ca:cb], stream=cs, sync=False)
+                eng.fetch(0, "like", ca, cb - ca, out=c_like.numpy()[ca:cb], stream=cs, sync=False)
+                eng.fetch(0, "accept", ca, cb - ca, out=c_acc.numpy()[ca:cb], stream=cs, sync=False)
         copy_stream.synchronize()
 
     e2e_steps = max(2, min(args.steps, 5))
@@ -286,6 +299,8 @@ def run_ours(args):
     e2e_value = float(world) * C * iters * e2e_steps / (e2e_ms * 1e-3)
     h2d = theta0.nbytes
     d2h = h_theta.numel() * h_theta.element_size() + 2 * h_prior.numel() * h_prior.element_size() + h_acc.numel()
+    if coarse_hist:
+        d2h += c_theta.numel() * c_theta.element_size() + 2 * c_prior.numel() * c_prior.element_size() + c_acc.numel()
 
     kernel_used = args.kernel if args.kernel != "auto" else ("tc16" if dtype == "float32" else "generic")
     ess = None
@@ -325,7 +340,10 @@ def run_ours(args):
             "config": {
                 "workload": w["name"], "chains_per_gpu": C, "fine_iterations_per_step": iters,
                 "transitions_per_step": world * C * iters, "rng": "philox4x32-10 in-kernel",
-                "history": "fine level theta+log-prior+log-like+accept (265 B/transition f32)",
+                "history": ("fine level theta+log-prior+log-like+accept (265 B/transition f32)" if not coarse_hist else
+                            "fine level theta+log-prior+log-like+accept and every coarse Link theta+log-like+accept "
+                            "(265 + %d x 261 = %d B/transition f32); coarse log-prior rebuilt from theta at fetch time"
+                            % (J0, 265 + J0 * 261)),
                 "l2": "256 MiB buffer written between timed steps (L2 flush); chain state is kept "
                       "L2/SMEM-resident by design", "kernel": eng_kernel_name(args, dtype),
             },
@@ -338,7 +356,7 @@ def run_ours(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum of one da_tc16_kernel launch of this very
                 # command (ncu --set full, profiles/r01_ncu_tc16_summary.txt): 0.164 + 1.148 GB against
                 # 0.868 GB of algorithmic history bytes (265 B x 3,276,800 transitions)
-                "traffic": 1.312e9 if (kernel_used == "tc16" and C == N_CHAINS_PER_GPU and iters == ITERS_PER_STEP) else None,
+                "traffic": 1.312e9 if (kernel_used == "tc16" and C == N_CHAINS_PER_GPU and iters == ITERS_PER_STEP and not coarse_hist) else None,
                 "executed_tflops": per_gpu_rate * F_EXEC_TC16 / 1e12 if kernel_used == "tc16" else None,
                 "executed_frac": per_gpu_rate * F_EXEC_TC16 / 1e12 / peak if kernel_used == "tc16" else None,
                 "note": "achieved = 458752 algorithmic flop/transition x per-GPU transitions/s "
@@ -351,6 +369,10 @@ def run_ours(args):
                             "fine": float(acc[1].mean() / max(1, eng.iterations_done))},
             "wall_ms_timed_region": wall_ms,
         }
+        if coarse_hist:
+            hb = 265 + J0 * 261
+            out["link_writeout"] = {"bytes_per_transition": hb, "achieved_gbs": per_gpu_rate * hb / 1e9,
+                                    "hbm_peak_gbs": float(pk["hbm_gbs"]), "frac": per_gpu_rate * hb / 1e9 / float(pk["hbm_gbs"])}
         if ess is not None:
             ess["min_ess_per_s"] = ess["min_ess_per_transition"] * value
             out["min_ess_per_s"] = ess["min_ess_per_s"]
@@ -586,6 +608,9 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tc", "tc16"])
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default: the workload's)")
     ap.add_argument("--iters", type=int, default=None, help="finest-level iterations per step (default: the workload's)")
+    ap.add_argument("--history", default="fine", choices=["fine", "coarse"],
+                    help="cfg2: 'fine' = fine-level Links only (the headline line); 'coarse' = the reference's "
+                         "store_coarse_chain=True: every coarse Link (theta, log-like, accept) is recorded too")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--quick", action="store_true")
