@@ -285,3 +285,51 @@ def test_tc16_full_storage_agrees_with_generic_kernel_and_alternates_with_it():
         F = np.transpose(a.fetch(level, "output").astype(np.float64), (0, 2, 1))
         F_ref = th @ Gl.T
         assert np.abs(F - F_ref).max() < 1e-5 * np.abs(F_ref).max(), level
+
+
+# ---- tc16 on shapes that are not the kernel's native 64 / 16k / 64k: zero-padded operands -------
+@pytest.mark.parametrize("d,m_c,m_f", [(32, 100, 1000), (48, 128, 1024), (16, 7, 70), (64, 120, 1900)])
+def test_tc16_padded_shapes_agree_with_generic_kernel(d, m_c, m_f):
+    """d in {16, 32, 48, 64}, any m_c <= 128, any m_f <= 1920: the host pads the operators with zero
+    rows / columns (prepare), the kernel only touches the d parameter rows that exist, and the z16
+    stream is consumed d normals per coarse step -- the same positions the generic kernel reads."""
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.engine import Engine, STORE_FULL
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da(d=d, m_f=m_f, m_c=m_c)
+    J = 10
+    spec = lower_problem(w["posteriors"], w["proposal"], J)
+    C, iters = 512, 20
+    theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1)).reshape(C, d)
+    engs = []
+    for kernel in ("tc16", "generic"):
+        e = Engine(spec, C, dtype="float32", rng="philox", seed=11, store=[STORE_FULL, STORE_FULL], capacity_iterations=iters)
+        e.select_kernel(kernel)
+        e.init(theta0)
+        if kernel == "generic":
+            e.set_z_round(True)
+        e.run(iters)
+        engs.append(e)
+    a, b = engs
+    assert a.kernel() == "tc16"
+    acc_a, acc_b = a.fetch(1, "accept"), b.fetch(1, "accept")
+    cacc_a, cacc_b = a.fetch(0, "accept"), b.fetch(0, "accept")
+    assert (acc_a == acc_b).mean() > 0.97 and (cacc_a == cacc_b).mean() > 0.97
+    ok = (acc_a == acc_b).all(axis=0) & (cacc_a == cacc_b).all(axis=0)
+    assert ok.mean() > 0.6, ok.mean()
+    for level in (0, 1):
+        for k, tol in (("theta", 2e-3), ("output", 2e-3)):
+            xa, xb = a.fetch(level, k), b.fetch(level, k)
+            assert xa.shape == xb.shape
+            assert np.abs(xa[:, :, ok] - xb[:, :, ok]).max() < tol * np.abs(xb).max(), (level, k)
+        for k in ("prior", "like"):
+            np.testing.assert_allclose(a.fetch(level, k)[:, ok], b.fetch(level, k)[:, ok], rtol=1e-3, atol=0.3)
+    assert np.array_equal(a.get("cursors")[0], b.get("cursors")[0])
+    # the links are consistent in float64 as well
+    idx = np.arange(0, m_f, m_f // m_c)[:m_c]
+    th = np.transpose(a.fetch(0, "theta").astype(np.float64), (0, 2, 1))
+    F_ref = th @ w["G"][idx].T
+    like_ref = -0.5 * ((F_ref - w["y"][idx]) ** 2).sum(axis=2) / w["sigma2"]
+    np.testing.assert_allclose(a.fetch(0, "like"), like_ref, rtol=2e-4, atol=2e-2)
+    for e in engs:
+        e.close()

@@ -335,6 +335,8 @@ __device__ __forceinline__ void t16_red_release_add(int* ptr, int v) {
 // normals one step ahead, in the shadow of the MMA -- 678 M / 636 M transitions/s against 701 M with
 // the RNG warps alone; the row threads are the critical path as soon as the normals are ahead.)
 
+// PAD = false: d == 64, the native shape (no guards on the parameter rows); PAD = true: d in {16, 32, 48}
+template <bool PAD>
 __global__ void __launch_bounds__(T16_THREADS, 1)
 da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ DaTc16Params q) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -384,6 +386,14 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         for (int s = 0; s < T16_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 2); }
         tc::fence_mbar_init();
     }
+    // d < 64 (multiples of 16): the operators are zero-padded to 64 rows on the host and the normals'
+    // columns d..63 stay zero -- the RNG warps only write the first d columns of a z image
+    const int d = PAD ? p.d : T16_K;
+    if (PAD) {
+        uint4* zz = reinterpret_cast<uint4*>(zbuf);
+        for (int i = tid; i < 4 * T16_IMG / 16; i += T16_THREADS) zz[i] = make_uint4(0u, 0u, 0u, 0u);
+        tc::fence_proxy_async_smem();
+    }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -420,13 +430,13 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 if (dbg_on) q.dbg[0 * 256 + 3 * n + 1] = clock64();
                 unsigned char* dst = zt + (size_t)b * T16_IMG;
                 if (!inj) {
-                    // z16 stream: 64 normals = 4 groups of 3 Philox blocks
-                    const unsigned long long grp0 = (unsigned long long)(tb * (T16_K / 16));
+                    // z16 stream: d normals = d / 16 groups of 3 Philox blocks
+                    const unsigned long long grp0 = (unsigned long long)(tb * (d >> 4));
 #pragma unroll 1
-                    for (int q4 = 0; q4 < T16_K / 16; q4++) t16_z_group(p.seed, gchain, grp0 + q4, dst, q4);
+                    for (int q4 = 0; q4 < (d >> 4); q4++) t16_z_group(p.seed, gchain, grp0 + q4, dst, q4);
                 } else {
-                    const long long z0 = tb * T16_K;
-                    for (int kg = 0; kg < T16_K / 8; kg++) {
+                    const long long z0 = tb * d;
+                    for (int kg = 0; kg < (d >> 3); kg++) {
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
@@ -566,6 +576,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         const int wq = rw & 3;                         // TMEM lane quarter (= warp % 4)
         const int cl = wq * 32 + lane;                 // chain within the tile
         const int col0 = h * T16_HK;                   // first theta column of this thread
+        const int nk = PAD ? min(T16_HK, max(0, d - col0)) : T16_HK;   // columns of this thread that exist (d <= 64)
         const uint32_t tA = tbase + ((uint32_t)(wq * 32) << 16) + t * 256;
         const uint32_t tD = tA + 64;
         uint64_t* reqA = bar_reqA + t;
@@ -612,7 +623,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 // (.cg loads: the state may have been written by another SM during this launch)
                 const float* src = t16_opaque(l1.theta + off0);
 #pragma unroll
-                for (int k = 0; k < T16_HK; k++) th[k] = __ldcg(src + k * cs) * th_scale;
+                for (int k = 0; k < T16_HK; k++) th[k] = (k < nk) ? __ldcg(src + k * cs) * th_scale : 0.0f;
             }
             float like_c = __ldcg(l0.like + g), like_cs = like_c, like_f = __ldcg(l1.like + g), prior_f = __ldcg(l1.prior + g);
             long long ucur = __ldcg(p.ucur + g);
@@ -728,9 +739,10 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                         const long long r0 = p.rec[0] + (long long)it * J + j;
                         if (r0 < l0.hist_cap) {
                             if (l0.store & TDA_STORE_THETA) {
-                                float* dst = t16_opaque(l0.h_theta + (size_t)r0 * T16_K * cs + off0);
+                                float* dst = t16_opaque(l0.h_theta + (size_t)r0 * d * cs + off0);
 #pragma unroll
-                                for (int k = 0; k < T16_HK; k++) __stcs(dst + k * cs, th[k] * th_unscale);
+                                for (int k = 0; k < T16_HK; k++)
+                                    if (k < nk) __stcs(dst + k * cs, th[k] * th_unscale);
                             }
                             if (h == 0) {
                                 if (l0.store & TDA_STORE_STATS) __stcs(l0.h_like + (size_t)r0 * cs + g, like_c);
@@ -799,12 +811,14 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     like_f = like_fp; prior_f = prior_p; like_cs = like_c; nacc_f++;
                     float* dst = t16_opaque(l1.theta + off0);
 #pragma unroll
-                    for (int k = 0; k < T16_HK; k++) dst[k * cs] = th[k] * th_unscale;
+                    for (int k = 0; k < T16_HK; k++)
+                        if (k < nk) dst[k * cs] = th[k] * th_unscale;
                 } else {
                     like_c = like_cs;
                     const float* src = t16_opaque(l1.theta + off0);
 #pragma unroll
-                    for (int k = 0; k < T16_HK; k++) th[k] = __ldcg(src + k * cs) * th_scale;
+                    for (int k = 0; k < T16_HK; k++)
+                        if (k < nk) th[k] = __ldcg(src + k * cs) * th_scale;
                 }
                 acc_any = 0;
                 // the A operand must hold the (possibly rewound) state before the next coarse job
@@ -818,9 +832,10 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 const long long r = p.rec[1] + it;
                 if (r < l1.hist_cap) {
                     if (l1.store & TDA_STORE_THETA) {
-                        float* dst = t16_opaque(l1.h_theta + (size_t)r * T16_K * cs + off0);
+                        float* dst = t16_opaque(l1.h_theta + (size_t)r * d * cs + off0);
 #pragma unroll
-                        for (int k = 0; k < T16_HK; k++) dst[k * cs] = th[k] * th_unscale;
+                        for (int k = 0; k < T16_HK; k++)
+                            if (k < nk) dst[k * cs] = th[k] * th_unscale;
                     }
                     if (h == 0) {
                         if (l1.store & TDA_STORE_STATS) { l1.h_prior[(size_t)r * p.Cs + g] = prior_f; l1.h_like[(size_t)r * p.Cs + g] = like_f; }
@@ -833,8 +848,10 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < T16_HK; k++) {
                         const float x = th[k] * th_unscale;
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s1 + k * cs), "f"(x) : "memory");
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s2 + k * cs), "f"(x * x) : "memory");
+                        if (k < nk) {
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s1 + k * cs), "f"(x) : "memory");
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s2 + k * cs), "f"(x * x) : "memory");
+                        }
                     }
                 }
             }
@@ -842,7 +859,8 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             {
                 float* dst = t16_opaque(l0.theta + off0);
 #pragma unroll
-                for (int k = 0; k < T16_HK; k++) dst[k * cs] = th[k] * th_unscale;
+                for (int k = 0; k < T16_HK; k++)
+                    if (k < nk) dst[k * cs] = th[k] * th_unscale;
             }
             if (h == 0) {
                 l0.like[g] = like_c; l0.prior[g] = prior_f; l1.like[g] = like_f; l1.prior[g] = prior_f;
@@ -889,11 +907,12 @@ struct DaTc16State<float> {
 
     bool eligible(const tda_config& c, const Params<float>& P) const {
         if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.mtm_k || c.prop_kind != TDA_PROP_PCN || c.adaptive) return false;
-        if (c.d != T16_K) return false;
+        // d, m_c and m_f are zero-padded to 64 / a multiple of 16 / a multiple of 64 (prepare)
+        if (c.d > T16_K || c.d < 16 || (c.d % 16) != 0) return false;
         for (int l = 0; l < 2; l++)
             if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
-        if (c.level[0].m > T16_MAX_MC || (c.level[0].m % 16) != 0) return false;
-        if (c.level[1].m > T16_MAX_MF || (c.level[1].m % T16_CH) != 0) return false;
+        if (c.level[0].m < 1 || c.level[0].m > T16_MAX_MC) return false;
+        if (c.level[1].m < 1 || c.level[1].m > T16_MAX_MF) return false;
         // Link.prior of the coarse records and Link.model_output of both levels are rebuilt from the
         // stored parameters when first fetched (engine: fill_lazy_history): they need the parameters
         if ((c.level[0].store & (TDA_STORE_STATS | TDA_STORE_OUTPUT)) && !(c.level[0].store & TDA_STORE_THETA)) return false;
@@ -945,20 +964,31 @@ struct DaTc16State<float> {
             h.assign(f.begin(), f.end());
             return e;
         };
-        const int mc = c.level[0].m, mf = c.level[1].m;
+        // real shapes (d0, mc0, mf0) and the padded ones the kernel runs on: zero rows / columns add
+        // nothing to a contraction, zero data under a zero operator column gives a zero residual
+        const int d0 = c.d, mc0 = c.level[0].m, mf0 = c.level[1].m;
+        const int mc = (mc0 + 15) / 16 * 16, mf = (mf0 + T16_CH - 1) / T16_CH * T16_CH;
         std::vector<double> T, LP, Ac, Af, bc, bf, dc, df, mu, sc;
         cudaError_t e = cudaSuccess;
-        if (e == cudaSuccess) e = fetch(P.T, (size_t)T16_K * P.ldD, T);
-        if (e == cudaSuccess) e = fetch(P.LP, (size_t)T16_K * P.ldD, LP);
-        if (e == cudaSuccess) e = fetch(P.lv[0].A, (size_t)T16_K * P.lv[0].ldA, Ac);
-        if (e == cudaSuccess) e = fetch(P.lv[1].A, (size_t)T16_K * P.lv[1].ldA, Af);
-        if (e == cudaSuccess) e = fetch(P.lv[0].b, mc, bc);
-        if (e == cudaSuccess) e = fetch(P.lv[1].b, mf, bf);
-        if (e == cudaSuccess) e = fetch(P.lv[0].data, mc, dc);
-        if (e == cudaSuccess) e = fetch(P.lv[1].data, mf, df);
-        if (e == cudaSuccess) e = fetch(P.prior_mean, T16_K, mu);
+        if (P.ldD < T16_K || P.lv[0].ldA < mc || P.lv[1].ldA < mf) { err = "tc16: operand leading dimensions"; return 1; }
+        if (e == cudaSuccess) e = fetch(P.T, (size_t)d0 * P.ldD, T);
+        if (e == cudaSuccess) e = fetch(P.LP, (size_t)d0 * P.ldD, LP);
+        if (e == cudaSuccess) e = fetch(P.lv[0].A, (size_t)d0 * P.lv[0].ldA, Ac);
+        if (e == cudaSuccess) e = fetch(P.lv[1].A, (size_t)d0 * P.lv[1].ldA, Af);
+        if (e == cudaSuccess) e = fetch(P.lv[0].b, mc0, bc);
+        if (e == cudaSuccess) e = fetch(P.lv[1].b, mf0, bf);
+        if (e == cudaSuccess) e = fetch(P.lv[0].data, mc0, dc);
+        if (e == cudaSuccess) e = fetch(P.lv[1].data, mf0, df);
+        if (e == cudaSuccess) e = fetch(P.prior_mean, d0, mu);
         if (e == cudaSuccess) e = fetch(P.scaling, (size_t)P.Cs, sc);
         if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
+        auto pad = [&](std::vector<double>& W, int ld, int cols) {
+            for (int k = 0; k < d0; k++)
+                for (int n = cols; n < ld; n++) W[(size_t)k * ld + n] = 0.0;
+            W.resize((size_t)T16_K * ld, 0.0);
+        };
+        pad(T, P.ldD, d0); pad(LP, P.ldD, d0); pad(Ac, P.lv[0].ldA, mc0); pad(Af, P.lv[1].ldA, mf0);
+        mu.resize(T16_K, 0.0);
         // the pCN step is folded into the operators: it must be the same for every chain
         const double beta = sc[0];
         for (int i = 0; i < P.C; i++)
@@ -1018,13 +1048,13 @@ struct DaTc16State<float> {
         if (e == cudaSuccess) e = cudaMemcpy(dF, hF.data(), hF.size() * 2, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
         std::vector<float> ny((size_t)T16_MAX_MC + T16_K + mf, 0.f);
-        for (int j = 0; j < mc; j++) ny[j] = -(float)(dc[j] - bc[j]);
+        for (int j = 0; j < mc0; j++) ny[j] = -(float)(dc[j] - bc[j]);
         for (int n = 0; n < T16_K; n++) {
             double s = 0;
             for (int k = 0; k < T16_K; k++) s += mu[k] * LP[(size_t)k * ldD + n];
             ny[T16_MAX_MC + n] = -(float)s;
         }
-        for (int j = 0; j < mf; j++) ny[T16_MAX_MC + T16_K + j] = -(float)(df[j] - bf[j]);
+        for (int j = 0; j < mf0; j++) ny[T16_MAX_MC + T16_K + j] = -(float)(df[j] - bf[j]);
         e = cudaMalloc(&dNY, ny.size() * 4);
         if (e == cudaSuccess) e = cudaMemcpy(dNY, ny.data(), ny.size() * 4, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
@@ -1080,12 +1110,13 @@ struct DaTc16State<float> {
         }
         q.progress = dProgress;
         const size_t smem = T16_SMEM_BYTES;
-        e = cudaFuncSetAttribute(da_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = (P.d == T16_K) ? da_tc16_kernel<false> : da_tc16_kernel<true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { err = std::string("tc16 attr: ") + cudaGetErrorString(e); return -2; }
         P.mode = MODE_RUN;
         P.iterations = iterations;
         P.z_round = 1;
-        da_tc16_kernel<<<grid, T16_THREADS, smem, st>>>(P, q);
+        kern<<<grid, T16_THREADS, smem, st>>>(P, q);
         e = cudaGetLastError();
         if (e != cudaSuccess) { err = std::string("tc16 launch: ") + cudaGetErrorString(e); return -2; }
         return 0;

@@ -105,14 +105,14 @@ __global__ void init_theta_kernel(const double* __restrict__ src, int C, int d, 
 template <typename R, int D>
 __global__ void __launch_bounds__(256) hist_fill_kernel(const R* __restrict__ theta, const R* __restrict__ W, int ldW, int ncol,
                                                         const R* __restrict__ off, const R* __restrict__ mu, R* __restrict__ out,
-                                                        int Cs, int mode, R logconst) {
+                                                        int d, int Cs, int mode, R logconst) {
     const int cblocks = Cs / 256;
     const size_t r = blockIdx.x / cblocks;
     const int c = (int)(blockIdx.x - r * cblocks) * 256 + threadIdx.x;
-    const R* th_src = theta + r * (size_t)D * Cs + c;
-    R th[D];
+    const R* th_src = theta + r * (size_t)d * Cs + c;
+    R th[D];                                   // d <= D; the missing rows are zero and skipped below
 #pragma unroll
-    for (int k = 0; k < D; k++) th[k] = th_src[(size_t)k * Cs] - (mu ? mu[k] : (R)0);
+    for (int k = 0; k < D; k++) th[k] = (k < d) ? th_src[(size_t)k * Cs] - (mu ? mu[k] : (R)0) : (R)0;
     R ssq = 0;
     R* dst = out + (mode == 0 ? r * (size_t)ncol * Cs : r * (size_t)Cs) + c;
     for (int n = 0; n < ncol; n += 4) {
@@ -120,12 +120,15 @@ __global__ void __launch_bounds__(256) hist_fill_kernel(const R* __restrict__ th
         if (n + 3 < ncol) {
 #pragma unroll
             for (int k = 0; k < D; k++) {
+                if (k >= d) break;
                 const R* w = W + (size_t)k * ldW + n;
                 a0 = fma(th[k], __ldg(w), a0); a1 = fma(th[k], __ldg(w + 1), a1);
                 a2 = fma(th[k], __ldg(w + 2), a2); a3 = fma(th[k], __ldg(w + 3), a3);
             }
         } else {
+#pragma unroll
             for (int k = 0; k < D; k++) {
+                if (k >= d) break;
                 const R* w = W + (size_t)k * ldW + n;
                 a0 = fma(th[k], __ldg(w), a0);
                 if (n + 1 < ncol) a1 = fma(th[k], __ldg(w + 1), a1);
@@ -528,7 +531,7 @@ struct EngineT : tda_engine {
     }
 
     int hist_fill(int l, const R* theta, long long nrec, R* out, int mode, cudaStream_t st) {
-        if (P.d != 64) return fail(-1, "history fill: d != 64");
+        if (P.d > 64) return fail(-1, "history fill: d > 64");
         const tda::LevelP<R>& v = P.lv[l];
         const long long per = Cs / 256;
         for (long long r0 = 0; r0 < nrec;) {
@@ -536,10 +539,10 @@ struct EngineT : tda_engine {
             const R* th = theta + (size_t)r0 * P.d * Cs;
             if (mode == 0)
                 hist_fill_kernel<R, 64><<<(unsigned)(n * per), 256, 0, st>>>(th, v.A, v.ldA, v.m, v.b, (const R*)nullptr,
-                                                                          out + (size_t)r0 * v.m * Cs, Cs, 0, (R)0);
+                                                                          out + (size_t)r0 * v.m * Cs, P.d, Cs, 0, (R)0);
             else
                 hist_fill_kernel<R, 64><<<(unsigned)(n * per), 256, 0, st>>>(th, P.LP, P.ldD, P.d, (const R*)nullptr, P.prior_mean,
-                                                                          out + (size_t)r0 * Cs, Cs, 1, P.prior_logconst);
+                                                                          out + (size_t)r0 * Cs, P.d, Cs, 1, P.prior_logconst);
             g_launches++;
             CUDA_TRY(cudaGetLastError());
             r0 += n;
