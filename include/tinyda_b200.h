@@ -196,7 +196,11 @@ int tda_engine_sync(tda_engine *e, void *cuda_stream);
 
 /* Copies history records [rec0, rec0+nrec) of one level into host memory (pinned or
  * pageable), in the device layout documented at TDA_F_*; async on cuda_stream when the host
- * buffer is pinned.  Returns the number of bytes written through *bytes. */
+ * buffer is pinned.  Returns the number of bytes written through *bytes.
+ * Records written by the tensor-core Delayed-Acceptance kernel carry the parameters, the
+ * log-likelihood and the accept flag; the coarse Links' log-prior (TDA_F_PRIOR) and the model
+ * outputs (TDA_F_OUTPUT, Link.model_output link.py:1-48) are rebuilt from the recorded
+ * parameters on cuda_stream the first time either field is fetched. */
 int tda_fetch(tda_engine *e, int level, int field, int64_t rec0, int64_t nrec,
               void *host_dst, size_t dst_bytes, size_t *bytes, void *cuda_stream);
 

@@ -333,3 +333,58 @@ def test_tc16_padded_shapes_agree_with_generic_kernel(d, m_c, m_f):
     np.testing.assert_allclose(a.fetch(0, "like"), like_ref, rtol=2e-4, atol=2e-2)
     for e in engs:
         e.close()
+
+
+@pytest.mark.parametrize("kind", ["diagonal", "dense"])
+def test_tc16_diagonal_and_dense_likelihoods_folded_into_the_operators(kind):
+    """DiagonalGaussianLogLike / DefaultGaussianLogLike (distributions.py:304-315, :246-301) on the
+    tensor-core kernel: prepare() whitens the linear models and the data with the Cholesky factor of the
+    precision, the kernel then scores an isotropic unit-variance residual.  Same decisions as the generic
+    kernel (which evaluates r^T prec r directly) and log-likelihoods that agree with float64."""
+    from scipy import stats
+    import tinyda_b200 as tda
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.engine import Engine, STORE_FULL
+    from tinyda_b200.workloads import exp_cov
+    from tinyda_b200.models import LinearModel
+    rng = np.random.default_rng(21)
+    d, m_f, m_c, J = 64, 512, 64, 10
+    prior = stats.multivariate_normal(np.zeros(d), exp_cov(d))
+    G = rng.standard_normal((m_f, d)) / 8
+    y = G @ prior.rvs(random_state=rng) + 0.1 * rng.standard_normal(m_f)
+    sd = 0.1 * (1 + 0.5 * rng.random(m_f))
+    if kind == "diagonal":
+        cov = np.diag(sd ** 2)
+    else:
+        i = np.arange(m_f)
+        cov = np.outer(sd, sd) * (0.4 ** np.abs(i[:, None] - i[None, :]))      # AR(1)-correlated noise
+    idx = np.arange(0, m_f, m_f // m_c)
+    posts = [tda.Posterior(prior, tda.GaussianLogLike(y[idx], cov[np.ix_(idx, idx)]), LinearModel(G[idx])),
+             tda.Posterior(prior, tda.GaussianLogLike(y, cov), LinearModel(G))]
+    spec = lower_problem(posts, tda.CrankNicolson(scaling=0.05), J)
+    C, iters = 256, 12
+    theta0 = prior.rvs(C, random_state=np.random.default_rng(1))
+    engs = []
+    for kernel in ("tc16", "generic"):
+        e = Engine(spec, C, dtype="float32", rng="philox", seed=5, store=[STORE_FULL, STORE_FULL], capacity_iterations=iters)
+        e.select_kernel(kernel)
+        e.init(theta0)
+        if kernel == "generic":
+            e.set_z_round(True)
+        e.run(iters)
+        engs.append(e)
+    a, b = engs
+    assert a.kernel() == "tc16"
+    ok = (a.fetch(1, "accept") == b.fetch(1, "accept")).all(axis=0) & (a.fetch(0, "accept") == b.fetch(0, "accept")).all(axis=0)
+    assert ok.mean() > 0.6, ok.mean()
+    prec = [np.linalg.inv(cov[np.ix_(idx, idx)]), np.linalg.inv(cov)]
+    for level, (Gl, yl) in enumerate([(G[idx], y[idx]), (G, y)]):
+        th_a, th_b = a.fetch(level, "theta"), b.fetch(level, "theta")
+        assert np.abs(th_a[:, :, ok] - th_b[:, :, ok]).max() < 2e-3 * np.abs(th_b).max()
+        r = np.transpose(th_a.astype(np.float64), (0, 2, 1)) @ Gl.T - yl
+        like_ref = -0.5 * np.einsum("rcm,mn,rcn->rc", r, prec[level], r)
+        np.testing.assert_allclose(a.fetch(level, "like"), like_ref, rtol=3e-4, atol=3e-2)
+        F = np.transpose(a.fetch(level, "output").astype(np.float64), (0, 2, 1))
+        assert np.abs(F - (r + yl)).max() < 1e-5 * np.abs(r + yl).max()       # Link.model_output is the unwhitened F
+    for e in engs:
+        e.close()

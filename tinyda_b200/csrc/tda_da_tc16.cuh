@@ -910,7 +910,7 @@ struct DaTc16State<float> {
         // d, m_c and m_f are zero-padded to 64 / a multiple of 16 / a multiple of 64 (prepare)
         if (c.d > T16_K || c.d < 16 || (c.d % 16) != 0) return false;
         for (int l = 0; l < 2; l++)
-            if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
+            if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind > TDA_LIK_DENSE) return false;
         if (c.level[0].m < 1 || c.level[0].m > T16_MAX_MC) return false;
         if (c.level[1].m < 1 || c.level[1].m > T16_MAX_MF) return false;
         // Link.prior of the coarse records and Link.model_output of both levels are rebuilt from the
@@ -989,6 +989,58 @@ struct DaTc16State<float> {
         };
         pad(T, P.ldD, d0); pad(LP, P.ldD, d0); pad(Ac, P.lv[0].ldA, mc0); pad(Af, P.lv[1].ldA, mf0);
         mu.resize(T16_K, 0.0);
+        // Diagonal and dense Gaussian likelihoods (distributions.py:304-315, :246-301) are folded into
+        // the operators: with prec = L L^T (diagonal: L = diag(var^-1/2)) the log-likelihood
+        // -0.5 r^T prec r is -0.5 |L^T r|^2 -- an isotropic unit-variance likelihood of the whitened
+        // model L^T G against the whitened data L^T (y - b)
+        std::vector<double> rc(mc0), rf(mf0);
+        for (int j = 0; j < mc0; j++) rc[j] = dc[j] - bc[j];
+        for (int j = 0; j < mf0; j++) rf[j] = df[j] - bf[j];
+        double lik_var[2] = {c.level[0].lik_var, c.level[1].lik_var};
+        for (int l = 0; l < 2; l++) {
+            const int kind = c.level[l].lik_kind, m0 = l ? mf0 : mc0, ld = P.lv[l].ldA;
+            std::vector<double>& A = l ? Af : Ac;
+            std::vector<double>& r = l ? rf : rc;
+            if (kind == TDA_LIK_ISO) continue;
+            lik_var[l] = 1.0;
+            if (kind == TDA_LIK_DIAG) {
+                std::vector<double> var;
+                e = fetch(P.lv[l].var, m0, var);
+                if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
+                for (int n = 0; n < m0; n++) {
+                    if (!(var[n] > 0.0)) { err = "tc16: non-positive likelihood variance"; return 1; }
+                    const double w = 1.0 / std::sqrt(var[n]);
+                    for (int k = 0; k < d0; k++) A[(size_t)k * ld + n] *= w;
+                    r[n] *= w;
+                }
+            } else {
+                std::vector<double> Lc;
+                e = fetch(P.lv[l].prec, (size_t)m0 * m0, Lc);
+                if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
+                for (int j = 0; j < m0; j++) {            // in-place lower Cholesky factor of the precision
+                    double dj = Lc[(size_t)j * m0 + j];
+                    for (int k = 0; k < j; k++) dj -= Lc[(size_t)j * m0 + k] * Lc[(size_t)j * m0 + k];
+                    if (!(dj > 0.0)) { err = "tc16: likelihood precision is not positive definite in float32"; return 1; }
+                    dj = std::sqrt(dj);
+                    Lc[(size_t)j * m0 + j] = dj;
+                    for (int i = j + 1; i < m0; i++) {
+                        double v = Lc[(size_t)i * m0 + j];
+                        for (int k = 0; k < j; k++) v -= Lc[(size_t)i * m0 + k] * Lc[(size_t)j * m0 + k];
+                        Lc[(size_t)i * m0 + j] = v / dj;
+                    }
+                }
+                std::vector<double> row(m0);
+                for (int k = 0; k <= d0; k++) {            // rows of G^T, then the data residual: x <- x L
+                    double* x = (k < d0) ? &A[(size_t)k * ld] : r.data();
+                    for (int n = 0; n < m0; n++) {
+                        double v = 0;
+                        for (int j = n; j < m0; j++) v += x[j] * Lc[(size_t)j * m0 + n];
+                        row[n] = v;
+                    }
+                    for (int n = 0; n < m0; n++) x[n] = row[n];
+                }
+            }
+        }
         // the pCN step is folded into the operators: it must be the same for every chain
         const double beta = sc[0];
         for (int i = 0; i < P.C; i++)
@@ -1048,19 +1100,19 @@ struct DaTc16State<float> {
         if (e == cudaSuccess) e = cudaMemcpy(dF, hF.data(), hF.size() * 2, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
         std::vector<float> ny((size_t)T16_MAX_MC + T16_K + mf, 0.f);
-        for (int j = 0; j < mc0; j++) ny[j] = -(float)(dc[j] - bc[j]);
+        for (int j = 0; j < mc0; j++) ny[j] = -(float)rc[j];
         for (int n = 0; n < T16_K; n++) {
             double s = 0;
             for (int k = 0; k < T16_K; k++) s += mu[k] * LP[(size_t)k * ldD + n];
             ny[T16_MAX_MC + n] = -(float)s;
         }
-        for (int j = 0; j < mf0; j++) ny[T16_MAX_MC + T16_K + j] = -(float)(df[j] - bf[j]);
+        for (int j = 0; j < mf0; j++) ny[T16_MAX_MC + T16_K + j] = -(float)rf[j];
         e = cudaMalloc(&dNY, ny.size() * 4);
         if (e == cudaSuccess) e = cudaMemcpy(dNY, ny.data(), ny.size() * 4, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
         q.G_hl = dG; q.M_hl = dM; q.T_hl = dT; q.F_chunks = dF; q.ny = dNY;
         q.mc = mc; q.mf = mf; q.n_chunks = nch; q.J = c.subchain[0];
-        q.var_c = (float)c.level[0].lik_var; q.var_f = (float)c.level[1].lik_var;
+        q.var_c = (float)lik_var[0]; q.var_f = (float)lik_var[1];
         q.prior_logconst = (float)c.prior_logconst;
         q.ca = (float)a;
         q.cxi = (float)(beta * std::ldexp(1.0, s_th - s_z - s_T));
