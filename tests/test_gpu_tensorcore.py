@@ -388,3 +388,34 @@ def test_tc16_diagonal_and_dense_likelihoods_folded_into_the_operators(kind):
         assert np.abs(F - (r + yl)).max() < 1e-5 * np.abs(r + yl).max()       # Link.model_output is the unwhitened F
     for e in engs:
         e.close()
+
+
+def test_tc16_coarse_chain_matches_reference_trajectory_until_near_tie():
+    """chain_coarse_i of the unmodified reference (cfg2 golden fixture, injected streams) against the
+    coarse Links the tc16 kernel records: parameters, log-likelihood, accept flags, and the log-prior
+    rebuilt at fetch time, up to the first decision that differs (float32 near-tie)."""
+    import golden_io
+    from tinyda_b200.engine import Engine, STORE_STATS
+    g = golden_io.load("da_pcn_cfg2")
+    C, iters, J = g["theta0"].shape[0], g["iterations"], 10
+    eng = Engine(g["spec"], C, dtype="float32", rng="injected", streams=(g["z"], g["u"]),
+                 store=[STORE_STATS, STORE_STATS], capacity_iterations=iters)
+    eng.select_kernel("tc16")
+    eng.init(g["theta0"])
+    eng.run(iters)
+    ref = g["ref"][0]
+    acc = eng.fetch(0, "accept").T.astype(bool)
+    th = np.transpose(eng.fetch(0, "theta"), (2, 0, 1)).astype(np.float64)
+    lk = eng.fetch(0, "like").T.astype(np.float64)
+    pr = eng.fetch(0, "prior").T.astype(np.float64)
+    assert acc.shape == ref["acc"].shape == (C, J * iters)
+    diff = acc != ref["acc"]
+    first = np.where(diff.any(axis=1), diff.argmax(axis=1), acc.shape[1])
+    assert first.min() >= 10 * J, first                # at least ten fine iterations in common
+    for c in range(C):
+        k = int(first[c])
+        scale = np.abs(ref["theta"][c, :k]).max()
+        np.testing.assert_allclose(th[c, :k], ref["theta"][c, :k], rtol=1e-4, atol=1e-4 * scale)
+        np.testing.assert_allclose(lk[c, :k], ref["like"][c, :k], rtol=2e-4, atol=2e-2)
+        np.testing.assert_allclose(pr[c, :k], ref["prior"][c, :k], rtol=2e-4, atol=2e-2)
+    eng.close()
