@@ -258,31 +258,36 @@ __device__ __forceinline__ void t16_warp_arrive(uint64_t* bar, int lane) {
     if (lane == 0) tc::mbar_arrive(bar);
 }
 
-// 3 products (A = theta hi | lo in TMEM, B hi | lo in shared memory), N columns, K = 64
-__device__ __forceinline__ void t16_issue_theta(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+// 3 products (A = theta hi | lo in TMEM, B hi | lo in shared memory), N columns, K = 16 nks (64 unless d < 64)
+__device__ __forceinline__ void t16_issue_theta(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                                int nks = T16_K / 16) {
 #pragma unroll
     for (int pass = 0; pass < 3; pass++) {
         const uint32_t a = a_tmem + (pass == 1 ? 32 : 0);
         const uint64_t b0 = tc::smem_desc_kmajor(pass == 2 ? b_lo : b_hi, 128, (T16_K / 8) * 128);
 #pragma unroll
         for (int ks = 0; ks < T16_K / 16; ks++) {
-            tc::mma_f16_ts(d_tmem, a + ks * 8, b0 + (uint64_t)(ks * 16), idesc, accumulate);
-            accumulate = 1;
+            if (ks < nks) {
+                tc::mma_f16_ts(d_tmem, a + ks * 8, b0 + (uint64_t)(ks * 16), idesc, accumulate);
+                accumulate = 1;
+            }
         }
     }
 }
 
 // z-operand products: z @ B_hi + z @ B_lo (+ z_lo @ B_hi when the stream is injected)
 __device__ __forceinline__ void t16_issue_z(uint32_t d_tmem, uint32_t z_hi, uint32_t z_lo, bool with_lo, uint32_t b_hi, uint32_t b_lo,
-                                            uint32_t idesc, uint32_t accumulate) {
+                                            uint32_t idesc, uint32_t accumulate, int nks = T16_K / 16) {
     const int npass = with_lo ? 3 : 2;
     for (int pass = 0; pass < npass; pass++) {
         const uint64_t a0 = tc::smem_desc_kmajor(pass == 2 ? z_lo : z_hi, 128, (T16_K / 8) * 128);
         const uint64_t b0 = tc::smem_desc_kmajor(pass == 1 ? b_lo : b_hi, 128, (T16_K / 8) * 128);
 #pragma unroll
         for (int ks = 0; ks < T16_K / 16; ks++) {
-            tc::mma_f16_ss(d_tmem, a0 + (uint64_t)(ks * 16), b0 + (uint64_t)(ks * 16), idesc, accumulate);
-            accumulate = 1;
+            if (ks < nks) {
+                tc::mma_f16_ss(d_tmem, a0 + (uint64_t)(ks * 16), b0 + (uint64_t)(ks * 16), idesc, accumulate);
+                accumulate = 1;
+            }
         }
     }
 }
@@ -501,6 +506,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             uint64_t* reqF = bar_reqF + t * 3;
             uint64_t* respF = bar_respF + t * 3;
             uint32_t pa = 0, pb = 0, pf = 0;              // pf: bit b = parity of reqF[b]
+            const int nks = PAD ? (d >> 4) : T16_K / 16; // K steps that carry parameters (the rest is zero padding)
             unsigned n = 0, gch = 0;
             int total_it = 0;
             {
@@ -524,16 +530,16 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     tc::mbar_wait(bar_zfull + t * 2 + b, (uint32_t)(use & 1));
                     tc::fence_after_sync();
                     if (dbg_on) q.dbg[1 * 256 + 6 * n + 2] = clock64();
-                    if (tc::elect_one()) t16_issue_z(tD, z_hi, z_lo, inj, sM_hi, sM_lo, idesc_c, 0);
+                    if (tc::elect_one()) t16_issue_z(tD, z_hi, z_lo, inj, sM_hi, sM_lo, idesc_c, 0, nks);
                     __syncwarp();
                     if (dbg_on) q.dbg[1 * 256 + 6 * n + 3] = clock64();
                     tc::mbar_wait(reqB, pb); pb ^= 1;
                     tc::fence_after_sync();
                     if (dbg_on) q.dbg[1 * 256 + 6 * n + 4] = clock64();
                     if (tc::elect_one()) {
-                        t16_issue_theta(tD, tA, sG_hi, sG_lo, idesc_c, 1);
+                        t16_issue_theta(tD, tA, sG_hi, sG_lo, idesc_c, 1, nks);
                         tc::mma_commit(respA);
-                        t16_issue_z(tD + 128, z_hi, z_lo, inj, sT_hi, sT_lo, idesc_64, 0);
+                        t16_issue_z(tD + 128, z_hi, z_lo, inj, sT_hi, sT_lo, idesc_64, 0, nks);
                         tc::mma_commit(respB);
                         tc::mma_commit(bar_zfree + t * 2 + b);
                     }
@@ -556,7 +562,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     tc::fence_after_sync();
                     if (tc::elect_one()) {
                         const uint32_t b_hi = ring_base + st * T16_CHUNK_BYTES, b_lo = b_hi + T16_TIMG;
-                        t16_issue_theta(tD + b * T16_CH, tA, b_hi, b_lo, idesc_64, 0);
+                        t16_issue_theta(tD + b * T16_CH, tA, b_hi, b_lo, idesc_64, 0, nks);
                         tc::mma_commit(respF + b);
                         tc::mma_commit(bar_empty + st);
                     }
