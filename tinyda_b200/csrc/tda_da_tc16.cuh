@@ -1,5 +1,13 @@
 // Tensor-core (tcgen05 / TMEM) Delayed-Acceptance kernel, third generation ("tc16"): two-level DA,
-// pCN proposal, linear forward operators, isotropic likelihoods (BASELINE cfg2), float32 engine.
+// pCN proposal, linear forward operators, Gaussian likelihoods (BASELINE cfg2), float32 engine.
+// Native shape d = 64, m_c a multiple of 16 (<= 128), m_f a multiple of 64 (<= 1920), isotropic
+// likelihoods; prepare() maps the rest onto it on the host: d in {16, 32, 48} and other output counts
+// by zero padding (kernel template PAD), diagonal / dense likelihoods (distributions.py:304-315,
+// :246-301) by whitening the operators and the data with the Cholesky factor of the precision.
+// History: fine-level Links, and -- the reference's default store_coarse_chain=True,
+// sampler.py:421-436 -- the parameters, log-likelihood and accept flag of every coarse Link; the
+// fields the kernel does not hold (coarse log-prior, Link.model_output) are rebuilt from the recorded
+// parameters when first fetched (EngineT::fill_lazy_history in tda_engine.cu).
 //
 // What changed against tda_da_tc.cuh (3xTF32, draws on the row threads):
 //
