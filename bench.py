@@ -173,6 +173,64 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def sharded_self_check(rank, world, local_rank):
+    """Untimed, N > 1 only: sharding a job over the ranks must change nothing.  (1) DREAM with the shared
+    archive -- the path's one real exchange step: each step's new archive rows all-gathered over NCCL
+    (ray.py:366-384) -- and (2) the Delayed-Acceptance job sharded by tda.sample() are compared, bit for
+    bit, with the same job on ONE engine.  The verdict is AND-reduced over the ranks."""
+    import contextlib
+    import io
+    import torch
+    import torch.distributed as dist
+    import tinyda_b200 as tda
+    from tinyda_b200 import lower_problem, parallel, workloads
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    ok = {}
+    try:
+        w = workloads.cfg5_dream()
+        C, iters, M0, d = 128 * world, 24, 16, 32
+        rng = np.random.default_rng(5)
+        theta0 = np.atleast_2d(w["prior"].rvs(C, random_state=rng))
+        archive0 = w["prior"].rvs(C * M0, random_state=rng).reshape(C, M0, d)
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = tda.sample(w["posteriors"][0], w["proposal"], iters, n_chains=C, initial_parameters=theta0, seed=9,
+                             initial_archive=archive0, store_model_output=False, dtype="float32", device=local_rank)
+        lo, hi = res.local_chains
+        mine = res.history.dense("theta")
+        eng = Engine(lower_problem(w["posteriors"], w["proposal"]), C, dtype="float32", seed=9, store=STORE_STATS,
+                     capacity_iterations=iters, device=local_rank, archive0=archive0)
+        eng.init(theta0)
+        eng.run(iters)
+        one = np.transpose(eng.fetch(0, "theta"), (2, 0, 1))
+        eng.close()
+        ok["dream_shared_allgather"] = bool(np.array_equal(mine, one[lo:hi]) and np.abs(np.diff(mine, axis=1)).max() > 0)
+
+        w2 = workloads.cfg2_da()
+        C2, it2 = 256 * world, 12
+        th2 = w2["prior"].rvs(C2, random_state=np.random.default_rng(2))
+        with contextlib.redirect_stdout(io.StringIO()):
+            res2 = tda.sample(w2["posteriors"], w2["proposal"], it2, n_chains=C2, initial_parameters=th2, subchain_length=10,
+                              seed=4, store_model_output=False, store_coarse_chain=False, dtype="float32", device=local_rank,
+                              chunk_iterations=5)
+        lo2, hi2 = res2.local_chains
+        mine2 = res2.history.dense("theta")
+        eng = Engine(lower_problem(w2["posteriors"], w2["proposal"], 10), C2, dtype="float32", seed=4,
+                     store=[STORE_NONE, STORE_STATS], capacity_iterations=it2, device=local_rank)
+        eng.init(th2)
+        eng.run(it2)
+        one2 = np.transpose(eng.fetch(1, "theta"), (2, 0, 1))
+        eng.close()
+        ok["da_sharded_by_sample"] = bool(np.array_equal(mine2, one2[lo2:hi2]))
+    except Exception as exc:                     # a failed check is reported, it does not kill the benchmark line
+        ok["error"] = repr(exc)[:300]
+    flag = torch.tensor([1 if (ok.get("dream_shared_allgather") and ok.get("da_sharded_by_sample")) else 0],
+                        dtype=torch.int32, device=torch.device("cuda", local_rank))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok["sharded_equals_single"] = bool(int(flag.item()))
+    ok["ranks"] = world
+    return ok
+
+
 def run_ours(args):
     import torch
     from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE, launch_count
@@ -204,7 +262,7 @@ def run_ours(args):
     if args.kernel != "auto":
         eng.select_kernel(args.kernel)
     eng.init(theta0)
-    eng.run(100 if not args.quick else 10)      # burn-in from the prior draws
+    eng.run(300 if not args.quick else 10, record=False)      # burn-in from the prior draws (nothing recorded)
     eng.sync()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
 
@@ -222,6 +280,7 @@ def run_ours(args):
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
+    acc_t0 = eng.get("accept_counts").astype(np.float64)
     l0 = launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
@@ -233,74 +292,99 @@ def run_ours(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = launch_count() - l0
+    acc_t1 = eng.get("accept_counts").astype(np.float64)
+    accept_timed = {"coarse": float((acc_t1[0] - acc_t0[0]).mean() / (iters * args.steps * J0)),
+                    "fine": float((acc_t1[1] - acc_t0[1]).mean() / (iters * args.steps))}
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     dev_ms = float(sum(ms_steps))
 
-    # ---- end-to-end arm: host buffers in, host buffers out -------------------------------
-    n_rec = iters
-    np_dt = np.float32 if dtype == "float32" else np.float64
-    pin_theta0 = torch.from_numpy(theta0).pin_memory()
-    h_theta = torch.empty((n_rec, d, C), dtype=torch.float32 if dtype == "float32" else torch.float64).pin_memory()
-    h_prior = torch.empty((n_rec, C), dtype=h_theta.dtype).pin_memory()
-    h_like = torch.empty((n_rec, C), dtype=h_theta.dtype).pin_memory()
-    h_acc = torch.empty((n_rec, C), dtype=torch.uint8).pin_memory()
-    if coarse_hist:
-        c_theta = torch.empty((n_rec * J0, d, C), dtype=h_theta.dtype).pin_memory()
-        c_prior = torch.empty((n_rec * J0, C), dtype=h_theta.dtype).pin_memory()
-        c_like = torch.empty((n_rec * J0, C), dtype=h_theta.dtype).pin_memory()
-        c_acc = torch.empty((n_rec * J0, C), dtype=torch.uint8).pin_memory()
+    # ---- end-to-end arm: the user's call, host buffers in, host buffers out -----------------
+    # tda.sample(...) itself (the drop-in for tinyDA.sample): initial parameters in pinned host memory ->
+    # H2D -> engine construction + initial Links + the run in blocks; after every block the finest level's
+    # records are compacted on the device to the accepted ones (a rejected step repeats the previous Link,
+    # chain.py:116, :434) and copied to pinned host memory while the next block runs.  The chains start from
+    # the burnt-in states the device arm left (so the accept rates are the stationary ones).
+    import contextlib
+    import io
+    import tinyda_b200 as tda
+    from tinyda_b200.engine import pinned_empty
+    e2e_iters = args.e2e_iters if args.e2e_iters is not None else (1000 if not args.quick else 40)
+    cur = eng.get("theta", 1)                                            # [C, d] float64, burnt-in states
+    theta_host = pinned_empty((world * C, d), np.float64)
+    theta_host[:] = 0.0
+    theta_host[rank * C:(rank + 1) * C] = cur
+    store_coarse = coarse_hist
+    d2h_seen = [0]
 
-    # the run is cut into chunks; the history of chunk k travels to the host on a second stream
-    # while chunk k+1 computes (the user-facing pattern for long runs: tda_engine_run is
-    # re-entrant and tda_fetch is asynchronous on its stream)
-    copy_stream = torch.cuda.Stream(device=dev)
-    n_chunks = max(1, min(5, iters // 5))
-    bounds = [iters * k // n_chunks for k in range(n_chunks + 1)]
-    chunk_events = [torch.cuda.Event() for _ in range(n_chunks)]
+    def e2e_step(k):
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = tda.sample(w["posteriors"], w["proposal"], e2e_iters, n_chains=world * C, initial_parameters=theta_host,
+                             subchain_length=J0, dtype=dtype, seed=5000 + k, store_model_output=False,
+                             store_coarse_chain=store_coarse, device=local_rank)
+        h = res.history
+        # the device->host read of the step's result: every block's accept flags, row offsets and accepted rows
+        d2h_seen[0] = sum(ch.accept.nbytes + ch.offsets.nbytes + ch.theta.nbytes + ch.prior.nbytes + ch.like.nbytes for ch in h.chunks)
+        assert h.n_records == e2e_iters + 1
+        return float(h.chunks[-1].like[-1])
 
-    def e2e_step():
-        eng.history_reset()
-        eng.init(pin_theta0.numpy())                     # H2D initial states + initial links
-        cur = torch.cuda.current_stream()
-        for k in range(n_chunks):
-            a, b = bounds[k], bounds[k + 1]
-            eng.run(b - a)
-            chunk_events[k].record(cur)
-            copy_stream.wait_event(chunk_events[k])
-            cs = copy_stream.cuda_stream
-            eng.fetch(1, "theta", 1 + a, b - a, out=h_theta.numpy()[a:b], stream=cs, sync=False)
-            eng.fetch(1, "prior", 1 + a, b - a, out=h_prior.numpy()[a:b], stream=cs, sync=False)
-            eng.fetch(1, "like", 1 + a, b - a, out=h_like.numpy()[a:b], stream=cs, sync=False)
-            eng.fetch(1, "accept", 1 + a, b - a, out=h_acc.numpy()[a:b], stream=cs, sync=False)
-            if coarse_hist:
-                ca, cb = a * J0, b * J0
-                eng.fetch(0, "theta", ca, cb - ca, out=c_theta.numpy()[ca:cb], stream=cs, sync=False)
-                eng.fetch(0, "prior", ca, cb - ca, out=c_prior.numpy()[ca:cb], stream=cs, sync=False)
-                eng.fetch(0, "like", ca, cb - ca, out=c_like.numpy()[ca:cb], stream=cs, sync=False)
-                eng.fetch(0, "accept", ca, cb - ca, out=c_acc.numpy()[ca:cb], stream=cs, sync=False)
-        copy_stream.synchronize()
-
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
+    e2e_steps = max(2, min(args.steps, 3))
+    e2e_step(-1)
     barrier()
+    l_e2e0 = launch_count()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for k in range(e2e_steps):
+        e2e_step(k)
     barrier()
     e2e_wall = time.perf_counter() - t0
+    e2e_launches = launch_count() - l_e2e0
+
+    # engine-level variant of the same thing (no engine construction in the timed region): init from the
+    # pinned states + run in blocks + compaction + D2H, through the C ABI calls sample() makes
+    from tinyda_b200.link import CompactHistory
+    n_chunks = max(1, min(5, iters // 5))
+    bounds = [iters * k // n_chunks for k in range(n_chunks + 1)]
+    pin_cur = pinned_empty((C, d), np.float64)
+    pin_cur[:] = cur
+
+    def engine_e2e_step():
+        hist = CompactHistory(C)
+        eng.init(pin_cur)
+        pending = None
+        for k in range(n_chunks):
+            if k:
+                eng.history_reset()
+            n = bounds[k + 1] - bounds[k]
+            eng.run(n)
+            eng.compact_begin(0, n + (k == 0), k == 0, ("theta", "stats"), slot=k & 1)
+            if pending is not None:
+                hist.append(eng.compact_collect(pending))
+            pending = k & 1
+        hist.append(eng.compact_collect(pending))
+        eng.compact_sync()
+        return hist
+
+    engine_e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    eng_e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(eng_e2e_steps):
+        hist_e = engine_e2e_step()
+    barrier()
+    eng_e2e_wall = time.perf_counter() - t0
+    eng_d2h = sum(ch.accept.nbytes + ch.offsets.nbytes + ch.theta.nbytes + ch.prior.nbytes + ch.like.nbytes for ch in hist_e.chunks)
     clock_info = clocks.stop()
 
-    times = torch.tensor([dev_ms, e2e_wall * 1e3, t_wall * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_wall * 1e3, t_wall * 1e3, eng_e2e_wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms = [float(x) for x in times.cpu()]
+    dev_ms, e2e_ms, wall_ms, eng_e2e_ms = [float(x) for x in times.cpu()]
     total_trans = float(world) * C * iters * args.steps
     value = total_trans / (dev_ms * 1e-3)
-    e2e_value = float(world) * C * iters * e2e_steps / (e2e_ms * 1e-3)
-    h2d = theta0.nbytes
-    d2h = h_theta.numel() * h_theta.element_size() + 2 * h_prior.numel() * h_prior.element_size() + h_acc.numel()
-    if coarse_hist:
-        d2h += c_theta.numel() * c_theta.element_size() + 2 * c_prior.numel() * c_prior.element_size() + c_acc.numel()
+    e2e_value = float(world) * C * e2e_iters * e2e_steps / (e2e_ms * 1e-3)
+    eng_e2e_value = float(world) * C * iters * eng_e2e_steps / (eng_e2e_ms * 1e-3)
+    h2d = C * d * 8
+    d2h = d2h_seen[0]
+    checks = sharded_self_check(rank, world, local_rank) if world > 1 else None
 
     kernel_used = args.kernel if args.kernel != "auto" else ("tc16" if dtype == "float32" else "generic")
     ess = None
@@ -330,8 +414,9 @@ def run_ours(args):
         pk, src = measured_peaks()
         per_gpu_rate = C * iters / (np.mean(ms_steps) * 1e-3)
         achieved = per_gpu_rate * F_ALG / 1e12
-        peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
-        acc = eng.get("accept_counts")
+        # every timed step is one isolated launch of a few milliseconds: the burst figure applies
+        peak = float(pk.get("bf16_tflops", pk.get("bf16_tflops_sustained")))
+        peak_sustained = float(pk.get("bf16_tflops_sustained", peak))
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -348,11 +433,23 @@ def run_ours(args):
                       "L2/SMEM-resident by design", "kernel": eng_kernel_name(args, dtype),
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "what": "pinned initial states H2D + init + run in %d chunks + fine history D2H to pinned, copies overlapped with the next chunk" % n_chunks},
+                    "steps": e2e_steps, "fine_iterations_per_step": e2e_iters, "gpu_launches": int(e2e_launches),
+                    "what": "tinyda_b200.sample(posteriors, pCN, %d iterations, n_chains=%d, initial_parameters=<pinned host array>, "
+                            "dtype=float32, store_model_output=False, store_coarse_chain=%s): engine construction, initial states "
+                            "H2D, initial Links, the run in blocks, device-side compaction of each block to its accepted "
+                            "records, D2H to pinned host memory overlapped with the next block, lazy result dict"
+                            % (e2e_iters, world * C, store_coarse),
+                    "d2h_bytes_per_transition": d2h / float(C * e2e_iters),
+                    "engine_level": {"value": eng_e2e_value, "unit": UNIT, "steps": eng_e2e_steps, "fine_iterations_per_step": iters,
+                                     "d2h_bytes_per_step": int(eng_d2h),
+                                     "what": "the same C-ABI calls on a live engine (no construction in the timed region): "
+                                             "pinned states H2D + tda_engine_init + %d x (tda_engine_run, tda_compact_begin, "
+                                             "tda_compact_fetch)" % n_chunks}},
             "gpu_launches": int(launches),
             "clocks": clock_info,
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "frac_of_sustained_peak": achieved / peak_sustained,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one da_tc16_kernel launch of this very
                 # command (ncu --set full, profiles/r01_ncu_tc16_summary.txt): 0.164 + 1.148 GB against
                 # 0.868 GB of algorithmic history bytes (265 B x 3,276,800 transitions)
@@ -360,15 +457,16 @@ def run_ours(args):
                 "executed_tflops": per_gpu_rate * F_EXEC_TC16 / 1e12 if kernel_used == "tc16" else None,
                 "executed_frac": per_gpu_rate * F_EXEC_TC16 / 1e12 / peak if kernel_used == "tc16" else None,
                 "note": "achieved = 458752 algorithmic flop/transition x per-GPU transitions/s "
-                        "(CUDA events, mean over timed launches); peak = bf16 dense sustained, " + src +
+                        "(CUDA events, mean over timed launches); peak = bf16 dense burst (each timed step is one isolated launch), " + src +
                         " (MEASURED_PEAKS.json). fp32-grade accuracy on 16-bit tensor cores needs a two-term "
                         "fp16 split (3 products per contraction), so the algorithmic figure caps near peak/3; "
                         "executed_* counts the fp16 tensor flop the kernel really issues (1.40 MFLOP/transition)",
             },
-            "accept_rate": {"coarse": float(acc[0].mean() / max(1, eng.iterations_done * spec["J"][0])),
-                            "fine": float(acc[1].mean() / max(1, eng.iterations_done))},
+            "accept_rate_timed_region": accept_timed,
             "wall_ms_timed_region": wall_ms,
         }
+        if checks is not None:
+            out["checks"] = checks
         if coarse_hist:
             hb = 265 + J0 * 261
             out["link_writeout"] = {"bytes_per_transition": hb, "achieved_gbs": per_gpu_rate * hb / 1e9,
@@ -611,6 +709,7 @@ def main():
     ap.add_argument("--history", default="fine", choices=["fine", "coarse"],
                     help="cfg2: 'fine' = fine-level Links only (the headline line); 'coarse' = the reference's "
                          "store_coarse_chain=True: every coarse Link (theta, log-like, accept) is recorded too")
+    ap.add_argument("--e2e-iters", type=int, default=None, help="fine iterations per tda.sample() call of the e2e arm (default 1000)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--quick", action="store_true")

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define TDA_ABI_VERSION 2
+#define TDA_ABI_VERSION 3
 #define TDA_MAX_LEVELS 4
 #define TDA_MAX_D 64
 
@@ -87,7 +87,8 @@ typedef struct tda_level_config {
     double lik_var;         /* isotropic variance                              */
     double model_scalars[4];
     int32_t store;          /* TDA_STORE_* flags                               */
-    int32_t reserved;
+    int32_t n_qoi;          /* quantities of interest the model returns next to its output
+                             * (posterior.py:95-105: a tuple -> (output, qoi)); 0 = none  */
     int64_t hist_capacity;  /* records per chain the level's history can hold  */
 } tda_level_config;
 
@@ -159,6 +160,9 @@ typedef struct tda_config {
                              * as TDA_UP_PROP_T, its whitening matrix as TDA_UP_PROP_S, its mean as TDA_UP_PROP_LAMBDA */
 #define TDA_UP_PROP_S2 17       /* adaptive OWPCN: [d][d] V^T                        */
 #define TDA_UP_PROP_LAMBDA 18   /* adaptive OWPCN: [d] eigenvalues of B              */
+#define TDA_UP_QOI_W 19         /* level: [n_qoi][m] Q, the quantity of interest is the linear functional
+                                 * qoi = Q @ F(theta) + q0 of the model output       */
+#define TDA_UP_QOI_B 20         /* level: [n_qoi] q0                                 */
 
 /* tda_fetch 'field' */
 #define TDA_F_THETA 1           /* [nrec][d][n_chains]   engine dtype               */
@@ -166,6 +170,9 @@ typedef struct tda_config {
 #define TDA_F_LIKE 3            /* [nrec][n_chains]      engine dtype               */
 #define TDA_F_OUTPUT 4          /* [nrec][m][n_chains]   engine dtype               */
 #define TDA_F_ACCEPT 5          /* [nrec][n_chains]      uint8                      */
+#define TDA_F_QOI 6             /* [nrec][n_qoi][n_chains] engine dtype: Link.qoi (link.py:38-48), rebuilt from the
+                                 * recorded parameters (linear models) or model outputs when it is fetched */
+#define TDA_CF_OFFSETS 7        /* tda_compact_fetch only: int64 [n_chains + 1] row offsets per chain */
 
 /* tda_get / tda_set 'what' (float64 on the host side unless noted) */
 #define TDA_G_SCALING 1         /* [n_chains]                                       */
@@ -178,6 +185,9 @@ typedef struct tda_config {
 #define TDA_G_MOMENTS 8         /* finest level running sums: [2][d][n_chains] (sum x, sum x^2) */
 #define TDA_G_TC16_TIMELINE 10  /* get only, diagnostic: int64 [4][256] clock64 stamps of CTA 0 of kernel 3 (first call arms the probe) */
 #define TDA_G_KERNEL 11         /* get only: int64 [1], the kernel tda_engine_run would launch now (ids of tda_select_kernel) */
+#define TDA_G_ERROR_FLAGS 12    /* get only: int64 [1], sticky numerical-trouble flags since tda_engine_init: bit 0 = a
+                                 * non-positive Cholesky pivot was clamped (error-model covariance / AM covariance);
+                                 * the reference's SVD / np.linalg.inv do not fail there, so the chains go on */
 #define TDA_G_ZROUND 9          /* set only: one float64 flag; non-zero = Philox normals on the fp16 grid
                                  * ("z16" stream) also for the generic / 3xTF32 kernels (float32 engine) */
 
@@ -191,7 +201,10 @@ int tda_engine_destroy(tda_engine *e);
 
 int tda_upload(tda_engine *e, int what, int level, const double *host, size_t count);
 int tda_engine_init(tda_engine *e, void *cuda_stream);
+/* Fails (-1) without launching when a level that stores history would run past its hist_capacity. */
 int tda_engine_run(tda_engine *e, int64_t iterations, void *cuda_stream);
+/* Same transitions with nothing recorded (burn-in): history position and buffers are untouched. */
+int tda_engine_burn(tda_engine *e, int64_t iterations, void *cuda_stream);
 int tda_engine_sync(tda_engine *e, void *cuda_stream);
 
 /* Copies history records [rec0, rec0+nrec) of one level into host memory (pinned or
@@ -218,6 +231,30 @@ int tda_dream_slots(tda_engine *e, int64_t *slots);
 /* Fills host arrays z[n_chains][nz], u[n_chains][nu] (float64) with the values the engine's
  * Philox streams deliver in the engine dtype -- what TDA_RNG_PHILOX mode consumes. */
 int tda_fill_streams(tda_engine *e, double *z, int64_t nz, double *u, int64_t nu);
+
+/* Compacted history of the FINEST level: a rejected step re-appends the same Link object in the
+ * reference (chain.py:116, :434; proposal.py:1601), so a record whose accept flag is 0 equals the record
+ * before it.  tda_compact_begin enqueues, on cuda_stream, the device-side compaction of records
+ * [rec0, rec0+nrec) into engine-owned buffers of `slot` (0 or 1): the accept flag of every record
+ * (first_is_full != 0: record rec0 counts as accepted whatever its flag -- the initial Link) and, chain by
+ * chain, the fields (TDA_STORE_THETA | TDA_STORE_STATS | TDA_STORE_OUTPUT, plus TDA_STORE_QOI) of the
+ * accepted records only.  tda_compact_rows blocks until the row count of the slot is known.
+ * tda_compact_fetch enqueues the device->host copy of one field on the engine's copy stream (pinned host
+ * memory makes it asynchronous, so that it overlaps the next tda_engine_run): TDA_F_ACCEPT
+ * [nrec][n_chains] uint8, TDA_CF_OFFSETS int64 [n_chains+1] (rows of chain c: offsets[c]..offsets[c+1]),
+ * TDA_F_THETA [n_rows][d], TDA_F_PRIOR / TDA_F_LIKE [n_rows], TDA_F_OUTPUT [n_rows][m], TDA_F_QOI
+ * [n_rows][n_qoi], engine dtype.  tda_compact_sync waits for the copies.  The next tda_engine_run may
+ * overwrite the dense records as soon as tda_compact_begin has been enqueued on the same stream. */
+#define TDA_STORE_QOI 16
+int tda_compact_begin(tda_engine *e, int level, int64_t rec0, int64_t nrec, int first_is_full, int fields,
+                      int slot, void *cuda_stream);
+int tda_compact_rows(tda_engine *e, int slot, int64_t *n_rows);
+int tda_compact_fetch(tda_engine *e, int slot, int field, void *host_dst, size_t dst_bytes, size_t *bytes);
+int tda_compact_sync(tda_engine *e);
+
+/* Page-locked host memory for asynchronous copies (cudaHostAlloc / cudaFreeHost). */
+int tda_host_alloc(size_t bytes, void **ptr);
+int tda_host_free(void *ptr);
 
 /* Rewinds the history write position of every level to record 0 (the buffers are reused;
  * call after the records have been fetched).  The chains themselves are unaffected. */

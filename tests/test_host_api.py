@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "library does not export %s" % name
     from tinyda_b200 import _lib
     assert set(_lib.EXPORTS) == declared
-    assert lib.tda_abi_version() == 2
+    assert lib.tda_abi_version() == 3
 
 
 def test_config_struct_layout_matches_header(tmp_path):
@@ -273,3 +273,83 @@ def test_model_classes_keep_the_reference_model_protocol():
     h = 1e-6
     fd = np.array([(r(th + h * np.eye(2)[i])[0] - r(th - h * np.eye(2)[i])[0]) / (2 * h) for i in range(2)])
     np.testing.assert_allclose(g, fd, rtol=1e-6)
+
+
+def _compact_numpy(theta, prior, like, acc, bounds):
+    """NumPy statement of the device compaction (tda_compact_*): dense [nrec, C(, d)] history -> chunks."""
+    from tinyda_b200.engine import CompactChunk
+    chunks = []
+    for k, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+        fl = acc[a:b].copy()
+        if k == 0:
+            fl[0] = 1
+        ch = CompactChunk(b - a)
+        ch.accept = fl.astype(np.uint8)
+        counts = fl.sum(axis=0)
+        ch.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        rows_t, rows_p, rows_l = [], [], []
+        for c in range(acc.shape[1]):
+            sel = np.nonzero(fl[:, c])[0] + a
+            rows_t.append(theta[sel, c]); rows_p.append(prior[sel, c]); rows_l.append(like[sel, c])
+        ch.theta = np.concatenate(rows_t); ch.prior = np.concatenate(rows_p); ch.like = np.concatenate(rows_l)
+        chunks.append(ch)
+    return chunks
+
+
+def test_compact_history_expands_to_the_dense_history():
+    """A rejected step repeats the previous Link (chain.py:116, :434): the compacted form (accept flags +
+    accepted rows, block by block) must expand to the dense history bit for bit, per chain and in bulk."""
+    from tinyda_b200.link import CompactHistory, SampleResult, LinkSequence
+    rng = np.random.default_rng(5)
+    nrec, C, d = 41, 7, 3
+    acc = (rng.random((nrec, C)) < 0.3).astype(np.uint8)
+    acc[:, 2] = 0                                  # a chain that never moves
+    acc[:, 4] = 1                                  # one that always does
+    theta = np.zeros((nrec, C, d)); prior = np.zeros((nrec, C)); like = np.zeros((nrec, C))
+    cur_t, cur_p, cur_l = rng.standard_normal((C, d)), rng.standard_normal(C), rng.standard_normal(C)
+    for r in range(nrec):
+        mv = acc[r].astype(bool) | (r == 0)
+        cur_t = np.where(mv[:, None], rng.standard_normal((C, d)), cur_t)
+        cur_p = np.where(mv, rng.standard_normal(C), cur_p)
+        cur_l = np.where(mv, rng.standard_normal(C), cur_l)
+        theta[r], prior[r], like[r] = cur_t, cur_p, cur_l
+    for bounds in ([0, nrec], [0, 1, 9, 10, 30, nrec]):
+        hist = CompactHistory(C)
+        for ch in _compact_numpy(theta, prior, like, acc, bounds):
+            hist.append(ch)
+        assert hist.n_records == nrec
+        for c in range(C):
+            seq = hist.chain(c)
+            assert np.array_equal(seq.parameters, theta[:, c]) and np.array_equal(seq.prior, prior[:, c])
+            assert np.array_equal(seq.likelihood, like[:, c])
+            assert np.array_equal(seq.accepted[1:], acc[1:, c].astype(bool)) and not seq.accepted[0]
+        assert np.array_equal(hist.dense("theta"), np.swapaxes(theta, 0, 1))
+        assert np.array_equal(hist.dense("like", burnin=4), like[4:].T)
+    # the result dict materialises a chain when its key is first read
+    res = SampleResult({"sampler": "MH", "n_chains": C, "iterations": nrec})
+    res.add_chains("chain_{}", 0, C, hist.chain)
+    res.history, res.local_chains = hist, (0, C)
+    assert not dict.__contains__(res, "chain_3") and "chain_3" in res and "chain_7" not in res and "chain_x" not in res
+    assert isinstance(res["chain_3"], LinkSequence) and dict.__contains__(res, "chain_3")
+    assert len(res) == 3 + C and list(res)[:3] == ["sampler", "n_chains", "iterations"] and list(res)[-1] == "chain_%d" % (C - 1)
+    assert all(isinstance(v, LinkSequence) for k, v in res.items() if k.startswith("chain_"))
+    with pytest.raises(KeyError):
+        res["chain_99"]
+    import tinyda_b200 as tda
+    s = tda.get_samples(res, "parameters", burnin=2)
+    assert np.array_equal(s["chain_5"], theta[2:, 5]) and s["iterations"] == nrec - 2
+    st = tda.get_samples(res, "stats")
+    assert np.array_equal(st["chain_1"][:, 2], prior[:, 1] + like[:, 1])
+
+
+def test_models_return_output_and_qoi_like_the_reference_protocol():
+    """posterior.py:95-105: a model may return (output, qoi)."""
+    import tinyda_b200 as tda
+    G = np.arange(12.0).reshape(4, 3)
+    Q = np.array([[1.0, 0, 0, -1.0], [0.5, 0.5, 0.5, 0.5]])
+    m = tda.LinearModel(G, qoi=(Q, [1.0, 2.0]))
+    out, q = m(np.array([1.0, 2.0, 3.0]))
+    assert np.allclose(q, Q @ out + [1.0, 2.0])
+    low = m.lower()
+    assert low["n_qoi"] == 2 and low["qoi_Q"].shape == (2, 4)
+    assert tda.LinearModel(G).lower()["n_qoi"] == 0 and isinstance(tda.LinearModel(G)(np.zeros(3)), np.ndarray)

@@ -10,19 +10,19 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtinyda_b200.so")
 
-TDA_ABI_VERSION = 2
+TDA_ABI_VERSION = 3
 TDA_MAX_LEVELS = 4
 TDA_MAX_D = 64
 TDA_F32, TDA_F64 = 0, 1
 TDA_RNG_PHILOX, TDA_RNG_INJECTED = 0, 1
-TDA_STORE_THETA, TDA_STORE_STATS, TDA_STORE_OUTPUT, TDA_STORE_ACCEPT = 1, 2, 4, 8
+TDA_STORE_THETA, TDA_STORE_STATS, TDA_STORE_OUTPUT, TDA_STORE_ACCEPT, TDA_STORE_QOI = 1, 2, 4, 8, 16
 (TDA_UP_PRIOR_MEAN, TDA_UP_PRIOR_LP, TDA_UP_PRIOR_PREC, TDA_UP_PROP_T, TDA_UP_MODEL_A, TDA_UP_MODEL_B,
  TDA_UP_LIK_DATA, TDA_UP_LIK_VAR, TDA_UP_LIK_PREC, TDA_UP_LIK_COV, TDA_UP_INIT_THETA, TDA_UP_STREAM_Z,
  TDA_UP_STREAM_U, TDA_UP_DREAM_ARCHIVE0, TDA_UP_AM_FACTORS, TDA_UP_PROP_S, TDA_UP_PROP_S2,
- TDA_UP_PROP_LAMBDA) = range(1, 19)
-TDA_F_THETA, TDA_F_PRIOR, TDA_F_LIKE, TDA_F_OUTPUT, TDA_F_ACCEPT = 1, 2, 3, 4, 5
+ TDA_UP_PROP_LAMBDA, TDA_UP_QOI_W, TDA_UP_QOI_B) = range(1, 21)
+TDA_F_THETA, TDA_F_PRIOR, TDA_F_LIKE, TDA_F_OUTPUT, TDA_F_ACCEPT, TDA_F_QOI, TDA_CF_OFFSETS = 1, 2, 3, 4, 5, 6, 7
 (TDA_G_SCALING, TDA_G_ACCEPT_COUNTS, TDA_G_CURSORS, TDA_G_AM_SIGMA, TDA_G_AM_MU, TDA_G_THETA,
- TDA_G_NRECORDS, TDA_G_MOMENTS, TDA_G_ZROUND, TDA_G_TC16_TIMELINE, TDA_G_KERNEL) = range(1, 12)
+ TDA_G_NRECORDS, TDA_G_MOMENTS, TDA_G_ZROUND, TDA_G_TC16_TIMELINE, TDA_G_KERNEL, TDA_G_ERROR_FLAGS) = range(1, 13)
 TDA_BUF_DREAM_ARCHIVE, TDA_BUF_HIST_THETA = 1, 2
 
 EXPORTS = [
@@ -31,6 +31,8 @@ EXPORTS = [
     "tda_device_buffer", "tda_dream_slots", "tda_fill_streams", "tda_history_reset",
     "tda_select_kernel", "tda_launch_count", "tda_tc_gemm_selftest", "tda_tc16_gemm_selftest",
     "tda_state_size", "tda_state_save", "tda_state_load",
+    "tda_engine_burn", "tda_compact_begin", "tda_compact_rows", "tda_compact_fetch", "tda_compact_sync",
+    "tda_host_alloc", "tda_host_free",
 ]
 
 
@@ -38,7 +40,7 @@ class LevelConfig(C.Structure):
     _fields_ = [
         ("model_kind", C.c_int32), ("m", C.c_int32), ("n_grid", C.c_int32), ("lik_kind", C.c_int32),
         ("lik_var", C.c_double), ("model_scalars", C.c_double * 4),
-        ("store", C.c_int32), ("reserved", C.c_int32), ("hist_capacity", C.c_int64),
+        ("store", C.c_int32), ("n_qoi", C.c_int32), ("hist_capacity", C.c_int64),
     ]
 
 
@@ -77,6 +79,13 @@ def _load():
     lib.tda_engine_init.argtypes = [vp, vp]
     lib.tda_engine_run.argtypes = [vp, i64, vp]
     lib.tda_engine_sync.argtypes = [vp, vp]
+    lib.tda_engine_burn.argtypes = [vp, i64, vp]
+    lib.tda_compact_begin.argtypes = [vp, i32, i64, i64, i32, i32, i32, vp]
+    lib.tda_compact_rows.argtypes = [vp, i32, C.POINTER(i64)]
+    lib.tda_compact_fetch.argtypes = [vp, i32, i32, vp, sz, C.POINTER(sz)]
+    lib.tda_compact_sync.argtypes = [vp]
+    lib.tda_host_alloc.argtypes = [sz, C.POINTER(vp)]
+    lib.tda_host_free.argtypes = [vp]
     lib.tda_fetch.argtypes = [vp, i32, i32, i64, i64, vp, sz, C.POINTER(sz), vp]
     lib.tda_get.argtypes = [vp, i32, i32, vp, sz]
     lib.tda_set.argtypes = [vp, i32, i32, vp, sz]

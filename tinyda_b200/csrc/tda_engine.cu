@@ -10,6 +10,7 @@
 #include "tda_da_tc.cuh"
 #include "tda_da_tc16.cuh"
 #include "tda_mh_reg.cuh"
+#include "tda_post.h"
 
 namespace {
 
@@ -36,7 +37,11 @@ struct tda_engine {
     virtual ~tda_engine() {}
     virtual int upload(int what, int level, const double* host, size_t count) = 0;
     virtual int init(cudaStream_t st) = 0;
-    virtual int run(long long iterations, cudaStream_t st) = 0;
+    virtual int run(long long iterations, cudaStream_t st, bool record = true) = 0;
+    virtual int compact_begin(int level, long long rec0, long long nrec, int first_is_full, int fields, int slot, cudaStream_t st) = 0;
+    virtual int compact_rows(int slot, long long* n_rows) = 0;
+    virtual int compact_fetch(int slot, int field, void* dst, size_t dst_bytes, size_t* bytes) = 0;
+    virtual int compact_sync() = 0;
     virtual int fetch(int level, int field, long long rec0, long long nrec, void* dst, size_t dst_bytes,
                       size_t* bytes, cudaStream_t st) = 0;
     virtual int get(int what, int level, void* dst, size_t bytes) = 0;
@@ -147,6 +152,22 @@ __global__ void __launch_bounds__(256) hist_fill_kernel(const R* __restrict__ th
     if (mode == 1) *dst = (R)-0.5 * (logconst + ssq);
 }
 
+// Link.qoi of models that are not linear in theta: qoi[r][j][c] = q0[j] + sum_n Q[j][n] * F[r][n][c]
+// (thread = one (record, chain); lane = chain -> coalesced)
+template <typename R>
+__global__ void __launch_bounds__(256) qoi_from_F_kernel(const R* __restrict__ F, const R* __restrict__ Q, const R* __restrict__ q0,
+                                                         R* __restrict__ out, int m, int nq, int Cs) {
+    const int cblocks = Cs / 256;
+    const size_t r = blockIdx.x / cblocks;
+    const int c = (int)(blockIdx.x - r * cblocks) * 256 + threadIdx.x;
+    const R* f = F + r * (size_t)m * Cs + c;
+    for (int j = 0; j < nq; j++) {
+        R a = q0 ? q0[j] : (R)0;
+        for (int n = 0; n < m; n++) a = fma(__ldg(Q + (size_t)j * m + n), f[(size_t)n * Cs], a);
+        out[(r * nq + j) * (size_t)Cs + c] = a;
+    }
+}
+
 template <typename R>
 struct EngineT : tda_engine {
     tda::Params<R> P;
@@ -169,10 +190,43 @@ struct EngineT : tda_engine {
     // have not been filled yet, per level; and: the levels' current model outputs lag behind theta
     long long lazy_lo[tda::MAXL] = {0, 0, 0, 0}, lazy_hi[tda::MAXL] = {0, 0, 0, 0};
     bool state_F_stale = false;
+    bool burning = false;      // inside tda_engine_burn: nothing is recorded
+    // quantities of interest: qoi = Q @ F(theta) + q0 per level.  Linear models: composed with the operator
+    // on upload (qoi_W = G^T Q^T [d][ldq], qoi_b = Q b + q0) so that Link.qoi comes straight from theta
+    int nq[tda::MAXL] = {0, 0, 0, 0}, ldq[tda::MAXL] = {0, 0, 0, 0};
+    R* qoi_Q[tda::MAXL] = {nullptr, nullptr, nullptr, nullptr};    // [nq][m]
+    R* qoi_q0[tda::MAXL] = {nullptr, nullptr, nullptr, nullptr};   // [nq]
+    R* qoi_W[tda::MAXL] = {nullptr, nullptr, nullptr, nullptr};    // linear: [d][ldq]
+    R* qoi_b[tda::MAXL] = {nullptr, nullptr, nullptr, nullptr};    // linear: [nq]
+    // compaction of the finest level's records to the accepted ones (tda_post.h), double-buffered
+    struct CompactSlot {
+        long long nrec = 0, n_rows = -1;
+        int fields = 0;
+        long long* offsets = nullptr;     // [C + 1]
+        long long* scratch = nullptr;
+        uint8_t* flags = nullptr;         // [nrec][Cs]
+        size_t flags_cap = 0;
+        void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // theta, prior, like, output, qoi rows
+        size_t cap[5] = {0, 0, 0, 0, 0};
+        long long* total_pinned = nullptr;
+        cudaEvent_t ready = nullptr, copied = nullptr;
+        bool pending = false, has_copies = false;
+    } cslot[2];
+    cudaStream_t copy_stream = nullptr;
 
     ~EngineT() override {
         cudaSetDevice(device);
         for (void* p : allocs) cudaFree(p);
+        for (auto& s : cslot) {
+            if (s.offsets) cudaFree(s.offsets);
+            if (s.scratch) cudaFree(s.scratch);
+            if (s.flags) cudaFree(s.flags);
+            for (void* b : s.buf) if (b) cudaFree(b);
+            if (s.total_pinned) cudaFreeHost(s.total_pinned);
+            if (s.ready) cudaEventDestroy(s.ready);
+            if (s.copied) cudaEventDestroy(s.copied);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         tc.destroy();
         tc16.destroy();
     }
@@ -282,6 +336,13 @@ struct EngineT : tda_engine {
             const int m = lc.m;
             v.model_kind = lc.model_kind; v.m = m; v.n_grid = lc.n_grid; v.lik_kind = lc.lik_kind;
             v.store = lc.store; v.hist_cap = lc.hist_capacity;
+            if (lc.n_qoi < 0 || lc.n_qoi > 64) return fail(-1, "n_qoi out of range (0..64)");
+            nq[l] = lc.n_qoi;
+            if (nq[l]) {
+                ldq[l] = round_up(nq[l], 4);
+                DALLOC(qoi_Q[l], (size_t)nq[l] * m); DALLOC(qoi_q0[l], nq[l]);
+                if (lc.model_kind == TDA_MODEL_LINEAR) { DALLOC(qoi_W[l], (size_t)d * ldq[l]); DALLOC(qoi_b[l], nq[l]); }
+            }
             v.lik_var = (R)lc.lik_var; v.sc0 = (R)lc.model_scalars[0]; v.sc1 = (R)lc.model_scalars[1];
             v.stride = (int)lc.model_scalars[0];
             v.need_F = (lc.lik_kind >= TDA_LIK_DENSE) || (lc.model_kind != TDA_MODEL_LINEAR) || c.aem ||
@@ -469,6 +530,32 @@ struct EngineT : tda_engine {
             if ((r = need((size_t)m * m))) return r;
             return put_matrix(P.lv[level].cov, host, m, m, m);
         }
+        case TDA_UP_QOI_W: {
+            if (level < 0 || level >= L || !nq[level]) return fail(-1, "upload: level has no quantity of interest");
+            const tda::LevelP<R>& v = P.lv[level];
+            if ((r = need((size_t)nq[level] * v.m))) return r;
+            if ((r = put_matrix(qoi_Q[level], host, nq[level], v.m, v.m))) return r;
+            if (qoi_W[level]) {            // compose with the linear operator: W[k][j] = sum_n G^T[k][n] Q[j][n]
+                std::vector<R> A((size_t)d * v.ldA);
+                CUDA_TRY(cudaMemcpy(A.data(), v.A, A.size() * sizeof(R), cudaMemcpyDeviceToHost));
+                std::vector<R> W((size_t)d * ldq[level], (R)0);
+                for (int k = 0; k < d; k++)
+                    for (int j = 0; j < nq[level]; j++) {
+                        double a = 0;
+                        for (int n = 0; n < v.m; n++) a += (double)A[(size_t)k * v.ldA + n] * host[(size_t)j * v.m + n];
+                        W[(size_t)k * ldq[level] + j] = (R)a;
+                    }
+                if ((r = put(qoi_W[level], W))) return r;
+                return compose_qoi_offset(level);
+            }
+            return 0;
+        }
+        case TDA_UP_QOI_B: {
+            if (level < 0 || level >= L || !nq[level]) return fail(-1, "upload: level has no quantity of interest");
+            if ((r = need((size_t)nq[level]))) return r;
+            if ((r = put_matrix(qoi_q0[level], host, 1, nq[level], nq[level]))) return r;
+            return qoi_W[level] ? compose_qoi_offset(level) : 0;
+        }
         case TDA_UP_INIT_THETA: {
             if ((r = need((size_t)P.C * d))) return r;
             // one H2D copy of the caller's [C][d] float64 array (asynchronous when it is pinned),
@@ -514,6 +601,51 @@ struct EngineT : tda_engine {
         default:
             return fail(-1, "upload: unknown item");
         }
+    }
+
+    // linear models: qoi_b = Q b + q0 from the device copies of Q, b and q0
+    int compose_qoi_offset(int l) {
+        const tda::LevelP<R>& v = P.lv[l];
+        std::vector<R> Q((size_t)nq[l] * v.m), b(v.m), q0(nq[l]), o(nq[l]);
+        CUDA_TRY(cudaMemcpy(Q.data(), qoi_Q[l], Q.size() * sizeof(R), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(b.data(), v.b, b.size() * sizeof(R), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(q0.data(), qoi_q0[l], q0.size() * sizeof(R), cudaMemcpyDeviceToHost));
+        for (int j = 0; j < nq[l]; j++) {
+            double a = q0[j];
+            for (int n = 0; n < v.m; n++) a += (double)Q[(size_t)j * v.m + n] * b[n];
+            o[j] = (R)a;
+        }
+        return put(qoi_b[l], o);
+    }
+
+    // Link.qoi of records [rec0, rec0 + nrec) of a level into out [nrec][nq][Cs]
+    int qoi_fill(int l, long long rec0, long long nrec, R* out, cudaStream_t st) {
+        const tda::LevelP<R>& v = P.lv[l];
+        if (!nq[l]) return fail(-1, "qoi: the level's model has no quantity of interest");
+        if (qoi_W[l]) {
+            if (!v.h_theta) return fail(-1, "qoi: needs the stored parameters of the level");
+            if (P.d > 64) return fail(-1, "history fill: d > 64");
+            const long long per = Cs / 256;
+            for (long long r0 = 0; r0 < nrec;) {
+                const long long n = nrec - r0 < (1 << 20) ? nrec - r0 : (1 << 20);
+                hist_fill_kernel<R, 64><<<(unsigned)(n * per), 256, 0, st>>>(v.h_theta + (size_t)(rec0 + r0) * P.d * Cs, qoi_W[l], ldq[l], nq[l],
+                                                                          qoi_b[l], (const R*)nullptr, out + (size_t)r0 * nq[l] * Cs, P.d, Cs, 0, (R)0);
+                g_launches++;
+                r0 += n;
+            }
+        } else {
+            if (!v.h_F) return fail(-1, "qoi: needs the stored model outputs of the level (store_model_output=True)");
+            const long long per = Cs / 256;
+            for (long long r0 = 0; r0 < nrec;) {
+                const long long n = nrec - r0 < (1 << 20) ? nrec - r0 : (1 << 20);
+                qoi_from_F_kernel<R><<<(unsigned)(n * per), 256, 0, st>>>(v.h_F + (size_t)(rec0 + r0) * v.m * Cs, qoi_Q[l], qoi_q0[l],
+                                                                       out + (size_t)r0 * nq[l] * Cs, v.m, nq[l], Cs);
+                g_launches++;
+                r0 += n;
+            }
+        }
+        CUDA_TRY(cudaGetLastError());
+        return 0;
     }
 
     // ---- launches ----------------------------------------------------------------------------
@@ -588,6 +720,8 @@ struct EngineT : tda_engine {
         if (tda::is_dream(P.prop_kind)) dream_slots = cfg.dream_M0;
         for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = 0; P.lvl_steps[l] = 0; lazy_lo[l] = lazy_hi[l] = 0; }
         state_F_stale = false;
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaMemsetAsync(P.error_flag, 0, sizeof(int), st));
         int r = launch(tda::MODE_INIT, 0, st);
         if (r) return r;
         P.rec[P.L - 1] = 1;
@@ -613,10 +747,34 @@ struct EngineT : tda_engine {
         return (resolved_kernel() == 3 || z_round_user) ? 1 : 0;
     }
 
-    int run(long long iterations, cudaStream_t st) override {
+    int run(long long iterations, cudaStream_t st, bool record = true) override {
         if (!initialised) return fail(-1, "run: call tda_engine_init first");
         if (iterations <= 0) return 0;
         const int L = P.L;
+        if (record) {
+            // a level that stores history must be able to hold every record of this run (the kernels
+            // drop records past the capacity)
+            long long st_l = iterations;
+            for (int l = L - 1; l >= 0; l--) {
+                if (l < L - 1) st_l *= P.J[l];
+                if (!burning && cfg.level[l].store && P.rec[l] + st_l > P.lv[l].hist_cap)
+                    return fail(-1, "run: level " + std::to_string(l) + " would write records " + std::to_string(P.rec[l]) + ".." +
+                                        std::to_string(P.rec[l] + st_l - 1) + " but its history holds " + std::to_string(P.lv[l].hist_cap) +
+                                        " (hist_capacity): fetch and tda_history_reset, or use tda_engine_burn for unrecorded iterations");
+            }
+        } else {
+            // burn-in: the same transitions with every store flag off for the launch(es)
+            int saved[tda::MAXL];
+            for (int l = 0; l < L; l++) { saved[l] = P.lv[l].store; P.lv[l].store = 0; }
+            long long rec_saved[tda::MAXL], lo_s[tda::MAXL], hi_s[tda::MAXL];
+            for (int l = 0; l < tda::MAXL; l++) { rec_saved[l] = P.rec[l]; lo_s[l] = lazy_lo[l]; hi_s[l] = lazy_hi[l]; }
+            burning = true;
+            const int r = run(iterations, st, true);
+            burning = false;
+            for (int l = 0; l < L; l++) P.lv[l].store = saved[l];
+            for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = rec_saved[l]; lazy_lo[l] = lo_s[l]; lazy_hi[l] = hi_s[l]; }
+            return r;
+        }
         if (P.prop_kind == TDA_PROP_AM && !P.am_device_refactor) {
             long long to_boundary = P.period - (P.t_base % P.period);
             if (iterations > to_boundary)
@@ -653,7 +811,7 @@ struct EngineT : tda_engine {
             // the fp16-split kernel counts its coarse steps per launch in 32 bits
             for (long long done = 0; done < iterations;) {
                 const long long n = iterations - done < (1 << 20) ? iterations - done : (1 << 20);
-                r = run(n, st);
+                r = run(n, st, true);
                 if (r) return r;
                 done += n;
             }
@@ -677,7 +835,7 @@ struct EngineT : tda_engine {
             // shared archive: lock-step visibility (every chain sees all rows through the
             // previous step) needs a grid-wide boundary per step -> one launch per step
             for (long long i = 0; i < iterations; i++) {
-                r = run(1, st);
+                r = run(1, st, true);
                 if (r) return r;
             }
             return 0;
@@ -694,10 +852,11 @@ struct EngineT : tda_engine {
         for (int l = 1; l < L; l++) w += steps[l];
         P.wcount += (L == 1) ? steps[0] : w;
         if (which == 3) {
-            for (int l = 0; l < L; l++) {
-                if (lazy_lo[l] == lazy_hi[l]) lazy_lo[l] = P.rec[l];
-                lazy_hi[l] = P.rec[l] + steps[l];
-            }
+            if (!burning)
+                for (int l = 0; l < L; l++) {
+                    if (lazy_lo[l] == lazy_hi[l]) lazy_lo[l] = P.rec[l];
+                    lazy_hi[l] = P.rec[l] + steps[l];
+                }
             state_F_stale = true;
         }
         for (int l = 0; l < L; l++) { P.rec[l] += steps[l]; if (l >= 1) P.lvl_steps[l] += steps[l]; }
@@ -784,6 +943,26 @@ struct EngineT : tda_engine {
             int r = fill_lazy_history(st);
             if (r) return r;
         }
+        if (field == TDA_F_QOI) {
+            // rebuilt into a scratch buffer, copied out, released: all in stream order
+            const size_t n = (size_t)nrec * nq[level];
+            const size_t need = n * (size_t)P.C * sizeof(R);
+            if (bytes) *bytes = need;
+            if (!nq[level]) return fail(-1, "fetch: the level's model has no quantity of interest");
+            if (dst_bytes < need) return fail(-1, "fetch: destination too small");
+            if (n == 0) return 0;
+            if (!qoi_W[level]) { int r0 = fill_lazy_history(st); if (r0) return r0; }
+            R* tmp = nullptr;
+            CUDA_TRY(cudaMallocAsync((void**)&tmp, n * Cs * sizeof(R), st));
+            int r = qoi_fill(level, rec0, nrec, tmp, st);
+            if (!r) {
+                cudaError_t ce = cudaMemcpy2DAsync(dst, (size_t)P.C * sizeof(R), tmp, (size_t)Cs * sizeof(R), (size_t)P.C * sizeof(R), n,
+                                                   cudaMemcpyDeviceToHost, st);
+                if (ce != cudaSuccess) r = fail(-2, std::string("fetch qoi: ") + cudaGetErrorString(ce));
+            }
+            cudaFreeAsync(tmp, st);
+            return r;
+        }
         const void* src = nullptr;
         size_t rows = 0, esz = sizeof(R);
         switch (field) {
@@ -804,6 +983,127 @@ struct EngineT : tda_engine {
         else
             CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)P.C * esz, src, (size_t)Cs * esz, (size_t)P.C * esz, rows,
                                        cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+
+    // ---- compacted history (tda_post.h) ------------------------------------------------------------
+    template <typename T>
+    int grow(T** ptr, size_t* cap, size_t need_bytes) {
+        if (*cap >= need_bytes && *ptr) return 0;
+        if (*ptr) cudaFree(*ptr);
+        *ptr = nullptr; *cap = 0;
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, need_bytes ? need_bytes : 1);
+        if (e != cudaSuccess) return fail(-3, std::string("cudaMalloc ") + std::to_string(need_bytes) + " bytes (compacted history): " + cudaGetErrorString(e));
+        *ptr = reinterpret_cast<T*>(q); *cap = need_bytes;
+        return 0;
+    }
+
+    int compact_begin(int level, long long rec0, long long nrec, int first_is_full, int fields, int slot, cudaStream_t st) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (slot < 0 || slot > 1) return fail(-1, "compact: slot must be 0 or 1");
+        if (level != P.L - 1) return fail(-1, "compact: only the finest level's records repeat on rejection");
+        const tda::LevelP<R>& v = P.lv[level];
+        if (!v.h_acc) return fail(-1, "compact: the level does not store accept flags");
+        if (rec0 < 0 || nrec < 1 || rec0 + nrec > P.rec[level] || rec0 + nrec > v.hist_cap) return fail(-1, "compact: record range has not been written");
+        if ((fields & TDA_STORE_THETA) && !v.h_theta) return fail(-1, "compact: parameters were not stored");
+        if ((fields & TDA_STORE_STATS) && !(v.h_prior && v.h_like)) return fail(-1, "compact: log-densities were not stored");
+        if ((fields & TDA_STORE_OUTPUT) && !v.h_F) return fail(-1, "compact: model outputs were not stored");
+        if ((fields & TDA_STORE_QOI) && !nq[level]) return fail(-1, "compact: the level's model has no quantity of interest");
+        CompactSlot& s = cslot[slot];
+        if (!copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        if (!s.ready) { CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)); }
+        if (!s.total_pinned) CUDA_TRY(cudaHostAlloc((void**)&s.total_pinned, sizeof(long long), cudaHostAllocPortable));
+        if (!s.offsets) {
+            size_t c0 = 0, c1 = 0;
+            int r0 = grow(&s.offsets, &c0, ((size_t)P.C + 1) * sizeof(long long));
+            if (!r0) r0 = grow(&s.scratch, &c1, ((size_t)(P.C + 255) / 256 + 2) * sizeof(long long));
+            if (r0) return r0;
+        }
+        // copies of the slot's previous contents must have left the device buffers
+        if (s.has_copies) CUDA_TRY(cudaStreamWaitEvent(st, s.copied, 0));
+        if (fields & (TDA_STORE_OUTPUT | TDA_STORE_STATS | TDA_STORE_QOI)) { int r0 = fill_lazy_history(st); if (r0) return r0; }
+        const size_t rows_max = (size_t)nrec * P.C;
+        int r = grow(&s.flags, &s.flags_cap, (size_t)nrec * Cs);
+        const int widths[5] = {P.d, 1, 1, v.m, nq[level]};
+        const bool want[5] = {(fields & TDA_STORE_THETA) != 0, (fields & TDA_STORE_STATS) != 0, (fields & TDA_STORE_STATS) != 0,
+                              (fields & TDA_STORE_OUTPUT) != 0, (fields & TDA_STORE_QOI) != 0};
+        for (int f = 0; f < 5 && !r; f++)
+            if (want[f]) r = grow(&s.buf[f], &s.cap[f], rows_max * widths[f] * sizeof(R));
+        if (r) return r;
+        const uint8_t* acc = v.h_acc + (size_t)rec0 * Cs;
+        namespace tp = tda::post;
+        r = tp::compact_offsets(acc, nrec, P.C, Cs, first_is_full, s.offsets, s.scratch, st);
+        if (!r) r = tp::compact_flags(acc, nrec, P.C, Cs, first_is_full, s.flags, st);
+        g_launches += 4;
+        CUDA_TRY(cudaMemcpyAsync(s.total_pinned, s.offsets + P.C, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        const void* srcs[5] = {v.h_theta ? v.h_theta + (size_t)rec0 * P.d * Cs : nullptr, v.h_prior ? v.h_prior + (size_t)rec0 * Cs : nullptr,
+                               v.h_like ? v.h_like + (size_t)rec0 * Cs : nullptr, v.h_F ? v.h_F + (size_t)rec0 * v.m * Cs : nullptr, nullptr};
+        R* qtmp = nullptr;
+        if (want[4] && !r) {
+            CUDA_TRY(cudaMallocAsync((void**)&qtmp, (size_t)nrec * nq[level] * Cs * sizeof(R), st));
+            r = qoi_fill(level, rec0, nrec, qtmp, st);
+            srcs[4] = qtmp;
+        }
+        for (int f = 0; f < 5 && !r; f++)
+            if (want[f]) {
+                r = tp::compact_gather(srcs[f], (int)sizeof(R), widths[f], acc, nrec, P.C, Cs, first_is_full, s.offsets, s.buf[f], st);
+                g_launches++;
+            }
+        if (qtmp) cudaFreeAsync(qtmp, st);
+        if (r) return fail(r, tp::last_error());
+        CUDA_TRY(cudaEventRecord(s.ready, st));
+        s.nrec = nrec; s.fields = fields; s.n_rows = -1; s.pending = true; s.has_copies = false;
+        return 0;
+    }
+
+    int compact_rows(int slot, long long* n_rows) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (slot < 0 || slot > 1 || !cslot[slot].pending) return fail(-1, "compact: no compaction was begun on this slot");
+        CompactSlot& s = cslot[slot];
+        if (s.n_rows < 0) {
+            CUDA_TRY(cudaEventSynchronize(s.ready));
+            s.n_rows = *s.total_pinned;
+        }
+        *n_rows = s.n_rows;
+        return 0;
+    }
+
+    int compact_fetch(int slot, int field, void* dst, size_t dst_bytes, size_t* bytes) override {
+        long long n = 0;
+        int r = compact_rows(slot, &n);
+        if (r) return r;
+        CompactSlot& s = cslot[slot];
+        const tda::LevelP<R>& v = P.lv[P.L - 1];
+        const void* src = nullptr;
+        size_t need = 0;
+        bool strided = false;
+        switch (field) {
+        case TDA_F_ACCEPT: src = s.flags; need = (size_t)s.nrec * P.C; strided = (P.C != Cs); break;
+        case TDA_CF_OFFSETS: src = s.offsets; need = ((size_t)P.C + 1) * sizeof(long long); break;
+        case TDA_F_THETA: src = (s.fields & TDA_STORE_THETA) ? s.buf[0] : nullptr; need = (size_t)n * P.d * sizeof(R); break;
+        case TDA_F_PRIOR: src = (s.fields & TDA_STORE_STATS) ? s.buf[1] : nullptr; need = (size_t)n * sizeof(R); break;
+        case TDA_F_LIKE: src = (s.fields & TDA_STORE_STATS) ? s.buf[2] : nullptr; need = (size_t)n * sizeof(R); break;
+        case TDA_F_OUTPUT: src = (s.fields & TDA_STORE_OUTPUT) ? s.buf[3] : nullptr; need = (size_t)n * v.m * sizeof(R); break;
+        case TDA_F_QOI: src = (s.fields & TDA_STORE_QOI) ? s.buf[4] : nullptr; need = (size_t)n * nq[P.L - 1] * sizeof(R); break;
+        default: return fail(-1, "compact fetch: unknown field");
+        }
+        if (!src) return fail(-1, "compact fetch: field was not compacted on this slot");
+        if (bytes) *bytes = need;
+        if (dst_bytes < need) return fail(-1, "compact fetch: destination too small");
+        CUDA_TRY(cudaStreamWaitEvent(copy_stream, s.ready, 0));
+        if (need) {
+            if (strided) CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)P.C, src, (size_t)Cs, (size_t)P.C, (size_t)s.nrec, cudaMemcpyDeviceToHost, copy_stream));
+            else CUDA_TRY(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, copy_stream));
+        }
+        CUDA_TRY(cudaEventRecord(s.copied, copy_stream));
+        s.has_copies = true;
+        return 0;
+    }
+
+    int compact_sync() override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (copy_stream) CUDA_TRY(cudaStreamSynchronize(copy_stream));
         return 0;
     }
 
@@ -857,6 +1157,13 @@ struct EngineT : tda_engine {
         case TDA_G_NRECORDS: {
             if (bytes < (size_t)P.L * sizeof(long long)) return fail(-1, "get: destination too small");
             for (int l = 0; l < P.L; l++) reinterpret_cast<long long*>(dst)[l] = P.rec[l];
+            return 0;
+        }
+        case TDA_G_ERROR_FLAGS: {
+            if (bytes < sizeof(long long)) return fail(-1, "get: destination too small");
+            int f = 0;
+            CUDA_TRY(cudaMemcpy(&f, P.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+            reinterpret_cast<long long*>(dst)[0] = f;
             return 0;
         }
         case TDA_G_KERNEL: {
@@ -1032,6 +1339,32 @@ int tda_upload(tda_engine* e, int what, int level, const double* host, size_t co
 }
 int tda_engine_init(tda_engine* e, void* s) { return e ? e->init((cudaStream_t)s) : fail(-1, "null engine"); }
 int tda_engine_run(tda_engine* e, int64_t it, void* s) { return e ? e->run(it, (cudaStream_t)s) : fail(-1, "null engine"); }
+int tda_engine_burn(tda_engine* e, int64_t it, void* s) { return e ? e->run(it, (cudaStream_t)s, false) : fail(-1, "null engine"); }
+int tda_compact_begin(tda_engine* e, int level, int64_t rec0, int64_t nrec, int first_is_full, int fields, int slot, void* s) {
+    return e ? e->compact_begin(level, rec0, nrec, first_is_full, fields, slot, (cudaStream_t)s) : fail(-1, "null engine");
+}
+int tda_compact_rows(tda_engine* e, int slot, int64_t* n_rows) {
+    if (!e || !n_rows) return fail(-1, "null argument");
+    long long n = 0;
+    int r = e->compact_rows(slot, &n);
+    *n_rows = n;
+    return r;
+}
+int tda_compact_fetch(tda_engine* e, int slot, int field, void* dst, size_t dst_bytes, size_t* bytes) {
+    if (!e || !dst) return fail(-1, "null argument");
+    return e->compact_fetch(slot, field, dst, dst_bytes, bytes);
+}
+int tda_compact_sync(tda_engine* e) { return e ? e->compact_sync() : fail(-1, "null engine"); }
+int tda_host_alloc(size_t bytes, void** ptr) {
+    if (!ptr) return fail(-1, "null argument");
+    *ptr = nullptr;
+    CUDA_TRY(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return 0;
+}
+int tda_host_free(void* ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return 0;
+}
 int tda_engine_sync(tda_engine* e, void* s) {
     if (!e) return fail(-1, "null engine");
     CUDA_TRY(cudaSetDevice(e->device));

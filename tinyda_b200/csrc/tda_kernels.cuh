@@ -493,6 +493,9 @@ struct Tile {
                 if (on) {
                     R djj = Wm[(j * m + j) * G + cg];
                     for (int k = 0; k < j; k++) { R t = Wm[(j * m + k) * G + cg]; djj -= t * t; }
+                    // a non-positive pivot (near-singular bias covariance in this dtype) is clamped and
+                    // flagged; the reference's np.linalg.inv does not fail there (distributions.py:402)
+                    if (!(djj > (R)0)) { djj = (R)1e-30; if (wk == 0) *p.error_flag = 1; }
                     djj = tsqrt(djj);
                     const R inv = (R)1 / djj;
                     if (wk == 0) dg[j * G + cg] = djj;
@@ -1155,6 +1158,7 @@ struct Tile {
                     for (int j = 0; j < d; j++) {
                         R djj = p.am_sigma[gi(j * d + j, c)];
                         for (int k = 0; k < j; k++) { R t2 = T[gi(k * d + j, c)]; djj -= t2 * t2; }
+                        if (!(djj > (R)0)) { djj = (R)1e-30; *p.error_flag = 1; }     // the reference factors by SVD
                         djj = tsqrt(djj);
                         T[gi(j * d + j, c)] = djj;
                         for (int i = j + 1; i < d; i++) {

@@ -1,0 +1,148 @@
+// Device-side post-processing of the Link history: compaction to accepted records (see tda_post.h).
+// HBM-bound byte shuffling: coalesced accept-byte reads (lane = chain), one warp per chain for the
+// row gather (strided sector reads of the chain-fastest history, coalesced row-major writes).
+#include <string>
+
+#include "tda_post.h"
+
+namespace tda {
+namespace post {
+
+namespace {
+thread_local std::string g_perr;
+int pfail(const char* what, cudaError_t e) {
+    g_perr = std::string(what) + ": " + cudaGetErrorString(e);
+    return -2;
+}
+
+constexpr int CB = 256;   // chains per block of the counting pass
+
+// pass 1: accepted records per chain, block-level exclusive scan, block totals
+__global__ void __launch_bounds__(CB) count_kernel(const uint8_t* __restrict__ acc, long long nrec, int C, int Cs, int force_first,
+                                                   long long* __restrict__ offsets, long long* __restrict__ block_tot) {
+    __shared__ long long s_w[CB / 32];
+    const int c = blockIdx.x * CB + threadIdx.x;
+    long long n = 0;
+    if (c < C) {
+        const uint8_t* a = acc + c;
+        for (long long r = 0; r < nrec; r++) n += (a[(size_t)r * Cs] != 0 || (force_first && r == 0)) ? 1 : 0;
+    }
+    // inclusive warp scan, then across the 8 warps
+    long long v = n;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) s_w[w] = v;
+    __syncthreads();
+    long long base = 0;
+    for (int i = 0; i < w; i++) base += s_w[i];
+    if (c < C) offsets[c] = base + v - n;            // exclusive within the block
+    if (threadIdx.x == CB - 1) block_tot[blockIdx.x] = base + v;
+}
+
+// pass 2: one block turns the block totals into exclusive block offsets (in place), total at [nblocks]
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(long long* __restrict__ block_tot, int nblocks) {
+    __shared__ long long s_w[32];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+        const int i = b0 + threadIdx.x;
+        const long long n = i < nblocks ? block_tot[i] : 0;
+        long long v = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) s_w[w] = v;
+        __syncthreads();
+        long long base = s_carry;
+        for (int k = 0; k < w; k++) base += s_w[k];
+        if (i < nblocks) block_tot[i] = base + v - n;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = base + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_tot[nblocks] = s_carry;
+}
+
+// pass 3: add the block offsets; offsets[C] = total
+__global__ void __launch_bounds__(CB) add_blocks_kernel(long long* __restrict__ offsets, const long long* __restrict__ block_off, int C, int nblocks) {
+    const int c = blockIdx.x * CB + threadIdx.x;
+    if (c < C) offsets[c] += block_off[blockIdx.x];
+    if (c == 0) offsets[C] = block_off[nblocks];
+}
+
+// one warp per chain: the accept bytes of 32 records at a time -> ballot -> rows
+template <typename R>
+__global__ void __launch_bounds__(256) gather_kernel(const R* __restrict__ src, int W, const uint8_t* __restrict__ acc, long long nrec, int C,
+                                                     int Cs, int force_first, const long long* __restrict__ offsets, R* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= C) return;
+    long long row = offsets[c];
+    for (long long r0 = 0; r0 < nrec; r0 += 32) {
+        const long long r = r0 + lane;
+        const bool a = r < nrec && (acc[(size_t)r * Cs + c] != 0 || (force_first && r == 0));
+        unsigned m = __ballot_sync(0xffffffffu, a);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const R* s = src + (size_t)(r0 + b) * W * Cs + c;
+            R* o = dst + (size_t)row * W;
+            for (int k = lane; k < W; k += 32) o[k] = s[(size_t)k * Cs];
+            row++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) flags_kernel(const uint8_t* __restrict__ acc, long long nrec, int C, int Cs, int force_first,
+                                                    uint8_t* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t total = (size_t)nrec * Cs;
+    if (i < total) {
+        const size_t r = i / Cs;
+        dst[i] = (acc[i] != 0 || (force_first && r == 0)) ? 1 : 0;
+    }
+}
+
+}  // namespace
+
+const char* last_error() { return g_perr.c_str(); }
+
+int compact_offsets(const uint8_t* acc, long long nrec, int C, int Cs, int force_first, long long* offsets, long long* scratch,
+                    cudaStream_t st) {
+    const int nblocks = (C + CB - 1) / CB;
+    count_kernel<<<nblocks, CB, 0, st>>>(acc, nrec, C, Cs, force_first, offsets, scratch);
+    scan_blocks_kernel<<<1, 1024, 0, st>>>(scratch, nblocks);
+    add_blocks_kernel<<<nblocks, CB, 0, st>>>(offsets, scratch, C, nblocks);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : pfail("compact_offsets", e);
+}
+
+int compact_gather(const void* src, int esz, int W, const uint8_t* acc, long long nrec, int C, int Cs, int force_first,
+                   const long long* offsets, void* dst, cudaStream_t st) {
+    const unsigned grid = (unsigned)((C + 7) / 8);
+    if (esz == 4)
+        gather_kernel<float><<<grid, 256, 0, st>>>((const float*)src, W, acc, nrec, C, Cs, force_first, offsets, (float*)dst);
+    else
+        gather_kernel<double><<<grid, 256, 0, st>>>((const double*)src, W, acc, nrec, C, Cs, force_first, offsets, (double*)dst);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : pfail("compact_gather", e);
+}
+
+int compact_flags(const uint8_t* acc, long long nrec, int C, int Cs, int force_first, uint8_t* dst, cudaStream_t st) {
+    const size_t total = (size_t)nrec * Cs;
+    if (!total) return 0;
+    flags_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(acc, nrec, C, Cs, force_first, dst);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : pfail("compact_flags", e);
+}
+
+}  // namespace post
+}  // namespace tda

@@ -1,0 +1,35 @@
+// Device-side post-processing of the Link history (separate translation unit, see Makefile):
+//   * compaction of the finest level's records to the ACCEPTED ones -- a rejected step re-appends the
+//     same Link object in the reference (chain.py:116, :434; proposal.py:1601), so only the accept
+//     byte of every record and the fields of the accepted records have to cross PCIe;
+//   * Link.qoi / Link.model_output of linear models rebuilt from stored parameters (tda_engine.cu);
+//   * rank-normalised split R-hat / bulk ESS of the finest level's parameter history
+//     (what ArviZ computes on the reference's to_inference_data output, diagnostics.py:6-69).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace tda {
+namespace post {
+
+// ---- compaction ---------------------------------------------------------------------------------
+// acc: [nrec][Cs] accept bytes of the records to compact.  force_first: record 0 is a full row whatever
+// its flag says (the initial Link).  Writes counts[c] (accepted records of chain c) and, after the scan,
+// offsets[C + 1] (chain-major exclusive prefix: the rows of chain c are offsets[c] .. offsets[c+1]).
+// `scratch` holds (C + 255) / 256 + 1 int64 values.  total_out (device) receives offsets[C].
+int compact_offsets(const uint8_t* acc, long long nrec, int C, int Cs, int force_first, long long* offsets,
+                    long long* scratch, cudaStream_t st);
+
+// dst[offsets[c] + j][0..W) = src[r_j][0..W)[c] for the j-th accepted record r_j of chain c
+// (src: [nrec][W][Cs], chain fastest; dst row-major [n_rows][W]); esz = 4 (float) or 8 (double)
+int compact_gather(const void* src, int esz, int W, const uint8_t* acc, long long nrec, int C, int Cs, int force_first,
+                   const long long* offsets, void* dst, cudaStream_t st);
+
+// accept bytes with the forced first record made explicit: dst[r][c] (dense [nrec][Cs])
+int compact_flags(const uint8_t* acc, long long nrec, int C, int Cs, int force_first, uint8_t* dst, cudaStream_t st);
+
+const char* last_error();
+
+}  // namespace post
+}  // namespace tda

@@ -20,7 +20,8 @@ def _attr_array(seq, attribute):
         if attribute == "stats":
             return np.stack([seq.prior, seq.likelihood, seq.prior + seq.likelihood], axis=1)
         if attribute == "qoi":
-            return np.array([None] * len(seq))
+            # link.py:38-48: None unless the model returns (output, qoi), posterior.py:95-105
+            return np.array([None] * len(seq)) if seq.qoi is None else np.asarray(seq.qoi)
     if attribute == "stats":
         return np.array([[l.prior, l.likelihood, l.posterior] for l in seq])
     return np.array([getattr(l, attribute) for l in seq])
@@ -42,14 +43,45 @@ def get_samples(chain, attribute="parameters", level="fine", burnin=0):
         key = "chain_l" + str(level) + "_{}"
     else:
         raise ValueError("unknown sampler %r" % chain["sampler"])
-    for i in range(chain["n_chains"]):
-        x = _attr_array(chain[key.format(i)][burnin:], attribute)
+    # under torch.distributed every rank holds its own shard of the chains (sample() records the range)
+    lo, hi = chain.get("local_chains", (0, chain["n_chains"]))
+    fast = _dense_from_history(chain, key, attribute, burnin)
+    for i in range(lo, hi):
+        if fast is not None:
+            x = fast[i - lo]
+        else:
+            x = _attr_array(chain[key.format(i)][burnin:], attribute)
         if x.ndim == 1:
             x = x[..., np.newaxis]
         samples["chain_{}".format(i)] = x
-    samples["iterations"] = samples["chain_0"].shape[0]
-    samples["dimension"] = samples["chain_0"].shape[1]
+    samples["iterations"] = samples["chain_{}".format(lo)].shape[0]
+    samples["dimension"] = samples["chain_{}".format(lo)].shape[1]
+    if (lo, hi) != (0, chain["n_chains"]):
+        samples["local_chains"] = (lo, hi)
     return samples
+
+
+def _dense_from_history(chain, key, attribute, burnin):
+    """All chains of the finest level at once from the compacted history sample() attaches to its result
+    (no per-chain Python objects); None when the request is for another level or a plain dict."""
+    hist = getattr(chain, "history", None)
+    if hist is None:
+        return None
+    fine_key = {"MH": "chain_{}", "DA": "chain_fine_{}"}.get(chain["sampler"], "chain_l%d_{}" % (chain.get("levels", 1) - 1))
+    if key != fine_key:
+        return None
+    if attribute == "parameters":
+        return hist.dense("theta", burnin)
+    if attribute == "model_output":
+        if hist.chunks and hist.chunks[0].output is None:
+            raise ValueError("model outputs were not stored (store_model_output=False)")
+        return hist.dense("output", burnin)
+    if attribute == "stats":
+        pr, lk = hist.dense("prior", burnin), hist.dense("like", burnin)
+        return np.stack([pr, lk, pr + lk], axis=2)
+    if attribute == "qoi" and hist.chunks and hist.chunks[0].qoi is not None:
+        return hist.dense("qoi", burnin)
+    return None
 
 
 def to_xarray(samples, keys):
@@ -57,11 +89,13 @@ def to_xarray(samples, keys):
     import xarray as xr
     data_vars = {}
     for i in range(samples["dimension"]):
-        x = np.array([samples["chain_{}".format(j)][:, i] for j in range(samples["n_chains"])])
+        lo, hi = samples.get("local_chains", (0, samples["n_chains"]))
+        x = np.array([samples["chain_{}".format(j)][:, i] for j in range(lo, hi)])
         data_vars[keys[i]] = (["chain", "draw"], x)
+    lo, hi = samples.get("local_chains", (0, samples["n_chains"]))
     return xr.Dataset(
         data_vars=data_vars,
-        coords=dict(chain=("chain", list(range(samples["n_chains"]))),
+        coords=dict(chain=("chain", list(range(lo, hi))),
                     draw=("draw", list(range(samples["iterations"])))),
     )
 

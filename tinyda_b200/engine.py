@@ -5,6 +5,8 @@ constant uploads of the C ABI, and exposes run / fetch.  All arithmetic happens 
 library behind ``_lib``; importing this module fails loudly if that library is missing.
 """
 import ctypes as C
+import warnings
+import weakref
 
 import numpy as np
 
@@ -23,6 +25,66 @@ def _dptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+# Page-locking is slow (of the order of 0.1-0.3 ms per MiB), so released pinned blocks are kept in a
+# small pool keyed by size class and handed out again (a long-lived process that calls sample()
+# repeatedly pays for its result buffers once).
+_PIN_POOL = {}
+_PIN_POOL_STATE = {"bytes": 0, "max_bytes": 16 << 30}
+
+
+def _pin_class(nbytes):
+    nbytes = max(int(nbytes), 1 << 16)
+    step = max(1 << 16, 1 << (nbytes.bit_length() - 3))       # <= 25 % slack
+    return (nbytes + step - 1) // step * step
+
+
+def _pin_release(ptr, cls):
+    if _PIN_POOL_STATE["bytes"] + cls <= _PIN_POOL_STATE["max_bytes"]:
+        _PIN_POOL.setdefault(cls, []).append(ptr)
+        _PIN_POOL_STATE["bytes"] += cls
+    else:
+        lib.tda_host_free(C.c_void_p(ptr))
+
+
+def pinned_pool_clear():
+    for cls, ptrs in _PIN_POOL.items():
+        for ptr in ptrs:
+            lib.tda_host_free(C.c_void_p(ptr))
+    _PIN_POOL.clear()
+    _PIN_POOL_STATE["bytes"] = 0
+
+
+def pinned_empty(shape, dtype):
+    """Page-locked host array (cudaHostAlloc through the C ABI): device->host copies into it are
+    asynchronous.  Returned to the pool when the array (and every view of it) is garbage collected."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    cls = _pin_class(count * dtype.itemsize)
+    free = _PIN_POOL.get(cls)
+    if free:
+        addr = free.pop()
+        _PIN_POOL_STATE["bytes"] -= cls
+    else:
+        ptr = C.c_void_p()
+        check(lib.tda_host_alloc(cls, C.byref(ptr)))
+        addr = ptr.value
+    buf = (C.c_ubyte * cls).from_address(addr)
+    weakref.finalize(buf, _pin_release, addr, cls)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+class CompactChunk:
+    """Host copy of one compacted block of finest-level records (tda_compact_*): the accept flag of
+    every record and the fields of the accepted records, chain-major (rows offsets[c]..offsets[c+1]
+    belong to chain c, in time order)."""
+
+    __slots__ = ("nrec", "accept", "offsets", "theta", "prior", "like", "output", "qoi")
+
+    def __init__(self, nrec):
+        self.nrec = nrec
+        self.accept = self.offsets = self.theta = self.prior = self.like = self.output = self.qoi = None
+
+
 def steps_per_iteration(spec):
     """Local steps each level takes per finest-level iteration."""
     Ln = spec["n_levels"]
@@ -35,7 +97,7 @@ def steps_per_iteration(spec):
 class Engine:
     def __init__(self, spec, n_chains, dtype="float64", rng="philox", seed=0, store=None,
                  capacity_iterations=0, streams=None, device=0, chain_offset=0, n_chains_global=None,
-                 archive0=None, am_device_refactor=True, stream=None):
+                 archive0=None, am_device_refactor=True, stream=None, archive_iterations=None):
         self.spec = spec
         self.C = int(n_chains)
         self.dtype = np.dtype(dtype)
@@ -89,7 +151,7 @@ class Engine:
             cfg.dream_b = float(prop["b"])
             cfg.dream_b_star = float(prop["b_star"])
             # one archive row per base-level step (proposal.py:794): steps[0] of them per finest iteration
-            cfg.dream_capacity = int(prop["M0"]) + int(capacity_iterations) * self.steps[0] + 1
+            cfg.dream_capacity = int(prop["M0"]) + int(capacity_iterations if archive_iterations is None else archive_iterations) * self.steps[0] + 1
         if rng == "injected":
             z, u = streams
             z = np.ascontiguousarray(z, dtype=np.float64)
@@ -108,6 +170,7 @@ class Engine:
             for i in range(4):
                 lc.model_scalars[i] = float(np.asarray(lv["model"]["scalars"])[i])
             lc.store = int(self.store[l])
+            lc.n_qoi = int(lv["model"].get("n_qoi", 0))
             cap = int(capacity_iterations) * self.steps[l] + (1 if l == Ln - 1 else 0)
             lc.hist_capacity = cap if lc.store else 0
             self.capacity.append(int(lc.hist_capacity))
@@ -136,6 +199,9 @@ class Engine:
                 self._up(L.TDA_UP_MODEL_A, l, lv["model"]["A"])
             if mk == MODEL_LINEAR:
                 self._up(L.TDA_UP_MODEL_B, l, lv["model"]["b"])
+            if int(lv["model"].get("n_qoi", 0)):
+                self._up(L.TDA_UP_QOI_W, l, lv["model"]["qoi_Q"])
+                self._up(L.TDA_UP_QOI_B, l, lv["model"]["qoi_q0"])
             lk = int(lv["lik"]["kind"])
             self._up(L.TDA_UP_LIK_DATA, l, lv["lik"]["data"])
             if lk == LIK_DIAG:
@@ -186,14 +252,74 @@ class Engine:
         check(lib.tda_engine_init(self._h, self._stream_ptr()))
         self.iterations_done = 0
 
-    def run(self, iterations, stream=None):
+    def run(self, iterations, stream=None, record=True):
         """Advances every chain by `iterations` finest-level iterations; asynchronous on the CUDA
-        stream (raw handle) given here or at construction."""
-        check(lib.tda_engine_run(self._h, int(iterations), self._stream_ptr(stream)))
+        stream (raw handle) given here or at construction.  record=False: burn-in, nothing is stored
+        and the history position does not move."""
+        fn = lib.tda_engine_run if record else lib.tda_engine_burn
+        check(fn(self._h, int(iterations), self._stream_ptr(stream)))
         self.iterations_done += int(iterations)
 
     def sync(self, stream=None):
         check(lib.tda_engine_sync(self._h, self._stream_ptr(stream)))
+        flags = self.error_flags()
+        if flags and flags != getattr(self, "_warned_flags", 0):
+            self._warned_flags = flags
+            warnings.warn("tinyda_b200: a non-positive Cholesky pivot of a per-chain covariance (error model / "
+                          "Adaptive Metropolis) was clamped on the device; the affected chains continue with a "
+                          "regularised factor", RuntimeWarning)
+
+    def error_flags(self):
+        out = np.zeros(1, dtype=np.int64)
+        check(lib.tda_get(self._h, L.TDA_G_ERROR_FLAGS, 0, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return int(out[0])
+
+    # ---- compacted history of the finest level -------------------------------------------------
+    def compact_begin(self, rec0, nrec, first_is_full, fields=("theta", "stats"), slot=0, stream=None):
+        """Enqueues the device-side compaction of finest-level records [rec0, rec0+nrec) to the accepted
+        ones (a rejected step repeats the previous Link, chain.py:116, :434)."""
+        bits = {"theta": L.TDA_STORE_THETA, "stats": L.TDA_STORE_STATS, "output": L.TDA_STORE_OUTPUT, "qoi": L.TDA_STORE_QOI}
+        mask = 0
+        for f in fields:
+            mask |= bits[f]
+        check(lib.tda_compact_begin(self._h, self.Ln - 1, int(rec0), int(nrec), int(bool(first_is_full)), mask, int(slot),
+                                    self._stream_ptr(stream)))
+        self._compact = getattr(self, "_compact", {})
+        self._compact[int(slot)] = (int(nrec), tuple(fields))
+
+    def compact_collect(self, slot=0, pinned=True):
+        """Waits for the row count of `slot`, enqueues the device->host copies on the engine's copy stream
+        and returns the CompactChunk they fill (valid after compact_sync())."""
+        nrec, fields = self._compact[int(slot)]
+        n = C.c_int64(0)
+        check(lib.tda_compact_rows(self._h, int(slot), C.byref(n)))
+        n = int(n.value)
+        alloc = pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dtype=dt))
+        ch = CompactChunk(nrec)
+        m = int(self.spec["levels"][self.Ln - 1]["model"]["m"])
+        nq = int(self.spec["levels"][self.Ln - 1]["model"].get("n_qoi", 0))
+
+        def get(field, shape, dt):
+            out = alloc(shape, dt)
+            nb = C.c_size_t(0)
+            check(lib.tda_compact_fetch(self._h, int(slot), field, out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(nb)))
+            return out
+
+        ch.accept = get(L.TDA_F_ACCEPT, (nrec, self.C), np.uint8)
+        ch.offsets = get(L.TDA_CF_OFFSETS, (self.C + 1,), np.int64)
+        if "theta" in fields:
+            ch.theta = get(L.TDA_F_THETA, (n, self.d), self.dtype)
+        if "stats" in fields:
+            ch.prior = get(L.TDA_F_PRIOR, (n,), self.dtype)
+            ch.like = get(L.TDA_F_LIKE, (n,), self.dtype)
+        if "output" in fields:
+            ch.output = get(L.TDA_F_OUTPUT, (n, m), self.dtype)
+        if "qoi" in fields:
+            ch.qoi = get(L.TDA_F_QOI, (n, nq), self.dtype)
+        return ch
+
+    def compact_sync(self):
+        check(lib.tda_compact_sync(self._h))
 
     def select_kernel(self, which):
         """"auto" | "generic" | "tc" (tcgen05, 3xTF32) | "tc16" (tcgen05, fp16 split + RNG warps) |
@@ -250,6 +376,7 @@ class Engine:
             "like": (L.TDA_F_LIKE, (nrec, self.C), self.dtype),
             "output": (L.TDA_F_OUTPUT, (nrec, m, self.C), self.dtype),
             "accept": (L.TDA_F_ACCEPT, (nrec, self.C), np.dtype(np.uint8)),
+            "qoi": (L.TDA_F_QOI, (nrec, int(self.spec["levels"][level]["model"].get("n_qoi", 0)), self.C), self.dtype),
         }[field]
         if out is None:
             out = np.empty(shape, dtype=dt)

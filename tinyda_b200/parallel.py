@@ -35,6 +35,19 @@ def local_device():
     return int(os.environ.get("LOCAL_RANK", "0")) if _dist() is not None else 0
 
 
+def broadcast_int(value, src=0):
+    """Rank `src`'s integer on every rank (identity without a process group)."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1:
+        return int(value)
+    import torch
+    t = torch.tensor([int(value)], dtype=torch.int64)
+    if d.get_backend() == "nccl":
+        t = t.cuda()
+    d.broadcast(t, src)
+    return int(t.cpu()[0])
+
+
 def shard_range(n_chains, rank, world):
     """Contiguous chain-id range [lo, hi) of `rank`; sizes differ by at most one."""
     base, rem = divmod(int(n_chains), int(world))

@@ -16,21 +16,40 @@ import scipy.stats as stats
 from .posterior import Posterior
 from .proposal import CrankNicolson, DREAMZ, DREAM, PROP_DREAM, PROP_DREAMZ, PROP_AM
 from .lowering import lower_problem
-from .link import LinkSequence
+from .link import LinkSequence, CompactHistory, SampleResult
 from . import parallel
 
 
-def _result_sequences(eng, level, n_chains_local, store_output):
-    theta = eng.fetch(level, "theta")            # [nrec, d, C]
-    prior = eng.fetch(level, "prior")            # [nrec, C]
-    like = eng.fetch(level, "like")
-    acc = eng.fetch(level, "accept").astype(bool)
-    out = eng.fetch(level, "output") if store_output else None
-    seqs = []
-    for c in range(n_chains_local):
-        seqs.append(LinkSequence(theta[:, :, c], prior[:, c], like[:, c],
-                                 None if out is None else out[:, :, c], acc[:, c]))
-    return seqs
+def _dense_family(parts):
+    """Coarser levels are fetched densely, block by block: parts = [(theta, prior, like, acc, out, qoi), ...]
+    in the device layout ([nrec, width, C] / [nrec, C]).  Returns the per-chain LinkSequence factory."""
+    cat = lambda xs: xs[0] if len(xs) == 1 else np.concatenate(xs, axis=0)
+    theta, prior, like, acc = (cat([p[k] for p in parts]) for k in range(4))
+    out = None if parts[0][4] is None else cat([p[4] for p in parts])
+    qoi = None if parts[0][5] is None else cat([p[5] for p in parts])
+    acc = acc.astype(bool)
+    return lambda c: LinkSequence(theta[:, :, c], prior[:, c], like[:, c], None if out is None else out[:, :, c], acc[:, c],
+                                  None if qoi is None else qoi[:, :, c])
+
+
+def _fresh_seed():
+    """seed=None: a fresh 63-bit seed from the legacy global generator -- un-seeded calls differ from one
+    another like the reference's do, and ``np.random.seed`` makes a run repeatable like it does there.
+    Under torch.distributed rank 0's draw is broadcast (one job, one seed)."""
+    seed = int(np.random.randint(0, np.iinfo(np.int64).max, dtype=np.int64))
+    return parallel.broadcast_int(seed)
+
+
+def _auto_chunk(iterations, n_local, spec, store, steps, itemsize, budget_bytes):
+    """Fine iterations per block so that the dense device history of a block stays within the budget."""
+    per_iter = 0
+    for l, lv in enumerate(spec["levels"]):
+        if not store[l]:
+            continue
+        w = spec["d"] + 2 + (int(lv["model"]["m"]) if store[l] & 4 else 0)
+        per_iter += steps[l] * (w * itemsize + 1)
+    pad = (n_local + 255) // 256 * 256
+    return int(max(1, min(iterations, budget_bytes // max(1, per_iter * pad))))
 
 
 def sample(
@@ -55,6 +74,8 @@ def sample(
     initial_archive=None,
     device=None,
     return_engine=False,
+    chunk_iterations=None,
+    history_budget_bytes=2 << 30,
 ):
     """Returns MCMC samples given a Posterior (or a list of them, coarsest first) and a proposal,
     exactly like ``tinyDA.sample``: one posterior -> Metropolis-Hastings, two -> Delayed
@@ -65,6 +86,14 @@ def sample(
     counter-based streams generated in-kernel, seeded by ``seed``) or 'injected' with
     ``streams=(normals[n_chains, nz], uniforms[n_chains, nu])``; ``store_model_output`` keeps
     F(theta) of every stored link (Link.model_output) -- switch it off for large runs.
+    ``seed=None`` draws a fresh seed from ``np.random`` (so ``np.random.seed`` makes the call repeatable,
+    as it does for the reference).
+
+    The run is cut into blocks of ``chunk_iterations`` fine iterations (default: as many as keep a block's
+    device history within ``history_budget_bytes``).  After each block the finest level's records are
+    compacted on the device to the accepted ones -- a rejected step repeats the previous Link
+    (chain.py:116, :434) -- and copied to pinned host memory while the next block runs; the result dict
+    expands a chain to a ``LinkSequence`` when its key is first read.
     """
     if subsampling_rate is not None:                                   # sampler.py:113-115
         warnings.warn(" subsampling_rate has been deprecated in favour of subchain_length.")
@@ -108,6 +137,8 @@ def sample(
         if not store_coarse_chain:
             raise ValueError("Randomize subchain length requires storing the coarse chain.")
 
+    if seed is None:
+        seed = _fresh_seed()
     # sharding: one process per GPU, contiguous chain ranges (ray.py:68-74 -> chain sharding)
     rank, world = parallel.rank_world()
     lo, hi = parallel.shard_range(n_chains, rank, world)
@@ -120,6 +151,8 @@ def sample(
             assert (
                 len(initial_parameters) == n_chains
             ), "If list of initial parameters is provided, it must have length n_chains"
+        elif type(initial_parameters) == np.ndarray and initial_parameters.ndim == 2 and initial_parameters.shape == (n_chains, d_prior):
+            pass                                     # extension: one row per chain (no Python list of 65536 arrays)
         elif type(initial_parameters) == np.ndarray:
             assert (
                 d_prior == initial_parameters.size
@@ -127,9 +160,12 @@ def sample(
             initial_parameters = [initial_parameters] * n_chains
         else:
             raise TypeError("Initial paramaters must be list, numpy array or None")
-        theta0 = np.array([np.atleast_1d(t) for t in initial_parameters[lo:hi]], dtype=np.float64)
+        if type(initial_parameters) == np.ndarray:
+            theta0 = np.ascontiguousarray(initial_parameters[lo:hi], dtype=np.float64)
+        else:
+            theta0 = np.array([np.atleast_1d(t) for t in initial_parameters[lo:hi]], dtype=np.float64)
     else:
-        host_rng = np.random.default_rng(None if seed is None else [int(seed), 7])
+        host_rng = np.random.default_rng([int(seed), 7])
         theta0 = np.atleast_2d(posteriors[0].prior.rvs(n_chains, random_state=host_rng)).reshape(n_chains, -1)[lo:hi]
 
     spec = lower_problem(posteriors, proposal, subchain_length if n_levels > 1 else None,
@@ -143,13 +179,14 @@ def sample(
         if initial_archive is not None:
             archive0 = np.asarray(initial_archive, dtype=np.float64)
         else:                                                           # proposal.py:788, per chain
-            host_rng = np.random.default_rng(None if seed is None else [int(seed), 11])
+            # every rank builds the same rows from the (broadcast) seed: one shared archive, ray.py:366-384
+            host_rng = np.random.default_rng([int(seed), 11])
             base = proposal.kernel if hasattr(proposal, "kernel") else proposal
             archive0 = np.stack([base.initial_archive(posteriors[0].prior, host_rng) for _ in range(n_chains)])
         if kind == PROP_DREAMZ:
             archive0 = archive0[lo:hi]
 
-    from .engine import Engine, STORE_FULL, STORE_STATS, STORE_NONE   # loads the CUDA library
+    from .engine import Engine, STORE_FULL, STORE_STATS, STORE_NONE, steps_per_iteration   # loads the CUDA library
     full = STORE_FULL if store_model_output else STORE_STATS
     store = [full] * n_levels
     if not store_coarse_chain:
@@ -160,58 +197,88 @@ def sample(
     if device is None:
         device = parallel.local_device()
     shared = kind == PROP_DREAM
+    steps = steps_per_iteration(spec)
+    itemsize = np.dtype(dtype).itemsize
+    if chunk_iterations is None:
+        chunk_iterations = _auto_chunk(iterations, n_local, spec, store, steps, itemsize, int(history_budget_bytes))
+    chunk_iterations = int(max(1, min(max(iterations, 1), chunk_iterations)))
     from ._lib import EngineError
     try:
-        eng = Engine(spec, n_local, dtype=dtype, rng=rng, seed=0 if seed is None else seed, store=store,
-                     capacity_iterations=iterations, streams=streams, device=device,
+        eng = Engine(spec, n_local, dtype=dtype, rng=rng, seed=seed, store=store,
+                     capacity_iterations=chunk_iterations, archive_iterations=iterations, streams=streams, device=device,
                      chain_offset=lo, n_chains_global=n_chains if shared else n_local,
                      archive0=archive0, am_device_refactor=True)
     except EngineError as exc:
         if "cudaMalloc" in str(exc):
             # the reference keeps every Link (with its model output) of every level in host lists;
-            # here that history lives in HBM until it is fetched
-            raise EngineError(str(exc) + " -- the Link history of %d chains x %d iterations does not fit in device "
-                              "memory: pass store_model_output=False and/or store_coarse_chain=False, or "
-                              "sample in several calls" % (n_local, iterations)) from None
+            # here a block of that history lives in HBM until it is fetched
+            raise EngineError(str(exc) + " -- a block of %d iterations of the Link history of %d chains does not fit in "
+                              "device memory: pass a smaller chunk_iterations, store_model_output=False and/or "
+                              "store_coarse_chain=False" % (chunk_iterations, n_local)) from None
         raise
-    if kind == PROP_DREAMZ:
-        # per-chain archives live in the same [slot][chain][d] array, indexed by the local chain
-        pass
     print("Sampling {} chains in lock-step on GPU {}".format(n_chains, device))
     eng.init(theta0)
-    if shared and world > 1:
-        parallel.run_dream_shared(eng, iterations, rank, world)
-    else:
-        eng.run(iterations)
+
+    top = n_levels - 1
+    n_qoi = [int(lv["model"].get("n_qoi", 0)) for lv in spec["levels"]]
+    fields = ["theta", "stats"] + (["output"] if store_model_output else []) + (["qoi"] if n_qoi[top] else [])
+    hist = CompactHistory(n_local)
+    dense_parts = {l: [] for l in range(top) if store[l]}
+    done, slot, pending, block = 0, 0, None, 0
+    while True:
+        n = min(chunk_iterations, iterations - done)
+        if block:
+            eng.history_reset()
+        if n > 0:
+            if shared and world > 1:
+                parallel.run_dream_shared(eng, n, rank, world)
+            else:
+                eng.run(n)
+        nrec = n + (1 if block == 0 else 0)          # block 0 starts with the initial Link
+        if nrec > 0:
+            for l in dense_parts:
+                nl = n * steps[l]
+                if nl:
+                    dense_parts[l].append((eng.fetch(l, "theta", 0, nl, sync=False), eng.fetch(l, "prior", 0, nl, sync=False),
+                                           eng.fetch(l, "like", 0, nl, sync=False), eng.fetch(l, "accept", 0, nl, sync=False),
+                                           eng.fetch(l, "output", 0, nl, sync=False) if store_model_output else None,
+                                           eng.fetch(l, "qoi", 0, nl, sync=False) if n_qoi[l] else None))
+            eng.compact_begin(0, nrec, block == 0, fields, slot)
+            if pending is not None:
+                hist.append(eng.compact_collect(pending))
+            pending, slot = slot, slot ^ 1
+        done += n
+        block += 1
+        if done >= iterations:
+            break
+    if pending is not None:
+        hist.append(eng.compact_collect(pending))
+    eng.compact_sync()
     eng.sync()
 
     # result dict, sampler.py:305-309, :406-439, :510-547
     if n_levels == 1:
-        info = {"sampler": "MH", "n_chains": n_chains, "iterations": iterations + 1}
-        seqs = _result_sequences(eng, 0, n_local, store_model_output)
-        chains = {"chain_{}".format(lo + i): s for i, s in enumerate(seqs)}
-        result = {**info, **chains}
+        result = SampleResult({"sampler": "MH", "n_chains": n_chains, "iterations": iterations + 1})
+        keys = ["chain_{}"]
     elif n_levels == 2:
-        info = {"sampler": "DA", "n_chains": n_chains, "iterations": iterations + 1,
-                "subchain_length": subchain_length}
-        if store_coarse_chain:
-            seqs = _result_sequences(eng, 0, n_local, store_model_output)
-            coarse = {"chain_coarse_{}".format(lo + i): s for i, s in enumerate(seqs)}
-        else:
-            coarse = {"chain_coarse_{}".format(lo + i): None for i in range(n_local)}
-        seqs = _result_sequences(eng, 1, n_local, store_model_output)
-        fine = {"chain_fine_{}".format(lo + i): s for i, s in enumerate(seqs)}
-        result = {**info, **coarse, **fine}
+        result = SampleResult({"sampler": "DA", "n_chains": n_chains, "iterations": iterations + 1,
+                               "subchain_length": subchain_length})
+        keys = ["chain_coarse_{}", "chain_fine_{}"]
     else:
-        info = {"sampler": "MLDA", "n_chains": n_chains, "iterations": iterations + 1,
-                "levels": n_levels, "subchain_lengths": list(spec["J"])}
-        result = dict(info)
-        for l in reversed(range(n_levels)):
-            if l == n_levels - 1 or store_coarse_chain:
-                seqs = _result_sequences(eng, l, n_local, store_model_output)
-                result.update({"chain_l{}_{}".format(l, lo + i): s for i, s in enumerate(seqs)})
-            else:
-                result.update({"chain_l{}_{}".format(l, lo + i): None for i in range(n_local)})
+        result = SampleResult({"sampler": "MLDA", "n_chains": n_chains, "iterations": iterations + 1,
+                               "levels": n_levels, "subchain_lengths": list(spec["J"])})
+        keys = ["chain_l%d_{}" % l for l in range(n_levels)]
+    for l in reversed(range(top)):
+        if not store_coarse_chain:
+            factory = lambda c: None                  # sampler.py:429-431, :541-543
+        elif dense_parts[l]:
+            factory = _dense_family(dense_parts[l])
+        else:
+            factory = lambda c: []                    # no iterations: no coarse Link exists yet
+        result.add_chains(keys[l], lo, hi, factory)
+    result.add_chains(keys[top], lo, hi, hist.chain)
+    result.history = hist                     # the finest level of the local chains, compacted (link.CompactHistory)
+    result.local_chains = (lo, hi)
     if world > 1:
         result["local_chains"] = (lo, hi)
     if return_engine:
