@@ -184,7 +184,49 @@ def make(name):
           % (name, L, C, iters, consumed[0].tolist(), os.path.basename(path), os.path.getsize(path) / 1024))
 
 
+def make_long(name="da_pcn_cfg2", C=8, iters=200, seed=143):
+    """BASELINE cfg2 at its real shape, 8 chains x 200 fine iterations (2000 coarse steps per chain): the
+    fixture the float32 kernels' measured state error and decision-flip rate are quoted on
+    (tests/golden/long/<name>.npz; tests/test_gpu_fp32_error.py, tests/test_oracle_golden.py).
+    To keep it small the normals sit on the fp16 grid at scale 4096 (stored as float16 of 4096 z: exactly
+    what the tensor-core kernel's operand image holds) and the coarse level keeps log-likelihood and accept
+    flags only."""
+    tda = rh.import_reference()
+    defn = problems.CASES[name]()
+    posts_ref, prop_ref, kw = defn["build"](tda)
+    posts_our, prop_our, kw2 = defn["build"](ours)
+    spec = ours.lower_problem(posts_our, prop_our, kw2.get("subchain_length"))
+    rng = np.random.default_rng(seed)
+    nz, nu = problems.stream_sizes(spec, iters)
+    z16 = (rng.standard_normal((C, nz)) * 4096.0).astype(np.float16)
+    z = z16.astype(np.float64) / 4096.0
+    u = rng.random((C, nu))
+    theta0 = np.atleast_2d(defn["prior"].rvs(C, random_state=rng)).reshape(C, -1)
+    out = dict(theta0=theta0, z16=z16, u=u, iterations=np.array(iters))
+    hists, consumed = [], []
+    for c in range(C):
+        S = rh.Streams(z[c], u[c])
+        np.random.seed(1000 + c)
+        with rh.injected(S):
+            h, ch = run_reference_chain(tda, posts_ref, prop_ref, kw, theta0[c], iters, False)
+        hists.append(h)
+        consumed.append([S.nz, S.nu])
+        print("chain", c, "fine accept rate", h[1]["acc"].mean(), "coarse", h[0]["acc"].mean())
+    out["consumed"] = np.array(consumed)
+    for l, keys in ((0, ("like", "acc")), (1, ("theta", "prior", "like", "acc"))):
+        for k in keys:
+            out["ref/l%d/%s" % (l, k)] = np.stack([hists[c][l][k] for c in range(C)])
+    out.update(spec_to_flat(spec))
+    os.makedirs(os.path.join(HERE, "long"), exist_ok=True)
+    path = os.path.join(HERE, "long", name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%s: %d chains x %d iterations -> %s (%.1f KB)" % (name, C, iters, path, os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
+    if sys.argv[1:2] == ["--long"]:
+        make_long()
+        sys.exit(0)
     names = sys.argv[1:] or list(problems.CASES)
     for n in names:
         make(n)

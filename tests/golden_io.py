@@ -13,8 +13,13 @@ def names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
-def load(name):
-    flat = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False))
+def load(name, long=False):
+    """long=True: tests/golden/long/<name>.npz (make_golden.py --long): normals stored on the fp16 grid
+    (float16 of 4096 z), coarse level without parameters."""
+    path = os.path.join(GOLDEN_DIR, "long", name + ".npz") if long else os.path.join(GOLDEN_DIR, name + ".npz")
+    flat = dict(np.load(path, allow_pickle=False))
+    if "z16" in flat:
+        flat["z"] = flat["z16"].astype(np.float64) / 4096.0
     spec = spec_from_flat(flat)
     L = spec["n_levels"]
     ref = []

@@ -1,0 +1,99 @@
+"""MEASURED float32 parity of every kernel that can run BASELINE cfg2, on the long reference fixture
+(tests/golden/long/da_pcn_cfg2.npz: the unmodified reference, 8 chains x 200 fine iterations = 2000
+coarse + 200 fine decisions per chain, injected streams).
+
+north_star: "states within 1e-5 relative in fp32 mode, excepting documented near-tie accepts".  For each
+kernel this test prints -- and writes to gpurun_out/fp32_parity.json -- the decision-flip rate (first
+divergence per chain over the decisions compared before it) and the largest relative state error on the
+common prefix, and asserts the tolerance written below.  After its first flipped near-tie a chain follows
+a different, equally valid trajectory, so only the common prefix is compared.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+STATE_RTOL = 1e-5          # north_star's fp32 tolerance, relative to the largest |theta| of the chain
+LIKE_ATOL = 0.05           # absolute, on log-likelihoods of magnitude 1e2 .. 1e5
+MAX_FLIP_RATE = 2e-3       # flipped near-ties per accept/reject decision
+
+
+def _run(g, kernel, dtype="float32"):
+    from tinyda_b200.engine import Engine, STORE_STATS
+    C, iters = g["theta0"].shape[0], g["iterations"]
+    eng = Engine(g["spec"], C, dtype=dtype, rng="injected", streams=(g["z"], g["u"]), store=[STORE_STATS, STORE_STATS],
+                 capacity_iterations=iters)
+    eng.select_kernel(kernel)
+    eng.init(g["theta0"])
+    eng.run(iters)
+    eng.sync()
+    out = dict(kernel=eng.kernel(),
+               acc_f=eng.fetch(1, "accept").T.astype(bool), acc_c=eng.fetch(0, "accept").T.astype(bool),
+               theta=np.transpose(eng.fetch(1, "theta"), (2, 0, 1)).astype(np.float64),
+               like_f=eng.fetch(1, "like").T.astype(np.float64), like_c=eng.fetch(0, "like").T.astype(np.float64),
+               prior=eng.fetch(1, "prior").T.astype(np.float64), cursors=eng.get("cursors").T)
+    eng.close()
+    return out
+
+
+def _measure(g, out):
+    """Common prefix per chain in units of fine iterations: the first fine iteration whose own decision or one
+    of whose J coarse decisions differs."""
+    c_ref, f_ref = g["ref"]
+    C, n_f = f_ref["acc"].shape          # n_f = iterations + 1 (record 0 = initial link)
+    J = c_ref["acc"].shape[1] // (n_f - 1)
+    first, decisions, flips = [], 0, 0
+    err_theta, err_like, err_like_c = 0.0, 0.0, 0.0
+    for c in range(C):
+        bad_f = np.nonzero(out["acc_f"][c, 1:] != f_ref["acc"][c, 1:])[0]
+        bad_c = np.nonzero(out["acc_c"][c] != c_ref["acc"][c])[0]
+        it_f = bad_f[0] if bad_f.size else n_f - 1
+        it_c = bad_c[0] // J if bad_c.size else n_f - 1
+        k = int(min(it_f, it_c))                       # fine iterations fully agreed: records 0..k of the fine chain
+        first.append(k)
+        decisions += k * (J + 1) + (J + 1 if k < n_f - 1 else 0)
+        flips += 1 if k < n_f - 1 else 0
+        scale = np.abs(f_ref["theta"][c]).max()
+        err_theta = max(err_theta, np.abs(out["theta"][c, :k + 1] - f_ref["theta"][c, :k + 1]).max() / scale)
+        err_like = max(err_like, np.abs(out["like_f"][c, :k + 1] - f_ref["like"][c, :k + 1]).max())
+        if k:
+            err_like_c = max(err_like_c, np.abs(out["like_c"][c, :k * J] - c_ref["like"][c, :k * J]).max())
+    return dict(first_divergence_fine_iteration=first, decisions_compared=int(decisions), flips=int(flips),
+                flip_rate_per_decision=flips / max(1, decisions), max_rel_state_error=float(err_theta),
+                max_abs_loglike_error_fine=float(err_like), max_abs_loglike_error_coarse=float(err_like_c))
+
+
+@pytest.mark.parametrize("kernel", ["tc16", "tc", "generic"])
+def test_fp32_kernels_measured_error_and_flip_rate_on_the_long_cfg2_fixture(kernel):
+    g = golden_io.load("da_pcn_cfg2", long=True)
+    out = _run(g, kernel)
+    assert out["kernel"] == kernel
+    m = _measure(g, out)
+    print("\nfp32 parity [%s]: %s" % (kernel, json.dumps(m)))
+    os.makedirs("gpurun_out", exist_ok=True)
+    path = os.path.join("gpurun_out", "fp32_parity.json")
+    allm = json.load(open(path)) if os.path.exists(path) else {}
+    allm[kernel] = m
+    json.dump(allm, open(path, "w"), indent=1)
+    assert m["max_rel_state_error"] <= STATE_RTOL, m
+    assert m["max_abs_loglike_error_fine"] <= LIKE_ATOL and m["max_abs_loglike_error_coarse"] <= LIKE_ATOL, m
+    assert m["flip_rate_per_decision"] <= MAX_FLIP_RATE, m
+    # the bulk of the 8 x 2200 decisions is compared before any chain leaves the reference trajectory
+    assert m["decisions_compared"] >= 0.5 * 8 * 2200, m
+
+
+def test_fp64_engine_reproduces_the_long_cfg2_fixture_exactly():
+    g = golden_io.load("da_pcn_cfg2", long=True)
+    out = _run(g, "generic", dtype="float64")
+    c_ref, f_ref = g["ref"]
+    assert np.array_equal(out["acc_f"][:, 1:], f_ref["acc"][:, 1:]) and np.array_equal(out["acc_c"], c_ref["acc"])
+    scale = np.abs(f_ref["theta"]).max()
+    np.testing.assert_allclose(out["theta"], f_ref["theta"], rtol=1e-10, atol=1e-10 * scale)
+    np.testing.assert_allclose(out["like_f"], f_ref["like"], rtol=1e-9, atol=1e-8)
+    np.testing.assert_allclose(out["like_c"], c_ref["like"], rtol=1e-9, atol=1e-8)
+    assert np.array_equal(out["cursors"], g["consumed"])

@@ -26,3 +26,19 @@ def test_oracle_matches_reference(name):
     # identical stream consumption (control-flow dependent)
     consumed = np.array([[ch.S.nz, ch.S.nu] for ch in chains])
     assert np.array_equal(consumed, g["consumed"])
+
+
+def test_oracle_matches_reference_on_the_long_cfg2_fixture():
+    """BASELINE cfg2 at its real shape, 8 chains x 200 fine iterations (tests/golden/long/, made by
+    make_golden.py --long from the unmodified reference): decisions of both levels identical, fine-level
+    states and densities at summation-order accuracy."""
+    g = golden_io.load("da_pcn_cfg2", long=True)
+    out, chains = orc.run_chains(g["spec"], g["theta0"], g["z"], g["u"], g["iterations"], None)
+    c_ref, f_ref = g["ref"]
+    assert np.array_equal(out[0]["acc"], c_ref["acc"]) and np.array_equal(out[1]["acc"], f_ref["acc"])
+    assert f_ref["acc"].shape == (8, 201) and c_ref["acc"].shape == (8, 2000)
+    np.testing.assert_allclose(out[1]["theta"], f_ref["theta"], rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(out[1]["prior"], f_ref["prior"], rtol=RTOL, atol=1e-11)
+    np.testing.assert_allclose(out[1]["like"], f_ref["like"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(out[0]["like"], c_ref["like"], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(np.array([[ch.S.nz, ch.S.nu] for ch in chains]), g["consumed"])
