@@ -703,7 +703,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tc", "tc16"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tc", "tc16", "tcr"])
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default: the workload's)")
     ap.add_argument("--iters", type=int, default=None, help="finest-level iterations per step (default: the workload's)")
     ap.add_argument("--history", default="fine", choices=["fine", "coarse"],

@@ -252,6 +252,10 @@ int tda_compact_rows(tda_engine *e, int slot, int64_t *n_rows);
 int tda_compact_fetch(tda_engine *e, int slot, int field, void *host_dst, size_t dst_bytes, size_t *bytes);
 int tda_compact_sync(tda_engine *e);
 
+/* Device blocks of destroyed engines are kept in a process-wide pool and reused by the next engine (cudaMalloc /
+ * cudaFree of multi-GB history buffers cost more than a short run); this returns them to the driver. */
+int tda_pool_trim(void);
+
 /* Page-locked host memory for asynchronous copies (cudaHostAlloc / cudaFreeHost). */
 int tda_host_alloc(size_t bytes, void **ptr);
 int tda_host_free(void *ptr);
@@ -265,7 +269,9 @@ int tda_history_reset(tda_engine *e);
  * isotropic or diagonal likelihood, Rosenbrock or a linear model with m <= 256; fails otherwise),
  * 2 = tcgen05 tensor-core Delayed-Acceptance kernel with 3xTF32 operands, 3 = tcgen05
  * Delayed-Acceptance kernel with two-term fp16-split operands and normals produced by dedicated
- * warps (2 and 3 fail if the configuration is not supported).  Kernel 3 consumes the "z16"
+ * warps, 5 = tcgen05 Delayed-Acceptance kernel with whitened chain state and output recursion
+ * (tda_da_tcr.cu; per-chain pCN step sizes; the coarse chain is not recorded) (2, 3 and 5 fail if the
+ * configuration is not supported).  Kernels 3 and 5 consume the "z16"
  * Philox normal stream (normals rounded to the fp16 grid at scale 4096); tda_fill_streams
  * exports whatever stream the selected kernel consumes. */
 int tda_select_kernel(tda_engine *e, int which);

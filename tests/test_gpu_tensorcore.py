@@ -64,7 +64,7 @@ def test_fp16_split_gemm_matches_fp64(a_in_tmem, N):
 
 
 # ---- tensor-core Delayed-Acceptance kernels --------------------------------------------------
-KERNELS = ["tc", "tc16"]
+KERNELS = ["tc", "tc16", "tcr"]
 
 
 def _cfg2_engine(C, kernel, seed=9, rng="philox", streams=None, iters=30, theta0=None, chain_offset=0, store=None):
@@ -114,7 +114,7 @@ def test_tc_kernel_agrees_with_generic_fp32_kernel(kernel):
     C, iters = 512, 30
     a, _ = _cfg2_engine(C, kernel, iters=iters)
     b, _ = _cfg2_engine(C, "generic", iters=iters)
-    if kernel == "tc16":
+    if kernel in ("tc16", "tcr"):
         b.set_z_round(True)            # same normal stream (fp16 grid) for the generic kernel
     a.run(iters)
     b.run(iters)
@@ -149,7 +149,8 @@ def test_tc_kernel_resume_and_sharding_exact(kernel):
     assert np.array_equal(th_a[:, :, 256:512], th_c)
 
 
-def test_tc16_iteration_blocks_hand_chains_between_sms_exactly(monkeypatch):
+@pytest.mark.parametrize("kernel", ["tc16", "tcr"])
+def test_tc16_iteration_blocks_hand_chains_between_sms_exactly(monkeypatch, kernel):
     """tc16 cuts a launch into (tile pair, iteration block) units dealt round-robin over the SMs; with
     more pairs than SMs consecutive blocks of a pair run on different SMs and the state travels through
     global memory.  The result must not depend on the block count, bit for bit."""
@@ -160,7 +161,7 @@ def test_tc16_iteration_blocks_hand_chains_between_sms_exactly(monkeypatch):
     outs = []
     for blocks in ("1", "3", "7"):
         monkeypatch.setenv("TDA_TC16_BLOCKS", blocks)
-        eng, _ = _cfg2_engine(C, "tc16", iters=iters, theta0=theta0)
+        eng, _ = _cfg2_engine(C, kernel, iters=iters, theta0=theta0)
         eng.run(3)
         eng.run(iters - 3)
         outs.append((eng.fetch(1, "theta"), eng.fetch(1, "like"), eng.fetch(1, "accept"), eng.get("accept_counts"),
@@ -172,15 +173,17 @@ def test_tc16_iteration_blocks_hand_chains_between_sms_exactly(monkeypatch):
     assert outs[0][2][1:].mean() > 0.3
 
 
-def test_tc16_philox_streams_fed_to_the_oracle():
+@pytest.mark.parametrize("kernel", ["tc16", "tcr"])
+def test_tc16_philox_streams_fed_to_the_oracle(kernel):
     """Production mode of the fp16-split kernel: its z16 / uniform streams exported with
     tda_fill_streams and fed to the CPU oracle reproduce the accept decisions and (to float32
     accuracy) the states, chain by chain until the first near-tie."""
     from oracle import tinyda_oracle as orc
     C, iters = 64, 12
-    eng, w = _cfg2_engine(C, "tc16", iters=iters, chain_offset=7)
+    eng, w = _cfg2_engine(C, kernel, iters=iters, chain_offset=7)
     theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1))
     eng.run(iters)
+    assert eng.kernel() == kernel
     z, u = eng.fill_streams(iters * 10 * 64, iters * 11)
     zh = (z * 4096).astype(np.float16).astype(np.float64) / 4096
     assert np.array_equal(zh, z)                                  # the stream lies on the fp16 grid

@@ -32,7 +32,7 @@ EXPORTS = [
     "tda_select_kernel", "tda_launch_count", "tda_tc_gemm_selftest", "tda_tc16_gemm_selftest",
     "tda_state_size", "tda_state_save", "tda_state_load",
     "tda_engine_burn", "tda_compact_begin", "tda_compact_rows", "tda_compact_fetch", "tda_compact_sync",
-    "tda_host_alloc", "tda_host_free",
+    "tda_host_alloc", "tda_host_free", "tda_pool_trim",
 ]
 
 

@@ -11,6 +11,9 @@
 #include "tda_da_tc16.cuh"
 #include "tda_mh_reg.cuh"
 #include "tda_post.h"
+#include "tda_da_tcr.h"
+#include <map>
+#include <mutex>
 
 namespace {
 
@@ -30,6 +33,65 @@ int fail(int code, const std::string& msg) {
     } while (0)
 
 inline int round_up(int x, int q) { return (x + q - 1) / q * q; }
+
+// Device-memory pool.  cudaMalloc / cudaFree of the multi-GB history and compaction buffers cost tens to
+// hundreds of milliseconds (and cudaFree synchronises the device), which would dominate a tda.sample() call
+// of a few hundred iterations: blocks released by a destroyed engine are kept, keyed by device and size
+// class (<= 12.5 % slack), and handed to the next engine.  tda_pool_trim() returns them to the driver; a
+// failed cudaMalloc trims and retries.
+struct DevPool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> blocks;
+    size_t held = 0;
+    size_t cap() const {
+        static const size_t c = [] { const char* e = getenv("TDA_DEVICE_POOL_MAX_GB"); return (size_t)(e ? atof(e) : 64.0) << 30; }();
+        return c;
+    }
+    static size_t size_class(size_t bytes) {
+        if (bytes < 512) return 512;
+        int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+        const size_t step = (size_t)1 << (lg > 12 ? lg - 3 : 9);
+        return (bytes + step - 1) / step * step;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto& kv : blocks) { cudaSetDevice(kv.first.first); cudaFree(kv.second); }
+        cudaSetDevice(cur);
+        blocks.clear();
+        held = 0;
+    }
+    cudaError_t alloc(void** out, size_t cls, int device) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = blocks.find({device, cls});
+            if (it != blocks.end()) {
+                *out = it->second;
+                blocks.erase(it);
+                held -= cls;
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc(out, cls);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(out, cls);
+        }
+        return e;
+    }
+    void release(void* ptr, size_t cls, int device) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (held + cls <= cap()) {
+            blocks.insert({{device, cls}, ptr});
+            held += cls;
+        } else {
+            cudaFree(ptr);
+        }
+    }
+};
+DevPool g_pool;
 
 }  // namespace
 
@@ -152,6 +214,30 @@ __global__ void __launch_bounds__(256) hist_fill_kernel(const R* __restrict__ th
     if (mode == 1) *dst = (R)-0.5 * (logconst + ssq);
 }
 
+// the tcr kernel lives in its own translation unit and is float only
+template <typename R>
+struct TcrAdapter {
+    std::string err;
+    bool eligible(const tda_config&, const tda::Params<R>&) const { return false; }
+    int ready(const tda::Params<R>&, const tda_config&, cudaStream_t) { return 1; }
+    int run(tda::Params<R>&, const tda_config&, long long, int, cudaStream_t) { return -5; }
+    void invalidate() {}
+    void destroy() {}
+};
+template <>
+struct TcrAdapter<float> {
+    tda::DaTcrState s;
+    std::string err;
+    bool eligible(const tda_config& c, const tda::Params<float>& P) const {
+        static const bool off = getenv("TDA_DISABLE_TCR") != nullptr;
+        return !off && s.eligible(c, P);
+    }
+    int ready(const tda::Params<float>& P, const tda_config& c, cudaStream_t st) { int r = s.ready(P, c, st); err = s.err; return r; }
+    int run(tda::Params<float>& P, const tda_config& c, long long it, int sms, cudaStream_t st) { int r = s.run(P, c, it, sms, st); err = s.err; return r; }
+    void invalidate() { s.invalidate(); }
+    void destroy() { s.destroy(); }
+};
+
 // Link.qoi of models that are not linear in theta: qoi[r][j][c] = q0[j] + sum_n Q[j][n] * F[r][n][c]
 // (thread = one (record, chain); lane = chain -> coalesced)
 template <typename R>
@@ -173,6 +259,7 @@ struct EngineT : tda_engine {
     tda::Params<R> P;
     std::vector<void*> allocs;
     std::vector<size_t> alloc_bytes;
+    std::vector<size_t> alloc_cls;      // size class the block came from (device pool)
     std::vector<char> alloc_is_state;   // 0: history buffer (not part of a checkpoint)
     bool alloc_history = false;
     int Cs = 0, n_tiles = 0, kt = 0, sm_count = 148;
@@ -186,6 +273,8 @@ struct EngineT : tda_engine {
     tda::DaTcState<R> tc;      // tcgen05 fast path (float only; inert for double)
     tda::DaTc16State<R> tc16;  // fp16-split tcgen05 fast path (float only)
     bool tc16_unfit = false;   // prepare() found operands that do not fit the fp16 range
+    TcrAdapter<R> tcr;         // whitened-state / output-recursion tcgen05 kernel (float only), tda_da_tcr.cu
+    bool tcr_unfit = false;
     // records written by the fp16-split kernel whose derived fields (coarse Link.prior, Link.model_output)
     // have not been filled yet, per level; and: the levels' current model outputs lag behind theta
     long long lazy_lo[tda::MAXL] = {0, 0, 0, 0}, lazy_hi[tda::MAXL] = {0, 0, 0, 0};
@@ -216,12 +305,13 @@ struct EngineT : tda_engine {
 
     ~EngineT() override {
         cudaSetDevice(device);
-        for (void* p : allocs) cudaFree(p);
+        cudaDeviceSynchronize();           // nothing of this engine is in flight when its blocks go back to the pool
+        for (size_t i = 0; i < allocs.size(); i++) g_pool.release(allocs[i], alloc_cls[i], device);
         for (auto& s : cslot) {
             if (s.offsets) cudaFree(s.offsets);
             if (s.scratch) cudaFree(s.scratch);
-            if (s.flags) cudaFree(s.flags);
-            for (void* b : s.buf) if (b) cudaFree(b);
+            if (s.flags) g_pool.release(s.flags, s.flags_cap, device);
+            for (int f = 0; f < 5; f++) if (s.buf[f]) g_pool.release(s.buf[f], s.cap[f], device);
             if (s.total_pinned) cudaFreeHost(s.total_pinned);
             if (s.ready) cudaEventDestroy(s.ready);
             if (s.copied) cudaEventDestroy(s.copied);
@@ -229,18 +319,22 @@ struct EngineT : tda_engine {
         if (copy_stream) cudaStreamDestroy(copy_stream);
         tc.destroy();
         tc16.destroy();
+        tcr.destroy();
     }
 
     template <typename T>
     int dalloc(T** out, size_t n) {
         void* p = nullptr;
         size_t bytes = (n ? n : 1) * sizeof(T);
-        cudaError_t e = cudaMalloc(&p, bytes);
+        const size_t cls = DevPool::size_class(bytes);
+        cudaError_t e = g_pool.alloc(&p, cls, device);
         if (e != cudaSuccess) return fail(-3, std::string("cudaMalloc ") + std::to_string(bytes) + " bytes: " + cudaGetErrorString(e));
-        e = cudaMemset(p, 0, bytes);
+        // history buffers are written before they are read (the record counters say how far): no clearing
+        if (!alloc_history) e = cudaMemsetAsync(p, 0, bytes, 0);
         if (e != cudaSuccess) return fail(-3, std::string("cudaMemset: ") + cudaGetErrorString(e));
         allocs.push_back(p);
         alloc_bytes.push_back(bytes);
+        alloc_cls.push_back(cls);
         alloc_is_state.push_back(alloc_history ? 0 : 1);
         *out = reinterpret_cast<T*>(p);
         return 0;
@@ -720,6 +814,8 @@ struct EngineT : tda_engine {
         if (tda::is_dream(P.prop_kind)) dream_slots = cfg.dream_M0;
         for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = 0; P.lvl_steps[l] = 0; lazy_lo[l] = lazy_hi[l] = 0; }
         state_F_stale = false;
+        tcr.invalidate();
+        tcr_unfit = false;
         CUDA_TRY(cudaSetDevice(device));
         CUDA_TRY(cudaMemsetAsync(P.error_flag, 0, sizeof(int), st));
         int r = launch(tda::MODE_INIT, 0, st);
@@ -731,11 +827,13 @@ struct EngineT : tda_engine {
 
     bool tc_eligible() const { return tc.eligible(cfg, P); }
     bool tc16_eligible() const { return !tc16_unfit && tc16.eligible(cfg, P); }
+    bool tcr_eligible() const { return !tcr_unfit && tcr.eligible(cfg, P); }
     bool reg_eligible() const { return tda::mh_reg_eligible(cfg, P.lv[0].need_F != 0) && !z_round_user; }
     // which kernel tda_engine_run launches: 1 generic, 2 tensor-core 3xTF32, 3 tensor-core fp16 split,
     // 4 register-resident single-level
     int resolved_kernel() const {
-        if (kernel_choice >= 1 && kernel_choice <= 4) return kernel_choice;
+        if (kernel_choice >= 1 && kernel_choice <= 5) return kernel_choice;
+        if (tcr_eligible()) return 5;
         if (tc16_eligible()) return 3;
         if (tc_eligible()) return 2;
         if (reg_eligible()) return 4;
@@ -744,7 +842,8 @@ struct EngineT : tda_engine {
     // the fp16-split kernel consumes the z16 normal stream; the others do on request
     int z_round_effective() const {
         if (cfg.dtype != TDA_F32 || P.rng_mode != TDA_RNG_PHILOX) return 0;
-        return (resolved_kernel() == 3 || z_round_user) ? 1 : 0;
+        const int k = resolved_kernel();
+        return (k == 3 || k == 5 || z_round_user) ? 1 : 0;
     }
 
     int run(long long iterations, cudaStream_t st, bool record = true) override {
@@ -789,7 +888,19 @@ struct EngineT : tda_engine {
         if (kernel_choice == 2 && !tc_eligible()) return fail(-1, "run: tensor-core DA kernel does not support this configuration");
         if (kernel_choice == 3 && !tc16.eligible(cfg, P)) return fail(-1, "run: fp16-split tensor-core DA kernel does not support this configuration");
         if (kernel_choice == 4 && !reg_eligible()) return fail(-1, "run: register-resident kernel does not support this configuration");
+        if (kernel_choice == 5 && !tcr.eligible(cfg, P)) return fail(-1, "run: whitened-state tensor-core DA kernel does not support this configuration");
         int which = resolved_kernel();
+        if (which == 5) {
+            // operand images on first use, whitened state when theta was last written by someone else; a
+            // problem (or a chain state) outside the fp16 range falls back to the older kernels
+            int r = tcr.ready(P, cfg, st);
+            if (r < 0) return fail(r, tcr.err);
+            if (r > 0) {
+                if (kernel_choice == 5) return fail(-1, "run: " + tcr.err);
+                tcr_unfit = true;
+                which = resolved_kernel();
+            }
+        }
         if (which == 3 && !tc16.prepared) {
             // operand scaling happens on first use; a problem that does not fit fp16 falls back
             int r = tc16.prepare(P, cfg);
@@ -802,12 +913,13 @@ struct EngineT : tda_engine {
         }
         P.z_round = z_round_effective();
         int r;
-        if (which != 3) {
+        if (which != 3 && which != 5) {
             r = fill_lazy_history(st);
             if (!r) r = refresh_state_outputs(st);
             if (r) return r;
         }
-        if (which == 3 && iterations > (1 << 20)) {
+        if (which != 5) tcr.invalidate();          // theta moves without the whitened copy
+        if ((which == 3 || which == 5) && iterations > (1 << 20)) {
             // the fp16-split kernel counts its coarse steps per launch in 32 bits
             for (long long done = 0; done < iterations;) {
                 const long long n = iterations - done < (1 << 20) ? iterations - done : (1 << 20);
@@ -817,7 +929,11 @@ struct EngineT : tda_engine {
             }
             return 0;
         }
-        if (which == 3) {
+        if (which == 5) {
+            r = tcr.run(P, cfg, iterations, sm_count, st);
+            if (r) return fail(r < 0 ? r : -1, tcr.err);
+            g_launches++;
+        } else if (which == 3) {
             r = tc16.run(P, cfg, iterations, sm_count, st);
             if (r) return fail(r, tc16.err);
             g_launches++;
@@ -851,7 +967,7 @@ struct EngineT : tda_engine {
         long long w = steps[0];
         for (int l = 1; l < L; l++) w += steps[l];
         P.wcount += (L == 1) ? steps[0] : w;
-        if (which == 3) {
+        if (which == 3 || which == 5) {
             if (!burning)
                 for (int l = 0; l < L; l++) {
                     if (lazy_lo[l] == lazy_hi[l]) lazy_lo[l] = P.rec[l];
@@ -899,6 +1015,7 @@ struct EngineT : tda_engine {
             if (r) return r;
         } else {
             state_F_stale = false;
+            tcr.invalidate();
             for (int l = 0; l < tda::MAXL; l++) lazy_lo[l] = lazy_hi[l] = 0;
         }
         CUDA_TRY(cudaDeviceSynchronize());
@@ -990,12 +1107,13 @@ struct EngineT : tda_engine {
     template <typename T>
     int grow(T** ptr, size_t* cap, size_t need_bytes) {
         if (*cap >= need_bytes && *ptr) return 0;
-        if (*ptr) cudaFree(*ptr);
+        if (*ptr) { CUDA_TRY(cudaDeviceSynchronize()); g_pool.release(*ptr, *cap, device); }
         *ptr = nullptr; *cap = 0;
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, need_bytes ? need_bytes : 1);
+        const size_t cls = DevPool::size_class(need_bytes ? need_bytes : 1);
+        cudaError_t e = g_pool.alloc(&q, cls, device);
         if (e != cudaSuccess) return fail(-3, std::string("cudaMalloc ") + std::to_string(need_bytes) + " bytes (compacted history): " + cudaGetErrorString(e));
-        *ptr = reinterpret_cast<T*>(q); *cap = need_bytes;
+        *ptr = reinterpret_cast<T*>(q); *cap = cls;
         return 0;
     }
 
@@ -1015,10 +1133,8 @@ struct EngineT : tda_engine {
         if (!s.ready) { CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)); }
         if (!s.total_pinned) CUDA_TRY(cudaHostAlloc((void**)&s.total_pinned, sizeof(long long), cudaHostAllocPortable));
         if (!s.offsets) {
-            size_t c0 = 0, c1 = 0;
-            int r0 = grow(&s.offsets, &c0, ((size_t)P.C + 1) * sizeof(long long));
-            if (!r0) r0 = grow(&s.scratch, &c1, ((size_t)(P.C + 255) / 256 + 2) * sizeof(long long));
-            if (r0) return r0;
+            CUDA_TRY(cudaMalloc((void**)&s.offsets, ((size_t)P.C + 1) * sizeof(long long)));
+            CUDA_TRY(cudaMalloc((void**)&s.scratch, ((size_t)(P.C + 255) / 256 + 2) * sizeof(long long)));
         }
         // copies of the slot's previous contents must have left the device buffers
         if (s.has_copies) CUDA_TRY(cudaStreamWaitEvent(st, s.copied, 0));
@@ -1359,6 +1475,10 @@ int tda_host_alloc(size_t bytes, void** ptr) {
     if (!ptr) return fail(-1, "null argument");
     *ptr = nullptr;
     CUDA_TRY(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return 0;
+}
+int tda_pool_trim(void) {
+    g_pool.trim();
     return 0;
 }
 int tda_host_free(void* ptr) {

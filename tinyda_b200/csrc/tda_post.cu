@@ -1,6 +1,7 @@
 // Device-side post-processing of the Link history: compaction to accepted records (see tda_post.h).
-// HBM-bound byte shuffling: coalesced accept-byte reads (lane = chain), one warp per chain for the
-// row gather (strided sector reads of the chain-fastest history, coalesced row-major writes).
+// HBM-bound byte shuffling: coalesced accept-byte reads (lane = chain); the row gather stages 32-chain slabs
+// through shared memory so that both its reads (chain-fastest history) and its writes (row-major rows) are
+// whole 128-byte lines.
 #include <string>
 
 #include "tda_post.h"
@@ -78,26 +79,47 @@ __global__ void __launch_bounds__(CB) add_blocks_kernel(long long* __restrict__ 
     if (c == 0) offsets[C] = block_off[nblocks];
 }
 
-// one warp per chain: the accept bytes of 32 records at a time -> ballot -> rows
+// One block = 32 consecutive chains.  Per record the [W][32] slab of the chain-fastest history is staged
+// through shared memory with coalesced loads (lane = chain, one 128-byte line per row) and the rows of the
+// accepted chains leave with coalesced stores: HBM traffic = one read of the dense records + one write of
+// the accepted rows, whatever the acceptance rate.
 template <typename R>
 __global__ void __launch_bounds__(256) gather_kernel(const R* __restrict__ src, int W, const uint8_t* __restrict__ acc, long long nrec, int C,
                                                      int Cs, int force_first, const long long* __restrict__ offsets, R* __restrict__ dst) {
-    const int lane = threadIdx.x & 31;
-    const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (c >= C) return;
-    long long row = offsets[c];
-    for (long long r0 = 0; r0 < nrec; r0 += 32) {
-        const long long r = r0 + lane;
-        const bool a = r < nrec && (acc[(size_t)r * Cs + c] != 0 || (force_first && r == 0));
-        unsigned m = __ballot_sync(0xffffffffu, a);
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const R* s = src + (size_t)(r0 + b) * W * Cs + c;
-            R* o = dst + (size_t)row * W;
-            for (int k = lane; k < W; k += 32) o[k] = s[(size_t)k * Cs];
-            row++;
+    __shared__ R tile[64][33];
+    __shared__ long long rowpos[32];
+    __shared__ unsigned s_mask;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32;
+    if (threadIdx.x < 32) rowpos[threadIdx.x] = (c0 + threadIdx.x < C) ? offsets[c0 + threadIdx.x] : 0;
+    __syncthreads();
+    for (long long r = 0; r < nrec; r++) {
+        if (warp == 0) {
+            const bool a = (c0 + lane < C) && (acc[(size_t)r * Cs + c0 + lane] != 0 || (force_first && r == 0));
+            const unsigned m = __ballot_sync(0xffffffffu, a);
+            if (lane == 0) s_mask = m;
         }
+        __syncthreads();
+        const unsigned mask = s_mask;
+        if (mask) {
+            for (int k0 = 0; k0 < W; k0 += 64) {
+                const int kw = W - k0 < 64 ? W - k0 : 64;
+                for (int k = warp; k < kw; k += 8) tile[k][lane] = src[((size_t)r * W + k0 + k) * Cs + c0 + lane];
+                __syncthreads();
+                unsigned m = mask;
+                for (int jj = 0; m; jj++) {
+                    const int c = __ffs(m) - 1;
+                    m &= m - 1;
+                    if ((jj & 7) == warp) {
+                        R* o = dst + (size_t)rowpos[c] * W + k0;
+                        for (int k = lane; k < kw; k += 32) o[k] = tile[k][c];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x < 32 && ((mask >> threadIdx.x) & 1u)) rowpos[threadIdx.x] += 1;
+        __syncthreads();
     }
 }
 
@@ -127,7 +149,7 @@ int compact_offsets(const uint8_t* acc, long long nrec, int C, int Cs, int force
 
 int compact_gather(const void* src, int esz, int W, const uint8_t* acc, long long nrec, int C, int Cs, int force_first,
                    const long long* offsets, void* dst, cudaStream_t st) {
-    const unsigned grid = (unsigned)((C + 7) / 8);
+    const unsigned grid = (unsigned)((C + 31) / 32);
     if (esz == 4)
         gather_kernel<float><<<grid, 256, 0, st>>>((const float*)src, W, acc, nrec, C, Cs, force_first, offsets, (float*)dst);
     else
