@@ -422,3 +422,95 @@ def test_tc16_coarse_chain_matches_reference_trajectory_until_near_tie():
         np.testing.assert_allclose(lk[c, :k], ref["like"][c, :k], rtol=2e-4, atol=2e-2)
         np.testing.assert_allclose(pr[c, :k], ref["prior"][c, :k], rtol=2e-4, atol=2e-2)
     eng.close()
+
+
+# ---- tcr: per-chain / adaptively scaled pCN steps, coarse chain through the whitened records -----------
+def _adaptive_cfg2(C, kernel, iters, period=20, store=None, seed=13):
+    from tinyda_b200 import lower_problem, CrankNicolson
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da()
+    spec = lower_problem(w["posteriors"], CrankNicolson(scaling=0.05, adaptive=True, period=period), 10)
+    theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1))
+    eng = Engine(spec, C, dtype="float32", seed=seed, store=[STORE_NONE, STORE_STATS] if store is None else store,
+                 capacity_iterations=iters)
+    if kernel:
+        eng.select_kernel(kernel)
+    eng.init(theta0)
+    return eng
+
+
+def test_tcr_runs_adaptive_pcn_and_agrees_with_the_generic_kernel():
+    """CrankNicolson(adaptive=True) -- what the reference's notebooks use -- selects the tensor-core kernel
+    automatically; step sizes follow proposal.py:228-245 with the window semantics of the generic kernel
+    (coarse decisions + one alignment entry per fine iteration)."""
+    C, iters = 512, 30                                  # 300 base steps: 15 adaptations with period 20
+    a = _adaptive_cfg2(C, None, iters)
+    assert a.kernel() == "tcr"
+    b = _adaptive_cfg2(C, "generic", iters)
+    b.set_z_round(True)
+    a.run(13); a.run(iters - 13)                        # a launch boundary inside an adaptation period
+    b.run(iters)
+    acc_a, acc_b = a.fetch(1, "accept"), b.fetch(1, "accept")
+    th_a, th_b = a.fetch(1, "theta"), b.fetch(1, "theta")
+    sa, sb = a.get("scaling"), b.get("scaling")
+    same = (acc_a == acc_b).all(axis=0) & (a.get("accept_counts")[0] == b.get("accept_counts")[0])
+    assert same.mean() > 0.5, same.mean()
+    # chains whose every decision agrees adapted identically and follow the same trajectory to float32 accuracy
+    np.testing.assert_allclose(sa[same], sb[same], rtol=1e-5)
+    scale = np.abs(th_b).max()
+    assert np.abs(th_a[:, :, same] - th_b[:, :, same]).max() < 2e-3 * scale
+    assert sa.std() > 0                                 # the steps moved away from the common start
+    assert np.array_equal(a.get("cursors"), b.get("cursors"))
+    a.close(); b.close()
+
+
+def test_tcr_per_chain_step_sizes():
+    """tda_set(TDA_G_SCALING): every chain its own pCN step; the kernel reads them per chain."""
+    C, iters = 512, 10
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da()
+    spec = lower_problem(w["posteriors"], w["proposal"], 10)
+    theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1))
+    steps = np.where(np.arange(C) % 2 == 0, 0.02, 0.11)
+    out = {}
+    for kern in ("tcr", "generic"):
+        eng = Engine(spec, C, dtype="float32", seed=3, store=[STORE_NONE, STORE_STATS], capacity_iterations=iters)
+        eng.select_kernel(kern)
+        if kern == "generic":
+            eng.set_z_round(True)
+        eng.init(theta0)
+        eng.set_scaling(steps)                          # after init: init restores the proposal's own step
+        eng.run(iters)
+        out[kern] = (eng.fetch(1, "accept"), eng.fetch(1, "theta"), eng.get("accept_counts"))
+        eng.close()
+    same = (out["tcr"][0] == out["generic"][0]).all(axis=0) & (out["tcr"][2][0] == out["generic"][2][0])
+    assert same.mean() > 0.8
+    scale = np.abs(out["generic"][1]).max()
+    assert np.abs(out["tcr"][1][:, :, same] - out["generic"][1][:, :, same]).max() < 1e-3 * scale
+    # smaller steps are accepted more often on the coarse level
+    cnt = out["tcr"][2][0]
+    assert cnt[0::2].mean() > 1.5 * cnt[1::2].mean()
+
+
+def test_tcr_coarse_chain_records_agree_with_the_generic_kernel():
+    """store_coarse_chain=True on the tcr kernel: coarse Links are recorded whitened and turned into
+    theta / log-prior / model output when first fetched."""
+    from tinyda_b200.engine import STORE_FULL
+    C, iters = 256, 6
+    a = _adaptive_cfg2(C, "tcr", iters, store=[STORE_FULL, STORE_FULL])
+    b = _adaptive_cfg2(C, "generic", iters, store=[STORE_FULL, STORE_FULL])
+    b.set_z_round(True)
+    a.run(iters); b.run(iters)
+    fa, fb = _link_fields(a, 0), _link_fields(b, 0)
+    same = (fa["accept"] == fb["accept"]).all(axis=0) & (a.fetch(1, "accept") == b.fetch(1, "accept")).all(axis=0)
+    assert same.mean() > 0.7
+    for k in ("theta", "output"):
+        scale = np.abs(fb[k]).max()
+        assert np.abs(fa[k][:, :, same] - fb[k][:, :, same]).max() < 1e-3 * scale, k
+    for k in ("prior", "like"):
+        np.testing.assert_allclose(fa[k][:, same], fb[k][:, same], rtol=2e-4, atol=0.05)
+    assert fa["theta"].shape[0] == iters * 10
+    a.close(); b.close()

@@ -64,7 +64,8 @@ constexpr int TR_OFF_Z = TR_OFF_RING + TR_NST * TR_CHUNK_BYTES;   // [tile 2][bu
 constexpr int TR_OFF_PART = TR_OFF_Z + 4 * TR_IMG;                // [buf 2][tile 2][half 2][val 2][128] f32
 constexpr int TR_OFF_U = TR_OFF_PART + 2 * 2 * 2 * 2 * 128 * 4;   // [buf 2][tile 2][128] f32
 constexpr int TR_OFF_PF = TR_OFF_U + 2 * 2 * 128 * 4;             // [tile 2][half 2][val 2][128] f32
-constexpr int TR_OFF_NY = TR_OFF_PF + 2 * 2 * 2 * 128 * 4;        // f32: [-y_c 128 | -(mu @ LP) 64 | -y_f mf]
+constexpr int TR_OFF_UB = TR_OFF_PF + 2 * 2 * 2 * 128 * 4;        // [tile 2][128] uint4: the chain's current Philox block of uniforms
+constexpr int TR_OFF_NY = TR_OFF_UB + 2 * 128 * 16;               // f32: [-y_c 128 | -(mu @ LP) 64 | -y_f mf]
 constexpr int TR_NY_FLOATS = TR_MAX_MC + TR_K + TR_MAX_MF;
 constexpr int TR_OFF_BARS = TR_OFF_NY + TR_NY_FLOATS * 4;
 constexpr size_t TR_SMEM_BYTES = TR_OFF_BARS + 512;
@@ -191,6 +192,7 @@ da_tcr_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ D
     float* s_u = reinterpret_cast<float*>(smem + TR_OFF_U);
     float* s_pf = reinterpret_cast<float*>(smem + TR_OFF_PF);
     const float* s_ny = reinterpret_cast<const float*>(smem + TR_OFF_NY);
+    uint4* s_ub = reinterpret_cast<uint4*>(smem + TR_OFF_UB);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TR_OFF_BARS);
     uint64_t* bar_res = bars;                       // resident operands landed
     uint64_t* bar_reqR = bars + 1;                  // [tile] rows -> MMA: split(w_current) stored, fine accumulators consumed
@@ -458,6 +460,23 @@ da_tcr_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ D
                 ca = sqrtf(1.0f - s * s);
                 cb = s * q.bz;
             }
+            // adaptive global scaling (proposal.py:228-245): the `accepted` window of the last `period` entries --
+            // coarse decisions and the alignment entry of every fine iteration -- as a ring
+            // in global memory, shared with the generic kernel; kept by the h == 0 thread of the chain
+            const bool adaptive = p.adaptive != 0;
+            int wsum = (adaptive && h == 0) ? __ldcg(p.win_sum + g) : 0;
+            long long wc = p.wcount + (long long)un.it0 * (J + 1);
+            int wpos = adaptive ? (int)(wc % p.period) : 0;
+            auto window_append = [&](int a) {
+                if (h == 0) {
+                    uint8_t* slot = p.win + (size_t)wpos * cs + g;
+                    const int old = (wc >= p.period) ? (int)__ldcg(slot) : 0;
+                    *slot = (uint8_t)a;
+                    wsum += a - old;
+                }
+                wc++;
+                wpos = (wpos + 1 == p.period) ? 0 : wpos + 1;
+            };
 
             auto store_A = [&]() {
                 uint32_t hi[16], lo[16];
@@ -467,9 +486,14 @@ da_tcr_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ D
                 tc::tmem_st16(tD + 32 + h * 16, lo);
                 tc::tmem_wait_st();
             };
+            // accept-test uniforms: one Philox block serves four draws (kept in shared memory, not in registers)
+            uint4* my_ub = s_ub + t * 128 + cl;
+            if (h == 0 && !inj && (ucur & 3)) *my_ub = philox_block(p.seed, gchain, STREAM_U, (unsigned long long)ucur >> 2);
             auto draw_u = [&]() -> float {
                 if (inj) return (live && ucur < p.ulen) ? p.us[(size_t)g * p.ulen + ucur] : 0.5f;
-                return philox_uniform<float>(p.seed, gchain, ucur);
+                const unsigned o = (unsigned)ucur & 3u;
+                if (o == 0) *my_ub = philox_block(p.seed, gchain, STREAM_U, (unsigned long long)ucur >> 2);
+                return u01<float>(reinterpret_cast<const uint32_t*>(my_ub)[o]);
             };
             auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
                 if (leader) tc::mbar_wait(bar, parity);
@@ -605,6 +629,39 @@ da_tcr_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ D
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(zfree + zb);            // normals consumed (shared-memory reads only)
                     if (acc) { like_c = like_p; acc_any = 1; nacc_c++; }
+                    // ---- coarse-level record (chain_coarse_i, sampler.py:421-436): whitened parameters, log-likelihood,
+                    // accept flag; theta = w T, Link.prior and Link.model_output are filled in when first fetched ----
+                    if (l0.store) {
+                        const long long r0 = p.rec[0] + (long long)it * J + j;
+                        if (r0 < l0.hist_cap) {
+                            if (l0.store & TDA_STORE_THETA) {
+                                float* dst = tr_opaque(l0.h_theta + (size_t)r0 * d * cs + off0);
+#pragma unroll
+                                for (int k = 0; k < TR_HK; k++)
+                                    if (k < nk) __stcs(dst + k * cs, w[k] * w_unscale);
+                            }
+                            if (h == 0) {
+                                if (l0.store & TDA_STORE_STATS) __stcs(l0.h_like + (size_t)r0 * cs + g, like_c);
+                                if (l0.store & TDA_STORE_ACCEPT) l0.h_acc[(size_t)r0 * cs + g] = (uint8_t)acc;
+                            }
+                        }
+                    }
+                    if (adaptive) {
+                        window_append(acc ? 1 : 0);
+                        const long long tnow = p.t_base + (long long)it * J + j + 1;       // proposal.t after this step
+                        if ((tnow % p.period) == 0) {
+                            if (h == 0) {
+                                const long long kk = tnow / p.period - 1;
+                                const float rate = (float)wsum / (float)p.period;
+                                const float s_old = __ldcg(p.scaling + g);
+                                p.scaling[g] = expf(logf(s_old) + powf(p.gamma, (float)(-(double)kk)) * (rate - p.alpha_star));
+                            }
+                            tc::named_bar_sync(1 + t, 256);          // the other half-thread of the chain reads the new step
+                            const float s_new = __ldcg(p.scaling + g);
+                            ca = sqrtf(1.0f - s_new * s_new);
+                            cb = s_new * q.bz;
+                        }
+                    }
                 }
                 // ---- fine level: w @ [T G_f^T | T LP | T] streamed in 64-column chunks ----
                 // the A operand overlays the z-product columns the OTHER half-thread of this chain may still be
@@ -680,19 +737,31 @@ da_tcr_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ D
                         float* s1 = tr_opaque(p.sum1 + off0);
                         float* s2 = tr_opaque(p.sum2 + off0);
 #pragma unroll
-                        for (int k = 0; k < TR_HK; k++) {
-                            if (k < nk) {
-                                const float prop = __uint_as_float(k < 16 ? v0[k & 15] : v1[k & 15]) * sc_t;
-                                float x;
-                                if (accf) { x = prop; th_state[k * cs] = x; }
-                                else x = __ldcg(th_state + k * cs);
-                                if (th_hist) th_hist[k * cs] = x;
-                                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s1 + k * cs), "f"(x) : "memory");
-                                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s2 + k * cs), "f"(x * x) : "memory");
+                        for (int k0 = 0; k0 < TR_HK; k0 += 8) {
+                            float x[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const int k = k0 + i;
+                                x[i] = 0.0f;
+                                if (k < nk) {
+                                    const float prop = __uint_as_float(k < 16 ? v0[k & 15] : v1[k & 15]) * sc_t;
+                                    x[i] = accf ? prop : __ldcg(th_state + k * cs);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const int k = k0 + i;
+                                if (k < nk) {
+                                    if (accf) th_state[k * cs] = x[i];
+                                    if (th_hist) th_hist[k * cs] = x[i];
+                                    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s1 + k * cs), "f"(x[i]) : "memory");
+                                    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s2 + k * cs), "f"(x[i] * x[i]) : "memory");
+                                }
                             }
                         }
                         if (accf) { like_f = like_fp; prior_f = prior_p; nacc_f++; }
                         like_cur = accf ? like_c : like_cs;
+                        if (adaptive) window_append(accf);           // the alignment entry (chain.py:391, :397)
                         if (rec_on && h == 0) {
                             if (l1.store & TDA_STORE_STATS) { l1.h_prior[(size_t)r * cs + g] = prior_f; l1.h_like[(size_t)r * cs + g] = like_f; }
                             if (l1.store & TDA_STORE_ACCEPT) l1.h_acc[(size_t)r * cs + g] = (uint8_t)accf;
@@ -735,6 +804,7 @@ da_tcr_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ D
                 l0.n_acc[g] = __ldcg(l0.n_acc + g) + nacc_c;
                 l1.n_acc[g] = __ldcg(l1.n_acc + g) + nacc_f;
                 p.ucur[g] = ucur;
+                if (adaptive) p.win_sum[g] = wsum;
             }
             if (q.nb > 1) {
                 __threadfence();
@@ -825,15 +895,16 @@ struct DaTcrImpl {
 };
 
 bool DaTcrState::eligible(const tda_config& c, const Params<float>& P) const {
-    if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.mtm_k || c.prop_kind != TDA_PROP_PCN || c.adaptive) return false;
+    if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.mtm_k || c.prop_kind != TDA_PROP_PCN) return false;
     if (c.d > TR_K || c.d < 16 || (c.d % 16) != 0) return false;
     for (int l = 0; l < 2; l++)
         if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind > TDA_LIK_DENSE) return false;
     if (c.level[0].m < 1 || c.level[0].m > TR_MAX_MC) return false;
     if (c.level[1].m < 1 || c.level[1].m > TR_MAX_MF) return false;
-    // the coarse chain is not recorded by this kernel (store_coarse_chain=False); Link.model_output of the
-    // fine level is rebuilt from the recorded parameters when first fetched
-    if (c.level[0].store) return false;
+    // Coarse Links are recorded as (whitened parameters, log-likelihood, accept flag); the engine turns the
+    // parameters into theta = w T and rebuilds Link.prior / Link.model_output from them when they are first
+    // fetched (EngineT::fill_lazy_history), so those fields need the parameters
+    if ((c.level[0].store & (TDA_STORE_STATS | TDA_STORE_OUTPUT)) && !(c.level[0].store & TDA_STORE_THETA)) return false;
     if ((c.level[1].store & TDA_STORE_OUTPUT) && !(c.level[1].store & TDA_STORE_THETA)) return false;
     if ((P.Cs % 256) != 0) return false;
     if (!(c.scaling > 0.0 && c.scaling < 1.0)) return false;
@@ -875,6 +946,7 @@ int DaTcrState::prepare(const Params<float>& P, const tda_config& c) {
     if (e != cudaSuccess) { err = std::string("tcr prepare: ") + cudaGetErrorString(e); return -2; }
     for (int i = 0; i < P.C; i++)
         if (!(sc[i] > 0.0 && sc[i] < 1.0)) { err = "tcr: pCN step outside (0, 1)"; return 1; }
+    if (c.adaptive && (!P.win || !P.win_sum)) { err = "tcr: adaptation window missing"; return 1; }
     const int ldD = P.ldD, ldc = P.lv[0].ldA, ldf = P.lv[1].ldA;
     // Diagonal and dense Gaussian likelihoods are folded into the operators (see tda_da_tc16.cuh):
     // -0.5 r^T prec r = -0.5 |L^T r|^2 with prec = L L^T

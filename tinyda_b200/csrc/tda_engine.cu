@@ -170,8 +170,8 @@ __global__ void init_theta_kernel(const double* __restrict__ src, int C, int d, 
 // the read-only cache at warp-uniform addresses, stores are coalesced (lane = chain).  Runs when the
 // fields are first fetched, i.e. next to a PCIe copy of the same records, never inside the sampling loop.
 template <typename R, int D>
-__global__ void __launch_bounds__(256) hist_fill_kernel(const R* __restrict__ theta, const R* __restrict__ W, int ldW, int ncol,
-                                                        const R* __restrict__ off, const R* __restrict__ mu, R* __restrict__ out,
+__global__ void __launch_bounds__(256) hist_fill_kernel(const R* theta, const R* __restrict__ W, int ldW, int ncol,
+                                                        const R* __restrict__ off, const R* __restrict__ mu, R* out,
                                                         int d, int Cs, int mode, R logconst) {
     const int cblocks = Cs / 256;
     const size_t r = blockIdx.x / cblocks;
@@ -278,6 +278,8 @@ struct EngineT : tda_engine {
     // records written by the fp16-split kernel whose derived fields (coarse Link.prior, Link.model_output)
     // have not been filled yet, per level; and: the levels' current model outputs lag behind theta
     long long lazy_lo[tda::MAXL] = {0, 0, 0, 0}, lazy_hi[tda::MAXL] = {0, 0, 0, 0};
+    // coarse records written by the tcr kernel hold WHITENED parameters until they are first needed
+    long long lazy_w_lo = 0, lazy_w_hi = 0;
     bool state_F_stale = false;
     bool burning = false;      // inside tda_engine_burn: nothing is recorded
     // quantities of interest: qoi = Q @ F(theta) + q0 per level.  Linear models: composed with the operator
@@ -779,6 +781,24 @@ struct EngineT : tda_engine {
     // kernel wrote since the last call
     int fill_lazy_history(cudaStream_t st) {
         CUDA_TRY(cudaSetDevice(device));
+        if (lazy_w_hi > lazy_w_lo && P.lv[0].h_theta) {
+            // theta = w @ T, in place: a thread reads its (record, chain) column before it writes it
+            const long long hi = lazy_w_hi < P.lv[0].hist_cap ? lazy_w_hi : P.lv[0].hist_cap;
+            if (hi > lazy_w_lo) {
+                if (P.d > 64) return fail(-1, "history fill: d > 64");
+                R* th = P.lv[0].h_theta + (size_t)lazy_w_lo * P.d * Cs;
+                const long long per = Cs / 256, nrec = hi - lazy_w_lo;
+                for (long long r0 = 0; r0 < nrec;) {
+                    const long long n = nrec - r0 < (1 << 20) ? nrec - r0 : (1 << 20);
+                    hist_fill_kernel<R, 64><<<(unsigned)(n * per), 256, 0, st>>>(th + (size_t)r0 * P.d * Cs, P.T, P.ldD, P.d, (const R*)nullptr,
+                                                                              (const R*)nullptr, th + (size_t)r0 * P.d * Cs, P.d, Cs, 0, (R)0);
+                    g_launches++;
+                    r0 += n;
+                }
+                CUDA_TRY(cudaGetLastError());
+            }
+        }
+        lazy_w_lo = lazy_w_hi = 0;
         for (int l = 0; l < P.L; l++) {
             const tda::LevelP<R>& v = P.lv[l];
             const long long lo = lazy_lo[l], hi = lazy_hi[l] < v.hist_cap ? lazy_hi[l] : v.hist_cap;
@@ -813,6 +833,7 @@ struct EngineT : tda_engine {
         P.t_base = 0; P.wcount = 0;
         if (tda::is_dream(P.prop_kind)) dream_slots = cfg.dream_M0;
         for (int l = 0; l < tda::MAXL; l++) { P.rec[l] = 0; P.lvl_steps[l] = 0; lazy_lo[l] = lazy_hi[l] = 0; }
+        lazy_w_lo = lazy_w_hi = 0;
         state_F_stale = false;
         tcr.invalidate();
         tcr_unfit = false;
@@ -833,8 +854,12 @@ struct EngineT : tda_engine {
     // 4 register-resident single-level
     int resolved_kernel() const {
         if (kernel_choice >= 1 && kernel_choice <= 5) return kernel_choice;
-        if (tcr_eligible()) return 5;
+        // fixed common step size: the fp16-split kernel with the step folded into its operators; per-chain /
+        // adaptively scaled steps: the whitened-state kernel (TDA_PREFER_TCR: always the latter when it can)
+        static const bool prefer_tcr = getenv("TDA_PREFER_TCR") != nullptr;
+        if (prefer_tcr && tcr_eligible()) return 5;
         if (tc16_eligible()) return 3;
+        if (tcr_eligible()) return 5;
         if (tc_eligible()) return 2;
         if (reg_eligible()) return 4;
         return 1;
@@ -967,6 +992,10 @@ struct EngineT : tda_engine {
         long long w = steps[0];
         for (int l = 1; l < L; l++) w += steps[l];
         P.wcount += (L == 1) ? steps[0] : w;
+        if (which == 5 && !burning && (cfg.level[0].store & TDA_STORE_THETA)) {
+            if (lazy_w_lo == lazy_w_hi) lazy_w_lo = P.rec[0];
+            lazy_w_hi = P.rec[0] + steps[0];
+        }
         if (which == 3 || which == 5) {
             if (!burning)
                 for (int l = 0; l < L; l++) {
@@ -982,6 +1011,7 @@ struct EngineT : tda_engine {
 
     int history_reset() override {
         for (int l = 0; l < P.L; l++) { P.rec[l] = 0; lazy_lo[l] = lazy_hi[l] = 0; }
+        lazy_w_lo = lazy_w_hi = 0;
         return 0;
     }
 
@@ -1056,7 +1086,7 @@ struct EngineT : tda_engine {
         if (level < 0 || level >= P.L) return fail(-1, "fetch: bad level");
         const tda::LevelP<R>& v = P.lv[level];
         if (rec0 < 0 || nrec < 0 || rec0 + nrec > v.hist_cap) return fail(-1, "fetch: record range outside the history buffer");
-        if (field == TDA_F_PRIOR || field == TDA_F_OUTPUT) {
+        if (field == TDA_F_PRIOR || field == TDA_F_OUTPUT || (field == TDA_F_THETA && lazy_w_hi > lazy_w_lo)) {
             int r = fill_lazy_history(st);
             if (r) return r;
         }
