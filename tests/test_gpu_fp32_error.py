@@ -26,7 +26,7 @@ MAX_FLIP_RATE = 2e-3       # flipped near-ties per accept/reject decision
 def _run(g, kernel, dtype="float32"):
     from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
     C, iters = g["theta0"].shape[0], g["iterations"]
-    coarse = True
+    coarse = kernel != "tc"             # the 3xTF32 kernel does not record the coarse chain
     eng = Engine(g["spec"], C, dtype=dtype, rng="injected", streams=(g["z"], g["u"]),
                  store=[STORE_STATS if coarse else STORE_NONE, STORE_STATS], capacity_iterations=iters)
     eng.select_kernel(kernel)

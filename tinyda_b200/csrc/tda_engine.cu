@@ -93,6 +93,42 @@ struct DevPool {
 };
 DevPool g_pool;
 
+// small page-locked scalars, copy streams and events are recycled too (cudaHostAlloc / cudaFreeHost /
+// cudaStreamCreate cost a millisecond or more each and synchronise)
+struct SmallPool {
+    std::mutex mu;
+    std::vector<long long*> pinned;
+    std::vector<std::pair<int, cudaStream_t>> streams;
+    std::vector<std::pair<int, cudaEvent_t>> events;
+    long long* get_pinned() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pinned.empty()) { long long* p = pinned.back(); pinned.pop_back(); return p; }
+        long long* p = nullptr;
+        if (cudaHostAlloc((void**)&p, 64, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+        return p;
+    }
+    void put_pinned(long long* p) { std::lock_guard<std::mutex> lk(mu); pinned.push_back(p); }
+    cudaStream_t get_stream(int dev) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < streams.size(); i++)
+            if (streams[i].first == dev) { cudaStream_t s = streams[i].second; streams.erase(streams.begin() + i); return s; }
+        cudaStream_t s = nullptr;
+        cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        return s;
+    }
+    void put_stream(int dev, cudaStream_t s) { std::lock_guard<std::mutex> lk(mu); streams.push_back({dev, s}); }
+    cudaEvent_t get_event(int dev) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < events.size(); i++)
+            if (events[i].first == dev) { cudaEvent_t e = events[i].second; events.erase(events.begin() + i); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        return e;
+    }
+    void put_event(int dev, cudaEvent_t e) { std::lock_guard<std::mutex> lk(mu); events.push_back({dev, e}); }
+};
+SmallPool g_small;
+
 }  // namespace
 
 struct tda_engine {
@@ -296,7 +332,7 @@ struct EngineT : tda_engine {
         long long* offsets = nullptr;     // [C + 1]
         long long* scratch = nullptr;
         uint8_t* flags = nullptr;         // [nrec][Cs]
-        size_t flags_cap = 0;
+        size_t flags_cap = 0, offsets_cap = 0, scratch_cap = 0;
         void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // theta, prior, like, output, qoi rows
         size_t cap[5] = {0, 0, 0, 0, 0};
         long long* total_pinned = nullptr;
@@ -310,15 +346,15 @@ struct EngineT : tda_engine {
         cudaDeviceSynchronize();           // nothing of this engine is in flight when its blocks go back to the pool
         for (size_t i = 0; i < allocs.size(); i++) g_pool.release(allocs[i], alloc_cls[i], device);
         for (auto& s : cslot) {
-            if (s.offsets) cudaFree(s.offsets);
-            if (s.scratch) cudaFree(s.scratch);
+            if (s.offsets) g_pool.release(s.offsets, s.offsets_cap, device);
+            if (s.scratch) g_pool.release(s.scratch, s.scratch_cap, device);
             if (s.flags) g_pool.release(s.flags, s.flags_cap, device);
             for (int f = 0; f < 5; f++) if (s.buf[f]) g_pool.release(s.buf[f], s.cap[f], device);
-            if (s.total_pinned) cudaFreeHost(s.total_pinned);
-            if (s.ready) cudaEventDestroy(s.ready);
-            if (s.copied) cudaEventDestroy(s.copied);
+            if (s.total_pinned) g_small.put_pinned(s.total_pinned);
+            if (s.ready) g_small.put_event(device, s.ready);
+            if (s.copied) g_small.put_event(device, s.copied);
         }
-        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (copy_stream) g_small.put_stream(device, copy_stream);
         tc.destroy();
         tc16.destroy();
         tcr.destroy();
@@ -1159,12 +1195,14 @@ struct EngineT : tda_engine {
         if ((fields & TDA_STORE_OUTPUT) && !v.h_F) return fail(-1, "compact: model outputs were not stored");
         if ((fields & TDA_STORE_QOI) && !nq[level]) return fail(-1, "compact: the level's model has no quantity of interest");
         CompactSlot& s = cslot[slot];
-        if (!copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-        if (!s.ready) { CUDA_TRY(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)); }
-        if (!s.total_pinned) CUDA_TRY(cudaHostAlloc((void**)&s.total_pinned, sizeof(long long), cudaHostAllocPortable));
+        if (!copy_stream) copy_stream = g_small.get_stream(device);
+        if (!s.ready) { s.ready = g_small.get_event(device); s.copied = g_small.get_event(device); }
+        if (!s.total_pinned) s.total_pinned = g_small.get_pinned();
+        if (!copy_stream || !s.ready || !s.copied || !s.total_pinned) return fail(-2, "compact: could not create the copy stream / events / pinned scalar");
         if (!s.offsets) {
-            CUDA_TRY(cudaMalloc((void**)&s.offsets, ((size_t)P.C + 1) * sizeof(long long)));
-            CUDA_TRY(cudaMalloc((void**)&s.scratch, ((size_t)(P.C + 255) / 256 + 2) * sizeof(long long)));
+            int r0 = grow(&s.offsets, &s.offsets_cap, ((size_t)P.C + 1) * sizeof(long long));
+            if (!r0) r0 = grow(&s.scratch, &s.scratch_cap, ((size_t)(P.C + 255) / 256 + 2) * sizeof(long long));
+            if (r0) return r0;
         }
         // copies of the slot's previous contents must have left the device buffers
         if (s.has_copies) CUDA_TRY(cudaStreamWaitEvent(st, s.copied, 0));
@@ -1191,9 +1229,16 @@ struct EngineT : tda_engine {
             r = qoi_fill(level, rec0, nrec, qtmp, st);
             srcs[4] = qtmp;
         }
+        // the log-densities ride with the parameter rows (one pass over the records) when both are wanted
+        const bool fused_stats = want[0] && want[1];
         for (int f = 0; f < 5 && !r; f++)
             if (want[f]) {
-                r = tp::compact_gather(srcs[f], (int)sizeof(R), widths[f], acc, nrec, P.C, Cs, first_is_full, s.offsets, s.buf[f], st);
+                if (fused_stats && (f == 1 || f == 2)) continue;
+                if (f == 0 && fused_stats)
+                    r = tp::compact_gather(srcs[0], (int)sizeof(R), widths[0], acc, nrec, P.C, Cs, first_is_full, s.offsets, s.buf[0], st,
+                                           srcs[1], srcs[2], s.buf[1], s.buf[2]);
+                else
+                    r = tp::compact_gather(srcs[f], (int)sizeof(R), widths[f], acc, nrec, P.C, Cs, first_is_full, s.offsets, s.buf[f], st);
                 g_launches++;
             }
         if (qtmp) cudaFreeAsync(qtmp, st);

@@ -83,10 +83,14 @@ __global__ void __launch_bounds__(CB) add_blocks_kernel(long long* __restrict__ 
 // through shared memory with coalesced loads (lane = chain, one 128-byte line per row) and the rows of the
 // accepted chains leave with coalesced stores: HBM traffic = one read of the dense records + one write of
 // the accepted rows, whatever the acceptance rate.
+// prior / like (optional): the records' log-densities travel with the rows in the same pass
 template <typename R>
 __global__ void __launch_bounds__(256) gather_kernel(const R* __restrict__ src, int W, const uint8_t* __restrict__ acc, long long nrec, int C,
-                                                     int Cs, int force_first, const long long* __restrict__ offsets, R* __restrict__ dst) {
+                                                     int Cs, int force_first, const long long* __restrict__ offsets, R* __restrict__ dst,
+                                                     const R* __restrict__ prior, const R* __restrict__ like, R* __restrict__ dst_prior,
+                                                     R* __restrict__ dst_like) {
     __shared__ R tile[64][33];
+    __shared__ R tile_s[2][32];
     __shared__ long long rowpos[32];
     __shared__ unsigned s_mask;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -101,6 +105,10 @@ __global__ void __launch_bounds__(256) gather_kernel(const R* __restrict__ src, 
         }
         __syncthreads();
         const unsigned mask = s_mask;
+        if (mask && prior) {
+            if (warp == 1) tile_s[0][lane] = prior[(size_t)r * Cs + c0 + lane];
+            if (warp == 2) tile_s[1][lane] = like[(size_t)r * Cs + c0 + lane];
+        }
         if (mask) {
             for (int k0 = 0; k0 < W; k0 += 64) {
                 const int kw = W - k0 < 64 ? W - k0 : 64;
@@ -113,6 +121,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const R* __restrict__ src, 
                     if ((jj & 7) == warp) {
                         R* o = dst + (size_t)rowpos[c] * W + k0;
                         for (int k = lane; k < kw; k += 32) o[k] = tile[k][c];
+                        if (prior && k0 == 0 && lane < 2) (lane ? dst_like : dst_prior)[rowpos[c]] = tile_s[lane][c];
                     }
                 }
                 __syncthreads();
@@ -148,12 +157,15 @@ int compact_offsets(const uint8_t* acc, long long nrec, int C, int Cs, int force
 }
 
 int compact_gather(const void* src, int esz, int W, const uint8_t* acc, long long nrec, int C, int Cs, int force_first,
-                   const long long* offsets, void* dst, cudaStream_t st) {
+                   const long long* offsets, void* dst, cudaStream_t st, const void* prior, const void* like, void* dst_prior,
+                   void* dst_like) {
     const unsigned grid = (unsigned)((C + 31) / 32);
     if (esz == 4)
-        gather_kernel<float><<<grid, 256, 0, st>>>((const float*)src, W, acc, nrec, C, Cs, force_first, offsets, (float*)dst);
+        gather_kernel<float><<<grid, 256, 0, st>>>((const float*)src, W, acc, nrec, C, Cs, force_first, offsets, (float*)dst,
+                                                   (const float*)prior, (const float*)like, (float*)dst_prior, (float*)dst_like);
     else
-        gather_kernel<double><<<grid, 256, 0, st>>>((const double*)src, W, acc, nrec, C, Cs, force_first, offsets, (double*)dst);
+        gather_kernel<double><<<grid, 256, 0, st>>>((const double*)src, W, acc, nrec, C, Cs, force_first, offsets, (double*)dst,
+                                                    (const double*)prior, (const double*)like, (double*)dst_prior, (double*)dst_like);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : pfail("compact_gather", e);
 }

@@ -23,8 +23,10 @@ int compact_offsets(const uint8_t* acc, long long nrec, int C, int Cs, int force
 
 // dst[offsets[c] + j][0..W) = src[r_j][0..W)[c] for the j-th accepted record r_j of chain c
 // (src: [nrec][W][Cs], chain fastest; dst row-major [n_rows][W]); esz = 4 (float) or 8 (double)
+// prior / like != nullptr: the records' log-densities ([nrec][Cs]) are gathered in the same pass into dst_prior / dst_like
 int compact_gather(const void* src, int esz, int W, const uint8_t* acc, long long nrec, int C, int Cs, int force_first,
-                   const long long* offsets, void* dst, cudaStream_t st);
+                   const long long* offsets, void* dst, cudaStream_t st, const void* prior = nullptr, const void* like = nullptr,
+                   void* dst_prior = nullptr, void* dst_like = nullptr);
 
 // accept bytes with the forced first record made explicit: dst[r][c] (dense [nrec][Cs])
 int compact_flags(const uint8_t* acc, long long nrec, int C, int Cs, int force_first, uint8_t* dst, cudaStream_t st);

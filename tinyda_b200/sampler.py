@@ -8,6 +8,9 @@ arguments select engine options (dtype, RNG mode, storage); the positional / ref
 keywords keep their meaning.  Under ``torch.distributed`` (one process per GPU) ``n_chains``
 is the global count and every rank samples its contiguous shard.
 """
+import os
+import sys
+import time
 import warnings
 
 import numpy as np
@@ -95,6 +98,13 @@ def sample(
     (chain.py:116, :434) -- and copied to pinned host memory while the next block runs; the result dict
     expands a chain to a ``LinkSequence`` when its key is first read.
     """
+    _prof = [] if os.environ.get("TDA_PROFILE") else None
+    _t0 = time.perf_counter()
+
+    def _lap(name):
+        if _prof is not None:
+            _prof.append((name, time.perf_counter()))
+
     if subsampling_rate is not None:                                   # sampler.py:113-115
         warnings.warn(" subsampling_rate has been deprecated in favour of subchain_length.")
         subchain_length = subsampling_rate
@@ -168,6 +178,7 @@ def sample(
         host_rng = np.random.default_rng([int(seed), 7])
         theta0 = np.atleast_2d(posteriors[0].prior.rvs(n_chains, random_state=host_rng)).reshape(n_chains, -1)[lo:hi]
 
+    _lap("arguments + initial parameters")
     spec = lower_problem(posteriors, proposal, subchain_length if n_levels > 1 else None,
                          adaptive_error_model if n_levels > 1 else None,
                          randomize_subchain_length if n_levels == 2 else False)
@@ -216,8 +227,10 @@ def sample(
                               "device memory: pass a smaller chunk_iterations, store_model_output=False and/or "
                               "store_coarse_chain=False" % (chunk_iterations, n_local)) from None
         raise
+    _lap("lowering + engine construction")
     print("Sampling {} chains in lock-step on GPU {}".format(n_chains, device))
     eng.init(theta0)
+    _lap("init (H2D + initial Links, enqueue)")
 
     top = n_levels - 1
     n_qoi = [int(lv["model"].get("n_qoi", 0)) for lv in spec["levels"]]
@@ -251,10 +264,12 @@ def sample(
         block += 1
         if done >= iterations:
             break
+    _lap("blocks enqueued (run + compaction + collect of the previous block)")
     if pending is not None:
         hist.append(eng.compact_collect(pending))
     eng.compact_sync()
     eng.sync()
+    _lap("last block: collect + sync")
 
     # result dict, sampler.py:305-309, :406-439, :510-547
     if n_levels == 1:
@@ -284,4 +299,12 @@ def sample(
     if return_engine:
         return result, eng
     eng.close()
+    _lap("result dict + engine close")
+    if _prof is not None:
+        prev = _t0
+        for name, t in _prof:
+            sys.stderr.write("[tda.sample] %-70s %8.2f ms\n" % (name, (t - prev) * 1e3))
+            prev = t
+        sys.stderr.write("[tda.sample] %-70s %8.2f ms (%d blocks, %d compact rows)\n"
+                         % ("total", (prev - _t0) * 1e3, len(hist.chunks), hist.n_rows()))
     return result
