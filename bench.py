@@ -231,6 +231,48 @@ def sharded_self_check(rank, world, local_rank):
     return ok
 
 
+def strong_scaling_arm(args, spec, w, rank, world, local_rank, dtype, stream, flush, barrier):
+    """north_star's own multi-GPU configuration: 65536 chains IN TOTAL (the reference's n_chains is a total,
+    sampler.py:21-34), i.e. 65536 / N chains per GPU -- strong scaling.  Device-timed like `value`."""
+    import torch
+    import torch.distributed as dist
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    total = N_CHAINS_PER_GPU
+    Cs = total // world
+    iters = args.iters if args.iters is not None else ITERS_PER_STEP
+    theta0 = w["prior"].rvs(Cs, random_state=np.random.default_rng(2000 + rank)).astype(np.float64)
+    eng = Engine(spec, Cs, dtype=dtype, rng="philox", seed=2024, store=[STORE_NONE, STORE_STATS], capacity_iterations=iters,
+                 device=local_rank, chain_offset=rank * Cs, n_chains_global=total, stream=stream)
+    if args.kernel != "auto":
+        eng.select_kernel(args.kernel)
+    eng.init(theta0)
+    eng.run(300 if not args.quick else 10, record=False)
+    for _ in range(args.warmup):
+        eng.history_reset()
+        eng.run(iters)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        eng.history_reset()
+        eng.run(iters)
+        ev[k][1].record()
+    barrier()
+    ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    kern = eng.kernel()
+    eng.close()
+    return {"value": float(total) * iters * args.steps / (ms * 1e-3), "unit": UNIT, "scaling": "strong", "chains_total": total,
+            "chains_per_gpu": Cs, "ms_per_step": ms / args.steps, "kernel": kern,
+            "tiles_per_gpu": (Cs + 127) // 128,
+            "note": "%d chains per GPU = %d tiles of 128 chains on 148 SMs; below 74 tile pairs every CTA advances a single tile"
+                    % (Cs, (Cs + 127) // 128)}
+
+
 def run_ours(args):
     import torch
     from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE, launch_count
@@ -390,6 +432,7 @@ def run_ours(args):
     h2d = C * d * 8
     d2h = d2h_seen[0]
     checks = sharded_self_check(rank, world, local_rank) if world > 1 else None
+    strong = strong_scaling_arm(args, spec, w, rank, world, local_rank, dtype, stream, flush, barrier) if world > 1 else None
 
     kernel_used = args.kernel if args.kernel != "auto" else ("tc16" if dtype == "float32" else "generic")
     ess = None
@@ -473,6 +516,8 @@ def run_ours(args):
         }
         if checks is not None:
             out["checks"] = checks
+        if strong is not None:
+            out["strong"] = strong
         if coarse_hist:
             hb = 265 + J0 * 261
             out["link_writeout"] = {"bytes_per_transition": hb, "achieved_gbs": per_gpu_rate * hb / 1e9,

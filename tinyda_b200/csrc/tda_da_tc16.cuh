@@ -90,7 +90,9 @@ struct DaTc16Params {
     float cxi;                // beta * 2^s_theta / 2^(s_z + s_T): scaled-theta increment per unit of D_xi
     float sc_c, sc_f, sc_p;   // accumulator -> model output: 2^-(s_theta + s_G), 2^-(s_theta + s_Gf), 2^-(s_theta + s_LP)
     float th_scale, th_unscale;
-    int n_pairs;
+    int n_pairs;              // units per block of iterations: tile pairs, or single tiles when `solo`
+    int solo;                 // fewer tile pairs than half the SMs: every CTA advances ONE 128-chain tile (the warps of
+                              // the second tile idle), so that twice as many SMs work (strong scaling)
     int ib, nb;               // work units: iterations per block, blocks per launch (unit = tile pair x block)
     int* progress;            // [n_pairs] tile completions of this launch (2 per finished block)
     long long* dbg;           // optional timeline probe (tools/tc16_timeline.py): [role 4][256] clock64 stamps of CTA 0
@@ -396,7 +398,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             tc::mbar_init(bar_zfull + i, 4);
             tc::mbar_init(bar_zfree + i, 1);
         }
-        for (int s = 0; s < T16_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 2); }
+        for (int s = 0; s < T16_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, q.solo ? 1 : 2); }
         tc::fence_mbar_init();
     }
     // d < 64 (multiples of 16): the operators are zero-padded to 64 rows on the host and the normals'
@@ -415,6 +417,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     const int J = q.J, mc = q.mc, NCH = q.n_chunks;
     const int iters = (int)p.iterations;          // per launch; checked on the host
     const bool inj = p.rng_mode == TDA_RNG_INJECTED;
+    const bool solo = q.solo != 0;
 
     if (warp >= T16_RNG_WARP0 && warp < T16_RNG_WARP0 + T16_RNG_WARPS) {
         // =====================================================================================
@@ -428,8 +431,8 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         uint64_t* zfree = bar_zfree + t * 2;
         unsigned n = 0;                                    // coarse steps produced
         T16Unit un;
-        for (int uk = 0; t16_unit(q, iters, uk, un); uk++) {
-            const int g = un.pair * 256 + t * 128 + row;
+        for (int uk = 0; !(solo && t == 1) && t16_unit(q, iters, uk, un); uk++) {
+            const int g = solo ? un.pair * 128 + row : un.pair * 256 + t * 128 + row;
             const long long gchain = p.chain_offset + g;
             const bool live = g < p.C;
             long long tb = p.t_base + (long long)un.it0 * J;
@@ -499,6 +502,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             // ===== MMA issuer of tile t: the whole warp runs the (uniform) control flow so that
             // descriptors live in uniform registers; one elected lane issues =====
             const int t = warp - T16_MMA_WARP0;
+            if (!(solo && t == 1)) {
             tc::mbar_wait(bar_res, 0);
             const uint32_t tA = tbase + t * 256, tD = tA + 64;
             const uint32_t sG_hi = tc::smem_u32(sG), sG_lo = sG_hi + T16_IMG;
@@ -577,6 +581,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     __syncwarp();
                 }
             }
+            }
         }
         __syncwarp();
     } else {
@@ -617,15 +622,15 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             tc::named_bar_sync(3 + t, 256);
             tc::fence_after_sync();
         };
-        tc::mbar_wait(bar_res, 0);                     // the data vector arrives with the resident operands
+        if (!(solo && t == 1)) tc::mbar_wait(bar_res, 0);   // the data vector arrives with the resident operands
 
         T16Unit un;
-        for (int uk = 0; t16_unit(q, iters, uk, un); uk++) {
+        for (int uk = 0; !(solo && t == 1) && t16_unit(q, iters, uk, un); uk++) {
             const int pair = un.pair;
-            const int g = pair * 256 + t * 128 + cl;                   // chain slot (padded arrays)
+            const int g = solo ? pair * 128 + cl : pair * 256 + t * 128 + cl;     // chain slot (padded arrays)
             if (un.blk > 0) {
                 // the previous block of this pair ran on another SM: wait for both of its tiles
-                if (leader) while (t16_ld_acquire(q.progress + pair) < 2 * un.blk) __nanosleep(200);
+                if (leader) while (t16_ld_acquire(q.progress + pair) < (solo ? 1 : 2) * un.blk) __nanosleep(200);
                 tc::named_bar_sync(3 + t, 256);
             }
             const long long gchain = p.chain_offset + g;
@@ -1143,6 +1148,8 @@ struct DaTc16State<float> {
         if (!prepared) { int r = prepare(P, c); if (r) return r; }
         cudaError_t e = cudaSuccess;
         q.n_pairs = P.Cs / 256;
+        q.solo = 0;
+        if (2 * q.n_pairs <= sm_count && !getenv("TDA_TC16_NO_SOLO")) { q.solo = 1; q.n_pairs = P.Cs / 128; }
         q.dbg = dDbg;
         const int grid = q.n_pairs < sm_count ? q.n_pairs : sm_count;
         // iteration blocks: the smallest block count (<= 16) whose round-robin deal of the
