@@ -252,6 +252,18 @@ int tda_compact_rows(tda_engine *e, int slot, int64_t *n_rows);
 int tda_compact_fetch(tda_engine *e, int slot, int field, void *host_dst, size_t dst_bytes, size_t *bytes);
 int tda_compact_sync(tda_engine *e);
 
+/* Rank-normalised split R-hat / bulk ESS (Vehtari et al. 2021: what ArviZ computes on the reference's
+ * to_inference_data output, diagnostics.py:6-69) of a level's recorded parameters [rec0, rec0+nrec), computed
+ * ON THE DEVICE -- the history does not cross PCIe.  For each of the d parameters the chains are split in
+ * halves (n_half = nrec / 2), every value is ranked (average ranks for ties) and turned into a normal score, and
+ * the plain sums the multi-chain estimators need are returned (so ranks of a multi-GPU job can all-reduce them):
+ *   sums[k][0 .. n_lag)      sum over the 2 n_chains split chains of the biased autocovariance at lag t
+ *   sums[k][n_lag + 0..3]    sum of split-chain means, sum of their squares, number of split chains, n_half
+ *   folded[k][0..3]          the same (lag 0 only) for the normal scores of |x - median|
+ * n_lag <= 0 or > n_half means n_half.  sums: float64 [d][n_lag + 4], folded: float64 [d][4]. */
+int tda_ess_sums(tda_engine *e, int level, int64_t rec0, int64_t nrec, int n_lag, double *sums, double *folded,
+                 void *cuda_stream);
+
 /* Device blocks of destroyed engines are kept in a process-wide pool and reused by the next engine (cudaMalloc /
  * cudaFree of multi-GB history buffers cost more than a short run); this returns them to the driver. */
 int tda_pool_trim(void);

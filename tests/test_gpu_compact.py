@@ -138,3 +138,25 @@ def test_link_qoi_is_the_models_second_return_value(case):
     res0 = tda.sample(tda.Posterior(prior, tda.GaussianLogLike(np.zeros(1), np.eye(1)), tda.LinearModel(np.ones((1, prior.mean.size)))),
                       tda.GaussianRandomWalk(np.eye(prior.mean.size)), 5, seed=1)
     assert res0["chain_0"][2].qoi is None
+
+
+@pytest.mark.parametrize("dtype,C,iters", [("float32", 256, 300), ("float64", 97, 121)])
+def test_device_ess_and_rhat_match_the_host_estimators(dtype, C, iters):
+    """tda_ess_sums (device: sort, average ranks, normal scores, all-lag autocovariance sums) against the
+    NumPy estimators (diagnostics.ess_bulk / rhat) on the fetched history of the same run."""
+    import tinyda_b200 as tda
+    from tinyda_b200.diagnostics import ess_rhat_from_sums
+    eng, w, spec = _cfg2(C, iters, dtype=dtype, kernel=None if dtype == "float32" else "generic")
+    eng.run(iters)
+    sums, folded = eng.ess_sums(1, 1, iters)                    # skip the initial link
+    ess, rh = ess_rhat_from_sums(sums, folded)
+    th = np.transpose(eng.fetch(1, "theta", 1, iters), (2, 0, 1)).astype(np.float32 if dtype == "float32" else np.float64)
+    for k in (0, 5, 63):
+        xk = th[:, :, k].astype(np.float32).astype(np.float64)  # the device ranks float32 keys
+        assert abs(ess[k] / tda.ess_bulk(xk) - 1) < 5e-3, (k, ess[k], tda.ess_bulk(xk))
+        assert abs(rh[k] / tda.rhat(xk) - 1) < 2e-3, (k, rh[k], tda.rhat(xk))
+    # a lag window that cuts positive autocorrelation mass off over-estimates the ESS (the default is all lags)
+    s2, f2 = eng.ess_sums(1, 1, iters, n_lag=48)
+    ess2, _ = ess_rhat_from_sums(s2, f2)
+    assert np.all(ess2 > 0.95 * ess)
+    eng.close()

@@ -353,3 +353,38 @@ def test_models_return_output_and_qoi_like_the_reference_protocol():
     low = m.lower()
     assert low["n_qoi"] == 2 and low["qoi_Q"].shape == (2, 4)
     assert tda.LinearModel(G).lower()["n_qoi"] == 0 and isinstance(tda.LinearModel(G)(np.zeros(3)), np.ndarray)
+
+
+def _ess_sums_numpy(x, n_lag=None):
+    """NumPy statement of tda_ess_sums for one parameter: x [n_chains, n_draws] -> (sums, folded)."""
+    from tinyda_b200.diagnostics import _split, _rank_normalise, _autocov
+    def sums_of(z, n_lag):
+        m, n = z.shape
+        ac = _autocov(z).sum(axis=0)[:n_lag]
+        means = z.mean(axis=1)
+        return np.concatenate([ac, [means.sum(), (means ** 2).sum(), m, n]])
+    xs = _split(np.asarray(x, dtype=np.float64))
+    n_half = xs.shape[1]
+    n_lag = n_half if n_lag is None else n_lag
+    s = sums_of(_rank_normalise(xs), n_lag)
+    f = sums_of(_rank_normalise(np.abs(xs - np.median(xs))), 1)[[0, 1, 2, 3]]
+    return s, f
+
+
+def test_ess_and_rhat_from_sums_equal_the_array_estimators():
+    """diagnostics.ess_rhat_from_sums (fed by the device kernels) against ess_bulk / rhat on host arrays."""
+    import tinyda_b200 as tda
+    from tinyda_b200.diagnostics import ess_rhat_from_sums
+    rng = np.random.default_rng(3)
+    m, n, rho = 16, 400, 0.8
+    x = np.zeros((m, n))
+    for t in range(1, n):
+        x[:, t] = rho * x[:, t - 1] + np.sqrt(1 - rho ** 2) * rng.standard_normal(m)
+    x[:, 100:140] = x[:, [100]]                      # a stretch of rejections: ties
+    s, f = _ess_sums_numpy(x)
+    ess, rh = ess_rhat_from_sums(s[None, :], f[None, :])
+    assert abs(ess[0] / tda.ess_bulk(x) - 1) < 1e-9 and abs(rh[0] / tda.rhat(x) - 1) < 1e-9
+    # truncated lags: same answer once the window covers the positive part of the autocorrelation
+    s2, f2 = _ess_sums_numpy(x, n_lag=120)
+    ess2, _ = ess_rhat_from_sums(s2[None, :], f2[None, :])
+    assert abs(ess2[0] / ess[0] - 1) < 0.05

@@ -140,6 +140,7 @@ struct tda_engine {
     virtual int compact_rows(int slot, long long* n_rows) = 0;
     virtual int compact_fetch(int slot, int field, void* dst, size_t dst_bytes, size_t* bytes) = 0;
     virtual int compact_sync() = 0;
+    virtual int ess_sums(int level, long long rec0, long long nrec, int n_lag, double* sums, double* folded, cudaStream_t st) = 0;
     virtual int fetch(int level, int field, long long rec0, long long nrec, void* dst, size_t dst_bytes,
                       size_t* bytes, cudaStream_t st) = 0;
     virtual int get(int what, int level, void* dst, size_t bytes) = 0;
@@ -1292,6 +1293,30 @@ struct EngineT : tda_engine {
         return 0;
     }
 
+    // rank-normalised split-chain diagnostics of a level's parameter history, on the device (tda_ess.cu)
+    int ess_sums(int level, long long rec0, long long nrec, int n_lag, double* sums, double* folded, cudaStream_t st) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (level < 0 || level >= P.L) return fail(-1, "ess: bad level");
+        const tda::LevelP<R>& v = P.lv[level];
+        if (!v.h_theta) return fail(-1, "ess: the level does not store parameters");
+        if (rec0 < 0 || nrec < 4 || rec0 + nrec > P.rec[level] || rec0 + nrec > v.hist_cap) return fail(-1, "ess: record range has not been written");
+        if (level == 0 && lazy_w_hi > lazy_w_lo) { int r0 = fill_lazy_history(st); if (r0) return r0; }
+        const int nh = (int)(nrec / 2);
+        if (n_lag < 1 || n_lag > nh) n_lag = nh;
+        namespace tp = tda::post;
+        tp::EssWorkspace* w = tp::ess_workspace_create(nrec, P.C, Cs, n_lag);
+        if (!w) return fail(-3, tp::ess_last_error());
+        int r = 0;
+        for (int k = 0; k < P.d && !r; k++) {
+            r = tp::ess_sums(w, v.h_theta + ((size_t)rec0 * P.d + k) * Cs, (int)sizeof(R), (long long)P.d * Cs,
+                             sums + (size_t)k * (n_lag + 4), folded + (size_t)k * 4, st);
+            g_launches += 10;
+        }
+        tp::ess_workspace_destroy(w);
+        if (r) return fail(r, tp::ess_last_error());
+        return 0;
+    }
+
     int compact_sync() override {
         CUDA_TRY(cudaSetDevice(device));
         if (copy_stream) CUDA_TRY(cudaStreamSynchronize(copy_stream));
@@ -1546,6 +1571,10 @@ int tda_compact_fetch(tda_engine* e, int slot, int field, void* dst, size_t dst_
     return e->compact_fetch(slot, field, dst, dst_bytes, bytes);
 }
 int tda_compact_sync(tda_engine* e) { return e ? e->compact_sync() : fail(-1, "null engine"); }
+int tda_ess_sums(tda_engine* e, int level, int64_t rec0, int64_t nrec, int n_lag, double* sums, double* folded, void* s) {
+    if (!e || !sums || !folded) return fail(-1, "null argument");
+    return e->ess_sums(level, rec0, nrec, n_lag, sums, folded, (cudaStream_t)s);
+}
 int tda_host_alloc(size_t bytes, void** ptr) {
     if (!ptr) return fail(-1, "null argument");
     *ptr = nullptr;

@@ -31,6 +31,27 @@ int compact_gather(const void* src, int esz, int W, const uint8_t* acc, long lon
 // accept bytes with the forced first record made explicit: dst[r][c] (dense [nrec][Cs])
 int compact_flags(const uint8_t* acc, long long nrec, int C, int Cs, int force_first, uint8_t* dst, cudaStream_t st);
 
+// ---- diagnostics on the device ----------------------------------------------------------------------
+// Rank-normalised split-chain diagnostics (Vehtari et al. 2021 -- what ArviZ computes on the reference's
+// to_inference_data output, diagnostics.py:6-69) of ONE parameter's history x[t][c] = hist[t * stride_t + c]
+// (t < n_draws, c < C, engine dtype esz).  Every chain is split in halves (n_half = n_draws / 2 draws each,
+// the middle draw of an odd run is dropped), all 2 C n_half values are ranked on the device (radix sort,
+// average ranks for ties -- a rejected step repeats its value), turned into normal scores, and the sums the
+// multi-chain estimators need are accumulated:
+//   sums[0 .. n_lag)  sum over the 2C split chains of the biased autocovariance at lag t
+//   sums[n_lag + 0]   sum of the split-chain means      sums[n_lag + 1]  sum of their squares
+//   sums[n_lag + 2]   number of split chains            sums[n_lag + 3]  n_half
+// `folded` (4 values: lag-0 autocovariance sum, mean sum, mean-square sum, split chains) is the same for the
+// normal scores of |x - median| (the second half of rank-normalised split R-hat).  Both are plain sums over
+// chains, so ranks of a multi-GPU job all-reduce them.  Workspace (about 20 bytes per value) is allocated
+// once per EssWorkspace and reused for every parameter.
+struct EssWorkspace;
+EssWorkspace* ess_workspace_create(long long n_draws, int C, int Cs, int n_lag);
+void ess_workspace_destroy(EssWorkspace* w);
+int ess_sums(EssWorkspace* w, const void* hist, int esz, long long stride_t, double* sums_host, double* folded_host, cudaStream_t st);
+
+const char* ess_last_error();
+
 const char* last_error();
 
 }  // namespace post

@@ -203,3 +203,57 @@ def ess_bulk(x):
     """Bulk effective sample size of draws x [n_chains, n_draws] (rank-normalised, split)."""
     x = np.asarray(x, dtype=np.float64)
     return _ess_plain(_rank_normalise(_split(x)))
+
+
+def ess_rhat_from_sums(sums, folded):
+    """Bulk ESS and rank-normalised split R-hat per parameter from the device-side sums of
+    ``Engine.ess_sums`` (tda_ess_sums): sums [d, n_lag + 4] = autocovariance sums over the split chains,
+    then (sum of means, sum of squared means, split chains, n_half); folded [d, 4] = (lag-0 sum, sum of
+    means, sum of squared means, split chains) of the folded scores.  Same estimators as ``ess_bulk`` /
+    ``rhat`` above, which work on host arrays."""
+    sums = np.atleast_2d(np.asarray(sums, dtype=np.float64))
+    folded = np.atleast_2d(np.asarray(folded, dtype=np.float64))
+    d, n_lag = sums.shape[0], sums.shape[1] - 4
+    ess, rh = np.zeros(d), np.zeros(d)
+
+    def _rhat(ac0_sum, mean_sum, mean_sq_sum, m, n):
+        W = ac0_sum / m * n / (n - 1.0)
+        B_over_n = (mean_sq_sum - mean_sum ** 2 / m) / (m - 1.0)
+        return np.sqrt(((n - 1.0) / n * W + B_over_n) / W)
+
+    for k in range(d):
+        m, n = int(round(sums[k, n_lag + 2])), int(round(sums[k, n_lag + 3]))
+        ac = np.zeros(n)
+        ac[:n_lag] = sums[k, :n_lag]                   # lags beyond n_lag count as zero correlation mass
+        ess[k] = _ess_from_sums(m, n, ac, sums[k, n_lag], sums[k, n_lag + 1]) if n_lag == n else \
+            _ess_from_sums_truncated(m, n, sums[k, :n_lag], sums[k, n_lag], sums[k, n_lag + 1])
+        rh[k] = max(_rhat(sums[k, 0], sums[k, n_lag], sums[k, n_lag + 1], m, n),
+                    _rhat(folded[k, 0], folded[k, 1], folded[k, 2], int(round(folded[k, 3])), n))
+    return ess, rh
+
+
+def _ess_from_sums_truncated(m, n, acov_sum, mean_sum, mean_sq_sum):
+    """Geyer's sequences on the first n_lag lags only (the caller chose n_lag beyond the point where the
+    paired autocorrelations turn negative)."""
+    n_lag = len(acov_sum)
+    acov_mean = np.asarray(acov_sum) / m
+    mean_var = acov_mean[0] * n / (n - 1.0)
+    var_plus = mean_var * (n - 1.0) / n
+    if m > 1:
+        var_plus += (mean_sq_sum - mean_sum ** 2 / m) / (m - 1.0)
+    rho = 1.0 - (mean_var - acov_mean) / var_plus
+    rho[0] = 1.0
+    tau = -1.0
+    prev = None
+    t = 0
+    while t + 1 < n_lag:
+        pair = rho[t] + rho[t + 1]
+        if pair < 0:
+            break
+        if prev is not None and pair > prev:
+            pair = prev                                # initial monotone sequence
+        tau += 2.0 * pair
+        prev = pair
+        t += 2
+    tau = max(tau, 1.0 / np.log10(m * n))
+    return m * n / tau

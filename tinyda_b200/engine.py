@@ -33,9 +33,10 @@ _PIN_POOL_STATE = {"bytes": 0, "max_bytes": 16 << 30}
 
 
 def _pin_class(nbytes):
+    # powers of two: the row count of a compacted block varies from call to call, and a call that falls into
+    # a class the pool has not seen yet pays for page-locking (hundreds of milliseconds per GiB)
     nbytes = max(int(nbytes), 1 << 16)
-    step = max(1 << 16, 1 << (nbytes.bit_length() - 3))       # <= 25 % slack
-    return (nbytes + step - 1) // step * step
+    return 1 << (nbytes - 1).bit_length()
 
 
 def _pin_release(ptr, cls):
@@ -320,6 +321,21 @@ class Engine:
 
     def compact_sync(self):
         check(lib.tda_compact_sync(self._h))
+
+    def ess_sums(self, level=None, rec0=0, nrec=None, n_lag=0, stream=None):
+        """Rank-normalised split-chain sums of the level's recorded parameters, computed on the device
+        (tda_ess_sums): (sums [d, n_lag + 4], folded [d, 4]); feed them to diagnostics.ess_rhat_from_sums,
+        after parallel.allreduce_sums when the chains are sharded over ranks."""
+        level = self.Ln - 1 if level is None else level
+        if nrec is None:
+            nrec = int(self.n_records()[level]) - rec0
+        nh = nrec // 2
+        if n_lag <= 0 or n_lag > nh:
+            n_lag = nh
+        sums = np.zeros((self.d, n_lag + 4))
+        folded = np.zeros((self.d, 4))
+        check(lib.tda_ess_sums(self._h, int(level), int(rec0), int(nrec), int(n_lag), _dptr(sums), _dptr(folded), self._stream_ptr(stream)))
+        return sums, folded
 
     def select_kernel(self, which):
         """"auto" | "generic" | "tc" (tcgen05, 3xTF32) | "tc16" (tcgen05, fp16 split + RNG warps) |

@@ -171,3 +171,38 @@ def allreduce_ess(x_local):
     pack = t.numpy()
     return np.array([_ess_from_sums(int(round(pack[k, n + 2])), n, pack[k, :n], pack[k, n], pack[k, n + 1])
                      for k in range(d)])
+
+
+def allreduce_sums(*arrays):
+    """Sums float64 arrays (e.g. the device-side ESS / R-hat sums of Engine.ess_sums) over all ranks; identity
+    without a process group.  Over NCCL the reduction runs on the device."""
+    import torch
+    dist = _dist()
+    out = []
+    for a in arrays:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if dist is None or dist.get_world_size() == 1:
+            out.append(a)
+            continue
+        t = torch.from_numpy(a.copy())
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t)
+        out.append(t.cpu().numpy())
+    return out if len(out) > 1 else out[0]
+
+
+def allreduce_ess_sums(sums, folded):
+    """All-reduces the per-parameter sums of Engine.ess_sums over the ranks (every rank ranks its own chains:
+    with thousands of chains per GPU the local empirical distribution is the pooled one to O(1/sqrt(N))); the
+    draw count per split chain is a property of the run, not a sum."""
+    dist = _dist()
+    world = 1 if dist is None else dist.get_world_size()
+    sums = np.array(sums, dtype=np.float64)
+    folded = np.array(folded, dtype=np.float64)
+    if world == 1:
+        return sums, folded
+    n_half = sums[:, -1].copy()
+    s, f = allreduce_sums(sums, folded)
+    s[:, -1] = n_half
+    return s, f
