@@ -620,6 +620,13 @@ def run_other(args):
                  capacity_iterations=iters if not shared else iters * total_runs + 64, device=local_rank,
                  chain_offset=rank * C, n_chains_global=world * C if shared else C, archive0=archive0, stream=stream)
     eng.init(theta0)
+    exchange = None
+    if shared:
+        exchange = "single device: persistent launch, grid barrier per step"
+        if world > 1:
+            ok = parallel.connect_dream_peers(eng, rank, world)
+            exchange = ("persistent launch; each step's rows stored into every replica over NVLink peer memory, flag handshake"
+                        if ok else "one launch + one NCCL all-gather per step")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -719,6 +726,7 @@ def run_other(args):
                     "h2d_bytes_per_step": int(theta0.nbytes) if not shared else 0, "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roof,
             "accept_rate_timed_region": accept_rate,
+            **({"archive_exchange": exchange, "us_per_lockstep_step": dev_ms / args.steps / iters * 1e3} if shared else {}),
         }))
     if world > 1:
         dist.destroy_process_group()

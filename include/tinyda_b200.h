@@ -252,6 +252,17 @@ int tda_compact_rows(tda_engine *e, int slot, int64_t *n_rows);
 int tda_compact_fetch(tda_engine *e, int slot, int field, void *host_dst, size_t dst_bytes, size_t *bytes);
 int tda_compact_sync(tda_engine *e);
 
+/* DREAM with the shared archive (proposal.py:1627-1656, ray.py:366-384) over several GPUs of one node, one
+ * process per GPU: tda_peer_export writes an opaque block (cudaIpc handles of this engine's archive replica and
+ * step flags; *needed = its size) that the ranks exchange (e.g. torch.distributed all-gather);
+ * tda_peer_import maps the other ranks' replicas.  From then on tda_engine_run is ONE persistent launch per
+ * call on every rank: each step's new rows are stored straight into every replica over NVLink and a flag
+ * handshake in peer memory closes the step (lock-step visibility, as on one GPU) -- every rank must call
+ * tda_engine_run with the same iteration count.  Without the import, callers all-gather each step's rows
+ * themselves (tda_device_buffer + NCCL). */
+int tda_peer_export(tda_engine *e, void *out, size_t bytes, size_t *needed);
+int tda_peer_import(tda_engine *e, int n_ranks, int my_rank, const void *handles, size_t bytes);
+
 /* Rank-normalised split R-hat / bulk ESS (Vehtari et al. 2021: what ArviZ computes on the reference's
  * to_inference_data output, diagnostics.py:6-69) of a level's recorded parameters [rec0, rec0+nrec), computed
  * ON THE DEVICE -- the history does not cross PCIe.  For each of the d parameters the chains are split in

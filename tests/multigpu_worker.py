@@ -39,6 +39,8 @@ def main(outdir):
                      seed=9, initial_archive=archive0, store_model_output=False, dtype="float32")
     lo, hi = res["local_chains"]
     assert (lo, hi) == parallel.shard_range(C, rank, world)
+    # the step's new archive rows travel inside the persistent kernel, through NVLink peer memory
+    assert res.dream_exchange == "peer-memory", res.dream_exchange
     mine = np.stack([res["chain_%d" % c].parameters for c in range(lo, hi)])          # [n_local, iters+1, d]
     spec = lower_problem(w["posteriors"], w["proposal"])
     eng = Engine(spec, C, dtype="float32", seed=9, store=STORE_STATS, capacity_iterations=iters,

@@ -32,7 +32,7 @@ EXPORTS = [
     "tda_select_kernel", "tda_launch_count", "tda_tc_gemm_selftest", "tda_tc16_gemm_selftest",
     "tda_state_size", "tda_state_save", "tda_state_load",
     "tda_engine_burn", "tda_compact_begin", "tda_compact_rows", "tda_compact_fetch", "tda_compact_sync",
-    "tda_host_alloc", "tda_host_free", "tda_pool_trim", "tda_ess_sums",
+    "tda_host_alloc", "tda_host_free", "tda_pool_trim", "tda_ess_sums", "tda_peer_export", "tda_peer_import",
 ]
 
 
@@ -84,6 +84,8 @@ def _load():
     lib.tda_compact_rows.argtypes = [vp, i32, C.POINTER(i64)]
     lib.tda_compact_fetch.argtypes = [vp, i32, i32, vp, sz, C.POINTER(sz)]
     lib.tda_compact_sync.argtypes = [vp]
+    lib.tda_peer_export.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    lib.tda_peer_import.argtypes = [vp, i32, i32, vp, sz]
     lib.tda_ess_sums.argtypes = [vp, i32, i64, i64, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
     lib.tda_host_alloc.argtypes = [sz, C.POINTER(vp)]
     lib.tda_host_free.argtypes = [vp]

@@ -145,6 +145,15 @@ struct Params {
     R* scratch;            // POISSON: [3][n_max][Cs]  (k-field, c', d')
     int n_max;
     int* error_flag;
+    // DREAM with the shared archive as ONE persistent launch: every step ends with a grid-wide barrier (all
+    // CTAs co-resident, one tile each) and, across GPUs, with the exchange of the step's new archive rows
+    // through peer memory (NVLink stores into every replica) plus a flag handshake
+    int grid_sync;                 // 1: barrier after every base-level step
+    unsigned int* grid_bar;        // device counter (zeroed before the launch)
+    int n_peers, my_rank;          // > 1: archive replicas of the other ranks are mapped (cudaIpc)
+    R* peer_archive[8];            // [rank] -> that rank's archive replica (own entry = archive)
+    unsigned int* peer_flags[8];   // [rank] -> that rank's flag array [8] (one slot per writer rank)
+    unsigned int flag_base;        // flags count steps across launches: value after step t of this launch = flag_base + t + 1
     LevelP<R> lv[MAXL];
 };
 

@@ -140,6 +140,8 @@ struct tda_engine {
     virtual int compact_rows(int slot, long long* n_rows) = 0;
     virtual int compact_fetch(int slot, int field, void* dst, size_t dst_bytes, size_t* bytes) = 0;
     virtual int compact_sync() = 0;
+    virtual int peer_export(void* out, size_t bytes, size_t* needed) = 0;
+    virtual int peer_import(int n_ranks, int my_rank, const void* handles, size_t bytes) = 0;
     virtual int ess_sums(int level, long long rec0, long long nrec, int n_lag, double* sums, double* folded, cudaStream_t st) = 0;
     virtual int fetch(int level, int field, long long rec0, long long nrec, void* dst, size_t dst_bytes,
                       size_t* bytes, cudaStream_t st) = 0;
@@ -319,6 +321,9 @@ struct EngineT : tda_engine {
     long long lazy_w_lo = 0, lazy_w_hi = 0;
     bool state_F_stale = false;
     bool burning = false;      // inside tda_engine_burn: nothing is recorded
+    unsigned int* dream_flags = nullptr;   // [8] step flags written by the peers (shared-archive DREAM over several GPUs)
+    unsigned int flag_next = 0;            // flag value of the next persistent launch's first step, minus one
+    std::vector<void*> peer_mapped;        // cudaIpcOpenMemHandle results
     // quantities of interest: qoi = Q @ F(theta) + q0 per level.  Linear models: composed with the operator
     // on upload (qoi_W = G^T Q^T [d][ldq], qoi_b = Q b + q0) so that Link.qoi comes straight from theta
     int nq[tda::MAXL] = {0, 0, 0, 0}, ldq[tda::MAXL] = {0, 0, 0, 0};
@@ -345,6 +350,7 @@ struct EngineT : tda_engine {
     ~EngineT() override {
         cudaSetDevice(device);
         cudaDeviceSynchronize();           // nothing of this engine is in flight when its blocks go back to the pool
+        for (void* m : peer_mapped) cudaIpcCloseMemHandle(m);
         for (size_t i = 0; i < allocs.size(); i++) g_pool.release(allocs[i], alloc_cls[i], device);
         for (auto& s : cslot) {
             if (s.offsets) g_pool.release(s.offsets, s.offsets_cap, device);
@@ -448,8 +454,10 @@ struct EngineT : tda_engine {
             DALLOC(P.am_T, (size_t)d * d * Cs);
         }
         if (c.prop_kind == TDA_PROP_MALA) { DALLOC(P.grad, (size_t)d * Cs); DALLOC(P.gradp, (size_t)d * Cs); }
+        DALLOC(P.grid_bar, 1);
         if (tda::is_dream(c.prop_kind)) {
             DALLOC(P.archive, (size_t)c.dream_capacity * P.Cg * d);
+            DALLOC(dream_flags, 8);
             dream_slots = c.dream_M0;
             if (c.adaptive) {
                 DALLOC(P.dream_pCR, (size_t)tda::MAX_NCR * Cs);
@@ -883,6 +891,12 @@ struct EngineT : tda_engine {
         return 0;
     }
 
+    // every tile of the lock-step kernel gets its own CTA and all of them fit on the device at once
+    bool dream_persistent_ok() const {
+        const int occ = (sizeof(R) == 4) ? 2 : 1;
+        static const bool off = getenv("TDA_DREAM_PER_STEP_LAUNCH") != nullptr;
+        return !off && n_tiles <= sm_count * occ;
+    }
     bool tc_eligible() const { return tc.eligible(cfg, P); }
     bool tc16_eligible() const { return !tc16_unfit && tc16.eligible(cfg, P); }
     bool tcr_eligible() const { return !tcr_unfit && tcr.eligible(cfg, P); }
@@ -1009,9 +1023,21 @@ struct EngineT : tda_engine {
             P.iterations = iterations;
             CUDA_TRY(tda::mh_reg_launch<R>(P, st));
             g_launches++;
+        } else if (P.prop_kind == TDA_PROP_DREAM && (iterations > 1 || P.n_peers > 1) && dream_persistent_ok()) {
+            // shared archive, lock-step visibility (every chain sees all rows through the previous step): ONE
+            // persistent launch whose steps end in a grid-wide barrier (and, over several GPUs, in the exchange
+            // of the new rows through peer memory); every tile has its own co-resident CTA
+            CUDA_TRY(cudaSetDevice(device));
+            CUDA_TRY(cudaMemsetAsync(P.grid_bar, 0, sizeof(unsigned int), st));
+            P.grid_sync = 1;
+            P.flag_base = flag_next;
+            flag_next += (unsigned int)iterations;
+            r = launch(tda::MODE_RUN, iterations, st);
+            P.grid_sync = 0;
+            if (r) return r;
         } else if (P.prop_kind == TDA_PROP_DREAM && iterations > 1) {
-            // shared archive: lock-step visibility (every chain sees all rows through the
-            // previous step) needs a grid-wide boundary per step -> one launch per step
+            // more tiles than resident CTAs: one launch per step is the grid-wide boundary
+            if (P.n_peers > 1) return fail(-1, "run: the peer-memory archive exchange needs every tile of the ensemble resident (fewer chains per GPU)");
             for (long long i = 0; i < iterations; i++) {
                 r = run(1, st, true);
                 if (r) return r;
@@ -1293,6 +1319,47 @@ struct EngineT : tda_engine {
         return 0;
     }
 
+    // ---- shared archive over several GPUs: the replicas and the step flags are mapped into each other ----
+    struct PeerHandles {
+        cudaIpcMemHandle_t archive, flags;
+    };
+    int peer_export(void* out, size_t bytes, size_t* needed) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (needed) *needed = sizeof(PeerHandles);
+        if (!out) return 0;
+        if (bytes < sizeof(PeerHandles)) return fail(-1, "peer export: buffer too small");
+        if (!P.archive || !dream_flags) return fail(-1, "peer export: the proposal has no shared archive");
+        PeerHandles h;
+        CUDA_TRY(cudaIpcGetMemHandle(&h.archive, P.archive));
+        CUDA_TRY(cudaIpcGetMemHandle(&h.flags, dream_flags));
+        memcpy(out, &h, sizeof(h));
+        return 0;
+    }
+    int peer_import(int n_ranks, int my_rank, const void* handles, size_t bytes) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (n_ranks < 1 || n_ranks > 8 || my_rank < 0 || my_rank >= n_ranks) return fail(-1, "peer import: 1..8 ranks");
+        if (bytes < (size_t)n_ranks * sizeof(PeerHandles)) return fail(-1, "peer import: one handle block per rank expected");
+        if (!P.archive || !dream_flags) return fail(-1, "peer import: the proposal has no shared archive");
+        if (!dream_persistent_ok()) return fail(-1, "peer import: the ensemble's tiles must all be resident for the in-kernel exchange");
+        const PeerHandles* h = reinterpret_cast<const PeerHandles*>(handles);
+        for (int r = 0; r < n_ranks; r++) {
+            if (r == my_rank) { P.peer_archive[r] = P.archive; P.peer_flags[r] = dream_flags; continue; }
+            void *a = nullptr, *f = nullptr;
+            cudaError_t e1 = cudaIpcOpenMemHandle(&a, h[r].archive, cudaIpcMemLazyEnablePeerAccess);
+            cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&f, h[r].flags, cudaIpcMemLazyEnablePeerAccess) : e1;
+            if (e1 != cudaSuccess || e2 != cudaSuccess) {
+                cudaGetLastError();
+                if (a) cudaIpcCloseMemHandle(a);
+                return fail(-2, std::string("peer import: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            }
+            peer_mapped.push_back(a); peer_mapped.push_back(f);
+            P.peer_archive[r] = reinterpret_cast<R*>(a);
+            P.peer_flags[r] = reinterpret_cast<unsigned int*>(f);
+        }
+        P.n_peers = n_ranks; P.my_rank = my_rank;
+        return 0;
+    }
+
     // rank-normalised split-chain diagnostics of a level's parameter history, on the device (tda_ess.cu)
     int ess_sums(int level, long long rec0, long long nrec, int n_lag, double* sums, double* folded, cudaStream_t st) override {
         CUDA_TRY(cudaSetDevice(device));
@@ -1571,6 +1638,11 @@ int tda_compact_fetch(tda_engine* e, int slot, int field, void* dst, size_t dst_
     return e->compact_fetch(slot, field, dst, dst_bytes, bytes);
 }
 int tda_compact_sync(tda_engine* e) { return e ? e->compact_sync() : fail(-1, "null engine"); }
+int tda_peer_export(tda_engine* e, void* out, size_t bytes, size_t* needed) { return e ? e->peer_export(out, bytes, needed) : fail(-1, "null engine"); }
+int tda_peer_import(tda_engine* e, int n_ranks, int my_rank, const void* handles, size_t bytes) {
+    if (!e || !handles) return fail(-1, "null argument");
+    return e->peer_import(n_ranks, my_rank, handles, bytes);
+}
 int tda_ess_sums(tda_engine* e, int level, int64_t rec0, int64_t nrec, int n_lag, double* sums, double* folded, void* s) {
     if (!e || !sums || !folded) return fail(-1, "null argument");
     return e->ess_sums(level, rec0, nrec, n_lag, sums, folded, (cudaStream_t)s);

@@ -828,7 +828,7 @@ struct Tile {
         const int d = p.d;
         if (tid < TC) {
             const int c = tid, delta = p.dream_delta;
-            const long long nslots = (p.prop_kind == TDA_PROP_DREAM) ? p.dream_slots : slots;
+            const long long nslots = slots;        // rows per chain visible now (advances inside a persistent launch)
             const long long M = (p.prop_kind == TDA_PROP_DREAM) ? nslots * p.Cg : nslots;
             const bool seq_z = !p.z_round;
             ChainStreams<R> rs(p, chain0 + c);
@@ -1176,8 +1176,14 @@ struct Tile {
             if (slots < p.dream_cap)
                 for (int e = tid; e < d * TC; e += NT) {
                     int c = e / d, k = e - c * d;
-                    if (chain0 + c < p.C)
-                        p.archive[((size_t)slots * p.Cg + p.arch_off + chain0 + c) * d + k] = p.lv[0].theta[gi(k, c)];
+                    if (chain0 + c < p.C) {
+                        const size_t o = ((size_t)slots * p.Cg + p.arch_off + chain0 + c) * d + k;
+                        const R x = p.lv[0].theta[gi(k, c)];
+                        p.archive[o] = x;
+                        // the other GPUs' replicas, straight over NVLink (ray.py:372-376: update_archive)
+                        for (int r = 0; r < p.n_peers; r++)
+                            if (r != p.my_rank) p.peer_archive[r][o] = x;
+                    }
                 }
             slots += 1;
             if (p.adaptive) {
@@ -1440,6 +1446,40 @@ struct Tile {
         record(L - 1);
     }
 
+    // End of a lock-step step of the shared-archive ensemble: every chain of every GPU has appended its row
+    // (proposal.py:1652) before any chain reads the archive again (proposal.py:1655).  Local CTAs meet at a
+    // counter in global memory (all co-resident: one tile per CTA, grid <= resident CTAs); across GPUs rank r
+    // announces "my rows of step t are in your replica" by a system-scope release store into slot r of every
+    // peer's flag array, and waits for the same from everybody.
+    __device__ void step_barrier(unsigned step) {
+        __syncthreads();
+        if (tid == 0) {
+            if (p.n_peers > 1) __threadfence_system();
+            else __threadfence();
+            atomicAdd(p.grid_bar, 1u);
+            const unsigned target = (step + 1u) * gridDim.x;
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.grid_bar) : "memory");
+                if (v < target) __nanosleep(40);
+            } while (v < target);
+            if (p.n_peers > 1) {
+                const unsigned flag = p.flag_base + step + 1u;
+                if (blockIdx.x == 0)
+                    for (int r = 0; r < p.n_peers; r++)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flags[r] + p.my_rank), "r"(flag) : "memory");
+                for (int r = 0; r < p.n_peers; r++) {
+                    const unsigned* f = p.peer_flags[p.my_rank] + r;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                        if ((int)(v - flag) < 0) __nanosleep(100);
+                    } while ((int)(v - flag) < 0);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
     __device__ void run() {
         const int L = p.L;
         int cnt[MAXL];
@@ -1448,6 +1488,7 @@ struct Tile {
         while (it < p.iterations) {
             if (p.randomize && cnt[0] == 0) draw_promoted();
             base_step();
+            if (p.grid_sync) step_barrier((unsigned)it);
             if (L == 1) { it++; continue; }
             cnt[0]++;
             if (p.randomize) snapshot_promoted(cnt[0]);

@@ -223,6 +223,7 @@ class Engine:
                 raise ValueError("DREAM(Z) needs the initial archive [n_chains_global, M0, d]")
             self._up(L.TDA_UP_DREAM_ARCHIVE0, 0, archive0)
         self.iterations_done = 0
+        self.peers_connected = False
 
     # ---- plumbing --------------------------------------------------------------------------
     def _up(self, what, level, arr):
@@ -321,6 +322,19 @@ class Engine:
 
     def compact_sync(self):
         check(lib.tda_compact_sync(self._h))
+
+    # ---- shared-archive DREAM over several GPUs: peer-memory exchange inside the kernel --------------------
+    def peer_export(self):
+        n = C.c_size_t(0)
+        check(lib.tda_peer_export(self._h, None, 0, C.byref(n)))
+        blob = np.zeros(n.value, dtype=np.uint8)
+        check(lib.tda_peer_export(self._h, blob.ctypes.data_as(C.c_void_p), blob.nbytes, C.byref(n)))
+        return blob
+
+    def peer_import(self, n_ranks, my_rank, blobs):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8)
+        check(lib.tda_peer_import(self._h, int(n_ranks), int(my_rank), blobs.ctypes.data_as(C.c_void_p), blobs.nbytes))
+        self.peers_connected = True
 
     def ess_sums(self, level=None, rec0=0, nrec=None, n_lag=0, stream=None):
         """Rank-normalised split-chain sums of the level's recorded parameters, computed on the device

@@ -100,12 +100,48 @@ def allgather_rows(rows, lo, hi, world):
     return rows
 
 
+def connect_dream_peers(eng, rank, world):
+    """Maps every rank's archive replica and step flags into the others (cudaIpc handles exchanged with one
+    all-gather) so that the engine's persistent kernel exchanges each step's rows through NVLink peer memory
+    itself.  Returns False -- and the per-step NCCL all-gather of run_dream_shared is used -- when the ranks are
+    not NCCL ranks of one node or the mapping fails on any of them."""
+    import torch
+    d = _dist()
+    if d is None or world == 1 or d.get_backend() != "nccl":
+        return False
+    ok = 1
+    try:
+        mine = eng.peer_export()
+    except Exception:
+        mine, ok = np.zeros(128, dtype=np.uint8), 0
+    dev = "cuda:%d" % eng.device
+    t = torch.from_numpy(mine.copy()).to(dev)
+    allb = torch.empty(world * t.numel(), dtype=torch.uint8, device=dev)
+    d.all_gather_into_tensor(allb, t)
+    if ok:
+        try:
+            eng.peer_import(world, rank, allb.cpu().numpy())
+        except Exception:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    d.all_reduce(flag, op=d.ReduceOp.MIN)
+    good = bool(int(flag.item()))
+    if not good:
+        eng.peers_connected = False
+    return good
+
+
 def run_dream_shared(eng, iterations, rank, world):
-    """DREAM with the shared archive over `world` GPUs: one lock-step step per launch, then the
+    """DREAM with the shared archive over `world` GPUs.  With the replicas mapped into each other
+    (connect_dream_peers) this is one persistent launch: the kernel stores each step's rows into every replica
+    and closes the step with a flag handshake.  Otherwise: one lock-step step per launch, then the NCCL
     all-gather of that step's new rows (chain-major archive slot)."""
+    M0 = int(eng.spec["proposal"]["M0"])
+    if getattr(eng, "peers_connected", False):
+        eng.run(iterations)
+        return M0
     arch = archive_tensor(eng)
     lo, hi = shard_range(eng.Cg, rank, world)
-    M0 = int(eng.spec["proposal"]["M0"])
     for t in range(iterations):
         slot = eng.dream_slots()
         eng.run(1)

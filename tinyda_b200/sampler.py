@@ -227,6 +227,8 @@ def sample(
                               "device memory: pass a smaller chunk_iterations, store_model_output=False and/or "
                               "store_coarse_chain=False" % (chunk_iterations, n_local)) from None
         raise
+    if shared and world > 1:
+        parallel.connect_dream_peers(eng, rank, world)      # in-kernel archive exchange over NVLink peer memory
     _lap("lowering + engine construction")
     print("Sampling {} chains in lock-step on GPU {}".format(n_chains, device))
     eng.init(theta0)
@@ -294,6 +296,9 @@ def sample(
     result.add_chains(keys[top], lo, hi, hist.chain)
     result.history = hist                     # the finest level of the local chains, compacted (link.CompactHistory)
     result.local_chains = (lo, hi)
+    if shared:
+        result.dream_exchange = ("peer-memory" if getattr(eng, "peers_connected", False) else
+                                 "nccl all-gather per step" if world > 1 else "single device")
     if world > 1:
         result["local_chains"] = (lo, hi)
     if return_engine:
