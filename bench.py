@@ -359,6 +359,7 @@ def run_ours(args):
     d2h_seen = [0]
 
     def e2e_step(k):
+        ta = time.perf_counter()
         with contextlib.redirect_stdout(io.StringIO()):
             res = tda.sample(w["posteriors"], w["proposal"], e2e_iters, n_chains=world * C, initial_parameters=theta_host,
                              subchain_length=J0, dtype=dtype, seed=5000 + k, store_model_output=False,
@@ -367,7 +368,12 @@ def run_ours(args):
         # the device->host read of the step's result: every block's accept flags, row offsets and accepted rows
         d2h_seen[0] = sum(ch.accept.nbytes + ch.offsets.nbytes + ch.theta.nbytes + ch.prior.nbytes + ch.like.nbytes for ch in h.chunks)
         assert h.n_records == e2e_iters + 1
-        return float(h.chunks[-1].like[-1])
+        out_val = float(h.chunks[-1].like[-1])
+        tb = time.perf_counter()
+        del res, h
+        if os.environ.get("TDA_PROFILE"):
+            sys.stderr.write("[bench e2e rank %d] sample() %.1f ms, release %.1f ms\n" % (rank, (tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3))
+        return out_val
 
     e2e_steps = max(2, min(args.steps, 3))
     for k in range(3):                      # warm-up: device / pinned pools, allocator, lazy imports
@@ -711,9 +717,16 @@ def run_other(args):
             roof = {"bound": "hbm", "achieved": per_gpu * cd["bytes_unit"] / 1e9, "peak": float(pk["hbm_gbs"]), "unit": "GB/s",
                     "note": "%d B/transition (SURVEY 8d) x per-GPU transitions/s; peak = copy bandwidth, %s" % (cd["bytes_unit"], src)}
         else:
-            peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            # measured with tools/ubench/fma_peak.cu on this pool's B200 (profiles/r02_measured_fma_peaks.json)
+            fpath = os.path.join(ROOT, "profiles", "r02_measured_fma_peaks.json")
+            fpk = json.load(open(fpath)) if os.path.exists(fpath) else {}
+            if args.dtype == "float64":
+                peak, what = float(fpk.get("fp64_dfma_tflops", 37.0)), "fp64 DFMA"
+            else:
+                peak, what = float(fpk.get("fp32_ffma_tflops", 71.0)), "fp32 FFMA"
             roof = {"bound": cd["bound"], "achieved": per_gpu * cd["flop_unit"] / 1e12, "peak": peak, "unit": "TFLOP/s",
-                    "note": "%.0f algorithmic flop/unit (SURVEY 8d) x per-GPU units/s; peak = fp32 FMA, computed 148 SM x 128 lanes x 2 x 1.965 GHz (not measured)" % cd["flop_unit"]}
+                    "note": "%.0f algorithmic flop/unit (SURVEY 8d) x per-GPU units/s; peak = %s measured with tools/ubench/fma_peak.cu "
+                            "(profiles/r02_measured_fma_peaks.json)" % (cd["flop_unit"], what)}
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["traffic"] = None
         print(json.dumps({
