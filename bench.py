@@ -525,10 +525,11 @@ def run_ours(args):
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "frac_of_sustained_peak": achieved / peak_sustained,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one da_tc16_kernel launch of this very
-                # command (ncu --set full, profiles/r01_ncu_tc16_summary.txt): 0.164 + 1.148 GB against
-                # 0.868 GB of algorithmic history bytes (265 B x 3,276,800 transitions)
-                "traffic": 1.312e9 if (kernel_used == "tc16" and C == N_CHAINS_PER_GPU and iters == ITERS_PER_STEP and not coarse_hist) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one da_tc16_kernel launch of this workload
+                # (ncu --set full, profiles/r02_ncu_tc16_summary.txt): 0.164 + 1.132 GB against 0.868 GB of
+                # algorithmic history bytes (265 B x 3,276,800 transitions); the rest is the chain-state hand-off
+                # between work units and the running moments (red.global.add)
+                "traffic": 1.296e9 if (kernel_used == "tc16" and C == N_CHAINS_PER_GPU and iters == ITERS_PER_STEP and not coarse_hist) else None,
                 "executed_tflops": per_gpu_rate * F_EXEC_TC16 / 1e12 if kernel_used == "tc16" else None,
                 "executed_frac": per_gpu_rate * F_EXEC_TC16 / 1e12 / peak if kernel_used == "tc16" else None,
                 "note": "achieved = 458752 algorithmic flop/transition x per-GPU transitions/s "
