@@ -350,7 +350,9 @@ def run_ours(args):
     import io
     import tinyda_b200 as tda
     from tinyda_b200.engine import pinned_empty
-    e2e_iters = args.e2e_iters if args.e2e_iters is not None else (1000 if not args.quick else 40)
+    # with every coarse Link recorded (10 x 264 B per fine iteration and chain, fetched densely) the host holds the
+    # whole coarse chain: keep that call short
+    e2e_iters = args.e2e_iters if args.e2e_iters is not None else ((1000 if not coarse_hist else 20) if not args.quick else 40)
     cur = eng.get("theta", 1)                                            # [C, d] float64, burnt-in states
     theta_host = pinned_empty((world * C, d), np.float64)
     theta_host[:] = 0.0

@@ -220,3 +220,29 @@ def test_create_link_and_get_map_run_on_the_device():
     np.testing.assert_allclose(ML, np.linalg.lstsq(G, y - 0.3, rcond=None)[0], atol=2e-4)
     MAP2 = tda.get_MAP(post, method="differential_evolution", bounds=[(-4, 4)] * d, seed=1, maxiter=300, tol=1e-10)
     np.testing.assert_allclose(MAP2, mu, atol=5e-3)
+
+
+def test_states_outside_the_fp16_operand_range_run_on_another_kernel():
+    """The fp16-split kernel's theta image is fixed-point at a scale taken from the prior (|mean| + 12 sd).
+    Initial parameters far outside it would overflow to inf and freeze the chain: such a job is moved to a
+    kernel that can hold them, and still moves."""
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    from tinyda_b200.workloads import cfg2_da
+    w = cfg2_da()
+    spec = lower_problem(w["posteriors"], w["proposal"], 10)
+    C = 256
+    theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1))
+    theta0[3] *= 400.0                                   # ~400 prior standard deviations out
+    eng = Engine(spec, C, dtype="float32", seed=1, store=[STORE_NONE, STORE_STATS], capacity_iterations=20)
+    eng.init(theta0)
+    assert eng.kernel() == "tc16"                        # by configuration ...
+    eng.run(20)
+    assert eng.kernel() != "tc16"                        # ... but not with these states
+    th = eng.fetch(1, "theta")
+    assert np.isfinite(th).all() and np.isfinite(eng.fetch(1, "like")).all()
+    acc = eng.get("accept_counts")
+    assert acc[0][3] > 0                                 # the far-out chain accepts coarse proposals (it is not frozen)
+    eng.init(w["prior"].rvs(C, random_state=np.random.default_rng(2)))
+    assert eng.kernel() == "tc16"                        # fresh states: the fast kernel again
+    eng.close()

@@ -906,6 +906,7 @@ template <typename R>
 struct DaTc16State {
     std::string err;
     bool prepared = false;
+    float theta_limit = 0.0f;
     bool eligible(const tda_config&, const Params<R>&) const { return false; }
     int prepare(const Params<R>&, const tda_config&) { err = "fp16-split tensor-core DA kernel is float32 only"; return 1; }
     int timeline(long long*) { return -5; }
@@ -922,6 +923,7 @@ struct DaTc16State<float> {
     int* dProgress = nullptr;
     int progress_len = 0;
     bool prepared = false;
+    float theta_limit = 0.0f;     // |theta| of a current state must stay below this (fp16 operand image at scale 2^s_theta)
     DaTc16Params q{};
 
     bool eligible(const tda_config& c, const Params<float>& P) const {
@@ -1140,6 +1142,7 @@ struct DaTc16State<float> {
         q.sc_p = (float)std::ldexp(1.0, -(s_th + s_LP));
         q.th_scale = (float)std::ldexp(1.0, s_th);
         q.th_unscale = (float)std::ldexp(1.0, -s_th);
+        theta_limit = (float)std::ldexp(65000.0, -s_th);
         prepared = true;
         return 0;
     }

@@ -311,7 +311,8 @@ struct EngineT : tda_engine {
     double* stage_theta = nullptr;   // device staging for the initial states ([C][d] float64)
     tda::DaTcState<R> tc;      // tcgen05 fast path (float only; inert for double)
     tda::DaTc16State<R> tc16;  // fp16-split tcgen05 fast path (float only)
-    bool tc16_unfit = false;   // prepare() found operands that do not fit the fp16 range
+    bool tc16_unfit = false;   // prepare() found operands (or a chain state) that do not fit the fp16 range
+    bool tc16_state_checked = false;   // the current states were checked against the operand range since they last changed hands
     TcrAdapter<R> tcr;         // whitened-state / output-recursion tcgen05 kernel (float only), tda_da_tcr.cu
     bool tcr_unfit = false;
     // records written by the fp16-split kernel whose derived fields (coarse Link.prior, Link.model_output)
@@ -882,6 +883,8 @@ struct EngineT : tda_engine {
         state_F_stale = false;
         tcr.invalidate();
         tcr_unfit = false;
+        tc16_state_checked = false;
+        if (tc16.prepared) tc16_unfit = false;      // the operands fit; only a previous run's states did not
         CUDA_TRY(cudaSetDevice(device));
         CUDA_TRY(cudaMemsetAsync(P.error_flag, 0, sizeof(int), st));
         int r = launch(tda::MODE_INIT, 0, st);
@@ -896,6 +899,24 @@ struct EngineT : tda_engine {
         const int occ = (sizeof(R) == 4) ? 2 : 1;
         static const bool off = getenv("TDA_DREAM_PER_STEP_LAUNCH") != nullptr;
         return !off && n_tiles <= sm_count * occ;
+    }
+    // 0: every current state fits the fp16-split kernel's theta image, 1: not, < 0: error
+    int check_tc16_state_range(cudaStream_t st) {
+        if constexpr (sizeof(R) != 4) {
+            return 0;
+        } else {
+            CUDA_TRY(cudaSetDevice(device));
+            unsigned int* bits = reinterpret_cast<unsigned int*>(P.grid_bar);      // a spare device word (zeroed by the check)
+            int r = tda::post::max_abs_f32(reinterpret_cast<const float*>(P.lv[P.L - 1].theta), (size_t)P.d * Cs, bits, st);
+            if (r) return fail(r, tda::post::last_error());
+            g_launches++;
+            unsigned int h = 0;
+            CUDA_TRY(cudaMemcpyAsync(&h, bits, sizeof(h), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            float m;
+            memcpy(&m, &h, sizeof(m));
+            return (m < tc16.theta_limit) ? 0 : 1;
+        }
     }
     bool tc_eligible() const { return tc.eligible(cfg, P); }
     bool tc16_eligible() const { return !tc16_unfit && tc16.eligible(cfg, P); }
@@ -987,6 +1008,25 @@ struct EngineT : tda_engine {
                 which = resolved_kernel();
             }
         }
+        if (which == 3 && !tc16_state_checked) {
+            // The theta operand image is fixed-point at a scale chosen from the prior (|mean| + 12 sd): a CURRENT
+            // state outside it (initial parameters far from the prior, a state another kernel left) would
+            // overflow to inf and freeze the chain.  Checked once per hand-over; such a job runs on another kernel.
+            int r = check_tc16_state_range(st);
+            if (r < 0) return r;
+            if (r > 0) {
+                if (kernel_choice == 3) return fail(-1, "run: a chain state lies outside the fp16 operand range of the fp16-split kernel");
+                tc16_unfit = true;
+                which = resolved_kernel();
+                if (which == 5) {
+                    int r5 = tcr.ready(P, cfg, st);
+                    if (r5 < 0) return fail(r5, tcr.err);
+                    if (r5 > 0) { tcr_unfit = true; which = resolved_kernel(); }
+                }
+            } else {
+                tc16_state_checked = true;
+            }
+        }
         P.z_round = z_round_effective();
         int r;
         if (which != 3 && which != 5) {
@@ -995,6 +1035,7 @@ struct EngineT : tda_engine {
             if (r) return r;
         }
         if (which != 5) tcr.invalidate();          // theta moves without the whitened copy
+        if (which != 3) tc16_state_checked = false;
         if ((which == 3 || which == 5) && iterations > (1 << 20)) {
             // the fp16-split kernel counts its coarse steps per launch in 32 bits
             for (long long done = 0; done < iterations;) {
@@ -1109,6 +1150,7 @@ struct EngineT : tda_engine {
         } else {
             state_F_stale = false;
             tcr.invalidate();
+            tc16_state_checked = false;
             for (int l = 0; l < tda::MAXL; l++) lazy_lo[l] = lazy_hi[l] = 0;
         }
         CUDA_TRY(cudaDeviceSynchronize());

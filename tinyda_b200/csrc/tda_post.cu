@@ -142,9 +142,29 @@ __global__ void __launch_bounds__(256) flags_kernel(const uint8_t* __restrict__ 
     }
 }
 
+__global__ void __launch_bounds__(256) max_abs_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ out) {
+    float m = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float v = fabsf(x[i]);
+        m = (v <= 3.0e38f) ? fmaxf(m, v) : 3.0e38f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
 }  // namespace
 
 const char* last_error() { return g_perr.c_str(); }
+
+int max_abs_f32(const float* x, size_t n, unsigned int* out_bits, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(out_bits, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return pfail("max_abs", e);
+    const unsigned grid = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    max_abs_kernel<<<grid ? grid : 1, 256, 0, st>>>(x, n, out_bits);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : pfail("max_abs", e);
+}
 
 int compact_offsets(const uint8_t* acc, long long nrec, int C, int Cs, int force_first, long long* offsets, long long* scratch,
                     cudaStream_t st) {

@@ -52,6 +52,9 @@ int ess_sums(EssWorkspace* w, const void* hist, int esz, long long stride_t, dou
 
 const char* ess_last_error();
 
+// max |x[i]| over n floats -> *out_bits (the bits of a non-negative float; NaN / inf count as 3e38); out_bits is zeroed here
+int max_abs_f32(const float* x, size_t n, unsigned int* out_bits, cudaStream_t st);
+
 const char* last_error();
 
 }  // namespace post
