@@ -9,6 +9,8 @@ import golden_io
 
 pytestmark = pytest.mark.gpu
 
+FP32_STATE_RTOL = 1e-5      # north_star's float32 tolerance, relative to the largest |theta| of the chain
+
 CASES = ["mh_rwmh_linreg", "mh_pcn_diag", "mala_rosenbrock", "mala_linear"]
 
 
@@ -41,11 +43,15 @@ def test_reg_kernel_fp32_matches_reference_until_near_tie(name):
     ref = g["ref"][0]
     fd = first_divergence(out[0]["acc"], ref["acc"])
     assert fd.sum() >= 0.5 * ref["acc"].size
+    worst = 0.0
     for c in range(fd.size):
         k = int(fd[c])
         if k:
-            scale = np.abs(ref["theta"][c, :k]).max() + 1e-30
-            np.testing.assert_allclose(out[0]["theta"][c, :k], ref["theta"][c, :k], rtol=2e-4, atol=2e-4 * scale)
+            scale = np.abs(ref["theta"][c]).max() + 1e-30
+            worst = max(worst, np.abs(out[0]["theta"][c, :k] - ref["theta"][c, :k]).max() / scale)
+    print("\nreg kernel fp32 [%s]: %d of %d decisions before a first flip, max relative state error %.2e"
+          % (name, int(fd.sum()), ref["acc"].size, worst))
+    assert worst <= FP32_STATE_RTOL, worst
 
 
 def _engine(g, dtype, kernel, iters, store, seed=77, C=None, offset=5):
