@@ -516,21 +516,23 @@ def test_tcr_coarse_chain_records_agree_with_the_generic_kernel():
     a.close(); b.close()
 
 
-def test_tc16_single_tile_mode_is_bit_identical_to_the_paired_mode(monkeypatch):
-    """With fewer tile pairs than half the SMs every CTA advances ONE 128-chain tile (twice as many SMs work:
-    the strong-scaling case, 8192 chains per GPU); the chains do not notice."""
+def test_tc16_single_tile_modes_are_bit_identical_to_the_paired_mode(monkeypatch):
+    """With fewer tile pairs than half the SMs every CTA advances ONE 128-chain tile, with fewer tiles than half
+    the SMs one 64-chain half tile (the strong-scaling case: 8192 chains per GPU use 128 SMs instead of 32);
+    the chains do not notice."""
     from tinyda_b200.workloads import cfg2_da
     C, iters = 2048 + 100, 9
     theta0 = cfg2_da()["prior"].rvs(C, random_state=np.random.default_rng(4))
     outs = []
-    for no_solo in ("1", None):
-        if no_solo:
-            monkeypatch.setenv("TDA_TC16_NO_SOLO", no_solo)
-        else:
-            monkeypatch.delenv("TDA_TC16_NO_SOLO", raising=False)
+    for env in ({"TDA_TC16_NO_SOLO": "1"}, {"TDA_TC16_NO_HALF": "1"}, {}):
+        for k in ("TDA_TC16_NO_SOLO", "TDA_TC16_NO_HALF"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         eng, _ = _cfg2_engine(C, "tc16", iters=iters, theta0=theta0)
         eng.run(4); eng.run(iters - 4)
         outs.append((eng.fetch(1, "theta"), eng.fetch(1, "like"), eng.fetch(1, "accept"), eng.get("accept_counts"), eng.get("cursors")))
         eng.close()
-    for a, b in zip(*outs):
-        assert np.array_equal(a, b)
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)

@@ -207,10 +207,18 @@ __host__ __device__ __forceinline__ void mulwide32(uint32_t a, uint32_t m, uint3
 #endif
 }
 
-__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+// Rounds: 10 for the uniform (accept-test) streams; TDA_PHILOX_Z_ROUNDS for the normal streams.  Philox4x32-7
+// is the smallest round count Salmon et al. report as Crush-resistant (BigCrush clean); 10 is their default
+// with a safety margin.  The normal generator is the pacing item of the tensor-core kernels (30 % of all
+// instructions, half of them Philox rounds), see DESIGN.md section 4.2.
+#ifndef TDA_PHILOX_Z_ROUNDS
+#define TDA_PHILOX_Z_ROUNDS 10
+#endif
+template <int ROUNDS>
+__host__ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
+    for (int i = 0; i < ROUNDS; i++) {
         uint32_t hi0, lo0, hi1, lo1;
         mulwide32(ctr.x, M0, hi0, lo0);
         mulwide32(ctr.z, M1, hi1, lo1);
@@ -220,13 +228,15 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     }
     return ctr;
 }
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) { return philox4x32<10>(ctr, key); }
 
 __device__ __forceinline__ uint4 philox_block(unsigned long long seed, long long chain, uint32_t stream,
                                               unsigned long long block) {
     uint4 ctr = make_uint4((uint32_t)block, (uint32_t)(block >> 32), (uint32_t)chain,
                            stream ^ (uint32_t)((unsigned long long)chain >> 32));
     uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    return philox4x32_10(ctr, key);
+    // `stream` is a compile-time constant at every call site: the branch folds away
+    return stream == STREAM_Z ? philox4x32<TDA_PHILOX_Z_ROUNDS>(ctr, key) : philox4x32<10>(ctr, key);
 }
 
 template <typename R> __device__ __forceinline__ R u01(uint32_t x);

@@ -93,6 +93,8 @@ struct DaTc16Params {
     int n_pairs;              // units per block of iterations: tile pairs, or single tiles when `solo`
     int solo;                 // fewer tile pairs than half the SMs: every CTA advances ONE 128-chain tile (the warps of
                               // the second tile idle), so that twice as many SMs work (strong scaling)
+    int half;                 // (with solo) fewer tiles than half the SMs: tiles of 64 chains -- only the warps of TMEM
+                              // lanes 0..63 work, the MMA's rows 64..127 are padding -- so that the SMs fill up again
     int ib, nb;               // work units: iterations per block, blocks per launch (unit = tile pair x block)
     int* progress;            // [n_pairs] tile completions of this launch (2 per finished block)
     long long* dbg;           // optional timeline probe (tools/tc16_timeline.py): [role 4][256] clock64 stamps of CTA 0
@@ -384,18 +386,19 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     if (warp == T16_MMA_WARP0) tc::tmem_alloc(s_tmem, 512);
     if (tid == T16_PROD_WARP * 32) {
         tc::mbar_init(bar_res, 1);
+        const int nrw = q.half ? 4 : 8;                 // row warps of a tile that take part
         for (int i = 0; i < 2; i++) {
-            tc::mbar_init(bar_reqA + i, 8);
-            tc::mbar_init(bar_reqB + i, 8);
+            tc::mbar_init(bar_reqA + i, nrw);
+            tc::mbar_init(bar_reqB + i, nrw);
             tc::mbar_init(bar_respA + i, 1);
             tc::mbar_init(bar_respB + i, 1);
         }
         for (int i = 0; i < 6; i++) {
-            tc::mbar_init(bar_reqF + i, 8);
+            tc::mbar_init(bar_reqF + i, nrw);
             tc::mbar_init(bar_respF + i, 1);
         }
         for (int i = 0; i < 4; i++) {
-            tc::mbar_init(bar_zfull + i, 4);
+            tc::mbar_init(bar_zfull + i, q.solo ? 8 : 4);          // single-tile modes: all eight RNG warps serve the tile
             tc::mbar_init(bar_zfree + i, 1);
         }
         for (int s = 0; s < T16_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, q.solo ? 1 : 2); }
@@ -404,7 +407,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     // d < 64 (multiples of 16): the operators are zero-padded to 64 rows on the host and the normals'
     // columns d..63 stay zero -- the RNG warps only write the first d columns of a z image
     const int d = PAD ? p.d : T16_K;
-    if (PAD) {
+    if (PAD || q.half) {
         uint4* zz = reinterpret_cast<uint4*>(zbuf);
         for (int i = tid; i < 4 * T16_IMG / 16; i += T16_THREADS) zz[i] = make_uint4(0u, 0u, 0u, 0u);
         tc::fence_proxy_async_smem();
@@ -418,21 +421,30 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
     const int iters = (int)p.iterations;          // per launch; checked on the host
     const bool inj = p.rng_mode == TDA_RNG_INJECTED;
     const bool solo = q.solo != 0;
+    const bool half = q.half != 0;                 // implies solo
+    const int nbt = half ? 128 : 256;              // threads of a tile's named barriers
 
     if (warp >= T16_RNG_WARP0 && warp < T16_RNG_WARP0 + T16_RNG_WARPS) {
         // =====================================================================================
         // RNG warps: thread = one chain of one tile; 64 normals per coarse step -> z image(s)
         // =====================================================================================
         tc::setmaxnreg_dec<T16_REGS_RNG>();
-        const int t = (warp - T16_RNG_WARP0) >> 2;
-        const int row = (warp & 3) * 32 + lane;
+        // paired mode: four warps per tile, a thread draws the 64 normals of its chain.  Single-tile modes: ALL
+        // eight RNG warps work for the one tile -- the generator's latency per z image (a serial chain of
+        // ~250 instructions per 16-normal group) paces a lone tile -- so a chain's groups are dealt to 2
+        // (128-chain tile) or 4 (64-chain tile) threads.
+        const int wi = warp - T16_RNG_WARP0;
+        const int t = solo ? 0 : (wi >> 2);
+        const int row = half ? (wi & 1) * 32 + lane : (wi & 3) * 32 + lane;
+        const int part = half ? (wi >> 1) : solo ? (wi >> 2) : 0;
+        const int nparts = half ? 4 : solo ? 2 : 1;
         unsigned char* zt = zbuf + (size_t)t * 2 * T16_IMG + (row >> 3) * ((T16_K / 8) * 128) + (row & 7) * 16;
         uint64_t* zfull = bar_zfull + t * 2;
         uint64_t* zfree = bar_zfree + t * 2;
         unsigned n = 0;                                    // coarse steps produced
         T16Unit un;
-        for (int uk = 0; !(solo && t == 1) && t16_unit(q, iters, uk, un); uk++) {
-            const int g = solo ? un.pair * 128 + row : un.pair * 256 + t * 128 + row;
+        for (int uk = 0; t16_unit(q, iters, uk, un); uk++) {
+            const int g = half ? un.pair * 64 + row : solo ? un.pair * 128 + row : un.pair * 256 + t * 128 + row;
             const long long gchain = p.chain_offset + g;
             const bool live = g < p.C;
             long long tb = p.t_base + (long long)un.it0 * J;
@@ -449,10 +461,10 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     // z16 stream: d normals = d / 16 groups of 3 Philox blocks
                     const unsigned long long grp0 = (unsigned long long)(tb * (d >> 4));
 #pragma unroll 1
-                    for (int q4 = 0; q4 < (d >> 4); q4++) t16_z_group(p.seed, gchain, grp0 + q4, dst, q4);
+                    for (int q4 = part; q4 < (d >> 4); q4 += nparts) t16_z_group(p.seed, gchain, grp0 + q4, dst, q4);
                 } else {
                     const long long z0 = tb * d;
-                    for (int kg = 0; kg < (d >> 3); kg++) {
+                    for (int kg = part; kg < (d >> 3); kg += nparts) {
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
@@ -619,19 +631,20 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         auto wait_mma = [&](uint64_t* bar, uint32_t& ph) {
             if (leader) tc::mbar_wait(bar, ph);
             ph ^= 1;
-            tc::named_bar_sync(3 + t, 256);
+            tc::named_bar_sync(3 + t, nbt);
             tc::fence_after_sync();
         };
-        if (!(solo && t == 1)) tc::mbar_wait(bar_res, 0);   // the data vector arrives with the resident operands
+        const bool idle = (solo && t == 1) || (half && wq >= 2);
+        if (!idle) tc::mbar_wait(bar_res, 0);   // the data vector arrives with the resident operands
 
         T16Unit un;
-        for (int uk = 0; !(solo && t == 1) && t16_unit(q, iters, uk, un); uk++) {
+        for (int uk = 0; !idle && t16_unit(q, iters, uk, un); uk++) {
             const int pair = un.pair;
-            const int g = solo ? pair * 128 + cl : pair * 256 + t * 128 + cl;     // chain slot (padded arrays)
+            const int g = half ? pair * 64 + cl : solo ? pair * 128 + cl : pair * 256 + t * 128 + cl;     // chain slot (padded arrays)
             if (un.blk > 0) {
                 // the previous block of this pair ran on another SM: wait for both of its tiles
                 if (leader) while (t16_ld_acquire(q.progress + pair) < (solo ? 1 : 2) * un.blk) __nanosleep(200);
-                tc::named_bar_sync(3 + t, 256);
+                tc::named_bar_sync(3 + t, nbt);
             }
             const long long gchain = p.chain_offset + g;
             const bool live = g < p.C;
@@ -722,7 +735,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                     sp[h * 128 + cl] = ssq;
                     if (h == 0) su[cl] = u_mine;
                     sbuf ^= 1;
-                    tc::named_bar_sync(1 + t, 256);
+                    tc::named_bar_sync(1 + t, nbt);
                     const float like_p = inv2vc * (sp[cl] + sp[128 + cl]);
                     const float u = su[cl];
                     const float alpha = isnan(like_p) ? 0.0f : expf(like_p - like_c);
@@ -817,7 +830,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 float* su = s_u + (sbuf * 2 + t) * 128;
                 if (h == 0) su[cl] = u2;
                 sbuf ^= 1;
-                tc::named_bar_sync(1 + t, 256);
+                tc::named_bar_sync(1 + t, nbt);
                 const float like_fp = inv2vf * (sf[cl] + sf[256 + cl]);
                 const float prior_p = -0.5f * (q.prior_logconst + (sf[128 + cl] + sf[256 + 128 + cl]));
                 int accf = 0;
@@ -892,7 +905,7 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
             if (q.nb > 1) {
                 // publish the block: state stores -> fence -> tile barrier -> release increment
                 __threadfence();
-                tc::named_bar_sync(3 + t, 256);
+                tc::named_bar_sync(3 + t, nbt);
                 if (leader && lane == 0) t16_red_release_add(q.progress + pair, 1);
             }
         }
@@ -1151,8 +1164,11 @@ struct DaTc16State<float> {
         if (!prepared) { int r = prepare(P, c); if (r) return r; }
         cudaError_t e = cudaSuccess;
         q.n_pairs = P.Cs / 256;
-        q.solo = 0;
-        if (2 * q.n_pairs <= sm_count && !getenv("TDA_TC16_NO_SOLO")) { q.solo = 1; q.n_pairs = P.Cs / 128; }
+        q.solo = 0; q.half = 0;
+        if (2 * q.n_pairs <= sm_count && !getenv("TDA_TC16_NO_SOLO")) {
+            q.solo = 1; q.n_pairs = P.Cs / 128;
+            if (2 * q.n_pairs <= sm_count && !getenv("TDA_TC16_NO_HALF")) { q.half = 1; q.n_pairs = P.Cs / 64; }
+        }
         q.dbg = dDbg;
         const int grid = q.n_pairs < sm_count ? q.n_pairs : sm_count;
         // iteration blocks: the smallest block count (<= 16) whose round-robin deal of the
