@@ -12,6 +12,7 @@
 #include "tda_mh_reg.cuh"
 #include "tda_post.h"
 #include "tda_da_tcr.h"
+#include "tda_dream_warp.h"
 #include <map>
 #include <mutex>
 
@@ -305,7 +306,9 @@ struct EngineT : tda_engine {
     size_t smem_bytes = 0;
     bool initialised = false;
     int kernel_choice = 0;     // 0 auto, 1 generic, 2 tensor-core DA (3xTF32), 3 tensor-core DA (fp16 split),
-                               // 4 register-resident single-level MH
+                               // 4 register-resident single-level MH, 5 tensor-core DA (whitened state),
+                               // 6 warp-per-chain DREAM(Z) / DREAM
+    int dreamw_grid = -1;      // CTAs of the warp-per-chain DREAM kernel (-1: not asked yet, 0: the job does not fit)
     int z_round_user = 0;      // generic / TF32 kernels: use the z16 normal stream (tda_set TDA_G_ZROUND)
     std::vector<int> ldA;
     double* stage_theta = nullptr;   // device staging for the initial states ([C][d] float64)
@@ -898,7 +901,15 @@ struct EngineT : tda_engine {
     bool dream_persistent_ok() const {
         const int occ = (sizeof(R) == 4) ? 2 : 1;
         static const bool off = getenv("TDA_DREAM_PER_STEP_LAUNCH") != nullptr;
+        if (!off && resolved_kernel() == 6) return true;      // its grid is co-resident by construction
         return !off && n_tiles <= sm_count * occ;
+    }
+    // warp-per-chain DREAM(Z) kernel: the configuration fits and every chain gets a register-resident slot
+    bool dreamw_eligible() const {
+        static const bool off = getenv("TDA_NO_DREAM_WARP") != nullptr;
+        if (off || !tda::dream_warp_eligible(cfg)) return false;
+        if (dreamw_grid < 0) const_cast<EngineT*>(this)->dreamw_grid = tda::dream_warp_grid<R>(P, sm_count);
+        return dreamw_grid > 0;
     }
     // 0: every current state fits the fp16-split kernel's theta image, 1: not, < 0: error
     int check_tc16_state_range(cudaStream_t st) {
@@ -925,7 +936,7 @@ struct EngineT : tda_engine {
     // which kernel tda_engine_run launches: 1 generic, 2 tensor-core 3xTF32, 3 tensor-core fp16 split,
     // 4 register-resident single-level
     int resolved_kernel() const {
-        if (kernel_choice >= 1 && kernel_choice <= 5) return kernel_choice;
+        if (kernel_choice >= 1 && kernel_choice <= 6) return kernel_choice;
         // fixed common step size: the fp16-split kernel with the step folded into its operators; per-chain /
         // adaptively scaled steps: the whitened-state kernel (TDA_PREFER_TCR: always the latter when it can)
         static const bool prefer_tcr = getenv("TDA_PREFER_TCR") != nullptr;
@@ -934,6 +945,7 @@ struct EngineT : tda_engine {
         if (tcr_eligible()) return 5;
         if (tc_eligible()) return 2;
         if (reg_eligible()) return 4;
+        if (dreamw_eligible()) return 6;
         return 1;
     }
     // the fp16-split kernel consumes the z16 normal stream; the others do on request
@@ -986,6 +998,7 @@ struct EngineT : tda_engine {
         if (kernel_choice == 3 && !tc16.eligible(cfg, P)) return fail(-1, "run: fp16-split tensor-core DA kernel does not support this configuration");
         if (kernel_choice == 4 && !reg_eligible()) return fail(-1, "run: register-resident kernel does not support this configuration");
         if (kernel_choice == 5 && !tcr.eligible(cfg, P)) return fail(-1, "run: whitened-state tensor-core DA kernel does not support this configuration");
+        if (kernel_choice == 6 && !dreamw_eligible()) return fail(-1, "run: warp-per-chain DREAM kernel does not support this configuration");
         int which = resolved_kernel();
         if (which == 5) {
             // operand images on first use, whitened state when theta was last written by someone else; a
@@ -1063,6 +1076,23 @@ struct EngineT : tda_engine {
             P.mode = tda::MODE_RUN;
             P.iterations = iterations;
             CUDA_TRY(tda::mh_reg_launch<R>(P, st));
+            g_launches++;
+        } else if (which == 6) {
+            // one warp per chain, one persistent launch; the shared-archive variant ends every step in the grid
+            // barrier / peer-memory exchange
+            CUDA_TRY(cudaSetDevice(device));
+            P.mode = tda::MODE_RUN;
+            P.iterations = iterations;
+            P.dream_slots = dream_slots;
+            P.grid_sync = (P.prop_kind == TDA_PROP_DREAM) ? 1 : 0;
+            if (P.grid_sync) {
+                CUDA_TRY(cudaMemsetAsync(P.grid_bar, 0, sizeof(unsigned int), st));
+                P.flag_base = flag_next;
+                flag_next += (unsigned int)iterations;
+            }
+            r = tda::dream_warp_launch<R>(P, dreamw_grid, st);
+            P.grid_sync = 0;
+            if (r) return fail(r, tda::dream_warp_last_error());
             g_launches++;
         } else if (P.prop_kind == TDA_PROP_DREAM && (iterations > 1 || P.n_peers > 1) && dream_persistent_ok()) {
             // shared archive, lock-step visibility (every chain sees all rows through the previous step): ONE

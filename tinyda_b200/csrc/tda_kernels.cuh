@@ -871,7 +871,7 @@ struct Tile {
                 const R* __restrict__ ra = archive_row(r1[i], c, nslots);
                 const R* __restrict__ rb = archive_row(r2[i], c, nslots);
 #pragma unroll 8
-                for (int k = 0; k < d; k++) { zt[k * TC + c] += ra[k]; pt[k * TC + c] += rb[k]; }
+                for (int k = 0; k < d; k++) { zt[k * TC + c] += __ldcg(ra + k); pt[k * TC + c] += __ldcg(rb + k); }   // L2: rows written by other CTAs / GPUs during this launch
             }
             for (int k = 0; k < d; k++) {
                 R e = -p.dream_b + (p.dream_b + p.dream_b) * rs.uniform();
