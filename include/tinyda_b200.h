@@ -294,7 +294,8 @@ int tda_history_reset(tda_engine *e);
  * Delayed-Acceptance kernel with two-term fp16-split operands and normals produced by dedicated
  * warps, 5 = tcgen05 Delayed-Acceptance kernel with whitened chain state and output recursion
  * (tda_da_tcr.cu; per-chain pCN step sizes), 6 = warp-per-chain DREAM(Z) / DREAM kernel (tda_dream_warp.cu:
- * single level, linear model, d <= 32, non-adaptive crossover) (2, 3, 5 and 6 fail if the
+ * single level, linear model, d <= 32, non-adaptive crossover), 7 = warp-per-chain MH / DA / MLDA kernel for the
+ * 1-D Poisson model with the state-independent error model (tda_mlda_warp.cu) (2, 3, 5, 6 and 7 fail if the
  * configuration is not supported).  Kernels 3 and 5 consume the "z16"
  * Philox normal stream (normals rounded to the fp16 grid at scale 4096); tda_fill_streams
  * exports whatever stream the selected kernel consumes. */

@@ -13,6 +13,7 @@
 #include "tda_post.h"
 #include "tda_da_tcr.h"
 #include "tda_dream_warp.h"
+#include "tda_mlda_warp.h"
 #include <map>
 #include <mutex>
 
@@ -308,6 +309,10 @@ struct EngineT : tda_engine {
     int kernel_choice = 0;     // 0 auto, 1 generic, 2 tensor-core DA (3xTF32), 3 tensor-core DA (fp16 split),
                                // 4 register-resident single-level MH, 5 tensor-core DA (whitened state),
                                // 6 warp-per-chain DREAM(Z) / DREAM
+    void* mw_sig = nullptr;    // warp-major images of the error-model matrices (kernel 7), allocated on first use
+    void* mw_li = nullptr;
+    void* mw_phi = nullptr;
+    size_t mw_cls = 0, mw_phi_cls = 0;
     int dreamw_grid = -1;      // CTAs of the warp-per-chain DREAM kernel (-1: not asked yet, 0: the job does not fit)
     int z_round_user = 0;      // generic / TF32 kernels: use the z16 normal stream (tda_set TDA_G_ZROUND)
     std::vector<int> ldA;
@@ -366,6 +371,9 @@ struct EngineT : tda_engine {
             if (s.copied) g_small.put_event(device, s.copied);
         }
         if (copy_stream) g_small.put_stream(device, copy_stream);
+        if (mw_sig) g_pool.release(mw_sig, mw_cls, device);
+        if (mw_li) g_pool.release(mw_li, mw_cls, device);
+        if (mw_phi) g_pool.release(mw_phi, mw_phi_cls, device);
         tc.destroy();
         tc16.destroy();
         tcr.destroy();
@@ -933,10 +941,14 @@ struct EngineT : tda_engine {
     bool tc16_eligible() const { return !tc16_unfit && tc16.eligible(cfg, P); }
     bool tcr_eligible() const { return !tcr_unfit && tcr.eligible(cfg, P); }
     bool reg_eligible() const { return tda::mh_reg_eligible(cfg, P.lv[0].need_F != 0) && !z_round_user; }
+    bool mldaw_eligible() const {
+        static const bool off = getenv("TDA_NO_MLDA_WARP") != nullptr;
+        return !off && !z_round_user && tda::mlda_warp_eligible(cfg);
+    }
     // which kernel tda_engine_run launches: 1 generic, 2 tensor-core 3xTF32, 3 tensor-core fp16 split,
     // 4 register-resident single-level
     int resolved_kernel() const {
-        if (kernel_choice >= 1 && kernel_choice <= 6) return kernel_choice;
+        if (kernel_choice >= 1 && kernel_choice <= 7) return kernel_choice;
         // fixed common step size: the fp16-split kernel with the step folded into its operators; per-chain /
         // adaptively scaled steps: the whitened-state kernel (TDA_PREFER_TCR: always the latter when it can)
         static const bool prefer_tcr = getenv("TDA_PREFER_TCR") != nullptr;
@@ -946,6 +958,7 @@ struct EngineT : tda_engine {
         if (tc_eligible()) return 2;
         if (reg_eligible()) return 4;
         if (dreamw_eligible()) return 6;
+        if (mldaw_eligible()) return 7;
         return 1;
     }
     // the fp16-split kernel consumes the z16 normal stream; the others do on request
@@ -998,6 +1011,7 @@ struct EngineT : tda_engine {
         if (kernel_choice == 3 && !tc16.eligible(cfg, P)) return fail(-1, "run: fp16-split tensor-core DA kernel does not support this configuration");
         if (kernel_choice == 4 && !reg_eligible()) return fail(-1, "run: register-resident kernel does not support this configuration");
         if (kernel_choice == 5 && !tcr.eligible(cfg, P)) return fail(-1, "run: whitened-state tensor-core DA kernel does not support this configuration");
+        if (kernel_choice == 7 && !tda::mlda_warp_eligible(cfg)) return fail(-1, "run: warp-per-chain MLDA kernel does not support this configuration");
         if (kernel_choice == 6 && !dreamw_eligible()) return fail(-1, "run: warp-per-chain DREAM kernel does not support this configuration");
         int which = resolved_kernel();
         if (which == 5) {
@@ -1077,6 +1091,29 @@ struct EngineT : tda_engine {
             P.iterations = iterations;
             CUDA_TRY(tda::mh_reg_launch<R>(P, st));
             g_launches++;
+        } else if (which == 7) {
+            CUDA_TRY(cudaSetDevice(device));
+            if (P.aem && !mw_sig) {
+                mw_cls = DevPool::size_class(tda::mlda_warp_image_elems(P.C) * sizeof(R));
+                cudaError_t e1 = g_pool.alloc(&mw_sig, mw_cls, device);
+                cudaError_t e2 = e1 == cudaSuccess ? g_pool.alloc(&mw_li, mw_cls, device) : e1;
+                if (e1 != cudaSuccess || e2 != cudaSuccess) {
+                    if (mw_sig) { g_pool.release(mw_sig, mw_cls, device); mw_sig = nullptr; }
+                    return fail(-3, std::string("warp-per-chain MLDA kernel: error-model images: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+                }
+                CUDA_TRY(cudaMemsetAsync(mw_sig, 0, mw_cls, st));
+                CUDA_TRY(cudaMemsetAsync(mw_li, 0, mw_cls, st));
+            }
+            if (!mw_phi) {
+                mw_phi_cls = DevPool::size_class(tda::mlda_warp_phi_elems(cfg) * sizeof(R));
+                cudaError_t e3 = g_pool.alloc(&mw_phi, mw_phi_cls, device);
+                if (e3 != cudaSuccess) return fail(-3, std::string("warp-per-chain MLDA kernel: Phi images: ") + cudaGetErrorString(e3));
+            }
+            P.mode = tda::MODE_RUN;
+            P.iterations = iterations;
+            r = tda::mlda_warp_run<R>(P, mw_sig, mw_li, mw_phi, sm_count, st);
+            if (r) return fail(r, tda::mlda_warp_last_error());
+            g_launches += tda::mlda_warp_launches(L, P.aem);
         } else if (which == 6) {
             // one warp per chain, one persistent launch; the shared-archive variant ends every step in the grid
             // barrier / peer-memory exchange

@@ -155,10 +155,10 @@ struct EpiLinear {         // F = v + b; optional store; residual reduction for 
 };
 
 template <typename R>
-struct EpiExpStore {       // Poisson: conductivity field k = exp(Phi theta) -> scratch
+struct EpiExpStore {       // Poisson: inverse conductivity field 1 / k = exp(-Phi theta) -> scratch
     R* kf; int Cs; int chain0;
     __device__ __forceinline__ void operator()(int, int c, int n, R v) {
-        kf[(size_t)n * Cs + chain0 + c] = texp(v);
+        kf[(size_t)n * Cs + chain0 + c] = texp(-v);
     }
 };
 
@@ -397,49 +397,38 @@ struct Tile {
             const int n = v.n_grid;
             R* kf = p.scratch;
             R* cp = p.scratch + (size_t)p.n_max * p.Cs;
-            R* dp = p.scratch + (size_t)2 * p.n_max * p.Cs;
             EpiExpStore<R> e;
             e.kf = kf; e.Cs = p.Cs; e.chain0 = chain0;
             tile_gemm<R>(pt, (const R*)nullptr, v.A, d, n, v.ldA, bs, KB, e);
             __syncthreads();
             if (tid < TC) {
-                const int c = tid, nn = n - 1;
-                // the three scratch arrays never alias: telling the compiler lets it issue the loads of
-                // a sweep ahead of the recurrence (only the divide / FMA chain stays serial)
+                // -(k u')' = 1, u(0) = u(1) = 0 in one dimension: the flux in cell i is q_i = q_0 - i h^2, so u at node j
+                // is sum_{i<j} q_i / k_i and u(1) = 0 fixes q_0 = h^2 sum(i / k_i) / sum(1 / k_i).  Algebraically the
+                // solution of the tridiagonal system models.py solves with the Thomas algorithm, but two running sums
+                // instead of a division recurrence whose pivots cancel: in float32 the Thomas sweeps lose 3-4 digits
+                // on a 512-cell grid (2.6e-4 relative against float64), these sums stay at rounding level.  The cell
+                // index is centred (i - n/2) to keep the two terms of u small.
+                const int c = tid;
                 const size_t Cs = (size_t)p.Cs;
-                const R* __restrict__ kfc = kf + chain0 + c;
-                R* __restrict__ cpc = cp + chain0 + c;
-                R* __restrict__ dpc = dp + chain0 + c;
-                const R h2 = (R)1 / ((R)n * (R)n);
-                R k0 = kfc[0], k1 = kfc[Cs];
-                R diag = k0 + k1;
-                R cprev = -k1 / diag, dprev = h2 / diag;
-                cpc[0] = cprev; dpc[0] = dprev;
-                R ki = k1;
-#pragma unroll 4
-                for (int i = 1; i < nn; i++) {
-                    R kn = kfc[(size_t)(i + 1) * Cs];
-                    R a = -ki;
-                    diag = (ki + kn) - a * cprev;
-                    cprev = -kn / diag;
-                    dprev = (h2 - a * dprev) / diag;
-                    cpc[(size_t)i * Cs] = cprev; dpc[(size_t)i * Cs] = dprev;
-                    ki = kn;
-                }
-                R u = dprev;     // u[nn-1]
+                const R* __restrict__ rfc = kf + chain0 + c;          // 1 / k_i
+                R* __restrict__ p1c = cp + chain0 + c;                // prefix sums of (i - n/2) / k_i at the sensors
+                const R h2 = (R)1 / ((R)n * (R)n), c0 = (R)(n / 2);
                 const int stride = v.stride;
-                // sensors sit on nodes (s+1)*stride, i.e. unknown index (s+1)*stride-1
-                if ((nn - 1 + 1) % stride == 0) { int s = (nn) / stride - 1; if (s < v.m) v.Fp[gi(s, c)] = u; }
-                int next_sensor = ((nn - 1) / stride) * stride - 1;      // largest sensor index <= nn-2
+                R P0 = (R)0, P1 = (R)0;
+                int s = 0, next = stride;
 #pragma unroll 4
-                for (int i = nn - 2; i >= 0; i--) {
-                    u = dpc[(size_t)i * Cs] - cpc[(size_t)i * Cs] * u;
-                    if (i == next_sensor) {
-                        int s = (i + 1) / stride - 1;
-                        if (s < v.m) v.Fp[gi(s, c)] = u;
-                        next_sensor -= stride;
+                for (int i = 0; i < n; i++) {
+                    const R r = rfc[(size_t)i * Cs];
+                    P0 += r;
+                    P1 = fma((R)i - c0, r, P1);
+                    if (i + 1 == next) {
+                        if (s < v.m) { v.Fp[gi(s, c)] = P0; p1c[(size_t)s * Cs] = P1; }
+                        s++;
+                        next += stride;
                     }
                 }
+                const R q = P1 / P0;
+                for (int j = 0; j < v.m; j++) v.Fp[gi(j, c)] = h2 * (q * v.Fp[gi(j, c)] - p1c[(size_t)j * Cs]);
                 if (v.lik_kind != TDA_LIK_ADAPTIVE) s_like[tid] = loglike_from_F(l, v.Fp, tid);
             }
             if (v.lik_kind == TDA_LIK_ADAPTIVE) { __syncthreads(); loglike_adaptive_tile(l, v.Fp, s_like); }

@@ -354,14 +354,15 @@ class Engine:
     def select_kernel(self, which):
         """"auto" | "generic" | "tc" (tcgen05, 3xTF32) | "tc16" (tcgen05, fp16 split + RNG warps) |
         "tcr" (tcgen05, whitened state + output recursion) | "reg" (register-resident single-level kernel, d <= 8) |
-        "dreamw" (warp-per-chain DREAM(Z) / DREAM, d <= 32)."""
-        check(lib.tda_select_kernel(self._h, {"auto": 0, "generic": 1, "tc": 2, "tc16": 3, "reg": 4, "tcr": 5, "dreamw": 6}[which]))
+        "dreamw" (warp-per-chain DREAM(Z) / DREAM, d <= 32) | "mldaw" (warp-per-chain MH / DA / MLDA on the 1-D Poisson
+        model, state-independent error model).""" 
+        check(lib.tda_select_kernel(self._h, {"auto": 0, "generic": 1, "tc": 2, "tc16": 3, "reg": 4, "tcr": 5, "dreamw": 6, "mldaw": 7}[which]))
 
     def kernel(self):
         """Name of the kernel `run` launches for this configuration."""
         out = np.zeros(1, dtype=np.int64)
         check(lib.tda_get(self._h, L.TDA_G_KERNEL, 0, out.ctypes.data_as(C.c_void_p), out.nbytes))
-        return {1: "generic", 2: "tc", 3: "tc16", 4: "reg", 5: "tcr", 6: "dreamw"}[int(out[0])]
+        return {1: "generic", 2: "tc", 3: "tc16", 4: "reg", 5: "tcr", 6: "dreamw", 7: "mldaw"}[int(out[0])]
 
     def set_z_round(self, on=True):
         """Philox normals on the fp16 grid (the "z16" stream the tc16 kernel consumes) also for the
