@@ -34,7 +34,7 @@ namespace {
 constexpr int MW_LIS = 33;     // row stride of an inverse-factor image: element (i, j) at j * 33 + i
 constexpr int MW_M = 31;       // matrices are padded to 31 x 31 (identity outside m x m)
 
-enum { V_TH = 0, V_F, V_BIAS, V_MD, V_BMU, V_SVF, NVEC = V_SVF + MAXL };
+enum { V_TH = 0, V_F, V_BIAS, V_MD, V_BMU, V_SVF, NVEC = V_SVF + MAXL - 1 };     // V_SVF + a - 1: saved output of level a >= 1
 enum { S_PRIOR = 0, S_LIKE, S_SVP, S_SVL = S_SVP + MAXL, NSC = S_SVL + MAXL };
 enum { I_SID = 0, I_ACCSUB, I_NACC, I_REC, NIS };     // I_REC: records written / steps taken by the level in this launch
 
@@ -283,17 +283,17 @@ struct Mw {
             if (acc) {
                 setS(j, S_SVP + l, S(j, S_PRIOR));
                 setS(j, S_SVL + l, S(j, S_LIKE));
-                V(j, V_SVF + l) = V(j, V_F);
+                V(j, V_SVF + l - 1) = V(j, V_F);
             } else {
                 const R sp = S(j, S_SVP + l), sl = S(j, S_SVL + l);
                 const int sid = I(l, I_SID);
                 __syncwarp();
                 setS(j, S_PRIOR, sp); setS(j, S_LIKE, sl);
                 setI(j, I_SID, sid);
-                const R f = V(j, V_SVF + l);
+                const R f = V(j, V_SVF + l - 1);
                 V(j, V_F) = f;
                 V(j, V_TH) = V(l, V_TH);
-                for (int a = j + 1; a < l; a++) { setS(j, S_SVP + a, sp); setS(j, S_SVL + a, sl); V(j, V_SVF + a) = f; }
+                for (int a = j + 1; a < l; a++) { setS(j, S_SVP + a, sp); setS(j, S_SVL + a, sl); V(j, V_SVF + a - 1) = f; }
             }
             setI(j, I_ACCSUB, 0);
         }
@@ -357,7 +357,8 @@ struct Mw {
                 if (nlev > 2) sg += sg0[2 * MW_MATW + k * 32];
                 const bool in = row && k < m;
                 if (in && k <= lane && !(sg < (R)1e-9)) big = 1;
-                acol[k * 32 + lane] = in ? sg + __ldg(lo.cov + lane * m + k) : ((k == lane) ? (R)1 : (R)0);
+                // lower triangle only (zeros above the diagonal: the in-place inverse below relies on them)
+                acol[k * 32 + lane] = (in && k <= lane) ? sg + __ldg(lo.cov + lane * m + k) : ((k == lane) ? (R)1 : (R)0);
             }
         }
         big = __any_sync(0xffffffffu, big);
@@ -366,14 +367,18 @@ struct Mw {
             __syncwarp();
             // Cholesky, left-looking, in place: column j of the factor from the lane's own row and row j (broadcast)
             for (int j = 0; j < MW_M; j++) {
-                R s0 = acol[j * 32 + lane], s1 = (R)0;
+                R s0 = acol[j * 32 + lane], s1 = (R)0, s2 = (R)0, s3 = (R)0;
+                const R* own = acol + lane;
+                const R* piv = acol + j;
                 int k = 0;
-                for (; k + 1 < j; k += 2) {
-                    s0 -= acol[k * 32 + lane] * acol[k * 32 + j];
-                    s1 -= acol[(k + 1) * 32 + lane] * acol[(k + 1) * 32 + j];
+                for (; k + 3 < j; k += 4) {
+                    s0 -= own[k * 32] * piv[k * 32];
+                    s1 -= own[(k + 1) * 32] * piv[(k + 1) * 32];
+                    s2 -= own[(k + 2) * 32] * piv[(k + 2) * 32];
+                    s3 -= own[(k + 3) * 32] * piv[(k + 3) * 32];
                 }
-                if (k < j) s0 -= acol[k * 32 + lane] * acol[k * 32 + j];
-                const R s = s0 + s1;
+                for (; k < j; k++) s0 -= own[k * 32] * piv[k * 32];
+                const R s = (s0 + s1) + (s2 + s3);
                 R djj = __shfl_sync(0xffffffffu, s, j);
                 // a non-positive pivot (near-singular bias covariance in this dtype) is clamped and flagged; the
                 // reference's np.linalg.inv does not fail there (distributions.py:402)
@@ -388,14 +393,22 @@ struct Mw {
             // Li[i][j] = -(sum_{k = j+1..i} Li[i][k] L[k][j]) Li[j][j]   (rows of the already inverted trailing block)
             for (int j = MW_M - 1; j >= 0; j--) {
                 const R dj = (R)1 / acol[j * 32 + j];
-                R s0 = (R)0, s1 = (R)0;
-                if (lane > j) {
+                R s0 = (R)0, s1 = (R)0, s2 = (R)0, s3 = (R)0;
+                {
+                    // every lane runs the loop of the last row (uniform trip count); rows above the diagonal of the
+                    // trailing block hold zeros, so the extra terms of the shorter rows vanish
+                    const R* own = acol + lane;
+                    const R* col = acol + j * 32;
                     int k = j + 1;
-                    for (; k + 1 <= lane; k += 2) {
-                        s0 -= acol[k * 32 + lane] * acol[j * 32 + k];
-                        s1 -= acol[(k + 1) * 32 + lane] * acol[j * 32 + k + 1];
+                    for (; k + 3 < MW_M; k += 4) {
+                        s0 -= own[k * 32] * col[k];
+                        s1 -= own[(k + 1) * 32] * col[k + 1];
+                        s2 -= own[(k + 2) * 32] * col[k + 2];
+                        s3 -= own[(k + 3) * 32] * col[k + 3];
                     }
-                    if (k <= lane) s0 -= acol[k * 32 + lane] * acol[j * 32 + k];
+                    for (; k < MW_M; k++) s0 -= own[k * 32] * col[k];
+                    s0 = (s0 + s1) + (s2 + s3);
+                    s1 = (R)0;
                 }
                 __syncwarp();
                 if (lane >= j) acol[j * 32 + lane] = (lane == j) ? dj : (s0 + s1) * dj;
@@ -519,7 +532,7 @@ __global__ void __launch_bounds__(MW_MAXW * 32, 1) mlda_warp_kernel(const __grid
             c.V(l, V_MD) = (up && lane < m) ? v.model_diff[(size_t)lane * Cs + g] : (R)0;
             c.V(l, V_BMU) = (up && lane < m) ? v.bias_mu[(size_t)lane * Cs + g] : (R)0;
             for (int a = 0; a < MAXL; a++)
-                c.V(l, V_SVF + a) = (a > l && a < L && lane < m) ? v.sv_F[a][(size_t)lane * Cs + g] : (R)0;
+                if (a >= 1) c.V(l, V_SVF + a - 1) = (a > l && a < L && lane < m) ? v.sv_F[a][(size_t)lane * Cs + g] : (R)0;
             if (lane == 0) {
                 c.sc[l * NSC + S_PRIOR] = v.prior[g];
                 c.sc[l * NSC + S_LIKE] = v.like[g];
@@ -574,7 +587,7 @@ __global__ void __launch_bounds__(MW_MAXW * 32, 1) mlda_warp_kernel(const __grid
                     v.model_diff[(size_t)lane * Cs + g] = c.V(l, V_MD);
                     v.bias_mu[(size_t)lane * Cs + g] = c.V(l, V_BMU);
                 }
-                for (int a = l + 1; a < L; a++) v.sv_F[a][(size_t)lane * Cs + g] = c.V(l, V_SVF + a);
+                for (int a = l + 1; a < L; a++) v.sv_F[a][(size_t)lane * Cs + g] = c.V(l, V_SVF + a - 1);
             }
             if (lane == 0) {
                 v.prior[g] = c.sc[l * NSC + S_PRIOR];
@@ -670,10 +683,10 @@ int mlda_warp_run(Params<R>& P, void* sigw, void* liw, void* phiw, int sm_count,
     const int L = P.L;
     MwParams mp;
     mp.sigw = sigw; mp.liw = liw; mp.phiw = phiw;
-    // Phi images; the coarse levels' go to shared memory while they fit into 16 KB
+    // Phi images; the coarsest level(s) go to shared memory while they fit into 1024 elements
     int cta_elems = 2 * 32 * 32, off = 0;
     const int d4 = (P.d + 3) / 4 * 4;
-    const int budget = cta_elems + (int)(16 * 1024 / sizeof(R));
+    const int budget = cta_elems + 1024;     // the coarsest level of a cfg4-sized problem; more would cost resident warps
     for (int l = 0; l < MAXL; l++) { mp.phi_off[l] = 0; mp.phi_elems[l] = 0; mp.phi_smem[l] = -1; }
     for (int l = 0; l < L; l++) {
         const LevelP<R>& v = P.lv[l];

@@ -7,7 +7,7 @@
 
 namespace tda {
 
-constexpr int MW_MAXW = 12;      // warps (= chains in flight) per CTA at most
+constexpr int MW_MAXW = 16;      // warps (= chains in flight) per CTA at most
 constexpr int MW_MATW = 1024;    // elements of one warp-major matrix image (31 x 32 / 31 x 33, padded)
 
 struct MwParams {
