@@ -405,9 +405,9 @@ struct EngineT : tda_engine {
     int create() {
         const tda_config& c = cfg;
         CUDA_TRY(cudaSetDevice(device));
-        cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-        sm_count = prop.multiProcessorCount;
+        // one attribute, not cudaGetDeviceProperties: that call also reads clocks and bus state through the driver and
+        // was measured at 3-70 ms, erratically, inside every tda.sample() call
+        CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
         memset(&P, 0, sizeof(P));
         const int L = c.n_levels, d = c.d;
         P.L = L; P.d = d; P.aem = c.aem; P.rng_mode = c.rng_mode; P.prop_kind = c.prop_kind;

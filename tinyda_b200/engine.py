@@ -177,7 +177,10 @@ class Engine:
             self.capacity.append(int(lc.hist_capacity))
         self.cfg = cfg
         self._h = C.c_void_p()
+        import os, time
+        _t0 = time.perf_counter()
         check(lib.tda_engine_create(C.byref(cfg), self.device, C.byref(self._h)))
+        _t1 = time.perf_counter()
 
         # constants
         pr = spec["prior"]
@@ -224,6 +227,9 @@ class Engine:
             self._up(L.TDA_UP_DREAM_ARCHIVE0, 0, archive0)
         self.iterations_done = 0
         self.peers_connected = False
+        if os.environ.get("TDA_PROFILE"):
+            import sys
+            sys.stderr.write("[Engine] tda_engine_create %.2f ms, uploads %.2f ms\n" % ((_t1 - _t0) * 1e3, (time.perf_counter() - _t1) * 1e3))
 
     # ---- plumbing --------------------------------------------------------------------------
     def _up(self, what, level, arr):

@@ -183,6 +183,7 @@ def sample(
                          adaptive_error_model if n_levels > 1 else None,
                          randomize_subchain_length if n_levels == 2 else False)
     kind = int(spec["proposal"]["kind"])
+    _lap("lowering")
 
     archive0 = None
     if kind in (PROP_DREAMZ, PROP_DREAM):
@@ -229,7 +230,7 @@ def sample(
         raise
     if shared and world > 1:
         parallel.connect_dream_peers(eng, rank, world)      # in-kernel archive exchange over NVLink peer memory
-    _lap("lowering + engine construction")
+    _lap("engine construction")
     print("Sampling {} chains in lock-step on GPU {}".format(n_chains, device))
     eng.init(theta0)
     _lap("init (H2D + initial Links, enqueue)")
