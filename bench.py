@@ -587,7 +587,9 @@ def _other_workload(name, world):
         cfgd = dict(chains=32768, iters=4, bytes_unit=(d + 2) * s + 1, flop_unit=float(flop), bound="fp32", store="stats")
     elif name == "cfg5":
         m = spec["levels"][0]["model"]["m"]
-        cfgd = dict(chains=8192 // world, iters=50, bytes_unit=(d + 2) * s + 1 + 3 * d * s, flop_unit=2.0 * d * m,
+        # 500 lock-step steps per launch: the ranks' persistent kernels wait for each other from their first step on, so
+        # the host-side launch skew between the processes (hundreds of microseconds) is part of every timed launch
+        cfgd = dict(chains=8192 // world, iters=500, bytes_unit=(d + 2) * s + 1 + 3 * d * s, flop_unit=2.0 * d * m,
                     bound="latency", store="stats")
     else:
         raise SystemExit("unknown workload " + name)
@@ -626,7 +628,7 @@ def run_other(args):
     store = [STORE_NONE] * (L - 1) + [STORE_FULL if cd["store"] == "full" else STORE_STATS]
     stream = torch.cuda.current_stream().cuda_stream
     eng = Engine(spec, C, dtype=args.dtype, rng="philox", seed=2024, store=store,
-                 capacity_iterations=iters if not shared else iters * total_runs + 64, device=local_rank,
+                 capacity_iterations=iters, archive_iterations=(iters * total_runs + 64) if shared else None, device=local_rank,
                  chain_offset=rank * C, n_chains_global=world * C if shared else C, archive0=archive0, stream=stream)
     eng.init(theta0)
     exchange = None

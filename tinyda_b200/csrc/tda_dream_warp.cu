@@ -107,9 +107,13 @@ __device__ __forceinline__ void dw_step_barrier(const Params<R>& p, unsigned ste
         } while (v < target);
         if (p.n_peers > 1) {
             const unsigned flag = p.flag_base + step + 1u;
-            if (blockIdx.x == 0)
+            if (blockIdx.x == 0) {
+                // one system-scope fence, then the eight flag stores back to back: a release store per peer would wait
+                // for the previous peer's store to be acknowledged over NVLink (measured: 19 us per step on 8 GPUs)
+                __threadfence_system();
                 for (int r = 0; r < p.n_peers; r++)
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flags[r] + p.my_rank), "r"(flag) : "memory");
+                    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.peer_flags[r] + p.my_rank), "r"(flag) : "memory");
+            }
             for (int r = 0; r < p.n_peers; r++) {
                 const unsigned* f = p.peer_flags[p.my_rank] + r;
                 do {

@@ -21,3 +21,7 @@ for rep in range(3):
     eng.history_reset()
     t0 = time.perf_counter(); eng.run(iters); eng.sync(); dt = time.perf_counter() - t0
     print("%s: %d chains x %d iterations in %.3f ms -> %.1f M transitions/s" % (eng.kernel(), C, iters, dt * 1e3, C * iters / dt / 1e6))
+if os.environ.get("NOSTORE"):
+    for rep in range(3):
+        t0 = time.perf_counter(); eng.run(iters, record=False); eng.sync(); dt = time.perf_counter() - t0
+        print("%s, unrecorded: %d chains x %d iterations in %.3f ms -> %.1f M transitions/s" % (eng.kernel(), C, iters, dt * 1e3, C * iters / dt / 1e6))
