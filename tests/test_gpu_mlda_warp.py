@@ -173,3 +173,44 @@ def test_warp_kernel_fp32_follows_the_fp64_run_until_a_near_tie():
     assert matched >= 0.5 * total
     assert worst <= 1e-5
     assert ferr <= 2e-5
+
+
+@pytest.mark.parametrize("levels,aem,msens,d,pcn", [(1, False, 7, 3, False), (2, True, 15, 5, True), (3, True, 3, 6, False),
+                                                    (2, False, 31, 2, True)])
+def test_other_shapes_agree_with_the_lockstep_kernel(levels, aem, msens, d, pcn):
+    """Single-level MH, two-level DA and three-level MLDA on the Poisson model with fewer sensors than lanes, parameter
+    counts that are not multiples of four, a dense prior covariance and both base proposals (the matvec path instead
+    of the diagonal shortcut): float64, same decisions and states as the lock-step kernel."""
+    import scipy.stats as stats
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.distributions import GaussianLogLike, AdaptiveGaussianLogLike
+    from tinyda_b200.models import Poisson1D
+    from tinyda_b200.posterior import Posterior
+    from tinyda_b200.proposal import CrankNicolson, GaussianRandomWalk
+    rng = np.random.default_rng(levels * 10 + msens)
+    A = rng.standard_normal((d, d))
+    cov = 0.3 * (A @ A.T / d + np.eye(d))
+    prior = stats.multivariate_normal(np.zeros(d), cov)
+    ns = [(msens + 1) * s for s in (1, 2, 4)][:levels]
+    truth = 0.5 * prior.rvs(random_state=rng)
+    sig = 2e-3
+    y = Poisson1D((msens + 1) * 8, d, msens)(truth) + sig * rng.standard_normal(msens)
+    posts = []
+    for i, n in enumerate(ns):
+        lk = (AdaptiveGaussianLogLike(y, sig ** 2 * np.eye(msens)) if (aem and i < levels - 1)
+              else GaussianLogLike(y, sig ** 2 * np.eye(msens)))
+        posts.append(Posterior(prior, lk, Poisson1D(n, d, msens)))
+    prop = CrankNicolson(scaling=0.08) if pcn else GaussianRandomWalk(C=2e-4 * cov)
+    J = [4, 3][:levels - 1]
+    spec = lower_problem(posts, prop, J if levels > 1 else None, "state-independent" if aem else None)
+    theta0 = 0.3 * np.atleast_2d(prior.rvs(70, random_state=rng)).reshape(70, d)
+    iters = 40 if levels == 1 else 6
+    a = _run(spec, theta0, [("mldaw", iters)], "float64")
+    b = _run(spec, theta0, [("generic", iters)], "float64")
+    assert np.array_equal(a["cursors"], b["cursors"])
+    for l in range(levels):
+        assert np.array_equal(a[l]["acc"], b[l]["acc"]), "level %d decisions" % l
+        np.testing.assert_allclose(a[l]["theta"], b[l]["theta"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(a[l]["F"], b[l]["F"], rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(a[l]["like"], b[l]["like"], rtol=1e-6, atol=1e-6)
+    assert 0.02 < a[0]["acc"][1:].mean() < 0.999
