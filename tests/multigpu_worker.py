@@ -52,6 +52,26 @@ def main(outdir):
     assert np.array_equal(mine, one[lo:hi]), "sharded DREAM differs from the single-engine run"
     assert np.abs(np.diff(mine, axis=1)).max() > 0
 
+    # ---- the same exchange on the lock-step kernel (flag handshake instead of arrival counters; it serves the
+    # adaptive crossover distribution and d > 32), engines driven directly ----
+    lo_g, hi_g = parallel.shard_range(C, rank, world)
+    eg = Engine(spec, hi_g - lo_g, dtype="float32", seed=9, store=STORE_STATS, capacity_iterations=iters, device=local,
+                chain_offset=lo_g, n_chains_global=C, archive0=archive0)
+    eg.select_kernel("generic")
+    assert parallel.connect_dream_peers(eg, rank, world)
+    eg.init(theta0[lo_g:hi_g])
+    parallel.run_dream_shared(eg, iters, rank, world)
+    mine_g = np.transpose(eg.fetch(0, "theta"), (2, 0, 1))
+    dist.barrier()
+    eg.close()
+    eng = Engine(spec, C, dtype="float32", seed=9, store=STORE_STATS, capacity_iterations=iters, device=local, archive0=archive0)
+    eng.select_kernel("generic")
+    eng.init(theta0)
+    eng.run(iters)
+    one_g = np.transpose(eng.fetch(0, "theta"), (2, 0, 1))
+    eng.close()
+    assert np.array_equal(mine_g, one_g[lo_g:hi_g]), "sharded DREAM (lock-step kernel) differs from the single-engine run"
+
     # ---- Delayed Acceptance, chains sharded by sample() ------------------------------------------
     w2 = workloads.cfg2_da()
     C2, it2 = 1024, 6

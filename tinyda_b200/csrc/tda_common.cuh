@@ -154,6 +154,12 @@ struct Params {
     R* peer_archive[8];            // [rank] -> that rank's archive replica (own entry = archive)
     unsigned int* peer_flags[8];   // [rank] -> that rank's flag array [8] (one slot per writer rank)
     unsigned int flag_base;        // flags count steps across launches: value after step t of this launch = flag_base + t + 1
+    // warp-per-chain DREAM kernel on several GPUs: every CTA of every rank adds 1 to arrival counter [8 + its rank] of
+    // every GPU's flag array after each step (one fence, no local barrier first); a step is complete on a GPU when
+    // counter [8 + r] has reached (arr_base + t + 1) * peer_grid[r] for every rank r
+    int arrive_mode;
+    unsigned int arr_base;
+    int peer_grid[8];
     LevelP<R> lv[MAXL];
 };
 

@@ -95,6 +95,27 @@ __device__ __forceinline__ void dw_eval(const Params<R>& p, const DwShared<R>& s
 template <typename R>
 __device__ __forceinline__ void dw_step_barrier(const Params<R>& p, unsigned step) {
     __syncthreads();
+    if (p.arrive_mode) {
+        // several GPUs, every rank on this kernel: ONE system-scope fence per CTA, then an arrival on every GPU's
+        // counter of this rank (remote reductions over NVLink, own GPU included), then wait until every rank's CTAs
+        // have all arrived here.  No local barrier in front, no second fence behind it.
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            for (int r = 0; r < p.n_peers; r++)
+                asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p.peer_flags[r] + 8 + p.my_rank), "r"(1u) : "memory");
+            for (int r = 0; r < p.n_peers; r++) {
+                const unsigned target = (p.arr_base + step + 1u) * (unsigned)p.peer_grid[r];
+                const unsigned* f = p.peer_flags[p.my_rank] + 8 + r;
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                    if ((int)(v - target) < 0) __nanosleep(20);
+                } while ((int)(v - target) < 0);
+            }
+        }
+        __syncthreads();
+        return;
+    }
     if (threadIdx.x == 0) {
         if (p.n_peers > 1) __threadfence_system();
         else __threadfence();

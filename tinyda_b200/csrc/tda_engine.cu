@@ -332,6 +332,7 @@ struct EngineT : tda_engine {
     bool burning = false;      // inside tda_engine_burn: nothing is recorded
     unsigned int* dream_flags = nullptr;   // [8] step flags written by the peers (shared-archive DREAM over several GPUs)
     unsigned int flag_next = 0;            // flag value of the next persistent launch's first step, minus one
+    unsigned int arr_next = 0;             // lock-step steps the warp-per-chain kernel has run with arrival counters
     std::vector<void*> peer_mapped;        // cudaIpcOpenMemHandle results
     // quantities of interest: qoi = Q @ F(theta) + q0 per level.  Linear models: composed with the operator
     // on upload (qoi_W = G^T Q^T [d][ldq], qoi_b = Q b + q0) so that Link.qoi comes straight from theta
@@ -469,7 +470,7 @@ struct EngineT : tda_engine {
         DALLOC(P.grid_bar, 1);
         if (tda::is_dream(c.prop_kind)) {
             DALLOC(P.archive, (size_t)c.dream_capacity * P.Cg * d);
-            DALLOC(dream_flags, 8);
+            DALLOC(dream_flags, 16);        // [0..8): step flags per writer rank, [8..16): arrival counters per writer rank
             dream_slots = c.dream_M0;
             if (c.adaptive) {
                 DALLOC(P.dream_pCR, (size_t)tda::MAX_NCR * Cs);
@@ -1124,10 +1125,18 @@ struct EngineT : tda_engine {
             P.grid_sync = (P.prop_kind == TDA_PROP_DREAM) ? 1 : 0;
             if (P.grid_sync) {
                 CUDA_TRY(cudaMemsetAsync(P.grid_bar, 0, sizeof(unsigned int), st));
-                P.flag_base = flag_next;
-                flag_next += (unsigned int)iterations;
+                if (P.n_peers > 1 && P.arrive_mode) {
+                    P.arr_base = arr_next;
+                    arr_next += (unsigned int)iterations;
+                } else {
+                    P.flag_base = flag_next;
+                    flag_next += (unsigned int)iterations;
+                }
             }
+            const int arrive_saved = P.arrive_mode;
+            if (P.n_peers <= 1) P.arrive_mode = 0;
             r = tda::dream_warp_launch<R>(P, dreamw_grid, st);
+            P.arrive_mode = arrive_saved;
             P.grid_sync = 0;
             if (r) return fail(r, tda::dream_warp_last_error());
             g_launches++;
@@ -1431,6 +1440,8 @@ struct EngineT : tda_engine {
     // ---- shared archive over several GPUs: the replicas and the step flags are mapped into each other ----
     struct PeerHandles {
         cudaIpcMemHandle_t archive, flags;
+        int dreamw_grid;          // CTAs of this rank's warp-per-chain DREAM kernel (0: it runs the lock-step kernel)
+        int pad[15];
     };
     int peer_export(void* out, size_t bytes, size_t* needed) override {
         CUDA_TRY(cudaSetDevice(device));
@@ -1441,6 +1452,8 @@ struct EngineT : tda_engine {
         PeerHandles h;
         CUDA_TRY(cudaIpcGetMemHandle(&h.archive, P.archive));
         CUDA_TRY(cudaIpcGetMemHandle(&h.flags, dream_flags));
+        memset(h.pad, 0, sizeof(h.pad));
+        h.dreamw_grid = (resolved_kernel() == 6) ? dreamw_grid : 0;
         memcpy(out, &h, sizeof(h));
         return 0;
     }
@@ -1466,6 +1479,14 @@ struct EngineT : tda_engine {
             P.peer_flags[r] = reinterpret_cast<unsigned int*>(f);
         }
         P.n_peers = n_ranks; P.my_rank = my_rank;
+        // arrival counters instead of the barrier + flag handshake when every rank runs the warp-per-chain kernel
+        P.arrive_mode = 1;
+        for (int r = 0; r < 8; r++) P.peer_grid[r] = 0;
+        for (int r = 0; r < n_ranks; r++) {
+            P.peer_grid[r] = h[r].dreamw_grid;
+            if (h[r].dreamw_grid <= 0) P.arrive_mode = 0;
+        }
+        if (getenv("TDA_DREAM_FLAG_HANDSHAKE")) P.arrive_mode = 0;
         return 0;
     }
 

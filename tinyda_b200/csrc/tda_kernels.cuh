@@ -1454,9 +1454,11 @@ struct Tile {
             } while (v < target);
             if (p.n_peers > 1) {
                 const unsigned flag = p.flag_base + step + 1u;
-                if (blockIdx.x == 0)
+                if (blockIdx.x == 0) {
+                    __threadfence_system();          // one fence, then the flag stores back to back (not a release per peer)
                     for (int r = 0; r < p.n_peers; r++)
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flags[r] + p.my_rank), "r"(flag) : "memory");
+                        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.peer_flags[r] + p.my_rank), "r"(flag) : "memory");
+                }
                 for (int r = 0; r < p.n_peers; r++) {
                     const unsigned* f = p.peer_flags[p.my_rank] + r;
                     do {

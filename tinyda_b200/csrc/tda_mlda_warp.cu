@@ -350,7 +350,7 @@ struct Mw {
             const bool row = lane < m;
             const R* sg0 = sigw + (size_t)l * MW_MATW + lane;
             const int nlev = kend - l + 1;
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < MW_M; k++) {
                 R sg = sg0[k * 32];
                 if (nlev > 1) sg += sg0[MW_MATW + k * 32];
@@ -387,12 +387,13 @@ struct Mw {
                 const R inv = (R)1 / djj;
                 __syncwarp();
                 if (lane >= j) acol[j * 32 + lane] = (lane == j) ? djj : s * inv;
+                if (lane == j) dinv[j] = inv;
                 __syncwarp();
             }
             // inverse of the factor, in place, last column first: Li[j][j] = 1 / L[j][j],
             // Li[i][j] = -(sum_{k = j+1..i} Li[i][k] L[k][j]) Li[j][j]   (rows of the already inverted trailing block)
             for (int j = MW_M - 1; j >= 0; j--) {
-                const R dj = (R)1 / acol[j * 32 + j];
+                const R dj = dinv[j];                      // 1 / L[j][j], kept from the factorisation
                 R s0 = (R)0, s1 = (R)0, s2 = (R)0, s3 = (R)0;
                 {
                     // every lane runs the loop of the last row (uniform trip count); rows above the diagonal of the

@@ -113,7 +113,7 @@ def connect_dream_peers(eng, rank, world):
     try:
         mine = eng.peer_export()
     except Exception:
-        mine, ok = np.zeros(128, dtype=np.uint8), 0
+        mine, ok = np.zeros(192, dtype=np.uint8), 0
     dev = "cuda:%d" % eng.device
     t = torch.from_numpy(mine.copy()).to(dev)
     allb = torch.empty(world * t.numel(), dtype=torch.uint8, device=dev)
