@@ -1,7 +1,8 @@
-// MH / Delayed Acceptance / MLDA on the 1-D Poisson model with the state-independent adaptive error model,
-// one WARP per chain (BASELINE cfg4 class): up to 4 levels, random-walk or pCN base proposal with a fixed step,
-// Gaussian likelihoods (isotropic / diagonal on any level, AdaptiveGaussianLogLike below the finest level),
-// at most 31 sensors and 32 parameters.
+// MH / Delayed Acceptance / MLDA with the state-independent adaptive error model, one WARP per chain (BASELINE cfg4
+// class and the small problems of the reference's notebooks): up to 4 levels, the 1-D Poisson model or a linear
+// operator per level, random-walk or pCN base proposal (fixed or adaptively scaled step), Gaussian likelihoods
+// (isotropic / diagonal on any level, AdaptiveGaussianLogLike below the finest level), at most 31 outputs per level
+// and 32 parameters.
 // Reference semantics: chain.py:680-769 + proposal.py:1502-1613 (the recursive MLDA proposal), chain.py:485-499 and
 // proposal.py:1442-1467 (state-independent error model), utils.py:113-124 (RecursiveSampleMoments),
 // distributions.py:332-449 (AdaptiveGaussianLogLike.set_bias) -- step for step what Tile::base_step /
@@ -89,7 +90,9 @@ struct Mw {
     R dT, dLP;
     R* sigw;      // this chain's bias covariances, [level][k * 32 + i]
     R* liw;       // this chain's inverse factors,  [level][j * 33 + i]
-    long long t_base, ucur;
+    long long t_base, ucur, wcount;
+    R scal;                 // proposal step of this chain (adapted when the proposal is adaptive, proposal.py:228-245)
+    int win_sum, win_old;   // sum over the accept window; ring entry that the latest append replaced (not subtracted yet)
 
     __device__ Mw(const Params<R>& p_, int lane_, int g_) : p(p_), lane(lane_), g(g_), gchain(p_.chain_offset + g_), Cs((size_t)p_.Cs) {}
 
@@ -168,6 +171,28 @@ struct Mw {
         return mw_sum<R>(t * t);
     }
 
+    // One entry joins the level-0 `accepted` window (ring [period][Cs] in global memory, shared with the lock-step
+    // kernel).  The entry it replaces is loaded here and subtracted at the NEXT append (or before the window is
+    // read): the load's latency stays off the step's dependency chain.
+    __device__ __forceinline__ void window_append(int acc) {
+        if (!p.adaptive) return;
+        win_sum += acc - win_old;
+        const int pos = (int)(wcount % p.period);
+        uint8_t* w = p.win + (size_t)pos * Cs + g;
+        win_old = (wcount >= p.period) ? (int)__ldcg(w) : 0;
+        __syncwarp();
+        if (lane == 0) *w = (uint8_t)acc;
+    }
+    // proposal.adapt() after a coarsest-level step (proposal.py:228-245)
+    __device__ __forceinline__ void adapt() {
+        if (!p.adaptive || (t_base % p.period) != 0) return;
+        win_sum -= win_old;
+        win_old = 0;
+        const long long k = t_base / p.period - 1;
+        const R rate = (R)win_sum / (R)p.period;
+        scal = texp(tlog(scal) + tpow(p.gamma, (R)(-(double)k)) * (rate - p.alpha_star));
+    }
+
     // Link of the parameters in prop[] on level l (posterior.py:78-110): log-prior, forward model -> Fp, log-likelihood
     __device__ __forceinline__ void eval(int l, R& pr, R& lk) {
         const LevelP<R>& v = p.lv[l];
@@ -179,9 +204,24 @@ struct Mw {
             const R y = matvec_d(LPs, diagLP, dLP, xb);
             pr = (R)-0.5 * (p.prior_logconst + mw_sum<R>(y * y));
         }
-        // forward model: u at the sensors from the cell fluxes (see the header)
+        // forward model: a linear operator (F = theta @ A + b, lane n forms output n), or u at the sensors of the
+        // Poisson problem from the cell fluxes (see the header)
         R F;
-        {
+        if (v.model_kind == TDA_MODEL_LINEAR) {
+            R a0 = (R)0, a1 = (R)0;
+            if (lane < m) {
+                const R* __restrict__ col = v.A + lane;
+                for (int k0 = 0; k0 < d; k0 += 4) {
+                    R th[4];
+                    Vec4<R>::ld(prop + k0, th);
+                    a0 = fma(th[0], __ldg(col + (size_t)k0 * v.ldA), a0);
+                    if (k0 + 1 < d) a1 = fma(th[1], __ldg(col + (size_t)(k0 + 1) * v.ldA), a1);
+                    if (k0 + 2 < d) a0 = fma(th[2], __ldg(col + (size_t)(k0 + 2) * v.ldA), a0);
+                    if (k0 + 3 < d) a1 = fma(th[3], __ldg(col + (size_t)(k0 + 3) * v.ldA), a1);
+                }
+            }
+            F = (lane < m) ? (a0 + a1) + __ldg(v.b + lane) : (R)0;
+        } else {
             const int n = v.n_grid, stride = v.stride;
             const R c0 = (R)(n / 2);
             R s0 = (R)0, s1 = (R)0;
@@ -247,7 +287,7 @@ struct Mw {
         __syncwarp();
         {
             const R xi = matvec_d(Ts, diagT, dT, xb);
-            const R s = p.scaling[g];
+            const R s = scal;
             const R ca = (p.prop_kind == TDA_PROP_PCN) ? tsqrt((R)1 - s * s) : (R)1;
             __syncwarp();
             prop[lane] = (lane < d) ? ca * V(0, V_TH) + s * xi : (R)0;
@@ -272,9 +312,12 @@ struct Mw {
             }
         }
         __syncwarp();
+        window_append(acc);
+        wcount += 1;
         t_base += 1;
         record(0, acc);
         if (p.L == 1) { const R th = V(0, V_TH); s1 += th; s2 += th * th; }
+        adapt();
     }
 
     // after a step of level l: the lower levels follow it (proposal.py:1583-1613)
@@ -296,7 +339,9 @@ struct Mw {
                 for (int a = j + 1; a < l; a++) { setS(j, S_SVP + a, sp); setS(j, S_SVL + a, sl); V(j, V_SVF + a - 1) = f; }
             }
             setI(j, I_ACCSUB, 0);
+            if (j == 0) window_append(acc);
         }
+        wcount += 1;
         __syncwarp();
     }
 
@@ -519,21 +564,25 @@ __global__ void __launch_bounds__(MW_MAXW * 32, 1) mlda_warp_kernel(const __grid
         c.sigw = reinterpret_cast<R*>(mp.sigw) + (size_t)g * MAXL * MW_MATW;
         c.liw = reinterpret_cast<R*>(mp.liw) + (size_t)g * MAXL * MW_MATW;
         c.t_base = p.t_base;
+        c.wcount = p.wcount;
         c.ucur = p.ucur[g];
+        c.scal = p.scaling[g];
+        c.win_sum = p.adaptive ? p.win_sum[g] : 0;
+        c.win_old = 0;
         __syncwarp();
         // ---- chain state: global (chain-fastest arrays shared with the lock-step kernel) -> shared memory ----
         for (int l = 0; l < L; l++) {
             const LevelP<R>& v = p.lv[l];
             const int m = v.m;
             c.V(l, V_TH) = (lane < d) ? v.theta[(size_t)lane * Cs + g] : (R)0;
-            c.V(l, V_F) = (lane < m) ? v.F[(size_t)lane * Cs + g] : (R)0;
+            c.V(l, V_F) = (v.need_F && lane < m) ? v.F[(size_t)lane * Cs + g] : (R)0;
             const bool ad = v.lik_kind == TDA_LIK_ADAPTIVE;
             c.V(l, V_BIAS) = (ad && lane < m) ? v.lik_bias[(size_t)lane * Cs + g] : (R)0;
             const bool up = p.aem && l >= 1;
             c.V(l, V_MD) = (up && lane < m) ? v.model_diff[(size_t)lane * Cs + g] : (R)0;
             c.V(l, V_BMU) = (up && lane < m) ? v.bias_mu[(size_t)lane * Cs + g] : (R)0;
             for (int a = 0; a < MAXL; a++)
-                if (a >= 1) c.V(l, V_SVF + a - 1) = (a > l && a < L && lane < m) ? v.sv_F[a][(size_t)lane * Cs + g] : (R)0;
+                if (a >= 1) c.V(l, V_SVF + a - 1) = (v.need_F && a > l && a < L && lane < m) ? v.sv_F[a][(size_t)lane * Cs + g] : (R)0;
             if (lane == 0) {
                 c.sc[l * NSC + S_PRIOR] = v.prior[g];
                 c.sc[l * NSC + S_LIKE] = v.like[g];
@@ -581,7 +630,7 @@ __global__ void __launch_bounds__(MW_MAXW * 32, 1) mlda_warp_kernel(const __grid
             const LevelP<R>& v = p.lv[l];
             const int m = v.m;
             if (lane < d) v.theta[(size_t)lane * Cs + g] = c.V(l, V_TH);
-            if (lane < m) {
+            if (lane < m && v.need_F) {
                 v.F[(size_t)lane * Cs + g] = c.V(l, V_F);
                 if (v.lik_kind == TDA_LIK_ADAPTIVE) v.lik_bias[(size_t)lane * Cs + g] = c.V(l, V_BIAS);
                 if (p.aem && l >= 1) {
@@ -602,7 +651,10 @@ __global__ void __launch_bounds__(MW_MAXW * 32, 1) mlda_warp_kernel(const __grid
         if (p.lv[0].lik_kind == TDA_LIK_ADAPTIVE)
             for (int e = lane; e < MW_MATW; e += 32) c.liw[e] = c.li0[e];
         if (lane < d) { p.sum1[(size_t)lane * Cs + g] = s1; p.sum2[(size_t)lane * Cs + g] = s2; }
-        if (lane == 0) p.ucur[g] = c.ucur;
+        if (lane == 0) {
+            p.ucur[g] = c.ucur;
+            if (p.adaptive) { p.scaling[g] = c.scal; p.win_sum[g] = c.win_sum - c.win_old; }
+        }
         __syncwarp();
     }
 }
@@ -664,17 +716,22 @@ size_t mw_smem_bytes(int warps, int cta_elems) { return ((size_t)cta_elems + (si
 const char* mlda_warp_last_error() { return g_mwerr.c_str(); }
 
 bool mlda_warp_eligible(const tda_config& c) {
-    if (c.n_levels < 1 || c.n_levels > MAXL || c.d > 32 || c.mtm_k || c.randomize_subchain || c.adaptive) return false;
+    if (c.n_levels < 1 || c.n_levels > MAXL || c.d > 32 || c.mtm_k || c.randomize_subchain) return false;
     if (c.prop_kind != TDA_PROP_RWMH && c.prop_kind != TDA_PROP_PCN) return false;
+    if (c.adaptive && c.period < 1) return false;
     if (c.aem != 0 && c.aem != 1) return false;
     for (int l = 0; l < c.n_levels; l++) {
         const tda_level_config& lc = c.level[l];
-        if (lc.model_kind != TDA_MODEL_POISSON1D || lc.m > MW_M || lc.m < 1) return false;
-        if (lc.n_grid % (lc.m + 1) != 0) return false;
+        if (lc.m > MW_M || lc.m < 1) return false;
+        if (lc.model_kind == TDA_MODEL_POISSON1D) {
+            if (lc.n_grid % (lc.m + 1) != 0) return false;
+        } else if (lc.model_kind != TDA_MODEL_LINEAR) {
+            return false;
+        }
         if (lc.lik_kind == TDA_LIK_DENSE) return false;
         if (lc.lik_kind == TDA_LIK_ADAPTIVE && (l == c.n_levels - 1 || !c.aem)) return false;
         if (c.aem && l < c.n_levels - 1 && lc.lik_kind != TDA_LIK_ADAPTIVE) return false;
-        if (l > 0 && lc.m != c.level[0].m) return false;
+        if (l > 0 && c.aem && lc.m != c.level[0].m) return false;
     }
     return true;
 }
@@ -691,6 +748,7 @@ int mlda_warp_run(Params<R>& P, void* sigw, void* liw, void* phiw, int sm_count,
     for (int l = 0; l < MAXL; l++) { mp.phi_off[l] = 0; mp.phi_elems[l] = 0; mp.phi_smem[l] = -1; }
     for (int l = 0; l < L; l++) {
         const LevelP<R>& v = P.lv[l];
+        if (v.model_kind != TDA_MODEL_POISSON1D) continue;        // linear levels read their operator directly
         const int elems = d4 * v.stride * 32;
         mp.phi_off[l] = off; mp.phi_elems[l] = elems;
         mw_phi_kernel<R><<<(elems + 255) / 256, 256, 0, st>>>(v.A, v.ldA, P.d, v.stride, v.m, reinterpret_cast<R*>(phiw) + off, elems);
@@ -731,8 +789,10 @@ int mlda_warp_run(Params<R>& P, void* sigw, void* liw, void* phiw, int sm_count,
 size_t mlda_warp_image_elems(int n_chains) { return (size_t)n_chains * MAXL * MW_MATW; }
 size_t mlda_warp_phi_elems(const tda_config& c) {
     size_t n = 0;
-    for (int l = 0; l < c.n_levels; l++) n += (size_t)((c.d + 3) / 4 * 4) * (size_t)(c.level[l].n_grid / (c.level[l].m + 1)) * 32;
-    return n;
+    for (int l = 0; l < c.n_levels; l++)
+        if (c.level[l].model_kind == TDA_MODEL_POISSON1D)
+            n += (size_t)((c.d + 3) / 4 * 4) * (size_t)(c.level[l].n_grid / (c.level[l].m + 1)) * 32;
+    return n ? n : 32;
 }
 int mlda_warp_launches(int L, int aem) {
     if (!aem) return 1 + L;

@@ -1,5 +1,6 @@
-// Host interface of the warp-per-chain MH / DA / MLDA kernel for the 1-D Poisson model with the state-independent
-// adaptive error model (tda_mlda_warp.cu, its own translation unit) -- BASELINE cfg4.  See the header comment there.
+// Host interface of the warp-per-chain MH / DA / MLDA kernel (1-D Poisson model or linear operators with at most 31
+// outputs, state-independent adaptive error model; tda_mlda_warp.cu, its own translation unit) -- BASELINE cfg4 and
+// the small problems of the reference's notebooks.  See the header comment there.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -7,7 +7,7 @@ from tinyda_b200.engine import Engine, STORE_NONE, STORE_STATS
 from tinyda_b200.workloads import cfg2_da
 w = cfg2_da()
 spec = lower_problem(w["posteriors"], w["proposal"], 10)
-Cn = 65536
+Cn = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 eng = Engine(spec, Cn, dtype="float32", seed=3, store=[STORE_NONE, STORE_STATS], capacity_iterations=4)
 eng.select_kernel("tc16")
 eng.init(w["prior"].rvs(Cn, random_state=np.random.default_rng(0)))
