@@ -944,7 +944,16 @@ struct EngineT : tda_engine {
     bool reg_eligible() const { return tda::mh_reg_eligible(cfg, P.lv[0].need_F != 0) && !z_round_user; }
     bool mldaw_eligible() const {
         static const bool off = getenv("TDA_NO_MLDA_WARP") != nullptr;
-        return !off && !z_round_user && tda::mlda_warp_eligible(cfg);
+        if (off || z_round_user || !tda::mlda_warp_eligible(cfg)) return false;
+        // A warp per chain pays when the per-chain work is wide (Poisson grids, 31 x 31 error-model matrices: cfg4 2.9 x
+        // the lock-step kernel at 32768 chains) or when there are too few chains to fill the lock-step kernel's
+        // 128-chain tiles (one round of either kernel: 38 against 119 us per finest iteration on the mlda3_linear
+        // fixture).  Small problems at tens of thousands of chains stay on the lock-step kernel, which deals a chain
+        // to a thread (2.8e8 against 6.3e7 finest transitions/s on that fixture at 32768 chains).
+        bool poisson = true;
+        for (int l = 0; l < cfg.n_levels; l++) poisson = poisson && cfg.level[l].model_kind == TDA_MODEL_POISSON1D;
+        const bool wide = poisson || (cfg.aem && cfg.level[0].m >= 16);
+        return wide || cfg.n_chains <= 4096;
     }
     // which kernel tda_engine_run launches: 1 generic, 2 tensor-core 3xTF32, 3 tensor-core fp16 split,
     // 4 register-resident single-level
