@@ -61,7 +61,14 @@ constexpr int T16_HK = T16_K / 2;               // theta columns per row thread
 constexpr int T16_IMG = 128 * T16_K * 2;        // one [128 x 64] fp16 image: 16 KB
 constexpr int T16_TIMG = 64 * T16_K * 2;        // one [64 x 64] fp16 image: 8 KB
 constexpr int T16_CHUNK_BYTES = 2 * T16_TIMG;   // hi + lo
-constexpr int T16_REGS_ROW = 96, T16_REGS_RNG = 40, T16_REGS_AUX = 40;   // 512*24 taken = 256*32 + 128*32 released (launch: 72)
+#ifndef T16_RNG_ILP
+#define T16_RNG_ILP 1          // 16-normal groups a generator thread has in flight; 2 (with 56 / 88 registers for generator / row threads) measured 780 M against 797 M transitions/s: the generator is not latency-bound, it competes with the row threads for issue slots
+#endif
+#if T16_RNG_ILP == 2
+constexpr int T16_REGS_ROW = 88, T16_REGS_RNG = 56, T16_REGS_AUX = 40;   // 512*16 taken = 256*(-16) ... see the budget below
+#else
+constexpr int T16_REGS_ROW = 96, T16_REGS_RNG = 40, T16_REGS_AUX = 40;
+#endif   // 512*24 taken = 256*32 + 128*32 released (launch: 72)
 
 constexpr int T16_OFF_G = 0;                                   // a G_c^T   (hi | lo)
 constexpr int T16_OFF_M = T16_OFF_G + 2 * T16_IMG;             // b T G_c^T (hi | lo)
@@ -98,6 +105,7 @@ struct DaTc16Params {
     int ib, nb;               // work units: iterations per block, blocks per launch (unit = tile pair x block)
     int* progress;            // [n_pairs] tile completions of this launch (2 per finished block)
     long long* dbg;           // optional timeline probe (tools/tc16_timeline.py): [role 4][256] clock64 stamps of CTA 0
+    PhiloxRoundKeys rk;       // round keys of the engine's seed (constant-bank operands of the generator warps)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -306,11 +314,10 @@ __device__ __forceinline__ void t16_issue_z(uint32_t d_tmem, uint32_t z_hi, uint
 
 // One 16-normal group (z16 stream) of one chain, packed to fp16 and stored into the chain's row of
 // a canonical K-major z image (row_ptr = image + row offset; columns 16 q4 .. 16 q4 + 15).
-__device__ __forceinline__ void t16_z_group(unsigned long long seed, long long gchain, unsigned long long group, unsigned char* row_ptr, int q4) {
+__device__ __forceinline__ void t16_z_group(const PhiloxRoundKeys& rk, long long gchain, unsigned long long group, unsigned char* row_ptr, int q4) {
     const unsigned long long b3 = 3 * group;
     float s[16];
-    z16_group_scaled(philox_block(seed, gchain, STREAM_Z, b3), philox_block(seed, gchain, STREAM_Z, b3 + 1),
-                     philox_block(seed, gchain, STREAM_Z, b3 + 2), s);
+    z16_group_scaled(philox_block_z_rk(rk, gchain, b3), philox_block_z_rk(rk, gchain, b3 + 1), philox_block_z_rk(rk, gchain, b3 + 2), s);
     uint4 w0, w1;
     w0.x = tc::pack_f16x2(s[0], s[1]);   w0.y = tc::pack_f16x2(s[2], s[3]);
     w0.z = tc::pack_f16x2(s[4], s[5]);   w0.w = tc::pack_f16x2(s[6], s[7]);
@@ -318,6 +325,34 @@ __device__ __forceinline__ void t16_z_group(unsigned long long seed, long long g
     w1.z = tc::pack_f16x2(s[12], s[13]); w1.w = tc::pack_f16x2(s[14], s[15]);
     *reinterpret_cast<uint4*>(row_ptr + (2 * q4) * 128) = w0;
     *reinterpret_cast<uint4*>(row_ptr + (2 * q4 + 1) * 128) = w1;
+}
+
+// Two groups of one chain at once: six independent Philox blocks and sixteen Box-Muller pairs in one basic block,
+// so that the generator warps -- two per scheduler, each a chain of dependent integer multiplies and special-function
+// results -- overlap their latencies (the z images pace the paired mode: ~6000 cycles per image with one group after
+// the other, measured with the clock64 probe).
+__device__ __forceinline__ void t16_z_group2(const PhiloxRoundKeys& rk, long long gchain, unsigned long long group0, unsigned char* row_ptr,
+                                             int qa, int qb) {
+    const unsigned long long a3 = 3 * (group0 + qa), b3 = 3 * (group0 + qb);
+    const uint4 pa0 = philox_block_z_rk(rk, gchain, a3), pb0 = philox_block_z_rk(rk, gchain, b3);
+    const uint4 pa1 = philox_block_z_rk(rk, gchain, a3 + 1), pb1 = philox_block_z_rk(rk, gchain, b3 + 1);
+    const uint4 pa2 = philox_block_z_rk(rk, gchain, a3 + 2), pb2 = philox_block_z_rk(rk, gchain, b3 + 2);
+    float sa[16], sb[16];
+    z16_group_scaled(pa0, pa1, pa2, sa);
+    z16_group_scaled(pb0, pb1, pb2, sb);
+    uint4 w0, w1, v0, v1;
+    w0.x = tc::pack_f16x2(sa[0], sa[1]);   w0.y = tc::pack_f16x2(sa[2], sa[3]);
+    w0.z = tc::pack_f16x2(sa[4], sa[5]);   w0.w = tc::pack_f16x2(sa[6], sa[7]);
+    w1.x = tc::pack_f16x2(sa[8], sa[9]);   w1.y = tc::pack_f16x2(sa[10], sa[11]);
+    w1.z = tc::pack_f16x2(sa[12], sa[13]); w1.w = tc::pack_f16x2(sa[14], sa[15]);
+    v0.x = tc::pack_f16x2(sb[0], sb[1]);   v0.y = tc::pack_f16x2(sb[2], sb[3]);
+    v0.z = tc::pack_f16x2(sb[4], sb[5]);   v0.w = tc::pack_f16x2(sb[6], sb[7]);
+    v1.x = tc::pack_f16x2(sb[8], sb[9]);   v1.y = tc::pack_f16x2(sb[10], sb[11]);
+    v1.z = tc::pack_f16x2(sb[12], sb[13]); v1.w = tc::pack_f16x2(sb[14], sb[15]);
+    *reinterpret_cast<uint4*>(row_ptr + (2 * qa) * 128) = w0;
+    *reinterpret_cast<uint4*>(row_ptr + (2 * qa + 1) * 128) = w1;
+    *reinterpret_cast<uint4*>(row_ptr + (2 * qb) * 128) = v0;
+    *reinterpret_cast<uint4*>(row_ptr + (2 * qb + 1) * 128) = v1;
 }
 
 // Work distribution.  A launch advances n_pairs tile pairs by `iterations`; 256 pairs on 148 SMs would
@@ -460,8 +495,18 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
                 if (!inj) {
                     // z16 stream: d normals = d / 16 groups of 3 Philox blocks
                     const unsigned long long grp0 = (unsigned long long)(tb * (d >> 4));
+#if T16_RNG_ILP == 2
+                    {
+                        const int ng = d >> 4;
+                        int q4 = part;
 #pragma unroll 1
-                    for (int q4 = part; q4 < (d >> 4); q4 += nparts) t16_z_group(p.seed, gchain, grp0 + q4, dst, q4);
+                        for (; q4 + nparts < ng; q4 += 2 * nparts) t16_z_group2(q.rk, gchain, grp0, dst, q4, q4 + nparts);
+                        if (q4 < ng) t16_z_group(q.rk, gchain, grp0 + q4, dst, q4);
+                    }
+#else
+#pragma unroll 1
+                    for (int q4 = part; q4 < (d >> 4); q4 += nparts) t16_z_group(q.rk, gchain, grp0 + q4, dst, q4);
+#endif
                 } else {
                     const long long z0 = tb * d;
                     for (int kg = part; kg < (d >> 3); kg += nparts) {
@@ -1170,6 +1215,7 @@ struct DaTc16State<float> {
             if (2 * q.n_pairs <= sm_count && !getenv("TDA_TC16_NO_HALF")) { q.half = 1; q.n_pairs = P.Cs / 64; }
         }
         q.dbg = dDbg;
+        q.rk = philox_round_keys(P.seed);
         const int grid = q.n_pairs < sm_count ? q.n_pairs : sm_count;
         // iteration blocks: the smallest block count (<= 16) whose round-robin deal of the
         // (pair, block) units fills at least 97 % of the last wave, else the best one
