@@ -636,7 +636,7 @@ def run_other(args):
         exchange = "single device: persistent launch, grid barrier per step"
         if world > 1:
             ok = parallel.connect_dream_peers(eng, rank, world)
-            exchange = ("persistent launch; each step's rows stored into every replica over NVLink peer memory, flag handshake"
+            exchange = ("persistent launch; each step's rows stored into every replica over NVLink peer memory, arrival counters (one system fence per CTA, remote reductions)"
                         if ok else "one launch + one NCCL all-gather per step")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
