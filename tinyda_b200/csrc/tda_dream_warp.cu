@@ -25,8 +25,9 @@ constexpr int DW_CPW = 4;            // chains per warp at most (state in regist
 
 template <typename R>
 struct DwShared {
-    // dynamic shared memory: A [d][ldA] | LP [d][ldD] | b [m] | data [m] | var [m] | mean [d]
+    // dynamic shared memory: A [d][m_pad] | LP [d][32] | b [m_pad] | data [m_pad] | var [m_pad] | mean [32]   (zero padded)
     R* A; R* LP; R* b; R* data; R* var; R* mean;
+    int m_pad;
 };
 
 template <typename R>
@@ -47,44 +48,77 @@ __device__ __forceinline__ R dw_warp_sum(R v) {
     return v;
 }
 
-// log-prior and log-likelihood of the parameter vector held one component per lane (lanes >= d hold 0)
+// eight consecutive values from (16-byte aligned) shared memory
+template <typename R> struct DwVec8;
+template <> struct DwVec8<float> {
+    static __device__ __forceinline__ void ld(const float* p, float (&o)[8]) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+};
+template <> struct DwVec8<double> {
+    static __device__ __forceinline__ void ld(const double* p, double (&o)[8]) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double2 a = *reinterpret_cast<const double2*>(p + 2 * i);
+            o[2 * i] = a.x; o[2 * i + 1] = a.y;
+        }
+    }
+};
+
+// output index handled by (lane, j) in the 256-output chunk starting at n0: eight CONSECUTIVE outputs per lane, so that
+// a row of the operator is two 16-byte shared-memory loads per lane and chunk
+__device__ __forceinline__ int dw_out(int n0, int lane, int j) { return n0 + lane * 8 + j; }
+
+// log-prior and log-likelihood of the parameter vector held one component per lane (lanes >= d hold 0).
+// Shared-memory operands are zero-padded (A, LP, b, data; var with ones) to m_pad = multiple of 256 outputs and 32
+// parameter columns: no bounds tests in the contractions.
 template <typename R>
 __device__ __forceinline__ void dw_eval(const Params<R>& p, const DwShared<R>& s, int lane, int g, R th, R& prior, R& like) {
     const LevelP<R>& v = p.lv[0];
-    const int d = p.d, m = v.m, ldA = v.ldA;
+    const int d = p.d, m = v.m, mp = s.m_pad;
     // prior: -0.5 * (logconst + |(x - mu) LP|^2)   (posterior.py:92, scipy's whitening matrix)
     {
         const R xc = (lane < d) ? th - s.mean[lane] : (R)0;
-        R y = (R)0;
-        for (int k = 0; k < d; k++) {
-            const R xk = __shfl_sync(0xffffffffu, xc, k);
-            if (lane < d) y = fma(xk, s.LP[k * p.ldD + lane], y);
+        R y0 = (R)0, y1 = (R)0;
+        const R* lp = s.LP + lane;
+        int k = 0;
+        for (; k + 1 < d; k += 2) {
+            y0 = fma(__shfl_sync(0xffffffffu, xc, k), lp[k * 32], y0);
+            y1 = fma(__shfl_sync(0xffffffffu, xc, k + 1), lp[(k + 1) * 32], y1);
         }
+        if (k < d) y0 = fma(__shfl_sync(0xffffffffu, xc, k), lp[k * 32], y0);
+        const R y = y0 + y1;
         prior = (R)-0.5 * (p.prior_logconst + dw_warp_sum<R>(y * y));
     }
     // model F = theta @ A + b (posterior.py:95), residual against the data, Gaussian log-likelihood
     R ssq = (R)0;
-    for (int n0 = 0; n0 < m; n0 += 256) {
+    for (int n0 = 0; n0 < mp; n0 += 256) {
         R acc[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j] = (R)0;
+        const R* col = s.A + n0 + lane * 8;
         for (int k = 0; k < d; k++) {
             const R tk = __shfl_sync(0xffffffffu, th, k);
-            const R* row = s.A + k * ldA + n0 + lane;
+            R a[8];
+            DwVec8<R>::ld(col + (size_t)k * mp, a);
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-                if (n0 + 32 * j + lane < m) acc[j] = fma(tk, row[32 * j], acc[j]);
+            for (int j = 0; j < 8; j++) acc[j] = fma(tk, a[j], acc[j]);
         }
+        R bb[8], dd[8], vv[8];
+        DwVec8<R>::ld(s.b + n0 + lane * 8, bb);
+        DwVec8<R>::ld(s.data + n0 + lane * 8, dd);
+        if (v.lik_kind != TDA_LIK_ISO) DwVec8<R>::ld(s.var + n0 + lane * 8, vv);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int n = n0 + 32 * j + lane;
-            if (n < m) {
-                const R F = acc[j] + s.b[n];
-                if (v.need_F) v.Fp[(size_t)n * p.Cs + g] = F;     // Link.model_output of the proposal (same lane reads it back)
-                const R res = F - s.data[n];
-                if (v.lik_kind == TDA_LIK_ISO) ssq = fma(res, res, ssq);
-                else ssq += res * res / s.var[n];
+            const R F = acc[j] + bb[j];
+            if (v.need_F) {     // Link.model_output of the proposal (the same lane reads it back)
+                const int n = dw_out(n0, lane, j);
+                if (n < m) v.Fp[(size_t)n * p.Cs + g] = F;
             }
+            const R res = F - dd[j];
+            if (v.lik_kind == TDA_LIK_ISO) ssq = fma(res, res, ssq);
+            else ssq += res * res / vv[j];
         }
     }
     ssq = dw_warp_sum<R>(ssq);
@@ -153,16 +187,28 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dream_warp_kernel(const __grid_
     const LevelP<R>& v = p.lv[0];
     const int d = p.d, m = v.m;
     DwShared<R> s;
+    const int mp = (m + 255) / 256 * 256;
+    s.m_pad = mp;
     s.A = reinterpret_cast<R*>(dw_smem);
-    s.LP = s.A + (size_t)d * v.ldA;
-    s.b = s.LP + (size_t)d * p.ldD;
-    s.data = s.b + m;
-    s.var = s.data + m;
-    s.mean = s.var + m;
-    for (int i = threadIdx.x; i < d * v.ldA; i += DW_THREADS) s.A[i] = v.A[i];
-    for (int i = threadIdx.x; i < d * p.ldD; i += DW_THREADS) s.LP[i] = p.LP[i];
-    for (int i = threadIdx.x; i < m; i += DW_THREADS) { s.b[i] = v.b[i]; s.data[i] = v.data[i]; s.var[i] = (v.lik_kind == TDA_LIK_DIAG) ? v.var[i] : (R)1; }
-    for (int i = threadIdx.x; i < d; i += DW_THREADS) s.mean[i] = p.prior_mean[i];
+    s.LP = s.A + (size_t)d * mp;
+    s.b = s.LP + (size_t)d * 32;
+    s.data = s.b + mp;
+    s.var = s.data + mp;
+    s.mean = s.var + mp;
+    for (int i = threadIdx.x; i < d * mp; i += DW_THREADS) {
+        const int k = i / mp, n = i - k * mp;
+        s.A[i] = (n < m) ? v.A[(size_t)k * v.ldA + n] : (R)0;
+    }
+    for (int i = threadIdx.x; i < d * 32; i += DW_THREADS) {
+        const int k = i >> 5, c = i & 31;
+        s.LP[i] = (c < d) ? p.LP[(size_t)k * p.ldD + c] : (R)0;
+    }
+    for (int i = threadIdx.x; i < mp; i += DW_THREADS) {
+        s.b[i] = (i < m) ? v.b[i] : (R)0;
+        s.data[i] = (i < m) ? v.data[i] : (R)0;
+        s.var[i] = (i < m && v.lik_kind == TDA_LIK_DIAG) ? v.var[i] : (R)1;
+    }
+    for (int i = threadIdx.x; i < 32; i += DW_THREADS) s.mean[i] = (i < d) ? p.prior_mean[i] : (R)0;
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -268,7 +314,12 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dream_warp_kernel(const __grid_
             if (acc) {
                 th[q] = prop; prior[q] = pr; like[q] = lk; nacc[q]++; lastacc[q] = (int)(t + 1);
                 if (v.need_F)
-                    for (int n = lane; n < m; n += 32) v.F[(size_t)n * Cs + g] = v.Fp[(size_t)n * Cs + g];
+                    for (int n0 = 0; n0 < m; n0 += 256)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const int n = dw_out(n0, lane, j);
+                            if (n < m) v.F[(size_t)n * Cs + g] = v.Fp[(size_t)n * Cs + g];
+                        }
             }
             // ---- record (chain.chain / chain.accepted) and running moments ----
             {
@@ -276,7 +327,12 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dream_warp_kernel(const __grid_
                 if (r < v.hist_cap) {
                     if ((v.store & TDA_STORE_THETA) && lane < d) v.h_theta[((size_t)r * d + lane) * Cs + g] = th[q];
                     if ((v.store & TDA_STORE_OUTPUT) && v.need_F)
-                        for (int n = lane; n < m; n += 32) v.h_F[((size_t)r * m + n) * Cs + g] = v.F[(size_t)n * Cs + g];
+                        for (int n0 = 0; n0 < m; n0 += 256)
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int n = dw_out(n0, lane, j);
+                                if (n < m) v.h_F[((size_t)r * m + n) * Cs + g] = v.F[(size_t)n * Cs + g];
+                            }
                     if (lane == 0) {
                         if (v.store & TDA_STORE_STATS) { v.h_prior[(size_t)r * Cs + g] = prior[q]; v.h_like[(size_t)r * Cs + g] = like[q]; }
                         if (v.store & TDA_STORE_ACCEPT) v.h_acc[(size_t)r * Cs + g] = (uint8_t)acc;
@@ -320,7 +376,8 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dream_warp_kernel(const __grid_
 template <typename R>
 size_t dw_smem_bytes(const Params<R>& P) {
     const LevelP<R>& v = P.lv[0];
-    return ((size_t)P.d * v.ldA + (size_t)P.d * P.ldD + 3 * (size_t)v.m + P.d) * sizeof(R) + 16;
+    const size_t mp = ((size_t)v.m + 255) / 256 * 256;
+    return ((size_t)P.d * mp + (size_t)P.d * 32 + 3 * mp + 32) * sizeof(R) + 16;
 }
 
 thread_local std::string g_dwerr;
