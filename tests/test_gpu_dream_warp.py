@@ -137,3 +137,37 @@ def test_warp_kernel_targets_the_closed_form_posterior():
     pooled_var = th.transpose(1, 0, 2).reshape(32, -1).var(axis=1)
     assert np.abs(pooled_mean - mu).max() < 0.1 * sd.max(), np.abs(pooled_mean - mu).max() / sd.max()
     assert np.abs(pooled_var / np.diag(S) - 1).max() < 0.2, pooled_var / np.diag(S)
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_diagonal_likelihood_model_outputs_and_odd_sizes_agree_with_the_lockstep_kernel(shared):
+    """d = 5 parameters, 37 observations (neither a multiple of the padding), a diagonal (non-isotropic) likelihood,
+    a dense prior covariance, delta = 2 pairs, model outputs recorded: float64, decision for decision."""
+    import scipy.stats as stats
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.distributions import GaussianLogLike
+    from tinyda_b200.engine import STORE_FULL
+    from tinyda_b200.models import LinearModel
+    from tinyda_b200.posterior import Posterior
+    from tinyda_b200.proposal import DREAM, DREAMZ
+    rng = np.random.default_rng(17)
+    d, m, C, M0 = 5, 37, 45, 9
+    A = rng.standard_normal((d, d))
+    prior = stats.multivariate_normal(0.2 * np.ones(d), A @ A.T / d + 0.5 * np.eye(d))
+    G = rng.standard_normal((m, d)) / np.sqrt(d)
+    var = 0.02 * (1.0 + rng.random(m))
+    y = G @ prior.rvs(random_state=rng) + np.sqrt(var) * rng.standard_normal(m)
+    post = Posterior(prior, GaussianLogLike(y, np.diag(var)), LinearModel(G, offset=0.1 * rng.standard_normal(m)))
+    prop = (DREAM if shared else DREAMZ)(M0=M0, delta=2, nCR=4)
+    spec = lower_problem([post], prop)
+    theta0 = prior.rvs(C, random_state=rng)
+    archive0 = prior.rvs(C * M0, random_state=rng).reshape(C, M0, d)
+    a = _run(spec, theta0, archive0, 35, "dreamw", "float64", STORE_FULL)
+    b = _run(spec, theta0, archive0, 35, "generic", "float64", STORE_FULL)
+    assert np.array_equal(a["acc"], b["acc"])
+    assert np.array_equal(a["cursors"], b["cursors"])
+    np.testing.assert_allclose(a["theta"], b["theta"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(a["prior"], b["prior"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(a["like"], b["like"], rtol=1e-9, atol=1e-8)
+    np.testing.assert_allclose(a["F"], b["F"], rtol=1e-10, atol=1e-12)
+    assert 0.02 < a["acc"][1:].mean() < 0.98

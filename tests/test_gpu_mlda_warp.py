@@ -214,3 +214,49 @@ def test_other_shapes_agree_with_the_lockstep_kernel(levels, aem, msens, d, pcn)
         np.testing.assert_allclose(a[l]["F"], b[l]["F"], rtol=1e-9, atol=1e-13)
         np.testing.assert_allclose(a[l]["like"], b[l]["like"], rtol=1e-6, atol=1e-6)
     assert 0.02 < a[0]["acc"][1:].mean() < 0.999
+
+
+def test_linear_levels_diagonal_likelihood_and_adaptive_pcn_agree_with_the_lockstep_kernel():
+    """Two-level DA on linear operators (11 and 23 outputs), diagonal likelihood on the fine level, the error model on
+    the coarse one, adaptive pCN (the window ring, crossing several adaptation periods): float64, decision for
+    decision, adapted step sizes included."""
+    import scipy.stats as stats
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.distributions import GaussianLogLike, AdaptiveGaussianLogLike
+    from tinyda_b200.engine import Engine, STORE_FULL
+    from tinyda_b200.models import LinearModel
+    from tinyda_b200.posterior import Posterior
+    from tinyda_b200.proposal import CrankNicolson
+    rng = np.random.default_rng(23)
+    d, m, C = 6, 23, 90
+    A = rng.standard_normal((d, d))
+    prior = stats.multivariate_normal(np.zeros(d), A @ A.T / d + 0.3 * np.eye(d))
+    G = rng.standard_normal((m, d)) / np.sqrt(d)
+    Gc = G + 0.05 * rng.standard_normal((m, d))
+    var = 0.01 * (1.0 + rng.random(m))
+    y = G @ prior.rvs(random_state=rng) + np.sqrt(var) * rng.standard_normal(m)
+    posts = [Posterior(prior, AdaptiveGaussianLogLike(y, np.diag(var)), LinearModel(Gc)),
+             Posterior(prior, GaussianLogLike(y, np.diag(var)), LinearModel(G))]
+    prop = CrankNicolson(scaling=0.3, adaptive=True, period=7)
+    spec = lower_problem(posts, prop, 3, "state-independent")
+    theta0 = prior.rvs(C, random_state=rng)
+    outs = {}
+    for kern in ("mldaw", "generic"):
+        eng = Engine(spec, C, dtype="float64", seed=77, store=STORE_FULL, capacity_iterations=40)
+        eng.select_kernel(kern)
+        eng.init(theta0)
+        eng.run(17)
+        eng.run(23)
+        outs[kern] = dict(scaling=eng.get("scaling"), cursors=eng.get("cursors"), counts=eng.get("accept_counts"),
+                          th=[eng.fetch(l, "theta") for l in range(2)], acc=[eng.fetch(l, "accept") for l in range(2)],
+                          like=[eng.fetch(l, "like") for l in range(2)], F=[eng.fetch(l, "output") for l in range(2)])
+        eng.close()
+    a, b = outs["mldaw"], outs["generic"]
+    assert np.array_equal(a["cursors"], b["cursors"]) and np.array_equal(a["counts"], b["counts"])
+    np.testing.assert_allclose(a["scaling"], b["scaling"], rtol=1e-12)
+    assert np.ptp(a["scaling"]) > 0 and not np.allclose(a["scaling"], 0.3)
+    for l in range(2):
+        assert np.array_equal(a["acc"][l], b["acc"][l]), "level %d decisions" % l
+        np.testing.assert_allclose(a["th"][l], b["th"][l], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(a["F"][l], b["F"][l], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(a["like"][l], b["like"][l], rtol=1e-7, atol=1e-7)
