@@ -566,10 +566,13 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------
 # Secondary workloads (BASELINE.json configs[2..4]); not the headline line, same timing rules
 # ------------------------------------------------------------------------------------------
-def _other_workload(name, world):
+def _other_workload(name, world, dream_sync=1):
     from tinyda_b200 import lower_problem, workloads
     w = workloads.WORKLOADS[name]()
     kw = w["kwargs"]
+    if name == "cfg5" and dream_sync > 1:
+        w["proposal"].sync_every = int(dream_sync)         # bounded staleness of the shared archive (extension)
+        w["name"] += ", sync_every=%d" % dream_sync
     spec = lower_problem(w["posteriors"], w["proposal"], kw.get("subchain_length"), kw.get("adaptive_error_model"))
     d = spec["d"]
     s = 4
@@ -612,7 +615,7 @@ def run_other(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    w, spec, cd = _other_workload(args.workload, world)
+    w, spec, cd = _other_workload(args.workload, world, args.dream_sync)
     C = args.chains if args.chains is not None else cd["chains"]
     iters = args.iters if args.iters is not None else cd["iters"]
     L, d = spec["n_levels"], spec["d"]
@@ -807,6 +810,8 @@ def main():
                     help="cfg2: 'fine' = fine-level Links only (the headline line); 'coarse' = the reference's "
                          "store_coarse_chain=True: every coarse Link (theta, log-like, accept) is recorded too")
     ap.add_argument("--e2e-iters", type=int, default=None, help="fine iterations per tda.sample() call of the e2e arm (default 1000)")
+    ap.add_argument("--dream-sync", type=int, default=1, help="cfg5: DREAM(sync_every=K), the chains' view of the shared archive "
+                    "is refreshed every K steps (default 1 = the lock-step rule)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--quick", action="store_true")

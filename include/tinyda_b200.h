@@ -106,7 +106,9 @@ typedef struct tda_config {
                                          * RWMH / AM / pCN kernels, 2 <= k <= 16) */
     int32_t mtm_include_current;        /* 0 = the reference's k-1 reference points; 1 = the current state is
                                          * the k-th reference point (Liu et al. 2000; detailed balance)      */
-    int32_t reserved0;
+    int32_t dream_sync_every;           /* DREAM (shared archive): the chains' view of the archive is refreshed every so many
+                                         * steps (0 or 1: every step, the lock-step rule of the golden fixtures; larger values
+                                         * need kernel 6).  Occupies the field that was `reserved0` (must-be-zero) in ABI 3. */
     uint64_t seed;
     int64_t n_chains;                   /* chains on THIS device                       */
     int64_t chain_offset;               /* global index of local chain 0 (Philox key)  */

@@ -634,19 +634,23 @@ class ChainOracle:
 
 
 class DreamEnsemble:
-    """DREAM with the shared archive (proposal.py:1627-1656, ray.py:366-384) under the
-    deterministic lock-step rule: at step t every chain sees all chains' rows through step
-    t-1; archive order is chain-major as in np.concatenate(shared_archive) (ray.py:381)."""
+    """DREAM with the shared archive (proposal.py:1627-1656, ray.py:366-384) under a deterministic
+    visibility rule: a chain at step t sees all chains' rows through the last multiple of
+    `sync_every` below t (sync_every = 1: through step t-1, the lock-step rule); archive order is
+    chain-major as in np.concatenate(shared_archive) (ray.py:381)."""
 
     def __init__(self, spec, theta0, z, u, archive0):
         C = theta0.shape[0]
         self.chains = [ChainOracle(spec, theta0[c], z[c], u[c], archive0=archive0[c]) for c in range(C)]
         self.blocks = [np.array(archive0[c], dtype=np.float64) for c in range(C)]
+        self.sync_every = max(1, int(spec["proposal"].get("sync_every", 1)))
+        self.t = 0
+        self.visible = self.blocks[0].shape[0]        # rows per chain every chain may draw from
         for ch in self.chains:
             ch.shared_view = self._view
 
     def _view(self):
-        rows = self.blocks[0].shape[0]
+        rows = self.visible
         M = rows * len(self.blocks)
         blocks = self.blocks
         return M, (lambda r: blocks[r // rows][r % rows, :])
@@ -656,6 +660,9 @@ class DreamEnsemble:
             for ch in self.chains:
                 ch.base_step()
             self.blocks = [np.vstack((b, ch.cur[0].theta)) for b, ch in zip(self.blocks, self.chains)]
+            self.t += 1
+            if self.t % self.sync_every == 0:
+                self.visible = self.blocks[0].shape[0]
 
 
 def run_chains(spec, theta0, z, u, iterations, archive0=None):

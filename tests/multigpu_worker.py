@@ -72,6 +72,26 @@ def main(outdir):
     eng.close()
     assert np.array_equal(mine_g, one_g[lo_g:hi_g]), "sharded DREAM (lock-step kernel) differs from the single-engine run"
 
+    # ---- bounded staleness: DREAM(sync_every=5), the ranks meet every fifth step only; launch cut off the grid ----
+    from tinyda_b200.proposal import DREAM
+    spec5 = lower_problem(w["posteriors"], DREAM(M0=16, delta=1, nCR=3, sync_every=5))
+    e5 = Engine(spec5, hi_g - lo_g, dtype="float32", seed=9, store=STORE_STATS, capacity_iterations=iters, device=local,
+                chain_offset=lo_g, n_chains_global=C, archive0=archive0)
+    assert e5.kernel() == "dreamw" and parallel.connect_dream_peers(e5, rank, world)
+    e5.init(theta0[lo_g:hi_g])
+    parallel.run_dream_shared(e5, 13, rank, world)
+    parallel.run_dream_shared(e5, iters - 13, rank, world)
+    mine_5 = np.transpose(e5.fetch(0, "theta"), (2, 0, 1))
+    dist.barrier()
+    e5.close()
+    eng = Engine(spec5, C, dtype="float32", seed=9, store=STORE_STATS, capacity_iterations=iters, device=local, archive0=archive0)
+    eng.init(theta0)
+    eng.run(iters)
+    one_5 = np.transpose(eng.fetch(0, "theta"), (2, 0, 1))
+    eng.close()
+    assert np.array_equal(mine_5, one_5[lo_g:hi_g]), "sharded DREAM(sync_every=5) differs from the single-engine run"
+    assert not np.array_equal(one_5, one), "sync_every=5 should not reproduce the lock-step trajectory"
+
     # ---- Delayed Acceptance, chains sharded by sample() ------------------------------------------
     w2 = workloads.cfg2_da()
     C2, it2 = 1024, 6

@@ -171,3 +171,70 @@ def test_diagonal_likelihood_model_outputs_and_odd_sizes_agree_with_the_lockstep
     np.testing.assert_allclose(a["like"], b["like"], rtol=1e-9, atol=1e-8)
     np.testing.assert_allclose(a["F"], b["F"], rtol=1e-10, atol=1e-12)
     assert 0.02 < a["acc"][1:].mean() < 0.98
+
+
+@pytest.mark.parametrize("K", [3, 8])
+def test_bounded_staleness_sync_every_matches_the_oracle_and_ignores_launch_cuts(K):
+    """DREAM(sync_every=K): a chain at step t draws its pairs from all chains' rows through the last multiple of K
+    below t.  float64 against the oracle's DreamEnsemble under the same rule (engine streams exported), then launch
+    cuts that do not fall on multiples of K bit for bit, and K = 1 against the default."""
+    import problems
+    from oracle import tinyda_oracle as orc
+    from tinyda_b200 import lower_problem, workloads
+    from tinyda_b200.engine import Engine, STORE_FULL
+    from tinyda_b200.proposal import DREAM
+    w = workloads.cfg5_dream()
+    spec = lower_problem(w["posteriors"], DREAM(M0=16, delta=1, nCR=3, sync_every=K))
+    assert int(spec["proposal"]["sync_every"]) == K
+    C, iters = 24, 37
+    rng = np.random.default_rng(8)
+    theta0 = w["prior"].rvs(C, random_state=rng)
+    archive0 = w["prior"].rvs(C * 16, random_state=rng).reshape(C, 16, 32)
+
+    def run(cuts, dtype="float64"):
+        eng = Engine(spec, C, dtype=dtype, seed=5, store=STORE_FULL, capacity_iterations=iters, archive0=archive0)
+        assert eng.kernel() == "dreamw"
+        eng.init(theta0)
+        for n in cuts:
+            eng.run(n)
+        out = (np.transpose(eng.fetch(0, "theta"), (2, 0, 1)), eng.fetch(0, "accept").T.astype(bool), eng.fetch(0, "like").T,
+               eng.get("cursors"))
+        nz, nu = problems.stream_sizes(spec, iters)
+        z, u = eng.fill_streams(nz, nu)
+        eng.close()
+        return out, z, u
+
+    (th, acc, lk, cur), z, u = run([iters])
+    ref, chains = orc.run_chains(spec, theta0, z, u, iters, archive0)
+    assert np.array_equal(acc, ref[0]["acc"])
+    np.testing.assert_allclose(th, ref[0]["theta"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(lk, ref[0]["like"], rtol=1e-9, atol=1e-8)
+    assert 0.02 < acc[:, 1:].mean() < 0.98
+    (th2, acc2, lk2, cur2), _, _ = run([5, 1, 14, 17])
+    assert np.array_equal(th, th2) and np.array_equal(acc, acc2) and np.array_equal(cur, cur2)
+    # the rule matters: the lock-step run (sync_every = 1) is a different trajectory
+    spec1 = lower_problem(w["posteriors"], DREAM(M0=16, delta=1, nCR=3))
+    e1 = Engine(spec1, C, dtype="float64", seed=5, store=STORE_FULL, capacity_iterations=iters, archive0=archive0)
+    e1.init(theta0)
+    e1.run(iters)
+    th1 = np.transpose(e1.fetch(0, "theta"), (2, 0, 1))
+    e1.close()
+    assert not np.array_equal(th1, th)
+    assert np.array_equal(th1[:, :2], th[:, :2])                  # the first step sees the initial rows under both rules
+
+
+def test_sync_every_needs_the_warp_kernel():
+    from tinyda_b200 import lower_problem, workloads
+    from tinyda_b200._lib import EngineError
+    from tinyda_b200.engine import Engine, STORE_STATS
+    from tinyda_b200.proposal import DREAM
+    w = workloads.cfg5_dream()
+    spec = lower_problem(w["posteriors"], DREAM(M0=16, delta=1, nCR=3, sync_every=4))
+    rng = np.random.default_rng(1)
+    eng = Engine(spec, 8, dtype="float32", seed=1, store=STORE_STATS, capacity_iterations=4,
+                 archive0=w["prior"].rvs(8 * 16, random_state=rng).reshape(8, 16, 32))
+    eng.select_kernel("generic")
+    eng.init(w["prior"].rvs(8, random_state=rng))
+    with pytest.raises(EngineError, match="sync_every"):
+        eng.run(4)
+    eng.close()

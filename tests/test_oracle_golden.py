@@ -42,3 +42,18 @@ def test_oracle_matches_reference_on_the_long_cfg2_fixture():
     np.testing.assert_allclose(out[1]["like"], f_ref["like"], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(out[0]["like"], c_ref["like"], rtol=1e-9, atol=1e-9)
     assert np.array_equal(np.array([[ch.S.nz, ch.S.nu] for ch in chains]), g["consumed"])
+
+
+def test_dream_ensemble_sync_every_one_is_the_lock_step_rule_and_larger_values_differ():
+    """DreamEnsemble(sync_every=K): K = 1 reproduces the dream_shared fixture (checked above through run_chains);
+    K = 4 gives the same first step (every chain sees the initial rows only) and different chains afterwards (at the
+    second step the lock-step rule already counts one more row per chain)."""
+    import copy
+    from oracle import tinyda_oracle as orc
+    g = golden_io.load("dream_shared")
+    spec4 = copy.deepcopy(g["spec"])
+    spec4["proposal"]["sync_every"] = 4
+    a, _ = orc.run_chains(g["spec"], g["theta0"], g["z"], g["u"], g["iterations"], g["archive0"])
+    b, _ = orc.run_chains(spec4, g["theta0"], g["z"], g["u"], g["iterations"], g["archive0"])
+    assert np.array_equal(a[0]["theta"][:, :2], b[0]["theta"][:, :2])
+    assert not np.array_equal(a[0]["theta"], b[0]["theta"])

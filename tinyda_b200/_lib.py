@@ -49,7 +49,7 @@ class Config(C.Structure):
         ("abi_version", C.c_int32), ("dtype", C.c_int32), ("n_levels", C.c_int32), ("d", C.c_int32),
         ("subchain", C.c_int32 * TDA_MAX_LEVELS), ("aem", C.c_int32), ("rng_mode", C.c_int32),
         ("randomize_subchain", C.c_int32), ("mtm_k", C.c_int32),
-        ("mtm_include_current", C.c_int32), ("reserved0", C.c_int32),
+        ("mtm_include_current", C.c_int32), ("dream_sync_every", C.c_int32),
         ("seed", C.c_uint64), ("n_chains", C.c_int64), ("chain_offset", C.c_int64),
         ("n_chains_global", C.c_int64),
         ("prop_kind", C.c_int32), ("adaptive", C.c_int32), ("period", C.c_int32), ("am_t0", C.c_int32),

@@ -91,6 +91,7 @@ struct Params {
     R gamma, alpha_star, am_sd, am_eps, dream_b, dream_b_star;
     R scaling0;                // proposal.scaling at construction (restored by init)
     int dream_M0, dream_delta, dream_nCR;
+    int dream_sync;            // shared archive: rows become visible at multiples of this many steps (>= 1)
     long long dream_cap, dream_slots;
     R prior_logconst;
     const R* prior_mean;   // [d]

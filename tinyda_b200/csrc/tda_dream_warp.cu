@@ -241,6 +241,8 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dream_warp_kernel(const __grid_
     }
 
     long long slots = p.dream_slots;
+    const long long Ksync = p.dream_sync;       // shared archive: rows become visible at multiples of Ksync steps
+    unsigned nbar = 0;                           // barriers passed in this launch
     for (long long it = 0; it < p.iterations; it++) {
         const long long t = p.t_base + it;                       // base-level steps done before this one
 #pragma unroll
@@ -249,7 +251,9 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dream_warp_kernel(const __grid_
             const int g = wglobal + q * nwarps;
             const long long gchain = p.chain_offset + g;
             // ---- proposal (proposal.py:811-852) ----
-            const long long nslots = slots;
+            // rows per chain every chain may draw from: all rows (own archive), or the rows through the last
+            // synchronisation point (shared archive; Ksync = 1: through the previous step)
+            const long long nslots = shared_arch ? slots - ((slots - p.dream_M0) % Ksync) : slots;
             const long long M = shared_arch ? nslots * p.Cg : nslots;
             long long uc = ucur[q];
             // lanes 0 .. 2 delta - 1: the pair draws; lane 2 delta: the crossover draw
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dream_warp_kernel(const __grid_
             }
         }
         slots += 1;
-        if (p.grid_sync) dw_step_barrier<R>(p, (unsigned)it);
+        if (p.grid_sync && ((slots - p.dream_M0) % Ksync) == 0) dw_step_barrier<R>(p, nbar++);
     }
 
     // ---- write the chain state back (layout shared with the lock-step kernel) ----

@@ -430,6 +430,7 @@ struct EngineT : tda_engine {
         P.gamma = (R)c.gamma; P.alpha_star = (R)c.alpha_star; P.am_sd = (R)c.am_sd; P.am_eps = (R)c.am_eps;
         P.dream_b = (R)c.dream_b; P.dream_b_star = (R)c.dream_b_star;
         P.dream_M0 = c.dream_M0; P.dream_delta = c.dream_delta; P.dream_nCR = c.dream_nCR;
+        P.dream_sync = (c.prop_kind == TDA_PROP_DREAM && c.dream_sync_every > 1) ? c.dream_sync_every : 1;
         P.dream_cap = c.dream_capacity;
         P.prior_logconst = (R)c.prior_logconst;
         P.scaling0 = (R)c.scaling;
@@ -1024,6 +1025,8 @@ struct EngineT : tda_engine {
         if (kernel_choice == 7 && !tda::mlda_warp_eligible(cfg)) return fail(-1, "run: warp-per-chain MLDA kernel does not support this configuration");
         if (kernel_choice == 6 && !dreamw_eligible()) return fail(-1, "run: warp-per-chain DREAM kernel does not support this configuration");
         int which = resolved_kernel();
+        if (P.dream_sync > 1 && which != 6)
+            return fail(-1, "run: DREAM sync_every > 1 needs the warp-per-chain DREAM kernel (d <= 32, linear model, fixed crossover distribution)");
         if (which == 5) {
             // operand images on first use, whitened state when theta was last written by someone else; a
             // problem (or a chain state) outside the fp16 range falls back to the older kernels
@@ -1134,12 +1137,15 @@ struct EngineT : tda_engine {
             P.grid_sync = (P.prop_kind == TDA_PROP_DREAM) ? 1 : 0;
             if (P.grid_sync) {
                 CUDA_TRY(cudaMemsetAsync(P.grid_bar, 0, sizeof(unsigned int), st));
+                // barriers of this launch: one per multiple of dream_sync among the steps it takes
+                const long long K = P.dream_sync, done0 = dream_slots - P.dream_M0;
+                const unsigned int nbar = (unsigned int)((done0 + iterations) / K - done0 / K);
                 if (P.n_peers > 1 && P.arrive_mode) {
                     P.arr_base = arr_next;
-                    arr_next += (unsigned int)iterations;
+                    arr_next += nbar;
                 } else {
                     P.flag_base = flag_next;
-                    flag_next += (unsigned int)iterations;
+                    flag_next += nbar;
                 }
             }
             const int arrive_saved = P.arrive_mode;

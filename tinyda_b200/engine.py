@@ -151,6 +151,7 @@ class Engine:
             cfg.dream_nCR = int(prop["nCR"])
             cfg.dream_b = float(prop["b"])
             cfg.dream_b_star = float(prop["b_star"])
+            cfg.dream_sync_every = int(prop.get("sync_every", 1))
             # one archive row per base-level step (proposal.py:794): steps[0] of them per finest iteration
             cfg.dream_capacity = int(prop["M0"]) + int(capacity_iterations if archive_iterations is None else archive_iterations) * self.steps[0] + 1
         if rng == "injected":

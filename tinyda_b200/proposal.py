@@ -232,11 +232,29 @@ class DREAMZ(GaussianRandomWalk):
 
 
 class DREAM(DREAMZ):
-    """DREAM(Z) with an archive shared by all chains (proposal.py:1627-1656).  On one GPU
-    the archive is a single HBM array; across GPUs every step's new rows are all-gathered
-    over NCCL (see sampler.py)."""
+    """DREAM(Z) with an archive shared by all chains (proposal.py:1627-1656).  On one GPU the archive is a single
+    HBM array; across GPUs every rank holds a replica and the kernel stores each step's new rows into all of them
+    over NVLink peer memory (see sampler.py, parallel.connect_dream_peers).
+
+    ``sync_every`` (extension, default 1): how often the chains agree on what the shared archive holds.  The
+    reference's archive is a Ray actor that the chains read whenever they get to it -- how stale a chain's view is
+    is left to the scheduler.  Here it is deterministic: a chain at step t draws its pairs from all chains' rows
+    through the last multiple of ``sync_every`` below t (1: through step t-1, the lock-step rule the golden fixtures
+    were generated under).  Larger values trade a bounded staleness for fewer grid / NVLink barriers."""
 
     kind = PROP_DREAM
+
+    def __init__(self, M0, delta=1, b=5e-2, b_star=1e-6, Z_method="random", nCR=3,
+                 adaptive=False, gamma=1.01, period=100, sync_every=1):
+        super().__init__(M0, delta, b, b_star, Z_method, nCR, adaptive, gamma, period)
+        if int(sync_every) < 1:
+            raise ValueError("sync_every must be a positive integer")
+        self.sync_every = int(sync_every)
+
+    def lower(self, prior):
+        out = super().lower(prior)
+        out["sync_every"] = int(getattr(self, "sync_every", 1))
+        return out
 
 
 class MultipleTry(Proposal):
