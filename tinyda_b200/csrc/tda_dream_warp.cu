@@ -181,8 +181,11 @@ __device__ __forceinline__ void dw_step_barrier(const Params<R>& p, unsigned ste
     __syncthreads();
 }
 
-template <typename R>
-__global__ void __launch_bounds__(DW_THREADS, 2) dream_warp_kernel(const __grid_constant__ Params<R> p) {
+// OCC = resident CTAs per SM the register budget is cut for: 2 (128 registers) is the fast single-chain-per-warp
+// variant; 3 (80 registers, a few spills in float) is selected when the chains would otherwise queue up three and
+// four deep on a warp (cfg5's 8192 chains on ONE GPU).
+template <typename R, int OCC>
+__global__ void __launch_bounds__(DW_THREADS, OCC) dream_warp_kernel(const __grid_constant__ Params<R> p) {
     extern __shared__ __align__(16) unsigned char dw_smem[];
     const LevelP<R>& v = p.lv[0];
     const int d = p.d, m = v.m;
@@ -390,39 +393,58 @@ thread_local std::string g_dwerr;
 
 const char* dream_warp_last_error() { return g_dwerr.c_str(); }
 
-template <typename R>
-int dream_warp_grid(const Params<R>& P, int sm_count) {
-    const size_t smem = dw_smem_bytes<R>(P);
-    if (smem > 100 * 1024) return 0;
-    cudaFuncSetAttribute(dream_warp_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+namespace {
+template <typename R, int OCC>
+int dw_max_blocks(size_t smem, int sm_count) {
+    cudaFuncSetAttribute(dream_warp_kernel<R, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dream_warp_kernel<R>, DW_THREADS, smem) != cudaSuccess || per_sm < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dream_warp_kernel<R, OCC>, DW_THREADS, smem) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         return 0;
     }
-    const int max_blocks = per_sm * sm_count;
+    return per_sm * sm_count;
+}
+}  // namespace
+
+template <typename R>
+int dream_warp_grid(const Params<R>& P, int sm_count, int* occ) {
+    const size_t smem = dw_smem_bytes<R>(P);
+    if (smem > 100 * 1024) return 0;
     const int wpb = DW_THREADS / 32;
-    int blocks = (P.C + wpb - 1) / wpb;                          // one chain per warp if they all fit ...
-    if (blocks > max_blocks) blocks = max_blocks;                // ... else several chains per warp, all CTAs resident
+    const int want = (P.C + wpb - 1) / wpb;                      // one chain per warp if they all fit ...
+    int variant = 2;
+    int max_blocks = dw_max_blocks<R, 2>(smem, sm_count);
+    if (max_blocks < 1) return 0;
+    if (sizeof(R) == 4 && want > 2 * max_blocks && !getenv("TDA_DREAM_WARP_OCC2")) {
+        // more than two chains per warp: the variant with three resident CTAs per SM keeps more chains in flight
+        const int m3 = dw_max_blocks<R, 3>(smem, sm_count);
+        if (m3 > max_blocks) { max_blocks = m3; variant = 3; }
+    }
+    int blocks = want < max_blocks ? want : max_blocks;          // ... else several chains per warp, all CTAs resident
     if ((long long)blocks * wpb * DW_CPW < P.C) return 0;        // too many chains for the register-resident state
+    if (occ) *occ = variant;
     return blocks;
 }
 
 template <typename R>
-int dream_warp_launch(Params<R>& P, int grid, cudaStream_t st) {
+int dream_warp_launch(Params<R>& P, int grid, int occ, cudaStream_t st) {
     const size_t smem = dw_smem_bytes<R>(P);
-    cudaError_t e = cudaFuncSetAttribute(dream_warp_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-        dream_warp_kernel<R><<<grid, DW_THREADS, smem, st>>>(P);
-        e = cudaGetLastError();
+    cudaError_t e;
+    if (occ == 3) {
+        e = cudaFuncSetAttribute(dream_warp_kernel<R, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) dream_warp_kernel<R, 3><<<grid, DW_THREADS, smem, st>>>(P);
+    } else {
+        e = cudaFuncSetAttribute(dream_warp_kernel<R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) dream_warp_kernel<R, 2><<<grid, DW_THREADS, smem, st>>>(P);
     }
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { g_dwerr = std::string("dream warp kernel: ") + cudaGetErrorString(e); return -2; }
     return 0;
 }
 
-template int dream_warp_grid<float>(const Params<float>&, int);
-template int dream_warp_grid<double>(const Params<double>&, int);
-template int dream_warp_launch<float>(Params<float>&, int, cudaStream_t);
-template int dream_warp_launch<double>(Params<double>&, int, cudaStream_t);
+template int dream_warp_grid<float>(const Params<float>&, int, int*);
+template int dream_warp_grid<double>(const Params<double>&, int, int*);
+template int dream_warp_launch<float>(Params<float>&, int, int, cudaStream_t);
+template int dream_warp_launch<double>(Params<double>&, int, int, cudaStream_t);
 
 }  // namespace tda

@@ -19,10 +19,10 @@ inline bool dream_warp_eligible(const tda_config& c) {
 // number of CTAs of a launch in which every chain has its register-resident slot and all CTAs are co-resident
 // (the shared-archive variant ends each step in a grid-wide barrier); 0 = the job does not fit this kernel
 template <typename R>
-int dream_warp_grid(const Params<R>& P, int sm_count);
+int dream_warp_grid(const Params<R>& P, int sm_count, int* occ);      // *occ: kernel variant (resident CTAs per SM, 2 or 3)
 
 template <typename R>
-int dream_warp_launch(Params<R>& P, int grid, cudaStream_t st);
+int dream_warp_launch(Params<R>& P, int grid, int occ, cudaStream_t st);
 
 const char* dream_warp_last_error();
 

@@ -313,6 +313,7 @@ struct EngineT : tda_engine {
     void* mw_li = nullptr;
     void* mw_phi = nullptr;
     size_t mw_cls = 0, mw_phi_cls = 0;
+    int dreamw_occ = 2;        // its variant: resident CTAs per SM
     int dreamw_grid = -1;      // CTAs of the warp-per-chain DREAM kernel (-1: not asked yet, 0: the job does not fit)
     int z_round_user = 0;      // generic / TF32 kernels: use the z16 normal stream (tda_set TDA_G_ZROUND)
     std::vector<int> ldA;
@@ -918,7 +919,7 @@ struct EngineT : tda_engine {
     bool dreamw_eligible() const {
         static const bool off = getenv("TDA_NO_DREAM_WARP") != nullptr;
         if (off || !tda::dream_warp_eligible(cfg)) return false;
-        if (dreamw_grid < 0) const_cast<EngineT*>(this)->dreamw_grid = tda::dream_warp_grid<R>(P, sm_count);
+        if (dreamw_grid < 0) const_cast<EngineT*>(this)->dreamw_grid = tda::dream_warp_grid<R>(P, sm_count, &const_cast<EngineT*>(this)->dreamw_occ);
         return dreamw_grid > 0;
     }
     // 0: every current state fits the fp16-split kernel's theta image, 1: not, < 0: error
@@ -1150,7 +1151,7 @@ struct EngineT : tda_engine {
             }
             const int arrive_saved = P.arrive_mode;
             if (P.n_peers <= 1) P.arrive_mode = 0;
-            r = tda::dream_warp_launch<R>(P, dreamw_grid, st);
+            r = tda::dream_warp_launch<R>(P, dreamw_grid, dreamw_occ, st);
             P.arrive_mode = arrive_saved;
             P.grid_sync = 0;
             if (r) return fail(r, tda::dream_warp_last_error());
