@@ -12,6 +12,7 @@
 // in shared memory, and a step of a chain is a few hundred instructions of one warp.  The launch is persistent
 // over all steps; the shared-archive variant closes every step with the grid barrier / NVLink peer-memory
 // handshake of the lock-step kernel (Tile::step_barrier).
+#include <cstdlib>
 #include <string>
 
 #include "tda_dream_warp.h"

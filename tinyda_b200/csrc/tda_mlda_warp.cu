@@ -24,6 +24,7 @@
 //     two warp scans over the per-lane segment sums of 1/k_c and c/k_c (lane s owns the cells between sensors
 //     s-1 and s).  Algebraically the solution of the same tridiagonal system the reference model solves with the
 //     Thomas algorithm (models.py Poisson1D); agreement to rounding is what the parity tests check.
+#include <cstdlib>
 #include <string>
 
 #include "tda_mlda_warp.h"

@@ -5,6 +5,9 @@ constant uploads of the C ABI, and exposes run / fetch.  All arithmetic happens 
 library behind ``_lib``; importing this module fails loudly if that library is missing.
 """
 import ctypes as C
+import os
+import sys
+import time
 import warnings
 import weakref
 
@@ -178,7 +181,6 @@ class Engine:
             self.capacity.append(int(lc.hist_capacity))
         self.cfg = cfg
         self._h = C.c_void_p()
-        import os, time
         _t0 = time.perf_counter()
         check(lib.tda_engine_create(C.byref(cfg), self.device, C.byref(self._h)))
         _t1 = time.perf_counter()
@@ -229,7 +231,6 @@ class Engine:
         self.iterations_done = 0
         self.peers_connected = False
         if os.environ.get("TDA_PROFILE"):
-            import sys
             sys.stderr.write("[Engine] tda_engine_create %.2f ms, uploads %.2f ms\n" % ((_t1 - _t0) * 1e3, (time.perf_counter() - _t1) * 1e3))
 
     # ---- plumbing --------------------------------------------------------------------------
