@@ -60,6 +60,9 @@ template <> struct Vec4<double> {
     }
 };
 
+__device__ __forceinline__ float mw_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double mw_rsqrt(double x) { return rsqrt(x); }
+
 template <typename R>
 __device__ __forceinline__ R mw_sum(R v) {
 #pragma unroll
@@ -429,8 +432,8 @@ struct Mw {
                 // a non-positive pivot (near-singular bias covariance in this dtype) is clamped and flagged; the
                 // reference's np.linalg.inv does not fail there (distributions.py:402)
                 if (!(djj > (R)0)) { djj = (R)1e-30; if (lane == 0) *p.error_flag = 1; }
-                djj = tsqrt(djj);
-                const R inv = (R)1 / djj;
+                const R inv = mw_rsqrt(djj);               // one reciprocal square root instead of a square root and a division
+                djj = djj * inv;
                 __syncwarp();
                 if (lane >= j) acol[j * 32 + lane] = (lane == j) ? djj : s * inv;
                 if (lane == j) dinv[j] = inv;
