@@ -106,6 +106,7 @@ struct DaTc16Params {
     int* progress;            // [n_pairs] tile completions of this launch (2 per finished block)
     long long* dbg;           // optional timeline probe (tools/tc16_timeline.py): [role 4][256] clock64 stamps of CTA 0
     PhiloxRoundKeys rk;       // round keys of the engine's seed (constant-bank operands of the generator warps)
+    int direct_wait;          // single-tile modes: every row warp waits on the MMA's mbarrier itself
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -673,7 +674,18 @@ da_tc16_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ 
         // One warp per tile waits on the MMA's mbarrier; the other seven block in a named barrier
         // (blocked warps take no issue slots, spinning mbarrier waiters do).
         const bool leader = (h == 0 && wq == 0);
+        // Single-tile modes: the few active warps leave issue slots free, so every row warp waits on the mbarrier
+        // itself -- one synchronisation hop less on the step's dependency chain (MMA -> rows -> MMA), which is what
+        // paces a lone tile.  (No phase can be missed: the MMA behind the next completion of `bar` needs every row
+        // warp's arrival after this one.)
+        const bool direct_wait = solo && q.direct_wait;
         auto wait_mma = [&](uint64_t* bar, uint32_t& ph) {
+            if (direct_wait) {
+                tc::mbar_wait(bar, ph);
+                ph ^= 1;
+                tc::fence_after_sync();
+                return;
+            }
             if (leader) tc::mbar_wait(bar, ph);
             ph ^= 1;
             tc::named_bar_sync(3 + t, nbt);
@@ -1216,6 +1228,7 @@ struct DaTc16State<float> {
         }
         q.dbg = dDbg;
         q.rk = philox_round_keys(P.seed);
+        q.direct_wait = getenv("TDA_TC16_LEADER_WAIT") ? 0 : 1;
         const int grid = q.n_pairs < sm_count ? q.n_pairs : sm_count;
         // iteration blocks: the smallest block count (<= 16) whose round-robin deal of the
         // (pair, block) units fills at least 97 % of the last wave, else the best one
