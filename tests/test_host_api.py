@@ -388,3 +388,21 @@ def test_ess_and_rhat_from_sums_equal_the_array_estimators():
     s2, f2 = _ess_sums_numpy(x, n_lag=120)
     ess2, _ = ess_rhat_from_sums(s2[None, :], f2[None, :])
     assert abs(ess2[0] / ess[0] - 1) < 0.05
+
+
+def test_dream_sync_every_extension_is_validated_and_lowered():
+    """DREAM(..., sync_every=K) (bounded staleness of the shared archive): the reference's signature is
+    unchanged by default, a non-positive value is refused, the value reaches the lowered spec, DREAMZ has no such
+    option."""
+    import scipy.stats as stats
+    import tinyda_b200 as tda
+    from tinyda_b200.lowering import lower_problem
+    prior = stats.multivariate_normal(np.zeros(3), np.eye(3))
+    post = tda.Posterior(prior, tda.GaussianLogLike(np.zeros(4), 0.1 * np.eye(4)), tda.LinearModel(np.ones((4, 3))))
+    assert int(lower_problem([post], tda.DREAM(M0=5))["proposal"]["sync_every"]) == 1
+    assert int(lower_problem([post], tda.DREAM(M0=5, sync_every=6))["proposal"]["sync_every"]) == 6
+    with pytest.raises(ValueError):
+        tda.DREAM(M0=5, sync_every=0)
+    with pytest.raises(TypeError):
+        tda.DREAMZ(M0=5, sync_every=2)
+    assert "sync_every" not in lower_problem([post], tda.DREAMZ(M0=5))["proposal"]
