@@ -536,3 +536,83 @@ def test_tc16_single_tile_modes_are_bit_identical_to_the_paired_mode(monkeypatch
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert np.array_equal(a, b)
+
+
+def _cfg2_rwmh(C, kernel, iters, dtype="float32", rng="philox", streams=None, seed=9):
+    """cfg2's problem with a GaussianRandomWalk proposal (dense covariance, fixed step) instead of pCN."""
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
+    from tinyda_b200.proposal import GaussianRandomWalk
+    from tinyda_b200.workloads import cfg2_da, exp_cov
+    w = cfg2_da()
+    prop = GaussianRandomWalk(C=exp_cov(64, 0.3), scaling=0.02)
+    spec = lower_problem(w["posteriors"], prop, 10)
+    theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1))
+    eng = Engine(spec, C, dtype=dtype, rng=rng, seed=seed, streams=streams, store=[STORE_NONE, STORE_STATS],
+                 capacity_iterations=iters)
+    eng.select_kernel(kernel)
+    eng.init(theta0)
+    return eng, spec, theta0
+
+
+def _prefix_agreement(th_a, acc_a, th_r, acc_r, jump=1e-4):
+    """Per chain: records before the first flipped decision -- a differing fine-level accept flag, or a state that
+    differs by more than `jump` relative (a flipped COARSE decision inside a subchain moves the state by a proposal
+    step without touching the fine-level flags; the coarse chain is not recorded on this kernel).  Returns (records
+    before a flip, all records, largest relative state error before the flip)."""
+    n, _, C = th_a.shape
+    matched, worst = 0, 0.0
+    for c in range(C):
+        sc = np.abs(th_r[:, :, c]).max() + 1e-30
+        err = np.abs(th_a[:, :, c] - th_r[:, :, c]).max(axis=1) / sc
+        bad = (acc_a[:, c] != acc_r[:, c]) | (err > jump)
+        k = int(np.argmax(bad)) if bad.any() else n
+        matched += k
+        if k:
+            worst = max(worst, float(err[:k].max()))
+    return matched, n * C, worst
+
+
+def test_random_walk_delayed_acceptance_runs_on_the_tensor_cores():
+    """GaussianRandomWalk-based two-level DA at cfg2's shape (proposal.py:132-258: theta' = theta + s xi, the
+    acceptance is the full posterior ratio): selected automatically onto the 3xTF32 tcgen05 kernel (a third job per
+    coarse step, theta' @ LP, gives the proposal's log-prior).  Against the lock-step float32 kernel on the same
+    Philox streams, and against the float64 engine fed those streams: identical trajectories up to a first near-tie,
+    states within 1e-5 relative before it (north_star's float32 tolerance)."""
+    import problems
+    C, iters = 512, 25
+    a, spec, theta0 = _cfg2_rwmh(C, "auto", iters)
+    assert a.kernel() == "tc"
+    b, _, _ = _cfg2_rwmh(C, "generic", iters)
+    a.run(iters)
+    b.run(iters)
+    acc_a, acc_b = a.fetch(1, "accept"), b.fetch(1, "accept")
+    th_a, th_b = a.fetch(1, "theta"), b.fetch(1, "theta")
+    assert (acc_a == acc_b).mean() > 0.97
+    assert np.array_equal(a.get("cursors")[0], b.get("cursors")[0])
+    ca, cb = a.get("accept_counts"), b.get("accept_counts")
+    assert ca[0].mean() > 0.02 * iters * 10 and abs(ca[0].mean() - cb[0].mean()) < 0.05 * cb[0].mean() + 1
+    m_g, tot, w_g = _prefix_agreement(th_a, acc_a, th_b, acc_b)
+    nz, nu = problems.stream_sizes(spec, iters)
+    z, u = a.fill_streams(nz, nu)
+    ref, _, _ = _cfg2_rwmh(C, "generic", iters, dtype="float64", rng="injected", streams=(z, u))
+    ref.run(iters)
+    m_r, _, w_r = _prefix_agreement(th_a, acc_a, ref.fetch(1, "theta"), ref.fetch(1, "accept"))
+    print("\ntc (random walk, float32): %d of %d fine records before a first flip against the lock-step float32 kernel "
+          "(max relative state error %.2e), %d against the float64 engine on the same streams (%.2e)" % (m_g, tot, w_g, m_r, w_r))
+    assert m_g >= 0.8 * tot and m_r >= 0.8 * tot
+    assert w_g <= 1e-5 and w_r <= 1e-5
+    for e in (a, b, ref):
+        e.close()
+
+
+def test_random_walk_tensor_core_kernel_resume_is_exact():
+    outs = []
+    for cuts in ([12], [5, 7]):
+        eng, _, _ = _cfg2_rwmh(512, "tc", sum(cuts))
+        for n in cuts:
+            eng.run(n)
+        outs.append((eng.fetch(1, "theta"), eng.fetch(1, "like"), eng.fetch(1, "prior"), eng.get("cursors")))
+        eng.close()
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y)

@@ -187,8 +187,10 @@ constexpr int TC_PROD_WARP = 17;
 constexpr int TC_THREADS = 32 * 18;
 constexpr int TC_HK = TC_K / 2;             // theta columns per thread
 constexpr int TC_CHUNK_BYTES = TC_CH * TC_K * 4 * 2;   // hi + lo
-constexpr size_t TC_SMEM_BYTES = (size_t)(2 * 64 * TC_K + 2 * TC_MAX_MC * TC_K) * 4 + (size_t)TC_NST * TC_CHUNK_BYTES +
-                                 (size_t)(2 * 2 * 2 * 128 + 2 * 2 * 2 * 128) * 4 + 256;
+inline size_t tc_smem_bytes(int rwmh, int nst) {
+    return (size_t)(2 * 64 * TC_K + 2 * TC_MAX_MC * TC_K + (rwmh ? 2 * 64 * TC_K : 0)) * 4 + (size_t)nst * TC_CHUNK_BYTES +
+           (size_t)(3 * 2 * 2 * 2 * 128) * 4 + 256;
+}
 
 __constant__ float c_yc[TC_MAX_MC];         // coarse data - offset
 __constant__ float c_yf[TC_MAX_MF];         // fine data - offset
@@ -201,6 +203,11 @@ struct DaTcParams {
     int mc, mf, n_chunks, J;
     float var_c, var_f, prior_logconst;
     int n_pairs;
+    // GaussianRandomWalk instead of pCN (proposal.py:247-258): theta' = theta + s xi, and the acceptance needs the
+    // proposal's log-prior as well -- a third job per coarse step, theta' @ LP, against a resident copy of LP; the
+    // ring then has two stages instead of three (shared memory)
+    int rwmh, nst;
+    const float* LP_hl;      // canonical [hi 64x64 | lo 64x64] (the last chunk of F_chunks)
 };
 
 __device__ __forceinline__ void tc_issue_job(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi_saddr, uint32_t b_lo_saddr, int N) {
@@ -244,15 +251,20 @@ __device__ __forceinline__ void tc_warp_arrive(uint64_t* bar, int lane) {
     if (lane == 0) tc::mbar_arrive(bar);
 }
 
+// RW = false: pCN (two jobs per coarse step, three ring stages); RW = true: random walk (see DaTcParams::rwmh)
+template <bool RW>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ DaTcParams q) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sT = reinterpret_cast<float*>(smem);                         // 32 KB (hi | lo)
     float* sGc = sT + 2 * 64 * TC_K;                                    // 64 KB (hi | lo), sized for mc = 128
-    unsigned char* ring = reinterpret_cast<unsigned char*>(sGc + 2 * TC_MAX_MC * TC_K);   // NST x 32 KB
-    float* s_part = reinterpret_cast<float*>(ring + TC_NST * TC_CHUNK_BYTES);   // [buf 2][tile 2][half 2][128]
+    float* sLP = sGc + 2 * TC_MAX_MC * TC_K;                            // 32 KB (hi | lo), random-walk variant only
+    constexpr int NST = RW ? 2 : TC_NST;
+    unsigned char* ring = reinterpret_cast<unsigned char*>(sLP + (RW ? 2 * 64 * TC_K : 0));   // NST x 32 KB
+    float* s_part = reinterpret_cast<float*>(ring + NST * TC_CHUNK_BYTES);      // [buf 2][tile 2][half 2][128]
     float* s_pf = s_part + 2 * 2 * 2 * 128;                                      // [tile 2][half 2][val 2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_pf + 2 * 2 * 2 * 128);
+    float* s_part2 = s_pf + 2 * 2 * 2 * 128;                                     // [buf 2][tile 2][half 2][128] prior partials
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part2 + 2 * 2 * 2 * 128);
     uint64_t* bar_res = bars;            // resident operands landed
     uint64_t* bar_req = bars + 1;        // [tile 2][buffer 2]
     uint64_t* bar_resp = bars + 5;       // [tile 2][buffer 2]
@@ -265,7 +277,7 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
     if (tid == TC_PROD_WARP * 32) {
         tc::mbar_init(bar_res, 1);
         for (int i = 0; i < 4; i++) { tc::mbar_init(bar_req + i, 8); tc::mbar_init(bar_resp + i, 1); }
-        for (int s = 0; s < TC_NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 2); }
+        for (int s = 0; s < NST; s++) { tc::mbar_init(bar_full + s, 1); tc::mbar_init(bar_empty + s, 2); }
         tc::fence_mbar_init();
     }
     tc::fence_before_sync();
@@ -282,15 +294,16 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
         if (lane == 0) {
             const long long total_chunks = (long long)my_pairs * iters * NCH;
             const uint32_t bT = 2u * 64 * TC_K * 4, bG = 2u * (uint32_t)mc * TC_K * 4;
-            tc::mbar_expect_tx(bar_res, bT + bG);
+            tc::mbar_expect_tx(bar_res, bT + bG + (RW ? bT : 0u));
             tc::bulk_g2s(sT, q.T_hl, bT, bar_res);
+            if (RW) tc::bulk_g2s(sLP, q.LP_hl, bT, bar_res);
             // hi part and lo part of G_c are stored back to back in global; in shared memory the lo
             // part starts at the fixed offset used by the MMA warp (mc rows each)
             tc::bulk_g2s(sGc, q.Gc_hl, bG / 2, bar_res);
             tc::bulk_g2s(sGc + TC_MAX_MC * TC_K, q.Gc_hl + (size_t)mc * TC_K, bG / 2, bar_res);
             for (long long g = 0; g < total_chunks; g++) {
-                const int st = (int)(g % TC_NST);
-                if (g >= TC_NST) tc::mbar_wait(bar_empty + st, (uint32_t)(((g / TC_NST) - 1) & 1));
+                const int st = (int)(g % NST);
+                if (g >= NST) tc::mbar_wait(bar_empty + st, (uint32_t)(((g / NST) - 1) & 1));
                 const int c = (int)(g % NCH);
                 tc::mbar_expect_tx(bar_full + st, TC_CHUNK_BYTES);
                 tc::bulk_g2s(ring + (size_t)st * TC_CHUNK_BYTES, q.F_chunks + (size_t)c * (TC_CHUNK_BYTES / 4), TC_CHUNK_BYTES, bar_full + st);
@@ -302,7 +315,9 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
             tc::mbar_wait(bar_res, 0);
             const uint32_t sT_hi = tc::smem_u32(sT), sT_lo = sT_hi + 64 * TC_K * 4;
             const uint32_t sG_hi = tc::smem_u32(sGc), sG_lo = sG_hi + TC_MAX_MC * TC_K * 4;
-            const int JOBS = 2 * J + NCH;
+            const uint32_t sL_hi = tc::smem_u32(sLP), sL_lo = sL_hi + 64 * TC_K * 4;
+            constexpr int CJ = RW ? 3 : 2;                  // jobs per coarse step
+            const int JOBS = CJ * J + NCH;
             const long long total = (long long)my_pairs * iters * JOBS;
             long long n0 = 0, n1 = 0, g0 = 0, g1 = 0;      // jobs done / chunks consumed per tile
             int q0 = 0, q1 = 0;                             // position inside the iteration
@@ -315,20 +330,22 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                     int& qq = t ? q1 : q0;
                     if (n >= total) continue;
                     const uint32_t tA = tbase + t * 256, tD = tA + 128;
-                    if (qq < 2 * J) {
+                    if (qq < CJ * J) {
                         uint64_t* rq = bar_req + t * 2;
                         if (!tc::mbar_test(rq, (rph >> (t * 2)) & 1u)) continue;
                         rph ^= 1u << (t * 2);
                         tc::fence_after_sync();
-                        if (qq & 1) tc_issue_job(tD, tA, sG_hi, sG_lo, mc);      // F_c = theta' @ G_c^T
-                        else tc_issue_job(tD, tA, sT_hi, sT_lo, 64);            // xi = z @ T
+                        const int kind = qq % CJ;
+                        if (kind == 1) tc_issue_job(tD, tA, sG_hi, sG_lo, mc);          // F_c = theta' @ G_c^T
+                        else if (kind == 0) tc_issue_job(tD, tA, sT_hi, sT_lo, 64);     // xi = z @ T
+                        else tc_issue_job(tD, tA, sL_hi, sL_lo, 64);                    // (theta') @ LP (random walk)
                         tc::mma_commit(bar_resp + t * 2);
                     } else {
-                        const int c = qq - 2 * J, b = c & 1;
-                        const int st = (int)(gch % TC_NST);
+                        const int c = qq - CJ * J, b = c & 1;
+                        const int st = (int)(gch % NST);
                         uint64_t* rq = bar_req + t * 2 + b;
                         if (!tc::mbar_test(rq, (rph >> (t * 2 + b)) & 1u)) continue;
-                        if (!tc::mbar_test(bar_full + st, (uint32_t)((gch / TC_NST) & 1))) continue;
+                        if (!tc::mbar_test(bar_full + st, (uint32_t)((gch / NST) & 1))) continue;
                         rph ^= 1u << (t * 2 + b);
                         tc::fence_after_sync();
                         const uint32_t b_hi = tc::smem_u32(ring + (size_t)st * TC_CHUNK_BYTES), b_lo = b_hi + TC_CH * TC_K * 4;
@@ -374,11 +391,12 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
             const size_t cs = (size_t)p.Cs;
             const size_t off0 = (size_t)col0 * cs + g;      // this thread's first column, this chain
             float like_c = l0.like[g], like_cs = like_c, like_f = l1.like[g], prior_f = l1.prior[g];
+            float prior_c = l0.prior[g], prior_cs = prior_c;        // random walk: log-prior of the coarse state / of the subchain start
             long long ucur = p.ucur[g];
             int nacc_c = 0, nacc_f = 0;
             int acc_any = 0;
             const float s = p.scaling[g];
-            const float ca = sqrtf(1.0f - s * s), cb = s;
+            const float ca = RW ? 1.0f : sqrtf(1.0f - s * s), cb = s;
             long long tb = p.t_base;
 
             for (long long it = 0; it < iters; it++) {
@@ -433,12 +451,39 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                             ssq = fmaf(r, r, ssq);
                         }
                     }
+                    float ssq_pc = 0.0f;
+                    if (RW) {
+                        // third job: (theta') @ LP into the accumulator the residual pass has just released
+                        tc_warp_arrive(req, lane);
+                        tc::mbar_wait(resp, ph0); ph0 ^= 1;
+                        tc::fence_after_sync();
+                        uint32_t v0[16], v1[16];
+                        tc::tmem_ld16(tD + col0, v0);
+                        tc::tmem_ld16(tD + col0 + 16, v1);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float w0 = __uint_as_float(v0[i]) - c_lp[col0 + i];
+                            const float w1 = __uint_as_float(v1[i]) - c_lp[col0 + 16 + i];
+                            ssq_pc = fmaf(w0, w0, ssq_pc);
+                            ssq_pc = fmaf(w1, w1, ssq_pc);
+                        }
+                    }
                     float* sp = s_part + ((sbuf * 2 + t) * 2) * 128;
+                    float* sp2 = s_part2 + ((sbuf * 2 + t) * 2) * 128;
                     sp[h * 128 + cl] = ssq;
+                    if (RW) sp2[h * 128 + cl] = ssq_pc;
                     sbuf ^= 1;
                     tc::named_bar_sync(1 + t, 256);
                     const float like_p = inv2vc * (sp[cl] + sp[128 + cl]);
-                    const float alpha = isnan(like_p) ? 0.0f : expf(like_p - like_c);
+                    float prior_p = 0.0f, alpha;
+                    if (RW) {
+                        // chain.py:105-117 with proposal.py:253-258: the full posterior ratio
+                        prior_p = -0.5f * (q.prior_logconst + (sp2[cl] + sp2[128 + cl]));
+                        alpha = isnan(prior_p + like_p) ? 0.0f : expf((prior_p + like_p) - (prior_c + like_c));
+                    } else {
+                        alpha = isnan(like_p) ? 0.0f : expf(like_p - like_c);
+                    }
                     float u;
                     if (inj) u = (live && ucur < p.ulen) ? p.us[(size_t)g * p.ulen + ucur] : 0.5f;
                     else u = philox_uniform<float>(p.seed, gchain, ucur);
@@ -457,7 +502,7 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                                 th[c0 + i] = acc ? __uint_as_float(vh[i]) + __uint_as_float(vl[i]) : th[c0 + i];
                         }
                     }
-                    if (acc) { like_c = like_p; acc_any = 1; nacc_c++; }
+                    if (acc) { like_c = like_p; prior_c = prior_p; acc_any = 1; nacc_c++; }
                     tb++;
                 }
                 // ---- fine level: A <- current coarse state ----
@@ -512,12 +557,13 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                     accf = (u < alpha2) ? 1 : 0;
                 }
                 if (accf) {
-                    like_f = like_fp; prior_f = prior_p; like_cs = like_c; nacc_f++;
+                    like_f = like_fp; prior_f = prior_p; like_cs = like_c; prior_cs = prior_c; nacc_f++;
                     float* dst = tc_opaque(l1.theta + off0);
 #pragma unroll
                     for (int k = 0; k < TC_HK; k++) dst[k * cs] = th[k];
                 } else {
                     like_c = like_cs;
+                    prior_c = prior_cs;
                     const float* src = tc_opaque(l1.theta + off0);
 #pragma unroll
                     for (int k = 0; k < TC_HK; k++) th[k] = src[k * cs];
@@ -586,7 +632,8 @@ struct DaTcState<float> {
     std::vector<float> yc, yf, clp;
 
     bool eligible(const tda_config& c, const Params<float>& P) const {
-        if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.mtm_k || c.prop_kind != TDA_PROP_PCN || c.adaptive) return false;
+        if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.mtm_k || c.adaptive) return false;
+        if (c.prop_kind != TDA_PROP_PCN && c.prop_kind != TDA_PROP_RWMH) return false;
         if (c.d != TC_K) return false;
         for (int l = 0; l < 2; l++)
             if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
@@ -659,6 +706,9 @@ struct DaTcState<float> {
             clp[n] = (float)a;
         }
         q.T_hl = dT; q.Gc_hl = dGc; q.F_chunks = dF;
+        q.rwmh = (c.prop_kind == TDA_PROP_RWMH) ? 1 : 0;
+        q.nst = q.rwmh ? 2 : TC_NST;
+        q.LP_hl = dF + (size_t)nfc * 2 * TC_CH * TC_K;
         q.mc = mc; q.mf = mf; q.n_chunks = nch; q.J = c.subchain[0];
         q.var_c = (float)c.level[0].lik_var; q.var_f = (float)c.level[1].lik_var;
         q.prior_logconst = (float)c.prior_logconst;
@@ -674,13 +724,15 @@ struct DaTcState<float> {
         if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_lp, clp.data(), TC_K * 4, 0, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) { err = std::string("tc constants: ") + cudaGetErrorString(e); return -2; }
         q.n_pairs = P.Cs / 256;
-        const size_t smem = TC_SMEM_BYTES;
-        e = cudaFuncSetAttribute(da_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const size_t smem = tc_smem_bytes(q.rwmh, q.nst);
+        e = q.rwmh ? cudaFuncSetAttribute(da_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                   : cudaFuncSetAttribute(da_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { err = std::string("tc attr: ") + cudaGetErrorString(e); return -2; }
         P.mode = MODE_RUN;
         P.iterations = iterations;
         int grid = q.n_pairs < sm_count ? q.n_pairs : sm_count;
-        da_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P, q);
+        if (q.rwmh) da_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(P, q);
+        else da_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(P, q);
         e = cudaGetLastError();
         if (e != cudaSuccess) { err = std::string("tc launch: ") + cudaGetErrorString(e); return -2; }
         return 0;
