@@ -538,14 +538,14 @@ def test_tc16_single_tile_modes_are_bit_identical_to_the_paired_mode(monkeypatch
             assert np.array_equal(a, b)
 
 
-def _cfg2_rwmh(C, kernel, iters, dtype="float32", rng="philox", streams=None, seed=9):
-    """cfg2's problem with a GaussianRandomWalk proposal (dense covariance, fixed step) instead of pCN."""
+def _cfg2_rwmh(C, kernel, iters, dtype="float32", rng="philox", streams=None, seed=9, adaptive=False):
+    """cfg2's problem with a GaussianRandomWalk proposal (dense covariance) instead of pCN."""
     from tinyda_b200 import lower_problem
     from tinyda_b200.engine import Engine, STORE_STATS, STORE_NONE
     from tinyda_b200.proposal import GaussianRandomWalk
     from tinyda_b200.workloads import cfg2_da, exp_cov
     w = cfg2_da()
-    prop = GaussianRandomWalk(C=exp_cov(64, 0.3), scaling=0.02)
+    prop = GaussianRandomWalk(C=exp_cov(64, 0.3), scaling=0.02, adaptive=adaptive, period=15)
     spec = lower_problem(w["posteriors"], prop, 10)
     theta0 = w["prior"].rvs(C, random_state=np.random.default_rng(1))
     eng = Engine(spec, C, dtype=dtype, rng=rng, seed=seed, streams=streams, store=[STORE_NONE, STORE_STATS],
@@ -616,3 +616,36 @@ def test_random_walk_tensor_core_kernel_resume_is_exact():
         eng.close()
     for x, y in zip(*outs):
         assert np.array_equal(x, y)
+
+
+def test_adaptive_random_walk_delayed_acceptance_on_the_tensor_cores():
+    """GaussianRandomWalk(adaptive=True) -- what the reference's notebooks use -- at cfg2's shape: the accept window
+    (coarse decisions + the alignment entry of every fine iteration) and the step-size rule of proposal.py:228-245
+    inside the tcgen05 kernel, across several adaptation periods (period 15, 275 window entries).  Against the
+    float64 engine on the same streams: trajectories and adapted step sizes."""
+    import problems
+    C, iters = 512, 25
+    a, spec, theta0 = _cfg2_rwmh(C, "auto", iters, adaptive=True)
+    assert a.kernel() == "tc"
+    a.run(11)
+    a.run(iters - 11)                                   # the window and the counters carry over launches
+    acc_a, th_a, sc_a = a.fetch(1, "accept"), a.fetch(1, "theta"), a.get("scaling")
+    nz, nu = problems.stream_sizes(spec, iters)
+    z, u = a.fill_streams(nz, nu)
+    ref, _, _ = _cfg2_rwmh(C, "generic", iters, dtype="float64", rng="injected", streams=(z, u), adaptive=True)
+    ref.run(iters)
+    acc_r, th_r, sc_r = ref.fetch(1, "accept"), ref.fetch(1, "theta"), ref.get("scaling")
+    m, tot, w = _prefix_agreement(th_a, acc_a, th_r, acc_r)
+    print("\ntc (adaptive random walk, float32) vs float64: %d of %d fine records before a first flip, max relative state "
+          "error %.2e" % (m, tot, w))
+    assert m >= 0.8 * tot and w <= 1e-5
+    assert np.array_equal(a.get("cursors")[0], ref.get("cursors")[0])
+    assert np.ptp(sc_r) > 0 and not np.allclose(sc_r, 0.02)
+    # chains that never flipped adapted their step exactly like the float64 run
+    n = th_a.shape[0]
+    clean = np.array([(acc_a[:, c] == acc_r[:, c]).all() and
+                      (np.abs(th_a[:, :, c] - th_r[:, :, c]).max() <= 1e-4 * np.abs(th_r[:, :, c]).max()) for c in range(C)])
+    assert clean.mean() > 0.7
+    np.testing.assert_allclose(sc_a[clean], sc_r[clean], rtol=2e-5)
+    a.close()
+    ref.close()

@@ -395,9 +395,30 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
             long long ucur = p.ucur[g];
             int nacc_c = 0, nacc_f = 0;
             int acc_any = 0;
-            const float s = p.scaling[g];
-            const float ca = RW ? 1.0f : sqrtf(1.0f - s * s), cb = s;
+            float ca, cb;
+            {
+                const float s = __ldcg(p.scaling + g);
+                ca = RW ? 1.0f : sqrtf(1.0f - s * s);
+                cb = s;
+            }
             long long tb = p.t_base;
+            // adaptive global scaling (proposal.py:228-245): the `accepted` window of the last `period` entries -- coarse
+            // decisions and the alignment entry of every fine iteration -- as a ring in global memory shared with the
+            // lock-step kernel; kept by the h == 0 thread of the chain (same scheme as the whitened-state kernel)
+            const bool adaptive = p.adaptive != 0;
+            int wsum = (adaptive && h == 0) ? __ldcg(p.win_sum + g) : 0;
+            long long wc = p.wcount;
+            int wpos = adaptive ? (int)(wc % p.period) : 0;
+            auto window_append = [&](int a) {
+                if (h == 0) {
+                    uint8_t* slot = p.win + (size_t)wpos * cs + g;
+                    const int old = (wc >= p.period) ? (int)__ldcg(slot) : 0;
+                    *slot = (uint8_t)a;
+                    wsum += a - old;
+                }
+                wc++;
+                wpos = (wpos + 1 == p.period) ? 0 : wpos + 1;
+            };
 
             for (long long it = 0; it < iters; it++) {
                 for (int j = 0; j < J; j++) {
@@ -504,6 +525,21 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                     }
                     if (acc) { like_c = like_p; prior_c = prior_p; acc_any = 1; nacc_c++; }
                     tb++;
+                    if (adaptive) {
+                        window_append(acc ? 1 : 0);
+                        if ((tb % p.period) == 0) {                   // tb: proposal.t after this step
+                            if (h == 0) {
+                                const long long kk = tb / p.period - 1;
+                                const float rate = (float)wsum / (float)p.period;
+                                const float s_old = __ldcg(p.scaling + g);
+                                p.scaling[g] = expf(logf(s_old) + powf(p.gamma, (float)(-(double)kk)) * (rate - p.alpha_star));
+                            }
+                            tc::named_bar_sync(1 + t, 256);          // the other half-thread of the chain reads the new step
+                            const float s_new = __ldcg(p.scaling + g);
+                            ca = RW ? 1.0f : sqrtf(1.0f - s_new * s_new);
+                            cb = s_new;
+                        }
+                    }
                 }
                 // ---- fine level: A <- current coarse state ----
 #pragma unroll
@@ -569,6 +605,7 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                     for (int k = 0; k < TC_HK; k++) th[k] = src[k * cs];
                 }
                 acc_any = 0;
+                if (adaptive) window_append(accf);                   // the alignment entry (chain.py:391, :397)
                 // ---- fine-level record (coalesced: consecutive lanes = consecutive chains) ----
                 const long long r = p.rec[1] + it;
                 if (r < l1.hist_cap) {
@@ -605,6 +642,7 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                 l0.acc_sub[g] = 0;
                 l0.n_acc[g] += nacc_c; l1.n_acc[g] += nacc_f;
                 p.ucur[g] = ucur;
+                if (adaptive) p.win_sum[g] = wsum;
             }
             // both halves must have read the pair's scalars before anyone starts the next pair's
             // loads only matters for p.ucur / like arrays of THIS pair, which are per chain: no hazard
@@ -632,7 +670,8 @@ struct DaTcState<float> {
     std::vector<float> yc, yf, clp;
 
     bool eligible(const tda_config& c, const Params<float>& P) const {
-        if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.mtm_k || c.adaptive) return false;
+        if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.mtm_k) return false;
+        if (c.adaptive && (c.period < 1 || !P.win || !P.win_sum)) return false;
         if (c.prop_kind != TDA_PROP_PCN && c.prop_kind != TDA_PROP_RWMH) return false;
         if (c.d != TC_K) return false;
         for (int l = 0; l < 2; l++)
