@@ -44,6 +44,16 @@ def cfg2_da(seed=2, d=64, m_f=1024, m_c=128, J=10, beta=0.05):
                 name="cfg2: 2-level DA, pCN, linear-Gaussian %d params / %d obs (coarse %d), J=%d" % (d, m_f, m_c, J))
 
 
+def cfg2_rw(seed=2, adaptive=True):
+    """cfg2's problem with the proposal most tinyDA notebooks use: an adaptively scaled Gaussian random walk (dense
+    covariance) instead of pCN -- the acceptance then needs the proposal's log-prior too."""
+    from .proposal import GaussianRandomWalk
+    w = cfg2_da(seed=seed)
+    w["proposal"] = GaussianRandomWalk(C=exp_cov(64, 0.3), scaling=0.02, adaptive=adaptive, period=100)
+    w["name"] = "cfg2 shape, 2-level DA with GaussianRandomWalk(adaptive=%s): 64 params / 1024 obs (coarse 128), J=10" % adaptive
+    return w
+
+
 def cfg3_mala(seed=3):
     """MALA on the 2-D Rosenbrock likelihood (examples/MALA Rosenbrock.ipynb)."""
     prior = stats.multivariate_normal(np.zeros(2), np.eye(2))
@@ -90,4 +100,4 @@ def conjugate_posterior(G, y, sigma2, prior):
     return mu, S
 
 
-WORKLOADS = dict(cfg1=cfg1_linreg, cfg2=cfg2_da, cfg3=cfg3_mala, cfg4=cfg4_mlda, cfg5=cfg5_dream)
+WORKLOADS = dict(cfg1=cfg1_linreg, cfg2=cfg2_da, cfg2rw=cfg2_rw, cfg3=cfg3_mala, cfg4=cfg4_mlda, cfg5=cfg5_dream)
