@@ -418,3 +418,34 @@ def test_sample_defaults_on_cfg2_run_on_the_tensor_core_kernel():
             np.testing.assert_allclose(link.prior, w["prior"].logpdf(th), rtol=2e-4, atol=2e-2)
             np.testing.assert_allclose(link.posterior, link.prior + link.likelihood, rtol=1e-6)
     eng.close()
+
+
+def test_sample_defaults_with_an_adaptive_random_walk_run_on_the_tensor_core_kernel():
+    """tda.sample([coarse, fine], GaussianRandomWalk(C, adaptive=True), ...) with the reference's default storage
+    (coarse chain kept, Link.model_output kept) at cfg2's shape: the 3xTF32 tcgen05 kernel records the coarse chain's
+    parameters, log-likelihoods and accept flags; log-priors and model outputs are rebuilt from the parameters when the
+    Links are fetched.  Complete, self-consistent Links at both levels; the coarse chain moves."""
+    import tinyda_b200 as tda
+    from tinyda_b200.workloads import cfg2_rw
+    w = cfg2_rw()
+    C, iters, J = 256, 8, 10
+    res, eng = tda.sample(w["posteriors"], w["proposal"], iters, n_chains=C, subchain_length=J, seed=3,
+                          dtype="float32", return_engine=True)
+    assert eng.kernel() == "tc"
+    assert res["sampler"] == "DA" and res["iterations"] == iters + 1 and res["subchain_length"] == J
+    idx = np.arange(0, 1024, 8)
+    moved = 0
+    for c in (0, 5, 255):
+        coarse, fine = res["chain_coarse_%d" % c], res["chain_fine_%d" % c]
+        assert len(coarse) == J * iters and len(fine) == iters + 1
+        moved += int(np.abs(np.asarray(coarse[-1].parameters) - np.asarray(coarse[0].parameters)).max() > 0)
+        for seq, G, y in ((coarse, w["G"][idx], w["y"][idx]), (fine, w["G"], w["y"])):
+            for link in (seq[0], seq[len(seq) // 2], seq[-1]):
+                th = np.asarray(link.parameters, dtype=np.float64)
+                F = G @ th
+                np.testing.assert_allclose(link.model_output, F, rtol=1e-4, atol=1e-5 * np.abs(F).max())
+                np.testing.assert_allclose(link.likelihood, -0.5 * ((F - y) ** 2).sum() / w["sigma2"], rtol=2e-4, atol=2e-2)
+                np.testing.assert_allclose(link.prior, w["prior"].logpdf(th), rtol=2e-4, atol=2e-2)
+                np.testing.assert_allclose(link.posterior, link.prior + link.likelihood, rtol=1e-6)
+    assert moved >= 2
+    eng.close()

@@ -393,17 +393,18 @@ def test_tc16_diagonal_and_dense_likelihoods_folded_into_the_operators(kind):
         e.close()
 
 
-def test_tc16_coarse_chain_matches_reference_trajectory_until_near_tie():
+@pytest.mark.parametrize("kernel", ["tc16", "tc"])
+def test_tc16_coarse_chain_matches_reference_trajectory_until_near_tie(kernel):
     """chain_coarse_i of the unmodified reference (cfg2 golden fixture, injected streams) against the
-    coarse Links the tc16 kernel records: parameters, log-likelihood, accept flags, and the log-prior
-    rebuilt at fetch time, up to the first decision that differs (float32 near-tie)."""
+    coarse Links the tc16 (and, since round 2, the 3xTF32 tc) kernel records: parameters, log-likelihood, accept
+    flags, and the log-prior rebuilt at fetch time, up to the first decision that differs (float32 near-tie)."""
     import golden_io
     from tinyda_b200.engine import Engine, STORE_STATS
     g = golden_io.load("da_pcn_cfg2")
     C, iters, J = g["theta0"].shape[0], g["iterations"], 10
     eng = Engine(g["spec"], C, dtype="float32", rng="injected", streams=(g["z"], g["u"]),
                  store=[STORE_STATS, STORE_STATS], capacity_iterations=iters)
-    eng.select_kernel("tc16")
+    eng.select_kernel(kernel)
     eng.init(g["theta0"])
     eng.run(iters)
     ref = g["ref"][0]

@@ -525,6 +525,23 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                     }
                     if (acc) { like_c = like_p; prior_c = prior_p; acc_any = 1; nacc_c++; }
                     tb++;
+                    // ---- coarse-level record (chain_coarse_i, sampler.py:421-436): the state after this step, its
+                    // log-likelihood and accept flag; Link.prior / Link.model_output of these records are filled from
+                    // the stored parameters when they are first fetched (engine: fill_lazy_history) ----
+                    if (l0.store) {
+                        const long long r0 = p.rec[0] + it * J + j;
+                        if (r0 < l0.hist_cap) {
+                            if (l0.store & TDA_STORE_THETA) {
+                                float* dst = tc_opaque(l0.h_theta + (size_t)r0 * TC_K * cs + off0);
+#pragma unroll
+                                for (int k = 0; k < TC_HK; k++) __stcs(dst + k * cs, th[k]);
+                            }
+                            if (h == 0) {
+                                if (l0.store & TDA_STORE_STATS) __stcs(l0.h_like + (size_t)r0 * cs + g, like_c);
+                                if (l0.store & TDA_STORE_ACCEPT) l0.h_acc[(size_t)r0 * cs + g] = (uint8_t)acc;
+                            }
+                        }
+                    }
                     if (adaptive) {
                         window_append(acc ? 1 : 0);
                         if ((tb % p.period) == 0) {                   // tb: proposal.t after this step
@@ -678,7 +695,10 @@ struct DaTcState<float> {
             if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
         if (c.level[0].m > TC_MAX_MC || (c.level[0].m % 16) != 0) return false;
         if (c.level[1].m > TC_MAX_MF || (c.level[1].m % TC_CH) != 0) return false;
-        if (c.level[0].store != 0 || (c.level[1].store & TDA_STORE_OUTPUT)) return false;
+        // Link.prior (coarse) and Link.model_output (both levels) are not kept by the kernel: rebuilt from the stored
+        // parameters when first fetched (engine: fill_lazy_history), so they need the parameters
+        if ((c.level[0].store & (TDA_STORE_STATS | TDA_STORE_OUTPUT)) && !(c.level[0].store & TDA_STORE_THETA)) return false;
+        if ((c.level[1].store & TDA_STORE_OUTPUT) && !(c.level[1].store & TDA_STORE_THETA)) return false;
         if ((P.Cs % 256) != 0) return false;
         return true;
     }

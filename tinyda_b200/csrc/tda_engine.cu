@@ -1070,7 +1070,9 @@ struct EngineT : tda_engine {
         }
         P.z_round = z_round_effective();
         int r;
-        if (which != 3 && which != 5) {
+        // the tensor-core kernels record parameters only; prior / model outputs of the records are filled on first fetch
+        const bool lazy_kernel = (which == 2 || which == 3 || which == 5);
+        if (!lazy_kernel) {
             r = fill_lazy_history(st);
             if (!r) r = refresh_state_outputs(st);
             if (r) return r;
@@ -1192,7 +1194,7 @@ struct EngineT : tda_engine {
             if (lazy_w_lo == lazy_w_hi) lazy_w_lo = P.rec[0];
             lazy_w_hi = P.rec[0] + steps[0];
         }
-        if (which == 3 || which == 5) {
+        if (which == 2 || which == 3 || which == 5) {
             if (!burning)
                 for (int l = 0; l < L; l++) {
                     if (lazy_lo[l] == lazy_hi[l]) lazy_lo[l] = P.rec[l];
