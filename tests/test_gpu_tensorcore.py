@@ -650,3 +650,50 @@ def test_adaptive_random_walk_delayed_acceptance_on_the_tensor_cores():
     np.testing.assert_allclose(sc_a[clean], sc_r[clean], rtol=2e-5)
     a.close()
     ref.close()
+
+
+@pytest.mark.parametrize("d,adaptive", [(32, True), (48, False), (16, True)])
+def test_random_walk_tensor_core_kernel_with_fewer_than_64_parameters(d, adaptive):
+    """d in {16, 32, 48}: operators zero-padded to 64 rows on the host, the padded parameter columns draw no normals
+    (stream positions t d + k as on the lock-step kernel).  Two-level random-walk DA, 256 / 64 observations, against
+    the float64 engine on the same streams."""
+    import problems
+    import scipy.stats as stats
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.distributions import GaussianLogLike
+    from tinyda_b200.engine import Engine, STORE_STATS
+    from tinyda_b200.models import LinearModel
+    from tinyda_b200.posterior import Posterior
+    from tinyda_b200.proposal import GaussianRandomWalk
+    from tinyda_b200.workloads import exp_cov
+    rng = np.random.default_rng(d)
+    m_f, m_c, C, iters = 256, 64, 256, 20
+    prior = stats.multivariate_normal(np.zeros(d), exp_cov(d))
+    G = rng.standard_normal((m_f, d)) / np.sqrt(d)
+    y = G @ prior.rvs(random_state=rng) + 0.1 * rng.standard_normal(m_f)
+    idx = np.arange(0, m_f, m_f // m_c)
+    posts = [Posterior(prior, GaussianLogLike(y[idx], 0.01 * np.eye(m_c)), LinearModel(G[idx])),
+             Posterior(prior, GaussianLogLike(y, 0.01 * np.eye(m_f)), LinearModel(G))]
+    prop = GaussianRandomWalk(C=exp_cov(d, 0.3), scaling=0.03, adaptive=adaptive, period=12)
+    spec = lower_problem(posts, prop, 5)
+    theta0 = prior.rvs(C, random_state=rng)
+    a = Engine(spec, C, dtype="float32", seed=4, store=[STORE_STATS, STORE_STATS], capacity_iterations=iters)
+    assert a.kernel() == "tc"
+    a.init(theta0)
+    a.run(iters)
+    nz, nu = problems.stream_sizes(spec, iters)
+    z, u = a.fill_streams(nz, nu)
+    ref = Engine(spec, C, dtype="float64", rng="injected", streams=(z, u), store=[STORE_STATS, STORE_STATS], capacity_iterations=iters)
+    ref.select_kernel("generic")
+    ref.init(theta0)
+    ref.run(iters)
+    m, tot, w = _prefix_agreement(a.fetch(1, "theta"), a.fetch(1, "accept"), ref.fetch(1, "theta"), ref.fetch(1, "accept"))
+    mc_, totc, wc_ = _prefix_agreement(a.fetch(0, "theta"), a.fetch(0, "accept"), ref.fetch(0, "theta"), ref.fetch(0, "accept"))
+    print("\ntc, d = %d (adaptive=%s): %d of %d fine and %d of %d coarse records before a first flip, max relative state error "
+          "%.2e / %.2e" % (d, adaptive, m, tot, mc_, totc, w, wc_))
+    assert m >= 0.8 * tot and mc_ >= 0.8 * totc
+    assert w <= 1e-5 and wc_ <= 1e-5
+    assert np.array_equal(a.get("cursors"), ref.get("cursors"))
+    assert a.fetch(0, "accept").mean() > 0.02
+    a.close()
+    ref.close()

@@ -385,9 +385,13 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
             const int g = pair * 256 + t * 128 + cl;                   // chain slot (padded arrays)
             const long long gchain = p.chain_offset + g;
             const bool live = g < p.C;
+            // d < 64 (16, 32, 48): the operators are zero-padded to 64 rows / columns on the host; this thread owns the
+            // nk parameter columns [col0, col0 + nk) that exist, the padded ones stay zero (their normals are not drawn)
+            const int d = p.d;
+            const int nk = max(0, min(TC_HK, d - col0));
             float th[TC_HK];
 #pragma unroll
-            for (int k = 0; k < TC_HK; k++) th[k] = l1.theta[(size_t)(col0 + k) * p.Cs + g];
+            for (int k = 0; k < TC_HK; k++) th[k] = (k < nk) ? l1.theta[(size_t)(col0 + k) * p.Cs + g] : 0.0f;
             const size_t cs = (size_t)p.Cs;
             const size_t off0 = (size_t)col0 * cs + g;      // this thread's first column, this chain
             float like_c = l0.like[g], like_cs = like_c, like_f = l1.like[g], prior_f = l1.prior[g];
@@ -423,13 +427,16 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
             for (long long it = 0; it < iters; it++) {
                 for (int j = 0; j < J; j++) {
                     // ---- proposal draws (this thread's 32 of the 64 normals) -> A (hi | lo) ----
-                    const long long z0 = tb * TC_K + col0;
+                    const long long z0 = tb * d + col0;
 #pragma unroll
                     for (int c0 = 0; c0 < TC_HK; c0 += 8) {
                         float v[8];
 #pragma unroll
                         for (int b4 = 0; b4 < 2; b4++) {
-                            if (inj) {
+                            if (c0 >= nk) {                         // padded parameter columns (d is a multiple of 16)
+#pragma unroll
+                                for (int i = 0; i < 4; i++) v[b4 * 4 + i] = 0.0f;
+                            } else if (inj) {
 #pragma unroll
                                 for (int i = 0; i < 4; i++) {
                                     long long idx = z0 + c0 + b4 * 4 + i;
@@ -532,9 +539,10 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                         const long long r0 = p.rec[0] + it * J + j;
                         if (r0 < l0.hist_cap) {
                             if (l0.store & TDA_STORE_THETA) {
-                                float* dst = tc_opaque(l0.h_theta + (size_t)r0 * TC_K * cs + off0);
+                                float* dst = tc_opaque(l0.h_theta + (size_t)r0 * d * cs + off0);
 #pragma unroll
-                                for (int k = 0; k < TC_HK; k++) __stcs(dst + k * cs, th[k]);
+                                for (int k = 0; k < TC_HK; k++)
+                                    if (k < nk) __stcs(dst + k * cs, th[k]);
                             }
                             if (h == 0) {
                                 if (l0.store & TDA_STORE_STATS) __stcs(l0.h_like + (size_t)r0 * cs + g, like_c);
@@ -613,13 +621,15 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                     like_f = like_fp; prior_f = prior_p; like_cs = like_c; prior_cs = prior_c; nacc_f++;
                     float* dst = tc_opaque(l1.theta + off0);
 #pragma unroll
-                    for (int k = 0; k < TC_HK; k++) dst[k * cs] = th[k];
+                    for (int k = 0; k < TC_HK; k++)
+                        if (k < nk) dst[k * cs] = th[k];
                 } else {
                     like_c = like_cs;
                     prior_c = prior_cs;
                     const float* src = tc_opaque(l1.theta + off0);
 #pragma unroll
-                    for (int k = 0; k < TC_HK; k++) th[k] = src[k * cs];
+                    for (int k = 0; k < TC_HK; k++)
+                        if (k < nk) th[k] = src[k * cs];
                 }
                 acc_any = 0;
                 if (adaptive) window_append(accf);                   // the alignment entry (chain.py:391, :397)
@@ -627,9 +637,10 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
                 const long long r = p.rec[1] + it;
                 if (r < l1.hist_cap) {
                     if (l1.store & TDA_STORE_THETA) {
-                        float* dst = tc_opaque(l1.h_theta + (size_t)r * TC_K * cs + off0);
+                        float* dst = tc_opaque(l1.h_theta + (size_t)r * d * cs + off0);
 #pragma unroll
-                        for (int k = 0; k < TC_HK; k++) dst[k * cs] = th[k];
+                        for (int k = 0; k < TC_HK; k++)
+                            if (k < nk) dst[k * cs] = th[k];
                     }
                     if (h == 0) {
                         if (l1.store & TDA_STORE_STATS) { l1.h_prior[(size_t)r * p.Cs + g] = prior_f; l1.h_like[(size_t)r * p.Cs + g] = like_f; }
@@ -642,8 +653,10 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
 #pragma unroll
                     for (int k = 0; k < TC_HK; k++) {
                         // fire-and-forget reductions (one adder per address: deterministic), no load latency
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s1 + k * cs), "f"(th[k]) : "memory");
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s2 + k * cs), "f"(th[k] * th[k]) : "memory");
+                        if (k < nk) {
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s1 + k * cs), "f"(th[k]) : "memory");
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(s2 + k * cs), "f"(th[k] * th[k]) : "memory");
+                        }
                     }
                 }
             }
@@ -651,7 +664,8 @@ da_tc_kernel(const __grid_constant__ Params<float> p, const __grid_constant__ Da
             {
                 float* dst = tc_opaque(l0.theta + off0);
 #pragma unroll
-                for (int k = 0; k < TC_HK; k++) dst[k * cs] = th[k];
+                for (int k = 0; k < TC_HK; k++)
+                    if (k < nk) dst[k * cs] = th[k];
             }
             if (h == 0) {
                 l0.like[g] = like_c; l0.prior[g] = prior_f; l1.like[g] = like_f; l1.prior[g] = prior_f;
@@ -690,7 +704,7 @@ struct DaTcState<float> {
         if (c.dtype != TDA_F32 || c.n_levels != 2 || c.aem || c.randomize_subchain || c.mtm_k) return false;
         if (c.adaptive && (c.period < 1 || !P.win || !P.win_sum)) return false;
         if (c.prop_kind != TDA_PROP_PCN && c.prop_kind != TDA_PROP_RWMH) return false;
-        if (c.d != TC_K) return false;
+        if (c.d != 16 && c.d != 32 && c.d != 48 && c.d != TC_K) return false;      // zero-padded to 64 on the host
         for (int l = 0; l < 2; l++)
             if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
         if (c.level[0].m > TC_MAX_MC || (c.level[0].m % 16) != 0) return false;
@@ -730,15 +744,22 @@ struct DaTcState<float> {
         const int mc = c.level[0].m, mf = c.level[1].m;
         std::vector<float> T, LP, Ac, Af, bc, bf, dc, df, mu;
         cudaError_t e = cudaSuccess;
-        if (e == cudaSuccess) e = fetch(P.T, (size_t)TC_K * P.ldD, T);
-        if (e == cudaSuccess) e = fetch(P.LP, (size_t)TC_K * P.ldD, LP);
-        if (e == cudaSuccess) e = fetch(P.lv[0].A, (size_t)TC_K * P.lv[0].ldA, Ac);
-        if (e == cudaSuccess) e = fetch(P.lv[1].A, (size_t)TC_K * P.lv[1].ldA, Af);
+        // matrices with d rows on the device -> 64 rows on the host (zero rows for the parameters that do not exist;
+        // the columns beyond d of T and LP are zero in the device images already)
+        const int d0 = c.d;
+        auto fetch_rows = [&](const float* dev, size_t ld, std::vector<float>& h) {
+            h.assign((size_t)TC_K * ld, 0.f);
+            return cudaMemcpy(h.data(), dev, (size_t)d0 * ld * sizeof(float), cudaMemcpyDeviceToHost);
+        };
+        if (e == cudaSuccess) e = fetch_rows(P.T, P.ldD, T);
+        if (e == cudaSuccess) e = fetch_rows(P.LP, P.ldD, LP);
+        if (e == cudaSuccess) e = fetch_rows(P.lv[0].A, P.lv[0].ldA, Ac);
+        if (e == cudaSuccess) e = fetch_rows(P.lv[1].A, P.lv[1].ldA, Af);
         if (e == cudaSuccess) e = fetch(P.lv[0].b, mc, bc);
         if (e == cudaSuccess) e = fetch(P.lv[1].b, mf, bf);
         if (e == cudaSuccess) e = fetch(P.lv[0].data, mc, dc);
         if (e == cudaSuccess) e = fetch(P.lv[1].data, mf, df);
-        if (e == cudaSuccess) e = fetch(P.prior_mean, TC_K, mu);
+        if (e == cudaSuccess) { e = fetch(P.prior_mean, d0, mu); mu.resize(TC_K, 0.f); }
         if (e != cudaSuccess) { err = std::string("tc prepare: ") + cudaGetErrorString(e); return -2; }
         const int nfc = mf / TC_CH, nch = nfc + 1;
         std::vector<float> hT((size_t)2 * 64 * TC_K), hG((size_t)2 * mc * TC_K), hF((size_t)nch * 2 * TC_CH * TC_K);
