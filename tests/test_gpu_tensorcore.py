@@ -652,11 +652,11 @@ def test_adaptive_random_walk_delayed_acceptance_on_the_tensor_cores():
     ref.close()
 
 
-@pytest.mark.parametrize("d,adaptive", [(32, True), (48, False), (16, True)])
-def test_random_walk_tensor_core_kernel_with_fewer_than_64_parameters(d, adaptive):
+@pytest.mark.parametrize("d,adaptive,m_f,m_c", [(32, True, 256, 64), (48, False, 300, 50), (16, True, 200, 25), (64, True, 1000, 100)])
+def test_random_walk_tensor_core_kernel_with_fewer_than_64_parameters(d, adaptive, m_f, m_c):
     """d in {16, 32, 48}: operators zero-padded to 64 rows on the host, the padded parameter columns draw no normals
-    (stream positions t d + k as on the lock-step kernel).  Two-level random-walk DA, 256 / 64 observations, against
-    the float64 engine on the same streams."""
+    (stream positions t d + k as on the lock-step kernel); observation counts that are not multiples of 16 / 64 are
+    zero-padded too.  Two-level random-walk DA against the float64 engine on the same streams."""
     import problems
     import scipy.stats as stats
     from tinyda_b200 import lower_problem
@@ -667,11 +667,11 @@ def test_random_walk_tensor_core_kernel_with_fewer_than_64_parameters(d, adaptiv
     from tinyda_b200.proposal import GaussianRandomWalk
     from tinyda_b200.workloads import exp_cov
     rng = np.random.default_rng(d)
-    m_f, m_c, C, iters = 256, 64, 256, 20
+    C, iters = 256, 20
     prior = stats.multivariate_normal(np.zeros(d), exp_cov(d))
     G = rng.standard_normal((m_f, d)) / np.sqrt(d)
     y = G @ prior.rvs(random_state=rng) + 0.1 * rng.standard_normal(m_f)
-    idx = np.arange(0, m_f, m_f // m_c)
+    idx = np.arange(0, m_f, m_f // m_c)[:m_c]
     posts = [Posterior(prior, GaussianLogLike(y[idx], 0.01 * np.eye(m_c)), LinearModel(G[idx])),
              Posterior(prior, GaussianLogLike(y, 0.01 * np.eye(m_f)), LinearModel(G))]
     prop = GaussianRandomWalk(C=exp_cov(d, 0.3), scaling=0.03, adaptive=adaptive, period=12)

@@ -707,8 +707,10 @@ struct DaTcState<float> {
         if (c.d != 16 && c.d != 32 && c.d != 48 && c.d != TC_K) return false;      // zero-padded to 64 on the host
         for (int l = 0; l < 2; l++)
             if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
-        if (c.level[0].m > TC_MAX_MC || (c.level[0].m % 16) != 0) return false;
-        if (c.level[1].m > TC_MAX_MF || (c.level[1].m % TC_CH) != 0) return false;
+        // observation counts are zero-padded on the host to multiples of 16 (coarse) / 64 (fine): a zero operator
+        // column against a zero datum adds nothing to a residual sum
+        if (c.level[0].m < 1 || c.level[0].m > TC_MAX_MC) return false;
+        if (c.level[1].m < 1 || c.level[1].m > TC_MAX_MF) return false;
         // Link.prior (coarse) and Link.model_output (both levels) are not kept by the kernel: rebuilt from the stored
         // parameters when first fetched (engine: fill_lazy_history), so they need the parameters
         if ((c.level[0].store & (TDA_STORE_STATS | TDA_STORE_OUTPUT)) && !(c.level[0].store & TDA_STORE_THETA)) return false;
@@ -741,7 +743,8 @@ struct DaTcState<float> {
             h.resize(n);
             return cudaMemcpy(h.data(), dev, n * sizeof(float), cudaMemcpyDeviceToHost);
         };
-        const int mc = c.level[0].m, mf = c.level[1].m;
+        const int mc0 = c.level[0].m, mf0 = c.level[1].m;
+        const int mc = (mc0 + 15) / 16 * 16, mf = (mf0 + TC_CH - 1) / TC_CH * TC_CH;      // padded shapes the kernel sees
         std::vector<float> T, LP, Ac, Af, bc, bf, dc, df, mu;
         cudaError_t e = cudaSuccess;
         // matrices with d rows on the device -> 64 rows on the host (zero rows for the parameters that do not exist;
@@ -755,10 +758,11 @@ struct DaTcState<float> {
         if (e == cudaSuccess) e = fetch_rows(P.LP, P.ldD, LP);
         if (e == cudaSuccess) e = fetch_rows(P.lv[0].A, P.lv[0].ldA, Ac);
         if (e == cudaSuccess) e = fetch_rows(P.lv[1].A, P.lv[1].ldA, Af);
-        if (e == cudaSuccess) e = fetch(P.lv[0].b, mc, bc);
-        if (e == cudaSuccess) e = fetch(P.lv[1].b, mf, bf);
-        if (e == cudaSuccess) e = fetch(P.lv[0].data, mc, dc);
-        if (e == cudaSuccess) e = fetch(P.lv[1].data, mf, df);
+        if (e == cudaSuccess) e = fetch(P.lv[0].b, mc0, bc);
+        if (e == cudaSuccess) e = fetch(P.lv[1].b, mf0, bf);
+        if (e == cudaSuccess) e = fetch(P.lv[0].data, mc0, dc);
+        if (e == cudaSuccess) e = fetch(P.lv[1].data, mf0, df);
+        if (P.lv[0].ldA < mc || P.lv[1].ldA < mf) { err = "tc prepare: operator images narrower than the padded shapes"; return 1; }
         if (e == cudaSuccess) { e = fetch(P.prior_mean, d0, mu); mu.resize(TC_K, 0.f); }
         if (e != cudaSuccess) { err = std::string("tc prepare: ") + cudaGetErrorString(e); return -2; }
         const int nfc = mf / TC_CH, nch = nfc + 1;
@@ -778,8 +782,8 @@ struct DaTcState<float> {
         if (e == cudaSuccess) e = cudaMemcpy(dF, hF.data(), hF.size() * 4, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { err = std::string("tc prepare: ") + cudaGetErrorString(e); return -2; }
         yc.assign(TC_MAX_MC, 0.f); yf.assign(TC_MAX_MF, 0.f); clp.assign(TC_K, 0.f);
-        for (int j = 0; j < mc; j++) yc[j] = dc[j] - bc[j];
-        for (int j = 0; j < mf; j++) yf[j] = df[j] - bf[j];
+        for (int j = 0; j < mc0; j++) yc[j] = dc[j] - bc[j];
+        for (int j = 0; j < mf0; j++) yf[j] = df[j] - bf[j];
         for (int n = 0; n < TC_K; n++) {
             double a = 0;
             for (int k = 0; k < TC_K; k++) a += (double)mu[k] * (double)LP[(size_t)k * P.ldD + n];
