@@ -697,3 +697,56 @@ def test_random_walk_tensor_core_kernel_with_fewer_than_64_parameters(d, adaptiv
     assert a.fetch(0, "accept").mean() > 0.02
     a.close()
     ref.close()
+
+
+def test_random_walk_tensor_core_kernel_folds_diagonal_and_dense_likelihoods():
+    """A dense Gaussian likelihood on the coarse level and a diagonal one on the fine level (distributions.py:246-315)
+    are folded into the operator images on the host (Cholesky of the precision); the recorded Links still carry the
+    un-whitened model output.  Random-walk DA, d = 32, against the float64 engine on the same streams."""
+    import problems
+    import scipy.stats as stats
+    from tinyda_b200 import lower_problem
+    from tinyda_b200.distributions import GaussianLogLike
+    from tinyda_b200.engine import Engine, STORE_FULL
+    from tinyda_b200.models import LinearModel
+    from tinyda_b200.posterior import Posterior
+    from tinyda_b200.proposal import GaussianRandomWalk
+    from tinyda_b200.workloads import exp_cov
+    rng = np.random.default_rng(77)
+    d, m_f, m_c, C, iters = 32, 200, 40, 256, 16
+    prior = stats.multivariate_normal(np.zeros(d), exp_cov(d))
+    G = rng.standard_normal((m_f, d)) / np.sqrt(d)
+    var = 0.01 * (1.0 + rng.random(m_f))
+    y = G @ prior.rvs(random_state=rng) + np.sqrt(var) * rng.standard_normal(m_f)
+    idx = np.arange(0, m_f, m_f // m_c)[:m_c]
+    B = rng.standard_normal((m_c, m_c))
+    cov_c = 0.01 * (np.eye(m_c) + 0.3 * B @ B.T / m_c)                       # dense coarse covariance
+    posts = [Posterior(prior, GaussianLogLike(y[idx], cov_c), LinearModel(G[idx])),
+             Posterior(prior, GaussianLogLike(y, np.diag(var)), LinearModel(G))]
+    spec = lower_problem(posts, GaussianRandomWalk(C=exp_cov(d, 0.3), scaling=0.03), 5)
+    assert [int(lv["lik"]["kind"]) for lv in spec["levels"]] == [2, 1]          # dense, diagonal
+    theta0 = prior.rvs(C, random_state=rng)
+    a = Engine(spec, C, dtype="float32", seed=4, store=[STORE_FULL, STORE_FULL], capacity_iterations=iters)
+    assert a.kernel() == "tc"
+    a.init(theta0)
+    a.run(iters)
+    nz, nu = problems.stream_sizes(spec, iters)
+    z, u = a.fill_streams(nz, nu)
+    ref = Engine(spec, C, dtype="float64", rng="injected", streams=(z, u), store=[STORE_FULL, STORE_FULL], capacity_iterations=iters)
+    ref.select_kernel("generic")
+    ref.init(theta0)
+    ref.run(iters)
+    for l in (0, 1):
+        m, tot, w = _prefix_agreement(a.fetch(l, "theta"), a.fetch(l, "accept"), ref.fetch(l, "theta"), ref.fetch(l, "accept"))
+        assert m >= 0.8 * tot and w <= 1e-5, (l, m, tot, w)
+    # records of chains that never flipped: log-likelihoods and (un-whitened) model outputs of both levels
+    for l in (0, 1):
+        th_a, th_r = a.fetch(l, "theta"), ref.fetch(l, "theta")
+        clean = np.abs(th_a - th_r).max(axis=(0, 1)) <= 1e-4 * np.abs(th_r).max()      # this level's chain never flipped
+        assert clean.mean() > 0.7
+        la, lr = a.fetch(l, "like")[:, clean], ref.fetch(l, "like")[:, clean]
+        np.testing.assert_allclose(la, lr, rtol=2e-4, atol=2e-4 * np.abs(lr).max())
+        Fa, Fr = a.fetch(l, "output")[:, :, clean], ref.fetch(l, "output")[:, :, clean]
+        np.testing.assert_allclose(Fa, Fr, rtol=1e-4, atol=1e-5 * np.abs(Fr).max())
+    a.close()
+    ref.close()

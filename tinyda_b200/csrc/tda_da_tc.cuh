@@ -705,8 +705,13 @@ struct DaTcState<float> {
         if (c.adaptive && (c.period < 1 || !P.win || !P.win_sum)) return false;
         if (c.prop_kind != TDA_PROP_PCN && c.prop_kind != TDA_PROP_RWMH) return false;
         if (c.d != 16 && c.d != 32 && c.d != 48 && c.d != TC_K) return false;      // zero-padded to 64 on the host
-        for (int l = 0; l < 2; l++)
-            if (c.level[l].model_kind != TDA_MODEL_LINEAR || c.level[l].lik_kind != TDA_LIK_ISO) return false;
+        for (int l = 0; l < 2; l++) {
+            if (c.level[l].model_kind != TDA_MODEL_LINEAR) return false;
+            // diagonal and dense Gaussian likelihoods are folded into the operators on the host (prepare)
+            const int lk = c.level[l].lik_kind;
+            if (lk != TDA_LIK_ISO && lk != TDA_LIK_DIAG && lk != TDA_LIK_DENSE) return false;
+            if (lk == TDA_LIK_DENSE && c.level[l].m > 1920) return false;      // host Cholesky of the precision
+        }
         // observation counts are zero-padded on the host to multiples of 16 (coarse) / 64 (fine): a zero operator
         // column against a zero datum adds nothing to a residual sum
         if (c.level[0].m < 1 || c.level[0].m > TC_MAX_MC) return false;
@@ -765,6 +770,64 @@ struct DaTcState<float> {
         if (P.lv[0].ldA < mc || P.lv[1].ldA < mf) { err = "tc prepare: operator images narrower than the padded shapes"; return 1; }
         if (e == cudaSuccess) { e = fetch(P.prior_mean, d0, mu); mu.resize(TC_K, 0.f); }
         if (e != cudaSuccess) { err = std::string("tc prepare: ") + cudaGetErrorString(e); return -2; }
+        // Diagonal and dense Gaussian likelihoods (distributions.py:304-315, :246-301) are folded into the operators:
+        // with prec = L L^T (diagonal: L = diag(var^-1/2)) the log-likelihood -0.5 r^T prec r is -0.5 |L^T r|^2 -- an
+        // isotropic unit-variance likelihood of the whitened model L^T G against the whitened data L^T (y - b).
+        // (Link.model_output of the records is rebuilt from the engine's own operator, not from these images.)
+        std::vector<double> rres[2];
+        double lik_var[2] = {c.level[0].lik_var, c.level[1].lik_var};
+        for (int l = 0; l < 2; l++) {
+            const int kind = c.level[l].lik_kind, m0 = l ? mf0 : mc0, ld = P.lv[l].ldA;
+            std::vector<float>& A = l ? Af : Ac;
+            const std::vector<float>& bb = l ? bf : bc;
+            const std::vector<float>& dd = l ? df : dc;
+            std::vector<double>& r = rres[l];
+            r.resize(m0);
+            for (int j = 0; j < m0; j++) r[j] = (double)dd[j] - (double)bb[j];
+            if (kind == TDA_LIK_ISO) continue;
+            lik_var[l] = 1.0;
+            if (kind == TDA_LIK_DIAG) {
+                std::vector<float> var;
+                e = fetch(P.lv[l].var, m0, var);
+                if (e != cudaSuccess) { err = std::string("tc prepare: ") + cudaGetErrorString(e); return -2; }
+                for (int n = 0; n < m0; n++) {
+                    if (!(var[n] > 0.f)) { err = "tc: non-positive likelihood variance"; return 1; }
+                    const double w = 1.0 / std::sqrt((double)var[n]);
+                    for (int k = 0; k < d0; k++) A[(size_t)k * ld + n] = (float)(A[(size_t)k * ld + n] * w);
+                    r[n] *= w;
+                }
+            } else {
+                std::vector<float> pf;
+                e = fetch(P.lv[l].prec, (size_t)m0 * m0, pf);
+                if (e != cudaSuccess) { err = std::string("tc prepare: ") + cudaGetErrorString(e); return -2; }
+                std::vector<double> Lc(pf.begin(), pf.end());
+                for (int j = 0; j < m0; j++) {            // in-place lower Cholesky factor of the precision
+                    double dj = Lc[(size_t)j * m0 + j];
+                    for (int k = 0; k < j; k++) dj -= Lc[(size_t)j * m0 + k] * Lc[(size_t)j * m0 + k];
+                    if (!(dj > 0.0)) { err = "tc: likelihood precision is not positive definite in float32"; return 1; }
+                    dj = std::sqrt(dj);
+                    Lc[(size_t)j * m0 + j] = dj;
+                    for (int i = j + 1; i < m0; i++) {
+                        double v = Lc[(size_t)i * m0 + j];
+                        for (int k = 0; k < j; k++) v -= Lc[(size_t)i * m0 + k] * Lc[(size_t)j * m0 + k];
+                        Lc[(size_t)i * m0 + j] = v / dj;
+                    }
+                }
+                std::vector<double> row(m0), x(m0);
+                for (int k = 0; k <= d0; k++) {            // rows of G^T, then the data residual: x <- x L
+                    for (int n = 0; n < m0; n++) x[n] = (k < d0) ? (double)A[(size_t)k * ld + n] : r[n];
+                    for (int n = 0; n < m0; n++) {
+                        double v = 0;
+                        for (int j = n; j < m0; j++) v += x[j] * Lc[(size_t)j * m0 + n];
+                        row[n] = v;
+                    }
+                    for (int n = 0; n < m0; n++) {
+                        if (k < d0) A[(size_t)k * ld + n] = (float)row[n];
+                        else r[n] = row[n];
+                    }
+                }
+            }
+        }
         const int nfc = mf / TC_CH, nch = nfc + 1;
         std::vector<float> hT((size_t)2 * 64 * TC_K), hG((size_t)2 * mc * TC_K), hF((size_t)nch * 2 * TC_CH * TC_K);
         canon_split(T, P.ldD, 0, 64, hT.data(), hT.data() + 64 * TC_K);
@@ -782,8 +845,8 @@ struct DaTcState<float> {
         if (e == cudaSuccess) e = cudaMemcpy(dF, hF.data(), hF.size() * 4, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { err = std::string("tc prepare: ") + cudaGetErrorString(e); return -2; }
         yc.assign(TC_MAX_MC, 0.f); yf.assign(TC_MAX_MF, 0.f); clp.assign(TC_K, 0.f);
-        for (int j = 0; j < mc0; j++) yc[j] = dc[j] - bc[j];
-        for (int j = 0; j < mf0; j++) yf[j] = df[j] - bf[j];
+        for (int j = 0; j < mc0; j++) yc[j] = (float)rres[0][j];
+        for (int j = 0; j < mf0; j++) yf[j] = (float)rres[1][j];
         for (int n = 0; n < TC_K; n++) {
             double a = 0;
             for (int k = 0; k < TC_K; k++) a += (double)mu[k] * (double)LP[(size_t)k * P.ldD + n];
@@ -794,7 +857,7 @@ struct DaTcState<float> {
         q.nst = q.rwmh ? 2 : TC_NST;
         q.LP_hl = dF + (size_t)nfc * 2 * TC_CH * TC_K;
         q.mc = mc; q.mf = mf; q.n_chunks = nch; q.J = c.subchain[0];
-        q.var_c = (float)c.level[0].lik_var; q.var_f = (float)c.level[1].lik_var;
+        q.var_c = (float)lik_var[0]; q.var_f = (float)lik_var[1];
         q.prior_logconst = (float)c.prior_logconst;
         prepared = true;
         return 0;
