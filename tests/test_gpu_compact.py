@@ -58,6 +58,33 @@ def test_compacted_history_expands_bit_identically_to_the_dense_one(C, kernel):
     eng.close()
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_compaction_of_wide_rows_many_segments_and_both_gather_paths(dtype):
+    """The gather kernel's corners in one run: model outputs of 1024 columns (sixteen 64-column chunks), 70 chains
+    (a ragged last group of 32), 90 records (record segments whose row positions start from a count of the earlier
+    accept bytes), records where many chains of a group accept (shared-memory slab) and records where few do (direct
+    sector gather; the ragged group has six chains)."""
+    from tinyda_b200.engine import STORE_FULL, STORE_NONE
+    from tinyda_b200.link import CompactHistory
+    C, iters = 70, 89
+    eng, w, spec = _cfg2(C, iters, store=[STORE_NONE, STORE_FULL], dtype=dtype, kernel="generic")
+    eng.run(iters)
+    nrec = iters + 1
+    th = eng.fetch(1, "theta", 0, nrec); out = eng.fetch(1, "output", 0, nrec); pr = eng.fetch(1, "prior", 0, nrec)
+    ac = eng.fetch(1, "accept", 0, nrec)
+    eng.compact_begin(0, nrec, True, ("theta", "stats", "output"), slot=0)
+    hist = CompactHistory(C)
+    hist.append(eng.compact_collect(0))
+    eng.compact_sync()
+    flags = ac[1:].astype(bool).reshape(iters, -1)[:, :C]
+    per_group = np.stack([flags[:, g:g + 32].sum(axis=1) for g in range(0, C, 32)])
+    assert (per_group > 4).any() and ((per_group >= 1) & (per_group <= 4)).any()          # both regimes occur
+    assert np.array_equal(hist.dense("theta"), np.transpose(th, (2, 0, 1)))
+    assert np.array_equal(hist.dense("output"), np.transpose(out, (2, 0, 1)))
+    assert np.array_equal(hist.dense("prior"), pr.T)
+    eng.close()
+
+
 def test_sample_runs_in_blocks_and_returns_the_same_chains():
     """tda.sample cut into blocks (chunk_iterations) returns what one block returns, chain by chain."""
     import tinyda_b200 as tda

@@ -35,6 +35,8 @@
 #pragma once
 #include <cuda_fp16.h>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -219,9 +221,12 @@ inline int pow2_scale_for(double maxabs, int top) {
 
 // canonical K-major fp16 hi / lo images of B[n][k] = factor * W[k][n0 + n] * 2^s   (W row-major [K][ldw])
 inline void canon_split16(const std::vector<double>& W, int ldw, int n0, int rows, double factor, int s, __half* hi, __half* lo) {
-    for (int n = 0; n < rows; n++)
-        for (int k = 0; k < T16_K; k++) {
-            const float x = (float)std::ldexp(factor * W[(size_t)k * ldw + n0 + n], s);
+    // factor * 2^s once: scaling by a power of two commutes with the rounding of factor * W (no
+    // subnormals at these magnitudes), so the images are the ones ldexp(factor * W, s) gives
+    const double scale = std::ldexp(factor, s);
+    for (int k = 0; k < T16_K; k++)
+        for (int n = 0; n < rows; n++) {
+            const float x = (float)(scale * W[(size_t)k * ldw + n0 + n]);
             const __half h = __float2half_rn(x);
             const __half l = __float2half_rn(x - __half2float(h));
             const size_t o = tc::canon_offset_f16(n, k, T16_K) / 2;
@@ -1049,6 +1054,12 @@ struct DaTc16State<float> {
 
     // returns 1 when the problem cannot be scaled into fp16 (caller falls back to another kernel)
     int prepare(const Params<float>& P, const tda_config& c) {
+        const bool prof = std::getenv("TDA_PROFILE") != nullptr;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        const auto t_start = now();
         auto fetch = [&](const float* dev, size_t n, std::vector<double>& h) {
             std::vector<float> f(n);
             cudaError_t e = cudaMemcpy(f.data(), dev, n * sizeof(float), cudaMemcpyDeviceToHost);
@@ -1073,6 +1084,7 @@ struct DaTc16State<float> {
         if (e == cudaSuccess) e = fetch(P.prior_mean, d0, mu);
         if (e == cudaSuccess) e = fetch(P.scaling, (size_t)P.Cs, sc);
         if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
+        const auto t_fetched = now();
         auto pad = [&](std::vector<double>& W, int ld, int cols) {
             for (int k = 0; k < d0; k++)
                 for (int n = cols; n < ld; n++) W[(size_t)k * ld + n] = 0.0;
@@ -1141,12 +1153,13 @@ struct DaTc16State<float> {
         const int ldD = P.ldD, ldc = P.lv[0].ldA, ldf = P.lv[1].ldA;
 
         // composed coarse operator M[k][n] = sum_j T[k][j] * G_c^T[j][n]
-        std::vector<double> M((size_t)T16_K * mc);
+        std::vector<double> M((size_t)T16_K * mc, 0.0);
         for (int k = 0; k < T16_K; k++)
-            for (int n = 0; n < mc; n++) {
-                double s = 0;
-                for (int j = 0; j < T16_K; j++) s += T[(size_t)k * ldD + j] * Ac[(size_t)j * ldc + n];
-                M[(size_t)k * mc + n] = s;
+            for (int j = 0; j < T16_K; j++) {         // same summation order over j for every (k, n)
+                const double t = T[(size_t)k * ldD + j];
+                const double* g = &Ac[(size_t)j * ldc];
+                double* mrow = &M[(size_t)k * mc];
+                for (int n = 0; n < mc; n++) mrow[n] += t * g[n];
             }
         // scales: theta from the prior (mean +- 12 sd must stay below 2^15), operators to [2^13, 2^14)
         double th_max = 0;
@@ -1180,6 +1193,7 @@ struct DaTc16State<float> {
                           hF.data() + (size_t)ch * 2 * T16_CH * T16_K + T16_CH * T16_K);
         canon_split16(LP, ldD, 0, T16_CH, 1.0, s_LP, hF.data() + (size_t)nfc * 2 * T16_CH * T16_K,
                       hF.data() + (size_t)nfc * 2 * T16_CH * T16_K + T16_CH * T16_K);
+        const auto t_composed = now();
         destroy();
         if (e == cudaSuccess) e = cudaMalloc(&dG, hG.size() * 2);
         if (e == cudaSuccess) e = cudaMalloc(&dM, hM.size() * 2);
@@ -1213,6 +1227,9 @@ struct DaTc16State<float> {
         q.th_scale = (float)std::ldexp(1.0, s_th);
         q.th_unscale = (float)std::ldexp(1.0, -s_th);
         theta_limit = (float)std::ldexp(65000.0, -s_th);
+        if (prof)
+            std::fprintf(stderr, "[tc16 prepare] operands D2H %.2f ms, host composition %.2f ms, device images %.2f ms\n",
+                         ms(t_start, t_fetched), ms(t_fetched, t_composed), ms(t_composed, now()));
         prepared = true;
         return 0;
     }

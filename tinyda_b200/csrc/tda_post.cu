@@ -79,56 +79,116 @@ __global__ void __launch_bounds__(CB) add_blocks_kernel(long long* __restrict__ 
     if (c == 0) offsets[C] = block_off[nblocks];
 }
 
-// One block = 32 consecutive chains.  Per record the [W][32] slab of the chain-fastest history is staged
-// through shared memory with coalesced loads (lane = chain, one 128-byte line per row) and the rows of the
-// accepted chains leave with coalesced stores: HBM traffic = one read of the dense records + one write of
-// the accepted rows, whatever the acceptance rate.
+// One warp = 32 consecutive chains x one segment of the records (lane = chain); warps never wait for each other.
+// Per record the accept bytes of the group are one coalesced load (the next record's is already in flight).  A record
+// with few accepted chains (<= GW_DIRECT, the usual case at MCMC acceptance rates) is gathered directly: lane k reads
+// elements k, k + 32, ... of the accepted chain's row (one 32-byte sector each in the chain-fastest history) and
+// the row leaves with coalesced stores.  A record with many accepted chains stages the [W][32] slab through the
+// warp's shared-memory tile with 128-byte loads instead (one read of the slab whatever the number of rows).
+// Segments other than the first start by counting the group's accepted records before their first one.
 // prior / like (optional): the records' log-densities travel with the rows in the same pass
+constexpr int GW_DIRECT = 4;
 template <typename R>
 __global__ void __launch_bounds__(256) gather_kernel(const R* __restrict__ src, int W, const uint8_t* __restrict__ acc, long long nrec, int C,
                                                      int Cs, int force_first, const long long* __restrict__ offsets, R* __restrict__ dst,
                                                      const R* __restrict__ prior, const R* __restrict__ like, R* __restrict__ dst_prior,
-                                                     R* __restrict__ dst_like) {
-    __shared__ R tile[64][33];
-    __shared__ R tile_s[2][32];
-    __shared__ long long rowpos[32];
-    __shared__ unsigned s_mask;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * 32;
-    if (threadIdx.x < 32) rowpos[threadIdx.x] = (c0 + threadIdx.x < C) ? offsets[c0 + threadIdx.x] : 0;
-    __syncthreads();
-    for (long long r = 0; r < nrec; r++) {
-        if (warp == 0) {
-            const bool a = (c0 + lane < C) && (acc[(size_t)r * Cs + c0 + lane] != 0 || (force_first && r == 0));
-            const unsigned m = __ballot_sync(0xffffffffu, a);
-            if (lane == 0) s_mask = m;
+                                                     R* __restrict__ dst_like, int n_groups, int n_seg, long long seg_len) {
+    extern __shared__ __align__(16) unsigned char gw_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    R(*tile)[33] = reinterpret_cast<R(*)[33]>(gw_smem + (size_t)warp * 64 * 33 * sizeof(R));
+    const long long job = (long long)blockIdx.x * wpb + warp;
+    if (job >= (long long)n_groups * n_seg) return;
+    // consecutive warps take consecutive chain groups of one segment: neighbouring lines of the same records
+    const int seg = (int)(job / n_groups), group = (int)(job % n_groups);
+    const int c0 = group * 32;
+    const bool live = c0 + lane < C;
+    const long long r0 = seg * seg_len, r1 = (r0 + seg_len < nrec) ? r0 + seg_len : nrec;
+    long long rowpos = live ? offsets[c0 + lane] : 0;
+    {
+        int cnt = 0;
+        long long r = 0;
+        for (; r + 8 <= r0; r += 8) {
+            uint8_t f[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) f[u] = acc[(size_t)(r + u) * Cs + c0 + lane];
+#pragma unroll
+            for (int u = 0; u < 8; u++) cnt += (f[u] != 0 || (force_first && r + u == 0)) ? 1 : 0;
         }
-        __syncthreads();
-        const unsigned mask = s_mask;
-        if (mask && prior) {
-            if (warp == 1) tile_s[0][lane] = prior[(size_t)r * Cs + c0 + lane];
-            if (warp == 2) tile_s[1][lane] = like[(size_t)r * Cs + c0 + lane];
+        for (; r < r0; r++) cnt += (acc[(size_t)r * Cs + c0 + lane] != 0 || (force_first && r == 0)) ? 1 : 0;
+        if (live) rowpos += cnt;
+    }
+    uint8_t a_next = (r0 < r1) ? acc[(size_t)r0 * Cs + c0 + lane] : 0;
+    for (long long r = r0; r < r1; r++) {
+        const bool a = live && (a_next != 0 || (force_first && r == 0));
+        if (r + 1 < r1) a_next = acc[(size_t)(r + 1) * Cs + c0 + lane];
+        const unsigned mask = __ballot_sync(0xffffffffu, a);
+        if (!mask) continue;
+        if (prior && a) {
+            dst_prior[rowpos] = prior[(size_t)r * Cs + c0 + lane];
+            dst_like[rowpos] = like[(size_t)r * Cs + c0 + lane];
         }
-        if (mask) {
+        const R* rec = src + (size_t)r * W * Cs + c0;
+        if (__popc(mask) <= GW_DIRECT) {
+            // all rows' loads of a 64-column chunk in flight before the first store
+            int cs[GW_DIRECT];
+            long long ps[GW_DIRECT];
+            unsigned m = mask;
+#pragma unroll
+            for (int i = 0; i < GW_DIRECT; i++) {
+                cs[i] = m ? __ffs(m) - 1 : 0;
+                ps[i] = __shfl_sync(0xffffffffu, rowpos, cs[i]);
+                if (!m) ps[i] = -1;
+                m &= m - 1;
+            }
+            for (int k0 = 0; k0 < W; k0 += 64) {
+                R v[GW_DIRECT][2];
+#pragma unroll
+                for (int i = 0; i < GW_DIRECT; i++)
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int k = k0 + lane + 32 * u;
+                        if (ps[i] >= 0 && k < W) v[i][u] = rec[(size_t)k * Cs + cs[i]];
+                    }
+#pragma unroll
+                for (int i = 0; i < GW_DIRECT; i++)
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int k = k0 + lane + 32 * u;
+                        if (ps[i] >= 0 && k < W) dst[(size_t)ps[i] * W + k] = v[i][u];
+                    }
+            }
+        } else {
             for (int k0 = 0; k0 < W; k0 += 64) {
                 const int kw = W - k0 < 64 ? W - k0 : 64;
-                for (int k = warp; k < kw; k += 8) tile[k][lane] = src[((size_t)r * W + k0 + k) * Cs + c0 + lane];
-                __syncthreads();
+                int k = 0;
+                for (; k + 32 <= kw; k += 32) {            // 32 independent 128-byte loads per lane in flight
+                    R v[32];
+#pragma unroll
+                    for (int u = 0; u < 32; u++) v[u] = rec[(size_t)(k0 + k + u) * Cs + lane];
+#pragma unroll
+                    for (int u = 0; u < 32; u++) tile[k + u][lane] = v[u];
+                }
+                for (; k + 8 <= kw; k += 8) {
+                    R v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v[u] = rec[(size_t)(k0 + k + u) * Cs + lane];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) tile[k + u][lane] = v[u];
+                }
+                for (; k < kw; k++) tile[k][lane] = rec[(size_t)(k0 + k) * Cs + lane];
+                __syncwarp();
                 unsigned m = mask;
-                for (int jj = 0; m; jj++) {
+                while (m) {
                     const int c = __ffs(m) - 1;
                     m &= m - 1;
-                    if ((jj & 7) == warp) {
-                        R* o = dst + (size_t)rowpos[c] * W + k0;
-                        for (int k = lane; k < kw; k += 32) o[k] = tile[k][c];
-                        if (prior && k0 == 0 && lane < 2) (lane ? dst_like : dst_prior)[rowpos[c]] = tile_s[lane][c];
-                    }
+                    const long long pos = __shfl_sync(0xffffffffu, rowpos, c);
+                    R* o = dst + (size_t)pos * W + k0;
+                    for (int kk = lane; kk < kw; kk += 32) o[kk] = tile[kk][c];
                 }
-                __syncthreads();
+                __syncwarp();
             }
         }
-        if (threadIdx.x < 32 && ((mask >> threadIdx.x) & 1u)) rowpos[threadIdx.x] += 1;
-        __syncthreads();
+        if (a) rowpos += 1;
     }
 }
 
@@ -176,17 +236,40 @@ int compact_offsets(const uint8_t* acc, long long nrec, int C, int Cs, int force
     return e == cudaSuccess ? 0 : pfail("compact_offsets", e);
 }
 
+template <typename R>
+static cudaError_t gather_launch(const void* src, int W, const uint8_t* acc, long long nrec, int C, int Cs, int force_first,
+                                 const long long* offsets, void* dst, cudaStream_t st, const void* prior, const void* like, void* dst_prior,
+                                 void* dst_like) {
+    // 64 KB of tiles per block (8 warps in float, 4 in double), three blocks per SM
+    const int wpb = sizeof(R) == 4 ? 8 : 4;
+    const size_t smem = (size_t)wpb * 64 * 33 * sizeof(R);
+    cudaError_t ea = cudaFuncSetAttribute(gather_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea != cudaSuccess) return ea;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_groups = (C + 31) / 32;
+    // enough warps for about two rounds of the machine's resident warps, at least 8 records per segment
+    const long long slots = (long long)sms * 3 * wpb;
+    long long n_seg = (2 * slots + n_groups - 1) / n_groups;
+    if (n_seg > nrec / 8) n_seg = nrec / 8;
+    if (n_seg > 64) n_seg = 64;
+    if (n_seg < 1) n_seg = 1;
+    const long long seg_len = (nrec + n_seg - 1) / n_seg;
+    n_seg = (nrec + seg_len - 1) / seg_len;
+    const long long jobs = (long long)n_groups * n_seg;
+    const unsigned grid = (unsigned)((jobs + wpb - 1) / wpb);
+    gather_kernel<R><<<grid, wpb * 32, smem, st>>>((const R*)src, W, acc, nrec, C, Cs, force_first, offsets, (R*)dst, (const R*)prior,
+                                                   (const R*)like, (R*)dst_prior, (R*)dst_like, n_groups, (int)n_seg, seg_len);
+    return cudaGetLastError();
+}
+
 int compact_gather(const void* src, int esz, int W, const uint8_t* acc, long long nrec, int C, int Cs, int force_first,
                    const long long* offsets, void* dst, cudaStream_t st, const void* prior, const void* like, void* dst_prior,
                    void* dst_like) {
-    const unsigned grid = (unsigned)((C + 31) / 32);
-    if (esz == 4)
-        gather_kernel<float><<<grid, 256, 0, st>>>((const float*)src, W, acc, nrec, C, Cs, force_first, offsets, (float*)dst,
-                                                   (const float*)prior, (const float*)like, (float*)dst_prior, (float*)dst_like);
-    else
-        gather_kernel<double><<<grid, 256, 0, st>>>((const double*)src, W, acc, nrec, C, Cs, force_first, offsets, (double*)dst,
-                                                    (const double*)prior, (const double*)like, (double*)dst_prior, (double*)dst_like);
-    cudaError_t e = cudaGetLastError();
+    if (nrec <= 0 || C <= 0) return 0;
+    const cudaError_t e = (esz == 4) ? gather_launch<float>(src, W, acc, nrec, C, Cs, force_first, offsets, dst, st, prior, like, dst_prior, dst_like)
+                                     : gather_launch<double>(src, W, acc, nrec, C, Cs, force_first, offsets, dst, st, prior, like, dst_prior, dst_like);
     return e == cudaSuccess ? 0 : pfail("compact_gather", e);
 }
 
