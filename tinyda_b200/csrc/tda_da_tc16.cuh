@@ -38,6 +38,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "tda_common.cuh"
@@ -981,6 +982,7 @@ template <typename R>
 struct DaTc16State {
     std::string err;
     bool prepared = false;
+    cudaStream_t fetch_stream = nullptr;   // engine's copy stream: prepare() reads the operands on it
     float theta_limit = 0.0f;
     bool eligible(const tda_config&, const Params<R>&) const { return false; }
     int prepare(const Params<R>&, const tda_config&) { err = "fp16-split tensor-core DA kernel is float32 only"; return 1; }
@@ -998,6 +1000,7 @@ struct DaTc16State<float> {
     int* dProgress = nullptr;
     int progress_len = 0;
     bool prepared = false;
+    cudaStream_t fetch_stream = nullptr;   // engine's copy stream: prepare() reads the operands on it
     float theta_limit = 0.0f;     // |theta| of a current state must stay below this (fp16 operand image at scale 2^s_theta)
     DaTc16Params q{};
 
@@ -1066,6 +1069,41 @@ struct DaTc16State<float> {
             h.assign(f.begin(), f.end());
             return e;
         };
+        // The constant operands were complete when the last upload returned (uploads end with a synchronisation),
+        // so they are read on the engine's copy stream -- not behind the initial-Link kernel queued on the run
+        // stream -- into one page-locked staging buffer kept for the life of the process, with one wait at the end.
+        struct Pending { const float* dev; size_t n; std::vector<double>* h; };
+        std::vector<Pending> pend;
+        auto fetch_all = [&]() -> cudaError_t {
+            static std::mutex mu;
+            static float* stage = nullptr;
+            static size_t stage_cap = 0;
+            size_t total = 0;
+            for (const Pending& x : pend) total += x.n;
+            if (!fetch_stream || !total) {
+                for (const Pending& x : pend) { cudaError_t e1 = fetch(x.dev, x.n, *x.h); if (e1 != cudaSuccess) return e1; }
+                return cudaSuccess;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (stage_cap < total) {
+                if (stage) cudaFreeHost(stage);
+                stage = nullptr; stage_cap = 0;
+                cudaError_t e1 = cudaHostAlloc((void**)&stage, total * sizeof(float), cudaHostAllocPortable);
+                if (e1 != cudaSuccess) return e1;
+                stage_cap = total;
+            }
+            size_t off = 0;
+            for (const Pending& x : pend) {
+                cudaError_t e1 = cudaMemcpyAsync(stage + off, x.dev, x.n * sizeof(float), cudaMemcpyDeviceToHost, fetch_stream);
+                if (e1 != cudaSuccess) return e1;
+                off += x.n;
+            }
+            cudaError_t e1 = cudaStreamSynchronize(fetch_stream);
+            if (e1 != cudaSuccess) return e1;
+            off = 0;
+            for (const Pending& x : pend) { x.h->assign(stage + off, stage + off + x.n); off += x.n; }
+            return cudaSuccess;
+        };
         // real shapes (d0, mc0, mf0) and the padded ones the kernel runs on: zero rows / columns add
         // nothing to a contraction, zero data under a zero operator column gives a zero residual
         const int d0 = c.d, mc0 = c.level[0].m, mf0 = c.level[1].m;
@@ -1073,16 +1111,12 @@ struct DaTc16State<float> {
         std::vector<double> T, LP, Ac, Af, bc, bf, dc, df, mu, sc;
         cudaError_t e = cudaSuccess;
         if (P.ldD < T16_K || P.lv[0].ldA < mc || P.lv[1].ldA < mf) { err = "tc16: operand leading dimensions"; return 1; }
-        if (e == cudaSuccess) e = fetch(P.T, (size_t)d0 * P.ldD, T);
-        if (e == cudaSuccess) e = fetch(P.LP, (size_t)d0 * P.ldD, LP);
-        if (e == cudaSuccess) e = fetch(P.lv[0].A, (size_t)d0 * P.lv[0].ldA, Ac);
-        if (e == cudaSuccess) e = fetch(P.lv[1].A, (size_t)d0 * P.lv[1].ldA, Af);
-        if (e == cudaSuccess) e = fetch(P.lv[0].b, mc0, bc);
-        if (e == cudaSuccess) e = fetch(P.lv[1].b, mf0, bf);
-        if (e == cudaSuccess) e = fetch(P.lv[0].data, mc0, dc);
-        if (e == cudaSuccess) e = fetch(P.lv[1].data, mf0, df);
-        if (e == cudaSuccess) e = fetch(P.prior_mean, d0, mu);
-        if (e == cudaSuccess) e = fetch(P.scaling, (size_t)P.Cs, sc);
+        pend = {{P.T, (size_t)d0 * P.ldD, &T},        {P.LP, (size_t)d0 * P.ldD, &LP},
+                {P.lv[0].A, (size_t)d0 * P.lv[0].ldA, &Ac}, {P.lv[1].A, (size_t)d0 * P.lv[1].ldA, &Af},
+                {P.lv[0].b, (size_t)mc0, &bc},        {P.lv[1].b, (size_t)mf0, &bf},
+                {P.lv[0].data, (size_t)mc0, &dc},     {P.lv[1].data, (size_t)mf0, &df},
+                {P.prior_mean, (size_t)d0, &mu},      {P.scaling, (size_t)P.Cs, &sc}};
+        e = fetch_all();
         if (e != cudaSuccess) { err = std::string("tc16 prepare: ") + cudaGetErrorString(e); return -2; }
         const auto t_fetched = now();
         auto pad = [&](std::vector<double>& W, int ld, int cols) {

@@ -598,6 +598,9 @@ struct EngineT : tda_engine {
     // ---- uploads ---------------------------------------------------------------------------
     int put(const R* dst, const std::vector<R>& h) {
         CUDA_TRY(cudaMemcpy(const_cast<R*>(dst), h.data(), h.size() * sizeof(R), cudaMemcpyHostToDevice));
+        // a copy from pageable memory may return before its DMA has landed: other streams (the operand fetch of the
+        // tensor-core kernels' prepare step) must see the data
+        CUDA_TRY(cudaStreamSynchronize(0));
         return 0;
     }
 
@@ -1041,6 +1044,8 @@ struct EngineT : tda_engine {
         }
         if (which == 3 && !tc16.prepared) {
             // operand scaling happens on first use; a problem that does not fit fp16 falls back
+            if (!copy_stream) copy_stream = g_small.get_stream(device);
+            tc16.fetch_stream = copy_stream;
             int r = tc16.prepare(P, cfg);
             if (r < 0) return fail(r, tc16.err);
             if (r > 0) {
